@@ -1,0 +1,158 @@
+/* sigma_b200.h - C ABI of the B200-native SIGmA inprocessing pass (libsigma_b200.so).
+ *
+ * The reference (muhos/SeqFROST) has no plugin/FFI interface: the pass is a set of Solver
+ * member functions.  The boundary this library sits behind is the narrowest cut through
+ * Solver::simplifying() (reference src/simplify.cpp:155-233):
+ *
+ *     ... rootify(); shrinkTop(false); awaken();            simplify.cpp:161-171  (host, kept)
+ *     >>> while (litsbefore) { resizeCNF .. filterElected }  simplify.cpp:180-197  (REPLACED)
+ *     >>> prop();                                            simplify.cpp:204      (REPLACED)
+ *     >>> clearMapFrozen(); countFinal(); shrinkSimp();      simplify.cpp:208-210  (REPLACED)
+ *     ... SAT check; map()/newBeginning(); rebuildWT(); ..   simplify.cpp:218-229  (host, kept)
+ *
+ * The hand-off object on both sides is the reference's own SCNF (simptypes.hpp:48-95): a bump
+ * arena of uint32 buckets holding SCLAUSE records (sclause.hpp:45-49: word0 bitfield
+ * st:2 f:1 a:1 u:2 lbd:26, word1 sig, word2 size, then `size` ascending literals, literal =
+ * 2*var+sign, constants.hpp:77-82) plus the `refs` vector (bucket index per clause, allocation
+ * order), together with the solver state the pass reads and writes.
+ *
+ * Plain C: pointers + sizes only, no C++ types, no exceptions across the boundary.  One
+ * sigma_ctx per GPU; a ctx is not thread-safe; different ctxs are independent.
+ * There is NO CPU fallback: every entry point fails with SIGMA_E_CUDA when no device is usable.
+ */
+#ifndef SIGMA_B200_H
+#define SIGMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (reference: prop()/VE()/strengthen() end in learnEmpty();killSolver(),
+ *      control.cpp:221; allocators throw MEMOUTEXCEPTION, malloc.hpp:28-58) ---------------- */
+enum {
+    SIGMA_OK = 0,
+    SIGMA_UNSAT = 1,          /* the pass derived the empty clause                            */
+    SIGMA_INTERRUPTED = 2,    /* *interrupt_flag became non-zero between stages               */
+    SIGMA_E_NOMEM = 3,        /* device or host allocation failed                             */
+    SIGMA_E_CUDA = 4,         /* no device / launch failure (see sigma_last_error)            */
+    SIGMA_E_NOSPACE = 5,      /* an output buffer is too small: required sizes are filled in  */
+    SIGMA_E_ARG = 6,          /* malformed input                                              */
+    SIGMA_E_UNSUPPORTED = 7   /* option combination outside the implemented path              */
+};
+
+/* ---- options: OPTION fields that parameterise the pass (options.hpp:108-130, defaults
+ *      options.cpp:24-51,146; derived rules options.cpp:315-351).  32 x int32, the same order
+ *      as the "opts" section written by oracle/ref_harness.cpp. ----------------------------- */
+typedef struct sigma_opts {
+    int32_t phases;            /* --phases (5), decremented by the caller after each call     */
+    int32_t phase_lits_min;    /* --eliminationphasemin (500)                                  */
+    int32_t mu_pos, mu_neg;    /* --mupos/--muneg (32/32)                                      */
+    int32_t lcve_max_occurs;   /* --electionsmax (3000)                                        */
+    int32_t lcve_clause_max;   /* --electionsclausemax (30000)                                 */
+    int32_t lcve_min_vars;     /* --electionsmin (1)                                           */
+    int32_t sub_max_occurs;    /* --subsumemaxoccurs (1000)                                    */
+    int32_t sub_clause_max;    /* --subsumeclausemax (100)                                     */
+    int32_t ve_clause_max;     /* --boundedclausemax (100, 0 = unlimited)                      */
+    int32_t xor_max_arity;     /* --xormaxarity (10)                                           */
+    int32_t bce_max_occurs;    /* --blockedmaxoccurs (1000)                                    */
+    int32_t ere_max_occurs;    /* --redundancymaxoccurs (1000)                                 */
+    int32_t ere_clause_max;    /* --redundancyclausemax (200)                                  */
+    int32_t collect_freq;      /* --collectfrequency (2)                                       */
+    int32_t lbd_tier1;         /* --lbdtier1 (2), used by bumpShrunken, solve.hpp:725          */
+    int32_t sub_en, ve_en, ve_plus_en, ve_fun_en, ve_lbound_en;
+    int32_t bce_en, ere_en, ere_extend, all_en, proof_en;
+    int32_t reserved[6];
+} sigma_opts;
+
+/* ---- the formula + solver state at the cut (used for input and output) ------------------- */
+typedef struct sigma_formula {
+    uint32_t  nvars;           /* inf.maxVar                                                   */
+    uint32_t  n_clauses;       /* scnf.size(): number of refs                                  */
+    uint64_t  n_buckets;       /* used uint32 buckets of the arena                             */
+    uint64_t  n_literals;      /* inf.nLiterals                                                */
+    uint32_t *arena;           /* SCLAUSE records, sclause.hpp:45-49                           */
+    uint64_t *refs;            /* S_REF per clause, simptypes.hpp:43                           */
+    uint8_t  *state;           /* sp->state[v].state, nvars+1 bytes (state.hpp:26-41)          */
+    int8_t   *value;           /* sp->value[lit], 2*nvars+2 bytes (-1 unassigned, 0, 1)        */
+    uint32_t *trail;           /* root trail                                                   */
+    uint32_t  trail_size;
+    uint32_t  propagated;      /* sp->propagated                                               */
+    uint32_t *vorg;            /* current -> original variable id, nvars+1 (model.hpp:65)      */
+    uint8_t  *ifrozen;         /* incremental freeze mask or NULL (solve.hpp:816)              */
+    uint32_t *model;           /* MODEL::resolved (model.hpp:31)                               */
+    uint64_t  model_size;
+    uint32_t  unassigned;      /* inf.unassigned                                               */
+    uint32_t  max_frozen;      /* inf.maxFrozen                                                */
+    uint32_t  max_melted;      /* inf.maxMelted                                                */
+    uint32_t  simplify_calls;  /* stats.simplify.calls (1 = first call, bounded.cpp:39)        */
+    /* capacities of the caller-owned OUTPUT buffers (ignored on input) */
+    uint64_t  arena_cap;       /* in uint32 buckets                                            */
+    uint32_t  refs_cap;
+    uint32_t  trail_cap;
+    uint64_t  model_cap;
+} sigma_formula;
+
+/* ---- what a run did: counters mirror stats.simplify.* (statistics.hpp:42-52) and the
+ *      per-stage timers timer.{vo,cot,sot,rot,ve,sub,gc} (timer.hpp:35-51) ------------------- */
+enum { SIGMA_T_H2D = 0, SIGMA_T_INGEST, SIGMA_T_COT, SIGMA_T_PROP, SIGMA_T_VO, SIGMA_T_ELECT,
+       SIGMA_T_SOT, SIGMA_T_SUB, SIGMA_T_VE, SIGMA_T_COUNT, SIGMA_T_GC, SIGMA_T_EXPORT,
+       SIGMA_T_D2H, SIGMA_T_ERE, SIGMA_T_TOTAL_DEVICE, SIGMA_T_N = 16 };
+
+typedef struct sigma_report {
+    int32_t  status;
+    int32_t  phases_run;
+    uint32_t n_clauses, max_melted_delta;
+    uint64_t n_literals;
+    uint64_t literals_in;           /* inf.nLiterals after extract(): the "literals/s" numerator */
+    int64_t  pures, inverters, andors, ites, xors, funs, resolutions, subsumed, strengthened;
+    int64_t  units, sort_ties_gt24;
+    float    stage_ms[SIGMA_T_N];   /* CUDA-event milliseconds per stage, summed over phases      */
+    uint64_t kernel_launches;       /* kernels of this library launched by the last execute       */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t elected_per_phase[8];
+    uint64_t reserved[8];
+} sigma_report;
+
+typedef struct sigma_ctx sigma_ctx;
+
+/* lifecycle */
+int  sigma_create(int device, sigma_ctx **out);
+void sigma_destroy(sigma_ctx *ctx);
+void sigma_default_opts(sigma_opts *o);               /* reference defaults, ERE as options.cpp:28 */
+const char *sigma_strerror(int code);
+const char *sigma_last_error(sigma_ctx *ctx);
+
+/* one-shot: replaces simplify.cpp:180-210.  `out` holds caller-owned buffers with capacities;
+ * on SIGMA_E_NOSPACE the required n_buckets / n_clauses / trail_size / model_size are set and
+ * the device result is kept so that sigma_download() can be retried with larger buffers. */
+int  sigma_run(sigma_ctx *ctx, const sigma_opts *o, const sigma_formula *in, sigma_formula *out,
+               sigma_report *rep);
+
+/* split form (what sigma_run does internally; lets the host overlap, re-time or diff stages) */
+int  sigma_upload(sigma_ctx *ctx, const sigma_opts *o, const sigma_formula *in);   /* H2D + AoS->SoA */
+int  sigma_execute(sigma_ctx *ctx);                                                /* kernels only   */
+int  sigma_result_sizes(sigma_ctx *ctx, sigma_formula *sizes);                     /* after execute  */
+int  sigma_download(sigma_ctx *ctx, sigma_formula *out);                           /* SoA->AoS + D2H */
+int  sigma_get_report(sigma_ctx *ctx, sigma_report *rep);
+int  sigma_reset(sigma_ctx *ctx);   /* restore the uploaded formula on the device (re-timing)     */
+
+/* host-polled interrupt flag (reference `interrupted`, control.cpp:130-159) */
+void sigma_set_interrupt_flag(sigma_ctx *ctx, const volatile int *flag);
+
+/* stage-level parity hooks: stop after `stage` (SIGMA_T_* id of the stage) of `phase`, then copy
+ * a named device array to the host.  Names: c_off c_size c_w0 c_sig lits ot_off ot_len ot_data
+ * occ order elected state value trail model marks n (scalars). phase < 0 disables. */
+int  sigma_set_stop(sigma_ctx *ctx, int phase, int stage);
+int  sigma_snapshot(sigma_ctx *ctx, const char *name, void *dst, uint64_t cap_bytes, uint64_t *nbytes);
+
+/* roofline probe: run ONE streaming kernel of the pass `iters` times on the uploaded formula
+ * and return its mean CUDA-event milliseconds and the algorithmic bytes of one launch
+ * (DESIGN.md table). kernel: "ot_build" | "histogram" | "compact" | "ingest" | "count". */
+int  sigma_time_kernel(sigma_ctx *ctx, const char *kernel, int iters, float *ms, uint64_t *algo_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGMA_B200_H */

@@ -1,0 +1,229 @@
+// ref_harness.cpp - TEST INFRASTRUCTURE (never linked into the product).
+//
+// Drives the UNMODIFIED reference (libseqfrost_ref.a, compiled by oracle/Makefile from
+// /root/reference/src) through one SIGmA pass, stage by stage, exactly as
+// Solver::simplifying() does (reference simplify.cpp:155-233), and writes
+//   --sgin=<file>   the drop-in boundary INPUT  (state right after awaken(), simplify.cpp:171)
+//   --sgout=<file>  the drop-in boundary OUTPUT (state right after shrinkSimp(), simplify.cpp:210)
+//   --trace=<file>  per-phase elected lists / counters (debug aid for stage-level parity)
+// in the sectioned binary format read by seqfrost_b200/boundary.py.  It is also the
+// "reference" CPU baseline: it times the replaced region (simplify.cpp:180-206) on one core.
+//
+// usage: ref_sigma <file.cnf> [reference CLI options] [--sgin=..] [--sgout=..] [--trace=..] [--repeat-timing]
+//
+// All members touched are public/protected in the reference's Solver (solve.hpp:75-844);
+// the reference sources are not modified.
+#include "control.hpp"
+#include "solve.hpp"
+#include "version.hpp"
+#include <chrono>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+using namespace SeqFROST;
+
+bool quiet_en = false;
+bool competition_en = false;
+int verbose = -1;
+
+namespace {
+
+struct Writer {
+	FILE* f = nullptr;
+	bool open(const std::string& p) { f = fopen(p.c_str(), "wb"); if (!f) return false; fwrite("SGMA0001", 1, 8, f); return true; }
+	void section(const char* name, const void* data, uint64_t nbytes) {
+		char nm[8] = { 0 };
+		strncpy(nm, name, 8);
+		fwrite(nm, 1, 8, f);
+		fwrite(&nbytes, 8, 1, f);
+		if (nbytes) fwrite(data, 1, nbytes, f);
+	}
+	void close() { if (f) fclose(f), f = nullptr; }
+};
+
+std::string g_sgout;
+bool g_out_written = false;
+
+// killSolver() (control.cpp:221) ends the process through exit(); when that happens inside the
+// pass (UNSAT found by prop/SUB/VE) record the verdict so the parity tests can compare it.
+void write_unsat_at_exit() {
+	if (g_out_written || g_sgout.empty()) return;
+	Writer w;
+	if (!w.open(g_sgout)) return;
+	uint64_t meta[16] = { 0 };
+	meta[0] = 1; // status: 1 = UNSAT / process ended inside the pass
+	w.section("meta", meta, sizeof(meta));
+	w.close();
+}
+
+class Probe : public Solver {
+public:
+	Probe(const std::string& path) : Solver(path) {}
+
+	void dumpStore(Writer& w) {
+		// SCNF arena verbatim (sclause.hpp:45-49 AoS, simptypes.hpp:48-95) + refs in allocation order
+		uint32* base = (uint32*)scnf.clause(0);
+		const uint64_t buckets = scnf.STYPE::size(); // bump pointer of the arena (memory.hpp:94)
+		const uint32 n = scnf.size();
+		w.section("arena", base, buckets * sizeof(uint32));
+		w.section("refs", scnf.refs().data(), uint64_t(n) * sizeof(S_REF));
+	}
+
+	void dumpCommon(Writer& w, uint64_t status, double passms) {
+		uint64_t meta[16] = { 0 };
+		meta[0] = status;
+		meta[1] = inf.maxVar;
+		meta[2] = inf.nClauses;
+		meta[3] = inf.nLiterals;
+		meta[4] = inf.unassigned;
+		meta[5] = inf.maxFrozen;
+		meta[6] = inf.maxMelted;
+		meta[7] = trail.size();
+		meta[8] = sp->propagated;
+		meta[9] = stats.simplify.calls;
+		meta[10] = (uint64_t)(passms * 1000.0); // microseconds in replaced region
+		meta[11] = inf.orgVars;
+		meta[12] = (uint64_t)phase;
+		w.section("meta", meta, sizeof(meta));
+		std::vector<uint8_t> st(inf.maxVar + 1);
+		for (uint32 v = 0; v <= inf.maxVar; ++v) st[v] = (uint8_t)sp->state[v].state;
+		w.section("state", st.data(), st.size());
+		w.section("value", sp->value, inf.nDualVars);
+		w.section("trail", trail.data(), uint64_t(trail.size()) * 4);
+		w.section("vorg", vorg.data(), uint64_t(vorg.size()) * 4);
+		w.section("model", model.resolved.data(), uint64_t(model.resolved.size()) * 4);
+		int32_t o[32] = { 0 };
+		o[0] = opts.phases; o[1] = opts.phase_lits_min; o[2] = opts.mu_pos; o[3] = opts.mu_neg;
+		o[4] = opts.lcve_max_occurs; o[5] = opts.lcve_clause_max; o[6] = opts.lcve_min_vars;
+		o[7] = opts.sub_max_occurs; o[8] = opts.sub_clause_max; o[9] = opts.ve_clause_max;
+		o[10] = opts.xor_max_arity; o[11] = opts.bce_max_occurs; o[12] = opts.ere_max_occurs;
+		o[13] = opts.ere_clause_max; o[14] = opts.collect_freq; o[15] = opts.lbd_tier1;
+		o[16] = opts.sub_en; o[17] = opts.ve_en; o[18] = opts.ve_plus_en; o[19] = opts.ve_fun_en;
+		o[20] = opts.ve_lbound_en; o[21] = opts.bce_en; o[22] = opts.ere_en; o[23] = opts.ere_extend;
+		o[24] = opts.all_en; o[25] = opts.proof_en;
+		w.section("opts", o, sizeof(o));
+#ifdef STATISTICS
+		int64_t s[16] = { 0 };
+		s[0] = stats.simplify.bve.pures; s[1] = stats.simplify.bve.inverters; s[2] = stats.simplify.bve.andors;
+		s[3] = stats.simplify.bve.ites; s[4] = stats.simplify.bve.xors; s[5] = stats.simplify.bve.funs;
+		s[6] = stats.simplify.bve.resolutions; s[7] = stats.simplify.sub.subsumed; s[8] = stats.simplify.sub.strengthened;
+		w.section("stats", s, sizeof(s));
+#endif
+	}
+
+	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep) {
+		using clk = std::chrono::steady_clock;
+		timer.start();
+		initLimits();
+		if (!opts.preprocess_en) { fprintf(stderr, "ref_sigma: preprocess disabled\n"); return 2; }
+		if (!opts.phases && !(opts.all_en || opts.ere_en)) { fprintf(stderr, "ref_sigma: no phases\n"); return 2; }
+		stats.simplify.calls++;            // simplify.cpp:108
+		rootify();                         // simplify.cpp:161
+		shrinkTop(false);                  // simplify.cpp:162
+		if (orgs.empty()) { fprintf(stderr, "ref_sigma: formula empty after root shrinking\n"); return 3; }
+		awaken();                          // simplify.cpp:171
+		if (simpstate == AWAKEN_FAIL) return 4;
+		if (!sgin.empty()) {
+			Writer w;
+			if (!w.open(sgin)) return 5;
+			dumpCommon(w, 0, 0.0);
+			dumpStore(w);
+			w.close();
+		}
+		Writer tw;
+		const bool tracing = !tracep.empty() && tw.open(tracep);
+		// ---- replaced region: simplify.cpp:178-206 ----
+		auto t0 = clk::now();
+		int64 litsbefore = inf.nLiterals, diff = INT64_MAX;
+		while (litsbefore) {
+			resizeCNF();
+			createOT();
+			if (!prop()) killSolver();
+			if (!LCVE()) break;
+			sortOT();
+			if (tracing) {
+				char nm[16];
+				snprintf(nm, sizeof nm, "elect%d", phase);
+				tw.section(nm, elected.data(), uint64_t(elected.size()) * 4);
+			}
+			if ((phase == opts.phases) || (diff <= opts.phase_lits_min && phase > 2)) { ERE(); break; }
+			SUB(), VE(), BCE();
+			countAll(), filterElected();
+			inf.nClauses = inf.nClausesAfter, inf.nLiterals = inf.nLiteralsAfter;
+			diff = litsbefore - inf.nLiterals, litsbefore = inf.nLiterals;
+			if (tracing) {
+				char nm[16];
+				snprintf(nm, sizeof nm, "count%d", phase);
+				uint64_t c[4] = { inf.nClauses, inf.nLiterals, trail.size(), model.resolved.size() };
+				tw.section(nm, c, sizeof c);
+			}
+			phase++;
+			multiplier++;
+			multiplier += phase == opts.phases;
+		}
+		if (!prop()) killSolver();
+		auto t1 = clk::now();
+		// ---- write back prologue: simplify.cpp:207-210 ----
+		occurs.clear(true), ot.clear(true);
+		clearMapFrozen();
+		countFinal();
+		shrinkSimp();
+		auto t2 = clk::now();
+		const double passms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+		const double gcms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+		if (tracing) tw.close();
+		if (!sgout.empty()) {
+			Writer w;
+			if (!w.open(sgout)) return 5;
+			dumpCommon(w, 0, passms);
+			dumpStore(w);
+			w.close();
+		}
+		g_out_written = true;
+		printf("ref_sigma: pass_ms=%.3f final_compact_ms=%.3f phases=%d vars=%u clauses=%u literals=%u melted=%u units=%u model=%u\n",
+			passms, gcms, phase, inf.maxVar, inf.nClauses, inf.nLiterals, inf.maxMelted, (unsigned)trail.size(), (unsigned)model.resolved.size());
+		fflush(stdout);
+		return 0;
+	}
+};
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+	BOOL_OPT opt_competition_en("competition", "engage SAT competition mode", false);
+	BOOL_OPT opt_quiet_en("quiet", "enable quiet mode, same as verbose=0", false);
+	INT_OPT opt_verbose("verbose", "set the verbosity", 1, INT32R(0, 4));
+	INT_OPT opt_timeout("timeout", "set out-of-time limit in seconds", 0, INT32R(0, INT32_MAX));
+	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
+	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
+	std::string sgin, sgout, tracep;
+	std::vector<char*> pass;
+	for (int i = 0; i < argc; ++i) {
+		std::string a = argv[i];
+		if (a.rfind("--sgin=", 0) == 0) sgin = a.substr(7);
+		else if (a.rfind("--sgout=", 0) == 0) sgout = a.substr(8);
+		else if (a.rfind("--trace=", 0) == 0) tracep = a.substr(8);
+		else pass.push_back(argv[i]);
+	}
+	g_sgout = sgout;
+	atexit(write_unsat_at_exit);
+	try {
+		int pargc = (int)pass.size();
+		parseArguments(pargc, pass.data());
+		competition_en = opt_competition_en;
+		quiet_en = opt_quiet_en, verbose = opt_verbose;
+		if (quiet_en || competition_en) verbose = 0;
+		else if (!verbose || competition_en) quiet_en = true;
+		std::string formula = argv[1];
+		Probe* p = new Probe(formula);
+		solver = p;
+		int rc = p->run(sgin, sgout, tracep);
+		g_out_written = g_out_written || rc != 0;
+		fflush(stdout);
+		_exit(rc); // skip the reference's destructors (process-global singletons)
+	}
+	catch (std::bad_alloc&) { fprintf(stderr, "ref_sigma: bad_alloc\n"); g_out_written = true; return 9; }
+	catch (MEMOUTEXCEPTION&) { fprintf(stderr, "ref_sigma: memout\n"); g_out_written = true; return 9; }
+}

@@ -1,0 +1,190 @@
+"""The drop-in boundary of the SIGmA pass as plain numpy arrays.
+
+The reference has no plugin/FFI interface; the boundary this repo replaces is the cut through
+``Solver::simplifying()`` right after ``awaken()`` (reference simplify.cpp:171) and right after
+``shrinkSimp()`` (simplify.cpp:210).  At both cuts the formula is an ``SCNF``: a bump arena of
+uint32 buckets holding ``SCLAUSE`` records (sclause.hpp:45-49: word0 bitfield
+``st:2 f:1 a:1 u:2 lbd:26``, word1 ``sig``, word2 ``size``, then the sorted literals) plus the
+``refs`` vector of bucket indices in allocation order (simptypes.hpp:48-95).
+
+``Boundary`` carries exactly that plus the solver state the pass reads/writes (state bytes,
+literal values, trail, vorg, model stack).  ``read``/``write`` use the sectioned file format that
+``oracle/ref_harness.cpp`` emits, so inputs/outputs of the real reference, of the C oracle port
+and of the CUDA path are interchangeable.
+"""
+from __future__ import annotations
+
+import dataclasses
+import struct
+
+import numpy as np
+
+MAGIC = b"SGMA0001"
+
+# clause status / flag bits in SCLAUSE word0 (constants.hpp:69-71, sclause.hpp:45)
+ST_MASK, ST_LEARNT, ST_DELETED = 0x3, 0x1, 0x2
+F_MOLTEN, F_ADDED = 0x4, 0x8
+# per-variable state bits (constants.hpp:56-58)
+MELTED_M, FROZEN_M, SUBSTITUTED_M = 1, 2, 4
+
+OPT_NAMES = [
+    "phases", "phase_lits_min", "mu_pos", "mu_neg", "lcve_max_occurs", "lcve_clause_max",
+    "lcve_min_vars", "sub_max_occurs", "sub_clause_max", "ve_clause_max", "xor_max_arity",
+    "bce_max_occurs", "ere_max_occurs", "ere_clause_max", "collect_freq", "lbd_tier1",
+    "sub_en", "ve_en", "ve_plus_en", "ve_fun_en", "ve_lbound_en", "bce_en", "ere_en",
+    "ere_extend", "all_en", "proof_en",
+]
+# reference defaults (options.cpp:24-51, :146) with ERE off: the parity configuration
+# (`-no-redundancy`) until ERE is built.
+DEFAULT_OPTS = dict(
+    phases=5, phase_lits_min=500, mu_pos=32, mu_neg=32, lcve_max_occurs=3000,
+    lcve_clause_max=30000, lcve_min_vars=1, sub_max_occurs=1000, sub_clause_max=100,
+    ve_clause_max=100, xor_max_arity=10, bce_max_occurs=1000, ere_max_occurs=1000,
+    ere_clause_max=200, collect_freq=2, lbd_tier1=2, sub_en=1, ve_en=1, ve_plus_en=1,
+    ve_fun_en=1, ve_lbound_en=0, bce_en=0, ere_en=0, ere_extend=1, all_en=0, proof_en=0,
+)
+
+
+@dataclasses.dataclass
+class Boundary:
+    status: int = 0                      # 0 OK, 1 UNSAT (reference: killSolver inside the pass)
+    nvars: int = 0                       # inf.maxVar
+    n_clauses: int = 0                   # inf.nClauses
+    n_literals: int = 0                  # inf.nLiterals
+    unassigned: int = 0
+    max_frozen: int = 0
+    max_melted: int = 0
+    propagated: int = 0
+    simplify_calls: int = 1
+    pass_us: int = 0
+    arena: np.ndarray = None             # uint32 buckets
+    refs: np.ndarray = None              # uint64 bucket index per clause
+    state: np.ndarray = None             # uint8[nvars+1]
+    value: np.ndarray = None             # int8[2*nvars+2]
+    trail: np.ndarray = None             # uint32
+    vorg: np.ndarray = None              # uint32[nvars+1]
+    model: np.ndarray = None             # uint32 (MODEL::resolved)
+    opts: dict = None
+    stats: np.ndarray = None
+
+    # ---- canonical views used by the parity tests ------------------------------------
+    def clauses(self):
+        """List of (status, added, tuple(lits)) in refs order."""
+        a = self.arena
+        out = []
+        for r in self.refs.tolist():
+            w0, sz = int(a[r]), int(a[r + 2])
+            out.append((w0 & ST_MASK, (w0 >> 3) & 1, tuple(a[r + 3:r + 3 + sz].tolist())))
+        return out
+
+    def clause_multiset(self):
+        """Canonically sorted clause multiset: sorted literals + status + added flag."""
+        return sorted((tuple(sorted(l)), st, ad) for st, ad, l in self.clauses())
+
+    def eliminated(self):
+        return np.nonzero(self.state & MELTED_M)[0]
+
+    def soa(self):
+        """(word0, sig, size, off, lits) structure-of-arrays copy of the store, refs order."""
+        a, r = self.arena, self.refs.astype(np.int64)
+        w0, sig, sz = a[r], a[r + 1], a[r + 2].astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(sz)]).astype(np.int64)
+        idx = np.repeat(r + 3 - off[:-1], sz) + np.arange(int(off[-1]), dtype=np.int64)
+        return w0, sig, sz, off, a[idx]
+
+
+def read(path) -> Boundary:
+    with open(path, "rb") as f:
+        blob = f.read()
+    if blob[:8] != MAGIC:
+        raise ValueError(f"{path}: not a sigma boundary file")
+    pos, sec = 8, {}
+    while pos < len(blob):
+        name = blob[pos:pos + 8].rstrip(b"\0").decode()
+        (n,) = struct.unpack_from("<Q", blob, pos + 8)
+        sec[name] = blob[pos + 16:pos + 16 + n]
+        pos += 16 + n
+    meta = np.frombuffer(sec["meta"], dtype=np.uint64)
+    b = Boundary(status=int(meta[0]))
+    if b.status != 0 and "arena" not in sec:
+        return b
+    b.nvars, b.n_clauses, b.n_literals = int(meta[1]), int(meta[2]), int(meta[3])
+    b.unassigned, b.max_frozen, b.max_melted = int(meta[4]), int(meta[5]), int(meta[6])
+    b.propagated, b.simplify_calls, b.pass_us = int(meta[8]), int(meta[9]), int(meta[10])
+    b.arena = np.frombuffer(sec["arena"], dtype=np.uint32).copy()
+    b.refs = np.frombuffer(sec["refs"], dtype=np.uint64).copy()
+    b.state = np.frombuffer(sec["state"], dtype=np.uint8).copy()
+    b.value = np.frombuffer(sec["value"], dtype=np.int8).copy()
+    b.trail = np.frombuffer(sec["trail"], dtype=np.uint32).copy()
+    b.vorg = np.frombuffer(sec["vorg"], dtype=np.uint32).copy()
+    b.model = np.frombuffer(sec["model"], dtype=np.uint32).copy()
+    if "opts" in sec:
+        o = np.frombuffer(sec["opts"], dtype=np.int32)
+        b.opts = {k: int(o[i]) for i, k in enumerate(OPT_NAMES)}
+    if "stats" in sec:
+        b.stats = np.frombuffer(sec["stats"], dtype=np.int64).copy()
+    return b
+
+
+def read_trace(path):
+    with open(path, "rb") as f:
+        blob = f.read()
+    pos, sec = 8, {}
+    while pos < len(blob):
+        name = blob[pos:pos + 8].rstrip(b"\0").decode()
+        (n,) = struct.unpack_from("<Q", blob, pos + 8)
+        raw = blob[pos + 16:pos + 16 + n]
+        sec[name] = np.frombuffer(raw, dtype=np.uint32 if name.startswith("elect") else np.uint64).copy()
+        pos += 16 + n
+    return sec
+
+
+def write(path, b: Boundary):
+    def section(f, name, arr):
+        raw = np.ascontiguousarray(arr).tobytes()
+        f.write(name.encode().ljust(8, b"\0"))
+        f.write(struct.pack("<Q", len(raw)))
+        f.write(raw)
+    meta = np.zeros(16, dtype=np.uint64)
+    meta[:11] = [b.status, b.nvars, b.n_clauses, b.n_literals, b.unassigned, b.max_frozen,
+                 b.max_melted, 0 if b.trail is None else b.trail.size, b.propagated,
+                 b.simplify_calls, b.pass_us]
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        section(f, "meta", meta)
+        if b.arena is None:
+            return
+        for name in ("state", "value", "trail", "vorg", "model", "arena", "refs"):
+            section(f, name, getattr(b, name))
+        if b.opts:
+            section(f, "opts", np.array([b.opts.get(k, 0) for k in OPT_NAMES] + [0] * (32 - len(OPT_NAMES)), dtype=np.int32))
+
+
+def from_cnf(nvars, offsets, lits) -> Boundary:
+    """Host mirror of ``awaken()``/``extract()`` (reference simplify.cpp:118-153) for a first call
+    on a formula with no units, repeated literals or tautologies: each clause becomes an ORIGINAL
+    SCLAUSE with ascending literals (``lit = 2*var + sign``, constants.hpp:77-82) and
+    ``sig = OR 1<<(lit&31)`` (sclause.hpp:158-162), allocated back to back in input order."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lits = np.asarray(lits, dtype=np.int64)
+    n = offsets.size - 1
+    sizes = np.diff(offsets)
+    enc = (2 * np.abs(lits) + (lits < 0)).astype(np.uint32)
+    cid = np.repeat(np.arange(n, dtype=np.int64), sizes)
+    order = np.lexsort((enc, cid))           # ascending literals inside every clause
+    enc = enc[order]
+    sig = np.zeros(n, dtype=np.uint32)
+    np.bitwise_or.at(sig, cid, (np.uint32(1) << (enc & np.uint32(31))).astype(np.uint32))
+    refs = (offsets[:-1] + 3 * np.arange(n, dtype=np.int64)).astype(np.uint64)
+    arena = np.zeros(int(offsets[-1]) + 3 * n, dtype=np.uint32)
+    r = refs.astype(np.int64)
+    arena[r + 1] = sig
+    arena[r + 2] = sizes.astype(np.uint32)
+    arena[np.repeat(r + 3 - offsets[:-1], sizes) + np.arange(int(offsets[-1]), dtype=np.int64)] = enc
+    return Boundary(
+        status=0, nvars=int(nvars), n_clauses=n, n_literals=int(offsets[-1]), unassigned=int(nvars),
+        max_frozen=0, max_melted=0, propagated=0, simplify_calls=1, arena=arena, refs=refs,
+        state=np.zeros(nvars + 1, dtype=np.uint8), value=np.full(2 * nvars + 2, -1, dtype=np.int8),
+        trail=np.zeros(0, dtype=np.uint32), vorg=np.arange(nvars + 1, dtype=np.uint32),
+        model=np.zeros(0, dtype=np.uint32), opts=dict(DEFAULT_OPTS),
+    )
