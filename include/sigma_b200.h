@@ -95,10 +95,27 @@ typedef struct sigma_formula {
 } sigma_formula;
 
 /* ---- what a run did: counters mirror stats.simplify.* (statistics.hpp:42-52) and the
- *      per-stage timers timer.{vo,cot,sot,rot,ve,sub,gc} (timer.hpp:35-51) ------------------- */
-enum { SIGMA_T_H2D = 0, SIGMA_T_INGEST, SIGMA_T_COT, SIGMA_T_PROP, SIGMA_T_VO, SIGMA_T_ELECT,
-       SIGMA_T_SOT, SIGMA_T_SUB, SIGMA_T_VE, SIGMA_T_COUNT, SIGMA_T_GC, SIGMA_T_EXPORT,
-       SIGMA_T_D2H, SIGMA_T_ERE, SIGMA_T_TOTAL_DEVICE, SIGMA_T_N = 16 };
+ *      per-stage timers timer.{vo,cot,sot,rot,ve,sub,gc} (timer.hpp:35-51).  Every stage is a
+ *      group of kernels bracketed by CUDA events on the library's stream; ms / launches / bytes
+ *      are summed over the phases of the last sigma_execute. ---------------------------------- */
+enum { SIGMA_T_H2D = 0,      /* sigma_upload: host -> device copies                                   */
+       SIGMA_T_INGEST,       /* AoS arena -> device store                                             */
+       SIGMA_T_OT_HIST,      /* createOT: per-literal histogram            (simplify.cpp:39-61)       */
+       SIGMA_T_OT_SCAN,      /* createOT: exclusive scan of the histogram                              */
+       SIGMA_T_OT_SCATTER,   /* createOT: clause ids into the lists                                    */
+       SIGMA_T_OT_ORDER,     /* createOT: per-list order fix (push order of the reference)             */
+       SIGMA_T_PROP,         /* prop()                                      (propelim.cpp:46-81)       */
+       SIGMA_T_VO,           /* histCNF + scores + stable sort              (lcve.cpp:34-40)           */
+       SIGMA_T_ELECT,        /* election + marks                            (lcve.cpp:52-102)          */
+       SIGMA_T_SOT,          /* sortOT                                      (simplify.cpp:85-100)      */
+       SIGMA_T_SUB,          /* SUB + its units                             (subsume.cpp:23-43)        */
+       SIGMA_T_VE,           /* VE count + scan + emit + its units          (bounded.cpp:27-185)       */
+       SIGMA_T_COUNT,        /* countAll / countFinal                       (solve.hpp:645-671)        */
+       SIGMA_T_GC,           /* shrinkSimp between phases                   (simplify.cpp:235-247)     */
+       SIGMA_T_EXPORT,       /* final shrinkSimp fused with the device store -> AoS arena export       */
+       SIGMA_T_D2H,          /* sigma_download: device -> host copies                                  */
+       SIGMA_T_TOTAL_DEVICE, /* first kernel of sigma_execute to its last                              */
+       SIGMA_T_N = 20 };
 
 typedef struct sigma_report {
     int32_t  status;
@@ -108,10 +125,13 @@ typedef struct sigma_report {
     uint64_t literals_in;           /* inf.nLiterals after extract(): the "literals/s" numerator */
     int64_t  pures, inverters, andors, ites, xors, funs, resolutions, subsumed, strengthened;
     int64_t  units, sort_ties_gt24;
-    float    stage_ms[SIGMA_T_N];   /* CUDA-event milliseconds per stage, summed over phases      */
+    float    stage_ms[SIGMA_T_N];        /* CUDA-event milliseconds per stage                       */
+    uint32_t stage_launches[SIGMA_T_N];  /* kernels launched per stage                              */
+    uint64_t stage_bytes[SIGMA_T_N];     /* algorithmic bytes per stage, 0 = n/a  */
     uint64_t kernel_launches;       /* kernels of this library launched by the last execute       */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t elected_per_phase[8];
+    uint32_t election_rounds[8];
     uint64_t reserved[8];
 } sigma_report;
 
@@ -131,26 +151,27 @@ int  sigma_run(sigma_ctx *ctx, const sigma_opts *o, const sigma_formula *in, sig
                sigma_report *rep);
 
 /* split form (what sigma_run does internally; lets the host overlap, re-time or diff stages) */
-int  sigma_upload(sigma_ctx *ctx, const sigma_opts *o, const sigma_formula *in);   /* H2D + AoS->SoA */
-int  sigma_execute(sigma_ctx *ctx);                                                /* kernels only   */
+int  sigma_upload(sigma_ctx *ctx, const sigma_opts *o, const sigma_formula *in);   /* H2D only       */
+int  sigma_execute(sigma_ctx *ctx);                          /* ingest + phases + export, on device */
 int  sigma_result_sizes(sigma_ctx *ctx, sigma_formula *sizes);                     /* after execute  */
-int  sigma_download(sigma_ctx *ctx, sigma_formula *out);                           /* SoA->AoS + D2H */
+int  sigma_download(sigma_ctx *ctx, sigma_formula *out);                           /* D2H only       */
 int  sigma_get_report(sigma_ctx *ctx, sigma_report *rep);
-int  sigma_reset(sigma_ctx *ctx);   /* restore the uploaded formula on the device (re-timing)     */
+/* sigma_execute always starts from the uploaded formula, so it can be repeated for timing.     */
+
+/* pinned host memory for the hand-off buffers (the solver's SCNF arena allocator would call this
+ * instead of malloc, malloc.hpp:60-69, so that H2D/D2H run at full PCIe rate) */
+void *sigma_host_alloc(uint64_t bytes);
+void  sigma_host_free(void *p);
 
 /* host-polled interrupt flag (reference `interrupted`, control.cpp:130-159) */
 void sigma_set_interrupt_flag(sigma_ctx *ctx, const volatile int *flag);
 
 /* stage-level parity hooks: stop after `stage` (SIGMA_T_* id of the stage) of `phase`, then copy
- * a named device array to the host.  Names: c_off c_size c_w0 c_sig lits ot_off ot_len ot_data
- * occ order elected state value trail model marks n (scalars). phase < 0 disables. */
+ * a named device array to the host.  Names: hdr lits ot_off ot_len ot_data occ order elected
+ * state value trail model marks. phase < 0 disables. */
 int  sigma_set_stop(sigma_ctx *ctx, int phase, int stage);
 int  sigma_snapshot(sigma_ctx *ctx, const char *name, void *dst, uint64_t cap_bytes, uint64_t *nbytes);
 
-/* roofline probe: run ONE streaming kernel of the pass `iters` times on the uploaded formula
- * and return its mean CUDA-event milliseconds and the algorithmic bytes of one launch
- * (DESIGN.md table). kernel: "ot_build" | "histogram" | "compact" | "ingest" | "count". */
-int  sigma_time_kernel(sigma_ctx *ctx, const char *kernel, int iters, float *ms, uint64_t *algo_bytes);
 
 #ifdef __cplusplus
 }

@@ -299,3 +299,46 @@ def write_dimacs(path, nvars, offsets, lits, chunk=1 << 20):
                 # zeros mark clause ends; print with newline after each zero
                 txt = " ".join(map(str, out.tolist())).replace(" 0 ", " 0\n")
                 f.write(txt + "\n")
+
+
+def fuzz_mix(seed):
+    """Small mixed instance (8-120 variables): random 2..5-literal clauses, a few Tseitin gates,
+    duplicated and subsumed clauses.  Roughly one seed in twelve makes the pass derive units, one
+    in twelve makes it derive the empty clause: the edge cases of prop()/strengthen()/addResolvent
+    (reference propelim.cpp:46-81, subsume.cpp:45-76, bounded.cpp:279-307)."""
+    import random
+    rng = random.Random(seed)
+    nv = rng.randint(8, 120)
+    clauses = []
+    kind = rng.random()
+    nc = int(nv * rng.uniform(1.5, 4.5))
+    for _ in range(nc):
+        k = rng.choice([2, 2, 3, 3, 3, 4, 5]) if kind < 0.7 else rng.choice([2, 3])
+        k = min(k, nv)
+        vs = rng.sample(range(1, nv + 1), k)
+        clauses.append([v if rng.random() < 0.5 else -v for v in vs])
+    for _ in range(rng.randint(0, nv // 3)):
+        if nv < 4:
+            break
+        x, a, b, c = rng.sample(range(1, nv + 1), 4)
+        t = rng.random()
+        if t < 0.25:
+            clauses += [[-x, a], [-x, b], [x, -a, -b]]
+        elif t < 0.5:
+            clauses += [[-x, a, b], [-x, -a, -b], [x, -a, b], [x, a, -b]]
+        elif t < 0.75:
+            clauses += [[-x, -a, b], [-x, a, c], [x, -a, -b], [x, a, -c]]
+        else:
+            clauses += [[-x, a], [x, -a]]
+    for _ in range(rng.randint(0, 5)):
+        c = rng.choice(clauses)
+        clauses.append(list(c))
+        c = rng.choice(clauses)
+        extra = [v for v in range(1, nv + 1) if v not in [abs(l) for l in c]]
+        if extra:
+            clauses.append(c + [rng.choice(extra) * rng.choice([1, -1])])
+    rng.shuffle(clauses)
+    sizes = np.array([len(c) for c in clauses], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    lits = np.array([l for c in clauses for l in c], dtype=np.int32)
+    return nv, off, lits

@@ -1,0 +1,93 @@
+/* sigma_backend.h - the launch layer between the pass driver (sigma_pass.cpp) and the device.
+ *
+ * libsigma_b200.so links sigma_pass.cpp against sigma_kernels.cu, which implements every
+ * function below as CUDA kernels for sm_100a.  There is no other implementation in the product.
+ * (tests/emul/ links the same driver against a serial host stand-in so that the host logic and
+ * the per-item bodies of sigma_items.cuh can be exercised in a container without a GPU; that
+ * build is test infrastructure, is never installed and cannot be loaded by the library.)
+ */
+#ifndef SIGMA_BACKEND_H
+#define SIGMA_BACKEND_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "sigma_types.h"
+
+/* one work item per thread, bodies in sigma_items.cuh */
+enum SgItemKind {
+    SGK_IDSORT = 0,     /* n = nlit      : order fix of every occurrence list                     */
+    SGK_REDUCE,         /* n = nlit      : reduceOT                                                */
+    SGK_ELECT_PREP,     /* n = nvars     : static election classes                                 */
+    SGK_SORTOT,         /* n = 2*elected : sortOT                                                  */
+    SGK_SCRATCH_LEN,    /* n = elected   : scratch words per elected variable                      */
+    SGK_SUB,            /* n = elected                                                             */
+    SGK_VE_COUNT,       /* n = elected                                                             */
+    SGK_VE_EMIT,        /* n = elected                                                             */
+    SGK_N
+};
+/* sequential stages, one thread */
+enum SgSerialKind { SGS_PROP = 0, SGS_MARKS, SGS_APPLY_UNITS, SGS_N };
+
+#ifdef __cplusplus
+extern "C++" {
+#endif
+
+/* ---- device lifetime / memory ---------------------------------------------------------------- */
+int   be_init(int device, void **stream_out, char *err, size_t errlen);   /* 0 = ok */
+void  be_shutdown(void *stream);
+void *be_malloc(size_t bytes);                 /* NULL on failure */
+void  be_free(void *p);
+void *be_host_alloc(size_t bytes);             /* pinned host memory */
+void  be_host_free(void *p);
+int   be_h2d(void *stream, void *dst, const void *src, size_t bytes);
+int   be_d2h(void *stream, void *dst, const void *src, size_t bytes);
+int   be_d2d(void *stream, void *dst, const void *src, size_t bytes);
+int   be_memset(void *stream, void *dst, int byte, size_t bytes);
+int   be_sync(void *stream, char *err, size_t errlen);                      /* 0 = ok */
+void *be_event_create(void);
+void  be_event_destroy(void *ev);
+void  be_event_record(void *stream, void *ev);
+float be_event_ms(void *a, void *b);
+uint64_t be_launch_count(void);                /* kernels launched so far by this library */
+
+/* ---- streaming kernels ------------------------------------------------------------------------ */
+/* AoS SCNF arena -> device store (reference hand-off layout, sclause.hpp:45-49) */
+void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes);
+void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs,
+                    sg_u4 *hdr, uint32_t *lits);
+/* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */
+void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp);
+size_t be_scan_tmp_words(uint32_t n);
+/* per-literal occurrence histogram over live clauses (histogram.hpp:43-50, simplify.cpp:50-58) */
+void be_hist(void *s, const SgView &v, uint32_t *counts);
+/* scatter clause ids into the lists; cursor must be zero */
+void be_scatter(void *s, const SgView &v, uint32_t *cursor);
+/* scores[v] = ps*ns (uint32 wrap, histogram.hpp:23), order[v-1] = v */
+void be_scores(void *s, const SgView &v);
+/* stable ascending sort of (keys, vals); result in keys/vals; tmp arrays of n each */
+void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t *tmpk, uint32_t *tmpv, uint32_t *tmp,
+                   uint32_t key_bits);
+size_t be_sort_tmp_words(uint32_t n);
+void be_rank(void *s, const SgView &v);                                           /* rank[order[r]] = r */
+/* election rounds */
+void be_elect_init(void *s, const SgView &v, uint32_t *wl);                        /* fills wl, sc->wl_count[0] */
+void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity);
+void be_acting_flags(void *s, const SgView &v, uint32_t *flags_acting, uint32_t *flags_elected);   /* per rank position */
+void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe);
+/* generic item / serial launches */
+void be_items(void *s, int kind, const SgView &v, uint32_t n);
+void be_serial(void *s, int kind, const SgView &v, uint32_t arg);
+void be_sort_units(void *s, const SgView &v, uint32_t n);                          /* by (eidx, seq) */
+/* live clause / literal count (solve.hpp:661-671) and melted variable count (solve.hpp:645-654) */
+void be_count_live(void *s, const SgView &v);
+void be_count_melted(void *s, const SgView &v, uint32_t *out);
+/* compaction (simplify.cpp:235-247): flags/sizes of live clauses, then the move */
+void be_live_flags(void *s, const SgView &v, uint32_t *flags, uint32_t *sizes);
+void be_compact_move(void *s, const SgView &v, const uint32_t *newid, const uint32_t *newoff, sg_u4 *hdr2, uint32_t *lits2);
+/* device store -> AoS SCNF arena + refs in the reference's layout */
+void be_export(void *s, const SgView &v, const uint32_t *newid, const uint32_t *newoff, uint32_t *arena, uint64_t *refs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

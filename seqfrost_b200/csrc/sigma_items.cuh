@@ -1,0 +1,1291 @@
+/* sigma_items.cuh - the per-work-item bodies of the irregular SIGmA stages.
+ *
+ * Every function here processes ONE independent work item (one elected variable, one
+ * occurrence list, one election candidate) and touches only that item's clause neighbourhood,
+ * which LCVE guarantees to be disjoint from every other elected variable's (reference
+ * src/lcve.cpp:64-83,121-145).  The CUDA kernels in sigma_kernels.cu run one item per thread;
+ * the behaviour of each item follows the cited reference lines so that the result is
+ * bit-identical to the reference's sequential loop (ledger 4-7).
+ */
+#ifndef SIGMA_ITEMS_CUH
+#define SIGMA_ITEMS_CUH
+
+#include "sigma_types.h"
+
+/* ------------------------------------------------------------------------------------------ */
+/* atomics (plain memory operations when compiled for the host test harness)                    */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD uint32_t sg_atomic_add(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    uint32_t o = *p; *p = o + v; return o;
+#endif
+}
+SG_HD void sg_atomic_sub(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicSub(p, v);
+#else
+    *p -= v;
+#endif
+}
+SG_HD void sg_atomic_min(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+SG_HD void sg_atomic_add64(unsigned long long *p, unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+SG_HD void sg_set_flag(uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    atomicExch(p, 1u);
+#else
+    *p = 1u;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* clause accessors                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+#define SG_OFF(v, c)   ((v).hdr[c].x)
+#define SG_SIZE(v, c)  ((int)(v).hdr[c].y)
+#define SG_W0(v, c)    ((v).hdr[c].z)
+#define SG_SIG(v, c)   ((v).hdr[c].w)
+#define SG_LITS(v, c)  ((v).lits + (v).hdr[c].x)
+
+SG_HD bool sg_original(const SgView &v, uint32_t c) { return (SG_W0(v, c) & SG_ST_MASK) == 0; }
+SG_HD bool sg_deleted(const SgView &v, uint32_t c)  { return (SG_W0(v, c) & SG_DELETED) != 0; }
+SG_HD bool sg_learnt(const SgView &v, uint32_t c)   { return (SG_W0(v, c) & SG_LEARNT) != 0; }
+SG_HD bool sg_molten(const SgView &v, uint32_t c)   { return (SG_W0(v, c) & SG_MOLTEN) != 0; }
+SG_HD void sg_melt(const SgView &v, uint32_t c)     { v.hdr[c].z |= SG_MOLTEN; }
+SG_HD void sg_freeze(const SgView &v, uint32_t c)   { v.hdr[c].z &= ~SG_MOLTEN; }
+SG_HD void sg_mark_deleted(const SgView &v, uint32_t c) { v.hdr[c].z = (v.hdr[c].z & ~SG_ST_MASK) | SG_DELETED; }
+
+SG_HD uint32_t *sg_list(const SgView &v, uint32_t lit) { return v.ot_data + v.ot_off[lit]; }
+
+SG_HD void sg_push_unit(const SgView &v, uint32_t eidx, uint32_t &seq, uint32_t lit)
+{
+    const uint32_t k = sg_atomic_add(&v.sc->n_units, 1u);
+    if (k < v.ubuf_cap) {
+        SgUnit u; u.eidx = eidx; u.seq = seq; u.lit = lit; u.pad = 0;
+        v.ubuf[k] = u;
+    }
+    seq++;
+}
+
+/* ascending sort of a short literal array (sort.hpp:36-44 SORT: any correct sort gives the
+ * same result on plain integers) */
+SG_HD void sg_sort_lits(uint32_t *d, int n)
+{
+    for (int i = 1; i < n; ++i) {
+        const uint32_t t = d[i];
+        int j = i;
+        while (j > 0 && d[j - 1] > t) { d[j] = d[j - 1]; --j; }
+        d[j] = t;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* sortOT (simplify.cpp:85-100): CNF_CMP_KEY (simplify.hpp:30-47) through SORTCMP (sort.hpp:64-72) */
+/* <= 24 entries: the reference's insertion sort; larger: libstdc++ std::sort (introsort),       */
+/* restated step for step so that even the order of tied keys is the reference's.                */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD bool sg_key_less(const SgView &v, uint32_t a, uint32_t b)
+{
+    const sg_u4 x = v.hdr[a], y = v.hdr[b];
+    const int xs = (int)x.y, ys = (int)y.y;
+    if (xs < ys) return true;
+    if (xs > ys) return false;
+    uint32_t xk = v.lits[x.x], yk = v.lits[y.x];
+    if (xk < yk) return true;
+    if (xk > yk) return false;
+    xk = v.lits[x.x + xs - 1], yk = v.lits[y.x + ys - 1];
+    if (xk < yk) return true;
+    if (xk > yk) return false;
+    return x.w < y.w;
+}
+
+SG_HD void sg_ins_sort_ref(const SgView &v, uint32_t *d, int size)
+{   /* sort.hpp:92-108 */
+    if (size == 2) { if (sg_key_less(v, d[1], d[0])) { uint32_t t = d[0]; d[0] = d[1]; d[1] = t; } }
+    else if (size > 2) {
+        for (int i = 1; i < size; ++i) {
+            if (sg_key_less(v, d[i], d[i - 1])) {
+                const uint32_t tmp = d[i];
+                int j = i, j1 = i - 1;
+                do { d[j--] = d[j1]; } while (j != 0 && sg_key_less(v, tmp, d[--j1]));
+                d[j] = tmp;
+            }
+        }
+    }
+}
+
+/* libstdc++ (GCC 13) bits/stl_algo.h + bits/stl_heap.h, restated over an index range */
+SG_HD void sg_std_unguarded_linear_insert(const SgView &v, uint32_t *d, int last)
+{
+    const uint32_t val = d[last];
+    int next = last - 1;
+    while (sg_key_less(v, val, d[next])) { d[last] = d[next]; last = next; --next; }
+    d[last] = val;
+}
+SG_HD void sg_std_insertion_sort(const SgView &v, uint32_t *d, int first, int last)
+{
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (sg_key_less(v, d[i], d[first])) {
+            const uint32_t val = d[i];
+            for (int k = i; k > first; --k) d[k] = d[k - 1];
+            d[first] = val;
+        } else sg_std_unguarded_linear_insert(v, d, i);
+    }
+}
+SG_HD void sg_std_adjust_heap(const SgView &v, uint32_t *d, int first, int hole, int len, uint32_t value)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (sg_key_less(v, d[first + child], d[first + child - 1])) child--;
+        d[first + hole] = d[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        d[first + hole] = d[first + child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;       /* __push_heap */
+    while (hole > top && sg_key_less(v, d[first + parent], value)) {
+        d[first + hole] = d[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    d[first + hole] = value;
+}
+SG_HD void sg_std_heapsort(const SgView &v, uint32_t *d, int first, int last)
+{   /* __partial_sort(first,last,last): __heap_select = make_heap, then __sort_heap */
+    const int len = last - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            const uint32_t value = d[first + parent];
+            sg_std_adjust_heap(v, d, first, parent, len, value);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int l = last;
+    while (l - first > 1) {
+        --l;
+        const uint32_t value = d[l];
+        d[l] = d[first];
+        sg_std_adjust_heap(v, d, first, 0, l - first, value);
+    }
+}
+SG_HDN inline void sg_std_sort(const SgView &v, uint32_t *d, int n)
+{
+    if (n < 2) return;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) lg++;
+    int sf[64], sl[64], sd[64], sp = 0;
+    sf[0] = 0; sl[0] = n; sd[0] = 2 * lg; sp = 1;
+    while (sp) {
+        --sp;
+        int first = sf[sp], last = sl[sp], depth = sd[sp];
+        while (last - first > 16) {
+            if (depth == 0) { sg_std_heapsort(v, d, first, last); break; }
+            --depth;
+            /* __unguarded_partition_pivot */
+            const int mid = first + (last - first) / 2;
+            {   /* __move_median_to_first(first, first+1, mid, last-1) */
+                const int a = first + 1, b = mid, c = last - 1;
+                int m;
+                if (sg_key_less(v, d[a], d[b])) {
+                    if (sg_key_less(v, d[b], d[c])) m = b;
+                    else if (sg_key_less(v, d[a], d[c])) m = c;
+                    else m = a;
+                } else if (sg_key_less(v, d[a], d[c])) m = a;
+                else if (sg_key_less(v, d[b], d[c])) m = c;
+                else m = b;
+                const uint32_t t = d[first]; d[first] = d[m]; d[m] = t;
+            }
+            int lo = first + 1, hi = last;
+            while (true) {
+                while (sg_key_less(v, d[lo], d[first])) ++lo;
+                --hi;
+                while (sg_key_less(v, d[first], d[hi])) --hi;
+                if (!(lo < hi)) break;
+                const uint32_t t = d[lo]; d[lo] = d[hi]; d[hi] = t;
+                ++lo;
+            }
+            const int cut = lo;
+            /* recurse on [cut,last), iterate on [first,cut) */
+            if (sp < 64) { sf[sp] = cut; sl[sp] = last; sd[sp] = depth; sp++; }
+            last = cut;
+        }
+    }
+    /* __final_insertion_sort */
+    if (n > 16) {
+        sg_std_insertion_sort(v, d, 0, 16);
+        for (int i = 16; i < n; ++i) sg_std_unguarded_linear_insert(v, d, i);
+    } else sg_std_insertion_sort(v, d, 0, n);
+}
+
+/* one occurrence list of an elected variable */
+SG_HDN inline void sg_sortot_item(const SgView &v, uint32_t lit)
+{
+    const int n = (int)v.ot_len[lit];
+    if (n < 2) return;
+    uint32_t *d = sg_list(v, lit);
+    if (n <= 24) sg_ins_sort_ref(v, d, n);
+    else {
+        sg_std_sort(v, d, n);
+        uint32_t ties = 0;
+        for (int i = 1; i < n; ++i)
+            if (!sg_key_less(v, d[i - 1], d[i])) ties++;
+        if (ties) sg_atomic_add64(&v.sc->sort_ties_gt24, ties);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* occurrence-list order fix after the atomic scatter: ascending clause id == the reference's   */
+/* push order (simplify.cpp:50-58)                                                              */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD void sg_idsort_item(const SgView &v, uint32_t lit)
+{
+    const int n = (int)v.ot_len[lit];
+    uint32_t *d = sg_list(v, lit);
+    for (int i = 1; i < n; ++i) {
+        const uint32_t t = d[i];
+        int j = i;
+        while (j > 0 && d[j - 1] > t) { d[j] = d[j - 1]; --j; }
+        d[j] = t;
+    }
+}
+
+/* reduceOL (simplify.cpp:63-72) */
+SG_HD void sg_reduce_item(const SgView &v, uint32_t lit)
+{
+    const int n = (int)v.ot_len[lit];
+    if (!n) return;
+    uint32_t *d = sg_list(v, lit);
+    int j = 0;
+    for (int i = 0; i < n; ++i) {
+        if (sg_deleted(v, d[i])) continue;
+        d[j++] = d[i];
+    }
+    v.ot_len[lit] = (uint32_t)j;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* units: enqueueUnit (solve.hpp:373-398, markFrozen :485-490)                                   */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD bool sg_unassigned(const SgView &v, uint32_t lit) { return (v.value[lit] & (int8_t)-2) != 0; }
+
+SG_HD void sg_enqueue_unit(const SgView &v, uint32_t lit)
+{
+    const uint32_t var = SG_ABS(lit);
+    v.state[var] = (uint8_t)SG_FROZEN_M;
+    v.sc->max_frozen++;
+    v.value[lit] = 1;
+    v.value[SG_FLIP(lit)] = 0;
+    v.trail[v.sc->n_trail++] = lit;
+    v.sc->unassigned--;
+}
+
+/* applies the units collected by one SUB or VE stage in the reference's sequential order.
+ * Run by ONE thread; `n` units already sorted by (eidx, seq). */
+SG_HDN inline void sg_apply_units_serial(const SgView &v, uint32_t n)
+{
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t lit = v.ubuf[k].lit;
+        if (sg_unassigned(v, lit)) { sg_enqueue_unit(v, lit); v.sc->units_forced++; }
+        else if (!v.value[lit]) { v.sc->unsat = 1; return; }   /* subsume.cpp:64-68, bounded.cpp:290-294 */
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* prop (propelim.cpp:23-81): BCP over the occurrence table; sequential, ONE thread.            */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD void sg_toblivion_list(const SgView &v, uint32_t lit)
+{   /* simplify.hpp:385-391 */
+    const int n = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    for (int i = 0; i < n; ++i) sg_mark_deleted(v, d[i]);
+    v.ot_len[lit] = 0;
+}
+
+SG_HDN inline void sg_prop_serial(const SgView &v)
+{
+    SgScalars *sc = v.sc;
+    while (sc->propagated < sc->n_trail) {
+        const uint32_t assign = v.trail[sc->propagated++], flipped = SG_FLIP(assign);
+        const int n = (int)v.ot_len[flipped];
+        const uint32_t *d = sg_list(v, flipped);
+        for (int i = 0; i < n; ++i) {
+            const uint32_t c = d[i];
+            if (sg_deleted(v, c)) continue;
+            /* propClause (propelim.cpp:23-44), including its partial rewrite of a satisfied clause */
+            uint32_t *l = SG_LITS(v, c);
+            const int size = SG_SIZE(v, c);
+            uint32_t sig = 0;
+            int j = 0;
+            bool sat = false;
+            for (int k = 0; k < size; ++k) {
+                const uint32_t other = l[k];
+                if (other != flipped) {
+                    if (v.value[other] > 0) { sat = true; break; }
+                    l[j++] = other;
+                    sig |= SG_HASH(other);
+                }
+            }
+            if (sat) { sg_mark_deleted(v, c); continue; }
+            v.hdr[c].w = sig;
+            v.hdr[c].y = (uint32_t)(size - 1);
+            const int nsize = size - 1;
+            if (!nsize) { sc->unsat = 1; return; }
+            if (nsize == 1) {
+                const uint32_t unit = l[0];
+                if (sg_unassigned(v, unit)) sg_enqueue_unit(v, unit);
+                else { sc->unsat = 1; return; }
+            }
+        }
+        v.ot_len[flipped] = 0;
+        sg_toblivion_list(v, assign);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* LCVE election (lcve.cpp:52-83, depFreeze :121-145) as a deterministic parallel greedy:       */
+/* a candidate is decided once every earlier-ranked clause neighbour is decided.                */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD bool sg_freezable(const SgView &v, uint32_t var)
+{   /* lcve.cpp:137 */
+    return v.occ[2 * var] < v.pmax || v.occ[2 * var + 1] < v.nmax;
+}
+SG_HD bool sg_break_cond(const SgView &v, uint32_t var)
+{   /* lcve.cpp:70,73 */
+    const uint32_t maxoccurs = (uint32_t)v.o.lcve_max_occurs;
+    const uint32_t ps = v.occ[2 * var], ns = v.occ[2 * var + 1];
+    if (ps > maxoccurs || ns > maxoccurs) return true;
+    return v.ot_len[2 * var] >= v.pmax && v.ot_len[2 * var + 1] >= v.nmax;
+}
+
+/* static classification, one thread per variable (lcve.cpp:66-70) */
+SG_HD void sg_elect_prep_item(const SgView &v, uint32_t var)
+{
+    const uint32_t ps = v.occ[2 * var], ns = v.occ[2 * var + 1];
+    uint8_t st;
+    if ((v.ifrozen && v.ifrozen[var]) || v.state[var] || (!ps && !ns)) st = SG_E_SKIP;
+    else if (!sg_freezable(v, var)) {
+        /* can never be frozen, and ot sizes >= occurrences >= mu: the loop ends here if reached */
+        st = SG_E_BREAK;
+        sg_atomic_min(&v.sc->brk_rank, v.rank[var]);
+    } else st = SG_E_UNDECIDED;
+    v.estat[var] = st;
+}
+
+/* returns true when the candidate stays undecided (goes to the next round's worklist) */
+SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
+{
+    const uint32_t rc = v.rank[cand];
+    if (rc > *(volatile uint32_t *)&v.sc->brk_rank) { v.estat[cand] = SG_E_SKIP; return false; }
+    const int maxcsize = v.o.lcve_clause_max;
+    bool blocked = false, fail[2] = { false, false };
+    uint32_t visits = 0;
+    for (uint32_t side = 0; side < 2; ++side) {
+        const uint32_t lit = 2 * cand + side;
+        const int n = (int)v.ot_len[lit];
+        const uint32_t *d = sg_list(v, lit);
+        for (int i = 0; i < n; ++i) {
+            const sg_u4 h = v.hdr[d[i]];
+            if (h.z & SG_DELETED) continue;
+            const int size = (int)h.y;
+            if (size > maxcsize) fail[side] = true;
+            const uint32_t *l = v.lits + h.x;
+            for (int k = 0; k < size; ++k) {
+                const uint32_t other = l[k], u = SG_ABS(other);
+                if (u == cand) continue;
+                visits++;
+                if (v.rank[u] > rc) continue;
+                const uint8_t s = *(volatile uint8_t *)&v.estat[u];
+                if (s == SG_E_UNDECIDED) blocked = true;
+                else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other))) {
+                    v.estat[cand] = SG_E_FROZEN;
+                    return false;
+                }
+            }
+        }
+    }
+#if !defined(__CUDA_ARCH__)
+    v.sc->elect_visits += visits;
+#endif
+    if (blocked) return true;
+    uint8_t st;
+    if (sg_break_cond(v, cand)) { st = SG_E_BREAK; sg_atomic_min(&v.sc->brk_rank, rc); }
+    else if (fail[0]) st = SG_E_NONE;
+    else if (fail[1]) st = SG_E_PONLY;
+    else st = SG_E_BOTH;
+#if defined(__CUDA_ARCH__)
+    __threadfence();
+#endif
+    *(volatile uint8_t *)&v.estat[cand] = st;
+    return false;
+}
+
+/* function-table core marks (lcve.cpp:85-102): the first 12 variables of the freeze stack.
+ * ONE thread; `acting` holds the acting candidates in election order (bit31 = P only). */
+SG_HDN inline void sg_marks_serial(const SgView &v, uint32_t n_acting)
+{
+    SgScalars *sc = v.sc;
+    for (uint32_t i = 0; i < sc->n_core; ++i) v.marks[sc->core[i]] = -1;   /* clearMapFrozen, solve.hpp:337-345 */
+    sc->n_core = 0;
+    if (!v.o.ve_fun_en) return;
+    uint32_t core[12];
+    uint32_t nc = 0;
+    for (uint32_t a = 0; a < n_acting && nc < 12; ++a) {
+        const uint32_t cand = v.acting[a] & 0x7fffffffu;
+        const uint32_t sides = (v.acting[a] >> 31) ? 1u : 2u;
+        for (uint32_t side = 0; side < sides && nc < 12; ++side) {
+            const uint32_t lit = 2 * cand + side;
+            const int n = (int)v.ot_len[lit];
+            const uint32_t *d = sg_list(v, lit);
+            for (int i = 0; i < n && nc < 12; ++i) {
+                const uint32_t c = d[i];
+                if (sg_deleted(v, c)) continue;
+                const uint32_t *l = SG_LITS(v, c);
+                const int size = SG_SIZE(v, c);
+                for (int k = 0; k < size && nc < 12; ++k) {
+                    const uint32_t u = SG_ABS(l[k]);
+                    if (u == cand || !sg_freezable(v, u)) continue;
+                    bool seen = false;
+                    for (uint32_t q = 0; q < nc; ++q) if (core[q] == u) { seen = true; break; }
+                    if (!seen) core[nc++] = u;
+                }
+            }
+        }
+    }
+    for (uint32_t q = 0; q < nc; ++q) { v.marks[core[q]] = (int8_t)q; sc->core[q] = core[q]; }
+    sc->n_core = nc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* SUB: self-subsuming strengthening + backward subsumption (subsume.hpp:26-218, subsume.cpp:45-76) */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD bool sg_sig_sub(uint32_t A, uint32_t B) { return !(A & ~B); }                 /* simplify.hpp:119 */
+SG_HD bool sg_sig_selfsub(uint32_t A, uint32_t B)
+{   /* simplify.hpp:121-125 */
+    const uint32_t Bt = B | ((B & 0xAAAAAAAAu) >> 1) | ((B & 0x55555555u) << 1);
+    return !(A & ~Bt);
+}
+
+SG_HD bool sg_sub_lits(const uint32_t *d1, int n1, const uint32_t *d2, int n2)
+{   /* subsume.hpp:38-64 */
+    int i = 0, j = 0, sub = 0;
+    while (i < n1 && j < n2) {
+        const uint32_t a = d1[i], b = d2[j];
+        if (a < b) i++;
+        else if (b < a) j++;
+        else { sub++; i++; j++; }
+    }
+    return sub == n1;
+}
+
+SG_HD bool sg_selfsub_lits(uint32_t x, uint32_t fx, const uint32_t *d1, int n1, const uint32_t *d2, int n2)
+{   /* subsume.hpp:93-137 */
+    int i = 0, j = 0, sub = 0;
+    bool self = false;
+    while (i < n1 && j < n2) {
+        const uint32_t a = d1[i], b = d2[j];
+        if (a == fx) i++;
+        else if (b == x) { self = true; j++; }
+        else if (a < b) i++;
+        else if (b < a) j++;
+        else { sub++; i++; j++; }
+    }
+    if (sub + 1 == n1) {
+        if (self) return true;
+        while (j < n2) { if (d2[j] == x) return true; j++; }
+    }
+    return false;
+}
+
+SG_HD void sg_strengthen(const SgView &v, uint32_t c, uint32_t me, uint32_t eidx, uint32_t &seq)
+{   /* subsume.cpp:45-76 */
+    uint32_t *l = SG_LITS(v, c);
+    const int size = SG_SIZE(v, c);
+    uint32_t sig = 0;
+    int j = 0;
+    for (int k = 0; k < size; ++k) {
+        const uint32_t lit = l[k];
+        if (lit != me) { l[j++] = lit; sig |= SG_HASH(lit); }
+    }
+    v.hdr[c].w = sig;
+    v.hdr[c].y = (uint32_t)(size - 1);
+    if (size - 1 == 1) sg_push_unit(v, eidx, seq, l[0]);
+    else if (sg_learnt(v, c)) {
+        /* bumpShrunken (solve.hpp:725-737) */
+        const uint32_t w0 = SG_W0(v, c);
+        const int old_lbd = (int)(w0 >> SG_LBD_SH);
+        if (old_lbd > v.o.lbd_tier1) {
+            const int sz = size - 2;
+            const int new_lbd = sz < old_lbd ? sz : old_lbd;
+            if (new_lbd < old_lbd)
+                v.hdr[c].z = (w0 & 0xFu) | (1u << SG_USAGE_SH) | ((uint32_t)new_lbd << SG_LBD_SH);
+        }
+    }
+}
+
+SG_HDN inline void sg_self_sub_half(const SgView &v, uint32_t x, uint32_t fx, uint32_t eidx, uint32_t &seq,
+                                    uint32_t &n_str, uint32_t &n_sub)
+{   /* one loop of self_sub_x (subsume.hpp:186-199): clauses of `x` against the list of `fx` */
+    const int maxsz = v.o.sub_clause_max;
+    uint32_t *me = sg_list(v, x);
+    const int nme = (int)v.ot_len[x];
+    const uint32_t *ot = sg_list(v, fx);
+    const int not_ = (int)v.ot_len[fx];
+    for (int i = 0; i < nme; ++i) {
+        const uint32_t c = me[i];
+        if (SG_SIZE(v, c) > maxsz) break;
+        if (sg_deleted(v, c)) continue;
+        {   /* selfsubsume (subsume.hpp:158-177) */
+            const int candsz = SG_SIZE(v, c);
+            const uint32_t candsig = SG_SIG(v, c);
+            for (int j = 0; j < not_; ++j) {
+                const uint32_t s = ot[j];
+                const sg_u4 hs = v.hdr[s];
+                const int subsize = (int)hs.y;
+                if (subsize > candsz) break;
+                if (hs.z & SG_DELETED) continue;
+                if (subsize > 1 && sg_sig_selfsub(hs.w, candsig) &&
+                    sg_selfsub_lits(x, fx, v.lits + hs.x, subsize, SG_LITS(v, c), candsz)) {
+                    sg_strengthen(v, c, x, eidx, seq);
+                    sg_melt(v, c);
+                    n_str++;
+                    break;
+                }
+            }
+        }
+        {   /* subsume (subsume.hpp:139-156) */
+            const int candsz = SG_SIZE(v, c);
+            const bool cmolten = sg_molten(v, c);
+            const uint32_t candsig = SG_SIG(v, c);
+            for (int j = 0; j < i; ++j) {
+                const uint32_t s = me[j];
+                const sg_u4 hs = v.hdr[s];
+                if (hs.z & SG_DELETED) continue;
+                const int ssz = (int)hs.y;
+                if (cmolten && ssz > candsz) continue;
+                if (ssz > 1 && sg_sig_sub(hs.w, candsig) && sg_sub_lits(v.lits + hs.x, ssz, SG_LITS(v, c), candsz)) {
+                    if ((hs.z & SG_LEARNT) && sg_original(v, c)) v.hdr[s].z = hs.z & ~SG_ST_MASK;
+                    sg_mark_deleted(v, c);
+                    n_sub++;
+                    break;
+                }
+            }
+        }
+    }
+    /* updateOL (subsume.hpp:26-36) */
+    int j = 0;
+    for (int i = 0; i < nme; ++i) {
+        const uint32_t c = me[i];
+        if (sg_molten(v, c)) sg_freeze(v, c);
+        else if (!sg_deleted(v, c)) me[j++] = c;
+    }
+    v.ot_len[x] = (uint32_t)j;
+}
+
+SG_HDN inline void sg_sub_item(const SgView &v, uint32_t eidx)
+{   /* subsume.cpp:32-39 */
+    const uint32_t var = v.elected[eidx];
+    const uint32_t p = 2 * var, n = p | 1u;
+    const int maxoccurs = v.o.sub_max_occurs;
+    if ((int)v.ot_len[p] > maxoccurs || (int)v.ot_len[n] > maxoccurs) return;
+    uint32_t seq = 0, n_str = 0, n_sub = 0;
+    sg_self_sub_half(v, p, n, eidx, seq, n_str, n_sub);
+    sg_self_sub_half(v, n, p, eidx, seq, n_str, n_sub);
+    if (n_str) sg_atomic_add64(&v.sc->strengthened, n_str);
+    if (n_sub) sg_atomic_add64(&v.sc->subsumed, n_sub);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* BVE: decision + resolvent counting (bounded.cpp:41-160 and the gate headers)                 */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD int sg_merge_count(uint32_t x, const uint32_t *d1, int n1, const uint32_t *d2, int n2)
+{   /* simplify.hpp:228-260; x is a VARIABLE */
+    int i = 0, j = 0, len = n1 + n2 - 2;
+    while (i < n1 && j < n2) {
+        const uint32_t l1 = d1[i], l2 = d2[j];
+        const uint32_t v1 = SG_ABS(l1), v2 = SG_ABS(l2);
+        if (v1 == x) i++;
+        else if (v2 == x) j++;
+        else if ((l1 ^ l2) == 1u) return 0;
+        else if (v1 < v2) i++;
+        else if (v2 < v1) j++;
+        else { i++; j++; len--; }
+    }
+    return len;
+}
+
+SG_HD int sg_merge_emit(uint32_t x, const uint32_t *d1, int n1, const uint32_t *d2, int n2, uint32_t *out, uint32_t *sig_out)
+{   /* simplify.hpp:181-226; returns -1 for a tautology, else the resolvent size */
+    int i = 0, j = 0, n = 0;
+    uint32_t sig = 0;
+    while (i < n1 && j < n2) {
+        const uint32_t l1 = d1[i], l2 = d2[j];
+        const uint32_t v1 = SG_ABS(l1), v2 = SG_ABS(l2);
+        if (v1 == x) i++;
+        else if (v2 == x) j++;
+        else if ((l1 ^ l2) == 1u) return -1;
+        else if (v1 < v2) { i++; out[n++] = l1; sig |= SG_HASH(l1); }
+        else if (v2 < v1) { j++; out[n++] = l2; sig |= SG_HASH(l2); }
+        else { i++; j++; out[n++] = l1; sig |= SG_HASH(l1); }
+    }
+    while (i < n1) { const uint32_t l1 = d1[i++]; if (SG_ABS(l1) != x) { out[n++] = l1; sig |= SG_HASH(l1); } }
+    while (j < n2) { const uint32_t l2 = d2[j++]; if (SG_ABS(l2) != x) { out[n++] = l2; sig |= SG_HASH(l2); } }
+    *sig_out = sig;
+    return n;
+}
+
+/* pair filter shared by the three count loops and the three emit loops:
+ * mode RESOLVE: all original pairs; SUBST: a != b; CORE: !a || !b (bounded.cpp:205,235; function.hpp:109) */
+SG_HD bool sg_pair_ok(int mode, bool a, bool b)
+{
+    return mode == SG_VE_RESOLVE ? true : (mode == SG_VE_SUBST ? (a != b) : (!a || !b));
+}
+
+SG_HD void sg_count_lits_before(const SgView &v, uint32_t lit, int &n)
+{   /* simplify.hpp:288-296 */
+    const int len = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    for (int i = 0; i < len; ++i) if (sg_original(v, d[i])) n += SG_SIZE(v, d[i]);
+}
+
+/* countSubstituted (simplify.hpp:298-328) / countMinResolvents (function.hpp:95-126) /
+ * countResolvents bounded (simplify.hpp:355-383): returns TRUE when the bound is EXCEEDED. */
+SG_HDN inline bool sg_count_bounded(const SgView &v, int mode, uint32_t x, int clsbefore, uint32_t me, uint32_t other,
+                                    int &nAddedCls, int &nAddedLits)
+{
+    const int rlimit = v.o.ve_clause_max;
+    const int nme = (int)v.ot_len[me], noth = (int)v.ot_len[other];
+    const uint32_t *dm = sg_list(v, me), *dt = sg_list(v, other);
+    for (int i = 0; i < nme; ++i) {
+        const sg_u4 hi = v.hdr[dm[i]];
+        if (hi.z & SG_ST_MASK) continue;
+        const bool a = (hi.z & SG_MOLTEN) != 0;
+        for (int j = 0; j < noth; ++j) {
+            const sg_u4 hj = v.hdr[dt[j]];
+            if (hj.z & SG_ST_MASK) continue;
+            const bool b = (hj.z & SG_MOLTEN) != 0;
+            int rsize;
+            if (sg_pair_ok(mode, a, b) &&
+                (rsize = sg_merge_count(x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y)) > 1) {
+                if (++nAddedCls > clsbefore || (rlimit && rsize > rlimit)) return true;
+                nAddedLits += rsize;
+            }
+        }
+    }
+    if (v.o.ve_lbound_en) {
+        int before = 0;
+        sg_count_lits_before(v, me, before);
+        sg_count_lits_before(v, other, before);
+        if (nAddedLits > before) return true;
+    }
+    return false;
+}
+
+/* countResolvents for the 1xm case (simplify.hpp:330-353): only the size bound; TRUE = ok */
+SG_HDN inline bool sg_count_simple(const SgView &v, uint32_t x, uint32_t me, uint32_t other, int &nAddedCls, int &nAddedLits)
+{
+    const int rlimit = v.o.ve_clause_max;
+    const int nme = (int)v.ot_len[me], noth = (int)v.ot_len[other];
+    const uint32_t *dm = sg_list(v, me), *dt = sg_list(v, other);
+    for (int i = 0; i < nme; ++i) {
+        const sg_u4 hi = v.hdr[dm[i]];
+        if (hi.z & SG_ST_MASK) continue;
+        for (int j = 0; j < noth; ++j) {
+            const sg_u4 hj = v.hdr[dt[j]];
+            if (hj.z & SG_ST_MASK) continue;
+            const int rsize = sg_merge_count(x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y);
+            if (rsize > 1) {
+                if (rlimit && rsize > rlimit) return false;
+                nAddedCls++;
+                nAddedLits += rsize;
+            }
+        }
+    }
+    return true;
+}
+
+SG_HD void sg_freeze_binaries(const SgView &v, uint32_t lit)
+{   /* simplify.hpp:262-269 */
+    const int n = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    for (int i = 0; i < n; ++i) if (sg_original(v, d[i]) && SG_SIZE(v, d[i]) == 2) sg_freeze(v, d[i]);
+}
+SG_HD void sg_freeze_all(const SgView &v, uint32_t lit)
+{   /* simplify.hpp:271-278 */
+    const int n = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    for (int i = 0; i < n; ++i) if (sg_original(v, d[i])) sg_freeze(v, d[i]);
+}
+
+/* equivalence / inverter gate (equivalence.hpp:103-161) */
+SG_HDN inline uint32_t sg_find_bn_gate(const SgView &v, uint32_t p, uint32_t n)
+{
+    const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
+    const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
+    if (SG_SIZE(v, dp[0]) > 2 || SG_SIZE(v, dn[0]) > 2) return 0;
+    uint32_t imp = 0;
+    {   /* find_sfanin */
+        int nImps = 0;
+        bool many = false;
+        for (int i = 0; i < np; ++i) {
+            const uint32_t c = dp[i];
+            if (sg_original(v, c) && SG_SIZE(v, c) == 2) {
+                const uint32_t *l = SG_LITS(v, c);
+                imp = SG_FLIP(l[0] ^ l[1] ^ p);
+                sg_melt(v, c);
+                nImps++;
+            }
+            if (nImps > 1) { many = true; break; }
+        }
+        if (many) imp = 0;
+    }
+    if (imp) {
+        uint32_t first = imp, second = n;
+        const uint32_t def = imp;
+        if (second < first) { first = second; second = def; }
+        for (int i = 0; i < nn; ++i) {
+            const uint32_t c = dn[i];
+            if (sg_original(v, c) && SG_SIZE(v, c) == 2) {
+                const uint32_t *l = SG_LITS(v, c);
+                if (l[0] == first && l[1] == second) { sg_melt(v, c); return def; }
+            }
+        }
+    }
+    sg_freeze_binaries(v, p);
+    return 0;
+}
+
+/* AND/OR gate (and.hpp:27-111); `out_c` is this variable's scratch slice */
+SG_HDN inline bool sg_find_ao_gate(const SgView &v, uint32_t dx, uint32_t fx, uint32_t *out_c, int orgCls,
+                                   int &nAddedCls, int &nAddedLits)
+{
+    const int nd = (int)v.ot_len[dx], nf = (int)v.ot_len[fx];
+    const uint32_t *dd = sg_list(v, dx), *df = sg_list(v, fx);
+    if (SG_SIZE(v, dd[0]) > 2 || SG_SIZE(v, df[nf - 1]) < 3) return false;
+    uint32_t sig = 0;
+    int nout = 0;
+    for (int i = 0; i < nd; ++i) {           /* find_fanin */
+        const uint32_t c = dd[i];
+        if (sg_original(v, c) && SG_SIZE(v, c) == 2) {
+            const uint32_t *l = SG_LITS(v, c);
+            const uint32_t imp = SG_FLIP(l[0] ^ l[1] ^ dx);
+            out_c[nout++] = imp;
+            sig |= SG_HASH(imp);
+            sg_melt(v, c);
+        }
+    }
+    if (nout > 1) {
+        out_c[nout++] = fx;
+        sig |= SG_HASH(fx);
+        sg_sort_lits(out_c, nout);
+        const uint32_t x = SG_ABS(dx);
+        for (int i = 0; i < nf; ++i) {
+            const uint32_t c = df[i];
+            if (sg_original(v, c) && SG_SIZE(v, c) == nout && sg_sig_sub(SG_SIG(v, c), sig)) {
+                const uint32_t *l = SG_LITS(v, c);
+                bool eq = true;
+                for (int k = 0; k < nout; ++k) if (l[k] != out_c[k]) { eq = false; break; }
+                if (!eq) continue;
+                sg_melt(v, c);
+                nAddedCls = 0, nAddedLits = 0;
+                if (sg_count_bounded(v, SG_VE_SUBST, x, orgCls, dx, fx, nAddedCls, nAddedLits)) {
+                    sg_freeze(v, c);
+                    break;
+                }
+                return true;
+            }
+        }
+    }
+    sg_freeze_binaries(v, dx);
+    return false;
+}
+
+/* ITE gate (ifthenelse.hpp:26-125) */
+SG_HD void sg_swap(uint32_t &a, uint32_t &b) { const uint32_t t = a; a = b; b = t; }
+
+SG_HDN inline uint32_t sg_fast_equality_check(const SgView &v, uint32_t x, uint32_t y, uint32_t z)
+{   /* returns clause id or 0xFFFFFFFF */
+    if (v.ot_len[y] > v.ot_len[z]) sg_swap(y, z);
+    if (v.ot_len[x] > v.ot_len[y]) sg_swap(x, y);
+    const int n = (int)v.ot_len[x];
+    const uint32_t *d = sg_list(v, x);
+    /* sort3 (simplify.hpp:150-157) */
+    { uint32_t a = y < z ? y : z, b = y < z ? z : y; y = a; z = b; }
+    { uint32_t a = x < z ? x : z, b = x < z ? z : x; x = a; z = b; }
+    { uint32_t a = x < y ? x : y, b = x < y ? y : x; x = a; y = b; }
+    for (int i = 0; i < n; ++i) {
+        const sg_u4 h = v.hdr[d[i]];
+        if (h.z & SG_MOLTEN) continue;
+        if (!(h.z & SG_ST_MASK) && h.y == 3) {
+            const uint32_t *l = v.lits + h.x;
+            if (l[0] == x && l[1] == y && l[2] == z) return d[i];
+        }
+    }
+    return 0xFFFFFFFFu;
+}
+
+SG_HDN inline bool sg_find_ite_gate(const SgView &v, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls, int &nAddedLits)
+{
+    const int nd = (int)v.ot_len[dx];
+    const uint32_t *dd = sg_list(v, dx);
+    if (SG_SIZE(v, dd[nd - 1]) == 2) return false;
+    const uint32_t var = SG_ABS(dx);
+    for (int i = 0; i < nd; ++i) {
+        const uint32_t ci = dd[i];
+        if (!(sg_original(v, ci) && SG_SIZE(v, ci) == 3)) continue;
+        const uint32_t *li = SG_LITS(v, ci);
+        uint32_t xi = li[0], yi = li[1], zi = li[2];
+        if (yi == dx) sg_swap(xi, yi);
+        if (zi == dx) sg_swap(xi, zi);
+        for (int j = i + 1; j < nd; ++j) {
+            const uint32_t cj = dd[j];
+            if (!(sg_original(v, cj) && SG_SIZE(v, cj) == 3)) continue;
+            const uint32_t *lj = SG_LITS(v, cj);
+            uint32_t xj = lj[0], yj = lj[1], zj = lj[2];
+            if (yj == dx) sg_swap(xj, yj);
+            if (zj == dx) sg_swap(xj, zj);
+            if (SG_ABS(yi) == SG_ABS(zj)) sg_swap(yj, zj);
+            if (SG_ABS(zi) == SG_ABS(zj)) continue;
+            if (yi != SG_FLIP(yj)) continue;
+            const uint32_t d1 = sg_fast_equality_check(v, fx, yi, SG_FLIP(zi));
+            if (d1 == 0xFFFFFFFFu) continue;
+            const uint32_t d2 = sg_fast_equality_check(v, fx, yj, SG_FLIP(zj));
+            if (d2 == 0xFFFFFFFFu) continue;
+            sg_melt(v, ci), sg_melt(v, cj), sg_melt(v, d1), sg_melt(v, d2);
+            nAddedCls = 0, nAddedLits = 0;
+            if (sg_count_bounded(v, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
+                sg_freeze(v, ci), sg_freeze(v, cj), sg_freeze(v, d1), sg_freeze(v, d2);
+                return false;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+/* XOR gate (xor.hpp:26-181) */
+SG_HD void sg_freeze_arities(const SgView &v, uint32_t a, uint32_t b)
+{
+    for (int s = 0; s < 2; ++s) {
+        const uint32_t lit = s ? b : a;
+        const int n = (int)v.ot_len[lit];
+        const uint32_t *d = sg_list(v, lit);
+        for (int i = 0; i < n; ++i) if (SG_SIZE(v, d[i]) > 2 && sg_molten(v, d[i])) sg_freeze(v, d[i]);
+    }
+}
+
+SG_HDN inline bool sg_make_arity(const SgView &v, uint32_t &parity, uint32_t *literals, int size)
+{
+    const uint32_t oldparity = parity;
+    do { ++parity; } while (
+#if defined(__CUDA_ARCH__)
+        __popc(parity) & 1
+#else
+        __builtin_parity(parity)
+#endif
+    );
+    for (int k = 0; k < size; ++k) {
+        const uint32_t bit = 1u << k;
+        if ((parity & bit) != (oldparity & bit)) literals[k] = SG_FLIP(literals[k]);
+    }
+    uint32_t best = literals[0];
+    int minsize = (int)v.ot_len[best];
+    for (int k = 1; k < size; ++k) {
+        const int lsize = (int)v.ot_len[literals[k]];
+        if (lsize < minsize) { minsize = lsize; best = literals[k]; }
+    }
+    const int n = (int)v.ot_len[best];
+    const uint32_t *d = sg_list(v, best);
+    for (int i = 0; i < n; ++i) {
+        const sg_u4 h = v.hdr[d[i]];
+        if (!(h.z & SG_ST_MASK) && (int)h.y == size) {
+            const uint32_t *l = v.lits + h.x;
+            bool all = true;
+            for (int a = 0; a < size && all; ++a) {     /* checkArity (xor.hpp:53-68) */
+                bool found = false;
+                for (int b = 0; b < size; ++b) if (l[a] == literals[b]) { found = true; break; }
+                all = found;
+            }
+            if (all) { sg_melt(v, d[i]); return true; }
+        }
+    }
+    return false;
+}
+
+SG_HDN inline bool sg_find_xor_gate(const SgView &v, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls, int &nAddedLits)
+{
+    const int nd = (int)v.ot_len[dx], nf = (int)v.ot_len[fx];
+    const uint32_t *dd = sg_list(v, dx), *df = sg_list(v, fx);
+    if (SG_SIZE(v, dd[nd - 1]) == 2 || SG_SIZE(v, df[nf - 1]) == 2) return false;
+    const int maxarity = v.o.xor_max_arity;
+    int arity = SG_SIZE(v, dd[0]) - 1;
+    if (arity > maxarity) return false;
+    const uint32_t var = SG_ABS(dx);
+    uint32_t out_c[32];
+    for (int i = 0; i < nd; ++i) {
+        const uint32_t ci = dd[i];
+        if (!sg_original(v, ci)) continue;
+        const int size = SG_SIZE(v, ci);
+        arity = size - 1;
+        if (size < 3 || arity > maxarity || size > 32) continue;
+        const uint32_t *l = SG_LITS(v, ci);
+        for (int k = 0; k < size; ++k) out_c[k] = l[k];
+        uint32_t parity = 0;
+        int itargets = 1 << arity;
+        while (--itargets && sg_make_arity(v, parity, out_c, size));
+        if (itargets) sg_freeze_arities(v, dx, fx);
+        else {
+            sg_melt(v, ci);
+            nAddedCls = 0, nAddedLits = 0;
+            if (sg_count_bounded(v, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
+                sg_freeze_arities(v, dx, fx);
+                break;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+/* function-table gate (function.hpp:128-261), evaluated one 64-bit table word at a time */
+SG_HD unsigned long long sg_fun_col(int mvar, bool sign, uint32_t w)
+{   /* clause2fun (function.hpp:71-93) */
+    if (mvar < 6) {
+        const unsigned long long magic[6] = {
+            0xaaaaaaaaaaaaaaaaull, 0xccccccccccccccccull, 0xf0f0f0f0f0f0f0f0ull,
+            0xff00ff00ff00ff00ull, 0xffff0000ffff0000ull, 0xffffffff00000000ull };
+        const unsigned long long val = magic[mvar];
+        return sign ? ~val : val;
+    }
+    const unsigned long long base = sign ? ~0ull : 0ull;
+    return ((w >> (mvar - 6)) & 1u) ? ~base : base;
+}
+SG_HD unsigned long long sg_fun_clause_word(const SgView &v, uint32_t c, uint32_t lit, uint32_t w)
+{
+    const uint32_t *l = SG_LITS(v, c);
+    const int size = SG_SIZE(v, c);
+    unsigned long long f = 0;
+    for (int k = 0; k < size; ++k) {
+        const uint32_t other = l[k];
+        if (other == lit) continue;
+        f |= sg_fun_col((int)v.marks[SG_ABS(other)], SG_SIGN(other) != 0, w);
+    }
+    return f;
+}
+/* word w of buildfuntab(lit) restricted to the first `upto` list entries (function.hpp:128-196) */
+SG_HD unsigned long long sg_fun_list_word(const SgView &v, uint32_t lit, int upto, uint32_t w, unsigned long long init)
+{
+    const uint32_t *d = sg_list(v, lit);
+    unsigned long long f = init;
+    for (int i = 0; i < upto; ++i) {
+        if (sg_learnt(v, d[i])) continue;
+        f &= sg_fun_clause_word(v, d[i], lit, w);
+    }
+    return f;
+}
+SG_HD bool sg_fun_in_core(const SgView &v, uint32_t lit)
+{   /* buildfuntab bails out on the first literal outside the 12 marked variables (function.hpp:150) */
+    const int n = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    for (int i = 0; i < n; ++i) {
+        if (sg_learnt(v, d[i])) continue;
+        const uint32_t *l = SG_LITS(v, d[i]);
+        const int size = SG_SIZE(v, d[i]);
+        for (int k = 0; k < size; ++k) {
+            if (l[k] == lit) continue;
+            if (v.marks[SG_ABS(l[k])] < 0) return false;
+        }
+    }
+    return true;
+}
+
+SG_HDN inline bool sg_find_fun_gate(const SgView &v, uint32_t p, int orgCls, int &nAddedCls, int &nAddedLits)
+{
+    if (!v.o.ve_fun_en) return false;
+    const uint32_t n = p | 1u;
+    if (!sg_fun_in_core(v, p) || !sg_fun_in_core(v, n)) return false;
+    const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
+    unsigned long long unsat = 0, allzero = 0;
+    for (uint32_t w = 0; w < 64; ++w) {       /* collapsefun (function.hpp:198-209) */
+        const unsigned long long b = sg_fun_list_word(v, p, np, w, ~0ull);
+        const unsigned long long c = sg_fun_list_word(v, n, nn, w, ~0ull);
+        unsat |= (b | c);
+        allzero |= (b & c);
+    }
+    if (!unsat) { sg_set_flag(&v.sc->unsat); return true; }
+    if (allzero) return false;
+    bool core = false;
+    const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
+    for (int i = np - 1; i >= 0; --i) {
+        if (!sg_original(v, dp[i])) continue;
+        bool isfalse = true;
+        for (uint32_t w = 0; w < 64 && isfalse; ++w) {
+            const unsigned long long negw = sg_fun_list_word(v, n, nn, w, ~0ull);
+            if (sg_fun_list_word(v, p, i, w, negw)) isfalse = false;
+        }
+        if (isfalse) { sg_melt(v, dp[i]); core = true; }
+    }
+    for (int i = nn - 1; i >= 0; --i) {
+        if (!sg_original(v, dn[i])) continue;
+        bool isfalse = true;
+        for (uint32_t w = 0; w < 64 && isfalse; ++w)
+            if (sg_fun_list_word(v, n, i, w, ~0ull)) isfalse = false;
+        if (isfalse) { sg_melt(v, dn[i]); core = true; }
+    }
+    nAddedCls = 0, nAddedLits = 0;
+    if (sg_count_bounded(v, SG_VE_CORE, SG_ABS(p), orgCls, p, n, nAddedCls, nAddedLits)) {
+        if (core) { sg_freeze_all(v, p); sg_freeze_all(v, n); }
+        return false;
+    }
+    return true;
+}
+
+/* model words written by toblivion / save_BN_gate for this variable (simplify.hpp:393-423) */
+SG_HD uint32_t sg_model_words(const SgView &v, uint32_t p, int pOrgs, int nOrgs)
+{
+    const uint32_t side = (pOrgs > nOrgs) ? (p | 1u) : p;
+    const int n = (int)v.ot_len[side];
+    const uint32_t *d = sg_list(v, side);
+    uint32_t words = 2;
+    for (int i = 0; i < n; ++i) if (sg_original(v, d[i])) words += (uint32_t)SG_SIZE(v, d[i]) + 1u;
+    return words;
+}
+
+SG_HDN inline void sg_ve_count_item(const SgView &v, uint32_t eidx)
+{
+    const uint32_t var = v.elected[eidx];
+    const uint32_t p = 2 * var, n = p | 1u;
+    const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
+    const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
+    int pOrgs = 0, nOrgs = 0, nAddedCls = 0, nAddedLits = 0;
+    if (v.o.firstcall) { pOrgs = np; nOrgs = nn; }
+    else {
+        for (int i = 0; i < np; ++i) if (sg_original(v, dp[i])) pOrgs++;
+        for (int i = 0; i < nn; ++i) if (sg_original(v, dn[i])) nOrgs++;
+    }
+    uint32_t type = SG_VE_NONE, aux = 0;
+    uint32_t def;
+    if (!pOrgs || !nOrgs) {
+        type = SG_VE_PURE;
+        sg_atomic_add64(&v.sc->pures, 1);
+    } else if ((def = sg_find_bn_gate(v, p, n)) != 0) {
+        type = SG_VE_INVERTER;
+        aux = def;
+        sg_atomic_add64(&v.sc->inverters, 1);
+    } else if ((pOrgs == 1 || nOrgs == 1) && sg_count_simple(v, var, p, n, nAddedCls, nAddedLits)) {
+        type = SG_VE_RESOLVE;
+        sg_atomic_add64(&v.sc->resolutions, 1);
+    } else {
+        nAddedCls = 0, nAddedLits = 0;
+        const int orgCls = pOrgs + nOrgs;
+        uint32_t *out_c = v.scratch + v.scr_off[eidx];
+        if (orgCls > 2) {
+            if (sg_find_ao_gate(v, n, p, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            else if (!nAddedCls && sg_find_ao_gate(v, p, n, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            if (type) sg_atomic_add64(&v.sc->andors, 1);
+        }
+        if (!type && orgCls > 3) {
+            if (sg_find_ite_gate(v, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->ites, 1); }
+            else if (!nAddedCls && sg_find_ite_gate(v, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->ites, 1); }
+            else if (sg_find_xor_gate(v, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->xors, 1); }
+            else if (!nAddedCls && sg_find_xor_gate(v, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->xors, 1); }
+        }
+        if (!type && orgCls > 2 && sg_find_fun_gate(v, p, orgCls, nAddedCls, nAddedLits)) {
+            if (*(volatile uint32_t *)&v.sc->unsat) { type = SG_VE_NONE; nAddedCls = 0; nAddedLits = 0; }
+            else { type = SG_VE_CORE; sg_atomic_add64(&v.sc->funs, 1); }
+        } else if (!type && !nAddedCls) {
+            if (!sg_count_bounded(v, SG_VE_RESOLVE, var, orgCls, p, n, nAddedCls, nAddedLits)) {
+                type = SG_VE_RESOLVE;
+                sg_atomic_add64(&v.sc->resolutions, 1);
+            }
+        }
+    }
+    uint32_t ncls = 0, nlits = 0, nmodel = 0;
+    if (type != SG_VE_NONE) {
+        nmodel = sg_model_words(v, p, pOrgs, nOrgs);
+        if (type == SG_VE_RESOLVE || type == SG_VE_SUBST || type == SG_VE_CORE) { ncls = (uint32_t)nAddedCls; nlits = (uint32_t)nAddedLits; }
+        aux |= 0;
+    }
+    v.ve_type[eidx] = type | ((uint32_t)(pOrgs > nOrgs) << 8);
+    v.ve_aux[eidx] = aux;
+    v.ve_ncls[eidx] = ncls;
+    v.ve_nlits[eidx] = nlits;
+    v.ve_nmodel[eidx] = nmodel;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* BVE: emission (bounded.cpp:187-307), model records (simplify.hpp:393-423, model.hpp:65-101)  */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD void sg_save_clause(const SgView &v, uint32_t c, uint32_t witlit, unsigned long long &mpos)
+{   /* model.hpp:86-101 */
+    const uint32_t *l = SG_LITS(v, c);
+    const int size = SG_SIZE(v, c);
+    const unsigned long long last = mpos;
+    int pos = -1;
+    for (int i = 0; i < size; ++i) {
+        const uint32_t lit = l[i];
+        v.model[mpos++] = (v.vorg[SG_ABS(lit)] << 1) | SG_SIGN(lit);
+        if (lit == witlit) pos = i;
+    }
+    if (pos > 0) { const uint32_t t = v.model[last + pos]; v.model[last + pos] = v.model[last]; v.model[last] = t; }
+    v.model[mpos++] = (uint32_t)size;
+}
+SG_HD void sg_save_witness(const SgView &v, uint32_t lit, unsigned long long &mpos)
+{   /* model.hpp:72-76 */
+    v.model[mpos++] = (v.vorg[SG_ABS(lit)] << 1) | SG_SIGN(lit);
+    v.model[mpos++] = 1;
+}
+
+/* substitute_single on one clause (equivalence.hpp:27-56): returns the unit or 0 */
+SG_HD uint32_t sg_substitute_clause(const SgView &v, uint32_t c, uint32_t dx, uint32_t def)
+{
+    uint32_t *l = SG_LITS(v, c);
+    const int size = SG_SIZE(v, c);
+    int j = 0;
+    for (int i = 0; i < size; ++i) {
+        const uint32_t lit = l[i];
+        if (lit == dx) l[j++] = def;
+        else if (lit != def) l[j++] = lit;
+    }
+    v.hdr[c].y = (uint32_t)j;
+    if (j == 1) return l[0];
+    sg_sort_lits(l, j);
+    uint32_t sig = 0;
+    for (int i = 0; i < j; ++i) sig |= SG_HASH(l[i]);
+    v.hdr[c].w = sig;
+    return 0;
+}
+
+SG_HD bool sg_clause_has(const SgView &v, uint32_t c, uint32_t lit)
+{   /* SCLAUSE::has (sclause.hpp:165-184): membership in a sorted clause */
+    const uint32_t *l = SG_LITS(v, c);
+    const int size = SG_SIZE(v, c);
+    for (int i = 0; i < size; ++i) if (l[i] == lit) return true;
+    return false;
+}
+
+SG_HDN inline void sg_ve_emit_item(const SgView &v, uint32_t eidx)
+{
+    const uint32_t tw = v.ve_type[eidx];
+    const uint32_t type = tw & 0xffu;
+    if (type == SG_VE_NONE) return;
+    const bool save_neg = (tw >> 8) & 1u;               /* pOrgs > nOrgs */
+    const uint32_t var = v.elected[eidx];
+    const uint32_t p = 2 * var, n = p | 1u;
+    const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
+    const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
+    unsigned long long mpos = v.model_base + v.ve_mod_off[eidx];
+    uint32_t seq = 0;
+
+    if (type == SG_VE_INVERTER) {
+        /* save_BN_gate (equivalence.hpp:163-183) */
+        if (save_neg) {
+            for (int i = 0; i < nn; ++i) if (sg_original(v, dn[i])) sg_save_clause(v, dn[i], n, mpos);
+            sg_save_witness(v, p, mpos);
+        } else {
+            for (int i = 0; i < np; ++i) if (sg_original(v, dp[i])) sg_save_clause(v, dp[i], p, mpos);
+            sg_save_witness(v, n, mpos);
+        }
+        /* substitute_single (equivalence.hpp:58-101) */
+        const uint32_t def = v.ve_aux[eidx], def_f = SG_FLIP(def);
+        for (int i = 0; i < nn; ++i) {
+            const uint32_t c = dn[i];
+            const uint32_t w0 = SG_W0(v, c);
+            if ((w0 & SG_LEARNT) || (w0 & SG_MOLTEN) || sg_clause_has(v, c, def)) sg_mark_deleted(v, c);
+            else if (!(w0 & SG_ST_MASK)) {
+                const uint32_t unit = sg_substitute_clause(v, c, n, def_f);
+                if (unit) sg_push_unit(v, eidx, seq, unit);
+            }
+        }
+        for (int i = 0; i < np; ++i) {
+            const uint32_t c = dp[i];
+            const uint32_t w0 = SG_W0(v, c);
+            if ((w0 & SG_LEARNT) || (w0 & SG_MOLTEN) || sg_clause_has(v, c, def_f)) sg_mark_deleted(v, c);
+            else if (!(w0 & SG_ST_MASK)) {
+                const uint32_t unit = sg_substitute_clause(v, c, p, def);
+                if (unit) sg_push_unit(v, eidx, seq, unit);
+            }
+        }
+    } else {
+        if (type != SG_VE_PURE && v.ve_ncls[eidx]) {
+            /* resolve / substitute / resolveCore (bounded.cpp:187-277): outer loop = shorter list */
+            uint32_t dx = p, fx = n;
+            if (v.ot_len[dx] > v.ot_len[fx]) { dx = n; fx = p; }
+            const int nme = (int)v.ot_len[dx], noth = (int)v.ot_len[fx];
+            const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
+            uint32_t cid = v.n_cls + v.ve_cls_off[eidx];
+            uint32_t off = v.pool_used + v.ve_lit_off[eidx];
+            const uint32_t cid_end = cid + v.ve_ncls[eidx];
+            for (int i = 0; i < nme; ++i) {
+                const sg_u4 hi = v.hdr[dm[i]];
+                if (hi.z & SG_ST_MASK) continue;
+                const bool a = (hi.z & SG_MOLTEN) != 0;
+                for (int j = 0; j < noth; ++j) {
+                    const sg_u4 hj = v.hdr[dt[j]];
+                    if (hj.z & SG_ST_MASK) continue;
+                    const bool b = (hj.z & SG_MOLTEN) != 0;
+                    if (!sg_pair_ok((int)type, a, b)) continue;
+                    /* a unit resolvent is never counted (simplify.hpp:341,366), so size it first */
+                    const int rsize = sg_merge_count(var, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y);
+                    if (rsize > 1 && cid < cid_end) {
+                        uint32_t sig;
+                        const int sz = sg_merge_emit(var, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y, v.lits + off, &sig);
+                        sg_u4 h; h.x = off; h.y = (uint32_t)sz; h.z = SG_ADDED; h.w = sig;   /* addResolvent, bounded.cpp:296-306 */
+                        v.hdr[cid] = h;
+                        cid++; off += (uint32_t)sz;
+                    } else if (rsize == 1) {
+                        uint32_t tmp[2], sig;
+                        const uint32_t *a1 = v.lits + hi.x, *a2 = v.lits + hj.x;
+                        /* at most one literal survives: find it without touching the pool */
+                        (void)sig; tmp[0] = 0;
+                        for (int k = 0; k < (int)hi.y; ++k) if (SG_ABS(a1[k]) != var) tmp[0] = a1[k];
+                        for (int k = 0; k < (int)hj.y; ++k) if (SG_ABS(a2[k]) != var) tmp[0] = a2[k];
+                        if (tmp[0]) sg_push_unit(v, eidx, seq, tmp[0]);
+                    }
+                }
+            }
+        }
+        /* toblivion (simplify.hpp:393-423) */
+        if (save_neg) {
+            for (int i = 0; i < nn; ++i) { if (sg_original(v, dn[i])) sg_save_clause(v, dn[i], n, mpos); sg_mark_deleted(v, dn[i]); }
+            sg_save_witness(v, p, mpos);
+            for (int i = 0; i < np; ++i) sg_mark_deleted(v, dp[i]);
+        } else {
+            for (int i = 0; i < np; ++i) { if (sg_original(v, dp[i])) sg_save_clause(v, dp[i], p, mpos); sg_mark_deleted(v, dp[i]); }
+            sg_save_witness(v, n, mpos);
+            for (int i = 0; i < nn; ++i) sg_mark_deleted(v, dn[i]);
+        }
+        v.ot_len[p] = 0;
+        v.ot_len[n] = 0;
+    }
+    /* markEliminated (solve.hpp:491-498) */
+    v.state[var] = (uint8_t)SG_MELTED_M;
+    sg_atomic_sub(&v.sc->unassigned, 1u);
+}
+
+#endif /* SIGMA_ITEMS_CUH */

@@ -1,0 +1,602 @@
+/* sigma_kernels.cu - the CUDA (sm_100a) implementation of sigma_backend.h.
+ *
+ * Streaming kernels (ingest, histogram, scan, scatter, radix sort, count, compaction, export)
+ * are HBM-bound integer work: coalesced 128-bit header loads, grid sized from the element count,
+ * no tensor cores (nothing here is a contraction).  The irregular stages run one work item per
+ * thread with the bodies of sigma_items.cuh.  Everything is launched on one stream per context.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sigma_backend.h"
+#include "sigma_items.cuh"
+
+namespace {
+
+unsigned long long g_launches = 0;
+char g_err[256] = { 0 };
+
+inline void note_err(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && !g_err[0]) snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define ST(s) ((cudaStream_t)(s))
+#define LAUNCH(kernel, grid, block, stream, ...)                      \
+    do {                                                              \
+        kernel<<<(grid), (block), 0, ST(stream)>>>(__VA_ARGS__);      \
+        g_launches++;                                                 \
+        note_err(#kernel);                                            \
+    } while (0)
+
+constexpr int TPB = 256;
+inline unsigned blocks_for(uint64_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* ingest                                                                                           */
+/* ---------------------------------------------------------------------------------------------- */
+__global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
+                               uint32_t *__restrict__ sizes)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sizes[i] = arena[refs[i] + 2];
+}
+
+__global__ void k_ingest_copy(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
+                              const uint32_t *__restrict__ offs, uint4 *__restrict__ hdr, uint32_t *__restrict__ lits)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r = refs[i];
+    const uint32_t w0 = arena[r], sig = arena[r + 1], size = arena[r + 2], off = offs[i];
+    hdr[i] = make_uint4(off, size, w0, sig);
+    const uint32_t *src = arena + r + 3;
+    uint32_t *dst = lits + off;
+    for (uint32_t k = 0; k < size; ++k) dst[k] = src[k];
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* exclusive scan (reduce-then-scan, 2048 elements per block)                                       */
+/* ---------------------------------------------------------------------------------------------- */
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *total)
+{   /* exclusive scan of one value per thread over a 256-thread block */
+    __shared__ uint32_t warp_sums[TPB / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < TPB / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < TPB / 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += y;
+        }
+        if (lane < TPB / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t base = warp ? warp_sums[warp - 1] : 0;
+    if (total) *total = warp_sums[TPB / 32 - 1];
+    __syncthreads();
+    return base + incl - x;
+}
+
+__global__ void k_scan_reduce(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ partial)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * TPB + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    __shared__ uint32_t tot;
+    (void)block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void k_scan_partials(uint32_t *__restrict__ partial, uint32_t nb, uint32_t *__restrict__ total)
+{   /* one block: exclusive scan of the block sums, in chunks of 256 */
+    __shared__ uint32_t carry, tot;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += TPB) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < nb ? partial[i] : 0;
+        const uint32_t e = block_exclusive_scan(x, &tot);
+        if (i < nb) partial[i] = carry + e;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void k_scan_down(const uint32_t *in, uint32_t *out, uint32_t n, const uint32_t *__restrict__ partial)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t x[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + k;
+        x[k] = i < n ? in[i] : 0;
+        s += x[k];
+    }
+    uint32_t e = block_exclusive_scan(s, nullptr) + partial[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + k;
+        if (i < n) out[i] = e;
+        e += x[k];
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* occurrence table build                                                                           */
+/* ---------------------------------------------------------------------------------------------- */
+__global__ void k_hist(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
+                       uint32_t *__restrict__ counts)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cls) return;
+    const uint4 h = hdr[c];
+    if (h.z & SG_DELETED) return;
+    const uint32_t *l = lits + h.x;
+    for (uint32_t k = 0; k < h.y; ++k) atomicAdd(&counts[l[k]], 1u);
+}
+
+__global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
+                          const uint32_t *__restrict__ ot_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ ot_data)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cls) return;
+    const uint4 h = hdr[c];
+    if (h.z & SG_DELETED) return;
+    const uint32_t *l = lits + h.x;
+    for (uint32_t k = 0; k < h.y; ++k) {
+        const uint32_t lit = l[k];
+        const uint32_t pos = atomicAdd(&cursor[lit], 1u);
+        ot_data[ot_off[lit] + pos] = c;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* variable ordering: scores + stable LSD radix sort (8-bit digits)                                  */
+/* ---------------------------------------------------------------------------------------------- */
+__global__ void k_scores(SgView v)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (x > v.nvars) return;
+    v.scores[x] = v.occ[2 * x] * v.occ[2 * x + 1];
+    v.order[x - 1] = x;
+}
+
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = TPB * RS_ITEMS;
+
+__global__ void k_rs_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t nblocks, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * TPB + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void k_rs_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n, int shift,
+                             uint32_t nblocks, const uint32_t *__restrict__ hist, uint32_t *__restrict__ okeys,
+                             uint32_t *__restrict__ ovals)
+{
+    __shared__ uint32_t base[256];
+    __shared__ uint32_t wcnt[TPB / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    base[threadIdx.x] = hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+    for (int w = 0; w < TPB / 32; ++w) wcnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t tile = (uint64_t)blockIdx.x * RS_TILE;
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint64_t i = tile + (uint64_t)k * TPB + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t key = valid ? keys[i] : 0xFFFFFFFFu;
+        const uint32_t val = valid ? vals[i] : 0;
+        const uint32_t d = valid ? ((key >> shift) & 255u) : 256u;   /* 256 = no digit */
+        const uint32_t mask = __match_any_sync(0xffffffffu, d);
+        const uint32_t before = __popc(mask & ((1u << lane) - 1u));
+        if (valid && before == 0) wcnt[warp][d] = __popc(mask);
+        __syncthreads();
+        if (valid) {
+            uint32_t off = base[d] + before;
+            for (int w = 0; w < warp; ++w) off += wcnt[w][d];
+            okeys[off] = key;
+            ovals[off] = val;
+        }
+        __syncthreads();
+        {
+            uint32_t s = 0;
+            for (int w = 0; w < TPB / 32; ++w) { s += wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = 0; }
+            base[threadIdx.x] += s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_rank(SgView v)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < v.nvars) v.rank[v.order[r]] = r;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* election                                                                                         */
+/* ---------------------------------------------------------------------------------------------- */
+__global__ void k_elect_init(SgView v, uint32_t *__restrict__ wl)
+{
+    const uint32_t var = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (var > v.nvars) return;
+    if (v.estat[var] != SG_E_UNDECIDED) return;
+    if (v.rank[var] > v.sc->brk_rank) { v.estat[var] = SG_E_SKIP; return; }
+    wl[atomicAdd(&v.sc->wl_count[0], 1u)] = var;
+}
+
+__global__ void k_elect_round(SgView v, const uint32_t *__restrict__ wl_in, uint32_t *__restrict__ wl_out, int parity)
+{
+    const uint32_t n = v.sc->wl_count[parity];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t cand = wl_in[i];
+        if (sg_elect_round_item(v, cand)) wl_out[atomicAdd(&v.sc->wl_count[parity ^ 1], 1u)] = cand;
+    }
+}
+
+__global__ void k_acting_flags(SgView v, uint32_t *__restrict__ fa, uint32_t *__restrict__ fe)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= v.nvars) return;
+    const uint8_t s = v.estat[v.order[r]];
+    const bool in = r < v.sc->brk_rank;
+    fa[r] = in && (s == SG_E_BOTH || s == SG_E_PONLY);
+    fe[r] = in && s == SG_E_BOTH;
+}
+
+__global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, const uint32_t *__restrict__ pa,
+                                 const uint32_t *__restrict__ fe, const uint32_t *__restrict__ pe)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= v.nvars) return;
+    const uint32_t var = v.order[r];
+    if (fa[r]) v.acting[pa[r]] = var | (v.estat[var] == SG_E_PONLY ? 0x80000000u : 0u);
+    if (fe[r]) v.elected[pe[r]] = var;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* one item per thread                                                                              */
+/* ---------------------------------------------------------------------------------------------- */
+template <int KIND> __global__ void k_items(SgView v, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (KIND == SGK_IDSORT) sg_idsort_item(v, i);
+    else if (KIND == SGK_REDUCE) sg_reduce_item(v, i);
+    else if (KIND == SGK_ELECT_PREP) sg_elect_prep_item(v, i + 1);
+    else if (KIND == SGK_SORTOT) sg_sortot_item(v, 2 * v.elected[i >> 1] + (i & 1));
+    else if (KIND == SGK_SCRATCH_LEN) {
+        const uint32_t var = v.elected[i];
+        const uint32_t a = v.ot_len[2 * var], b = v.ot_len[2 * var + 1];
+        v.scr_off[i] = (a > b ? a : b) + 2;
+    }
+    else if (KIND == SGK_SUB) sg_sub_item(v, i);
+    else if (KIND == SGK_VE_COUNT) sg_ve_count_item(v, i);
+    else if (KIND == SGK_VE_EMIT) sg_ve_emit_item(v, i);
+}
+
+__global__ void k_serial(SgView v, int kind, uint32_t arg)
+{
+    if (kind == SGS_PROP) sg_prop_serial(v);
+    else if (kind == SGS_MARKS) sg_marks_serial(v, arg);
+    else if (kind == SGS_APPLY_UNITS) sg_apply_units_serial(v, arg);
+}
+
+__global__ void k_sort_units_small(SgView v, uint32_t n)
+{   /* one thread: insertion sort by (eidx, seq); n is tiny in practice */
+    for (uint32_t i = 1; i < n; ++i) {
+        const SgUnit t = v.ubuf[i];
+        uint32_t j = i;
+        while (j > 0 && (v.ubuf[j - 1].eidx > t.eidx || (v.ubuf[j - 1].eidx == t.eidx && v.ubuf[j - 1].seq > t.seq))) {
+            v.ubuf[j] = v.ubuf[j - 1];
+            --j;
+        }
+        v.ubuf[j] = t;
+    }
+}
+__global__ void k_units_keys(SgView v, uint32_t n, uint32_t *keys, uint32_t *idx, int which)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = which ? idx[i] : i;
+    keys[i] = which ? v.ubuf[src].eidx : v.ubuf[src].seq;
+    if (!which) idx[i] = i;
+}
+__global__ void k_units_gather(SgView v, uint32_t n, const uint32_t *idx, SgUnit *tmp)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tmp[i] = v.ubuf[idx[i]];
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* counts, compaction, export                                                                       */
+/* ---------------------------------------------------------------------------------------------- */
+__global__ void k_zero_live(SgView v) { v.sc->live_cls = 0; v.sc->live_lits = 0; }
+
+__global__ void k_count_live(SgView v)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nc = 0, nl = 0;
+    if (c < v.n_cls) {
+        const uint4 h = v.hdr[c];
+        if (!(h.z & SG_DELETED)) { nc = 1; nl = h.y; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nc += __shfl_down_sync(0xffffffffu, nc, d);
+        nl += __shfl_down_sync(0xffffffffu, nl, d);
+    }
+    __shared__ uint32_t sc_[TPB / 32], sl_[TPB / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sc_[warp] = nc; sl_[warp] = nl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0; unsigned long long b = 0;
+        for (int w = 0; w < TPB / 32; ++w) { a += sc_[w]; b += sl_[w]; }
+        if (a) { atomicAdd(&v.sc->live_cls, a); atomicAdd(&v.sc->live_lits, b); }
+    }
+}
+
+__global__ void k_zero_u32(uint32_t *p) { *p = 0; }
+__global__ void k_count_melted(SgView v, uint32_t *out)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const bool m = x <= v.nvars && (v.state[x] & SG_MELTED_M);
+    const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, m));
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+__global__ void k_live_flags(SgView v, uint32_t *__restrict__ flags, uint32_t *__restrict__ sizes)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.n_cls) return;
+    const uint4 h = v.hdr[c];
+    const bool live = !(h.z & SG_DELETED);
+    flags[c] = live;
+    sizes[c] = live ? h.y : 0;
+}
+
+__global__ void k_compact_move(SgView v, const uint32_t *__restrict__ newid, const uint32_t *__restrict__ newoff,
+                               uint4 *__restrict__ hdr2, uint32_t *__restrict__ lits2)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.n_cls) return;
+    uint4 h = v.hdr[c];
+    if (h.z & SG_DELETED) return;
+    const uint32_t *src = v.lits + h.x;
+    h.x = newoff[c];
+    hdr2[newid[c]] = h;
+    uint32_t *dst = lits2 + h.x;
+    for (uint32_t k = 0; k < h.y; ++k) dst[k] = src[k];
+}
+
+__global__ void k_export(SgView v, const uint32_t *__restrict__ newid, const uint32_t *__restrict__ newoff,
+                         uint32_t *__restrict__ arena, unsigned long long *__restrict__ refs)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.n_cls) return;
+    const uint4 h = v.hdr[c];
+    if (h.z & SG_DELETED) return;
+    const unsigned long long r = 3ull * newid[c] + newoff[c];
+    refs[newid[c]] = r;
+    arena[r] = h.z; arena[r + 1] = h.w; arena[r + 2] = h.y;
+    const uint32_t *src = v.lits + h.x;
+    uint32_t *dst = arena + r + 3;
+    for (uint32_t k = 0; k < h.y; ++k) dst[k] = src[k];
+}
+
+} // namespace
+
+/* ================================================================================================ */
+/* host side of the launch layer                                                                     */
+/* ================================================================================================ */
+int be_init(int device, void **stream_out, char *err, size_t errlen)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(err, errlen, "no CUDA device: %s (libsigma_b200 has no CPU fallback)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return 1;
+    }
+    if (device < 0 || device >= n) { snprintf(err, errlen, "device %d out of range (%d devices)", device, n); return 1; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { snprintf(err, errlen, "cudaSetDevice: %s", cudaGetErrorString(e)); return 1; }
+    cudaStream_t s;
+    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) { snprintf(err, errlen, "cudaStreamCreate: %s", cudaGetErrorString(e)); return 1; }
+    *stream_out = (void *)s;
+    g_err[0] = 0;
+    return 0;
+}
+void be_shutdown(void *s) { if (s) cudaStreamDestroy(ST(s)); }
+void *be_malloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+void be_free(void *p) { if (p) cudaFree(p); }
+void *be_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+void be_host_free(void *p) { if (p) cudaFreeHost(p); }
+int be_h2d(void *s, void *d, const void *h, size_t n) { if (n) cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ST(s)); note_err("h2d"); return 0; }
+int be_d2h(void *s, void *h, const void *d, size_t n) { if (n) cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, ST(s)); note_err("d2h"); return 0; }
+int be_d2d(void *s, void *d, const void *src, size_t n) { if (n) cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, ST(s)); note_err("d2d"); return 0; }
+int be_memset(void *s, void *d, int b, size_t n) { if (n) cudaMemsetAsync(d, b, n, ST(s)); note_err("memset"); return 0; }
+int be_sync(void *s, char *err, size_t errlen)
+{
+    cudaError_t e = cudaStreamSynchronize(ST(s));
+    if (e != cudaSuccess && !g_err[0]) snprintf(g_err, sizeof g_err, "stream sync: %s", cudaGetErrorString(e));
+    if (g_err[0]) { snprintf(err, errlen, "%s", g_err); return 1; }
+    return 0;
+}
+void *be_event_create(void) { cudaEvent_t e; cudaEventCreate(&e); return (void *)e; }
+void be_event_destroy(void *e) { cudaEventDestroy((cudaEvent_t)e); }
+void be_event_record(void *s, void *e) { cudaEventRecord((cudaEvent_t)e, ST(s)); }
+float be_event_ms(void *a, void *b) { float ms = 0; if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) { (void)cudaGetLastError(); ms = 0; } return ms; }
+uint64_t be_launch_count(void) { return g_launches; }
+
+void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
+{
+    if (n) LAUNCH(k_ingest_sizes, blocks_for(n), TPB, s, arena, refs, n, sizes);
+}
+void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs, sg_u4 *hdr, uint32_t *lits)
+{
+    if (n) LAUNCH(k_ingest_copy, blocks_for(n), TPB, s, arena, refs, n, offs, hdr, lits);
+}
+
+size_t be_scan_tmp_words(uint32_t n) { return (size_t)(n / SCAN_TILE) + 2; }
+void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp)
+{
+    if (!n) { if (total) LAUNCH(k_zero_u32, 1, 1, s, total); return; }
+    const uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    LAUNCH(k_scan_reduce, nb, TPB, s, in, n, tmp);
+    LAUNCH(k_scan_partials, 1, TPB, s, tmp, nb, total);
+    LAUNCH(k_scan_down, nb, TPB, s, in, out, n, tmp);
+}
+
+void be_hist(void *s, const SgView &v, uint32_t *counts)
+{
+    if (v.n_cls) LAUNCH(k_hist, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, counts);
+}
+void be_scatter(void *s, const SgView &v, uint32_t *cursor)
+{
+    if (v.n_cls) LAUNCH(k_scatter, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, v.ot_off, cursor, v.ot_data);
+}
+void be_scores(void *s, const SgView &v) { if (v.nvars) LAUNCH(k_scores, blocks_for(v.nvars), TPB, s, v); }
+
+size_t be_sort_tmp_words(uint32_t n)
+{
+    const size_t nb = ((size_t)n + RS_TILE - 1) / RS_TILE;
+    return 256 * nb + be_scan_tmp_words((uint32_t)(256 * nb)) + 16;
+}
+void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t *tmpk, uint32_t *tmpv, uint32_t *tmp, uint32_t key_bits)
+{
+    if (n < 2) return;
+    const uint32_t nb = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t *hist = tmp, *scantmp = tmp + 256ull * nb;
+    uint32_t *ik = keys, *iv = vals, *ok = tmpk, *ov = tmpv;
+    int passes = 0;
+    for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+        LAUNCH(k_rs_hist, nb, TPB, s, ik, n, (int)shift, nb, hist);
+        be_scan_u32(s, hist, hist, 256 * nb, nullptr, scantmp);
+        LAUNCH(k_rs_scatter, nb, TPB, s, ik, iv, n, (int)shift, nb, hist, ok, ov);
+        uint32_t *t = ik; ik = ok; ok = t;
+        t = iv; iv = ov; ov = t;
+        passes++;
+    }
+    if (passes & 1) {
+        be_d2d(s, keys, ik, (size_t)n * 4);
+        be_d2d(s, vals, iv, (size_t)n * 4);
+    }
+}
+void be_rank(void *s, const SgView &v) { if (v.nvars) LAUNCH(k_rank, blocks_for(v.nvars), TPB, s, v); }
+
+void be_elect_init(void *s, const SgView &v, uint32_t *wl) { if (v.nvars) LAUNCH(k_elect_init, blocks_for(v.nvars), TPB, s, v, wl); }
+void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity)
+{
+    cudaMemsetAsync(&v.sc->wl_count[parity ^ 1], 0, sizeof(uint32_t), ST(s));
+    unsigned grid = blocks_for(v.nvars, 128);
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    if (!grid) grid = 1;
+    LAUNCH(k_elect_round, grid, 128, s, v, wl_in, wl_out, parity);
+}
+void be_acting_flags(void *s, const SgView &v, uint32_t *fa, uint32_t *fe) { if (v.nvars) LAUNCH(k_acting_flags, blocks_for(v.nvars), TPB, s, v, fa, fe); }
+void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe)
+{
+    if (v.nvars) LAUNCH(k_acting_scatter, blocks_for(v.nvars), TPB, s, v, fa, pa, fe, pe);
+}
+
+void be_items(void *s, int kind, const SgView &v, uint32_t n)
+{
+    if (!n) return;
+    switch (kind) {
+    case SGK_IDSORT: LAUNCH(k_items<SGK_IDSORT>, blocks_for(n), TPB, s, v, n); break;
+    case SGK_REDUCE: LAUNCH(k_items<SGK_REDUCE>, blocks_for(n), TPB, s, v, n); break;
+    case SGK_ELECT_PREP: LAUNCH(k_items<SGK_ELECT_PREP>, blocks_for(n), TPB, s, v, n); break;
+    case SGK_SORTOT: LAUNCH(k_items<SGK_SORTOT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_SCRATCH_LEN: LAUNCH(k_items<SGK_SCRATCH_LEN>, blocks_for(n), TPB, s, v, n); break;
+    case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_VE_EMIT: LAUNCH(k_items<SGK_VE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
+    default: snprintf(g_err, sizeof g_err, "be_items: bad kind %d", kind);
+    }
+}
+void be_serial(void *s, int kind, const SgView &v, uint32_t arg) { LAUNCH(k_serial, 1, 1, s, v, kind, arg); }
+
+void be_sort_units(void *s, const SgView &v, uint32_t n)
+{
+    if (n < 2) return;
+    if (n <= 2048) { LAUNCH(k_sort_units_small, 1, 1, s, v, n); return; }
+    /* rare: LSD by (seq, eidx) through an index permutation */
+    uint32_t *keys = (uint32_t *)be_malloc(4ull * n), *idx = (uint32_t *)be_malloc(4ull * n);
+    uint32_t *tk = (uint32_t *)be_malloc(4ull * n), *tv = (uint32_t *)be_malloc(4ull * n);
+    uint32_t *tmp = (uint32_t *)be_malloc(4ull * be_sort_tmp_words(n));
+    SgUnit *ut = (SgUnit *)be_malloc(sizeof(SgUnit) * (size_t)n);
+    if (!keys || !idx || !tk || !tv || !tmp || !ut) { snprintf(g_err, sizeof g_err, "be_sort_units: out of memory"); }
+    else {
+        for (int which = 0; which < 2; ++which) {
+            LAUNCH(k_units_keys, blocks_for(n), TPB, s, v, n, keys, idx, which);
+            be_sort_pairs(s, keys, idx, n, tk, tv, tmp, 32);
+        }
+        LAUNCH(k_units_gather, blocks_for(n), TPB, s, v, n, idx, ut);
+        be_d2d(s, v.ubuf, ut, sizeof(SgUnit) * (size_t)n);
+    }
+    cudaStreamSynchronize(ST(s));
+    be_free(keys); be_free(idx); be_free(tk); be_free(tv); be_free(tmp); be_free(ut);
+}
+
+void be_count_live(void *s, const SgView &v)
+{
+    LAUNCH(k_zero_live, 1, 1, s, v);
+    if (v.n_cls) LAUNCH(k_count_live, blocks_for(v.n_cls), TPB, s, v);
+}
+void be_count_melted(void *s, const SgView &v, uint32_t *out)
+{
+    LAUNCH(k_zero_u32, 1, 1, s, out);
+    LAUNCH(k_count_melted, blocks_for((uint64_t)v.nvars + 1), TPB, s, v, out);
+}
+void be_live_flags(void *s, const SgView &v, uint32_t *flags, uint32_t *sizes)
+{
+    if (v.n_cls) LAUNCH(k_live_flags, blocks_for(v.n_cls), TPB, s, v, flags, sizes);
+}
+void be_compact_move(void *s, const SgView &v, const uint32_t *newid, const uint32_t *newoff, sg_u4 *hdr2, uint32_t *lits2)
+{
+    if (v.n_cls) LAUNCH(k_compact_move, blocks_for(v.n_cls), TPB, s, v, newid, newoff, hdr2, lits2);
+}
+void be_export(void *s, const SgView &v, const uint32_t *newid, const uint32_t *newoff, uint32_t *arena, uint64_t *refs)
+{
+    if (v.n_cls) LAUNCH(k_export, blocks_for(v.n_cls), TPB, s, v, newid, newoff, arena, (unsigned long long *)refs);
+}

@@ -1,0 +1,732 @@
+/* sigma_pass.cpp - host driver of the B200 SIGmA pass and its C ABI (include/sigma_b200.h).
+ *
+ * Replaces the phase loop of Solver::simplifying() (reference src/simplify.cpp:180-210): the
+ * loop control below is the reference's (same stop rule, same compaction schedule, same
+ * multiplier), every stage is a group of CUDA kernels launched through sigma_backend.h.
+ * There is no CPU implementation of any stage in this library.
+ */
+#include "../../include/sigma_b200.h"
+#include "sigma_backend.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+namespace {
+
+template <class T> struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;             /* elements */
+    bool ensure(size_t n, void *stream = nullptr, size_t keep = 0) {
+        if (n <= cap) return true;
+        size_t ncap = n + n / 4 + 1024;
+        T *q = (T *)be_malloc(ncap * sizeof(T));
+        if (!q) return false;
+        if (p && keep) be_d2d(stream, q, p, keep * sizeof(T));
+        if (p) { if (stream) { char e[8]; be_sync(stream, e, sizeof e); } be_free(p); }
+        p = q; cap = ncap;
+        return true;
+    }
+    void release() { if (p) be_free(p); p = nullptr; cap = 0; }
+};
+
+struct StageEv { void *a, *b; int stage; };
+
+} // namespace
+
+struct sigma_ctx {
+    int device = 0;
+    void *stream = nullptr;
+    char err[512] = { 0 };
+    const volatile int *interrupt = nullptr;
+    int stop_phase = -1, stop_stage = -1;
+    bool uploaded = false, executed = false;
+
+    sigma_opts opts;
+    /* uploaded input (pristine, device + small host scalars) */
+    uint32_t in_nvars = 0, in_ncls = 0, in_trail = 0, in_propagated = 0, in_unassigned = 0, in_max_frozen = 0,
+             in_max_melted = 0, in_calls = 1;
+    uint64_t in_buckets = 0, in_literals = 0, in_model = 0;
+    bool in_has_ifrozen = false;
+    DBuf<uint32_t> d_arena_in; DBuf<uint64_t> d_refs_in;
+    DBuf<uint8_t> d_state_in; DBuf<int8_t> d_value_in; DBuf<uint32_t> d_trail_in, d_model_in;
+    DBuf<uint32_t> d_vorg; DBuf<uint8_t> d_ifrozen;
+
+    /* working store */
+    DBuf<sg_u4> hdr, hdr2; DBuf<uint32_t> lits, lits2;
+    DBuf<uint32_t> ot_off, ot_len, ot_data, occ, cursor;
+    DBuf<int8_t> value, marks; DBuf<uint8_t> state, estat;
+    DBuf<uint32_t> trail, model;
+    DBuf<uint32_t> scores, order, rank, tmpk, tmpv, sorttmp, scantmp;
+    DBuf<uint32_t> wl0, wl1, flags, pos, acting, elected;
+    DBuf<uint32_t> ve_type, ve_ncls, ve_nlits, ve_nmodel, ve_aux, ve_cls_off, ve_lit_off, ve_mod_off, scr_len, scr_off, scratch;
+    DBuf<SgUnit> ubuf;
+    DBuf<uint32_t> totals;          /* device slots for scan totals */
+    DBuf<SgScalars> sc;
+    DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
+    DBuf<uint32_t> arena_out; DBuf<uint64_t> refs_out;
+    SgScalars hsc;                  /* host mirror */
+    uint32_t *h_totals = nullptr;   /* pinned */
+    SgScalars *h_sc = nullptr;      /* pinned */
+
+    uint32_t nvars = 0, nlit = 0, n_cls = 0, pool_used = 0;
+    uint64_t model_words = 0;
+    /* result */
+    uint32_t out_ncls = 0; uint64_t out_buckets = 0, out_literals = 0;
+    uint32_t out_max_melted = 0;
+    sigma_report rep;
+    std::vector<StageEv> evs;
+    std::vector<void *> evpool;
+    size_t evused = 0;
+    uint64_t launches0 = 0;
+};
+
+namespace {
+
+const char *const kErr[] = { "ok", "formula is UNSATISFIABLE", "interrupted", "out of memory", "CUDA error",
+                             "output buffer too small", "bad argument", "unsupported option combination" };
+
+int fail(sigma_ctx *c, int code, const char *msg)
+{
+    snprintf(c->err, sizeof c->err, "%s", msg);
+    return code;
+}
+
+void *get_event(sigma_ctx *c)
+{
+    if (c->evused == c->evpool.size()) c->evpool.push_back(be_event_create());
+    return c->evpool[c->evused++];
+}
+
+struct Stage {
+    sigma_ctx *c; int stage; void *a; uint64_t l0;
+    Stage(sigma_ctx *ctx, int st, uint64_t bytes = 0) : c(ctx), stage(st) {
+        a = get_event(c);
+        be_event_record(c->stream, a);
+        l0 = be_launch_count();
+        c->rep.stage_bytes[st] += bytes;
+    }
+    ~Stage() {
+        void *b = get_event(c);
+        be_event_record(c->stream, b);
+        c->evs.push_back({ a, b, stage });
+        c->rep.stage_launches[stage] += (uint32_t)(be_launch_count() - l0);
+    }
+};
+
+SgView make_view(sigma_ctx *c)
+{
+    SgView v;
+    memset(&v, 0, sizeof v);
+    v.hdr = c->hdr.p; v.lits = c->lits.p;
+    v.ot_off = c->ot_off.p; v.ot_len = c->ot_len.p; v.ot_data = c->ot_data.p;
+    v.value = c->value.p; v.state = c->state.p; v.marks = c->marks.p;
+    v.ifrozen = c->in_has_ifrozen ? c->d_ifrozen.p : nullptr;
+    v.vorg = c->d_vorg.p; v.trail = c->trail.p; v.model = c->model.p;
+    v.occ = c->occ.p; v.scores = c->scores.p; v.order = c->order.p; v.rank = c->rank.p; v.estat = c->estat.p;
+    v.elected = c->elected.p; v.acting = c->acting.p;
+    v.ve_type = c->ve_type.p; v.ve_ncls = c->ve_ncls.p; v.ve_nlits = c->ve_nlits.p; v.ve_nmodel = c->ve_nmodel.p;
+    v.ve_aux = c->ve_aux.p; v.ve_cls_off = c->ve_cls_off.p; v.ve_lit_off = c->ve_lit_off.p; v.ve_mod_off = c->ve_mod_off.p;
+    v.scr_off = c->scr_off.p; v.scratch = c->scratch.p; v.ubuf = c->ubuf.p; v.ubuf_cap = (uint32_t)c->ubuf.cap;
+    v.sc = c->sc.p;
+    v.nvars = c->nvars; v.nlit = c->nlit; v.n_cls = c->n_cls; v.pool_used = c->pool_used;
+    v.model_base = c->model_words;
+    const sigma_opts &o = c->opts;
+    SgOpts &d = v.o;
+    d.phases = o.phases; d.phase_lits_min = o.phase_lits_min; d.mu_pos = o.mu_pos; d.mu_neg = o.mu_neg;
+    d.lcve_max_occurs = o.lcve_max_occurs; d.lcve_clause_max = o.lcve_clause_max; d.lcve_min_vars = o.lcve_min_vars;
+    d.sub_max_occurs = o.sub_max_occurs; d.sub_clause_max = o.sub_clause_max; d.ve_clause_max = o.ve_clause_max;
+    d.xor_max_arity = o.xor_max_arity; d.bce_max_occurs = o.bce_max_occurs; d.ere_max_occurs = o.ere_max_occurs;
+    d.ere_clause_max = o.ere_clause_max; d.collect_freq = o.collect_freq; d.lbd_tier1 = o.lbd_tier1;
+    d.sub_en = o.sub_en; d.ve_en = o.ve_en; d.ve_plus_en = o.ve_plus_en; d.ve_fun_en = o.ve_fun_en;
+    d.ve_lbound_en = o.ve_lbound_en; d.bce_en = o.bce_en; d.ere_en = o.ere_en; d.ere_extend = o.ere_extend;
+    d.all_en = o.all_en; d.proof_en = o.proof_en;
+    d.firstcall = c->in_calls == 1;
+    return v;
+}
+
+/* device scalars -> host mirror (one small D2H + sync) */
+int pull_scalars(sigma_ctx *c)
+{
+    be_d2h(c->stream, c->h_sc, c->sc.p, sizeof(SgScalars));
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    c->hsc = *c->h_sc;
+    return SIGMA_OK;
+}
+int push_scalars(sigma_ctx *c)
+{
+    *c->h_sc = c->hsc;
+    be_h2d(c->stream, c->sc.p, c->h_sc, sizeof(SgScalars));
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    return SIGMA_OK;
+}
+int pull_totals(sigma_ctx *c, uint32_t n)
+{
+    be_d2h(c->stream, c->h_totals, c->totals.p, n * sizeof(uint32_t));
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    return SIGMA_OK;
+}
+
+#define CK(x) do { int rc_ = (x); if (rc_ != SIGMA_OK) return rc_; } while (0)
+#define NOMEM(x) do { if (!(x)) return fail(c, SIGMA_E_NOMEM, "device allocation failed"); } while (0)
+
+/* ---- ingest: uploaded AoS arena -> device store --------------------------------------------- */
+int stage_ingest(sigma_ctx *c)
+{
+    const uint32_t n = c->in_ncls;
+    const uint64_t L = c->in_buckets - 3ull * n;
+    Stage st(c, SIGMA_T_INGEST, 2 * (4 * L + 12ull * n) + 8ull * n);
+    const size_t cap_cls = (size_t)n + n / 2 + (1u << 16);
+    const size_t cap_lits = (size_t)L + L / 2 + (1u << 18);
+    if (cap_lits >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "literal pool exceeds 32-bit offsets");
+    NOMEM(c->hdr.ensure(cap_cls)); NOMEM(c->lits.ensure(cap_lits));
+    NOMEM(c->c_sizes.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
+    NOMEM(c->scantmp.ensure(be_scan_tmp_words((uint32_t)cap_cls) + be_scan_tmp_words(c->nlit + 1) + 64));
+    be_ingest_sizes(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_sizes.p);
+    be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, nullptr, c->scantmp.p);
+    be_ingest_copy(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_newoff.p, c->hdr.p, c->lits.p);
+    c->n_cls = n;
+    c->pool_used = (uint32_t)L;
+    return SIGMA_OK;
+}
+
+/* ---- createOT (simplify.cpp:39-61) ------------------------------------------------------------ */
+int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
+{
+    const uint32_t nlit = c->nlit;
+    NOMEM(c->ot_data.ensure((size_t)live_lits + 16));
+    SgView v = make_view(c);
+    {
+        Stage st(c, SIGMA_T_OT_HIST, 4 * live_lits + 8ull * c->n_cls + 4ull * nlit);
+        be_memset(c->stream, c->ot_len.p, 0, nlit * sizeof(uint32_t));
+        be_hist(c->stream, v, c->ot_len.p);
+    }
+    {
+        Stage st(c, SIGMA_T_OT_SCAN, 8ull * nlit);
+        be_scan_u32(c->stream, c->ot_len.p, c->ot_off.p, nlit, c->totals.p, c->scantmp.p);
+    }
+    {
+        Stage st(c, SIGMA_T_OT_SCATTER, 8 * live_lits + 8ull * c->n_cls);
+        be_memset(c->stream, c->cursor.p, 0, nlit * sizeof(uint32_t));
+        be_scatter(c->stream, v, c->cursor.p);
+    }
+    {
+        Stage st(c, SIGMA_T_OT_ORDER, 8 * live_lits + 8ull * nlit);
+        be_items(c->stream, SGK_IDSORT, v, nlit);
+    }
+    (void)live_cls;
+    return SIGMA_OK;
+}
+
+/* ---- prop (propelim.cpp:46-81) ---------------------------------------------------------------- */
+int stage_prop(sigma_ctx *c)
+{
+    if (c->hsc.propagated >= c->hsc.n_trail) return SIGMA_OK;
+    {
+        Stage st(c, SIGMA_T_PROP);
+        SgView v = make_view(c);
+        be_serial(c->stream, SGS_PROP, v, 0);
+        if (!c->opts.sub_en) be_items(c->stream, SGK_REDUCE, v, c->nlit);   /* propelim.cpp:79 */
+    }
+    CK(pull_scalars(c));
+    if (c->hsc.unsat) return SIGMA_UNSAT;
+    return SIGMA_OK;
+}
+
+/* ---- LCVE (lcve.cpp:29-119) ------------------------------------------------------------------- */
+int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bool *enough)
+{
+    const uint32_t V = c->nvars, nlit = c->nlit;
+    SgView v = make_view(c);
+    v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
+    v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
+    {
+        Stage st(c, SIGMA_T_VO, 8ull * V + 4 * 16ull * V);
+        if (ot_is_hist) be_d2d(c->stream, c->occ.p, c->ot_len.p, nlit * sizeof(uint32_t));
+        else {
+            be_memset(c->stream, c->occ.p, 0, nlit * sizeof(uint32_t));
+            be_hist(c->stream, v, c->occ.p);                 /* histCNF (histogram.cpp:84-97) */
+        }
+        be_scores(c->stream, v);
+        be_sort_pairs(c->stream, c->scores.p + 1, c->order.p, V, c->tmpk.p, c->tmpv.p, c->sorttmp.p, 32);
+        be_rank(c->stream, v);
+    }
+    uint32_t rounds = 0;
+    {
+        Stage st(c, SIGMA_T_ELECT);
+        c->hsc.brk_rank = 0xFFFFFFFFu; c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
+        c->hsc.n_acting = c->hsc.n_ponly = c->hsc.n_elected = 0;
+        CK(push_scalars(c));
+        be_items(c->stream, SGK_ELECT_PREP, v, V);
+        be_elect_init(c->stream, v, c->wl0.p);
+        int parity = 0;
+        while (true) {
+            for (int k = 0; k < 4; ++k) {
+                be_elect_round(c->stream, v, parity ? c->wl1.p : c->wl0.p, parity ? c->wl0.p : c->wl1.p, parity);
+                parity ^= 1;
+                rounds++;
+            }
+            CK(pull_scalars(c));
+            if (!c->hsc.wl_count[parity]) break;
+            if (rounds > 4u * V + 16) return fail(c, SIGMA_E_CUDA, "election did not converge");
+        }
+        /* acting / elected candidates in election order, cut at the break (lcve.cpp:70,73) */
+        be_acting_flags(c->stream, v, c->flags.p, c->flags.p + V);
+        be_scan_u32(c->stream, c->flags.p, c->pos.p, V, c->totals.p, c->scantmp.p);
+        be_scan_u32(c->stream, c->flags.p + V, c->pos.p + V, V, c->totals.p + 1, c->scantmp.p);
+        be_acting_scatter(c->stream, v, c->flags.p, c->pos.p, c->flags.p + V, c->pos.p + V);
+        CK(pull_totals(c, 2));
+        c->hsc.n_acting = c->h_totals[0]; c->hsc.n_elected = c->h_totals[1];
+        be_serial(c->stream, SGS_MARKS, v, c->hsc.n_acting);
+    }
+    if (phase < 8) { c->rep.elected_per_phase[phase] = c->hsc.n_elected; c->rep.election_rounds[phase] = rounds; }
+    *enough = c->hsc.n_elected >= (uint32_t)c->opts.lcve_min_vars;
+    return SIGMA_OK;
+}
+
+int apply_units(sigma_ctx *c, SgView &v)
+{
+    CK(pull_scalars(c));
+    if (c->hsc.unsat) return SIGMA_UNSAT;
+    const uint32_t n = c->hsc.n_units;
+    if (!n) return SIGMA_OK;
+    if (n > c->ubuf.cap) return fail(c, SIGMA_E_UNSUPPORTED, "unit buffer overflow");
+    be_sort_units(c->stream, v, n);
+    be_serial(c->stream, SGS_APPLY_UNITS, v, n);
+    CK(pull_scalars(c));
+    c->hsc.n_units = 0;
+    CK(push_scalars(c));
+    if (c->hsc.unsat) return SIGMA_UNSAT;
+    return SIGMA_OK;
+}
+
+int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
+{
+    const uint32_t E = c->hsc.n_elected;
+    NOMEM(c->ve_type.ensure(E + 1)); NOMEM(c->ve_ncls.ensure(E + 1)); NOMEM(c->ve_nlits.ensure(E + 1));
+    NOMEM(c->ve_nmodel.ensure(E + 1)); NOMEM(c->ve_aux.ensure(E + 1)); NOMEM(c->ve_cls_off.ensure(E + 1));
+    NOMEM(c->ve_lit_off.ensure(E + 1)); NOMEM(c->ve_mod_off.ensure(E + 1)); NOMEM(c->scr_len.ensure(E + 1));
+    NOMEM(c->scr_off.ensure(E + 1));
+    SgView v = make_view(c);
+    v.n_elected = E;
+    v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
+    v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
+    {
+        Stage st(c, SIGMA_T_SOT);
+        be_items(c->stream, SGK_SORTOT, v, 2 * E);
+    }
+    /* scratch slices + unit buffer sized from the elected lists */
+    v.scr_off = c->scr_len.p;              /* SGK_SCRATCH_LEN writes lengths through scr_off */
+    be_items(c->stream, SGK_SCRATCH_LEN, v, E);
+    be_scan_u32(c->stream, c->scr_len.p, c->scr_off.p, E, c->totals.p, c->scantmp.p);
+    CK(pull_totals(c, 1));
+    const uint32_t scr_total = c->h_totals[0];
+    NOMEM(c->scratch.ensure((size_t)scr_total + 64));
+    NOMEM(c->ubuf.ensure(2ull * scr_total + 4096));
+    v = make_view(c);
+    v.n_elected = E;
+    v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
+    v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
+    if (c->opts.sub_en || c->opts.ve_plus_en) {            /* subsume.cpp:25 */
+        Stage st(c, SIGMA_T_SUB);
+        be_items(c->stream, SGK_SUB, v, E);
+        int rc = apply_units(c, v);
+        if (rc != SIGMA_OK) return rc;
+    }
+    if (c->opts.ve_en) {                                   /* bounded.cpp:29 */
+        Stage st(c, SIGMA_T_VE);
+        be_items(c->stream, SGK_VE_COUNT, v, E);
+        be_scan_u32(c->stream, c->ve_ncls.p, c->ve_cls_off.p, E, c->totals.p + 0, c->scantmp.p);
+        be_scan_u32(c->stream, c->ve_nlits.p, c->ve_lit_off.p, E, c->totals.p + 1, c->scantmp.p);
+        be_scan_u32(c->stream, c->ve_nmodel.p, c->ve_mod_off.p, E, c->totals.p + 2, c->scantmp.p);
+        CK(pull_totals(c, 3));
+        CK(pull_scalars(c));
+        if (c->hsc.unsat) return SIGMA_UNSAT;              /* function-table UNSAT, bounded.cpp:141-145 */
+        const uint32_t add_cls = c->h_totals[0], add_lits = c->h_totals[1], add_model = c->h_totals[2];
+        if ((uint64_t)c->pool_used + add_lits >= 0xFFFFFFF0ull)
+            return fail(c, SIGMA_E_UNSUPPORTED, "literal pool exceeds 32-bit offsets");
+        NOMEM(c->hdr.ensure((size_t)c->n_cls + add_cls, c->stream, c->n_cls));
+        NOMEM(c->lits.ensure((size_t)c->pool_used + add_lits, c->stream, c->pool_used));
+        NOMEM(c->model.ensure((size_t)c->model_words + add_model, c->stream, (size_t)c->model_words));
+        v = make_view(c);
+        v.n_elected = E;
+        be_items(c->stream, SGK_VE_EMIT, v, E);
+        c->n_cls += add_cls;
+        c->pool_used += add_lits;
+        c->model_words += add_model;
+        v = make_view(c);
+        int rc = apply_units(c, v);
+        if (rc != SIGMA_OK) return rc;
+    }
+    return SIGMA_OK;
+}
+
+int stage_count(sigma_ctx *c)
+{
+    {
+        Stage st(c, SIGMA_T_COUNT, 8ull * c->n_cls);
+        SgView v = make_view(c);
+        be_count_live(c->stream, v);
+    }
+    return pull_scalars(c);
+}
+
+/* shrinkSimp (simplify.cpp:235-247) between phases: device store -> compacted device store */
+int stage_compact(sigma_ctx *c)
+{
+    const uint32_t n = c->n_cls;
+    NOMEM(c->c_flags.ensure(n + 1)); NOMEM(c->c_sizes.ensure(n + 1));
+    NOMEM(c->c_newid.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
+    NOMEM(c->scantmp.ensure(be_scan_tmp_words(n) + 64));
+    uint32_t ncls, nlits;
+    {
+        Stage st(c, SIGMA_T_GC);
+        SgView v = make_view(c);
+        be_live_flags(c->stream, v, c->c_flags.p, c->c_sizes.p);
+        be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
+        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, c->totals.p + 1, c->scantmp.p);
+        CK(pull_totals(c, 2));
+        ncls = c->h_totals[0]; nlits = c->h_totals[1];
+        const size_t cap_cls = (size_t)ncls + ncls / 2 + (1u << 16);
+        const size_t cap_lits = (size_t)nlits + nlits / 2 + (1u << 18);
+        NOMEM(c->hdr2.ensure(cap_cls)); NOMEM(c->lits2.ensure(cap_lits));
+        be_compact_move(c->stream, v, c->c_newid.p, c->c_newoff.p, c->hdr2.p, c->lits2.p);
+        c->rep.stage_bytes[SIGMA_T_GC] += 4ull * c->pool_used + 16ull * n + 4ull * nlits + 16ull * ncls;
+    }
+    { DBuf<sg_u4> t = c->hdr; c->hdr = c->hdr2; c->hdr2 = t; }
+    { DBuf<uint32_t> t = c->lits; c->lits = c->lits2; c->lits2 = t; }
+    c->n_cls = ncls;
+    c->pool_used = nlits;
+    return SIGMA_OK;
+}
+
+/* final shrinkSimp fused with the export to the reference's AoS layout */
+int stage_export(sigma_ctx *c)
+{
+    const uint32_t n = c->n_cls;
+    NOMEM(c->c_flags.ensure(n + 1)); NOMEM(c->c_sizes.ensure(n + 1));
+    NOMEM(c->c_newid.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
+    NOMEM(c->scantmp.ensure(be_scan_tmp_words(n) + 64));
+    Stage st(c, SIGMA_T_EXPORT);
+    SgView v = make_view(c);
+    be_live_flags(c->stream, v, c->c_flags.p, c->c_sizes.p);
+    be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
+    be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, c->totals.p + 1, c->scantmp.p);
+    CK(pull_totals(c, 2));
+    const uint32_t ncls = c->h_totals[0], nlits = c->h_totals[1];
+    NOMEM(c->arena_out.ensure(3ull * ncls + nlits + 16)); NOMEM(c->refs_out.ensure((size_t)ncls + 16));
+    be_export(c->stream, v, c->c_newid.p, c->c_newoff.p, c->arena_out.p, c->refs_out.p);
+    c->out_ncls = ncls; c->out_literals = nlits; c->out_buckets = 3ull * ncls + nlits;
+    c->rep.stage_bytes[SIGMA_T_EXPORT] += 4ull * c->pool_used + 16ull * n + 4ull * nlits + 20ull * ncls;
+    return SIGMA_OK;
+}
+
+bool interrupted(sigma_ctx *c) { return c->interrupt && *c->interrupt; }
+bool stop_here(sigma_ctx *c, int phase, int stage) { return c->stop_phase == phase && c->stop_stage == stage; }
+
+int run_phases(sigma_ctx *c)
+{
+    const sigma_opts &o = c->opts;
+    if (o.ere_en || o.bce_en || o.all_en)
+        return fail(c, SIGMA_E_UNSUPPORTED, "ERE/BCE are not built yet: run with -no-redundancy (and without -blocked/-all)");
+    if (o.proof_en) return fail(c, SIGMA_E_UNSUPPORTED, "DRAT proof emission from the device pass is not built");
+    if (o.collect_freq <= 0) return fail(c, SIGMA_E_ARG, "collect_freq must be positive");
+    CK(stage_ingest(c));
+    int phase = 0;
+    uint32_t multiplier = 0;
+    int64_t litsbefore = (int64_t)c->in_literals, diff = INT64_MAX;
+    uint64_t live_lits = c->in_literals;
+    uint32_t live_cls = c->in_ncls;
+    while (litsbefore) {
+        if (interrupted(c)) return SIGMA_INTERRUPTED;
+        const int times = phase + 1;                       /* resizeCNF, solve.hpp:626-630 */
+        if (times > 1 && times != o.phases && (times % o.collect_freq) == 0) CK(stage_compact(c));
+        CK(stage_create_ot(c, live_lits, live_cls));
+        if (stop_here(c, phase, SIGMA_T_OT_ORDER)) return SIGMA_OK;
+        const bool had_units = c->hsc.propagated < c->hsc.n_trail;
+        CK(stage_prop(c));
+        bool enough = false;
+        CK(stage_lcve(c, phase, multiplier, !had_units, &enough));
+        if (stop_here(c, phase, SIGMA_T_ELECT)) return SIGMA_OK;
+        if (!enough) break;
+        if (phase == o.phases || (diff <= o.phase_lits_min && phase > 2)) {
+            /* ERE() would run here (simplify.cpp:188); it still needs sortOT's lists */
+            break;
+        }
+        CK(stage_sub_ve(c, multiplier));
+        if (stop_here(c, phase, SIGMA_T_VE)) return SIGMA_OK;
+        CK(stage_count(c));
+        live_cls = c->hsc.live_cls; live_lits = c->hsc.live_lits;
+        diff = litsbefore - (int64_t)live_lits; litsbefore = (int64_t)live_lits;
+        phase++;
+        multiplier++;
+        multiplier += phase == o.phases;
+    }
+    c->rep.phases_run = phase;
+    CK(stage_prop(c));                                     /* simplify.cpp:204 */
+    if (interrupted(c)) return SIGMA_INTERRUPTED;
+    /* countFinal (solve.hpp:655-660) */
+    {
+        Stage st(c, SIGMA_T_COUNT);
+        SgView v = make_view(c);
+        be_count_melted(c->stream, v, c->totals.p + 3);
+    }
+    CK(stage_export(c));
+    CK(pull_totals(c, 4));
+    c->out_max_melted = c->h_totals[3];
+    CK(pull_scalars(c));
+    return SIGMA_OK;
+}
+
+} // namespace
+
+/* =============================================================================================== */
+extern "C" {
+
+int sigma_create(int device, sigma_ctx **out)
+{
+    if (!out) return SIGMA_E_ARG;
+    sigma_ctx *c = new (std::nothrow) sigma_ctx();
+    if (!c) return SIGMA_E_NOMEM;
+    c->device = device;
+    memset(&c->rep, 0, sizeof c->rep);
+    memset(&c->hsc, 0, sizeof c->hsc);
+    sigma_default_opts(&c->opts);
+    if (be_init(device, &c->stream, c->err, sizeof c->err)) { *out = c; return SIGMA_E_CUDA; }
+    c->h_totals = (uint32_t *)be_host_alloc(64 * sizeof(uint32_t));
+    c->h_sc = (SgScalars *)be_host_alloc(sizeof(SgScalars));
+    if (!c->h_totals || !c->h_sc || !c->totals.ensure(64) || !c->sc.ensure(1)) { *out = c; return fail(c, SIGMA_E_NOMEM, "allocation failed"); }
+    *out = c;
+    return SIGMA_OK;
+}
+
+void sigma_destroy(sigma_ctx *c)
+{
+    if (!c) return;
+    if (c->stream) {
+        char e[64]; be_sync(c->stream, e, sizeof e);
+        c->d_arena_in.release(); c->d_refs_in.release(); c->d_state_in.release(); c->d_value_in.release();
+        c->d_trail_in.release(); c->d_model_in.release(); c->d_vorg.release(); c->d_ifrozen.release();
+        c->hdr.release(); c->hdr2.release(); c->lits.release(); c->lits2.release();
+        c->ot_off.release(); c->ot_len.release(); c->ot_data.release(); c->occ.release(); c->cursor.release();
+        c->value.release(); c->marks.release(); c->state.release(); c->estat.release(); c->trail.release(); c->model.release();
+        c->scores.release(); c->order.release(); c->rank.release(); c->tmpk.release(); c->tmpv.release();
+        c->sorttmp.release(); c->scantmp.release(); c->wl0.release(); c->wl1.release(); c->flags.release(); c->pos.release();
+        c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
+        c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
+        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->totals.release(); c->sc.release();
+        c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
+        c->arena_out.release(); c->refs_out.release();
+        for (void *e2 : c->evpool) be_event_destroy(e2);
+        if (c->h_totals) be_host_free(c->h_totals);
+        if (c->h_sc) be_host_free(c->h_sc);
+        be_shutdown(c->stream);
+    }
+    delete c;
+}
+
+void sigma_default_opts(sigma_opts *o)
+{   /* options.cpp:24-51,146 */
+    memset(o, 0, sizeof *o);
+    o->phases = 5; o->phase_lits_min = 500; o->mu_pos = 32; o->mu_neg = 32;
+    o->lcve_max_occurs = 3000; o->lcve_clause_max = 30000; o->lcve_min_vars = 1;
+    o->sub_max_occurs = 1000; o->sub_clause_max = 100; o->ve_clause_max = 100; o->xor_max_arity = 10;
+    o->bce_max_occurs = 1000; o->ere_max_occurs = 1000; o->ere_clause_max = 200; o->collect_freq = 2; o->lbd_tier1 = 2;
+    o->sub_en = 1; o->ve_en = 1; o->ve_plus_en = 1; o->ve_fun_en = 1; o->ve_lbound_en = 0;
+    o->bce_en = 0; o->ere_en = 1; o->ere_extend = 1; o->all_en = 0; o->proof_en = 0;
+}
+
+const char *sigma_strerror(int code) { return (code >= 0 && code <= 7) ? kErr[code] : "unknown"; }
+const char *sigma_last_error(sigma_ctx *c) { return c ? c->err : "null context"; }
+void sigma_set_interrupt_flag(sigma_ctx *c, const volatile int *flag) { if (c) c->interrupt = flag; }
+void *sigma_host_alloc(uint64_t bytes) { return be_host_alloc((size_t)bytes); }
+void sigma_host_free(void *p) { be_host_free(p); }
+
+int sigma_set_stop(sigma_ctx *c, int phase, int stage)
+{
+    if (!c) return SIGMA_E_ARG;
+    c->stop_phase = phase; c->stop_stage = stage;
+    return SIGMA_OK;
+}
+
+int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
+{
+    if (!c || !in) return SIGMA_E_ARG;
+    if (!c->stream) return fail(c, SIGMA_E_CUDA, c->err[0] ? c->err : "no CUDA device");
+    if (o) c->opts = *o;
+    if (!in->arena || !in->refs || !in->state || !in->value || !in->vorg) return fail(c, SIGMA_E_ARG, "null input array");
+    if (in->n_buckets >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "arena exceeds 32-bit bucket offsets");
+    if (in->n_buckets < 3ull * in->n_clauses) return fail(c, SIGMA_E_ARG, "n_buckets smaller than the clause headers");
+    c->uploaded = c->executed = false;
+    c->evused = 0; c->evs.clear();
+    memset(&c->rep, 0, sizeof c->rep);
+    const uint32_t V = in->nvars, nlit = 2 * V + 2, n = in->n_clauses;
+    c->in_nvars = V; c->in_ncls = n; c->in_buckets = in->n_buckets; c->in_literals = in->n_literals;
+    c->in_trail = in->trail_size; c->in_propagated = in->propagated; c->in_unassigned = in->unassigned;
+    c->in_max_frozen = in->max_frozen; c->in_max_melted = in->max_melted; c->in_calls = in->simplify_calls ? in->simplify_calls : 1;
+    c->in_model = in->model_size; c->in_has_ifrozen = in->ifrozen != nullptr;
+    c->nvars = V; c->nlit = nlit;
+    NOMEM(c->d_arena_in.ensure(in->n_buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)n + 16));
+    NOMEM(c->d_state_in.ensure(V + 1)); NOMEM(c->d_value_in.ensure(nlit)); NOMEM(c->d_trail_in.ensure((size_t)V + 16));
+    NOMEM(c->d_model_in.ensure((size_t)in->model_size + 16)); NOMEM(c->d_vorg.ensure(V + 1));
+    if (in->ifrozen) NOMEM(c->d_ifrozen.ensure(V + 1));
+    /* working arrays sized by the variable count */
+    NOMEM(c->ot_off.ensure(nlit + 1)); NOMEM(c->ot_len.ensure(nlit)); NOMEM(c->occ.ensure(nlit)); NOMEM(c->cursor.ensure(nlit));
+    NOMEM(c->value.ensure(nlit)); NOMEM(c->marks.ensure(V + 1)); NOMEM(c->state.ensure(V + 1)); NOMEM(c->estat.ensure(V + 1));
+    NOMEM(c->trail.ensure((size_t)V + 16));
+    NOMEM(c->scores.ensure(V + 2)); NOMEM(c->order.ensure(V + 1)); NOMEM(c->rank.ensure(V + 1));
+    NOMEM(c->tmpk.ensure(V + 1)); NOMEM(c->tmpv.ensure(V + 1)); NOMEM(c->sorttmp.ensure(be_sort_tmp_words(V) + 64));
+    NOMEM(c->wl0.ensure(V + 1)); NOMEM(c->wl1.ensure(V + 1)); NOMEM(c->flags.ensure(2 * (size_t)V + 2)); NOMEM(c->pos.ensure(2 * (size_t)V + 2));
+    NOMEM(c->acting.ensure(V + 1)); NOMEM(c->elected.ensure(V + 1));
+    void *e0 = get_event(c), *e1 = get_event(c);
+    be_event_record(c->stream, e0);
+    be_h2d(c->stream, c->d_arena_in.p, in->arena, in->n_buckets * 4);
+    be_h2d(c->stream, c->d_refs_in.p, in->refs, (size_t)n * 8);
+    be_h2d(c->stream, c->d_state_in.p, in->state, V + 1);
+    be_h2d(c->stream, c->d_value_in.p, in->value, nlit);
+    if (in->trail_size) be_h2d(c->stream, c->d_trail_in.p, in->trail, (size_t)in->trail_size * 4);
+    if (in->model_size) be_h2d(c->stream, c->d_model_in.p, in->model, (size_t)in->model_size * 4);
+    be_h2d(c->stream, c->d_vorg.p, in->vorg, (size_t)(V + 1) * 4);
+    if (in->ifrozen) be_h2d(c->stream, c->d_ifrozen.p, in->ifrozen, V + 1);
+    be_event_record(c->stream, e1);
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    c->rep.stage_ms[SIGMA_T_H2D] = be_event_ms(e0, e1);
+    c->rep.h2d_bytes = in->n_buckets * 4 + (uint64_t)n * 8 + (V + 1) + nlit + (uint64_t)in->trail_size * 4 +
+                       (uint64_t)in->model_size * 4 + (uint64_t)(V + 1) * 4 + (in->ifrozen ? V + 1 : 0);
+    c->uploaded = true;
+    return SIGMA_OK;
+}
+
+int sigma_execute(sigma_ctx *c)
+{
+    if (!c) return SIGMA_E_ARG;
+    if (!c->uploaded) return fail(c, SIGMA_E_ARG, "sigma_execute before sigma_upload");
+    const float h2d_ms = c->rep.stage_ms[SIGMA_T_H2D];
+    const uint64_t h2d_bytes = c->rep.h2d_bytes;
+    memset(&c->rep, 0, sizeof c->rep);
+    c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
+    c->evused = 0; c->evs.clear();
+    c->executed = false;
+    c->launches0 = be_launch_count();
+    const uint32_t V = c->nvars, nlit = c->nlit;
+    /* restore the pristine solver state */
+    NOMEM(c->model.ensure((size_t)c->in_model + (1u << 16)));
+    void *e0 = get_event(c), *e1 = get_event(c);
+    be_event_record(c->stream, e0);
+    be_d2d(c->stream, c->state.p, c->d_state_in.p, V + 1);
+    be_d2d(c->stream, c->value.p, c->d_value_in.p, nlit);
+    if (c->in_trail) be_d2d(c->stream, c->trail.p, c->d_trail_in.p, (size_t)c->in_trail * 4);
+    if (c->in_model) be_d2d(c->stream, c->model.p, c->d_model_in.p, (size_t)c->in_model * 4);
+    be_memset(c->stream, c->marks.p, 0xFF, V + 1);
+    be_memset(c->stream, c->ot_len.p, 0, (size_t)nlit * 4);
+    be_memset(c->stream, c->ot_off.p, 0, (size_t)(nlit + 1) * 4);
+    memset(&c->hsc, 0, sizeof c->hsc);
+    c->hsc.n_trail = c->in_trail; c->hsc.propagated = c->in_propagated; c->hsc.unassigned = c->in_unassigned;
+    c->hsc.max_frozen = c->in_max_frozen; c->hsc.brk_rank = 0xFFFFFFFFu;
+    c->model_words = c->in_model;
+    int rc = push_scalars(c);
+    if (rc == SIGMA_OK) rc = run_phases(c);
+    be_event_record(c->stream, e1);
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    /* resolve timers */
+    for (const StageEv &e : c->evs) c->rep.stage_ms[e.stage] += be_event_ms(e.a, e.b);
+    c->rep.stage_ms[SIGMA_T_TOTAL_DEVICE] = be_event_ms(e0, e1);
+    c->rep.kernel_launches = be_launch_count() - c->launches0;
+    c->rep.status = rc;
+    c->rep.literals_in = c->in_literals;
+    c->rep.n_clauses = c->out_ncls; c->rep.n_literals = c->out_literals;
+    c->rep.max_melted_delta = c->out_max_melted - c->in_max_melted;
+    const SgScalars &s = c->hsc;
+    c->rep.pures = (int64_t)s.pures; c->rep.inverters = (int64_t)s.inverters; c->rep.andors = (int64_t)s.andors;
+    c->rep.ites = (int64_t)s.ites; c->rep.xors = (int64_t)s.xors; c->rep.funs = (int64_t)s.funs;
+    c->rep.resolutions = (int64_t)s.resolutions; c->rep.subsumed = (int64_t)s.subsumed;
+    c->rep.strengthened = (int64_t)s.strengthened; c->rep.units = (int64_t)s.units_forced;
+    c->rep.sort_ties_gt24 = (int64_t)s.sort_ties_gt24;
+    c->executed = (rc == SIGMA_OK);
+    return rc;
+}
+
+int sigma_result_sizes(sigma_ctx *c, sigma_formula *sz)
+{
+    if (!c || !sz) return SIGMA_E_ARG;
+    if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    sz->nvars = c->nvars; sz->n_clauses = c->out_ncls; sz->n_buckets = c->out_buckets; sz->n_literals = c->out_literals;
+    sz->trail_size = c->hsc.n_trail; sz->propagated = c->hsc.propagated; sz->model_size = c->model_words;
+    sz->unassigned = c->hsc.unassigned; sz->max_frozen = c->hsc.max_frozen; sz->max_melted = c->out_max_melted;
+    sz->simplify_calls = c->in_calls;
+    return SIGMA_OK;
+}
+
+int sigma_download(sigma_ctx *c, sigma_formula *out)
+{
+    if (!c || !out) return SIGMA_E_ARG;
+    if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    const uint32_t V = c->nvars, nlit = c->nlit;
+    const bool small = out->arena_cap < c->out_buckets || out->refs_cap < c->out_ncls || out->trail_cap < c->hsc.n_trail ||
+                       out->model_cap < c->model_words;
+    const uint64_t acap = out->arena_cap, mcap = out->model_cap; const uint32_t rcap = out->refs_cap, tcap = out->trail_cap;
+    sigma_result_sizes(c, out);
+    out->arena_cap = acap; out->model_cap = mcap; out->refs_cap = rcap; out->trail_cap = tcap;
+    if (small) return fail(c, SIGMA_E_NOSPACE, "output buffers too small (required sizes filled in)");
+    if (!out->arena || !out->refs || !out->state || !out->value || !out->trail || !out->model) return fail(c, SIGMA_E_ARG, "null output array");
+    void *e0 = get_event(c), *e1 = get_event(c);
+    be_event_record(c->stream, e0);
+    if (c->out_buckets) be_d2h(c->stream, out->arena, c->arena_out.p, c->out_buckets * 4);
+    if (c->out_ncls) be_d2h(c->stream, out->refs, c->refs_out.p, (size_t)c->out_ncls * 8);
+    be_d2h(c->stream, out->state, c->state.p, V + 1);
+    be_d2h(c->stream, out->value, c->value.p, nlit);
+    if (c->hsc.n_trail) be_d2h(c->stream, out->trail, c->trail.p, (size_t)c->hsc.n_trail * 4);
+    if (c->model_words) be_d2h(c->stream, out->model, c->model.p, (size_t)c->model_words * 4);
+    be_event_record(c->stream, e1);
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    c->rep.stage_ms[SIGMA_T_D2H] = be_event_ms(e0, e1);
+    c->rep.d2h_bytes = c->out_buckets * 4 + (uint64_t)c->out_ncls * 8 + (V + 1) + nlit + (uint64_t)c->hsc.n_trail * 4 + c->model_words * 4;
+    return SIGMA_OK;
+}
+
+int sigma_get_report(sigma_ctx *c, sigma_report *rep)
+{
+    if (!c || !rep) return SIGMA_E_ARG;
+    *rep = c->rep;
+    return SIGMA_OK;
+}
+
+int sigma_run(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, sigma_formula *out, sigma_report *rep)
+{
+    int rc = sigma_upload(c, o, in);
+    if (rc == SIGMA_OK) rc = sigma_execute(c);
+    if (rc == SIGMA_OK && out) rc = sigma_download(c, out);
+    if (rep && c) { *rep = c->rep; rep->status = rc; }
+    return rc;
+}
+
+int sigma_snapshot(sigma_ctx *c, const char *name, void *dst, uint64_t cap_bytes, uint64_t *nbytes)
+{
+    if (!c || !name || !nbytes) return SIGMA_E_ARG;
+    const void *src = nullptr;
+    uint64_t n = 0;
+    const uint32_t V = c->nvars, nlit = c->nlit;
+    if (!strcmp(name, "hdr")) { src = c->hdr.p; n = 16ull * c->n_cls; }
+    else if (!strcmp(name, "lits")) { src = c->lits.p; n = 4ull * c->pool_used; }
+    else if (!strcmp(name, "ot_off")) { src = c->ot_off.p; n = 4ull * (nlit + 1); }
+    else if (!strcmp(name, "ot_len")) { src = c->ot_len.p; n = 4ull * nlit; }
+    else if (!strcmp(name, "ot_data")) { src = c->ot_data.p; n = 4ull * c->ot_data.cap; }
+    else if (!strcmp(name, "occ")) { src = c->occ.p; n = 4ull * nlit; }
+    else if (!strcmp(name, "order")) { src = c->order.p; n = 4ull * V; }
+    else if (!strcmp(name, "elected")) { src = c->elected.p; n = 4ull * c->hsc.n_elected; }
+    else if (!strcmp(name, "state")) { src = c->state.p; n = V + 1; }
+    else if (!strcmp(name, "value")) { src = c->value.p; n = nlit; }
+    else if (!strcmp(name, "trail")) { src = c->trail.p; n = 4ull * c->hsc.n_trail; }
+    else if (!strcmp(name, "model")) { src = c->model.p; n = 4ull * c->model_words; }
+    else if (!strcmp(name, "marks")) { src = c->marks.p; n = V + 1; }
+    else return fail(c, SIGMA_E_ARG, "unknown snapshot name");
+    *nbytes = n;
+    if (!dst || cap_bytes < n) return SIGMA_E_NOSPACE;
+    if (n) be_d2h(c->stream, dst, src, n);
+    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    return SIGMA_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,130 @@
+/* sigma_types.h - device-side data layout of the B200 SIGmA pass.
+ *
+ * The reference keeps the simplifier formula as an AoS bump arena of SCLAUSE records
+ * (reference src/sclause.hpp:45-49, src/simptypes.hpp:48-95) and the occurrence table as a
+ * vector of growable vectors (simptypes.hpp:39-46).  On the device the same information lives
+ * in flat arrays sized for HBM streaming:
+ *
+ *   clause store   hdr[i]  = {off, size, w0, sig}  one 16-byte record per clause id
+ *                  lits[]  = literal pool; clause i owns lits[off .. off+size)
+ *                  clause id i == position in the reference's `_refs` vector (allocation order)
+ *   occurrence     ot_off[lit], ot_len[lit], ot_data[] (clause ids, ascending inside a list right
+ *   table          after the build = the reference's push order, simplify.cpp:39-61)
+ *   solver state   value[lit], state[var], marks[var], trail[], model[] (MODEL::resolved)
+ *
+ * w0 is SCLAUSE word0 verbatim: st:2 (0 ORIGINAL, 1 LEARNT, 2 DELETED) f:1 (molten) a:1 (added)
+ * u:2 (usage) lbd:26, so the hand-off back to the solver needs no translation.
+ */
+#ifndef SIGMA_TYPES_H
+#define SIGMA_TYPES_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SG_HD __host__ __device__ __forceinline__
+#define SG_HDN __host__ __device__
+#else
+#define SG_HD inline
+#define SG_HDN
+#endif
+
+#if !defined(__CUDACC__)
+/* host-side stand-in for CUDA's uint4 (only used by the host emulation build under tests/) */
+struct sg_u4 { uint32_t x, y, z, w; };
+#else
+typedef uint4 sg_u4;
+#endif
+
+/* ---- SCLAUSE word0 bits (constants.hpp:69-71, sclause.hpp:45) -------------------------------- */
+#define SG_ST_MASK   0x3u
+#define SG_LEARNT    0x1u
+#define SG_DELETED   0x2u
+#define SG_MOLTEN    0x4u
+#define SG_ADDED     0x8u
+#define SG_USAGE_SH  4
+#define SG_LBD_SH    6
+/* per-variable state bits (constants.hpp:59-61) */
+#define SG_MELTED_M  1u
+#define SG_FROZEN_M  2u
+
+#define SG_ABS(l)   ((l) >> 1)
+#define SG_FLIP(l)  ((l) ^ 1u)
+#define SG_SIGN(l)  ((l) & 1u)
+#define SG_HASH(l)  (1u << ((l) & 31u))
+
+/* election status of a variable during one LCVE (lcve.cpp:52-83) */
+enum {
+    SG_E_UNDECIDED = 0,
+    SG_E_SKIP      = 1,   /* never acts: assumed / inactive / no occurrences / behind the static break */
+    SG_E_FROZEN    = 2,   /* frozen by an earlier acting candidate                                       */
+    SG_E_NONE      = 3,   /* reached, depFreeze(P) failed: freezes nothing                               */
+    SG_E_PONLY     = 4,   /* reached, depFreeze(P) ok, depFreeze(N) failed: P's freezes stay              */
+    SG_E_BOTH      = 5,   /* elected                                                                     */
+    SG_E_BREAK     = 6    /* reached a break condition (lcve.cpp:70,73)                                  */
+};
+
+/* what VE decided for an elected variable (bounded.cpp:41-182) */
+enum {
+    SG_VE_NONE = 0, SG_VE_PURE = 1, SG_VE_INVERTER = 2, SG_VE_RESOLVE = 3,
+    SG_VE_SUBST = 4, SG_VE_CORE = 5
+};
+
+typedef struct SgOpts {
+    int32_t phases, phase_lits_min, mu_pos, mu_neg, lcve_max_occurs, lcve_clause_max, lcve_min_vars;
+    int32_t sub_max_occurs, sub_clause_max, ve_clause_max, xor_max_arity, bce_max_occurs;
+    int32_t ere_max_occurs, ere_clause_max, collect_freq, lbd_tier1;
+    int32_t sub_en, ve_en, ve_plus_en, ve_fun_en, ve_lbound_en, bce_en, ere_en, ere_extend, all_en, proof_en;
+    int32_t firstcall;
+} SgOpts;
+
+/* scalars that kernels update and the host reads back at stage boundaries */
+typedef struct SgScalars {
+    uint32_t n_trail, propagated, unassigned, max_frozen;
+    uint32_t unsat, n_units, wl_count[2];
+    uint32_t brk_rank, n_acting, n_ponly, n_elected;
+    uint32_t live_cls, pad0;
+    unsigned long long live_lits;
+    unsigned long long n_model;
+    unsigned long long pures, inverters, andors, ites, xors, funs, resolutions, subsumed, strengthened;
+    unsigned long long units_forced, sort_ties_gt24, elect_visits;
+    uint32_t core[12];        /* orgcore[] (lcve.cpp:24): variables holding marks 0..11 */
+    uint32_t n_core, pad1;
+} SgScalars;
+
+/* one unit produced inside SUB/VE: applied in (elected index, sequence) order (SURVEY ledger 7) */
+typedef struct SgUnit { uint32_t eidx, seq, lit, pad; } SgUnit;
+
+typedef struct SgView {
+    sg_u4    *hdr;
+    uint32_t *lits;
+    uint32_t *ot_off, *ot_len, *ot_data;
+    int8_t   *value;
+    uint8_t  *state;
+    int8_t   *marks;
+    const uint8_t  *ifrozen;
+    const uint32_t *vorg;
+    uint32_t *trail;
+    uint32_t *model;
+    uint32_t *occ;           /* occurrences per literal at election time (histogram.cpp:84-97) */
+    uint32_t *scores, *order, *rank;
+    uint8_t  *estat;
+    uint32_t *elected;       /* elected variables in election order */
+    uint32_t *acting;        /* acting candidates in election order, bit31 = P-only */
+    /* per elected variable (index = position in `elected`) */
+    uint32_t *ve_type, *ve_ncls, *ve_nlits, *ve_nmodel, *ve_aux;
+    uint32_t *ve_cls_off, *ve_lit_off, *ve_mod_off;      /* exclusive scans of the three above */
+    uint32_t *scr_off;       /* per elected variable scratch slice in `scratch` */
+    uint32_t *scratch;
+    SgUnit   *ubuf;
+    SgScalars *sc;
+    uint32_t nvars, nlit;    /* nlit = 2*nvars + 2 */
+    uint32_t n_cls;          /* clause ids in use */
+    uint32_t pool_used;      /* literal pool bump pointer */
+    uint32_t n_elected;
+    uint32_t ubuf_cap;
+    uint32_t pmax, nmax;     /* mu << multiplier (lcve.cpp:59-60) */
+    uint64_t model_base;     /* model words present before this VE stage */
+    SgOpts   o;
+} SgView;
+
+#endif

@@ -1,0 +1,247 @@
+"""ctypes binding of libsigma_b200.so (include/sigma_b200.h) and the host-side mirror of the
+reference's pass entry point.
+
+``Sigma.simplify(boundary)`` is the drop-in for the replaced region of
+``Solver::simplifying()`` (reference simplify.cpp:180-210): it takes the formula + solver state
+exactly as they are right after ``awaken()`` and returns them exactly as they are right after
+``shrinkSimp()``, or raises ``Unsat`` where the reference would ``learnEmpty(); killSolver()``.
+
+There is no CPU fallback: if the CUDA library is missing or no device is usable this module
+raises, it never computes anything itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import boundary as B
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "csrc", "libsigma_b200.so")
+
+SIGMA_OK, SIGMA_UNSAT, SIGMA_INTERRUPTED, SIGMA_E_NOMEM, SIGMA_E_CUDA, SIGMA_E_NOSPACE, SIGMA_E_ARG, SIGMA_E_UNSUPPORTED = range(8)
+STAGES = ["h2d", "ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "prop", "vo", "elect", "sot", "sub", "ve",
+          "count", "gc", "export", "d2h", "total_device"]
+T_N = 20
+
+EXPORTS = [
+    "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",
+    "sigma_upload", "sigma_execute", "sigma_result_sizes", "sigma_download", "sigma_get_report", "sigma_host_alloc",
+    "sigma_host_free", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot",
+]
+
+
+class SigmaOpts(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in B.OPT_NAMES] + [("reserved", C.c_int32 * 6)]
+
+
+class SigmaFormula(C.Structure):
+    _fields_ = [
+        ("nvars", C.c_uint32), ("n_clauses", C.c_uint32), ("n_buckets", C.c_uint64), ("n_literals", C.c_uint64),
+        ("arena", C.c_void_p), ("refs", C.c_void_p), ("state", C.c_void_p), ("value", C.c_void_p),
+        ("trail", C.c_void_p), ("trail_size", C.c_uint32), ("propagated", C.c_uint32), ("vorg", C.c_void_p),
+        ("ifrozen", C.c_void_p), ("model", C.c_void_p), ("model_size", C.c_uint64),
+        ("unassigned", C.c_uint32), ("max_frozen", C.c_uint32), ("max_melted", C.c_uint32), ("simplify_calls", C.c_uint32),
+        ("arena_cap", C.c_uint64), ("refs_cap", C.c_uint32), ("trail_cap", C.c_uint32), ("model_cap", C.c_uint64),
+    ]
+
+
+class SigmaReport(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("phases_run", C.c_int32), ("n_clauses", C.c_uint32), ("max_melted_delta", C.c_uint32),
+        ("n_literals", C.c_uint64), ("literals_in", C.c_uint64),
+        ("pures", C.c_int64), ("inverters", C.c_int64), ("andors", C.c_int64), ("ites", C.c_int64), ("xors", C.c_int64),
+        ("funs", C.c_int64), ("resolutions", C.c_int64), ("subsumed", C.c_int64), ("strengthened", C.c_int64),
+        ("units", C.c_int64), ("sort_ties_gt24", C.c_int64),
+        ("stage_ms", C.c_float * T_N), ("stage_launches", C.c_uint32 * T_N), ("stage_bytes", C.c_uint64 * T_N),
+        ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("elected_per_phase", C.c_uint32 * 8), ("election_rounds", C.c_uint32 * 8), ("reserved", C.c_uint64 * 8),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k in ("status", "phases_run", "n_clauses", "max_melted_delta", "n_literals", "literals_in",
+                                            "pures", "inverters", "andors", "ites", "xors", "funs", "resolutions", "subsumed",
+                                            "strengthened", "units", "sort_ties_gt24", "kernel_launches", "h2d_bytes", "d2h_bytes")}
+        d["stage_ms"] = {s: float(self.stage_ms[i]) for i, s in enumerate(STAGES)}
+        d["stage_launches"] = {s: int(self.stage_launches[i]) for i, s in enumerate(STAGES)}
+        d["stage_bytes"] = {s: int(self.stage_bytes[i]) for i, s in enumerate(STAGES)}
+        d["elected_per_phase"] = list(self.elected_per_phase)
+        d["election_rounds"] = list(self.election_rounds)
+        return d
+
+
+class Unsat(Exception):
+    """The pass derived the empty clause (reference: learnEmpty(); killSolver(), control.cpp:221)."""
+
+
+class SigmaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sigma error {code}: {msg}")
+        self.code = code
+
+
+def load(path=None):
+    path = path or os.environ.get("SIGMA_B200_LIB") or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found: build it with `python __graft_entry__.py build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.sigma_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.sigma_destroy.argtypes = [C.c_void_p]
+    lib.sigma_default_opts.argtypes = [C.POINTER(SigmaOpts)]
+    lib.sigma_strerror.restype = C.c_char_p
+    lib.sigma_strerror.argtypes = [C.c_int]
+    lib.sigma_last_error.restype = C.c_char_p
+    lib.sigma_last_error.argtypes = [C.c_void_p]
+    lib.sigma_run.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaFormula), C.POINTER(SigmaFormula), C.POINTER(SigmaReport)]
+    lib.sigma_upload.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaFormula)]
+    lib.sigma_execute.argtypes = [C.c_void_p]
+    lib.sigma_result_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
+    lib.sigma_download.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
+    lib.sigma_get_report.argtypes = [C.c_void_p, C.POINTER(SigmaReport)]
+    lib.sigma_host_alloc.restype = C.c_void_p
+    lib.sigma_host_alloc.argtypes = [C.c_uint64]
+    lib.sigma_host_free.argtypes = [C.c_void_p]
+    lib.sigma_set_stop.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.sigma_snapshot.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from sigma_host_alloc (freed with the object)."""
+
+    def __init__(self, lib, dtype, n):
+        self.lib, self.nbytes = lib, max(1, int(n) * np.dtype(dtype).itemsize)
+        self.ptr = lib.sigma_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("sigma_host_alloc failed")
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                self.lib.sigma_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Sigma:
+    """One context per GPU (not thread-safe; different contexts are independent)."""
+
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load(lib_path)
+        self.ctx = C.c_void_p()
+        rc = self.lib.sigma_create(device, C.byref(self.ctx))
+        if rc != SIGMA_OK:
+            msg = self.lib.sigma_last_error(self.ctx).decode() if self.ctx else "no context"
+            if self.ctx:
+                self.lib.sigma_destroy(self.ctx)
+                self.ctx = None
+            raise SigmaError(rc, msg)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.sigma_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == SIGMA_UNSAT:
+            raise Unsat()
+        if rc != SIGMA_OK:
+            raise SigmaError(rc, self.lib.sigma_last_error(self.ctx).decode())
+
+    @staticmethod
+    def make_opts(opts=None):
+        o = SigmaOpts()
+        d = dict(B.DEFAULT_OPTS)
+        d.update(opts or {})
+        for k in B.OPT_NAMES:
+            setattr(o, k, int(d[k]))
+        return o
+
+    @staticmethod
+    def make_formula(b: B.Boundary):
+        f = SigmaFormula()
+        f.nvars, f.n_clauses = b.nvars, int(b.refs.size)
+        f.n_buckets, f.n_literals = int(b.arena.size), int(b.arena.size) - 3 * int(b.refs.size)
+        f.arena, f.refs, f.state, f.value = _ptr(b.arena), _ptr(b.refs), _ptr(b.state), _ptr(b.value)
+        f.trail, f.trail_size, f.propagated = _ptr(b.trail), int(b.trail.size), b.propagated
+        f.vorg, f.ifrozen = _ptr(b.vorg), None
+        f.model, f.model_size = _ptr(b.model), int(b.model.size)
+        f.unassigned, f.max_frozen, f.max_melted, f.simplify_calls = b.unassigned, b.max_frozen, b.max_melted, b.simplify_calls
+        return f
+
+    # ---- split form -------------------------------------------------------------------
+    def upload(self, b: B.Boundary, opts=None):
+        self._keep = (b, self.make_opts(opts if opts is not None else b.opts), self.make_formula(b))
+        self._check(self.lib.sigma_upload(self.ctx, C.byref(self._keep[1]), C.byref(self._keep[2])))
+
+    def execute(self):
+        self._check(self.lib.sigma_execute(self.ctx))
+
+    def report(self):
+        r = SigmaReport()
+        self.lib.sigma_get_report(self.ctx, C.byref(r))
+        return r.as_dict()
+
+    def download(self, pinned=False) -> B.Boundary:
+        sz = SigmaFormula()
+        self._check(self.lib.sigma_result_sizes(self.ctx, C.byref(sz)))
+        src = self._keep[0]
+        out = B.Boundary(status=0, nvars=sz.nvars, simplify_calls=sz.simplify_calls, vorg=src.vorg, opts=src.opts)
+        keep = []
+
+        def alloc(dtype, n):
+            if pinned:
+                p = PinnedArray(self.lib, dtype, n)
+                keep.append(p)
+                return p.array
+            return np.empty(int(n), dtype=dtype)
+        out.arena = alloc(np.uint32, sz.n_buckets)
+        out.refs = alloc(np.uint64, sz.n_clauses)
+        out.state = alloc(np.uint8, sz.nvars + 1)
+        out.value = alloc(np.int8, 2 * sz.nvars + 2)
+        out.trail = alloc(np.uint32, sz.trail_size)
+        out.model = alloc(np.uint32, sz.model_size)
+        f = SigmaFormula()
+        f.arena, f.refs, f.state, f.value, f.trail, f.model = (_ptr(out.arena), _ptr(out.refs), _ptr(out.state),
+                                                                _ptr(out.value), _ptr(out.trail), _ptr(out.model))
+        f.arena_cap, f.refs_cap, f.trail_cap, f.model_cap = sz.n_buckets, sz.n_clauses, sz.trail_size, sz.model_size
+        self._check(self.lib.sigma_download(self.ctx, C.byref(f)))
+        out.n_clauses, out.n_literals = f.n_clauses, f.n_literals
+        out.unassigned, out.max_frozen, out.max_melted, out.propagated = f.unassigned, f.max_frozen, f.max_melted, f.propagated
+        out._pinned = keep
+        return out
+
+    # ---- one-shot: the drop-in for simplify.cpp:180-210 ---------------------------------
+    def simplify(self, b: B.Boundary, opts=None):
+        """Returns (Boundary after the pass, report dict). Raises Unsat like the reference exits."""
+        self.upload(b, opts)
+        self.execute()
+        out = self.download()
+        return out, self.report()
+
+    def set_stop(self, phase, stage):
+        self._check(self.lib.sigma_set_stop(self.ctx, phase, STAGES.index(stage) if isinstance(stage, str) else stage))
+
+    def snapshot(self, name, dtype):
+        n = C.c_uint64()
+        self.lib.sigma_snapshot(self.ctx, name.encode(), None, 0, C.byref(n))
+        buf = np.empty(n.value // np.dtype(dtype).itemsize, dtype=dtype)
+        self._check(self.lib.sigma_snapshot(self.ctx, name.encode(), _ptr(buf), n.value, C.byref(n)))
+        return buf

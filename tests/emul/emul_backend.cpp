@@ -1,0 +1,240 @@
+/* emul_backend.cpp - TEST INFRASTRUCTURE ONLY (never part of libsigma_b200.so).
+ *
+ * A serial host stand-in for seqfrost_b200/csrc/sigma_backend.h so that the pass driver
+ * (sigma_pass.cpp) and the per-item bodies (sigma_items.cuh) can be exercised against the
+ * reference in a container without a GPU.  "Device memory" is the host heap; every "kernel" is a
+ * plain loop over its work items, optionally in a shuffled order (SIGMA_EMUL_SHUFFLE=seed) to
+ * shake out order dependence that the real, concurrent kernels would expose.
+ */
+#include "../../seqfrost_b200/csrc/sigma_backend.h"
+#include "../../seqfrost_b200/csrc/sigma_items.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <algorithm>
+#include <numeric>
+#include <random>
+#include <vector>
+
+static uint64_t g_launches = 0;
+static long g_shuffle = -1;
+
+static std::vector<uint32_t> item_order(uint32_t n)
+{
+    std::vector<uint32_t> o(n);
+    std::iota(o.begin(), o.end(), 0u);
+    if (g_shuffle >= 0) { std::mt19937 rng((unsigned)g_shuffle + n); std::shuffle(o.begin(), o.end(), rng); }
+    return o;
+}
+
+int be_init(int, void **stream_out, char *, size_t)
+{
+    const char *e = getenv("SIGMA_EMUL_SHUFFLE");
+    g_shuffle = e ? atol(e) : -1;
+    *stream_out = (void *)1;
+    return 0;
+}
+void be_shutdown(void *) {}
+void *be_malloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void be_free(void *p) { free(p); }
+void *be_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void be_host_free(void *p) { free(p); }
+int be_h2d(void *, void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int be_d2h(void *, void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int be_d2d(void *, void *d, const void *s, size_t n) { memmove(d, s, n); return 0; }
+int be_memset(void *, void *d, int b, size_t n) { memset(d, b, n); return 0; }
+int be_sync(void *, char *, size_t) { return 0; }
+struct Ev { double t; };
+static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+void *be_event_create(void) { return new Ev{ 0 }; }
+void be_event_destroy(void *e) { delete (Ev *)e; }
+void be_event_record(void *, void *e) { ((Ev *)e)->t = now_ms(); }
+float be_event_ms(void *a, void *b) { return (float)(((Ev *)b)->t - ((Ev *)a)->t); }
+uint64_t be_launch_count(void) { return g_launches; }
+
+void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
+{
+    g_launches++;
+    for (uint32_t i = 0; i < n; ++i) sizes[i] = arena[refs[i] + 2];
+}
+void be_ingest_copy(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs, sg_u4 *hdr, uint32_t *lits)
+{
+    g_launches++;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t r = refs[i];
+        sg_u4 h; h.x = offs[i]; h.y = arena[r + 2]; h.z = arena[r]; h.w = arena[r + 1];
+        hdr[i] = h;
+        for (uint32_t k = 0; k < h.y; ++k) lits[h.x + k] = arena[r + 3 + k];
+    }
+}
+size_t be_scan_tmp_words(uint32_t) { return 1; }
+void be_scan_u32(void *, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *)
+{
+    g_launches++;
+    uint32_t s = 0;
+    for (uint32_t i = 0; i < n; ++i) { const uint32_t x = in[i]; out[i] = s; s += x; }
+    if (total) *total = s;
+}
+void be_hist(void *, const SgView &v, uint32_t *counts)
+{
+    g_launches++;
+    for (uint32_t c = 0; c < v.n_cls; ++c) {
+        if (v.hdr[c].z & SG_DELETED) continue;
+        const uint32_t *l = v.lits + v.hdr[c].x;
+        for (uint32_t k = 0; k < v.hdr[c].y; ++k) counts[l[k]]++;
+    }
+}
+void be_scatter(void *, const SgView &v, uint32_t *cursor)
+{
+    g_launches++;
+    for (uint32_t c : item_order(v.n_cls)) {
+        if (v.hdr[c].z & SG_DELETED) continue;
+        const uint32_t *l = v.lits + v.hdr[c].x;
+        for (uint32_t k = 0; k < v.hdr[c].y; ++k) v.ot_data[v.ot_off[l[k]] + cursor[l[k]]++] = c;
+    }
+}
+void be_scores(void *, const SgView &v)
+{
+    g_launches++;
+    for (uint32_t x = 1; x <= v.nvars; ++x) { v.scores[x] = v.occ[2 * x] * v.occ[2 * x + 1]; v.order[x - 1] = x; }
+}
+size_t be_sort_tmp_words(uint32_t) { return 1; }
+void be_sort_pairs(void *, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t *, uint32_t *, uint32_t *, uint32_t)
+{
+    g_launches++;
+    std::vector<uint32_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> k2(n), v2(n);
+    for (uint32_t i = 0; i < n; ++i) { k2[i] = keys[idx[i]]; v2[i] = vals[idx[i]]; }
+    memcpy(keys, k2.data(), n * 4ull); memcpy(vals, v2.data(), n * 4ull);
+}
+void be_rank(void *, const SgView &v)
+{
+    g_launches++;
+    for (uint32_t r = 0; r < v.nvars; ++r) v.rank[v.order[r]] = r;
+}
+void be_elect_init(void *, const SgView &v, uint32_t *wl)
+{
+    g_launches++;
+    uint32_t n = 0;
+    for (uint32_t x : item_order(v.nvars)) {
+        const uint32_t var = x + 1;
+        if (v.estat[var] != SG_E_UNDECIDED) continue;
+        if (v.rank[var] > v.sc->brk_rank) { v.estat[var] = SG_E_SKIP; continue; }
+        wl[n++] = var;
+    }
+    v.sc->wl_count[0] = n;
+}
+void be_elect_round(void *, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity)
+{
+    g_launches++;
+    const uint32_t n = v.sc->wl_count[parity];
+    uint32_t m = 0;
+    for (uint32_t i : item_order(n))
+        if (sg_elect_round_item(v, wl_in[i])) wl_out[m++] = wl_in[i];
+    v.sc->wl_count[parity ^ 1] = m;
+}
+void be_acting_flags(void *, const SgView &v, uint32_t *fa, uint32_t *fe)
+{
+    g_launches++;
+    for (uint32_t r = 0; r < v.nvars; ++r) {
+        const uint8_t s = v.estat[v.order[r]];
+        const bool in = r < v.sc->brk_rank;
+        fa[r] = in && (s == SG_E_BOTH || s == SG_E_PONLY);
+        fe[r] = in && s == SG_E_BOTH;
+    }
+}
+void be_acting_scatter(void *, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe)
+{
+    g_launches++;
+    for (uint32_t r = 0; r < v.nvars; ++r) {
+        const uint32_t var = v.order[r];
+        if (fa[r]) v.acting[pa[r]] = var | (v.estat[var] == SG_E_PONLY ? 0x80000000u : 0u);
+        if (fe[r]) v.elected[pe[r]] = var;
+    }
+}
+void be_items(void *, int kind, const SgView &v, uint32_t n)
+{
+    g_launches++;
+    for (uint32_t i : item_order(n)) {
+        switch (kind) {
+        case SGK_IDSORT: sg_idsort_item(v, i); break;
+        case SGK_REDUCE: sg_reduce_item(v, i); break;
+        case SGK_ELECT_PREP: sg_elect_prep_item(v, i + 1); break;
+        case SGK_SORTOT: sg_sortot_item(v, 2 * v.elected[i >> 1] + (i & 1)); break;
+        case SGK_SCRATCH_LEN: {
+            const uint32_t var = v.elected[i];
+            const uint32_t a = v.ot_len[2 * var], b = v.ot_len[2 * var + 1];
+            v.scr_off[i] = (a > b ? a : b) + 2;
+        } break;
+        case SGK_SUB: sg_sub_item(v, i); break;
+        case SGK_VE_COUNT: sg_ve_count_item(v, i); break;
+        case SGK_VE_EMIT: sg_ve_emit_item(v, i); break;
+        default: abort();
+        }
+    }
+}
+void be_serial(void *, int kind, const SgView &v, uint32_t arg)
+{
+    g_launches++;
+    switch (kind) {
+    case SGS_PROP: sg_prop_serial(v); break;
+    case SGS_MARKS: sg_marks_serial(v, arg); break;
+    case SGS_APPLY_UNITS: sg_apply_units_serial(v, arg); break;
+    default: abort();
+    }
+}
+void be_sort_units(void *, const SgView &v, uint32_t n)
+{
+    g_launches++;
+    std::sort(v.ubuf, v.ubuf + n, [](const SgUnit &a, const SgUnit &b) { return a.eidx != b.eidx ? a.eidx < b.eidx : a.seq < b.seq; });
+}
+void be_count_live(void *, const SgView &v)
+{
+    g_launches++;
+    uint32_t nc = 0; unsigned long long nl = 0;
+    for (uint32_t c = 0; c < v.n_cls; ++c) if (!(v.hdr[c].z & SG_DELETED)) { nc++; nl += v.hdr[c].y; }
+    v.sc->live_cls = nc; v.sc->live_lits = nl;
+}
+void be_count_melted(void *, const SgView &v, uint32_t *out)
+{
+    g_launches++;
+    uint32_t n = 0;
+    for (uint32_t x = 1; x <= v.nvars; ++x) if (v.state[x] & SG_MELTED_M) n++;
+    *out = n;
+}
+void be_live_flags(void *, const SgView &v, uint32_t *flags, uint32_t *sizes)
+{
+    g_launches++;
+    for (uint32_t c = 0; c < v.n_cls; ++c) {
+        const bool live = !(v.hdr[c].z & SG_DELETED);
+        flags[c] = live; sizes[c] = live ? v.hdr[c].y : 0;
+    }
+}
+void be_compact_move(void *, const SgView &v, const uint32_t *newid, const uint32_t *newoff, sg_u4 *hdr2, uint32_t *lits2)
+{
+    g_launches++;
+    for (uint32_t c = 0; c < v.n_cls; ++c) {
+        if (v.hdr[c].z & SG_DELETED) continue;
+        sg_u4 h = v.hdr[c];
+        const uint32_t *l = v.lits + h.x;
+        h.x = newoff[c];
+        hdr2[newid[c]] = h;
+        for (uint32_t k = 0; k < h.y; ++k) lits2[h.x + k] = l[k];
+    }
+}
+void be_export(void *, const SgView &v, const uint32_t *newid, const uint32_t *newoff, uint32_t *arena, uint64_t *refs)
+{
+    g_launches++;
+    for (uint32_t c = 0; c < v.n_cls; ++c) {
+        if (v.hdr[c].z & SG_DELETED) continue;
+        const sg_u4 h = v.hdr[c];
+        const uint64_t r = 3ull * newid[c] + newoff[c];
+        refs[newid[c]] = r;
+        arena[r] = h.z; arena[r + 1] = h.w; arena[r + 2] = h.y;
+        for (uint32_t k = 0; k < h.y; ++k) arena[r + 3 + k] = v.lits[h.x + k];
+    }
+}

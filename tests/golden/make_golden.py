@@ -1,0 +1,63 @@
+"""Generates the committed golden fixtures from the UNMODIFIED reference (oracle/_ref/ref_sigma,
+built by `make -C oracle ref` from /root/reference/src).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+For every case it writes <name>.in (boundary right after awaken(), simplify.cpp:171) and
+<name>.out (boundary right after shrinkSimp(), simplify.cpp:210) in the sectioned format of
+seqfrost_b200/boundary.py.  The reference is run with -no-redundancy (ERE is SURVEY §8 "next #1").
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from seqfrost_b200 import cnfgen  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_sigma")
+
+# (name, generator, kwargs, extra reference options)
+CASES = [
+    ("gates_small", "gate_circuit", dict(nvars=3000, seed=11), []),
+    ("gates_w200", "gate_circuit", dict(nvars=1500, seed=5, window=200), []),
+    ("ksat3_small", "random_ksat", dict(nvars=2000, nclauses=8520, k=3, seed=1), []),
+    ("ksat5_planted", "planted_subsumption_ksat", dict(nvars=3000, nclauses=15000, k=5, seed=7), []),
+    ("xorphp_small", "xor_php_mix", dict(nclauses=6000, seed=3), []),
+    ("gates_bvebound", "gate_circuit", dict(nvars=1200, seed=21), ["-bvebound"]),
+    ("gates_phases2", "gate_circuit", dict(nvars=1200, seed=22), ["--phases=2"]),
+    ("gates_nofun_cm4", "gate_circuit", dict(nvars=1200, seed=23), ["-no-function", "--boundedclausemax=4"]),
+    ("fuzz_units1", "fuzz_mix", dict(seed=20), []),
+    ("fuzz_units2", "fuzz_mix", dict(seed=75), []),
+    ("fuzz_units4", "fuzz_mix", dict(seed=115), []),
+    ("fuzz_unsat_a", "fuzz_mix", dict(seed=83), []),
+    ("fuzz_unsat_b", "fuzz_mix", dict(seed=101), []),
+    ("fuzz_ok_a", "fuzz_mix", dict(seed=0), []),
+    ("fuzz_ok_b", "fuzz_mix", dict(seed=2), []),
+]
+
+
+def main():
+    if not os.path.exists(REF):
+        raise SystemExit(f"{REF} missing: run `make -C oracle ref` first")
+    for name, gen, kw, opts in CASES:
+        nv, off, lits = getattr(cnfgen, gen)(**kw)
+        with tempfile.TemporaryDirectory() as td:
+            cnf = os.path.join(td, name + ".cnf")
+            cnfgen.write_dimacs(cnf, nv, off, lits)
+            fin, fout = os.path.join(HERE, name + ".in"), os.path.join(HERE, name + ".out")
+            for f in (fin, fout):
+                if os.path.exists(f):
+                    os.remove(f)
+            r = subprocess.run([REF, cnf, "-no-redundancy", "-quiet", f"--sgin={fin}", f"--sgout={fout}"] + opts,
+                               capture_output=True, text=True)
+            print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"rc={r.returncode}",
+                  os.path.getsize(fin), os.path.getsize(fout))
+
+
+if __name__ == "__main__":
+    main()
