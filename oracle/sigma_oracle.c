@@ -1144,7 +1144,7 @@ static int run_pass(sgo_ctx *c)
         if (times > 1 && times != c->o.phases && (times % c->o.collect_freq) == 0) compact(c);
         STOP_AFTER(SIGMA_T_GC);
         create_ot(c);
-        STOP_AFTER(SIGMA_T_COT);
+        STOP_AFTER(SIGMA_T_OT_ORDER);
         if (!prop(c)) return SIGMA_UNSAT;
         STOP_AFTER(SIGMA_T_PROP);
         const int ok = lcve(c);
