@@ -166,21 +166,21 @@ def from_cnf(nvars, offsets, lits) -> Boundary:
     SCLAUSE with ascending literals (``lit = 2*var + sign``, constants.hpp:77-82) and
     ``sig = OR 1<<(lit&31)`` (sclause.hpp:158-162), allocated back to back in input order."""
     offsets = np.asarray(offsets, dtype=np.int64)
-    lits = np.asarray(lits, dtype=np.int64)
+    lits = np.asarray(lits)
     n = offsets.size - 1
     sizes = np.diff(offsets)
-    enc = (2 * np.abs(lits) + (lits < 0)).astype(np.uint32)
-    cid = np.repeat(np.arange(n, dtype=np.int64), sizes)
-    order = np.lexsort((enc, cid))           # ascending literals inside every clause
-    enc = enc[order]
-    sig = np.zeros(n, dtype=np.uint32)
-    np.bitwise_or.at(sig, cid, (np.uint32(1) << (enc & np.uint32(31))).astype(np.uint32))
+    enc = (2 * np.abs(lits).astype(np.uint32) + (lits < 0)).astype(np.uint32)
     refs = (offsets[:-1] + 3 * np.arange(n, dtype=np.int64)).astype(np.uint64)
     arena = np.zeros(int(offsets[-1]) + 3 * n, dtype=np.uint32)
     r = refs.astype(np.int64)
-    arena[r + 1] = sig
     arena[r + 2] = sizes.astype(np.uint32)
-    arena[np.repeat(r + 3 - offsets[:-1], sizes) + np.arange(int(offsets[-1]), dtype=np.int64)] = enc
+    # one vectorised row sort per distinct clause size (ascending literals inside every clause)
+    for k in np.unique(sizes).tolist():
+        idx = np.nonzero(sizes == k)[0]
+        rows = enc[offsets[idx][:, None] + np.arange(k, dtype=np.int64)[None, :]]
+        rows.sort(axis=1)
+        arena[r[idx] + 1] = np.bitwise_or.reduce(np.uint32(1) << (rows & np.uint32(31)), axis=1).astype(np.uint32)
+        arena[(r[idx] + 3)[:, None] + np.arange(k, dtype=np.int64)[None, :]] = rows
     return Boundary(
         status=0, nvars=int(nvars), n_clauses=n, n_literals=int(offsets[-1]), unassigned=int(nvars),
         max_frozen=0, max_melted=0, propagated=0, simplify_calls=1, arena=arena, refs=refs,

@@ -228,6 +228,39 @@ class Sigma:
         out._pinned = keep
         return out
 
+    # ---- reusable pinned hand-off buffers (what an integrated solver would own) -----------
+    def alloc_pinned_like(self, b: B.Boundary, slack=1.25):
+        """Pinned copies of the input arrays plus pinned output buffers with capacity
+        `slack` x the input sizes; returns (pinned input Boundary, output buffer dict)."""
+        keep = []
+
+        def pin(a, n=None):
+            p = PinnedArray(self.lib, a.dtype, a.size if n is None else n)
+            keep.append(p)
+            if n is None:
+                p.array[:] = a
+            return p.array
+        bi = B.Boundary(**{k: getattr(b, k) for k in ("status", "nvars", "n_clauses", "n_literals", "unassigned", "max_frozen",
+                                                       "max_melted", "propagated", "simplify_calls", "opts")})
+        bi.arena, bi.refs, bi.state, bi.value = pin(b.arena), pin(b.refs), pin(b.state), pin(b.value)
+        bi.trail, bi.vorg, bi.model = pin(b.trail), pin(b.vorg), pin(b.model)
+        bufs = dict(arena=pin(b.arena, int(b.arena.size * slack) + 1024), refs=pin(b.refs, int(b.refs.size * slack) + 1024),
+                    state=pin(b.state, b.nvars + 1), value=pin(b.value, 2 * b.nvars + 2),
+                    trail=pin(np.zeros(0, np.uint32), b.nvars + 16),
+                    model=pin(np.zeros(0, np.uint32), int(b.arena.size) + b.model.size + 1024))
+        bi._pinned = keep
+        return bi, bufs
+
+    def download_into(self, bufs) -> SigmaFormula:
+        """D2H into caller-owned buffers (raises SigmaError(E_NOSPACE) when too small)."""
+        f = SigmaFormula()
+        f.arena, f.refs, f.state, f.value, f.trail, f.model = (_ptr(bufs["arena"]), _ptr(bufs["refs"]), _ptr(bufs["state"]),
+                                                                _ptr(bufs["value"]), _ptr(bufs["trail"]), _ptr(bufs["model"]))
+        f.arena_cap, f.refs_cap = bufs["arena"].size, bufs["refs"].size
+        f.trail_cap, f.model_cap = bufs["trail"].size, bufs["model"].size
+        self._check(self.lib.sigma_download(self.ctx, C.byref(f)))
+        return f
+
     # ---- one-shot: the drop-in for simplify.cpp:180-210 ---------------------------------
     def simplify(self, b: B.Boundary, opts=None):
         """Returns (Boundary after the pass, report dict). Raises Unsat like the reference exits."""
