@@ -482,6 +482,87 @@ SG_HDN inline void sg_marks_serial(const SgView &v, uint32_t n_acting)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* warp-cooperative execution of one elected variable                                           */
+/*                                                                                              */
+/* SUB and the BVE decision run one WARP per elected variable.  Control flow is warp-uniform    */
+/* (every lane follows the reference's sequential decision tree with the same data); the heavy  */
+/* inner loops - sorted-clause merge tests over the |P| x |N| pair space, and "first clause in  */
+/* list order that ..." scans - are split over the lanes and recombined with ballots/reductions */
+/* so that the outcome is the sequential one.  Clause writes are made by lane 0.                */
+/* (The host test harness instantiates the same code with a warp of width 1.)                   */
+/* ------------------------------------------------------------------------------------------ */
+struct SgLane { uint32_t lane, width; };
+
+SG_HD SgLane sg_lane_ctx()
+{
+    SgLane L;
+#if defined(__CUDA_ARCH__)
+    L.lane = threadIdx.x & 31u; L.width = 32u;
+#else
+    L.lane = 0u; L.width = 1u;
+#endif
+    return L;
+}
+SG_HD uint32_t sg_ballot(bool p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ballot_sync(0xffffffffu, p);
+#else
+    return p ? 1u : 0u;
+#endif
+}
+SG_HD int sg_wsum(int x)
+{
+#if defined(__CUDA_ARCH__)
+    return __reduce_add_sync(0xffffffffu, x);
+#else
+    return x;
+#endif
+}
+SG_HD uint32_t sg_wor(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __reduce_or_sync(0xffffffffu, x);
+#else
+    return x;
+#endif
+}
+SG_HD void sg_wsync()
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+SG_HD int sg_ffs(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m);
+#else
+    return __builtin_ffs((int)m);
+#endif
+}
+SG_HD int sg_popc(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+
+/* index of the first entry in [0,n) satisfying pred, or -1; pred must be side-effect free */
+template <class P> SG_HD int sg_find_first(const SgLane &L, int n, P pred)
+{
+    for (int base = 0; base < n; base += (int)L.width) {
+        const int idx = base + (int)L.lane;
+        const bool p = idx < n && pred(idx);
+        const uint32_t m = sg_ballot(p);
+        if (m) return base + sg_ffs(m) - 1;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* SUB: self-subsuming strengthening + backward subsumption (subsume.hpp:26-218, subsume.cpp:45-76) */
 /* ------------------------------------------------------------------------------------------ */
 SG_HD bool sg_sig_sub(uint32_t A, uint32_t B) { return !(A & ~B); }                 /* simplify.hpp:119 */
@@ -522,33 +603,39 @@ SG_HD bool sg_selfsub_lits(uint32_t x, uint32_t fx, const uint32_t *d1, int n1, 
     return false;
 }
 
-SG_HD void sg_strengthen(const SgView &v, uint32_t c, uint32_t me, uint32_t eidx, uint32_t &seq)
-{   /* subsume.cpp:45-76 */
-    uint32_t *l = SG_LITS(v, c);
+/* strengthen (subsume.cpp:45-76); lane 0 rewrites the clause, every lane tracks `seq` */
+SG_HD void sg_strengthen(const SgView &v, const SgLane &L, uint32_t c, uint32_t me, uint32_t eidx, uint32_t &seq)
+{
     const int size = SG_SIZE(v, c);
-    uint32_t sig = 0;
-    int j = 0;
-    for (int k = 0; k < size; ++k) {
-        const uint32_t lit = l[k];
-        if (lit != me) { l[j++] = lit; sig |= SG_HASH(lit); }
-    }
-    v.hdr[c].w = sig;
-    v.hdr[c].y = (uint32_t)(size - 1);
-    if (size - 1 == 1) sg_push_unit(v, eidx, seq, l[0]);
-    else if (sg_learnt(v, c)) {
-        /* bumpShrunken (solve.hpp:725-737) */
-        const uint32_t w0 = SG_W0(v, c);
-        const int old_lbd = (int)(w0 >> SG_LBD_SH);
-        if (old_lbd > v.o.lbd_tier1) {
-            const int sz = size - 2;
-            const int new_lbd = sz < old_lbd ? sz : old_lbd;
-            if (new_lbd < old_lbd)
-                v.hdr[c].z = (w0 & 0xFu) | (1u << SG_USAGE_SH) | ((uint32_t)new_lbd << SG_LBD_SH);
+    sg_wsync();
+    if (L.lane == 0) {
+        uint32_t *l = SG_LITS(v, c);
+        uint32_t sig = 0;
+        int j = 0;
+        for (int k = 0; k < size; ++k) {
+            const uint32_t lit = l[k];
+            if (lit != me) { l[j++] = lit; sig |= SG_HASH(lit); }
         }
+        uint32_t w0 = SG_W0(v, c);
+        if (size - 1 == 1) { uint32_t s2 = seq; sg_push_unit(v, eidx, s2, l[0]); }
+        else if (w0 & SG_LEARNT) {
+            /* bumpShrunken (solve.hpp:725-737) */
+            const int old_lbd = (int)(w0 >> SG_LBD_SH);
+            if (old_lbd > v.o.lbd_tier1) {
+                const int sz = size - 2;
+                const int new_lbd = sz < old_lbd ? sz : old_lbd;
+                if (new_lbd < old_lbd) w0 = (w0 & 0xFu) | (1u << SG_USAGE_SH) | ((uint32_t)new_lbd << SG_LBD_SH);
+            }
+        }
+        sg_u4 h = v.hdr[c];
+        h.y = (uint32_t)(size - 1); h.z = w0 | SG_MOLTEN; h.w = sig;       /* cand.melt(), subsume.hpp:170 */
+        v.hdr[c] = h;
     }
+    if (size - 1 == 1) seq++;
+    sg_wsync();
 }
 
-SG_HDN inline void sg_self_sub_half(const SgView &v, uint32_t x, uint32_t fx, uint32_t eidx, uint32_t &seq,
+SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x, uint32_t fx, uint32_t eidx, uint32_t &seq,
                                     uint32_t &n_str, uint32_t &n_sub)
 {   /* one loop of self_sub_x (subsume.hpp:186-199): clauses of `x` against the list of `fx` */
     const int maxsz = v.o.sub_clause_max;
@@ -560,64 +647,82 @@ SG_HDN inline void sg_self_sub_half(const SgView &v, uint32_t x, uint32_t fx, ui
         const uint32_t c = me[i];
         if (SG_SIZE(v, c) > maxsz) break;
         if (sg_deleted(v, c)) continue;
-        {   /* selfsubsume (subsume.hpp:158-177) */
+        {   /* selfsubsume (subsume.hpp:158-177): first entry that either ends the scan or strengthens */
             const int candsz = SG_SIZE(v, c);
             const uint32_t candsig = SG_SIG(v, c);
-            for (int j = 0; j < not_; ++j) {
-                const uint32_t s = ot[j];
-                const sg_u4 hs = v.hdr[s];
+            const uint32_t *cl = SG_LITS(v, c);
+            const int k = sg_find_first(L, not_, [&](int j) {
+                const sg_u4 hs = v.hdr[ot[j]];
                 const int subsize = (int)hs.y;
-                if (subsize > candsz) break;
-                if (hs.z & SG_DELETED) continue;
-                if (subsize > 1 && sg_sig_selfsub(hs.w, candsig) &&
-                    sg_selfsub_lits(x, fx, v.lits + hs.x, subsize, SG_LITS(v, c), candsz)) {
-                    sg_strengthen(v, c, x, eidx, seq);
-                    sg_melt(v, c);
-                    n_str++;
-                    break;
-                }
+                if (subsize > candsz) return true;
+                if (hs.z & SG_DELETED) return false;
+                return subsize > 1 && sg_sig_selfsub(hs.w, candsig) && sg_selfsub_lits(x, fx, v.lits + hs.x, subsize, cl, candsz);
+            });
+            if (k >= 0 && (int)v.hdr[ot[k]].y <= candsz) {
+                sg_strengthen(v, L, c, x, eidx, seq);
+                n_str++;
             }
         }
         {   /* subsume (subsume.hpp:139-156) */
             const int candsz = SG_SIZE(v, c);
             const bool cmolten = sg_molten(v, c);
             const uint32_t candsig = SG_SIG(v, c);
-            for (int j = 0; j < i; ++j) {
-                const uint32_t s = me[j];
-                const sg_u4 hs = v.hdr[s];
-                if (hs.z & SG_DELETED) continue;
+            const uint32_t *cl = SG_LITS(v, c);
+            const int k = sg_find_first(L, i, [&](int j) {
+                const sg_u4 hs = v.hdr[me[j]];
+                if (hs.z & SG_DELETED) return false;
                 const int ssz = (int)hs.y;
-                if (cmolten && ssz > candsz) continue;
-                if (ssz > 1 && sg_sig_sub(hs.w, candsig) && sg_sub_lits(v.lits + hs.x, ssz, SG_LITS(v, c), candsz)) {
-                    if ((hs.z & SG_LEARNT) && sg_original(v, c)) v.hdr[s].z = hs.z & ~SG_ST_MASK;
+                if (cmolten && ssz > candsz) return false;
+                return ssz > 1 && sg_sig_sub(hs.w, candsig) && sg_sub_lits(v.lits + hs.x, ssz, cl, candsz);
+            });
+            if (k >= 0) {
+                if (L.lane == 0) {
+                    const uint32_t s = me[k];
+                    const uint32_t sz0 = v.hdr[s].z;
+                    if ((sz0 & SG_LEARNT) && sg_original(v, c)) v.hdr[s].z = sz0 & ~SG_ST_MASK;
                     sg_mark_deleted(v, c);
-                    n_sub++;
-                    break;
                 }
+                sg_wsync();
+                n_sub++;
             }
         }
     }
-    /* updateOL (subsume.hpp:26-36) */
+    /* updateOL (subsume.hpp:26-36): in-place, order-preserving */
     int j = 0;
-    for (int i = 0; i < nme; ++i) {
-        const uint32_t c = me[i];
-        if (sg_molten(v, c)) sg_freeze(v, c);
-        else if (!sg_deleted(v, c)) me[j++] = c;
+    for (int base = 0; base < nme; base += (int)L.width) {
+        const int idx = base + (int)L.lane;
+        uint32_t c = 0;
+        bool keep = false;
+        if (idx < nme) {
+            c = me[idx];
+            const uint32_t w0 = SG_W0(v, c);
+            if (w0 & SG_MOLTEN) v.hdr[c].z = w0 & ~SG_MOLTEN;
+            else keep = !(w0 & SG_DELETED);
+        }
+        const uint32_t m = sg_ballot(keep);
+        sg_wsync();
+        if (keep) me[j + sg_popc(m & ((1u << L.lane) - 1u))] = c;
+        j += sg_popc(m);
+        sg_wsync();
     }
-    v.ot_len[x] = (uint32_t)j;
+    if (L.lane == 0) v.ot_len[x] = (uint32_t)j;
+    sg_wsync();
 }
 
 SG_HDN inline void sg_sub_item(const SgView &v, uint32_t eidx)
 {   /* subsume.cpp:32-39 */
+    const SgLane L = sg_lane_ctx();
     const uint32_t var = v.elected[eidx];
     const uint32_t p = 2 * var, n = p | 1u;
     const int maxoccurs = v.o.sub_max_occurs;
     if ((int)v.ot_len[p] > maxoccurs || (int)v.ot_len[n] > maxoccurs) return;
     uint32_t seq = 0, n_str = 0, n_sub = 0;
-    sg_self_sub_half(v, p, n, eidx, seq, n_str, n_sub);
-    sg_self_sub_half(v, n, p, eidx, seq, n_str, n_sub);
-    if (n_str) sg_atomic_add64(&v.sc->strengthened, n_str);
-    if (n_sub) sg_atomic_add64(&v.sc->subsumed, n_sub);
+    sg_self_sub_half(v, L, p, n, eidx, seq, n_str, n_sub);
+    sg_self_sub_half(v, L, n, p, eidx, seq, n_str, n_sub);
+    if (L.lane == 0) {
+        if (n_str) sg_atomic_add64(&v.sc->strengthened, n_str);
+        if (n_sub) sg_atomic_add64(&v.sc->subsumed, n_sub);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -659,129 +764,145 @@ SG_HD int sg_merge_emit(uint32_t x, const uint32_t *d1, int n1, const uint32_t *
     return n;
 }
 
-/* pair filter shared by the three count loops and the three emit loops:
+/* pair filter shared by the count loops and the emit loops:
  * mode RESOLVE: all original pairs; SUBST: a != b; CORE: !a || !b (bounded.cpp:205,235; function.hpp:109) */
 SG_HD bool sg_pair_ok(int mode, bool a, bool b)
 {
     return mode == SG_VE_RESOLVE ? true : (mode == SG_VE_SUBST ? (a != b) : (!a || !b));
 }
 
-SG_HD void sg_count_lits_before(const SgView &v, uint32_t lit, int &n)
+SG_HD int sg_count_lits_before(const SgView &v, const SgLane &L, uint32_t lit)
 {   /* simplify.hpp:288-296 */
     const int len = (int)v.ot_len[lit];
     const uint32_t *d = sg_list(v, lit);
-    for (int i = 0; i < len; ++i) if (sg_original(v, d[i])) n += SG_SIZE(v, d[i]);
+    int n = 0;
+    for (int i = (int)L.lane; i < len; i += (int)L.width) if (sg_original(v, d[i])) n += SG_SIZE(v, d[i]);
+    return sg_wsum(n);
 }
 
 /* countSubstituted (simplify.hpp:298-328) / countMinResolvents (function.hpp:95-126) /
- * countResolvents bounded (simplify.hpp:355-383): returns TRUE when the bound is EXCEEDED. */
-SG_HDN inline bool sg_count_bounded(const SgView &v, int mode, uint32_t x, int clsbefore, uint32_t me, uint32_t other,
-                                    int &nAddedCls, int &nAddedLits)
+ * countResolvents bounded (simplify.hpp:355-383) / countResolvents 1xm (simplify.hpp:330-353,
+ * clsbefore < 0 = no clause bound).  Returns TRUE when a bound is EXCEEDED.  The pair space is
+ * split over the lanes: the sums are order free, and "some prefix exceeds the clause bound" is
+ * equivalent to "the total exceeds it", so the verdict is the sequential one; on TRUE only
+ * nAddedCls != 0 is relied upon by the caller (bounded.cpp:105,120,133,153), which holds. */
+SG_HDN inline bool sg_count_pairs(const SgView &v, const SgLane &L, int mode, uint32_t x, int clsbefore, uint32_t me,
+                                  uint32_t other, int &nAddedCls, int &nAddedLits)
 {
     const int rlimit = v.o.ve_clause_max;
     const int nme = (int)v.ot_len[me], noth = (int)v.ot_len[other];
     const uint32_t *dm = sg_list(v, me), *dt = sg_list(v, other);
-    for (int i = 0; i < nme; ++i) {
-        const sg_u4 hi = v.hdr[dm[i]];
-        if (hi.z & SG_ST_MASK) continue;
-        const bool a = (hi.z & SG_MOLTEN) != 0;
-        for (int j = 0; j < noth; ++j) {
+    const long long total = (long long)nme * noth;
+    const long long chunk = (long long)L.width * 8;
+    int cnt = 0, lits = 0;
+    for (long long base = 0; base < total; base += chunk) {
+        int c1 = 0, l1 = 0;
+        bool over = false;
+        for (int k = 0; k < 8; ++k) {
+            const long long q = base + (long long)k * L.width + L.lane;
+            if (q >= total) break;
+            const int i = (int)(q / noth), j = (int)(q - (long long)i * noth);
+            const sg_u4 hi = v.hdr[dm[i]];
+            if (hi.z & SG_ST_MASK) continue;
             const sg_u4 hj = v.hdr[dt[j]];
             if (hj.z & SG_ST_MASK) continue;
-            const bool b = (hj.z & SG_MOLTEN) != 0;
-            int rsize;
-            if (sg_pair_ok(mode, a, b) &&
-                (rsize = sg_merge_count(x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y)) > 1) {
-                if (++nAddedCls > clsbefore || (rlimit && rsize > rlimit)) return true;
-                nAddedLits += rsize;
+            if (!sg_pair_ok(mode, (hi.z & SG_MOLTEN) != 0, (hj.z & SG_MOLTEN) != 0)) continue;
+            const int rsize = sg_merge_count(x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y);
+            if (rsize > 1) {
+                c1++; l1 += rsize;
+                if (rlimit && rsize > rlimit) over = true;
             }
         }
+        cnt += sg_wsum(c1);
+        lits += sg_wsum(l1);
+        const bool anyover = sg_ballot(over) != 0;
+        if (anyover || (clsbefore >= 0 && cnt > clsbefore)) {
+            nAddedCls = cnt > 0 ? cnt : 1;
+            nAddedLits = lits;
+            return true;
+        }
     }
-    if (v.o.ve_lbound_en) {
-        int before = 0;
-        sg_count_lits_before(v, me, before);
-        sg_count_lits_before(v, other, before);
+    nAddedCls = cnt;
+    nAddedLits = lits;
+    if (clsbefore >= 0 && v.o.ve_lbound_en) {
+        const int before = sg_count_lits_before(v, L, me) + sg_count_lits_before(v, L, other);
         if (nAddedLits > before) return true;
     }
     return false;
 }
 
-/* countResolvents for the 1xm case (simplify.hpp:330-353): only the size bound; TRUE = ok */
-SG_HDN inline bool sg_count_simple(const SgView &v, uint32_t x, uint32_t me, uint32_t other, int &nAddedCls, int &nAddedLits)
+/* clears the molten flag of the list entries selected by pred; one entry per lane */
+template <class P> SG_HD void sg_freeze_if(const SgView &v, const SgLane &L, uint32_t lit, P pred)
 {
-    const int rlimit = v.o.ve_clause_max;
-    const int nme = (int)v.ot_len[me], noth = (int)v.ot_len[other];
-    const uint32_t *dm = sg_list(v, me), *dt = sg_list(v, other);
-    for (int i = 0; i < nme; ++i) {
-        const sg_u4 hi = v.hdr[dm[i]];
-        if (hi.z & SG_ST_MASK) continue;
-        for (int j = 0; j < noth; ++j) {
-            const sg_u4 hj = v.hdr[dt[j]];
-            if (hj.z & SG_ST_MASK) continue;
-            const int rsize = sg_merge_count(x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y);
-            if (rsize > 1) {
-                if (rlimit && rsize > rlimit) return false;
-                nAddedCls++;
-                nAddedLits += rsize;
-            }
-        }
+    const int n = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    sg_wsync();
+    for (int i = (int)L.lane; i < n; i += (int)L.width) {
+        const sg_u4 h = v.hdr[d[i]];
+        if ((h.z & SG_MOLTEN) && pred(h)) v.hdr[d[i]].z = h.z & ~SG_MOLTEN;
     }
-    return true;
+    sg_wsync();
 }
-
-SG_HD void sg_freeze_binaries(const SgView &v, uint32_t lit)
+SG_HD void sg_freeze_binaries(const SgView &v, const SgLane &L, uint32_t lit)
 {   /* simplify.hpp:262-269 */
-    const int n = (int)v.ot_len[lit];
-    const uint32_t *d = sg_list(v, lit);
-    for (int i = 0; i < n; ++i) if (sg_original(v, d[i]) && SG_SIZE(v, d[i]) == 2) sg_freeze(v, d[i]);
+    sg_freeze_if(v, L, lit, [](const sg_u4 &h) { return !(h.z & SG_ST_MASK) && h.y == 2; });
 }
-SG_HD void sg_freeze_all(const SgView &v, uint32_t lit)
+SG_HD void sg_freeze_all(const SgView &v, const SgLane &L, uint32_t lit)
 {   /* simplify.hpp:271-278 */
-    const int n = (int)v.ot_len[lit];
-    const uint32_t *d = sg_list(v, lit);
-    for (int i = 0; i < n; ++i) if (sg_original(v, d[i])) sg_freeze(v, d[i]);
+    sg_freeze_if(v, L, lit, [](const sg_u4 &h) { return !(h.z & SG_ST_MASK); });
+}
+SG_HD void sg_melt1(const SgView &v, const SgLane &L, uint32_t c)
+{
+    sg_wsync();
+    if (L.lane == 0) sg_melt(v, c);
+    sg_wsync();
+}
+SG_HD void sg_freeze1(const SgView &v, const SgLane &L, uint32_t c)
+{
+    sg_wsync();
+    if (L.lane == 0) sg_freeze(v, c);
+    sg_wsync();
 }
 
-/* equivalence / inverter gate (equivalence.hpp:103-161) */
-SG_HDN inline uint32_t sg_find_bn_gate(const SgView &v, uint32_t p, uint32_t n)
+/* equivalence / inverter gate (equivalence.hpp:103-161).  find_sfanin melts original binaries
+ * of P until it has seen two; with two or more the gate is rejected and freezeBinaries(P) clears
+ * them again, so only the one-binary case leaves a mark. */
+SG_HDN inline uint32_t sg_find_bn_gate(const SgView &v, const SgLane &L, uint32_t p, uint32_t n)
 {
     const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
     const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
     if (SG_SIZE(v, dp[0]) > 2 || SG_SIZE(v, dn[0]) > 2) return 0;
-    uint32_t imp = 0;
-    {   /* find_sfanin */
-        int nImps = 0;
-        bool many = false;
-        for (int i = 0; i < np; ++i) {
-            const uint32_t c = dp[i];
-            if (sg_original(v, c) && SG_SIZE(v, c) == 2) {
-                const uint32_t *l = SG_LITS(v, c);
-                imp = SG_FLIP(l[0] ^ l[1] ^ p);
-                sg_melt(v, c);
-                nImps++;
-            }
-            if (nImps > 1) { many = true; break; }
-        }
-        if (many) imp = 0;
+    int nbin = 0, first_bin = -1;
+    for (int base = 0; base < np; base += (int)L.width) {
+        const int idx = base + (int)L.lane;
+        bool b = false;
+        if (idx < np) { const sg_u4 h = v.hdr[dp[idx]]; b = !(h.z & SG_ST_MASK) && h.y == 2; }
+        const uint32_t m = sg_ballot(b);
+        if (m && first_bin < 0) first_bin = base + sg_ffs(m) - 1;
+        nbin += sg_popc(m);
+        if (nbin > 1) break;
     }
-    if (imp) {
-        uint32_t first = imp, second = n;
-        const uint32_t def = imp;
-        if (second < first) { first = second; second = def; }
-        for (int i = 0; i < nn; ++i) {
-            const uint32_t c = dn[i];
-            if (sg_original(v, c) && SG_SIZE(v, c) == 2) {
-                const uint32_t *l = SG_LITS(v, c);
-                if (l[0] == first && l[1] == second) { sg_melt(v, c); return def; }
-            }
-        }
-    }
-    sg_freeze_binaries(v, p);
-    return 0;
+    if (nbin != 1) return 0;      /* 0: nothing melted; >1: melted then frozen again (net nothing) */
+    const uint32_t cb = dp[first_bin];
+    const uint32_t *lb = SG_LITS(v, cb);
+    const uint32_t def = SG_FLIP(lb[0] ^ lb[1] ^ p);
+    uint32_t first = def, second = n;
+    if (second < first) { first = second; second = def; }
+    const int k = sg_find_first(L, nn, [&](int i) {
+        const sg_u4 h = v.hdr[dn[i]];
+        if ((h.z & SG_ST_MASK) || h.y != 2) return false;
+        const uint32_t *l = v.lits + h.x;
+        return l[0] == first && l[1] == second;
+    });
+    if (k < 0) return 0;          /* the binary of P was melted and frozen again: net nothing */
+    sg_wsync();
+    if (L.lane == 0) { sg_melt(v, cb); sg_melt(v, dn[k]); }
+    sg_wsync();
+    return def;
 }
 
 /* AND/OR gate (and.hpp:27-111); `out_c` is this variable's scratch slice */
-SG_HDN inline bool sg_find_ao_gate(const SgView &v, uint32_t dx, uint32_t fx, uint32_t *out_c, int orgCls,
+SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx, uint32_t fx, uint32_t *out_c, int orgCls,
                                    int &nAddedCls, int &nAddedLits)
 {
     const int nd = (int)v.ot_len[dx], nf = (int)v.ot_len[fx];
@@ -789,46 +910,55 @@ SG_HDN inline bool sg_find_ao_gate(const SgView &v, uint32_t dx, uint32_t fx, ui
     if (SG_SIZE(v, dd[0]) > 2 || SG_SIZE(v, df[nf - 1]) < 3) return false;
     uint32_t sig = 0;
     int nout = 0;
-    for (int i = 0; i < nd; ++i) {           /* find_fanin */
-        const uint32_t c = dd[i];
-        if (sg_original(v, c) && SG_SIZE(v, c) == 2) {
-            const uint32_t *l = SG_LITS(v, c);
-            const uint32_t imp = SG_FLIP(l[0] ^ l[1] ^ dx);
-            out_c[nout++] = imp;
-            sig |= SG_HASH(imp);
-            sg_melt(v, c);
+    sg_wsync();
+    for (int base = 0; base < nd; base += (int)L.width) {        /* find_fanin (and.hpp:27-44) */
+        const int idx = base + (int)L.lane;
+        bool b = false;
+        uint32_t imp = 0, c = 0;
+        if (idx < nd) {
+            c = dd[idx];
+            const sg_u4 h = v.hdr[c];
+            b = !(h.z & SG_ST_MASK) && h.y == 2;
+            if (b) { const uint32_t *l = v.lits + h.x; imp = SG_FLIP(l[0] ^ l[1] ^ dx); }
         }
+        const uint32_t m = sg_ballot(b);
+        if (b) {
+            out_c[nout + sg_popc(m & ((1u << L.lane) - 1u))] = imp;
+            v.hdr[c].z |= SG_MOLTEN;
+        }
+        sig |= sg_wor(b ? SG_HASH(imp) : 0u);
+        nout += sg_popc(m);
     }
+    sg_wsync();
     if (nout > 1) {
-        out_c[nout++] = fx;
+        if (L.lane == 0) { out_c[nout] = fx; sg_sort_lits(out_c, nout + 1); }
+        nout++;
         sig |= SG_HASH(fx);
-        sg_sort_lits(out_c, nout);
+        sg_wsync();
         const uint32_t x = SG_ABS(dx);
-        for (int i = 0; i < nf; ++i) {
-            const uint32_t c = df[i];
-            if (sg_original(v, c) && SG_SIZE(v, c) == nout && sg_sig_sub(SG_SIG(v, c), sig)) {
-                const uint32_t *l = SG_LITS(v, c);
-                bool eq = true;
-                for (int k = 0; k < nout; ++k) if (l[k] != out_c[k]) { eq = false; break; }
-                if (!eq) continue;
-                sg_melt(v, c);
-                nAddedCls = 0, nAddedLits = 0;
-                if (sg_count_bounded(v, SG_VE_SUBST, x, orgCls, dx, fx, nAddedCls, nAddedLits)) {
-                    sg_freeze(v, c);
-                    break;
-                }
-                return true;
-            }
+        const int k = sg_find_first(L, nf, [&](int i) {
+            const sg_u4 h = v.hdr[df[i]];
+            if ((h.z & SG_ST_MASK) || (int)h.y != nout || !sg_sig_sub(h.w, sig)) return false;
+            const uint32_t *l = v.lits + h.x;
+            for (int q = 0; q < nout; ++q) if (l[q] != out_c[q]) return false;
+            return true;
+        });
+        if (k >= 0) {
+            const uint32_t c = df[k];
+            sg_melt1(v, L, c);
+            nAddedCls = 0, nAddedLits = 0;
+            if (!sg_count_pairs(v, L, SG_VE_SUBST, x, orgCls, dx, fx, nAddedCls, nAddedLits)) return true;
+            sg_freeze1(v, L, c);
         }
     }
-    sg_freeze_binaries(v, dx);
+    sg_freeze_binaries(v, L, dx);
     return false;
 }
 
 /* ITE gate (ifthenelse.hpp:26-125) */
 SG_HD void sg_swap(uint32_t &a, uint32_t &b) { const uint32_t t = a; a = b; b = t; }
 
-SG_HDN inline uint32_t sg_fast_equality_check(const SgView &v, uint32_t x, uint32_t y, uint32_t z)
+SG_HDN inline uint32_t sg_fast_equality_check(const SgView &v, const SgLane &L, uint32_t x, uint32_t y, uint32_t z)
 {   /* returns clause id or 0xFFFFFFFF */
     if (v.ot_len[y] > v.ot_len[z]) sg_swap(y, z);
     if (v.ot_len[x] > v.ot_len[y]) sg_swap(x, y);
@@ -838,18 +968,17 @@ SG_HDN inline uint32_t sg_fast_equality_check(const SgView &v, uint32_t x, uint3
     { uint32_t a = y < z ? y : z, b = y < z ? z : y; y = a; z = b; }
     { uint32_t a = x < z ? x : z, b = x < z ? z : x; x = a; z = b; }
     { uint32_t a = x < y ? x : y, b = x < y ? y : x; x = a; y = b; }
-    for (int i = 0; i < n; ++i) {
+    const int k = sg_find_first(L, n, [&](int i) {
         const sg_u4 h = v.hdr[d[i]];
-        if (h.z & SG_MOLTEN) continue;
-        if (!(h.z & SG_ST_MASK) && h.y == 3) {
-            const uint32_t *l = v.lits + h.x;
-            if (l[0] == x && l[1] == y && l[2] == z) return d[i];
-        }
-    }
-    return 0xFFFFFFFFu;
+        if ((h.z & SG_MOLTEN) || (h.z & SG_ST_MASK) || h.y != 3) return false;
+        const uint32_t *l = v.lits + h.x;
+        return l[0] == x && l[1] == y && l[2] == z;
+    });
+    return k < 0 ? 0xFFFFFFFFu : d[k];
 }
 
-SG_HDN inline bool sg_find_ite_gate(const SgView &v, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls, int &nAddedLits)
+SG_HDN inline bool sg_find_ite_gate(const SgView &v, const SgLane &L, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls,
+                                    int &nAddedLits)
 {
     const int nd = (int)v.ot_len[dx];
     const uint32_t *dd = sg_list(v, dx);
@@ -872,14 +1001,18 @@ SG_HDN inline bool sg_find_ite_gate(const SgView &v, uint32_t dx, uint32_t fx, i
             if (SG_ABS(yi) == SG_ABS(zj)) sg_swap(yj, zj);
             if (SG_ABS(zi) == SG_ABS(zj)) continue;
             if (yi != SG_FLIP(yj)) continue;
-            const uint32_t d1 = sg_fast_equality_check(v, fx, yi, SG_FLIP(zi));
+            const uint32_t d1 = sg_fast_equality_check(v, L, fx, yi, SG_FLIP(zi));
             if (d1 == 0xFFFFFFFFu) continue;
-            const uint32_t d2 = sg_fast_equality_check(v, fx, yj, SG_FLIP(zj));
+            const uint32_t d2 = sg_fast_equality_check(v, L, fx, yj, SG_FLIP(zj));
             if (d2 == 0xFFFFFFFFu) continue;
-            sg_melt(v, ci), sg_melt(v, cj), sg_melt(v, d1), sg_melt(v, d2);
+            sg_wsync();
+            if (L.lane == 0) { sg_melt(v, ci), sg_melt(v, cj), sg_melt(v, d1), sg_melt(v, d2); }
+            sg_wsync();
             nAddedCls = 0, nAddedLits = 0;
-            if (sg_count_bounded(v, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
-                sg_freeze(v, ci), sg_freeze(v, cj), sg_freeze(v, d1), sg_freeze(v, d2);
+            if (sg_count_pairs(v, L, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
+                sg_wsync();
+                if (L.lane == 0) { sg_freeze(v, ci), sg_freeze(v, cj), sg_freeze(v, d1), sg_freeze(v, d2); }
+                sg_wsync();
                 return false;
             }
             return true;
@@ -889,26 +1022,16 @@ SG_HDN inline bool sg_find_ite_gate(const SgView &v, uint32_t dx, uint32_t fx, i
 }
 
 /* XOR gate (xor.hpp:26-181) */
-SG_HD void sg_freeze_arities(const SgView &v, uint32_t a, uint32_t b)
-{
-    for (int s = 0; s < 2; ++s) {
-        const uint32_t lit = s ? b : a;
-        const int n = (int)v.ot_len[lit];
-        const uint32_t *d = sg_list(v, lit);
-        for (int i = 0; i < n; ++i) if (SG_SIZE(v, d[i]) > 2 && sg_molten(v, d[i])) sg_freeze(v, d[i]);
-    }
+SG_HD void sg_freeze_arities(const SgView &v, const SgLane &L, uint32_t a, uint32_t b)
+{   /* xor.hpp:32-44 */
+    sg_freeze_if(v, L, a, [](const sg_u4 &h) { return (int)h.y > 2; });
+    sg_freeze_if(v, L, b, [](const sg_u4 &h) { return (int)h.y > 2; });
 }
 
-SG_HDN inline bool sg_make_arity(const SgView &v, uint32_t &parity, uint32_t *literals, int size)
-{
+SG_HDN inline bool sg_make_arity(const SgView &v, const SgLane &L, uint32_t &parity, uint32_t *literals, int size)
+{   /* xor.hpp:70-102 */
     const uint32_t oldparity = parity;
-    do { ++parity; } while (
-#if defined(__CUDA_ARCH__)
-        __popc(parity) & 1
-#else
-        __builtin_parity(parity)
-#endif
-    );
+    do { ++parity; } while (sg_popc(parity) & 1);
     for (int k = 0; k < size; ++k) {
         const uint32_t bit = 1u << k;
         if ((parity & bit) != (oldparity & bit)) literals[k] = SG_FLIP(literals[k]);
@@ -921,23 +1044,24 @@ SG_HDN inline bool sg_make_arity(const SgView &v, uint32_t &parity, uint32_t *li
     }
     const int n = (int)v.ot_len[best];
     const uint32_t *d = sg_list(v, best);
-    for (int i = 0; i < n; ++i) {
+    const int k = sg_find_first(L, n, [&](int i) {
         const sg_u4 h = v.hdr[d[i]];
-        if (!(h.z & SG_ST_MASK) && (int)h.y == size) {
-            const uint32_t *l = v.lits + h.x;
-            bool all = true;
-            for (int a = 0; a < size && all; ++a) {     /* checkArity (xor.hpp:53-68) */
-                bool found = false;
-                for (int b = 0; b < size; ++b) if (l[a] == literals[b]) { found = true; break; }
-                all = found;
-            }
-            if (all) { sg_melt(v, d[i]); return true; }
+        if ((h.z & SG_ST_MASK) || (int)h.y != size) return false;
+        const uint32_t *l = v.lits + h.x;
+        for (int a = 0; a < size; ++a) {            /* checkArity (xor.hpp:53-68) */
+            bool found = false;
+            for (int b = 0; b < size; ++b) if (l[a] == literals[b]) { found = true; break; }
+            if (!found) return false;
         }
-    }
-    return false;
+        return true;
+    });
+    if (k < 0) return false;
+    sg_melt1(v, L, d[k]);
+    return true;
 }
 
-SG_HDN inline bool sg_find_xor_gate(const SgView &v, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls, int &nAddedLits)
+SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls,
+                                    int &nAddedLits)
 {
     const int nd = (int)v.ot_len[dx], nf = (int)v.ot_len[fx];
     const uint32_t *dd = sg_list(v, dx), *df = sg_list(v, fx);
@@ -946,24 +1070,25 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, uint32_t dx, uint32_t fx, i
     int arity = SG_SIZE(v, dd[0]) - 1;
     if (arity > maxarity) return false;
     const uint32_t var = SG_ABS(dx);
-    uint32_t out_c[32];
+    uint32_t out_c[24];
     for (int i = 0; i < nd; ++i) {
         const uint32_t ci = dd[i];
         if (!sg_original(v, ci)) continue;
         const int size = SG_SIZE(v, ci);
         arity = size - 1;
-        if (size < 3 || arity > maxarity || size > 32) continue;
+        if (size < 3 || arity > maxarity || size > 24) continue;
         const uint32_t *l = SG_LITS(v, ci);
         for (int k = 0; k < size; ++k) out_c[k] = l[k];
         uint32_t parity = 0;
         int itargets = 1 << arity;
-        while (--itargets && sg_make_arity(v, parity, out_c, size));
-        if (itargets) sg_freeze_arities(v, dx, fx);
+        bool melted_any = false;
+        while (--itargets && sg_make_arity(v, L, parity, out_c, size)) melted_any = true;
+        if (itargets) { if (melted_any) sg_freeze_arities(v, L, dx, fx); }
         else {
-            sg_melt(v, ci);
+            sg_melt1(v, L, ci);
             nAddedCls = 0, nAddedLits = 0;
-            if (sg_count_bounded(v, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
-                sg_freeze_arities(v, dx, fx);
+            if (sg_count_pairs(v, L, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
+                sg_freeze_arities(v, L, dx, fx);
                 break;
             }
             return true;
@@ -1008,27 +1133,28 @@ SG_HD unsigned long long sg_fun_list_word(const SgView &v, uint32_t lit, int upt
     }
     return f;
 }
-SG_HD bool sg_fun_in_core(const SgView &v, uint32_t lit)
+SG_HD bool sg_fun_in_core(const SgView &v, const SgLane &L, uint32_t lit)
 {   /* buildfuntab bails out on the first literal outside the 12 marked variables (function.hpp:150) */
     const int n = (int)v.ot_len[lit];
     const uint32_t *d = sg_list(v, lit);
-    for (int i = 0; i < n; ++i) {
-        if (sg_learnt(v, d[i])) continue;
-        const uint32_t *l = SG_LITS(v, d[i]);
-        const int size = SG_SIZE(v, d[i]);
-        for (int k = 0; k < size; ++k) {
-            if (l[k] == lit) continue;
-            if (v.marks[SG_ABS(l[k])] < 0) return false;
+    const int k = sg_find_first(L, n, [&](int i) {
+        const sg_u4 h = v.hdr[d[i]];
+        if (h.z & SG_LEARNT) return false;
+        const uint32_t *l = v.lits + h.x;
+        for (int q = 0; q < (int)h.y; ++q) {
+            if (l[q] == lit) continue;
+            if (v.marks[SG_ABS(l[q])] < 0) return true;
         }
-    }
-    return true;
+        return false;
+    });
+    return k < 0;
 }
 
-SG_HDN inline bool sg_find_fun_gate(const SgView &v, uint32_t p, int orgCls, int &nAddedCls, int &nAddedLits)
+SG_HDN inline bool sg_find_fun_gate(const SgView &v, const SgLane &L, uint32_t p, int orgCls, int &nAddedCls, int &nAddedLits)
 {
     if (!v.o.ve_fun_en) return false;
     const uint32_t n = p | 1u;
-    if (!sg_fun_in_core(v, p) || !sg_fun_in_core(v, n)) return false;
+    if (!sg_fun_in_core(v, L, p) || !sg_fun_in_core(v, L, n)) return false;
     const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
     unsigned long long unsat = 0, allzero = 0;
     for (uint32_t w = 0; w < 64; ++w) {       /* collapsefun (function.hpp:198-209) */
@@ -1037,7 +1163,7 @@ SG_HDN inline bool sg_find_fun_gate(const SgView &v, uint32_t p, int orgCls, int
         unsat |= (b | c);
         allzero |= (b & c);
     }
-    if (!unsat) { sg_set_flag(&v.sc->unsat); return true; }
+    if (!unsat) { if (L.lane == 0) sg_set_flag(&v.sc->unsat); return true; }
     if (allzero) return false;
     bool core = false;
     const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
@@ -1048,94 +1174,103 @@ SG_HDN inline bool sg_find_fun_gate(const SgView &v, uint32_t p, int orgCls, int
             const unsigned long long negw = sg_fun_list_word(v, n, nn, w, ~0ull);
             if (sg_fun_list_word(v, p, i, w, negw)) isfalse = false;
         }
-        if (isfalse) { sg_melt(v, dp[i]); core = true; }
+        if (isfalse) { sg_melt1(v, L, dp[i]); core = true; }
     }
     for (int i = nn - 1; i >= 0; --i) {
         if (!sg_original(v, dn[i])) continue;
         bool isfalse = true;
         for (uint32_t w = 0; w < 64 && isfalse; ++w)
             if (sg_fun_list_word(v, n, i, w, ~0ull)) isfalse = false;
-        if (isfalse) { sg_melt(v, dn[i]); core = true; }
+        if (isfalse) { sg_melt1(v, L, dn[i]); core = true; }
     }
     nAddedCls = 0, nAddedLits = 0;
-    if (sg_count_bounded(v, SG_VE_CORE, SG_ABS(p), orgCls, p, n, nAddedCls, nAddedLits)) {
-        if (core) { sg_freeze_all(v, p); sg_freeze_all(v, n); }
+    if (sg_count_pairs(v, L, SG_VE_CORE, SG_ABS(p), orgCls, p, n, nAddedCls, nAddedLits)) {
+        if (core) { sg_freeze_all(v, L, p); sg_freeze_all(v, L, n); }
         return false;
     }
     return true;
 }
 
 /* model words written by toblivion / save_BN_gate for this variable (simplify.hpp:393-423) */
-SG_HD uint32_t sg_model_words(const SgView &v, uint32_t p, int pOrgs, int nOrgs)
+SG_HD uint32_t sg_model_words(const SgView &v, const SgLane &L, uint32_t p, int pOrgs, int nOrgs)
 {
     const uint32_t side = (pOrgs > nOrgs) ? (p | 1u) : p;
     const int n = (int)v.ot_len[side];
     const uint32_t *d = sg_list(v, side);
-    uint32_t words = 2;
-    for (int i = 0; i < n; ++i) if (sg_original(v, d[i])) words += (uint32_t)SG_SIZE(v, d[i]) + 1u;
-    return words;
+    int words = 0;
+    for (int i = (int)L.lane; i < n; i += (int)L.width) if (sg_original(v, d[i])) words += SG_SIZE(v, d[i]) + 1;
+    return (uint32_t)sg_wsum(words) + 2u;
+}
+
+SG_HD int sg_count_orgs(const SgView &v, const SgLane &L, uint32_t lit)
+{   /* simplify.hpp:280-286 */
+    const int n = (int)v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    int c = 0;
+    for (int i = (int)L.lane; i < n; i += (int)L.width) if (sg_original(v, d[i])) c++;
+    return sg_wsum(c);
 }
 
 SG_HDN inline void sg_ve_count_item(const SgView &v, uint32_t eidx)
 {
+    const SgLane L = sg_lane_ctx();
     const uint32_t var = v.elected[eidx];
     const uint32_t p = 2 * var, n = p | 1u;
     const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
-    const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
     int pOrgs = 0, nOrgs = 0, nAddedCls = 0, nAddedLits = 0;
     if (v.o.firstcall) { pOrgs = np; nOrgs = nn; }
-    else {
-        for (int i = 0; i < np; ++i) if (sg_original(v, dp[i])) pOrgs++;
-        for (int i = 0; i < nn; ++i) if (sg_original(v, dn[i])) nOrgs++;
-    }
+    else { pOrgs = sg_count_orgs(v, L, p); nOrgs = sg_count_orgs(v, L, n); }
     uint32_t type = SG_VE_NONE, aux = 0;
+    unsigned long long *stat = nullptr;
     uint32_t def;
     if (!pOrgs || !nOrgs) {
         type = SG_VE_PURE;
-        sg_atomic_add64(&v.sc->pures, 1);
-    } else if ((def = sg_find_bn_gate(v, p, n)) != 0) {
+        stat = &v.sc->pures;
+    } else if ((def = sg_find_bn_gate(v, L, p, n)) != 0) {
         type = SG_VE_INVERTER;
         aux = def;
-        sg_atomic_add64(&v.sc->inverters, 1);
-    } else if ((pOrgs == 1 || nOrgs == 1) && sg_count_simple(v, var, p, n, nAddedCls, nAddedLits)) {
+        stat = &v.sc->inverters;
+    } else if ((pOrgs == 1 || nOrgs == 1) && !sg_count_pairs(v, L, SG_VE_RESOLVE, var, -1, p, n, nAddedCls, nAddedLits)) {
         type = SG_VE_RESOLVE;
-        sg_atomic_add64(&v.sc->resolutions, 1);
+        stat = &v.sc->resolutions;
     } else {
         nAddedCls = 0, nAddedLits = 0;
         const int orgCls = pOrgs + nOrgs;
         uint32_t *out_c = v.scratch + v.scr_off[eidx];
         if (orgCls > 2) {
-            if (sg_find_ao_gate(v, n, p, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
-            else if (!nAddedCls && sg_find_ao_gate(v, p, n, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
-            if (type) sg_atomic_add64(&v.sc->andors, 1);
+            if (sg_find_ao_gate(v, L, n, p, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            else if (!nAddedCls && sg_find_ao_gate(v, L, p, n, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            if (type) stat = &v.sc->andors;
         }
         if (!type && orgCls > 3) {
-            if (sg_find_ite_gate(v, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->ites, 1); }
-            else if (!nAddedCls && sg_find_ite_gate(v, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->ites, 1); }
-            else if (sg_find_xor_gate(v, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->xors, 1); }
-            else if (!nAddedCls && sg_find_xor_gate(v, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; sg_atomic_add64(&v.sc->xors, 1); }
+            if (sg_find_ite_gate(v, L, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->ites; }
+            else if (!nAddedCls && sg_find_ite_gate(v, L, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->ites; }
+            else if (sg_find_xor_gate(v, L, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->xors; }
+            else if (!nAddedCls && sg_find_xor_gate(v, L, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->xors; }
         }
-        if (!type && orgCls > 2 && sg_find_fun_gate(v, p, orgCls, nAddedCls, nAddedLits)) {
+        if (!type && orgCls > 2 && sg_find_fun_gate(v, L, p, orgCls, nAddedCls, nAddedLits)) {
             if (*(volatile uint32_t *)&v.sc->unsat) { type = SG_VE_NONE; nAddedCls = 0; nAddedLits = 0; }
-            else { type = SG_VE_CORE; sg_atomic_add64(&v.sc->funs, 1); }
+            else { type = SG_VE_CORE; stat = &v.sc->funs; }
         } else if (!type && !nAddedCls) {
-            if (!sg_count_bounded(v, SG_VE_RESOLVE, var, orgCls, p, n, nAddedCls, nAddedLits)) {
+            if (!sg_count_pairs(v, L, SG_VE_RESOLVE, var, orgCls, p, n, nAddedCls, nAddedLits)) {
                 type = SG_VE_RESOLVE;
-                sg_atomic_add64(&v.sc->resolutions, 1);
+                stat = &v.sc->resolutions;
             }
         }
     }
     uint32_t ncls = 0, nlits = 0, nmodel = 0;
     if (type != SG_VE_NONE) {
-        nmodel = sg_model_words(v, p, pOrgs, nOrgs);
+        nmodel = sg_model_words(v, L, p, pOrgs, nOrgs);
         if (type == SG_VE_RESOLVE || type == SG_VE_SUBST || type == SG_VE_CORE) { ncls = (uint32_t)nAddedCls; nlits = (uint32_t)nAddedLits; }
-        aux |= 0;
     }
-    v.ve_type[eidx] = type | ((uint32_t)(pOrgs > nOrgs) << 8);
-    v.ve_aux[eidx] = aux;
-    v.ve_ncls[eidx] = ncls;
-    v.ve_nlits[eidx] = nlits;
-    v.ve_nmodel[eidx] = nmodel;
+    if (L.lane == 0) {
+        if (stat) sg_atomic_add64(stat, 1);
+        v.ve_type[eidx] = type | ((uint32_t)(pOrgs > nOrgs) << 8);
+        v.ve_aux[eidx] = aux;
+        v.ve_ncls[eidx] = ncls;
+        v.ve_nlits[eidx] = nlits;
+        v.ve_nmodel[eidx] = nmodel;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -288,7 +288,10 @@ __global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, cons
 /* ---------------------------------------------------------------------------------------------- */
 template <int KIND> __global__ void k_items(SgView v, uint32_t n)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    /* SUB and the BVE decision run one warp per elected variable, everything else one thread */
+    const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = warp_item ? (t >> 5) : t;
     if (i >= n) return;
     if (KIND == SGK_IDSORT) sg_idsort_item(v, i);
     else if (KIND == SGK_REDUCE) sg_reduce_item(v, i);
@@ -548,8 +551,8 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_ELECT_PREP: LAUNCH(k_items<SGK_ELECT_PREP>, blocks_for(n), TPB, s, v, n); break;
     case SGK_SORTOT: LAUNCH(k_items<SGK_SORTOT>, blocks_for(n, 64), 64, s, v, n); break;
     case SGK_SCRATCH_LEN: LAUNCH(k_items<SGK_SCRATCH_LEN>, blocks_for(n), TPB, s, v, n); break;
-    case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(n, 64), 64, s, v, n); break;
-    case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(32ull * n, 128), 128, s, v, n); break;
+    case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_EMIT: LAUNCH(k_items<SGK_VE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
     default: snprintf(g_err, sizeof g_err, "be_items: bad kind %d", kind);
     }
