@@ -70,7 +70,8 @@ void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t
 size_t be_sort_tmp_words(uint32_t n);
 void be_rank(void *s, const SgView &v);                                           /* rank[order[r]] = r */
 /* election rounds */
-void be_elect_init(void *s, const SgView &v, uint32_t *wl);                        /* fills wl, sc->wl_count[0] */
+/* worklist of the still-undecided candidates with rank in [r0, r1): fills wl, sc->wl_count[0] (must be 0) */
+void be_elect_batch(void *s, const SgView &v, uint32_t r0, uint32_t r1, uint32_t *wl);
 void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity);
 void be_acting_flags(void *s, const SgView &v, uint32_t *flags_acting, uint32_t *flags_elected);   /* per rank position */
 void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe);

@@ -383,28 +383,57 @@ SG_HD bool sg_break_cond(const SgView &v, uint32_t var)
     return v.ot_len[2 * var] >= v.pmax && v.ot_len[2 * var + 1] >= v.nmax;
 }
 
+/* election word of a variable: rank in the sorted candidate order (low 29 bits) | status << 29 */
+#define SG_ER_RANK(w)  ((w) & 0x1FFFFFFFu)
+#define SG_ER_STAT(w)  ((w) >> 29)
+#define SG_ER_MAKE(st, r) (((uint32_t)(st) << 29) | (r))
+
+SG_HD uint32_t sg_er_load(const SgView &v, uint32_t var) { return *(volatile uint32_t *)&v.rank[var]; }
+SG_HD void sg_er_set(const SgView &v, uint32_t var, uint32_t st)
+{
+    const uint32_t w = v.rank[var];
+#if defined(__CUDA_ARCH__)
+    __threadfence();
+#endif
+    *(volatile uint32_t *)&v.rank[var] = SG_ER_MAKE(st, SG_ER_RANK(w));
+}
+/* UNDECIDED -> FROZEN, and only that transition (an acting candidate freezing a neighbour) */
+SG_HD void sg_er_freeze(const SgView &v, uint32_t var, uint32_t w_undecided)
+{
+#if defined(__CUDA_ARCH__)
+    atomicCAS(&v.rank[var], w_undecided, SG_ER_MAKE(SG_E_FROZEN, SG_ER_RANK(w_undecided)));
+#else
+    if (v.rank[var] == w_undecided) v.rank[var] = SG_ER_MAKE(SG_E_FROZEN, SG_ER_RANK(w_undecided));
+#endif
+}
+
 /* static classification, one thread per variable (lcve.cpp:66-70) */
 SG_HD void sg_elect_prep_item(const SgView &v, uint32_t var)
 {
     const uint32_t ps = v.occ[2 * var], ns = v.occ[2 * var + 1];
-    uint8_t st;
+    const uint32_t r = SG_ER_RANK(v.rank[var]);
+    uint32_t st;
     if ((v.ifrozen && v.ifrozen[var]) || v.state[var] || (!ps && !ns)) st = SG_E_SKIP;
     else if (!sg_freezable(v, var)) {
         /* can never be frozen, and ot sizes >= occurrences >= mu: the loop ends here if reached */
         st = SG_E_BREAK;
-        sg_atomic_min(&v.sc->brk_rank, v.rank[var]);
+        sg_atomic_min(&v.sc->brk_rank, r);
     } else st = SG_E_UNDECIDED;
-    v.estat[var] = st;
+    v.rank[var] = SG_ER_MAKE(st, r);
 }
 
-/* returns true when the candidate stays undecided (goes to the next round's worklist) */
+/* One pull step for an undecided candidate of the current rank batch (every candidate of an
+ * earlier batch is decided).  Returns true when it stays undecided.  A candidate that turns
+ * out to act (depFreeze succeeded, lcve.cpp:76-78) freezes its still-undecided neighbours at
+ * once, so later batches never have to look at them. */
 SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
 {
-    const uint32_t rc = v.rank[cand];
-    if (rc > *(volatile uint32_t *)&v.sc->brk_rank) { v.estat[cand] = SG_E_SKIP; return false; }
+    const uint32_t wc = sg_er_load(v, cand);
+    if (SG_ER_STAT(wc) != SG_E_UNDECIDED) return false;       /* frozen by a push since it was queued */
+    const uint32_t rc = SG_ER_RANK(wc);
+    if (rc > *(volatile uint32_t *)&v.sc->brk_rank) { sg_er_set(v, cand, SG_E_SKIP); return false; }
     const int maxcsize = v.o.lcve_clause_max;
     bool blocked = false, fail[2] = { false, false };
-    uint32_t visits = 0;
     for (uint32_t side = 0; side < 2; ++side) {
         const uint32_t lit = 2 * cand + side;
         const int n = (int)v.ot_len[lit];
@@ -418,30 +447,46 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
             for (int k = 0; k < size; ++k) {
                 const uint32_t other = l[k], u = SG_ABS(other);
                 if (u == cand) continue;
-                visits++;
-                if (v.rank[u] > rc) continue;
-                const uint8_t s = *(volatile uint8_t *)&v.estat[u];
+                const uint32_t w = sg_er_load(v, u);
+                if (SG_ER_RANK(w) > rc) continue;
+                const uint32_t s = SG_ER_STAT(w);
                 if (s == SG_E_UNDECIDED) blocked = true;
                 else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other))) {
-                    v.estat[cand] = SG_E_FROZEN;
+                    sg_er_set(v, cand, SG_E_FROZEN);
                     return false;
                 }
             }
         }
     }
-#if !defined(__CUDA_ARCH__)
-    v.sc->elect_visits += visits;
-#endif
     if (blocked) return true;
-    uint8_t st;
+    uint32_t st;
     if (sg_break_cond(v, cand)) { st = SG_E_BREAK; sg_atomic_min(&v.sc->brk_rank, rc); }
     else if (fail[0]) st = SG_E_NONE;
     else if (fail[1]) st = SG_E_PONLY;
     else st = SG_E_BOTH;
-#if defined(__CUDA_ARCH__)
-    __threadfence();
-#endif
-    *(volatile uint8_t *)&v.estat[cand] = st;
+    /* a concurrent push may have frozen this candidate while it was scanning: that freezer is an
+     * earlier-ranked neighbour which was undecided when we read it, so `blocked` was set and we
+     * did not get here; the status word is therefore still ours to write */
+    sg_er_set(v, cand, st);
+    if (st == SG_E_BOTH || st == SG_E_PONLY) {
+        const uint32_t sides = st == SG_E_BOTH ? 2u : 1u;
+        for (uint32_t side = 0; side < sides; ++side) {
+            const uint32_t lit = 2 * cand + side;
+            const int n = (int)v.ot_len[lit];
+            const uint32_t *d = sg_list(v, lit);
+            for (int i = 0; i < n; ++i) {
+                const sg_u4 h = v.hdr[d[i]];
+                if (h.z & SG_DELETED) continue;
+                const uint32_t *l = v.lits + h.x;
+                for (int k = 0; k < (int)h.y; ++k) {
+                    const uint32_t u = SG_ABS(l[k]);
+                    if (u == cand) continue;
+                    const uint32_t w = sg_er_load(v, u);
+                    if (SG_ER_STAT(w) == SG_E_UNDECIDED && SG_ER_RANK(w) > rc) sg_er_freeze(v, u, w);
+                }
+            }
+        }
+    }
     return false;
 }
 

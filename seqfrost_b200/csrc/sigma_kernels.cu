@@ -245,12 +245,12 @@ __global__ void k_rank(SgView v)
 /* ---------------------------------------------------------------------------------------------- */
 /* election                                                                                         */
 /* ---------------------------------------------------------------------------------------------- */
-__global__ void k_elect_init(SgView v, uint32_t *__restrict__ wl)
+__global__ void k_elect_batch(SgView v, uint32_t r0, uint32_t r1, uint32_t *__restrict__ wl)
 {
-    const uint32_t var = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (var > v.nvars) return;
-    if (v.estat[var] != SG_E_UNDECIDED) return;
-    if (v.rank[var] > v.sc->brk_rank) { v.estat[var] = SG_E_SKIP; return; }
+    const uint32_t r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= r1) return;
+    const uint32_t var = v.order[r];
+    if (SG_ER_STAT(v.rank[var]) != SG_E_UNDECIDED) return;
     wl[atomicAdd(&v.sc->wl_count[0], 1u)] = var;
 }
 
@@ -267,7 +267,7 @@ __global__ void k_acting_flags(SgView v, uint32_t *__restrict__ fa, uint32_t *__
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= v.nvars) return;
-    const uint8_t s = v.estat[v.order[r]];
+    const uint32_t s = SG_ER_STAT(v.rank[v.order[r]]);
     const bool in = r < v.sc->brk_rank;
     fa[r] = in && (s == SG_E_BOTH || s == SG_E_PONLY);
     fe[r] = in && s == SG_E_BOTH;
@@ -279,7 +279,7 @@ __global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, cons
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= v.nvars) return;
     const uint32_t var = v.order[r];
-    if (fa[r]) v.acting[pa[r]] = var | (v.estat[var] == SG_E_PONLY ? 0x80000000u : 0u);
+    if (fa[r]) v.acting[pa[r]] = var | (SG_ER_STAT(v.rank[var]) == SG_E_PONLY ? 0x80000000u : 0u);
     if (fe[r]) v.elected[pe[r]] = var;
 }
 
@@ -527,7 +527,10 @@ void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t
 }
 void be_rank(void *s, const SgView &v) { if (v.nvars) LAUNCH(k_rank, blocks_for(v.nvars), TPB, s, v); }
 
-void be_elect_init(void *s, const SgView &v, uint32_t *wl) { if (v.nvars) LAUNCH(k_elect_init, blocks_for(v.nvars), TPB, s, v, wl); }
+void be_elect_batch(void *s, const SgView &v, uint32_t r0, uint32_t r1, uint32_t *wl)
+{
+    if (r1 > r0) LAUNCH(k_elect_batch, blocks_for(r1 - r0), TPB, s, v, r0, r1, wl);
+}
 void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity)
 {
     cudaMemsetAsync(&v.sc->wl_count[parity ^ 1], 0, sizeof(uint32_t), ST(s));

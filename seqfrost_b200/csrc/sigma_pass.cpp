@@ -57,7 +57,7 @@ struct sigma_ctx {
     /* working store */
     DBuf<sg_u4> hdr, hdr2; DBuf<uint32_t> lits, lits2;
     DBuf<uint32_t> ot_off, ot_len, ot_data, occ, cursor;
-    DBuf<int8_t> value, marks; DBuf<uint8_t> state, estat;
+    DBuf<int8_t> value, marks; DBuf<uint8_t> state;
     DBuf<uint32_t> trail, model;
     DBuf<uint32_t> scores, order, rank, tmpk, tmpv, sorttmp, scantmp;
     DBuf<uint32_t> wl0, wl1, flags, pos, acting, elected;
@@ -125,7 +125,7 @@ SgView make_view(sigma_ctx *c)
     v.value = c->value.p; v.state = c->state.p; v.marks = c->marks.p;
     v.ifrozen = c->in_has_ifrozen ? c->d_ifrozen.p : nullptr;
     v.vorg = c->d_vorg.p; v.trail = c->trail.p; v.model = c->model.p;
-    v.occ = c->occ.p; v.scores = c->scores.p; v.order = c->order.p; v.rank = c->rank.p; v.estat = c->estat.p;
+    v.occ = c->occ.p; v.scores = c->scores.p; v.order = c->order.p; v.rank = c->rank.p;
     v.elected = c->elected.p; v.acting = c->acting.p;
     v.ve_type = c->ve_type.p; v.ve_ncls = c->ve_ncls.p; v.ve_nlits = c->ve_nlits.p; v.ve_nmodel = c->ve_nmodel.p;
     v.ve_aux = c->ve_aux.p; v.ve_cls_off = c->ve_cls_off.p; v.ve_lit_off = c->ve_lit_off.p; v.ve_mod_off = c->ve_mod_off.p;
@@ -260,17 +260,30 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         c->hsc.n_acting = c->hsc.n_ponly = c->hsc.n_elected = 0;
         CK(push_scalars(c));
         be_items(c->stream, SGK_ELECT_PREP, v, V);
-        be_elect_init(c->stream, v, c->wl0.p);
-        int parity = 0;
-        while (true) {
-            for (int k = 0; k < 4; ++k) {
-                be_elect_round(c->stream, v, parity ? c->wl1.p : c->wl0.p, parity ? c->wl0.p : c->wl1.p, parity);
-                parity ^= 1;
-                rounds++;
-            }
+        /* rank-ordered batches of geometrically growing size: inside a batch, pull rounds until every
+         * candidate is decided; acting candidates push FROZEN onto their undecided neighbours, so the
+         * later (large) batches hold few candidates that are still undecided */
+        uint32_t r0 = 0, bsize = 4096;
+        while (r0 < V) {
+            const uint32_t r1 = (V - r0 <= bsize) ? V : r0 + bsize;
             CK(pull_scalars(c));
-            if (!c->hsc.wl_count[parity]) break;
-            if (rounds > 4u * V + 16) return fail(c, SIGMA_E_CUDA, "election did not converge");
+            if (c->hsc.brk_rank < r0) break;               /* the sequential loop ended before this batch */
+            c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
+            CK(push_scalars(c));
+            be_elect_batch(c->stream, v, r0, r1, c->wl0.p);
+            int parity = 0;
+            while (true) {
+                for (int k = 0; k < 4; ++k) {
+                    be_elect_round(c->stream, v, parity ? c->wl1.p : c->wl0.p, parity ? c->wl0.p : c->wl1.p, parity);
+                    parity ^= 1;
+                    rounds++;
+                }
+                CK(pull_scalars(c));
+                if (!c->hsc.wl_count[parity]) break;
+                if (rounds > 4u * V + 64) return fail(c, SIGMA_E_CUDA, "election did not converge");
+            }
+            r0 = r1;
+            if (bsize < (1u << 30)) bsize *= 4;
         }
         /* acting / elected candidates in election order, cut at the break (lcve.cpp:70,73) */
         be_acting_flags(c->stream, v, c->flags.p, c->flags.p + V);
@@ -511,7 +524,7 @@ void sigma_destroy(sigma_ctx *c)
         c->d_trail_in.release(); c->d_model_in.release(); c->d_vorg.release(); c->d_ifrozen.release();
         c->hdr.release(); c->hdr2.release(); c->lits.release(); c->lits2.release();
         c->ot_off.release(); c->ot_len.release(); c->ot_data.release(); c->occ.release(); c->cursor.release();
-        c->value.release(); c->marks.release(); c->state.release(); c->estat.release(); c->trail.release(); c->model.release();
+        c->value.release(); c->marks.release(); c->state.release(); c->trail.release(); c->model.release();
         c->scores.release(); c->order.release(); c->rank.release(); c->tmpk.release(); c->tmpv.release();
         c->sorttmp.release(); c->scantmp.release(); c->wl0.release(); c->wl1.release(); c->flags.release(); c->pos.release();
         c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
@@ -574,7 +587,7 @@ int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
     if (in->ifrozen) NOMEM(c->d_ifrozen.ensure(V + 1));
     /* working arrays sized by the variable count */
     NOMEM(c->ot_off.ensure(nlit + 1)); NOMEM(c->ot_len.ensure(nlit)); NOMEM(c->occ.ensure(nlit)); NOMEM(c->cursor.ensure(nlit));
-    NOMEM(c->value.ensure(nlit)); NOMEM(c->marks.ensure(V + 1)); NOMEM(c->state.ensure(V + 1)); NOMEM(c->estat.ensure(V + 1));
+    NOMEM(c->value.ensure(nlit)); NOMEM(c->marks.ensure(V + 1)); NOMEM(c->state.ensure(V + 1));
     NOMEM(c->trail.ensure((size_t)V + 16));
     NOMEM(c->scores.ensure(V + 2)); NOMEM(c->order.ensure(V + 1)); NOMEM(c->rank.ensure(V + 1));
     NOMEM(c->tmpk.ensure(V + 1)); NOMEM(c->tmpv.ensure(V + 1)); NOMEM(c->sorttmp.ensure(be_sort_tmp_words(V) + 64));

@@ -106,8 +106,8 @@ typedef struct SgView {
     uint32_t *trail;
     uint32_t *model;
     uint32_t *occ;           /* occurrences per literal at election time (histogram.cpp:84-97) */
-    uint32_t *scores, *order, *rank;
-    uint8_t  *estat;
+    uint32_t *scores, *order;
+    uint32_t *rank;          /* election word per variable: rank | status << 29 (sigma_items.cuh) */
     uint32_t *elected;       /* elected variables in election order */
     uint32_t *acting;        /* acting candidates in election order, bit31 = P-only */
     /* per elected variable (index = position in `elected`) */

@@ -116,15 +116,13 @@ void be_rank(void *, const SgView &v)
     g_launches++;
     for (uint32_t r = 0; r < v.nvars; ++r) v.rank[v.order[r]] = r;
 }
-void be_elect_init(void *, const SgView &v, uint32_t *wl)
+void be_elect_batch(void *, const SgView &v, uint32_t r0, uint32_t r1, uint32_t *wl)
 {
     g_launches++;
     uint32_t n = 0;
-    for (uint32_t x : item_order(v.nvars)) {
-        const uint32_t var = x + 1;
-        if (v.estat[var] != SG_E_UNDECIDED) continue;
-        if (v.rank[var] > v.sc->brk_rank) { v.estat[var] = SG_E_SKIP; continue; }
-        wl[n++] = var;
+    for (uint32_t i : item_order(r1 - r0)) {
+        const uint32_t var = v.order[r0 + i];
+        if (SG_ER_STAT(v.rank[var]) == SG_E_UNDECIDED) wl[n++] = var;
     }
     v.sc->wl_count[0] = n;
 }
@@ -141,7 +139,7 @@ void be_acting_flags(void *, const SgView &v, uint32_t *fa, uint32_t *fe)
 {
     g_launches++;
     for (uint32_t r = 0; r < v.nvars; ++r) {
-        const uint8_t s = v.estat[v.order[r]];
+        const uint32_t s = SG_ER_STAT(v.rank[v.order[r]]);
         const bool in = r < v.sc->brk_rank;
         fa[r] = in && (s == SG_E_BOTH || s == SG_E_PONLY);
         fe[r] = in && s == SG_E_BOTH;
@@ -152,7 +150,7 @@ void be_acting_scatter(void *, const SgView &v, const uint32_t *fa, const uint32
     g_launches++;
     for (uint32_t r = 0; r < v.nvars; ++r) {
         const uint32_t var = v.order[r];
-        if (fa[r]) v.acting[pa[r]] = var | (v.estat[var] == SG_E_PONLY ? 0x80000000u : 0u);
+        if (fa[r]) v.acting[pa[r]] = var | (SG_ER_STAT(v.rank[var]) == SG_E_PONLY ? 0x80000000u : 0u);
         if (fe[r]) v.elected[pe[r]] = var;
     }
 }
