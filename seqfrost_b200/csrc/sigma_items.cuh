@@ -368,6 +368,96 @@ SG_HDN inline void sg_prop_serial(const SgView &v)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* warp-cooperative execution of one elected variable                                           */
+/*                                                                                              */
+/* SUB and the BVE decision run one WARP per elected variable.  Control flow is warp-uniform    */
+/* (every lane follows the reference's sequential decision tree with the same data); the heavy  */
+/* inner loops - sorted-clause merge tests over the |P| x |N| pair space, and "first clause in  */
+/* list order that ..." scans - are split over the lanes and recombined with ballots/reductions */
+/* so that the outcome is the sequential one.  Clause writes are made by lane 0.                */
+/* (The host test harness instantiates the same code with a warp of width 1.)                   */
+/* ------------------------------------------------------------------------------------------ */
+struct SgLane { uint32_t lane, width; };
+
+SG_HD SgLane sg_lane_ctx()
+{
+    SgLane L;
+#if defined(__CUDA_ARCH__)
+    L.lane = threadIdx.x & 31u; L.width = 32u;
+#else
+    L.lane = 0u; L.width = 1u;
+#endif
+    return L;
+}
+SG_HD uint32_t sg_ballot(bool p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ballot_sync(0xffffffffu, p);
+#else
+    return p ? 1u : 0u;
+#endif
+}
+SG_HD int sg_wsum(int x)
+{
+#if defined(__CUDA_ARCH__)
+    return __reduce_add_sync(0xffffffffu, x);
+#else
+    return x;
+#endif
+}
+SG_HD uint32_t sg_wor(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __reduce_or_sync(0xffffffffu, x);
+#else
+    return x;
+#endif
+}
+SG_HD void sg_wsync()
+{
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+/* value of lane 0, for data another warp may be changing: every lane must act on ONE reading */
+SG_HD uint32_t sg_bcast(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(0xffffffffu, x, 0);
+#else
+    return x;
+#endif
+}
+SG_HD int sg_ffs(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m);
+#else
+    return __builtin_ffs((int)m);
+#endif
+}
+SG_HD int sg_popc(uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+
+/* index of the first entry in [0,n) satisfying pred, or -1; pred must be side-effect free */
+template <class P> SG_HD int sg_find_first(const SgLane &L, int n, P pred)
+{
+    for (int base = 0; base < n; base += (int)L.width) {
+        const int idx = base + (int)L.lane;
+        const bool p = idx < n && pred(idx);
+        const uint32_t m = sg_ballot(p);
+        if (m) return base + sg_ffs(m) - 1;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* LCVE election (lcve.cpp:52-83, depFreeze :121-145) as a deterministic parallel greedy:       */
 /* a candidate is decided once every earlier-ranked clause neighbour is decided.                */
 /* ------------------------------------------------------------------------------------------ */
@@ -425,65 +515,59 @@ SG_HD void sg_elect_prep_item(const SgView &v, uint32_t var)
 /* One pull step for an undecided candidate of the current rank batch (every candidate of an
  * earlier batch is decided).  Returns true when it stays undecided.  A candidate that turns
  * out to act (depFreeze succeeded, lcve.cpp:76-78) freezes its still-undecided neighbours at
- * once, so later batches never have to look at them. */
+ * once, so later batches never have to look at them.  One warp per candidate: the lanes take
+ * the clauses of both occurrence lists in turn. */
 SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
 {
-    const uint32_t wc = sg_er_load(v, cand);
+    const SgLane L = sg_lane_ctx();
+    const uint32_t wc = sg_bcast(sg_er_load(v, cand));
     if (SG_ER_STAT(wc) != SG_E_UNDECIDED) return false;       /* frozen by a push since it was queued */
     const uint32_t rc = SG_ER_RANK(wc);
-    if (rc > *(volatile uint32_t *)&v.sc->brk_rank) { sg_er_set(v, cand, SG_E_SKIP); return false; }
+    if (rc > sg_bcast(*(volatile uint32_t *)&v.sc->brk_rank)) { if (L.lane == 0) sg_er_set(v, cand, SG_E_SKIP); return false; }
     const int maxcsize = v.o.lcve_clause_max;
-    bool blocked = false, fail[2] = { false, false };
-    for (uint32_t side = 0; side < 2; ++side) {
-        const uint32_t lit = 2 * cand + side;
-        const int n = (int)v.ot_len[lit];
-        const uint32_t *d = sg_list(v, lit);
-        for (int i = 0; i < n; ++i) {
-            const sg_u4 h = v.hdr[d[i]];
-            if (h.z & SG_DELETED) continue;
-            const int size = (int)h.y;
-            if (size > maxcsize) fail[side] = true;
-            const uint32_t *l = v.lits + h.x;
-            for (int k = 0; k < size; ++k) {
-                const uint32_t other = l[k], u = SG_ABS(other);
-                if (u == cand) continue;
-                const uint32_t w = sg_er_load(v, u);
-                if (SG_ER_RANK(w) > rc) continue;
-                const uint32_t s = SG_ER_STAT(w);
-                if (s == SG_E_UNDECIDED) blocked = true;
-                else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other))) {
-                    sg_er_set(v, cand, SG_E_FROZEN);
-                    return false;
-                }
-            }
+    const int np = (int)v.ot_len[2 * cand], nn = (int)v.ot_len[2 * cand + 1];
+    const uint32_t *dp = sg_list(v, 2 * cand), *dn = sg_list(v, 2 * cand + 1);
+    bool blocked = false, frozen = false, failp = false, failn = false;
+    for (int q = (int)L.lane; q < np + nn; q += (int)L.width) {
+        const bool neg = q >= np;
+        const sg_u4 h = v.hdr[neg ? dn[q - np] : dp[q]];
+        if (h.z & SG_DELETED) continue;
+        const int size = (int)h.y;
+        if (size > maxcsize) { if (neg) failn = true; else failp = true; }
+        const uint32_t *l = v.lits + h.x;
+        for (int k = 0; k < size; ++k) {
+            const uint32_t other = l[k], u = SG_ABS(other);
+            if (u == cand) continue;
+            const uint32_t w = sg_er_load(v, u);
+            if (SG_ER_RANK(w) > rc) continue;
+            const uint32_t s = SG_ER_STAT(w);
+            if (s == SG_E_UNDECIDED) blocked = true;
+            else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other))) frozen = true;
         }
     }
-    if (blocked) return true;
+    const uint32_t flags = sg_wor((blocked ? 1u : 0u) | (frozen ? 2u : 0u) | (failp ? 4u : 0u) | (failn ? 8u : 0u));
+    if (flags & 2u) { if (L.lane == 0) sg_er_set(v, cand, SG_E_FROZEN); return false; }
+    if (flags & 1u) return true;
     uint32_t st;
-    if (sg_break_cond(v, cand)) { st = SG_E_BREAK; sg_atomic_min(&v.sc->brk_rank, rc); }
-    else if (fail[0]) st = SG_E_NONE;
-    else if (fail[1]) st = SG_E_PONLY;
+    if (sg_break_cond(v, cand)) { st = SG_E_BREAK; if (L.lane == 0) sg_atomic_min(&v.sc->brk_rank, rc); }
+    else if (flags & 4u) st = SG_E_NONE;
+    else if (flags & 8u) st = SG_E_PONLY;
     else st = SG_E_BOTH;
-    /* a concurrent push may have frozen this candidate while it was scanning: that freezer is an
-     * earlier-ranked neighbour which was undecided when we read it, so `blocked` was set and we
-     * did not get here; the status word is therefore still ours to write */
-    sg_er_set(v, cand, st);
+    /* a concurrent push can only come from an earlier-ranked acting neighbour; had it still been
+     * undecided when we read it we would be blocked, had it acted we would be frozen: the status
+     * word is ours to write */
+    if (L.lane == 0) sg_er_set(v, cand, st);
     if (st == SG_E_BOTH || st == SG_E_PONLY) {
-        const uint32_t sides = st == SG_E_BOTH ? 2u : 1u;
-        for (uint32_t side = 0; side < sides; ++side) {
-            const uint32_t lit = 2 * cand + side;
-            const int n = (int)v.ot_len[lit];
-            const uint32_t *d = sg_list(v, lit);
-            for (int i = 0; i < n; ++i) {
-                const sg_u4 h = v.hdr[d[i]];
-                if (h.z & SG_DELETED) continue;
-                const uint32_t *l = v.lits + h.x;
-                for (int k = 0; k < (int)h.y; ++k) {
-                    const uint32_t u = SG_ABS(l[k]);
-                    if (u == cand) continue;
-                    const uint32_t w = sg_er_load(v, u);
-                    if (SG_ER_STAT(w) == SG_E_UNDECIDED && SG_ER_RANK(w) > rc) sg_er_freeze(v, u, w);
-                }
+        const int total = st == SG_E_BOTH ? np + nn : np;
+        for (int q = (int)L.lane; q < total; q += (int)L.width) {
+            const sg_u4 h = v.hdr[q >= np ? dn[q - np] : dp[q]];
+            if (h.z & SG_DELETED) continue;
+            const uint32_t *l = v.lits + h.x;
+            for (int k = 0; k < (int)h.y; ++k) {
+                const uint32_t u = SG_ABS(l[k]);
+                if (u == cand) continue;
+                const uint32_t w = sg_er_load(v, u);
+                if (SG_ER_STAT(w) == SG_E_UNDECIDED && SG_ER_RANK(w) > rc) sg_er_freeze(v, u, w);
             }
         }
     }
@@ -524,87 +608,6 @@ SG_HDN inline void sg_marks_serial(const SgView &v, uint32_t n_acting)
     }
     for (uint32_t q = 0; q < nc; ++q) { v.marks[core[q]] = (int8_t)q; sc->core[q] = core[q]; }
     sc->n_core = nc;
-}
-
-/* ------------------------------------------------------------------------------------------ */
-/* warp-cooperative execution of one elected variable                                           */
-/*                                                                                              */
-/* SUB and the BVE decision run one WARP per elected variable.  Control flow is warp-uniform    */
-/* (every lane follows the reference's sequential decision tree with the same data); the heavy  */
-/* inner loops - sorted-clause merge tests over the |P| x |N| pair space, and "first clause in  */
-/* list order that ..." scans - are split over the lanes and recombined with ballots/reductions */
-/* so that the outcome is the sequential one.  Clause writes are made by lane 0.                */
-/* (The host test harness instantiates the same code with a warp of width 1.)                   */
-/* ------------------------------------------------------------------------------------------ */
-struct SgLane { uint32_t lane, width; };
-
-SG_HD SgLane sg_lane_ctx()
-{
-    SgLane L;
-#if defined(__CUDA_ARCH__)
-    L.lane = threadIdx.x & 31u; L.width = 32u;
-#else
-    L.lane = 0u; L.width = 1u;
-#endif
-    return L;
-}
-SG_HD uint32_t sg_ballot(bool p)
-{
-#if defined(__CUDA_ARCH__)
-    return __ballot_sync(0xffffffffu, p);
-#else
-    return p ? 1u : 0u;
-#endif
-}
-SG_HD int sg_wsum(int x)
-{
-#if defined(__CUDA_ARCH__)
-    return __reduce_add_sync(0xffffffffu, x);
-#else
-    return x;
-#endif
-}
-SG_HD uint32_t sg_wor(uint32_t x)
-{
-#if defined(__CUDA_ARCH__)
-    return __reduce_or_sync(0xffffffffu, x);
-#else
-    return x;
-#endif
-}
-SG_HD void sg_wsync()
-{
-#if defined(__CUDA_ARCH__)
-    __syncwarp();
-#endif
-}
-SG_HD int sg_ffs(uint32_t m)
-{
-#if defined(__CUDA_ARCH__)
-    return __ffs((int)m);
-#else
-    return __builtin_ffs((int)m);
-#endif
-}
-SG_HD int sg_popc(uint32_t m)
-{
-#if defined(__CUDA_ARCH__)
-    return __popc(m);
-#else
-    return __builtin_popcount(m);
-#endif
-}
-
-/* index of the first entry in [0,n) satisfying pred, or -1; pred must be side-effect free */
-template <class P> SG_HD int sg_find_first(const SgLane &L, int n, P pred)
-{
-    for (int base = 0; base < n; base += (int)L.width) {
-        const int idx = base + (int)L.lane;
-        const bool p = idx < n && pred(idx);
-        const uint32_t m = sg_ballot(p);
-        if (m) return base + sg_ffs(m) - 1;
-    }
-    return -1;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1294,7 +1297,7 @@ SG_HDN inline void sg_ve_count_item(const SgView &v, uint32_t eidx)
             else if (!nAddedCls && sg_find_xor_gate(v, L, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->xors; }
         }
         if (!type && orgCls > 2 && sg_find_fun_gate(v, L, p, orgCls, nAddedCls, nAddedLits)) {
-            if (*(volatile uint32_t *)&v.sc->unsat) { type = SG_VE_NONE; nAddedCls = 0; nAddedLits = 0; }
+            if (sg_bcast(*(volatile uint32_t *)&v.sc->unsat)) { type = SG_VE_NONE; nAddedCls = 0; nAddedLits = 0; }
             else { type = SG_VE_CORE; stat = &v.sc->funs; }
         } else if (!type && !nAddedCls) {
             if (!sg_count_pairs(v, L, SG_VE_RESOLVE, var, orgCls, p, n, nAddedCls, nAddedLits)) {

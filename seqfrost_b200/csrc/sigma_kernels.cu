@@ -255,11 +255,14 @@ __global__ void k_elect_batch(SgView v, uint32_t r0, uint32_t r1, uint32_t *__re
 }
 
 __global__ void k_elect_round(SgView v, const uint32_t *__restrict__ wl_in, uint32_t *__restrict__ wl_out, int parity)
-{
+{   /* one warp per queued candidate */
     const uint32_t n = v.sc->wl_count[parity];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+        __syncwarp();
         const uint32_t cand = wl_in[i];
-        if (sg_elect_round_item(v, cand)) wl_out[atomicAdd(&v.sc->wl_count[parity ^ 1], 1u)] = cand;
+        const bool stay = sg_elect_round_item(v, cand);
+        if (stay && (threadIdx.x & 31) == 0) wl_out[atomicAdd(&v.sc->wl_count[parity ^ 1], 1u)] = cand;
     }
 }
 
@@ -534,7 +537,7 @@ void be_elect_batch(void *s, const SgView &v, uint32_t r0, uint32_t r1, uint32_t
 void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity)
 {
     cudaMemsetAsync(&v.sc->wl_count[parity ^ 1], 0, sizeof(uint32_t), ST(s));
-    unsigned grid = blocks_for(v.nvars, 128);
+    unsigned grid = blocks_for(32ull * v.nvars, 128);
     if (grid > 148u * 16u) grid = 148u * 16u;
     if (!grid) grid = 1;
     LAUNCH(k_elect_round, grid, 128, s, v, wl_in, wl_out, parity);

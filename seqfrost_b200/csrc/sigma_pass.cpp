@@ -266,14 +266,11 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         uint32_t r0 = 0, bsize = 4096;
         while (r0 < V) {
             const uint32_t r1 = (V - r0 <= bsize) ? V : r0 + bsize;
-            CK(pull_scalars(c));
-            if (c->hsc.brk_rank < r0) break;               /* the sequential loop ended before this batch */
-            c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
-            CK(push_scalars(c));
+            be_memset(c->stream, &c->sc.p->wl_count[0], 0, 2 * sizeof(uint32_t));
             be_elect_batch(c->stream, v, r0, r1, c->wl0.p);
             int parity = 0;
             while (true) {
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 3; ++k) {
                     be_elect_round(c->stream, v, parity ? c->wl1.p : c->wl0.p, parity ? c->wl0.p : c->wl1.p, parity);
                     parity ^= 1;
                     rounds++;
@@ -282,6 +279,7 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
                 if (!c->hsc.wl_count[parity]) break;
                 if (rounds > 4u * V + 64) return fail(c, SIGMA_E_CUDA, "election did not converge");
             }
+            if (c->hsc.brk_rank < r1) break;               /* the sequential loop ended inside this batch */
             r0 = r1;
             if (bsize < (1u << 30)) bsize *= 4;
         }
