@@ -60,7 +60,7 @@ void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_
 size_t be_scan_tmp_words(uint32_t n);
 /* per-literal occurrence histogram over live clauses (histogram.hpp:43-50, simplify.cpp:50-58) */
 void be_hist(void *s, const SgView &v, uint32_t *counts);
-/* scatter clause ids into the lists; cursor must be zero */
+/* scatter clause ids into the lists; cursor must hold a copy of ot_off (absolute write positions) */
 void be_scatter(void *s, const SgView &v, uint32_t *cursor);
 /* scores[v] = ps*ns (uint32 wrap, histogram.hpp:23), order[v-1] = v */
 void be_scores(void *s, const SgView &v);

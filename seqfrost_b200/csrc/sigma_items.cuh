@@ -1076,35 +1076,76 @@ SG_HD void sg_freeze_arities(const SgView &v, const SgLane &L, uint32_t a, uint3
     sg_freeze_if(v, L, b, [](const sg_u4 &h) { return (int)h.y > 2; });
 }
 
-SG_HDN inline bool sg_make_arity(const SgView &v, const SgLane &L, uint32_t &parity, uint32_t *literals, int size)
-{   /* xor.hpp:70-102 */
+/* advances `parity` to the next even-popcount value and flips the literals whose bit changed (xor.hpp:26,72-78) */
+SG_HD void sg_next_arity(uint32_t &parity, uint32_t *literals, int size)
+{
     const uint32_t oldparity = parity;
     do { ++parity; } while (sg_popc(parity) & 1);
     for (int k = 0; k < size; ++k) {
         const uint32_t bit = 1u << k;
         if ((parity & bit) != (oldparity & bit)) literals[k] = SG_FLIP(literals[k]);
     }
-    uint32_t best = literals[0];
+}
+/* the list makeArity searches: shortest occurrence list among the pattern's literals, first minimum (xor.hpp:81-92) */
+SG_HD uint32_t sg_arity_best(const SgView &v, const uint32_t *literals, int size, uint32_t *sig_out)
+{
+    uint32_t best = literals[0], sig = SG_HASH(literals[0]);
     int minsize = (int)v.ot_len[best];
     for (int k = 1; k < size; ++k) {
         const int lsize = (int)v.ot_len[literals[k]];
+        sig |= SG_HASH(literals[k]);
         if (lsize < minsize) { minsize = lsize; best = literals[k]; }
     }
+    *sig_out = sig;
+    return best;
+}
+/* original clause of `size` literals made of exactly the pattern's literals (checkArity, xor.hpp:53-68);
+ * equal literal sets have equal signatures, so the signature is compared first */
+SG_HD bool sg_arity_match(const SgView &v, const sg_u4 &h, const uint32_t *literals, int size, uint32_t sig)
+{
+    if ((h.z & SG_ST_MASK) || (int)h.y != size || h.w != sig) return false;
+    const uint32_t *l = v.lits + h.x;
+    for (int a = 0; a < size; ++a) {
+        bool found = false;
+        for (int b = 0; b < size; ++b) if (l[a] == literals[b]) { found = true; break; }
+        if (!found) return false;
+    }
+    return true;
+}
+
+SG_HDN inline bool sg_make_arity(const SgView &v, const SgLane &L, uint32_t &parity, uint32_t *literals, int size)
+{   /* xor.hpp:70-102 */
+    sg_next_arity(parity, literals, size);
+    uint32_t sig;
+    const uint32_t best = sg_arity_best(v, literals, size, &sig);
     const int n = (int)v.ot_len[best];
     const uint32_t *d = sg_list(v, best);
-    const int k = sg_find_first(L, n, [&](int i) {
-        const sg_u4 h = v.hdr[d[i]];
-        if ((h.z & SG_ST_MASK) || (int)h.y != size) return false;
-        const uint32_t *l = v.lits + h.x;
-        for (int a = 0; a < size; ++a) {            /* checkArity (xor.hpp:53-68) */
-            bool found = false;
-            for (int b = 0; b < size; ++b) if (l[a] == literals[b]) { found = true; break; }
-            if (!found) return false;
-        }
-        return true;
-    });
+    const int k = sg_find_first(L, n, [&](int i) { return sg_arity_match(v, v.hdr[d[i]], literals, size, sig); });
     if (k < 0) return false;
     sg_melt1(v, L, d[k]);
+    return true;
+}
+
+/* does clause `ci` have all its 2^arity - 1 partner clauses?  Read-only, one lane: whether a
+ * partner exists does not depend on any molten flag, and a failed search leaves no mark behind
+ * (freezeArities, xor.hpp:141-142), so the lanes can test different clauses at the same time. */
+SG_HDN inline bool sg_xor_complete(const SgView &v, uint32_t ci, int size)
+{
+    uint32_t lits[24];
+    const uint32_t *l = SG_LITS(v, ci);
+    for (int k = 0; k < size; ++k) lits[k] = l[k];
+    uint32_t parity = 0;
+    int itargets = 1 << (size - 1);
+    while (--itargets) {
+        sg_next_arity(parity, lits, size);
+        uint32_t sig;
+        const uint32_t best = sg_arity_best(v, lits, size, &sig);
+        const int n = (int)v.ot_len[best];
+        const uint32_t *d = sg_list(v, best);
+        bool found = false;
+        for (int i = 0; i < n && !found; ++i) found = sg_arity_match(v, v.hdr[d[i]], lits, size, sig);
+        if (!found) return false;
+    }
     return true;
 }
 
@@ -1115,32 +1156,35 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
     const uint32_t *dd = sg_list(v, dx), *df = sg_list(v, fx);
     if (SG_SIZE(v, dd[nd - 1]) == 2 || SG_SIZE(v, df[nf - 1]) == 2) return false;
     const int maxarity = v.o.xor_max_arity;
-    int arity = SG_SIZE(v, dd[0]) - 1;
-    if (arity > maxarity) return false;
+    if (SG_SIZE(v, dd[0]) - 1 > maxarity) return false;
     const uint32_t var = SG_ABS(dx);
     uint32_t out_c[24];
-    for (int i = 0; i < nd; ++i) {
-        const uint32_t ci = dd[i];
-        if (!sg_original(v, ci)) continue;
+    for (int base = 0; base < nd; base += (int)L.width) {
+        /* the reference tries the clauses of dx in list order and stops at the first complete XOR */
+        const int idx = base + (int)L.lane;
+        bool complete = false;
+        if (idx < nd) {
+            const sg_u4 h = v.hdr[dd[idx]];
+            const int size = (int)h.y;
+            if (!(h.z & SG_ST_MASK) && size >= 3 && size - 1 <= maxarity && size <= 24) complete = sg_xor_complete(v, dd[idx], size);
+        }
+        const uint32_t m = sg_ballot(complete);
+        if (!m) continue;
+        const uint32_t ci = dd[base + sg_ffs(m) - 1];
         const int size = SG_SIZE(v, ci);
-        arity = size - 1;
-        if (size < 3 || arity > maxarity || size > 24) continue;
         const uint32_t *l = SG_LITS(v, ci);
         for (int k = 0; k < size; ++k) out_c[k] = l[k];
         uint32_t parity = 0;
-        int itargets = 1 << arity;
-        bool melted_any = false;
-        while (--itargets && sg_make_arity(v, L, parity, out_c, size)) melted_any = true;
-        if (itargets) { if (melted_any) sg_freeze_arities(v, L, dx, fx); }
-        else {
-            sg_melt1(v, L, ci);
-            nAddedCls = 0, nAddedLits = 0;
-            if (sg_count_pairs(v, L, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
-                sg_freeze_arities(v, L, dx, fx);
-                break;
-            }
-            return true;
+        int itargets = 1 << (size - 1);
+        while (--itargets && sg_make_arity(v, L, parity, out_c, size));
+        if (itargets) { sg_freeze_arities(v, L, dx, fx); continue; }      /* cannot happen: ci is complete */
+        sg_melt1(v, L, ci);
+        nAddedCls = 0, nAddedLits = 0;
+        if (sg_count_pairs(v, L, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
+            sg_freeze_arities(v, L, dx, fx);
+            break;
         }
+        return true;
     }
     return false;
 }

@@ -7,6 +7,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sigma_backend.h"
@@ -156,8 +157,12 @@ __global__ void k_hist(const uint4 *__restrict__ hdr, const uint32_t *__restrict
     for (uint32_t k = 0; k < h.y; ++k) atomicAdd(&counts[l[k]], 1u);
 }
 
+/* One pass writes the lists of the literals in [lo, hi) only: the slice of ot_data it touches
+ * stays resident in L2, so the 4-byte scattered stores merge there instead of each costing a
+ * 32-byte sector read + write in HBM (ncu: 3.9 GB of DRAM traffic for 0.48 GB of payload when the
+ * whole 204 MB table was scattered in one pass). */
 __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
-                          const uint32_t *__restrict__ ot_off, uint32_t *__restrict__ cursor, uint32_t *__restrict__ ot_data)
+                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ ot_data, uint32_t lo, uint32_t hi)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cls) return;
@@ -166,8 +171,9 @@ __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restr
     const uint32_t *l = lits + h.x;
     for (uint32_t k = 0; k < h.y; ++k) {
         const uint32_t lit = l[k];
-        const uint32_t pos = atomicAdd(&cursor[lit], 1u);
-        ot_data[ot_off[lit] + pos] = c;
+        if (lit >= hi) break;                 /* literals ascend inside a clause */
+        if (lit < lo) continue;
+        ot_data[atomicAdd(&cursor[lit], 1u)] = c;
     }
 }
 
@@ -499,7 +505,18 @@ void be_hist(void *s, const SgView &v, uint32_t *counts)
 }
 void be_scatter(void *s, const SgView &v, uint32_t *cursor)
 {
-    if (v.n_cls) LAUNCH(k_scatter, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, v.ot_off, cursor, v.ot_data);
+    if (!v.n_cls) return;
+    static long l2_mb = -1;
+    if (l2_mb < 0) { const char *e = getenv("SIGMA_SCATTER_L2_MB"); l2_mb = e ? atol(e) : 64; if (l2_mb < 1) l2_mb = 1; }
+    const uint64_t bytes = 4ull * v.pool_used;
+    uint32_t passes = (uint32_t)((bytes + ((uint64_t)l2_mb << 20) - 1) / ((uint64_t)l2_mb << 20));
+    if (passes < 1) passes = 1;
+    if (passes > 64) passes = 64;
+    const uint32_t step = (v.nlit + passes - 1) / passes;
+    for (uint32_t p = 0; p < passes; ++p) {
+        const uint32_t lo = p * step, hi = (p + 1 == passes) ? 0xFFFFFFFFu : (p + 1) * step;
+        LAUNCH(k_scatter, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, cursor, v.ot_data, lo, hi);
+    }
 }
 void be_scores(void *s, const SgView &v) { if (v.nvars) LAUNCH(k_scores, blocks_for(v.nvars), TPB, s, v); }
 

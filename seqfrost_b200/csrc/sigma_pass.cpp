@@ -209,7 +209,7 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
     }
     {
         Stage st(c, SIGMA_T_OT_SCATTER, 8 * live_lits + 8ull * c->n_cls);
-        be_memset(c->stream, c->cursor.p, 0, nlit * sizeof(uint32_t));
+        be_d2d(c->stream, c->cursor.p, c->ot_off.p, nlit * sizeof(uint32_t));
         be_scatter(c->stream, v, c->cursor.p);
     }
     {

@@ -92,7 +92,7 @@ void be_scatter(void *, const SgView &v, uint32_t *cursor)
     for (uint32_t c : item_order(v.n_cls)) {
         if (v.hdr[c].z & SG_DELETED) continue;
         const uint32_t *l = v.lits + v.hdr[c].x;
-        for (uint32_t k = 0; k < v.hdr[c].y; ++k) v.ot_data[v.ot_off[l[k]] + cursor[l[k]]++] = c;
+        for (uint32_t k = 0; k < v.hdr[c].y; ++k) v.ot_data[cursor[l[k]]++] = c;
     }
 }
 void be_scores(void *, const SgView &v)
