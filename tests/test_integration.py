@@ -1,0 +1,66 @@
+"""End-to-end drop-in check: SeqFROST with the SIGmA pass replaced (seqfrost_b200/host/seqfrost_sigma.cpp
+linked against the UNMODIFIED reference library) must give the same verdict, a verified model and the same
+search statistics as the reference binary on the same file with the same options.  Identical conflict and
+propagation counts mean that the CDCL search after the pass took the identical trajectory, i.e. the clause
+order, flags, trail and model stack handed back are the reference's.  Later `simplify()` calls during search
+exercise the non-first-call path (learnt clauses in the store, countOrgs, bumpShrunken).
+
+CPU variant: linked against the serial test stand-in of the launch layer (tests/emul).  GPU variant
+(-m gpu): the real libsigma_b200.so; the binaries are built in the container and travel to the GPU box."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from seqfrost_b200 import cnfgen
+
+REF_SOLVER = os.path.join(ROOT, "oracle", "_ref", "seqfrost")
+HOST_BIN = os.path.join(ROOT, "seqfrost_b200", "host", "_build", "seqfrost_sigma")
+KEYS = ("s SATISFIABLE", "s UNSATISFIABLE", "s UNKNOWN", "VERIFIED", "Conflicts", "Propagations", "Decisions", "Restarts  ")
+ANSI = re.compile(r"\x1b\[[0-9;]*m")
+
+
+def _digest(exe, cnf, opts):
+    r = subprocess.run([exe, cnf, "-no-redundancy", "-model", "-modelverify", "-no-modelprint", "-report", *opts],
+                       capture_output=True, text=True, timeout=120)
+    lines = [ANSI.sub("", l).strip() for l in r.stdout.splitlines()]
+    return [l for l in lines if any(k in l for k in KEYS) and "ORG" not in l], r.stdout[-400:] + r.stderr[-400:]
+
+
+CASES = [   # every case: the reference finishes in a few seconds (it is slow on anything harder)
+    ("ksat3_2000_r3.9", lambda: cnfgen.random_ksat(2000, 7800, k=3, seed=6), ()),       # 33k conflicts after the pass
+    ("ksat3_250_r4.3", lambda: cnfgen.random_ksat(250, 1075, k=3, seed=2), ()),         # 17k conflicts
+    ("gates_10000", lambda: cnfgen.gate_circuit(10000, seed=3), ()),
+    ("xorphp_20k", lambda: cnfgen.xor_php_mix(20000, seed=3), ()),
+    ("fuzz_unsat", lambda: cnfgen.fuzz_mix(83), ()),
+    ("fuzz_units", lambda: cnfgen.fuzz_mix(20), ()),
+    ("gates_phases3", lambda: cnfgen.gate_circuit(4000, seed=8), ("--phases=3", "-bvebound")),
+]
+
+
+def _check(exe, tmp_path, name, gen, opts):
+    cnf = str(tmp_path / (name + ".cnf"))
+    cnfgen.write_dimacs(cnf, *gen())
+    ref, _ = _digest(REF_SOLVER, cnf, opts)
+    ours, tail = _digest(exe, cnf, opts)
+    assert any(l.startswith("s ") for l in ref), ref
+    assert ours == ref, tail
+    if "s SATISFIABLE" in ref:
+        assert any("VERIFIED" in l for l in ours)
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_SOLVER) and os.path.exists("/root/reference/src")), reason="reference not present")
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_solver_with_replaced_pass_cpu_standin(tmp_path, case):
+    import __graft_entry__ as ge
+    exe = ge.build_host(emul=True)
+    _check(exe, tmp_path, *case)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF_SOLVER) and os.path.exists(HOST_BIN)), reason="binaries are built in the container (build())")
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_solver_with_replaced_pass_gpu(tmp_path, case):
+    _check(HOST_BIN, tmp_path, *case)
