@@ -16,6 +16,7 @@
 #include "control.hpp"
 #include "solve.hpp"
 #include "version.hpp"
+#include "can.hpp"
 #include <chrono>
 #include <cstdio>
 #include <string>
@@ -112,10 +113,30 @@ public:
 #endif
 	}
 
-	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep) {
+	// optional prologue: the reference's own first simplify() followed by `conflicts` conflicts of its CDCL
+	// loop (solve.cpp:161-175 without the inprocessing branches), so that the staged pass below is a LATER
+	// call: learnt clauses in the store, stats.simplify.calls > 1 (countOrgs, bumpShrunken paths)
+	bool presolve(const int64 conflicts) {
+		if (canPreSimplify()) simplify();
+		if (!UNSOLVED) return false;
+		MDMInit();
+		while (UNSOLVED && (int64)stats.conflicts < conflicts) {
+			if (BCP()) analyze();
+			else if (!inf.unassigned) SET_SAT;
+			else if (canReduce()) reduce();
+			else if (canRestart()) restart();
+			else if (canRephase()) rephase();
+			else if (canMMD()) MDM();
+			else decide();
+		}
+		return UNSOLVED;
+	}
+
+	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts) {
 		using clk = std::chrono::steady_clock;
 		timer.start();
 		initLimits();
+		if (presolve_conflicts > 0 && !presolve(presolve_conflicts)) { fprintf(stderr, "ref_sigma: solved during the prologue\n"); return 6; }
 		if (!opts.preprocess_en) { fprintf(stderr, "ref_sigma: preprocess disabled\n"); return 2; }
 		if (!opts.phases && !(opts.all_en || opts.ere_en)) { fprintf(stderr, "ref_sigma: no phases\n"); return 2; }
 		stats.simplify.calls++;            // simplify.cpp:108
@@ -199,12 +220,14 @@ int main(int argc, char** argv)
 	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
 	std::string sgin, sgout, tracep;
+	long long presolve_conflicts = 0;
 	std::vector<char*> pass;
 	for (int i = 0; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a.rfind("--sgin=", 0) == 0) sgin = a.substr(7);
 		else if (a.rfind("--sgout=", 0) == 0) sgout = a.substr(8);
 		else if (a.rfind("--trace=", 0) == 0) tracep = a.substr(8);
+		else if (a.rfind("--presolve-conflicts=", 0) == 0) presolve_conflicts = atoll(a.substr(21).c_str());
 		else pass.push_back(argv[i]);
 	}
 	g_sgout = sgout;
@@ -219,7 +242,7 @@ int main(int argc, char** argv)
 		std::string formula = argv[1];
 		Probe* p = new Probe(formula);
 		solver = p;
-		int rc = p->run(sgin, sgout, tracep);
+		int rc = p->run(sgin, sgout, tracep, presolve_conflicts);
 		g_out_written = g_out_written || rc != 0;
 		fflush(stdout);
 		_exit(rc); // skip the reference's destructors (process-global singletons)

@@ -26,7 +26,7 @@ CASES = [
     ("gates_small", "gate_circuit", dict(nvars=3000, seed=11), []),
     ("gates_w200", "gate_circuit", dict(nvars=1500, seed=5, window=200), []),
     ("ksat3_small", "random_ksat", dict(nvars=2000, nclauses=8520, k=3, seed=1), []),
-    ("ksat5_planted", "planted_subsumption_ksat", dict(nvars=3000, nclauses=15000, k=5, seed=7), []),
+    ("ksat5_planted", "planted_subsumption_ksat", dict(nvars=1500, nclauses=7500, k=5, seed=7), []),
     ("xorphp_small", "xor_php_mix", dict(nclauses=6000, seed=3), []),
     ("gates_bvebound", "gate_circuit", dict(nvars=1200, seed=21), ["-bvebound"]),
     ("gates_phases2", "gate_circuit", dict(nvars=1200, seed=22), ["--phases=2"]),
@@ -38,6 +38,10 @@ CASES = [
     ("fuzz_unsat_b", "fuzz_mix", dict(seed=101), []),
     ("fuzz_ok_a", "fuzz_mix", dict(seed=0), []),
     ("fuzz_ok_b", "fuzz_mix", dict(seed=2), []),
+    # LATER calls: the reference's own first simplify() + 3000 conflicts of its CDCL loop run first
+    # (ref_harness --presolve-conflicts), so the store holds learnt clauses and stats.simplify.calls == 2
+    ("later_ksat3", "random_ksat", dict(nvars=2000, nclauses=7800, k=3, seed=6), ["--presolve-conflicts=3000"]),
+    ("later_gates", "gate_circuit", dict(nvars=6000, seed=5), ["--presolve-conflicts=1500"]),
 ]
 
 
