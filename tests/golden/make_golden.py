@@ -41,7 +41,7 @@ CASES = [
     # LATER calls: the reference's own first simplify() + 3000 conflicts of its CDCL loop run first
     # (ref_harness --presolve-conflicts), so the store holds learnt clauses and stats.simplify.calls == 2
     ("later_ksat3", "random_ksat", dict(nvars=2000, nclauses=7800, k=3, seed=6), ["--presolve-conflicts=3000"]),
-    ("later_gates", "gate_circuit", dict(nvars=6000, seed=5), ["--presolve-conflicts=1500"]),
+    ("later_gates", "gate_circuit", dict(nvars=8000, seed=7), ["--presolve-conflicts=500"]),
 ]
 
 
