@@ -40,12 +40,12 @@ def workload(nvars, nclauses, seed):
     return cnfgen.planted_subsumption_ksat(nvars, nclauses, k=5, seed=seed)
 
 
-def workload_name(nvars, nclauses):
+def workload_name(nvars, nclauses, ere=True):
     return (f"random 5-SAT {nvars / 1e6:g}M vars / {nclauses / 1e6:g}M clauses + planted subsumption "
-            f"(BASELINE.json configs[1], SURVEY 8d C2), -no-redundancy")
+            f"(BASELINE.json configs[1], SURVEY 8d C2), " + ("reference default options (ERE on)" if ere else "-no-redundancy"))
 
 
-def reference_pass(nvars, nclauses, seed, runs=1, warm=0):
+def reference_pass(nvars, nclauses, seed, runs=1, warm=0, ere=True):
     """Runs the unmodified reference on a DIMACS file of the given shape; returns
     (literals_in, [pass seconds per run]) for the replaced region simplify.cpp:180-206."""
     from seqfrost_b200 import cnfgen
@@ -55,7 +55,7 @@ def reference_pass(nvars, nclauses, seed, runs=1, warm=0):
         cnf = os.path.join(td, "sample.cnf")
         cnfgen.write_dimacs(cnf, nv, off, lits)
         for i in range(warm + runs):
-            r = subprocess.run([REF_BIN, cnf, "-no-redundancy", "-quiet"], capture_output=True, text=True)
+            r = subprocess.run([REF_BIN, cnf, "-quiet"] + ([] if ere else ["-no-redundancy"]), capture_output=True, text=True)
             line = [l for l in r.stdout.splitlines() if l.startswith("ref_sigma:")]
             if not line:
                 raise RuntimeError("ref_sigma failed: " + r.stdout[-300:] + r.stderr[-300:])
@@ -117,14 +117,14 @@ def run_reference(args, rank, world):
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_sigma not built (make -C oracle ref needs /root/reference)"}))
         return
-    lits_in, secs = reference_pass(sv, sc, args.seed, runs=args.steps, warm=args.warmup)
+    lits_in, secs = reference_pass(sv, sc, args.seed, runs=args.steps, warm=args.warmup, ere=not args.no_ere)
     total = sum(secs)
     value = lits_in * len(secs) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.vars, args.clauses), "sample": f"1/{args.sample_div} of the workload per step"},
+        "config": {"workload": workload_name(args.vars, args.clauses, not args.no_ere), "sample": f"1/{args.sample_div} of the workload per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                          "sample": f"same generator at 1/{args.sample_div} size ({sv} vars / {sc} clauses / {lits_in} literals), "
                                    f"replaced region simplify.cpp:180-206, {cpu_model()}, {os.cpu_count()} host cores, SeqFROST is single-threaded"},
@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--sample-div", type=int, default=10, help="CPU baseline sample = workload / this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ere", action="store_true", help="run both sides with -no-redundancy")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -164,6 +165,7 @@ def main():
     # ---- instance (synthetic, seeded; one independent instance per rank) ------------------------
     nv, off, lits = workload(args.vars, args.clauses, args.seed + rank)
     b = B.from_cnf(nv, off, lits)
+    b.opts["ere_en"] = 0 if args.no_ere else 1          # reference default: ERE on (options.cpp:28)
     del off, lits
     s = sigma.Sigma(dev)
     bi, bufs = s.alloc_pinned_like(b)
@@ -242,9 +244,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.vars, args.clauses), "literals_per_instance": lits_in,
+        "config": {"workload": workload_name(args.vars, args.clauses, not args.no_ere), "literals_per_instance": lits_in,
                    "instances_per_step": world, "l2": "inputs larger than L2 (arena %.0f MB per instance)" % (b.arena.nbytes / 1e6),
-                   "options": "reference defaults, -no-redundancy"},
+                   "options": "reference defaults" + (", -no-redundancy" if args.no_ere else "")},
         "roofline": roof,
         "e2e": {"value": total_lits / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": rep2["h2d_bytes"], "d2h_bytes_per_step": rep2["d2h_bytes"],
@@ -258,7 +260,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
         sv, sc = args.vars // args.sample_div, args.clauses // args.sample_div
-        li, secs = reference_pass(sv, sc, args.seed, runs=1)
+        li, secs = reference_pass(sv, sc, args.seed, runs=1, ere=not args.no_ere)
         line["cpu_baseline"] = {"value": li / secs[0], "unit": UNIT, "cores": 1, "kind": "reference",
                                 "sample": f"same generator at 1/{args.sample_div} size ({sv} vars / {sc} clauses / {li} literals), one run of the "
                                           f"unmodified reference, region simplify.cpp:180-206, {cpu_model()}, {os.cpu_count()} host cores "

@@ -23,10 +23,12 @@ enum SgItemKind {
     SGK_SUB,            /* n = elected                                                             */
     SGK_VE_COUNT,       /* n = elected                                                             */
     SGK_VE_EMIT,        /* n = elected                                                             */
+    SGK_ERE_PROPOSE,    /* n = elected   : one warp per variable                                   */
+    SGK_ERE_DIRTY,      /* n = elected                                                             */
     SGK_N
 };
 /* sequential stages, one thread */
-enum SgSerialKind { SGS_PROP = 0, SGS_MARKS, SGS_APPLY_UNITS, SGS_N };
+enum SgSerialKind { SGS_PROP = 0, SGS_MARKS, SGS_APPLY_UNITS, SGS_ERE_REPLAY /* one warp */, SGS_N };
 
 #ifdef __cplusplus
 extern "C++" {
@@ -55,6 +57,8 @@ uint64_t be_launch_count(void);                /* kernels launched so far by thi
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes);
 void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs,
                     sg_u4 *hdr, uint32_t *lits);
+/* one-kernel ingest for a gap-free arena (what awaken() leaves); *gap != 0 afterwards: use the general path */
+void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap);
 /* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */
 void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp);
 size_t be_scan_tmp_words(uint32_t n);
@@ -82,11 +86,13 @@ void be_sort_units(void *s, const SgView &v, uint32_t n);                       
 /* live clause / literal count (solve.hpp:661-671) and melted variable count (solve.hpp:645-654) */
 void be_count_live(void *s, const SgView &v);
 void be_count_melted(void *s, const SgView &v, uint32_t *out);
-/* compaction (simplify.cpp:235-247): flags/sizes of live clauses, then the move */
-void be_live_flags(void *s, const SgView &v, uint32_t *flags, uint32_t *sizes);
-void be_compact_move(void *s, const SgView &v, const uint32_t *newid, const uint32_t *newoff, sg_u4 *hdr2, uint32_t *lits2);
+/* compaction (simplify.cpp:235-247): scan of (live, size) over the clause ids straight from the headers
+ * (totals[0] = live clauses, totals[1] = live literals), then the move fused with the down-sweep */
+size_t be_live_tmp_words(uint32_t n_cls);
+void be_live_scan(void *s, const SgView &v, uint32_t *tmp, uint32_t *totals);
+void be_compact_apply(void *s, const SgView &v, const uint32_t *tmp, sg_u4 *hdr2, uint32_t *lits2);
 /* device store -> AoS SCNF arena + refs in the reference's layout */
-void be_export(void *s, const SgView &v, const uint32_t *newid, const uint32_t *newoff, uint32_t *arena, uint64_t *refs);
+void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *arena, uint64_t *refs);
 
 #ifdef __cplusplus
 }

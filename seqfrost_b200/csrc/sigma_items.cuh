@@ -1366,6 +1366,231 @@ SG_HDN inline void sg_ve_count_item(const SgView &v, uint32_t eidx)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* ERE: eager redundancy elimination (redundancy.cpp:26-123, redundancy.hpp:26-122)             */
+/*                                                                                              */
+/* The reference walks the elected variables in order and, for every pair of live clauses,      */
+/* builds the resolvent m, picks the shortest occurrence list among m's literals and deletes or */
+/* strengthens clauses there that m subsumes.  Unlike SUB/VE the targets lie OUTSIDE the        */
+/* variable's neighbourhood, so the sequential order matters.  Exact parallel scheme:           */
+/*  1. propose (one warp per elected variable, lanes over pairs, read-only on the pre-ERE       */
+/*     state): every pair with at least one clause c that m subsumes is recorded as an event    */
+/*     and every such c is marked `touched`.  A target only ever shrinks and its signature is   */
+/*     never refreshed, so whatever a pair can hit later it could already hit now: the events   */
+/*     are a superset of the sequential hits as long as the pair's parents are unchanged.       */
+/*  2. an elected variable with a touched clause in its lists is `dirty` (its parents can       */
+/*     change under it).                                                                         */
+/*  3. replay (one warp, elected order): a dirty variable is processed in full exactly like the */
+/*     reference, a clean one only at its recorded pairs; whenever a clause that belongs to a   */
+/*     later elected variable is modified, that variable turns dirty before it is reached.      */
+/* ------------------------------------------------------------------------------------------ */
+#define SG_ERE_MAXLEN 256
+
+/* merge_ere (redundancy.hpp:26-122): resolvent literals, signature and the literal with the shortest
+ * occurrence list (first minimum in emission order).  Returns 0 for tautologies and oversize results. */
+SG_HD int sg_merge_ere(const SgView &v, uint32_t x, const uint32_t *d1, int n1, const uint32_t *d2, int n2, int maxlen,
+                       uint32_t *out, uint32_t *sig_out, uint32_t *best_out)
+{
+    int i = 0, j = 0, n = 0;
+    uint32_t sig = 0, best = 0;
+    int minsize = 0x7fffffff;
+#define SG_ERE_PUSH(l) do { const int ls_ = (int)v.ot_len[l]; if (ls_ < minsize) { minsize = ls_; best = (l); } \
+                            sig |= SG_HASH(l); if (n < SG_ERE_MAXLEN) out[n] = (l); n++; } while (0)
+    while (i < n1 && j < n2) {
+        if (n > maxlen) return 0;
+        const uint32_t l1 = d1[i], l2 = d2[j];
+        const uint32_t v1 = SG_ABS(l1), v2 = SG_ABS(l2);
+        if (v1 == x) i++;
+        else if (v2 == x) j++;
+        else if ((l1 ^ l2) == 1u) return 0;
+        else if (v1 < v2) { i++; SG_ERE_PUSH(l1); }
+        else if (v2 < v1) { j++; SG_ERE_PUSH(l2); }
+        else { i++; j++; SG_ERE_PUSH(l1); }
+    }
+    while (i < n1) { const uint32_t l1 = d1[i++]; if (SG_ABS(l1) != x) SG_ERE_PUSH(l1); }
+    if (n > maxlen) return 0;
+    while (j < n2) { const uint32_t l2 = d2[j++]; if (SG_ABS(l2) != x) SG_ERE_PUSH(l2); }
+#undef SG_ERE_PUSH
+    if (n > maxlen) return 0;
+    *sig_out = sig; *best_out = best;
+    return n;
+}
+
+/* does the resolvent subsume c (redundancy.cpp:84)?  c is read as it is NOW */
+SG_HD bool sg_ere_hits(const SgView &v, const uint32_t *merged, int len, uint32_t sig, uint32_t c)
+{
+    const sg_u4 h = v.hdr[c];
+    if (h.z & SG_DELETED) return false;
+    return len <= (int)h.y && sg_sig_sub(sig, h.w) && sg_sub_lits(merged, len, v.lits + h.x, (int)h.y);
+}
+
+/* list setup shared by propose and replay (redundancy.cpp:44-58); false = the variable is skipped */
+SG_HD bool sg_ere_lists(const SgView &v, uint32_t x, uint32_t &dx, uint32_t &fx)
+{
+    dx = 2 * x; fx = dx | 1u;
+    if (v.ot_len[dx] > v.ot_len[fx]) { const uint32_t t = dx; dx = fx; fx = t; }
+    const int ds = (int)v.ot_len[dx], fs = (int)v.ot_len[fx];
+    const int maxoccurs = v.o.ere_max_occurs;
+    if (!(ds && fs && ds <= maxoccurs && fs <= maxoccurs)) return false;
+    const int maxsize = v.o.ere_clause_max;
+    if (SG_SIZE(v, sg_list(v, dx)[0]) > maxsize || SG_SIZE(v, sg_list(v, fx)[0]) > maxsize) return false;
+    return true;
+}
+
+SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t eidx)
+{
+    const SgLane L = sg_lane_ctx();
+    const uint32_t x = v.elected[eidx];
+    if (L.lane == 0) v.ere_eidx[x] = eidx;
+    uint32_t dx, fx;
+    if (!sg_ere_lists(v, x, dx, fx)) return;
+    const int ds = (int)v.ot_len[dx], fs = (int)v.ot_len[fx];
+    const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
+    const int maxsize = v.o.ere_clause_max;
+    uint32_t merged[SG_ERE_MAXLEN];
+    uint32_t seq = 0;
+    bool any = false;
+    const long long total = (long long)ds * fs;
+    for (long long q = L.lane; q < total; q += L.width) {
+        const int i = (int)(q / fs), j = (int)(q - (long long)i * fs);
+        const uint32_t iref = dm[i], jref = dt[j];
+        const sg_u4 hi = v.hdr[iref];
+        if (hi.z & SG_DELETED) continue;
+        const sg_u4 hj = v.hdr[jref];
+        if (hj.z & SG_DELETED) continue;
+        uint32_t sig, best;
+        const int len = sg_merge_ere(v, x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y, maxsize, merged, &sig, &best);
+        if (len < 2) continue;
+        const int nm = (int)v.ot_len[best];
+        const uint32_t *ml = sg_list(v, best);
+        bool hit = false;
+        for (int m = 0; m < nm; ++m) {
+            const uint32_t c = ml[m];
+            if (c == iref || c == jref) continue;
+            if (sg_ere_hits(v, merged, len, sig, c)) { hit = true; v.ere_touched[c] = 1; }
+        }
+        if (hit) { uint32_t s2 = ((uint32_t)i << 16) | (uint32_t)j; sg_push_unit(v, eidx, s2, 0); any = true; }
+    }
+    (void)seq;
+    if (sg_ballot(any) && L.lane == 0) v.ere_flags[eidx] |= 1u;
+}
+
+/* dirty = some clause of the variable's own lists may be modified by an event */
+SG_HD void sg_ere_dirty_item(const SgView &v, uint32_t eidx)
+{
+    const uint32_t x = v.elected[eidx];
+    for (uint32_t side = 0; side < 2; ++side) {
+        const uint32_t lit = 2 * x + side;
+        const int n = (int)v.ot_len[lit];
+        const uint32_t *d = sg_list(v, lit);
+        for (int i = 0; i < n; ++i) if (v.ere_touched[d[i]]) { v.ere_flags[eidx] |= 2u; return; }
+    }
+}
+
+/* a clause was deleted or rewritten: the elected variable it belongs to (if any, and if still ahead in the
+ * sequential order) must be processed in full */
+SG_HD void sg_ere_mark_owner(const SgView &v, uint32_t c, const uint32_t *oldlits, int oldsize, uint32_t cur_eidx)
+{
+    for (int k = 0; k < oldsize; ++k) {
+        const uint32_t u = SG_ABS(oldlits[k]);
+        const uint32_t w = v.rank[u];
+        if (SG_ER_STAT(w) == SG_E_BOTH && SG_ER_RANK(w) < v.sc->brk_rank) {
+            const uint32_t e = v.ere_eidx[u];
+            if (e > cur_eidx) v.ere_flags[e] |= 2u;
+        }
+    }
+    (void)c;
+}
+
+/* the body of the reference's pair loop for one (ci, cj) (redundancy.cpp:59-117), current state */
+SG_HDN inline void sg_ere_pair(const SgView &v, const SgLane &L, uint32_t x, uint32_t eidx, uint32_t iref, uint32_t jref, uint32_t *merged)
+{
+    const sg_u4 hi = v.hdr[iref];
+    if (hi.z & SG_DELETED) return;
+    const sg_u4 hj = v.hdr[jref];
+    if (hj.z & SG_DELETED) return;
+    const bool ciorg = !(hi.z & SG_ST_MASK), cjorg = !(hj.z & SG_ST_MASK);
+    uint32_t sig, best;
+    const int len = sg_merge_ere(v, x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y, v.o.ere_clause_max, merged, &sig, &best);
+    if (len < 2) return;
+    const int ereextend = v.o.ere_extend;
+    const int nm = (int)v.ot_len[best];
+    const uint32_t *ml = sg_list(v, best);
+    for (int base = 0; base < nm; base += (int)L.width) {
+        const int m = base + (int)L.lane;
+        bool hit = false;
+        if (m < nm) { const uint32_t c = ml[m]; hit = c != iref && c != jref && sg_ere_hits(v, merged, len, sig, c); }
+        uint32_t mask = sg_ballot(hit);
+        while (mask) {
+            const int k = sg_ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t c = ml[base + k];
+            const sg_u4 hc = v.hdr[c];
+            const bool learnt = (hc.z & SG_LEARNT) != 0, equal = len == (int)hc.y;
+            if (equal && (learnt || (ciorg && cjorg))) {
+                sg_wsync();
+                if (L.lane == 0) { sg_mark_deleted(v, c); sg_ere_mark_owner(v, c, v.lits + hc.x, (int)hc.y, eidx); }
+                sg_wsync();
+                return;                                   /* break: next pair */
+            } else if (!equal && ereextend) {
+                if (learnt && ereextend == 1) continue;
+                sg_wsync();
+                if (L.lane == 0) {
+                    sg_ere_mark_owner(v, c, v.lits + hc.x, (int)hc.y, eidx);
+                    uint32_t *l = v.lits + hc.x;
+                    for (int q = 0; q < len; ++q) l[q] = merged[q];
+                    uint32_t w0 = hc.z;
+                    if (learnt) {                         /* bumpShrunken (solve.hpp:725-737) */
+                        const int old_lbd = (int)(w0 >> SG_LBD_SH);
+                        if (old_lbd > v.o.lbd_tier1) {
+                            const int sz = len - 1, new_lbd = sz < old_lbd ? sz : old_lbd;
+                            if (new_lbd < old_lbd) w0 = (w0 & 0xFu) | (1u << SG_USAGE_SH) | ((uint32_t)new_lbd << SG_LBD_SH);
+                        }
+                    }
+                    v.hdr[c].y = (uint32_t)len;          /* signature deliberately left stale (redundancy.cpp:110-111) */
+                    v.hdr[c].z = w0;
+                }
+                sg_wsync();
+            }
+        }
+    }
+}
+
+/* ONE warp: sequential replay in elected order */
+SG_HDN inline void sg_ere_replay_serial(const SgView &v, uint32_t n_events)
+{
+    const SgLane L = sg_lane_ctx();
+    uint32_t merged[SG_ERE_MAXLEN];
+    uint32_t ep = 0;
+    for (uint32_t e = 0; e < v.n_elected; ++e) {
+        sg_wsync();
+        const uint32_t fl = sg_bcast(*(volatile uint8_t *)&v.ere_flags[e]);
+        if (!fl) continue;
+        const uint32_t x = v.elected[e];
+        while (ep < n_events && v.ubuf[ep].eidx < e) ep++;
+        if (fl & 2u) {
+            uint32_t dx, fx;
+            if (sg_ere_lists(v, x, dx, fx)) {
+                const int ds = (int)v.ot_len[dx], fs = (int)v.ot_len[fx];
+                const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
+                for (int i = 0; i < ds; ++i) {
+                    if (sg_deleted(v, dm[i])) continue;
+                    for (int j = 0; j < fs; ++j) sg_ere_pair(v, L, x, e, dm[i], dt[j], merged);
+                }
+            }
+        } else {
+            uint32_t dx, fx;
+            if (!sg_ere_lists(v, x, dx, fx)) continue;
+            const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
+            while (ep < n_events && v.ubuf[ep].eidx == e) {
+                const uint32_t key = v.ubuf[ep].seq;
+                sg_ere_pair(v, L, x, e, dm[key >> 16], dt[key & 0xffffu], merged);
+                ep++;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* BVE: emission (bounded.cpp:187-307), model records (simplify.hpp:393-423, model.hpp:65-101)  */
 /* ------------------------------------------------------------------------------------------ */
 SG_HD void sg_save_clause(const SgView &v, uint32_t c, uint32_t witlit, unsigned long long &mpos)

@@ -63,6 +63,7 @@ struct sigma_ctx {
     DBuf<uint32_t> wl0, wl1, flags, pos, acting, elected;
     DBuf<uint32_t> ve_type, ve_ncls, ve_nlits, ve_nmodel, ve_aux, ve_cls_off, ve_lit_off, ve_mod_off, scr_len, scr_off, scratch;
     DBuf<SgUnit> ubuf;
+    DBuf<uint8_t> ere_touched, ere_flags;
     DBuf<uint32_t> totals;          /* device slots for scan totals */
     DBuf<SgScalars> sc;
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
@@ -130,6 +131,7 @@ SgView make_view(sigma_ctx *c)
     v.ve_type = c->ve_type.p; v.ve_ncls = c->ve_ncls.p; v.ve_nlits = c->ve_nlits.p; v.ve_nmodel = c->ve_nmodel.p;
     v.ve_aux = c->ve_aux.p; v.ve_cls_off = c->ve_cls_off.p; v.ve_lit_off = c->ve_lit_off.p; v.ve_mod_off = c->ve_mod_off.p;
     v.scr_off = c->scr_off.p; v.scratch = c->scratch.p; v.ubuf = c->ubuf.p; v.ubuf_cap = (uint32_t)c->ubuf.cap;
+    v.ere_touched = c->ere_touched.p; v.ere_flags = c->ere_flags.p; v.ere_eidx = c->scores.p;
     v.sc = c->sc.p;
     v.nvars = c->nvars; v.nlit = c->nlit; v.n_cls = c->n_cls; v.pool_used = c->pool_used;
     v.model_base = c->model_words;
@@ -184,9 +186,13 @@ int stage_ingest(sigma_ctx *c)
     NOMEM(c->hdr.ensure(cap_cls)); NOMEM(c->lits.ensure(cap_lits));
     NOMEM(c->c_sizes.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
     NOMEM(c->scantmp.ensure(be_scan_tmp_words((uint32_t)cap_cls) + be_scan_tmp_words(c->nlit + 1) + 64));
-    be_ingest_sizes(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_sizes.p);
-    be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, nullptr, c->scantmp.p);
-    be_ingest_copy(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_newoff.p, c->hdr.p, c->lits.p);
+    be_ingest_fused(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->hdr.p, c->lits.p, c->totals.p + 8);
+    CK(pull_totals(c, 9));
+    if (c->h_totals[8]) {                                  /* arena with gaps: general path */
+        be_ingest_sizes(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_sizes.p);
+        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, nullptr, c->scantmp.p);
+        be_ingest_copy(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_newoff.p, c->hdr.p, c->lits.p);
+    }
     c->n_cls = n;
     c->pool_used = (uint32_t)L;
     return SIGMA_OK;
@@ -313,6 +319,17 @@ int apply_units(sigma_ctx *c, SgView &v)
     return SIGMA_OK;
 }
 
+/* sortOT (simplify.cpp:85-100) */
+int stage_sortot(sigma_ctx *c)
+{
+    const uint32_t E = c->hsc.n_elected;
+    Stage st(c, SIGMA_T_SOT);
+    SgView v = make_view(c);
+    v.n_elected = E;
+    be_items(c->stream, SGK_SORTOT, v, 2 * E);
+    return SIGMA_OK;
+}
+
 int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
 {
     const uint32_t E = c->hsc.n_elected;
@@ -324,10 +341,6 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     v.n_elected = E;
     v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
     v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
-    {
-        Stage st(c, SIGMA_T_SOT);
-        be_items(c->stream, SGK_SORTOT, v, 2 * E);
-    }
     /* scratch slices + unit buffer sized from the elected lists */
     v.scr_off = c->scr_len.p;              /* SGK_SCRATCH_LEN writes lengths through scr_off */
     be_items(c->stream, SGK_SCRATCH_LEN, v, E);
@@ -374,6 +387,37 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     return SIGMA_OK;
 }
 
+/* ERE (redundancy.cpp:26-123): propose in parallel, replay the few recorded pairs in sequential order */
+int stage_ere(sigma_ctx *c)
+{
+    if (!c->opts.ere_en) return SIGMA_OK;
+    if (c->opts.ere_clause_max > 256) return fail(c, SIGMA_E_UNSUPPORTED, "--redundancyclausemax above 256 is not supported");
+    if (c->opts.ere_max_occurs > 65535) return fail(c, SIGMA_E_UNSUPPORTED, "--redundancymaxoccurs above 65535 is not supported");
+    const uint32_t E = c->hsc.n_elected;
+    if (!E) return SIGMA_OK;
+    NOMEM(c->ere_touched.ensure((size_t)c->n_cls + 16)); NOMEM(c->ere_flags.ensure((size_t)E + 16));
+    NOMEM(c->ubuf.ensure((size_t)(1u << 20) + 4ull * E));
+    Stage st(c, SIGMA_T_ERE);
+    be_memset(c->stream, c->ere_touched.p, 0, c->n_cls);
+    be_memset(c->stream, c->ere_flags.p, 0, E);
+    c->hsc.n_units = 0;
+    CK(push_scalars(c));
+    SgView v = make_view(c);
+    v.n_elected = E;
+    be_items(c->stream, SGK_ERE_PROPOSE, v, E);
+    CK(pull_scalars(c));
+    const uint32_t n = c->hsc.n_units;
+    if (n > c->ubuf.cap) return fail(c, SIGMA_E_UNSUPPORTED, "ERE event buffer overflow");
+    if (n) {
+        be_sort_units(c->stream, v, n);
+        be_items(c->stream, SGK_ERE_DIRTY, v, E);
+        be_serial(c->stream, SGS_ERE_REPLAY, v, n);
+    }
+    c->hsc.n_units = 0;
+    CK(push_scalars(c));
+    return SIGMA_OK;
+}
+
 int stage_count(sigma_ctx *c)
 {
     {
@@ -388,22 +432,18 @@ int stage_count(sigma_ctx *c)
 int stage_compact(sigma_ctx *c)
 {
     const uint32_t n = c->n_cls;
-    NOMEM(c->c_flags.ensure(n + 1)); NOMEM(c->c_sizes.ensure(n + 1));
-    NOMEM(c->c_newid.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
-    NOMEM(c->scantmp.ensure(be_scan_tmp_words(n) + 64));
+    NOMEM(c->scantmp.ensure(be_live_tmp_words(n) + 64));
     uint32_t ncls, nlits;
     {
         Stage st(c, SIGMA_T_GC);
         SgView v = make_view(c);
-        be_live_flags(c->stream, v, c->c_flags.p, c->c_sizes.p);
-        be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
-        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, c->totals.p + 1, c->scantmp.p);
+        be_live_scan(c->stream, v, c->scantmp.p, c->totals.p);
         CK(pull_totals(c, 2));
         ncls = c->h_totals[0]; nlits = c->h_totals[1];
         const size_t cap_cls = (size_t)ncls + ncls / 2 + (1u << 16);
         const size_t cap_lits = (size_t)nlits + nlits / 2 + (1u << 18);
         NOMEM(c->hdr2.ensure(cap_cls)); NOMEM(c->lits2.ensure(cap_lits));
-        be_compact_move(c->stream, v, c->c_newid.p, c->c_newoff.p, c->hdr2.p, c->lits2.p);
+        be_compact_apply(c->stream, v, c->scantmp.p, c->hdr2.p, c->lits2.p);
         c->rep.stage_bytes[SIGMA_T_GC] += 4ull * c->pool_used + 16ull * n + 4ull * nlits + 16ull * ncls;
     }
     { DBuf<sg_u4> t = c->hdr; c->hdr = c->hdr2; c->hdr2 = t; }
@@ -417,18 +457,14 @@ int stage_compact(sigma_ctx *c)
 int stage_export(sigma_ctx *c)
 {
     const uint32_t n = c->n_cls;
-    NOMEM(c->c_flags.ensure(n + 1)); NOMEM(c->c_sizes.ensure(n + 1));
-    NOMEM(c->c_newid.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
-    NOMEM(c->scantmp.ensure(be_scan_tmp_words(n) + 64));
+    NOMEM(c->scantmp.ensure(be_live_tmp_words(n) + 64));
     Stage st(c, SIGMA_T_EXPORT);
     SgView v = make_view(c);
-    be_live_flags(c->stream, v, c->c_flags.p, c->c_sizes.p);
-    be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
-    be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, c->totals.p + 1, c->scantmp.p);
+    be_live_scan(c->stream, v, c->scantmp.p, c->totals.p);
     CK(pull_totals(c, 2));
     const uint32_t ncls = c->h_totals[0], nlits = c->h_totals[1];
     NOMEM(c->arena_out.ensure(3ull * ncls + nlits + 16)); NOMEM(c->refs_out.ensure((size_t)ncls + 16));
-    be_export(c->stream, v, c->c_newid.p, c->c_newoff.p, c->arena_out.p, c->refs_out.p);
+    be_export_apply(c->stream, v, c->scantmp.p, c->arena_out.p, c->refs_out.p);
     c->out_ncls = ncls; c->out_literals = nlits; c->out_buckets = 3ull * ncls + nlits;
     c->rep.stage_bytes[SIGMA_T_EXPORT] += 4ull * c->pool_used + 16ull * n + 4ull * nlits + 20ull * ncls;
     return SIGMA_OK;
@@ -440,8 +476,8 @@ bool stop_here(sigma_ctx *c, int phase, int stage) { return c->stop_phase == pha
 int run_phases(sigma_ctx *c)
 {
     const sigma_opts &o = c->opts;
-    if (o.ere_en || o.bce_en || o.all_en)
-        return fail(c, SIGMA_E_UNSUPPORTED, "ERE/BCE are not built yet: run with -no-redundancy (and without -blocked/-all)");
+    if (o.bce_en || o.all_en)
+        return fail(c, SIGMA_E_UNSUPPORTED, "BCE is not built yet: run without -blocked/-all");
     if (o.proof_en) return fail(c, SIGMA_E_UNSUPPORTED, "DRAT proof emission from the device pass is not built");
     if (o.collect_freq <= 0) return fail(c, SIGMA_E_ARG, "collect_freq must be positive");
     CK(stage_ingest(c));
@@ -462,8 +498,9 @@ int run_phases(sigma_ctx *c)
         CK(stage_lcve(c, phase, multiplier, !had_units, &enough));
         if (stop_here(c, phase, SIGMA_T_ELECT)) return SIGMA_OK;
         if (!enough) break;
+        CK(stage_sortot(c));
         if (phase == o.phases || (diff <= o.phase_lits_min && phase > 2)) {
-            /* ERE() would run here (simplify.cpp:188); it still needs sortOT's lists */
+            CK(stage_ere(c));                               /* simplify.cpp:189 */
             break;
         }
         CK(stage_sub_ve(c, multiplier));
@@ -527,7 +564,7 @@ void sigma_destroy(sigma_ctx *c)
         c->sorttmp.release(); c->scantmp.release(); c->wl0.release(); c->wl1.release(); c->flags.release(); c->pos.release();
         c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
         c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
-        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->totals.release(); c->sc.release();
+        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release(); c->totals.release(); c->sc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
         c->arena_out.release(); c->refs_out.release();
         for (void *e2 : c->evpool) be_event_destroy(e2);

@@ -116,6 +116,9 @@ typedef struct SgView {
     uint32_t *scr_off;       /* per elected variable scratch slice in `scratch` */
     uint32_t *scratch;
     SgUnit   *ubuf;
+    uint8_t  *ere_touched;   /* per clause: may be deleted/strengthened by ERE */
+    uint8_t  *ere_flags;     /* per elected variable: 1 = has recorded pairs, 2 = dirty */
+    uint32_t *ere_eidx;      /* variable -> position in `elected` */
     SgScalars *sc;
     uint32_t nvars, nlit;    /* nlit = 2*nvars + 2 */
     uint32_t n_cls;          /* clause ids in use */

@@ -59,6 +59,19 @@ void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32
     g_launches++;
     for (uint32_t i = 0; i < n; ++i) sizes[i] = arena[refs[i] + 2];
 }
+void be_ingest_fused(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap)
+{
+    g_launches++;
+    *gap = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t r = refs[i];
+        const uint32_t size = arena[r + 2];
+        if ((i + 1 < n && refs[i + 1] != r + 3 + size) || (i == 0 && r != 0) || r < 3ull * i) { *gap = 1; return; }
+        sg_u4 h; h.x = (uint32_t)(r - 3ull * i); h.y = size; h.z = arena[r]; h.w = arena[r + 1];
+        hdr[i] = h;
+        for (uint32_t k = 0; k < size; ++k) lits[h.x + k] = arena[r + 3 + k];
+    }
+}
 void be_ingest_copy(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs, sg_u4 *hdr, uint32_t *lits)
 {
     g_launches++;
@@ -171,6 +184,8 @@ void be_items(void *, int kind, const SgView &v, uint32_t n)
         case SGK_SUB: sg_sub_item(v, i); break;
         case SGK_VE_COUNT: sg_ve_count_item(v, i); break;
         case SGK_VE_EMIT: sg_ve_emit_item(v, i); break;
+        case SGK_ERE_PROPOSE: sg_ere_propose_item(v, i); break;
+        case SGK_ERE_DIRTY: sg_ere_dirty_item(v, i); break;
         default: abort();
         }
     }
@@ -182,6 +197,7 @@ void be_serial(void *, int kind, const SgView &v, uint32_t arg)
     case SGS_PROP: sg_prop_serial(v); break;
     case SGS_MARKS: sg_marks_serial(v, arg); break;
     case SGS_APPLY_UNITS: sg_apply_units_serial(v, arg); break;
+    case SGS_ERE_REPLAY: sg_ere_replay_serial(v, arg); break;
     default: abort();
     }
 }
@@ -204,34 +220,37 @@ void be_count_melted(void *, const SgView &v, uint32_t *out)
     for (uint32_t x = 1; x <= v.nvars; ++x) if (v.state[x] & SG_MELTED_M) n++;
     *out = n;
 }
-void be_live_flags(void *, const SgView &v, uint32_t *flags, uint32_t *sizes)
-{
+size_t be_live_tmp_words(uint32_t n_cls) { return 2ull * n_cls + 4; }
+void be_live_scan(void *, const SgView &v, uint32_t *tmp, uint32_t *totals)
+{   /* tmp[2c], tmp[2c+1] = new id / new offset of clause c */
     g_launches++;
+    uint32_t id = 0, off = 0;
     for (uint32_t c = 0; c < v.n_cls; ++c) {
-        const bool live = !(v.hdr[c].z & SG_DELETED);
-        flags[c] = live; sizes[c] = live ? v.hdr[c].y : 0;
+        tmp[2 * c] = id; tmp[2 * c + 1] = off;
+        if (!(v.hdr[c].z & SG_DELETED)) { id++; off += v.hdr[c].y; }
     }
+    totals[0] = id; totals[1] = off;
 }
-void be_compact_move(void *, const SgView &v, const uint32_t *newid, const uint32_t *newoff, sg_u4 *hdr2, uint32_t *lits2)
+void be_compact_apply(void *, const SgView &v, const uint32_t *tmp, sg_u4 *hdr2, uint32_t *lits2)
 {
     g_launches++;
     for (uint32_t c = 0; c < v.n_cls; ++c) {
         if (v.hdr[c].z & SG_DELETED) continue;
         sg_u4 h = v.hdr[c];
         const uint32_t *l = v.lits + h.x;
-        h.x = newoff[c];
-        hdr2[newid[c]] = h;
+        h.x = tmp[2 * c + 1];
+        hdr2[tmp[2 * c]] = h;
         for (uint32_t k = 0; k < h.y; ++k) lits2[h.x + k] = l[k];
     }
 }
-void be_export(void *, const SgView &v, const uint32_t *newid, const uint32_t *newoff, uint32_t *arena, uint64_t *refs)
+void be_export_apply(void *, const SgView &v, const uint32_t *tmp, uint32_t *arena, uint64_t *refs)
 {
     g_launches++;
     for (uint32_t c = 0; c < v.n_cls; ++c) {
         if (v.hdr[c].z & SG_DELETED) continue;
         const sg_u4 h = v.hdr[c];
-        const uint64_t r = 3ull * newid[c] + newoff[c];
-        refs[newid[c]] = r;
+        const uint64_t r = 3ull * tmp[2 * c] + tmp[2 * c + 1];
+        refs[tmp[2 * c]] = r;
         arena[r] = h.z; arena[r + 1] = h.w; arena[r + 2] = h.y;
         for (uint32_t k = 0; k < h.y; ++k) arena[r + 3 + k] = v.lits[h.x + k];
     }

@@ -38,6 +38,13 @@ CASES = [
     ("fuzz_unsat_b", "fuzz_mix", dict(seed=101), []),
     ("fuzz_ok_a", "fuzz_mix", dict(seed=0), []),
     ("fuzz_ok_b", "fuzz_mix", dict(seed=2), []),
+    # ERE on (reference default): "+ere" = do not pass -no-redundancy
+    ("ere_gates", "gate_circuit", dict(nvars=3000, seed=11), ["+ere"]),
+    ("ere_gates_w200", "gate_circuit", dict(nvars=2500, seed=31, window=200), ["+ere"]),
+    ("ere_ksat3", "random_ksat", dict(nvars=2000, nclauses=8520, k=3, seed=1), ["+ere"]),
+    ("ere_xorphp", "xor_php_mix", dict(nclauses=6000, seed=4), ["+ere"]),
+    ("ere_extend2", "gate_circuit", dict(nvars=2500, seed=32), ["+ere", "--redundancyextend=2"]),
+    ("ere_fuzz", "fuzz_mix", dict(seed=5), ["+ere"]),
     # LATER calls: the reference's own first simplify() + 3000 conflicts of its CDCL loop run first
     # (ref_harness --presolve-conflicts), so the store holds learnt clauses and stats.simplify.calls == 2
     ("later_ksat3", "random_ksat", dict(nvars=2000, nclauses=7800, k=3, seed=6), ["--presolve-conflicts=3000"]),
@@ -57,7 +64,8 @@ def main():
             for f in (fin, fout):
                 if os.path.exists(f):
                     os.remove(f)
-            r = subprocess.run([REF, cnf, "-no-redundancy", "-quiet", f"--sgin={fin}", f"--sgout={fout}"] + opts,
+            base = [] if "+ere" in opts else ["-no-redundancy"]
+            r = subprocess.run([REF, cnf, *base, "-quiet", f"--sgin={fin}", f"--sgout={fout}"] + [o for o in opts if o != "+ere"],
                                capture_output=True, text=True)
             print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"rc={r.returncode}",
                   os.path.getsize(fin), os.path.getsize(fout))

@@ -23,7 +23,7 @@ ANSI = re.compile(r"\x1b\[[0-9;]*m")
 
 
 def _digest(exe, cnf, opts):
-    r = subprocess.run([exe, cnf, "-no-redundancy", "-model", "-modelverify", "-no-modelprint", "-report", *opts],
+    r = subprocess.run([exe, cnf, "-model", "-modelverify", "-no-modelprint", "-report", *opts],     # reference defaults (ERE on)
                        capture_output=True, text=True, timeout=120)
     lines = [ANSI.sub("", l).strip() for l in r.stdout.splitlines()]
     return [l for l in lines if any(k in l for k in KEYS) and "ORG" not in l], r.stdout[-400:] + r.stderr[-400:]
