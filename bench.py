@@ -163,7 +163,8 @@ def main():
     dev = local if world > 1 else 0
 
     # ---- instance (synthetic, seeded; one independent instance per rank) ------------------------
-    nv, off, lits = workload(args.vars, args.clauses, args.seed + rank)
+    from seqfrost_b200 import batch
+    nv, off, lits = workload(args.vars, args.clauses, batch.rank_seed(args.seed, rank))
     b = B.from_cnf(nv, off, lits)
     b.opts["ere_en"] = 0 if args.no_ere else 1          # reference default: ERE on (options.cpp:28)
     del off, lits
@@ -177,11 +178,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return batch.max_over_ranks(x, dist, f"cuda:{dev}")
 
     # ---- device-resident arm: sigma_execute on the uploaded formula ------------------------------
     s.upload(bi)
@@ -221,8 +218,8 @@ def main():
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     rep2 = s.report()
 
-    total_lits = lits_in * world * args.steps
-    value = total_lits / (dev_ms / 1e3)
+    total_lits = batch.sum_over_ranks(lits_in, dist, f"cuda:{dev}") * args.steps     # all ranks' instances
+    value = batch.throughput(total_lits, dev_ms)
     # ---- roofline of the dominant streaming stage ------------------------------------------------
     peaks = {}
     try:
@@ -248,7 +245,7 @@ def main():
                    "instances_per_step": world, "l2": "inputs larger than L2 (arena %.0f MB per instance)" % (b.arena.nbytes / 1e6),
                    "options": "reference defaults" + (", -no-redundancy" if args.no_ere else "")},
         "roofline": roof,
-        "e2e": {"value": total_lits / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+        "e2e": {"value": batch.throughput(total_lits, e2e_ms), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": rep2["h2d_bytes"], "d2h_bytes_per_step": rep2["d2h_bytes"],
                 "h2d_ms": rep2["stage_ms"]["h2d"], "d2h_ms": rep2["stage_ms"]["d2h"]},
         "gpu_launches": launches, "clocks": clocks,

@@ -8,7 +8,7 @@
 // top-level control flow (solve.cpp:155-181, simplify.cpp:102-116,155-233) and swaps the phase
 // loop simplify.cpp:180-210 for one sigma_run() call.  Usage is the reference CLI's:
 //
-//     seqfrost_sigma <formula.cnf> [reference options]        (needs -no-redundancy for now)
+//     seqfrost_sigma <formula.cnf> [reference options]
 //
 // Build: g++ -std=c++17 -O3 -DNDEBUG -DSTATISTICS -I<reference>/src
 //     seqfrost_sigma.cpp libseqfrost.a -L. -lsigma_b200
