@@ -243,13 +243,54 @@ SG_HDN inline void sg_std_sort(const SgView &v, uint32_t *d, int n)
     } else sg_std_insertion_sort(v, d, 0, n);
 }
 
+/* short lists (the common case): fetch every key once, then run the reference's insertion sort
+ * (sort.hpp:92-108) on the local copies - the same comparisons in the same order, so the same result */
+struct SgKey { uint32_t size, first, last, sig; };
+SG_HD bool sg_key_lt(const SgKey &x, const SgKey &y)
+{   /* CNF_CMP_KEY (simplify.hpp:30-47) */
+    if ((int)x.size < (int)y.size) return true;
+    if ((int)x.size > (int)y.size) return false;
+    if (x.first < y.first) return true;
+    if (x.first > y.first) return false;
+    if (x.last < y.last) return true;
+    if (x.last > y.last) return false;
+    return x.sig < y.sig;
+}
+SG_HDN inline void sg_sortot_small(const SgView &v, uint32_t *d, int size)
+{
+    SgKey key[24];
+    uint32_t id[24];
+    for (int i = 0; i < size; ++i) {
+        id[i] = d[i];
+        const sg_u4 h = v.hdr[id[i]];
+        key[i].size = h.y; key[i].sig = h.w;
+        key[i].first = v.lits[h.x]; key[i].last = v.lits[h.x + h.y - 1];
+    }
+    bool moved = false;
+    if (size == 2) {
+        if (sg_key_lt(key[1], key[0])) { const uint32_t t = id[0]; id[0] = id[1]; id[1] = t; moved = true; }
+    } else {
+        for (int i = 1; i < size; ++i) {
+            if (sg_key_lt(key[i], key[i - 1])) {
+                const SgKey tk = key[i];
+                const uint32_t ti = id[i];
+                int j = i, j1 = i - 1;
+                do { key[j] = key[j1]; id[j] = id[j1]; j--; } while (j != 0 && sg_key_lt(tk, key[--j1]));
+                key[j] = tk; id[j] = ti;
+                moved = true;
+            }
+        }
+    }
+    if (moved) for (int i = 0; i < size; ++i) d[i] = id[i];
+}
+
 /* one occurrence list of an elected variable */
 SG_HDN inline void sg_sortot_item(const SgView &v, uint32_t lit)
 {
     const int n = (int)v.ot_len[lit];
     if (n < 2) return;
     uint32_t *d = sg_list(v, lit);
-    if (n <= 24) sg_ins_sort_ref(v, d, n);
+    if (n <= 24) sg_sortot_small(v, d, n);
     else {
         sg_std_sort(v, d, n);
         uint32_t ties = 0;
@@ -535,14 +576,20 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
         const int size = (int)h.y;
         if (size > maxcsize) { if (neg) failn = true; else failp = true; }
         const uint32_t *l = v.lits + h.x;
-        for (int k = 0; k < size; ++k) {
-            const uint32_t other = l[k], u = SG_ABS(other);
-            if (u == cand) continue;
-            const uint32_t w = sg_er_load(v, u);
-            if (SG_ER_RANK(w) > rc) continue;
-            const uint32_t s = SG_ER_STAT(w);
-            if (s == SG_E_UNDECIDED) blocked = true;
-            else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other))) frozen = true;
+        for (int base = 0; base < size; base += 8) {
+            /* literals first, then their election words: independent loads in flight together */
+            uint32_t other[8], w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) other[k] = base + k < size ? l[base + k] : 2 * cand;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = SG_ABS(other[k]) == cand ? 0xFFFFFFFFu : sg_er_load(v, SG_ABS(other[k]));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (w[k] == 0xFFFFFFFFu || SG_ER_RANK(w[k]) > rc) continue;
+                const uint32_t s = SG_ER_STAT(w[k]);
+                if (s == SG_E_UNDECIDED) blocked = true;
+                else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other[k]))) frozen = true;
+            }
         }
     }
     const uint32_t flags = sg_wor((blocked ? 1u : 0u) | (frozen ? 2u : 0u) | (failp ? 4u : 0u) | (failn ? 8u : 0u));
@@ -563,11 +610,15 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
             const sg_u4 h = v.hdr[q >= np ? dn[q - np] : dp[q]];
             if (h.z & SG_DELETED) continue;
             const uint32_t *l = v.lits + h.x;
-            for (int k = 0; k < (int)h.y; ++k) {
-                const uint32_t u = SG_ABS(l[k]);
-                if (u == cand) continue;
-                const uint32_t w = sg_er_load(v, u);
-                if (SG_ER_STAT(w) == SG_E_UNDECIDED && SG_ER_RANK(w) > rc) sg_er_freeze(v, u, w);
+            for (int base = 0; base < (int)h.y; base += 8) {
+                uint32_t u[8], w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) u[k] = base + k < (int)h.y ? SG_ABS(l[base + k]) : cand;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = u[k] == cand ? 0xFFFFFFFFu : sg_er_load(v, u[k]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (w[k] != 0xFFFFFFFFu && SG_ER_STAT(w[k]) == SG_E_UNDECIDED && SG_ER_RANK(w[k]) > rc) sg_er_freeze(v, u[k], w[k]);
             }
         }
     }

@@ -269,14 +269,24 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         /* rank-ordered batches of geometrically growing size: inside a batch, pull rounds until every
          * candidate is decided; acting candidates push FROZEN onto their undecided neighbours, so the
          * later (large) batches hold few candidates that are still undecided */
-        uint32_t r0 = 0, bsize = 4096;
+        static long env_b0 = -1, env_grow = -1, env_rps = -1;
+        if (env_b0 < 0) {
+            const char *e;
+            env_b0 = (e = getenv("SIGMA_ELECT_B0")) ? atol(e) : 4096;
+            env_grow = (e = getenv("SIGMA_ELECT_GROW")) ? atol(e) : 4;
+            env_rps = (e = getenv("SIGMA_ELECT_RPS")) ? atol(e) : 3;
+            if (env_b0 < 32) env_b0 = 32;
+            if (env_grow < 2) env_grow = 2;
+            if (env_rps < 1) env_rps = 1;
+        }
+        uint32_t r0 = 0, bsize = (uint32_t)env_b0;
         while (r0 < V) {
             const uint32_t r1 = (V - r0 <= bsize) ? V : r0 + bsize;
             be_memset(c->stream, &c->sc.p->wl_count[0], 0, 2 * sizeof(uint32_t));
             be_elect_batch(c->stream, v, r0, r1, c->wl0.p);
             int parity = 0;
             while (true) {
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < (int)env_rps; ++k) {
                     be_elect_round(c->stream, v, parity ? c->wl1.p : c->wl0.p, parity ? c->wl0.p : c->wl1.p, parity);
                     parity ^= 1;
                     rounds++;
@@ -287,7 +297,7 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
             }
             if (c->hsc.brk_rank < r1) break;               /* the sequential loop ended inside this batch */
             r0 = r1;
-            if (bsize < (1u << 30)) bsize *= 4;
+            if (bsize < (1u << 28)) bsize *= (uint32_t)env_grow;
         }
         /* acting / elected candidates in election order, cut at the break (lcve.cpp:70,73) */
         be_acting_flags(c->stream, v, c->flags.p, c->flags.p + V);
