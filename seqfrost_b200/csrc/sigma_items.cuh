@@ -1217,7 +1217,20 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
         if (idx < nd) {
             const sg_u4 h = v.hdr[dd[idx]];
             const int size = (int)h.y;
-            if (!(h.z & SG_ST_MASK) && size >= 3 && size - 1 <= maxarity && size <= 24) complete = sg_xor_complete(v, dd[idx], size);
+            if (!(h.z & SG_ST_MASK) && size >= 3 && size - 1 <= maxarity && size <= 24) {
+                /* necessary condition, from the headers of the variable's own two lists only: the 2^arity clauses
+                 * of an XOR are over ONE variable set and all contain x or -x, so at least 2^arity original
+                 * clauses of this size with the same sign-blind signature must be in the two lists */
+                const uint32_t wide = h.w | ((h.w & 0xAAAAAAAAu) >> 1) | ((h.w & 0x55555555u) << 1);
+                int same = 0;
+                for (int q = 0; q < nd + nf; ++q) {
+                    const sg_u4 g = v.hdr[q < nd ? dd[q] : df[q - nd]];
+                    if ((g.z & SG_ST_MASK) || (int)g.y != size) continue;
+                    const uint32_t gw = g.w | ((g.w & 0xAAAAAAAAu) >> 1) | ((g.w & 0x55555555u) << 1);
+                    if (gw == wide) same++;
+                }
+                if (same >= (1 << (size - 1))) complete = sg_xor_complete(v, dd[idx], size);
+            }
         }
         const uint32_t m = sg_ballot(complete);
         if (!m) continue;

@@ -290,14 +290,36 @@ __global__ void k_elect_batch(SgView v, uint32_t r0, uint32_t r1, uint32_t *__re
 }
 
 __global__ void k_elect_round(SgView v, const uint32_t *__restrict__ wl_in, uint32_t *__restrict__ wl_out, int parity)
-{   /* one warp per queued candidate */
+{   /* one warp per queued candidate; still-undecided candidates are re-queued through a per-warp buffer so
+     * that the single queue counter sees one atomic per 32 candidates (same-address atomics serialise in L2) */
+    __shared__ uint32_t s_buf[4][32];
     const uint32_t n = v.sc->wl_count[parity];
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t held = 0;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
         __syncwarp();
         const uint32_t cand = wl_in[i];
         const bool stay = sg_elect_round_item(v, cand);
-        if (stay && (threadIdx.x & 31) == 0) wl_out[atomicAdd(&v.sc->wl_count[parity ^ 1], 1u)] = cand;
+        if (stay) {
+            if (lane == 0) s_buf[wib][held] = cand;
+            held++;
+            if (held == 32) {
+                __syncwarp();
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&v.sc->wl_count[parity ^ 1], 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                wl_out[base + lane] = s_buf[wib][lane];
+                held = 0;
+            }
+        }
+    }
+    __syncwarp();
+    if (held) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&v.sc->wl_count[parity ^ 1], held);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < held) wl_out[base + lane] = s_buf[wib][lane];
     }
 }
 
