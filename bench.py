@@ -228,7 +228,7 @@ def main():
     except OSError:
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    streaming = [k for k in ("ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "vo", "count", "gc", "export") if stage_bytes.get(k)]
+    streaming = [k for k in ("ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "ot_update", "vo", "count", "gc", "export") if stage_bytes.get(k)]
     dom = max(streaming, key=lambda k: stage_ms[k])
     dom_launches = max(1, stage_launches[dom])
     ach = stage_bytes[dom] / 1e9 / (stage_ms[dom] / 1e3)

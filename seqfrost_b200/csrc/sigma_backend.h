@@ -66,6 +66,27 @@ size_t be_scan_tmp_words(uint32_t n);
 void be_hist(void *s, const SgView &v, uint32_t *counts);
 /* scatter clause ids into the lists; cursor must hold a copy of ot_off (absolute write positions) */
 void be_scatter(void *s, const SgView &v, uint32_t *cursor);
+/* Incremental createOT for phases after the first.  The occurrence table the reference rebuilds from
+ * scratch (simplify.cpp:39-61) differs from the table at the end of the previous phase only by: deleted
+ * clauses (dropped), lists of eliminated variables (emptied), the order inside the elected lists (sortOT),
+ * clause renumbering by shrinkSimp (newid, or NULL), the clauses with id >= first_new (resolvents) and the
+ * (literal, clause) pairs in v.ot_add (equivalence substitution).  Writes the new table into
+ * off2/len2/data2 exactly as a full rebuild would.  tmp: be_ot_update_tmp_words() words. */
+struct SgOtUpdate {
+    int      renumber;          /* the store was compacted since be_ot_prepare: clause ids change to their rank among the live */
+    uint32_t n_cls_old;         /* clause ids covered by the old numbering */
+    uint32_t first_new;         /* first clause id (OLD numbering) that has no entry in the old table */
+    uint32_t n_add;             /* pairs in v.ot_add (old numbering) */
+    uint32_t *off2, *len2, *data2, *tmp, *total;
+};
+size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls);
+/* step 1, on the store BEFORE an optional compaction: liveness bitmap + rank prefix of the old clause ids */
+void be_ot_prepare(void *s, const SgView &v, uint32_t *tmp);
+/* step 2, on the store AFTER it: v = new store + old table */
+void be_ot_update(void *s, const SgView &v, const SgOtUpdate &u);
+/* compare two occurrence tables entry by entry (test hook); *mismatch receives the number of differences */
+void be_ot_compare(void *s, const SgView &v, const uint32_t *off2, const uint32_t *len2, const uint32_t *data2, uint32_t *mismatch);
+
 /* scores[v] = ps*ns (uint32 wrap, histogram.hpp:23), order[v-1] = v */
 void be_scores(void *s, const SgView &v);
 /* stable ascending sort of (keys, vals); result in keys/vals; tmp arrays of n each */

@@ -1683,12 +1683,20 @@ SG_HD uint32_t sg_substitute_clause(const SgView &v, uint32_t c, uint32_t dx, ui
     uint32_t *l = SG_LITS(v, c);
     const int size = SG_SIZE(v, c);
     int j = 0;
+    bool had_def = false;
     for (int i = 0; i < size; ++i) {
         const uint32_t lit = l[i];
         if (lit == dx) l[j++] = def;
         else if (lit != def) l[j++] = lit;
+        else had_def = true;
     }
     v.hdr[c].y = (uint32_t)j;
+    /* the clause now occurs in the list of `def` (it did already if a copy of `def` was dropped): remembered
+     * for the incremental occurrence-table update of the next phase */
+    if (!had_def && v.ot_add) {
+        const uint32_t k = sg_atomic_add(&v.sc->n_ot_add, 1u);
+        if (k < v.ot_add_cap) { v.ot_add[2 * k] = def; v.ot_add[2 * k + 1] = c; }
+    }
     if (j == 1) return l[0];
     sg_sort_lits(l, j);
     uint32_t sig = 0;

@@ -544,6 +544,130 @@ __global__ void k_live_apply(SgView v, const uint2 *__restrict__ part, uint4 *__
     }
 }
 
+/* ---------------------------------------------------------------------------------------------- */
+/* incremental occurrence-table update (see sigma_backend.h)                                         */
+/* ---------------------------------------------------------------------------------------------- */
+struct OtuTmp { uint32_t *bits, *prefix, *kept, *addc, *cursor, *flag, *scan; uint32_t words; };
+__host__ __device__ inline OtuTmp otu_layout(uint32_t *tmp, uint32_t nlit, uint32_t n_cls)
+{
+    OtuTmp t;
+    t.words = n_cls / 32 + 1;
+    t.bits = tmp; t.prefix = t.bits + t.words; t.kept = t.prefix + t.words + 1; t.addc = t.kept + nlit;
+    t.cursor = t.addc + nlit; t.flag = t.cursor + nlit; t.scan = t.flag + nlit;
+    return t;
+}
+__device__ __forceinline__ bool otu_live(const uint32_t *bits, uint32_t c) { return (bits[c >> 5] >> (c & 31)) & 1u; }
+__device__ __forceinline__ uint32_t otu_rank(const uint32_t *bits, const uint32_t *prefix, uint32_t c)
+{
+    return prefix[c >> 5] + __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u));
+}
+
+__global__ void k_otu_bitmap(SgView v, uint32_t *__restrict__ bits, uint32_t *__restrict__ pop)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < v.n_cls && !(v.hdr[c].z & SG_DELETED);
+    const uint32_t m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && (c >> 5) <= v.n_cls / 32) { bits[c >> 5] = m; pop[c >> 5] = __popc(m); }
+}
+
+__global__ void k_otu_count(SgView v, const uint32_t *__restrict__ bits, uint32_t *__restrict__ kept, uint32_t *__restrict__ flag)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit >= v.nlit) return;
+    uint32_t n = 0, unsorted = 0;
+    if (!(v.state[lit >> 1] & SG_MELTED_M)) {
+        const uint32_t len = v.ot_len[lit];
+        const uint32_t *d = v.ot_data + v.ot_off[lit];
+        uint32_t prev = 0;
+        for (uint32_t i = 0; i < len; ++i) {
+            const uint32_t c = d[i];
+            if (!otu_live(bits, c)) continue;
+            if (n && c < prev) unsorted = 1;
+            prev = c; n++;
+        }
+    }
+    kept[lit] = n;
+    flag[lit] = unsorted;
+}
+
+/* occurrences that are not in the old table: literals of the clauses created last phase ... */
+__global__ void k_otu_new_clauses(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber,
+                                  uint32_t first_new, uint32_t n_cls_old, uint32_t *__restrict__ ctr, uint32_t *__restrict__ flag,
+                                  uint32_t *__restrict__ data2)
+{
+    const uint32_t c = first_new + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cls_old || !otu_live(bits, c)) return;
+    const uint32_t id = renumber ? otu_rank(bits, prefix, c) : c;
+    const uint4 h = v.hdr[id];
+    const uint32_t *l = v.lits + h.x;
+    for (uint32_t k = 0; k < h.y; ++k) {
+        const uint32_t pos = atomicAdd(&ctr[l[k]], 1u);
+        if (data2) data2[pos] = id; else flag[l[k]] = 1;
+    }
+}
+/* ... and the (literal, clause) pairs created by equivalence substitution */
+__global__ void k_otu_pairs(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber, uint32_t n,
+                            uint32_t *__restrict__ ctr, uint32_t *__restrict__ flag, uint32_t *__restrict__ data2)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lit = v.ot_add[2 * i], c = v.ot_add[2 * i + 1];
+    if (!otu_live(bits, c)) return;
+    const uint32_t pos = atomicAdd(&ctr[lit], 1u);
+    if (data2) data2[pos] = renumber ? otu_rank(bits, prefix, c) : c; else flag[lit] = 1;
+}
+
+__global__ void k_otu_len(uint32_t nlit, const uint32_t *__restrict__ kept, const uint32_t *__restrict__ addc, uint32_t *__restrict__ len2)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit < nlit) len2[lit] = kept[lit] + addc[lit];
+}
+
+__global__ void k_otu_copy(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber,
+                           const uint32_t *__restrict__ kept, const uint32_t *__restrict__ off2, uint32_t *__restrict__ cursor,
+                           uint32_t *__restrict__ data2)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit >= v.nlit) return;
+    const uint32_t base = off2[lit];
+    cursor[lit] = base + kept[lit];
+    if (!kept[lit]) return;
+    const uint32_t len = v.ot_len[lit];
+    const uint32_t *d = v.ot_data + v.ot_off[lit];
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint32_t c = d[i];
+        if (!otu_live(bits, c)) continue;
+        data2[base + n++] = renumber ? otu_rank(bits, prefix, c) : c;
+    }
+}
+
+__global__ void k_otu_sort(uint32_t nlit, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ off2,
+                           const uint32_t *__restrict__ len2, uint32_t *__restrict__ data2)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit >= nlit || !flag[lit]) return;
+    uint32_t *d = data2 + off2[lit];
+    const int n = (int)len2[lit];
+    for (int i = 1; i < n; ++i) {
+        const uint32_t t = d[i];
+        int j = i;
+        while (j > 0 && d[j - 1] > t) { d[j] = d[j - 1]; --j; }
+        d[j] = t;
+    }
+}
+
+__global__ void k_ot_compare(SgView v, const uint32_t *__restrict__ off2, const uint32_t *__restrict__ len2,
+                             const uint32_t *__restrict__ data2, uint32_t *mismatch)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit >= v.nlit) return;
+    uint32_t bad = 0;
+    if (v.ot_len[lit] != len2[lit] || v.ot_off[lit] != off2[lit]) bad = 1;
+    else for (uint32_t i = 0; i < len2[lit]; ++i) if (v.ot_data[v.ot_off[lit] + i] != data2[off2[lit] + i]) { bad = 1; break; }
+    if (bad) atomicAdd(mismatch, 1u);
+}
+
 } // namespace
 
 /* ================================================================================================ */
@@ -756,4 +880,37 @@ void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *ar
 {
     const uint32_t nb = (v.n_cls + CP_TILE - 1) / CP_TILE;
     if (nb) LAUNCH(k_live_apply<true>, nb, TPB, s, v, (const uint2 *)tmp, (uint4 *)nullptr, (uint32_t *)nullptr, arena, (unsigned long long *)refs);
+}
+
+size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls)
+{
+    const size_t words = (size_t)n_cls / 32 + 1;
+    return 2 * words + 1 + 4 * (size_t)nlit + be_scan_tmp_words(nlit > words ? nlit : (uint32_t)words) + 64;
+}
+void be_ot_prepare(void *s, const SgView &v, uint32_t *tmp)
+{
+    const OtuTmp t = otu_layout(tmp, v.nlit, v.n_cls);
+    LAUNCH(k_otu_bitmap, blocks_for((uint64_t)t.words * 32), TPB, s, v, t.bits, t.prefix);
+    be_scan_u32(s, t.prefix, t.prefix, t.words, nullptr, t.scan);
+}
+void be_ot_update(void *s, const SgView &v, const SgOtUpdate &u)
+{
+    const OtuTmp t = otu_layout(u.tmp, v.nlit, u.n_cls_old);
+    const uint32_t nlit = v.nlit;
+    LAUNCH(k_otu_count, blocks_for(nlit), TPB, s, v, t.bits, t.kept, t.flag);
+    cudaMemsetAsync(t.addc, 0, (size_t)nlit * 4, ST(s));
+    const uint32_t n_new = u.n_cls_old > u.first_new ? u.n_cls_old - u.first_new : 0;
+    if (n_new) LAUNCH(k_otu_new_clauses, blocks_for(n_new), TPB, s, v, t.bits, t.prefix, u.renumber, u.first_new, u.n_cls_old, t.addc, t.flag, (uint32_t *)nullptr);
+    if (u.n_add) LAUNCH(k_otu_pairs, blocks_for(u.n_add), TPB, s, v, t.bits, t.prefix, u.renumber, u.n_add, t.addc, t.flag, (uint32_t *)nullptr);
+    LAUNCH(k_otu_len, blocks_for(nlit), TPB, s, nlit, t.kept, t.addc, u.len2);
+    be_scan_u32(s, u.len2, u.off2, nlit, u.total, t.scan);
+    LAUNCH(k_otu_copy, blocks_for(nlit), TPB, s, v, t.bits, t.prefix, u.renumber, t.kept, u.off2, t.cursor, u.data2);
+    if (n_new) LAUNCH(k_otu_new_clauses, blocks_for(n_new), TPB, s, v, t.bits, t.prefix, u.renumber, u.first_new, u.n_cls_old, t.cursor, t.flag, u.data2);
+    if (u.n_add) LAUNCH(k_otu_pairs, blocks_for(u.n_add), TPB, s, v, t.bits, t.prefix, u.renumber, u.n_add, t.cursor, t.flag, u.data2);
+    LAUNCH(k_otu_sort, blocks_for(nlit), TPB, s, nlit, t.flag, u.off2, u.len2, u.data2);
+}
+void be_ot_compare(void *s, const SgView &v, const uint32_t *off2, const uint32_t *len2, const uint32_t *data2, uint32_t *mismatch)
+{
+    LAUNCH(k_zero_u32, 1, 1, s, mismatch);
+    LAUNCH(k_ot_compare, blocks_for(v.nlit), TPB, s, v, off2, len2, data2, mismatch);
 }

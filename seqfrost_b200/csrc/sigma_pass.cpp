@@ -64,6 +64,9 @@ struct sigma_ctx {
     DBuf<uint32_t> ve_type, ve_ncls, ve_nlits, ve_nmodel, ve_aux, ve_cls_off, ve_lit_off, ve_mod_off, scr_len, scr_off, scratch;
     DBuf<SgUnit> ubuf;
     DBuf<uint8_t> ere_touched, ere_flags;
+    DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add;
+    bool ot_valid = false, ot_incremental = true, ot_verify = false;
+    uint32_t ot_first_new = 0;
     DBuf<uint32_t> totals;          /* device slots for scan totals */
     DBuf<SgScalars> sc;
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
@@ -131,6 +134,7 @@ SgView make_view(sigma_ctx *c)
     v.ve_type = c->ve_type.p; v.ve_ncls = c->ve_ncls.p; v.ve_nlits = c->ve_nlits.p; v.ve_nmodel = c->ve_nmodel.p;
     v.ve_aux = c->ve_aux.p; v.ve_cls_off = c->ve_cls_off.p; v.ve_lit_off = c->ve_lit_off.p; v.ve_mod_off = c->ve_mod_off.p;
     v.scr_off = c->scr_off.p; v.scratch = c->scratch.p; v.ubuf = c->ubuf.p; v.ubuf_cap = (uint32_t)c->ubuf.cap;
+    v.ot_add = c->ot_add.p; v.ot_add_cap = (uint32_t)(c->ot_add.cap / 2);
     v.ere_touched = c->ere_touched.p; v.ere_flags = c->ere_flags.p; v.ere_eidx = c->scores.p;
     v.sc = c->sc.p;
     v.nvars = c->nvars; v.nlit = c->nlit; v.n_cls = c->n_cls; v.pool_used = c->pool_used;
@@ -226,6 +230,40 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
     return SIGMA_OK;
 }
 
+/* ---- createOT for a later phase, as an update of the previous phase's table (sigma_backend.h) ---- */
+int stage_update_ot(sigma_ctx *c, uint64_t live_lits, uint32_t n_cls_old, bool renumber)
+{
+    const uint32_t nlit = c->nlit;
+    NOMEM(c->ot_off2.ensure(nlit + 1)); NOMEM(c->ot_len2.ensure(nlit)); NOMEM(c->ot_data2.ensure((size_t)live_lits + 16));
+    SgView v = make_view(c);
+    SgOtUpdate u;
+    u.renumber = renumber ? 1 : 0; u.n_cls_old = n_cls_old; u.first_new = c->ot_first_new; u.n_add = c->hsc.n_ot_add;
+    u.off2 = c->ot_off2.p; u.len2 = c->ot_len2.p; u.data2 = c->ot_data2.p; u.tmp = c->otutmp.p; u.total = c->totals.p;
+    {
+        Stage st(c, SIGMA_T_OT_UPDATE, 12 * live_lits + 16ull * nlit);
+        be_ot_update(c->stream, v, u);
+    }
+    { DBuf<uint32_t> t = c->ot_off; c->ot_off = c->ot_off2; c->ot_off2 = t; }
+    { DBuf<uint32_t> t = c->ot_len; c->ot_len = c->ot_len2; c->ot_len2 = t; }
+    { DBuf<uint32_t> t = c->ot_data; c->ot_data = c->ot_data2; c->ot_data2 = t; }
+    if (c->ot_verify) {
+        /* test hook: rebuild from scratch into the spare buffers and compare */
+        sigma_ctx &x = *c;
+        DBuf<uint32_t> so = x.ot_off, sl = x.ot_len, sd = x.ot_data;
+        NOMEM(x.ot_data2.ensure((size_t)live_lits + 16));
+        x.ot_off = x.ot_off2; x.ot_len = x.ot_len2; x.ot_data = x.ot_data2;
+        int rc = stage_create_ot(c, live_lits, 0);
+        x.ot_off2 = x.ot_off; x.ot_len2 = x.ot_len; x.ot_data2 = x.ot_data;
+        x.ot_off = so; x.ot_len = sl; x.ot_data = sd;
+        if (rc != SIGMA_OK) return rc;
+        SgView w = make_view(c);
+        be_ot_compare(c->stream, w, x.ot_off2.p, x.ot_len2.p, x.ot_data2.p, c->totals.p + 10);
+        CK(pull_totals(c, 11));
+        if (c->h_totals[10]) { snprintf(c->err, sizeof c->err, "incremental occurrence table differs from a rebuild in %u lists", c->h_totals[10]); return SIGMA_E_CUDA; }
+    }
+    return SIGMA_OK;
+}
+
 /* ---- prop (propelim.cpp:46-81) ---------------------------------------------------------------- */
 int stage_prop(sigma_ctx *c)
 {
@@ -264,6 +302,7 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         Stage st(c, SIGMA_T_ELECT);
         c->hsc.brk_rank = 0xFFFFFFFFu; c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
         c->hsc.n_acting = c->hsc.n_ponly = c->hsc.n_elected = 0;
+        c->hsc.n_ot_add = 0;
         CK(push_scalars(c));
         be_items(c->stream, SGK_ELECT_PREP, v, V);
         /* rank-ordered batches of geometrically growing size: inside a batch, pull rounds until every
@@ -359,6 +398,8 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     const uint32_t scr_total = c->h_totals[0];
     NOMEM(c->scratch.ensure((size_t)scr_total + 64));
     NOMEM(c->ubuf.ensure(2ull * scr_total + 4096));
+    NOMEM(c->ot_add.ensure(2ull * scr_total + 128));
+    c->ot_first_new = c->n_cls;
     v = make_view(c);
     v.n_elected = E;
     v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
@@ -499,8 +540,19 @@ int run_phases(sigma_ctx *c)
     while (litsbefore) {
         if (interrupted(c)) return SIGMA_INTERRUPTED;
         const int times = phase + 1;                       /* resizeCNF, solve.hpp:626-630 */
-        if (times > 1 && times != o.phases && (times % o.collect_freq) == 0) CK(stage_compact(c));
-        CK(stage_create_ot(c, live_lits, live_cls));
+        const bool compact = times > 1 && times != o.phases && (times % o.collect_freq) == 0;
+        const bool incr = c->ot_incremental && c->ot_valid && c->hsc.n_ot_add <= c->ot_add.cap / 2;
+        const uint32_t n_cls_old = c->n_cls;
+        if (incr) {
+            NOMEM(c->otutmp.ensure(be_ot_update_tmp_words(c->nlit, n_cls_old)));
+            Stage st(c, SIGMA_T_OT_UPDATE, 16ull * n_cls_old);
+            SgView v = make_view(c);
+            be_ot_prepare(c->stream, v, c->otutmp.p);
+        }
+        if (compact) CK(stage_compact(c));
+        if (incr) CK(stage_update_ot(c, live_lits, n_cls_old, compact));
+        else CK(stage_create_ot(c, live_lits, live_cls));
+        c->ot_valid = false;
         if (stop_here(c, phase, SIGMA_T_OT_ORDER)) return SIGMA_OK;
         const bool had_units = c->hsc.propagated < c->hsc.n_trail;
         CK(stage_prop(c));
@@ -516,6 +568,7 @@ int run_phases(sigma_ctx *c)
         CK(stage_sub_ve(c, multiplier));
         if (stop_here(c, phase, SIGMA_T_VE)) return SIGMA_OK;
         CK(stage_count(c));
+        c->ot_valid = true;                                /* a complete phase: the table can be updated in place of a rebuild */
         live_cls = c->hsc.live_cls; live_lits = c->hsc.live_lits;
         diff = litsbefore - (int64_t)live_lits; litsbefore = (int64_t)live_lits;
         phase++;
@@ -574,7 +627,8 @@ void sigma_destroy(sigma_ctx *c)
         c->sorttmp.release(); c->scantmp.release(); c->wl0.release(); c->wl1.release(); c->flags.release(); c->pos.release();
         c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
         c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
-        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release(); c->totals.release(); c->sc.release();
+        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release();
+        c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->totals.release(); c->sc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
         c->arena_out.release(); c->refs_out.release();
         for (void *e2 : c->evpool) be_event_destroy(e2);
@@ -667,6 +721,9 @@ int sigma_execute(sigma_ctx *c)
     c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
     c->evused = 0; c->evs.clear();
     c->executed = false;
+    c->ot_valid = false;
+    { const char *e = getenv("SIGMA_OT_INCREMENTAL"); c->ot_incremental = !(e && e[0] == '0'); }
+    { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
     c->launches0 = be_launch_count();
     const uint32_t V = c->nvars, nlit = c->nlit;
     /* restore the pristine solver state */

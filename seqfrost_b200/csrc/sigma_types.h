@@ -88,7 +88,7 @@ typedef struct SgScalars {
     unsigned long long pures, inverters, andors, ites, xors, funs, resolutions, subsumed, strengthened;
     unsigned long long units_forced, sort_ties_gt24, elect_visits;
     uint32_t core[12];        /* orgcore[] (lcve.cpp:24): variables holding marks 0..11 */
-    uint32_t n_core, pad1;
+    uint32_t n_core, n_ot_add;
 } SgScalars;
 
 /* one unit produced inside SUB/VE: applied in (elected index, sequence) order (SURVEY ledger 7) */
@@ -116,6 +116,8 @@ typedef struct SgView {
     uint32_t *scr_off;       /* per elected variable scratch slice in `scratch` */
     uint32_t *scratch;
     SgUnit   *ubuf;
+    uint32_t *ot_add;        /* (literal, clause id) pairs: occurrences created by substitution this phase */
+    uint32_t  ot_add_cap;
     uint8_t  *ere_touched;   /* per clause: may be deleted/strengthened by ERE */
     uint8_t  *ere_flags;     /* per elected variable: 1 = has recorded pairs, 2 = dirty */
     uint32_t *ere_eidx;      /* variable -> position in `elected` */

@@ -255,3 +255,27 @@ void be_export_apply(void *, const SgView &v, const uint32_t *tmp, uint32_t *are
         for (uint32_t k = 0; k < h.y; ++k) arena[r + 3 + k] = v.lits[h.x + k];
     }
 }
+
+size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t) { return (size_t)nlit + 16; }
+void be_ot_prepare(void *, const SgView &, uint32_t *) { g_launches++; }
+void be_ot_update(void *st, const SgView &v, const SgOtUpdate &u)
+{   /* the stand-in simply rebuilds the table from the (new) store: what the incremental kernels must equal */
+    SgView w = v;
+    w.ot_off = u.off2; w.ot_len = u.len2; w.ot_data = u.data2;
+    memset(u.len2, 0, (size_t)v.nlit * 4);
+    be_hist(st, w, u.len2);
+    be_scan_u32(st, u.len2, u.off2, v.nlit, u.total, nullptr);
+    memcpy(u.tmp, u.off2, (size_t)v.nlit * 4);
+    be_scatter(st, w, u.tmp);
+    be_items(st, SGK_IDSORT, w, v.nlit);
+}
+void be_ot_compare(void *, const SgView &v, const uint32_t *off2, const uint32_t *len2, const uint32_t *data2, uint32_t *mismatch)
+{
+    g_launches++;
+    uint32_t bad = 0;
+    for (uint32_t l = 0; l < v.nlit; ++l) {
+        if (v.ot_len[l] != len2[l] || v.ot_off[l] != off2[l]) { bad++; continue; }
+        for (uint32_t i = 0; i < len2[l]; ++i) if (v.ot_data[v.ot_off[l] + i] != data2[off2[l] + i]) { bad++; break; }
+    }
+    *mismatch = bad;
+}
