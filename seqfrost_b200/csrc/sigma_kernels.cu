@@ -570,26 +570,6 @@ __global__ void k_otu_bitmap(SgView v, uint32_t *__restrict__ bits, uint32_t *__
     if ((threadIdx.x & 31) == 0 && (c >> 5) <= v.n_cls / 32) { bits[c >> 5] = m; pop[c >> 5] = __popc(m); }
 }
 
-__global__ void k_otu_count(SgView v, const uint32_t *__restrict__ bits, uint32_t *__restrict__ kept, uint32_t *__restrict__ flag)
-{
-    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lit >= v.nlit) return;
-    uint32_t n = 0, unsorted = 0;
-    if (!(v.state[lit >> 1] & SG_MELTED_M)) {
-        const uint32_t len = v.ot_len[lit];
-        const uint32_t *d = v.ot_data + v.ot_off[lit];
-        uint32_t prev = 0;
-        for (uint32_t i = 0; i < len; ++i) {
-            const uint32_t c = d[i];
-            if (!otu_live(bits, c)) continue;
-            if (n && c < prev) unsorted = 1;
-            prev = c; n++;
-        }
-    }
-    kept[lit] = n;
-    flag[lit] = unsorted;
-}
-
 /* occurrences that are not in the old table: literals of the clauses created last phase ... */
 __global__ void k_otu_new_clauses(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber,
                                   uint32_t first_new, uint32_t n_cls_old, uint32_t *__restrict__ ctr, uint32_t *__restrict__ flag,
@@ -617,29 +597,58 @@ __global__ void k_otu_pairs(SgView v, const uint32_t *__restrict__ bits, const u
     if (data2) data2[pos] = renumber ? otu_rank(bits, prefix, c) : c; else flag[lit] = 1;
 }
 
-__global__ void k_otu_len(uint32_t nlit, const uint32_t *__restrict__ kept, const uint32_t *__restrict__ addc, uint32_t *__restrict__ len2)
+/* room for every list: its current length (an upper bound of what survives) plus its additions; the lists need
+ * not be packed, so no liveness count is needed before the copy */
+__global__ void k_otu_room(SgView v, const uint32_t *__restrict__ addc, uint32_t *__restrict__ room)
 {
     const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lit < nlit) len2[lit] = kept[lit] + addc[lit];
+    if (lit >= v.nlit) return;
+    room[lit] = ((v.state[lit >> 1] & SG_MELTED_M) ? 0u : v.ot_len[lit]) + addc[lit];
 }
 
 __global__ void k_otu_copy(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber,
-                           const uint32_t *__restrict__ kept, const uint32_t *__restrict__ off2, uint32_t *__restrict__ cursor,
-                           uint32_t *__restrict__ data2)
+                           const uint32_t *__restrict__ off2, uint32_t *__restrict__ cursor, uint32_t *__restrict__ flag,
+                           uint32_t *__restrict__ len2, const uint32_t *__restrict__ addc, uint32_t *__restrict__ data2)
 {
     const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
     if (lit >= v.nlit) return;
     const uint32_t base = off2[lit];
-    cursor[lit] = base + kept[lit];
-    if (!kept[lit]) return;
-    const uint32_t len = v.ot_len[lit];
-    const uint32_t *d = v.ot_data + v.ot_off[lit];
-    uint32_t n = 0;
-    for (uint32_t i = 0; i < len; ++i) {
-        const uint32_t c = d[i];
-        if (!otu_live(bits, c)) continue;
-        data2[base + n++] = renumber ? otu_rank(bits, prefix, c) : c;
+    uint32_t n = 0, unsorted = 0;
+    if (!(v.state[lit >> 1] & SG_MELTED_M)) {
+        const uint32_t len = v.ot_len[lit];
+        const uint32_t *d = v.ot_data + v.ot_off[lit];
+        uint32_t prev = 0;
+        for (uint32_t i0 = 0; i0 < len; i0 += 8) {
+            /* 8 entries at a time: ids, then their bitmap words, then their rank prefixes - independent loads */
+            uint32_t c[8], w[8], r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[k] = i0 + k < len ? d[i0 + k] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = c[k] != 0xFFFFFFFFu ? bits[c[k] >> 5] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = (renumber && c[k] != 0xFFFFFFFFu) ? prefix[c[k] >> 5] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (c[k] == 0xFFFFFFFFu || !((w[k] >> (c[k] & 31)) & 1u)) continue;
+                const uint32_t id = renumber ? r[k] + __popc(w[k] & ((1u << (c[k] & 31)) - 1u)) : c[k];
+                if (n && id < prev) unsorted = 1;
+                prev = id;
+                data2[base + n++] = id;
+            }
+        }
+        if (unsorted) {                       /* an elected list (sortOT order): back to clause-id order */
+            uint32_t *o = data2 + base;
+            for (uint32_t i = 1; i < n; ++i) {
+                const uint32_t t = o[i];
+                uint32_t j = i;
+                while (j > 0 && o[j - 1] > t) { o[j] = o[j - 1]; --j; }
+                o[j] = t;
+            }
+        }
     }
+    cursor[lit] = base + n;
+    len2[lit] = n + addc[lit];
+    (void)flag;
 }
 
 __global__ void k_otu_sort(uint32_t nlit, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ off2,
@@ -663,7 +672,7 @@ __global__ void k_ot_compare(SgView v, const uint32_t *__restrict__ off2, const 
     const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
     if (lit >= v.nlit) return;
     uint32_t bad = 0;
-    if (v.ot_len[lit] != len2[lit] || v.ot_off[lit] != off2[lit]) bad = 1;
+    if (v.ot_len[lit] != len2[lit]) bad = 1;
     else for (uint32_t i = 0; i < len2[lit]; ++i) if (v.ot_data[v.ot_off[lit] + i] != data2[off2[lit] + i]) { bad = 1; break; }
     if (bad) atomicAdd(mismatch, 1u);
 }
@@ -897,14 +906,14 @@ void be_ot_update(void *s, const SgView &v, const SgOtUpdate &u)
 {
     const OtuTmp t = otu_layout(u.tmp, v.nlit, u.n_cls_old);
     const uint32_t nlit = v.nlit;
-    LAUNCH(k_otu_count, blocks_for(nlit), TPB, s, v, t.bits, t.kept, t.flag);
     cudaMemsetAsync(t.addc, 0, (size_t)nlit * 4, ST(s));
+    cudaMemsetAsync(t.flag, 0, (size_t)nlit * 4, ST(s));
     const uint32_t n_new = u.n_cls_old > u.first_new ? u.n_cls_old - u.first_new : 0;
     if (n_new) LAUNCH(k_otu_new_clauses, blocks_for(n_new), TPB, s, v, t.bits, t.prefix, u.renumber, u.first_new, u.n_cls_old, t.addc, t.flag, (uint32_t *)nullptr);
     if (u.n_add) LAUNCH(k_otu_pairs, blocks_for(u.n_add), TPB, s, v, t.bits, t.prefix, u.renumber, u.n_add, t.addc, t.flag, (uint32_t *)nullptr);
-    LAUNCH(k_otu_len, blocks_for(nlit), TPB, s, nlit, t.kept, t.addc, u.len2);
-    be_scan_u32(s, u.len2, u.off2, nlit, u.total, t.scan);
-    LAUNCH(k_otu_copy, blocks_for(nlit), TPB, s, v, t.bits, t.prefix, u.renumber, t.kept, u.off2, t.cursor, u.data2);
+    LAUNCH(k_otu_room, blocks_for(nlit), TPB, s, v, t.addc, t.kept);
+    be_scan_u32(s, t.kept, u.off2, nlit, u.total, t.scan);
+    LAUNCH(k_otu_copy, blocks_for(nlit), TPB, s, v, t.bits, t.prefix, u.renumber, u.off2, t.cursor, t.flag, u.len2, t.addc, u.data2);
     if (n_new) LAUNCH(k_otu_new_clauses, blocks_for(n_new), TPB, s, v, t.bits, t.prefix, u.renumber, u.first_new, u.n_cls_old, t.cursor, t.flag, u.data2);
     if (u.n_add) LAUNCH(k_otu_pairs, blocks_for(u.n_add), TPB, s, v, t.bits, t.prefix, u.renumber, u.n_add, t.cursor, t.flag, u.data2);
     LAUNCH(k_otu_sort, blocks_for(nlit), TPB, s, nlit, t.flag, u.off2, u.len2, u.data2);

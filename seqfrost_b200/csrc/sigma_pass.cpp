@@ -67,6 +67,8 @@ struct sigma_ctx {
     DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add;
     bool ot_valid = false, ot_incremental = true, ot_verify = false;
     uint32_t ot_first_new = 0;
+    uint64_t ot_room = 0;            /* upper bound of the words the (unpacked) table can occupy */
+    uint64_t ot_pending_add = 0;     /* literals of the clauses created since the table was last built/updated */
     DBuf<uint32_t> totals;          /* device slots for scan totals */
     DBuf<SgScalars> sc;
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
@@ -206,6 +208,7 @@ int stage_ingest(sigma_ctx *c)
 int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
 {
     const uint32_t nlit = c->nlit;
+    c->ot_room = live_lits; c->ot_pending_add = 0;
     NOMEM(c->ot_data.ensure((size_t)live_lits + 16));
     SgView v = make_view(c);
     {
@@ -234,7 +237,10 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
 int stage_update_ot(sigma_ctx *c, uint64_t live_lits, uint32_t n_cls_old, bool renumber)
 {
     const uint32_t nlit = c->nlit;
-    NOMEM(c->ot_off2.ensure(nlit + 1)); NOMEM(c->ot_len2.ensure(nlit)); NOMEM(c->ot_data2.ensure((size_t)live_lits + 16));
+    /* the updated lists are not packed: each keeps room for its previous length plus its additions */
+    c->ot_room += c->ot_pending_add + c->hsc.n_ot_add;
+    c->ot_pending_add = 0;
+    NOMEM(c->ot_off2.ensure(nlit + 1)); NOMEM(c->ot_len2.ensure(nlit)); NOMEM(c->ot_data2.ensure((size_t)c->ot_room + 16));
     SgView v = make_view(c);
     SgOtUpdate u;
     u.renumber = renumber ? 1 : 0; u.n_cls_old = n_cls_old; u.first_new = c->ot_first_new; u.n_add = c->hsc.n_ot_add;
@@ -430,6 +436,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         be_items(c->stream, SGK_VE_EMIT, v, E);
         c->n_cls += add_cls;
         c->pool_used += add_lits;
+        c->ot_pending_add += add_lits;
         c->model_words += add_model;
         v = make_view(c);
         int rc = apply_units(c, v);
