@@ -23,8 +23,11 @@ enum SgItemKind {
     SGK_SUB,            /* n = elected                                                             */
     SGK_VE_COUNT,       /* n = elected                                                             */
     SGK_VE_EMIT,        /* n = elected                                                             */
-    SGK_ERE_PROPOSE,    /* n = elected   : one warp per variable                                   */
+    SGK_ERE_CHUNKS,     /* n = elected   : 256-pair work items per variable                        */
+    SGK_ERE_PROPOSE,    /* n = work items: one warp each                                           */
     SGK_ERE_DIRTY,      /* n = elected                                                             */
+    SGK_ERE_LIST,       /* n = elected   : positions with recorded pairs or dirty -> v.acting (ordered)    */
+    SGK_ERE_FLAG01,     /* n = elected   : ve_ncls[e] = (ere_flags[e] != 0)                               */
     SGK_N
 };
 /* sequential stages, one thread */
@@ -102,7 +105,7 @@ void be_acting_flags(void *s, const SgView &v, uint32_t *flags_acting, uint32_t 
 void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe);
 /* generic item / serial launches */
 void be_items(void *s, int kind, const SgView &v, uint32_t n);
-void be_serial(void *s, int kind, const SgView &v, uint32_t arg);
+void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2 = 0);
 void be_sort_units(void *s, const SgView &v, uint32_t n);                          /* by (eidx, seq) */
 /* live clause / literal count (solve.hpp:661-671) and melted variable count (solve.hpp:645-654) */
 void be_count_live(void *s, const SgView &v);

@@ -1500,29 +1500,51 @@ SG_HD bool sg_ere_lists(const SgView &v, uint32_t x, uint32_t &dx, uint32_t &fx)
     return true;
 }
 
-SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t eidx)
+/* work decomposition of the proposal pass: 256 clause pairs per warp-sized item, so that a variable with
+ * long lists (up to 1000 x 1000 pairs) is spread over many warps */
+#define SG_ERE_CHUNK 256
+SG_HD void sg_ere_chunks_item(const SgView &v, uint32_t eidx)
+{
+    const uint32_t x = v.elected[eidx];
+    v.ere_eidx[x] = eidx;
+    uint32_t dx, fx, n = 0;
+    if (sg_ere_lists(v, x, dx, fx)) {
+        const unsigned long long pairs = (unsigned long long)v.ot_len[dx] * v.ot_len[fx];
+        n = (uint32_t)((pairs + SG_ERE_CHUNK - 1) / SG_ERE_CHUNK);
+    }
+    v.ve_ncls[eidx] = n;                      /* scanned into ve_cls_off by the driver */
+}
+
+SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t chunk)
 {
     const SgLane L = sg_lane_ctx();
+    /* which elected variable owns this chunk: last e with ve_cls_off[e] <= chunk */
+    uint32_t lo = 0, hi = v.n_elected;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (v.ve_cls_off[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    const uint32_t eidx = lo;
     const uint32_t x = v.elected[eidx];
-    if (L.lane == 0) v.ere_eidx[x] = eidx;
     uint32_t dx, fx;
     if (!sg_ere_lists(v, x, dx, fx)) return;
     const int ds = (int)v.ot_len[dx], fs = (int)v.ot_len[fx];
     const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
     const int maxsize = v.o.ere_clause_max;
     uint32_t merged[SG_ERE_MAXLEN];
-    uint32_t seq = 0;
     bool any = false;
     const long long total = (long long)ds * fs;
-    for (long long q = L.lane; q < total; q += L.width) {
+    const long long first = (long long)(chunk - v.ve_cls_off[eidx]) * SG_ERE_CHUNK;
+    const long long last = first + SG_ERE_CHUNK < total ? first + SG_ERE_CHUNK : total;
+    for (long long q = first + L.lane; q < last; q += L.width) {
         const int i = (int)(q / fs), j = (int)(q - (long long)i * fs);
         const uint32_t iref = dm[i], jref = dt[j];
-        const sg_u4 hi = v.hdr[iref];
-        if (hi.z & SG_DELETED) continue;
+        const sg_u4 hi2 = v.hdr[iref];
+        if (hi2.z & SG_DELETED) continue;
         const sg_u4 hj = v.hdr[jref];
         if (hj.z & SG_DELETED) continue;
         uint32_t sig, best;
-        const int len = sg_merge_ere(v, x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y, maxsize, merged, &sig, &best);
+        const int len = sg_merge_ere(v, x, v.lits + hi2.x, (int)hi2.y, v.lits + hj.x, (int)hj.y, maxsize, merged, &sig, &best);
         if (len < 2) continue;
         const int nm = (int)v.ot_len[best];
         const uint32_t *ml = sg_list(v, best);
@@ -1534,7 +1556,6 @@ SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t eidx)
         }
         if (hit) { uint32_t s2 = ((uint32_t)i << 16) | (uint32_t)j; sg_push_unit(v, eidx, s2, 0); any = true; }
     }
-    (void)seq;
     if (sg_ballot(any) && L.lane == 0) v.ere_flags[eidx] |= 1u;
 }
 
@@ -1559,7 +1580,17 @@ SG_HD void sg_ere_mark_owner(const SgView &v, uint32_t c, const uint32_t *oldlit
         const uint32_t w = v.rank[u];
         if (SG_ER_STAT(w) == SG_E_BOTH && SG_ER_RANK(w) < v.sc->brk_rank) {
             const uint32_t e = v.ere_eidx[u];
-            if (e > cur_eidx) v.ere_flags[e] |= 2u;
+            if (e <= cur_eidx) continue;
+            if (!v.ere_flags[e]) {
+                /* not on the replay list yet: queue it (ascending) so that the replay reaches it in order */
+                SgScalars *sc = v.sc;
+                if (sc->ere_npending < 64) {
+                    uint32_t j = sc->ere_npending++;
+                    while (j > 0 && sc->ere_pending[j - 1] > e) { sc->ere_pending[j] = sc->ere_pending[j - 1]; --j; }
+                    sc->ere_pending[j] = e;
+                } else sc->ere_overflow = 1;
+            }
+            v.ere_flags[e] |= 2u;
         }
     }
     (void)c;
@@ -1619,38 +1650,71 @@ SG_HDN inline void sg_ere_pair(const SgView &v, const SgLane &L, uint32_t x, uin
     }
 }
 
-/* ONE warp: sequential replay in elected order */
-SG_HDN inline void sg_ere_replay_serial(const SgView &v, uint32_t n_events)
+/* processes elected variable e during the replay: in full when dirty, else only at its recorded pairs */
+SG_HDN inline void sg_ere_replay_var(const SgView &v, const SgLane &L, uint32_t e, uint32_t fl, uint32_t &ep, uint32_t n_events, uint32_t *merged)
+{
+    const uint32_t x = v.elected[e];
+    while (ep < n_events && v.ubuf[ep].eidx < e) ep++;
+    uint32_t dx, fx;
+    if (fl & 2u) {
+        if (L.lane == 0) v.sc->ere_dirty_vars++;
+        if (sg_ere_lists(v, x, dx, fx)) {
+            const int ds = (int)v.ot_len[dx], fs = (int)v.ot_len[fx];
+            const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
+            if (L.lane == 0) v.sc->ere_full_pairs += (unsigned long long)ds * fs;
+            for (int i = 0; i < ds; ++i) {
+                if (sg_deleted(v, dm[i])) continue;
+                for (int j = 0; j < fs; ++j) sg_ere_pair(v, L, x, e, dm[i], dt[j], merged);
+            }
+        }
+    } else {
+        if (!sg_ere_lists(v, x, dx, fx)) return;
+        const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
+        while (ep < n_events && v.ubuf[ep].eidx == e) {
+            const uint32_t key = v.ubuf[ep].seq;
+            sg_ere_pair(v, L, x, e, dm[key >> 16], dt[key & 0xffffu], merged);
+            if (L.lane == 0) v.sc->ere_event_pairs++;
+            ep++;
+        }
+    }
+}
+
+/* ONE warp: sequential replay in elected order over the variables that have recorded pairs or are dirty
+ * (`list`, ascending), merged with the variables that turn dirty on the way (sc->ere_pending) */
+SG_HDN inline void sg_ere_replay_serial(const SgView &v, uint32_t n_events, uint32_t n_list)
 {
     const SgLane L = sg_lane_ctx();
     uint32_t merged[SG_ERE_MAXLEN];
-    uint32_t ep = 0;
-    for (uint32_t e = 0; e < v.n_elected; ++e) {
+    const uint32_t *list = v.acting;
+    uint32_t ep = 0, li = 0, cur = 0;
+    bool started = false;
+    while (true) {
+        sg_wsync();
+        if (sg_bcast(*(volatile uint32_t *)&v.sc->ere_overflow)) break;
+        const uint32_t npend = sg_bcast(*(volatile uint32_t *)&v.sc->ere_npending);
+        const uint32_t pend0 = npend ? sg_bcast(*(volatile uint32_t *)&v.sc->ere_pending[0]) : 0xFFFFFFFFu;
+        const uint32_t next = li < n_list ? list[li] : 0xFFFFFFFFu;
+        if (next == 0xFFFFFFFFu && pend0 == 0xFFFFFFFFu) return;
+        uint32_t e;
+        if (pend0 < next) {
+            e = pend0;
+            if (L.lane == 0) {                                  /* pop the head of the pending queue */
+                SgScalars *sc = v.sc;
+                for (uint32_t k = 1; k < sc->ere_npending; ++k) sc->ere_pending[k - 1] = sc->ere_pending[k];
+                sc->ere_npending--;
+            }
+        } else { e = next; li++; }
         sg_wsync();
         const uint32_t fl = sg_bcast(*(volatile uint8_t *)&v.ere_flags[e]);
-        if (!fl) continue;
-        const uint32_t x = v.elected[e];
-        while (ep < n_events && v.ubuf[ep].eidx < e) ep++;
-        if (fl & 2u) {
-            uint32_t dx, fx;
-            if (sg_ere_lists(v, x, dx, fx)) {
-                const int ds = (int)v.ot_len[dx], fs = (int)v.ot_len[fx];
-                const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
-                for (int i = 0; i < ds; ++i) {
-                    if (sg_deleted(v, dm[i])) continue;
-                    for (int j = 0; j < fs; ++j) sg_ere_pair(v, L, x, e, dm[i], dt[j], merged);
-                }
-            }
-        } else {
-            uint32_t dx, fx;
-            if (!sg_ere_lists(v, x, dx, fx)) continue;
-            const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
-            while (ep < n_events && v.ubuf[ep].eidx == e) {
-                const uint32_t key = v.ubuf[ep].seq;
-                sg_ere_pair(v, L, x, e, dm[key >> 16], dt[key & 0xffffu], merged);
-                ep++;
-            }
-        }
+        sg_ere_replay_var(v, L, e, fl, ep, n_events, merged);
+        cur = e; started = true;
+    }
+    /* more than 64 variables were waiting at once: finish with a plain scan over the flags of the
+     * variables after the last one processed (everything queued or listed has a non-zero flag) */
+    for (uint32_t e = started ? cur + 1 : 0; e < v.n_elected; ++e) {
+        sg_wsync();
+        const uint32_t fl = sg_bcast(*(volatile uint8_t *)&v.ere_flags[e]);
+        if (fl) sg_ere_replay_var(v, L, e, fl, ep, n_events, merged);
     }
 }
 

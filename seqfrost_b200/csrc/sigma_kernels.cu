@@ -365,13 +365,16 @@ template <int KIND> __global__ void k_items(SgView v, uint32_t n)
     else if (KIND == SGK_SUB) sg_sub_item(v, i);
     else if (KIND == SGK_VE_COUNT) sg_ve_count_item(v, i);
     else if (KIND == SGK_VE_EMIT) sg_ve_emit_item(v, i);
+    else if (KIND == SGK_ERE_CHUNKS) sg_ere_chunks_item(v, i);
     else if (KIND == SGK_ERE_PROPOSE) sg_ere_propose_item(v, i);
     else if (KIND == SGK_ERE_DIRTY) sg_ere_dirty_item(v, i);
+    else if (KIND == SGK_ERE_FLAG01) v.ve_ncls[i] = v.ere_flags[i] != 0;
+    else if (KIND == SGK_ERE_LIST) { if (v.ere_flags[i]) v.acting[v.ve_cls_off[i]] = i; }
 }
 
-__global__ void k_serial(SgView v, int kind, uint32_t arg)
+__global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
 {   /* launched with one warp; only the ERE replay uses more than lane 0 */
-    if (kind == SGS_ERE_REPLAY) { sg_ere_replay_serial(v, arg); return; }
+    if (kind == SGS_ERE_REPLAY) { sg_ere_replay_serial(v, arg, arg2); return; }
     if (threadIdx.x) return;
     if (kind == SGS_PROP) sg_prop_serial(v);
     else if (kind == SGS_MARKS) sg_marks_serial(v, arg);
@@ -388,6 +391,33 @@ __global__ void k_sort_units_small(SgView v, uint32_t n)
             --j;
         }
         v.ubuf[j] = t;
+    }
+}
+/* up to 2048 units: bitonic sort of (eidx, seq) keys in shared memory by one block */
+__global__ void k_sort_units_block(SgView v, uint32_t n)
+{
+    __shared__ unsigned long long key[2048];
+    __shared__ uint32_t lit[2048];
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) {
+        if (i < n) { const SgUnit u = v.ubuf[i]; key[i] = ((unsigned long long)u.eidx << 32) | u.seq; lit[i] = u.lit; }
+        else { key[i] = ~0ull; lit[i] = 0; }
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= 2048; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) {
+                const uint32_t p = i ^ j;
+                if (p > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = key[i], b = key[p];
+                    if ((a > b) == up) { key[i] = b; key[p] = a; const uint32_t t = lit[i]; lit[i] = lit[p]; lit[p] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        SgUnit u; u.eidx = (uint32_t)(key[i] >> 32); u.seq = (uint32_t)key[i]; u.lit = lit[i]; u.pad = 0;
+        v.ubuf[i] = u;
     }
 }
 __global__ void k_units_keys(SgView v, uint32_t n, uint32_t *keys, uint32_t *idx, int which)
@@ -833,17 +863,21 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_EMIT: LAUNCH(k_items<SGK_VE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_ERE_CHUNKS: LAUNCH(k_items<SGK_ERE_CHUNKS>, blocks_for(n), TPB, s, v, n); break;
     case SGK_ERE_PROPOSE: LAUNCH(k_items<SGK_ERE_PROPOSE>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_ERE_DIRTY: LAUNCH(k_items<SGK_ERE_DIRTY>, blocks_for(n, 128), 128, s, v, n); break;
+    case SGK_ERE_FLAG01: LAUNCH(k_items<SGK_ERE_FLAG01>, blocks_for(n), TPB, s, v, n); break;
+    case SGK_ERE_LIST: LAUNCH(k_items<SGK_ERE_LIST>, blocks_for(n), TPB, s, v, n); break;
     default: snprintf(g_err, sizeof g_err, "be_items: bad kind %d", kind);
     }
 }
-void be_serial(void *s, int kind, const SgView &v, uint32_t arg) { LAUNCH(k_serial, 1, 32, s, v, kind, arg); }
+void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2) { LAUNCH(k_serial, 1, 32, s, v, kind, arg, arg2); }
 
 void be_sort_units(void *s, const SgView &v, uint32_t n)
 {
     if (n < 2) return;
-    if (n <= 2048) { LAUNCH(k_sort_units_small, 1, 1, s, v, n); return; }
+    if (n <= 32) { LAUNCH(k_sort_units_small, 1, 1, s, v, n); return; }
+    if (n <= 2048) { LAUNCH(k_sort_units_block, 1, 512, s, v, n); return; }
     /* rare: LSD by (seq, eidx) through an index permutation */
     uint32_t *keys = (uint32_t *)be_malloc(4ull * n), *idx = (uint32_t *)be_malloc(4ull * n);
     uint32_t *tk = (uint32_t *)be_malloc(4ull * n), *tv = (uint32_t *)be_malloc(4ull * n);

@@ -460,17 +460,33 @@ int stage_ere(sigma_ctx *c)
     be_memset(c->stream, c->ere_flags.p, 0, E);
     c->hsc.n_units = 0;
     CK(push_scalars(c));
+    NOMEM(c->ve_ncls.ensure(E + 1)); NOMEM(c->ve_cls_off.ensure(E + 1));
     SgView v = make_view(c);
     v.n_elected = E;
-    be_items(c->stream, SGK_ERE_PROPOSE, v, E);
+    be_items(c->stream, SGK_ERE_CHUNKS, v, E);
+    be_scan_u32(c->stream, c->ve_ncls.p, c->ve_cls_off.p, E, c->totals.p, c->scantmp.p);
+    CK(pull_totals(c, 1));
+    const uint32_t n_items = c->h_totals[0];
+    if (n_items) be_items(c->stream, SGK_ERE_PROPOSE, v, n_items);
     CK(pull_scalars(c));
     const uint32_t n = c->hsc.n_units;
     if (n > c->ubuf.cap) return fail(c, SIGMA_E_UNSUPPORTED, "ERE event buffer overflow");
+    c->hsc.ere_events += n;
     if (n) {
         be_sort_units(c->stream, v, n);
         be_items(c->stream, SGK_ERE_DIRTY, v, E);
-        be_serial(c->stream, SGS_ERE_REPLAY, v, n);
+        /* ordered list of the positions to visit: flags -> 0/1 -> exclusive scan -> scatter into v.acting */
+        be_memset(c->stream, c->ve_ncls.p, 0, (size_t)E * 4);
+        be_items(c->stream, SGK_ERE_FLAG01, v, E);
+        be_scan_u32(c->stream, c->ve_ncls.p, c->ve_cls_off.p, E, c->totals.p, c->scantmp.p);
+        CK(pull_totals(c, 1));
+        const uint32_t n_list = c->h_totals[0];
+        be_items(c->stream, SGK_ERE_LIST, v, E);
+        c->hsc.ere_npending = 0; c->hsc.ere_overflow = 0;
+        CK(push_scalars(c));
+        be_serial(c->stream, SGS_ERE_REPLAY, v, n, n_list);
     }
+    CK(pull_scalars(c));
     c->hsc.n_units = 0;
     CK(push_scalars(c));
     return SIGMA_OK;
@@ -766,6 +782,7 @@ int sigma_execute(sigma_ctx *c)
     c->rep.resolutions = (int64_t)s.resolutions; c->rep.subsumed = (int64_t)s.subsumed;
     c->rep.strengthened = (int64_t)s.strengthened; c->rep.units = (int64_t)s.units_forced;
     c->rep.sort_ties_gt24 = (int64_t)s.sort_ties_gt24;
+    c->rep.reserved[0] = s.ere_events; c->rep.reserved[1] = s.ere_dirty_vars; c->rep.reserved[2] = s.ere_full_pairs; c->rep.reserved[3] = s.ere_event_pairs;
     c->executed = (rc == SIGMA_OK);
     return rc;
 }

@@ -87,8 +87,11 @@ typedef struct SgScalars {
     unsigned long long n_model;
     unsigned long long pures, inverters, andors, ites, xors, funs, resolutions, subsumed, strengthened;
     unsigned long long units_forced, sort_ties_gt24, elect_visits;
+    unsigned long long ere_events, ere_dirty_vars, ere_full_pairs, ere_event_pairs;
     uint32_t core[12];        /* orgcore[] (lcve.cpp:24): variables holding marks 0..11 */
     uint32_t n_core, n_ot_add;
+    uint32_t ere_npending, ere_overflow;
+    uint32_t ere_pending[64];  /* elected positions that turned dirty during the replay and are not on its list */
 } SgScalars;
 
 /* one unit produced inside SUB/VE: applied in (elected index, sequence) order (SURVEY ledger 7) */

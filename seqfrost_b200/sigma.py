@@ -69,6 +69,7 @@ class SigmaReport(C.Structure):
         d["stage_bytes"] = {s: int(self.stage_bytes[i]) for i, s in enumerate(STAGES)}
         d["elected_per_phase"] = list(self.elected_per_phase)
         d["election_rounds"] = list(self.election_rounds)
+        d["ere"] = dict(zip(("events", "dirty_vars", "full_pairs", "event_pairs"), list(self.reserved)[:4]))
         return d
 
 

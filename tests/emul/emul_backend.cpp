@@ -184,20 +184,23 @@ void be_items(void *, int kind, const SgView &v, uint32_t n)
         case SGK_SUB: sg_sub_item(v, i); break;
         case SGK_VE_COUNT: sg_ve_count_item(v, i); break;
         case SGK_VE_EMIT: sg_ve_emit_item(v, i); break;
+        case SGK_ERE_CHUNKS: sg_ere_chunks_item(v, i); break;
         case SGK_ERE_PROPOSE: sg_ere_propose_item(v, i); break;
         case SGK_ERE_DIRTY: sg_ere_dirty_item(v, i); break;
+        case SGK_ERE_FLAG01: v.ve_ncls[i] = v.ere_flags[i] != 0; break;
+        case SGK_ERE_LIST: if (v.ere_flags[i]) v.acting[v.ve_cls_off[i]] = i; break;
         default: abort();
         }
     }
 }
-void be_serial(void *, int kind, const SgView &v, uint32_t arg)
+void be_serial(void *, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
 {
     g_launches++;
     switch (kind) {
     case SGS_PROP: sg_prop_serial(v); break;
     case SGS_MARKS: sg_marks_serial(v, arg); break;
     case SGS_APPLY_UNITS: sg_apply_units_serial(v, arg); break;
-    case SGS_ERE_REPLAY: sg_ere_replay_serial(v, arg); break;
+    case SGS_ERE_REPLAY: sg_ere_replay_serial(v, arg, arg2); break;
     default: abort();
     }
 }
