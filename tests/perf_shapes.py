@@ -17,7 +17,10 @@ SHAPES = {
 
 if __name__ == "__main__":
     s = sigma.Sigma(0)
+    only = os.environ.get("SHAPE")
     for name, gen in SHAPES.items():
+        if only and not name.startswith(only):
+            continue
         t = time.time()
         b = B.from_cnf(*gen())
         b.opts["ere_en"] = 1
