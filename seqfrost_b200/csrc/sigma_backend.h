@@ -27,11 +27,14 @@ enum SgItemKind {
     SGK_ERE_PROPOSE,    /* n = work items: one warp each                                           */
     SGK_ERE_DIRTY,      /* n = elected                                                             */
     SGK_ERE_LIST,       /* n = elected   : positions with recorded pairs or dirty -> v.acting (ordered)    */
+    SGK_ERE_CLAIM,      /* n = recorded pairs before the first dirty variable: one warp each       */
+    SGK_ERE_SAFE,
+    SGK_ERE_APPLY,
     SGK_ERE_FLAG01,     /* n = elected   : ve_ncls[e] = (ere_flags[e] != 0)                               */
     SGK_N
 };
 /* sequential stages, one thread */
-enum SgSerialKind { SGS_PROP = 0, SGS_MARKS, SGS_APPLY_UNITS, SGS_ERE_REPLAY /* one warp */, SGS_N };
+enum SgSerialKind { SGS_PROP = 0, SGS_MARKS, SGS_APPLY_UNITS, SGS_ERE_REPLAY /* one warp */, SGS_ERE_SPLIT, SGS_N };
 
 #ifdef __cplusplus
 extern "C++" {

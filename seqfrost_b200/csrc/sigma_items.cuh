@@ -1567,7 +1567,7 @@ SG_HD void sg_ere_dirty_item(const SgView &v, uint32_t eidx)
         const uint32_t lit = 2 * x + side;
         const int n = (int)v.ot_len[lit];
         const uint32_t *d = sg_list(v, lit);
-        for (int i = 0; i < n; ++i) if (v.ere_touched[d[i]]) { v.ere_flags[eidx] |= 2u; return; }
+        for (int i = 0; i < n; ++i) if (v.ere_touched[d[i]]) { v.ere_flags[eidx] |= 2u; sg_atomic_min(&v.sc->ere_first_dirty, eidx); return; }
     }
 }
 
@@ -1650,6 +1650,71 @@ SG_HDN inline void sg_ere_pair(const SgView &v, const SgLane &L, uint32_t x, uin
     }
 }
 
+/* ---- recorded pairs of the variables BEFORE the first dirty one: parallel rounds ------------------------------
+ * Such a pair reads only its (untouched) parents and the clauses of its shortest list, and writes only clauses
+ * its resolvent subsumes.  Per round every pending pair claims the clauses it could write (atomicMin of its
+ * position in the sequential order); a pair that holds all its claims is the earliest pending writer of each of
+ * them, so the state it sees is the state it would see in the sequential run, and the pairs applied in one round
+ * write disjoint clauses.  The earliest pending pair always qualifies, so the rounds terminate. */
+template <class F> SG_HD void sg_ere_event_hits(const SgView &v, const SgLane &L, uint32_t k, uint32_t *merged, F on_hit)
+{
+    const uint32_t eidx = v.ubuf[k].eidx, key = v.ubuf[k].seq;
+    const uint32_t x = v.elected[eidx];
+    uint32_t dx, fx;
+    if (!sg_ere_lists(v, x, dx, fx)) return;
+    const uint32_t iref = sg_list(v, dx)[key >> 16], jref = sg_list(v, fx)[key & 0xffffu];
+    const sg_u4 hi = v.hdr[iref], hj = v.hdr[jref];
+    if ((hi.z | hj.z) & SG_DELETED) return;
+    uint32_t sig, best;
+    const int len = sg_merge_ere(v, x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y, v.o.ere_clause_max, merged, &sig, &best);
+    if (len < 2) return;
+    const int nm = (int)v.ot_len[best];
+    const uint32_t *ml = sg_list(v, best);
+    for (int m = (int)L.lane; m < nm; m += (int)L.width) {
+        const uint32_t c = ml[m];
+        if (c != iref && c != jref && sg_ere_hits(v, merged, len, sig, c)) on_hit(c);
+    }
+}
+SG_HDN inline void sg_ere_claim_item(const SgView &v, uint32_t k)
+{
+    if (v.ere_done[k]) return;
+    const SgLane L = sg_lane_ctx();
+    uint32_t merged[SG_ERE_MAXLEN];
+    sg_ere_event_hits(v, L, k, merged, [&](uint32_t c) { sg_atomic_min(&v.ere_owner[c], k); });
+}
+SG_HDN inline void sg_ere_safe_item(const SgView &v, uint32_t k)
+{
+    if (v.ere_done[k]) return;
+    const SgLane L = sg_lane_ctx();
+    uint32_t merged[SG_ERE_MAXLEN];
+    bool mine = true;
+    sg_ere_event_hits(v, L, k, merged, [&](uint32_t c) { if (v.ere_owner[c] != k) mine = false; });
+    const bool all = sg_ballot(!mine) == 0;
+    if (L.lane == 0) v.ere_done[k] = all ? 2u : 0u;          /* 2 = apply in this round */
+}
+SG_HDN inline void sg_ere_apply_item(const SgView &v, uint32_t k)
+{
+    if (v.ere_done[k] != 2u) return;
+    const SgLane L = sg_lane_ctx();
+    uint32_t merged[SG_ERE_MAXLEN];
+    const uint32_t eidx = v.ubuf[k].eidx, key = v.ubuf[k].seq;
+    const uint32_t x = v.elected[eidx];
+    uint32_t dx, fx;
+    if (sg_ere_lists(v, x, dx, fx)) sg_ere_pair(v, L, x, eidx, sg_list(v, dx)[key >> 16], sg_list(v, fx)[key & 0xffffu], merged);
+    if (L.lane == 0) { v.ere_done[k] = 1u; sg_atomic_add(&v.sc->ere_applied, 1u); }
+}
+/* ONE thread: how many recorded pairs / list entries lie before the first dirty variable */
+SG_HD void sg_ere_split_serial(const SgView &v, uint32_t n_events, uint32_t n_list)
+{
+    const uint32_t fd = v.sc->ere_first_dirty;
+    uint32_t lo = 0, hi = n_events;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (v.ubuf[mid].eidx < fd) lo = mid + 1; else hi = mid; }
+    v.sc->ere_par_events = lo;
+    lo = 0; hi = n_list;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (v.acting[mid] < fd) lo = mid + 1; else hi = mid; }
+    v.sc->ere_list_start = lo;
+}
+
 /* processes elected variable e during the replay: in full when dirty, else only at its recorded pairs */
 SG_HDN inline void sg_ere_replay_var(const SgView &v, const SgLane &L, uint32_t e, uint32_t fl, uint32_t &ep, uint32_t n_events, uint32_t *merged)
 {
@@ -1672,8 +1737,10 @@ SG_HDN inline void sg_ere_replay_var(const SgView &v, const SgLane &L, uint32_t 
         const uint32_t *dm = sg_list(v, dx), *dt = sg_list(v, fx);
         while (ep < n_events && v.ubuf[ep].eidx == e) {
             const uint32_t key = v.ubuf[ep].seq;
-            sg_ere_pair(v, L, x, e, dm[key >> 16], dt[key & 0xffffu], merged);
-            if (L.lane == 0) v.sc->ere_event_pairs++;
+            if (!(v.ere_done && v.ere_done[ep])) {             /* not already applied by a parallel round */
+                sg_ere_pair(v, L, x, e, dm[key >> 16], dt[key & 0xffffu], merged);
+                if (L.lane == 0) v.sc->ere_event_pairs++;
+            }
             ep++;
         }
     }
@@ -1686,7 +1753,10 @@ SG_HDN inline void sg_ere_replay_serial(const SgView &v, uint32_t n_events, uint
     const SgLane L = sg_lane_ctx();
     uint32_t merged[SG_ERE_MAXLEN];
     const uint32_t *list = v.acting;
-    uint32_t ep = 0, li = 0, cur = 0;
+    /* when the parallel rounds finished every pair before the first dirty variable, start there */
+    const bool skip = v.ere_done && sg_bcast(*(volatile uint32_t *)&v.sc->ere_applied) == sg_bcast(*(volatile uint32_t *)&v.sc->ere_par_events);
+    uint32_t ep = skip ? sg_bcast(*(volatile uint32_t *)&v.sc->ere_par_events) : 0u;
+    uint32_t li = skip ? sg_bcast(*(volatile uint32_t *)&v.sc->ere_list_start) : 0u, cur = 0;
     bool started = false;
     while (true) {
         sg_wsync();

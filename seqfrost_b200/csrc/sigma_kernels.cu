@@ -349,7 +349,8 @@ __global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, cons
 template <int KIND> __global__ void k_items(SgView v, uint32_t n)
 {
     /* SUB and the BVE decision run one warp per elected variable, everything else one thread */
-    const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_ERE_PROPOSE);
+    const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
+                            KIND == SGK_ERE_SAFE || KIND == SGK_ERE_APPLY);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = warp_item ? (t >> 5) : t;
     if (i >= n) return;
@@ -368,6 +369,9 @@ template <int KIND> __global__ void k_items(SgView v, uint32_t n)
     else if (KIND == SGK_ERE_CHUNKS) sg_ere_chunks_item(v, i);
     else if (KIND == SGK_ERE_PROPOSE) sg_ere_propose_item(v, i);
     else if (KIND == SGK_ERE_DIRTY) sg_ere_dirty_item(v, i);
+    else if (KIND == SGK_ERE_CLAIM) sg_ere_claim_item(v, i);
+    else if (KIND == SGK_ERE_SAFE) sg_ere_safe_item(v, i);
+    else if (KIND == SGK_ERE_APPLY) sg_ere_apply_item(v, i);
     else if (KIND == SGK_ERE_FLAG01) v.ve_ncls[i] = v.ere_flags[i] != 0;
     else if (KIND == SGK_ERE_LIST) { if (v.ere_flags[i]) v.acting[v.ve_cls_off[i]] = i; }
 }
@@ -379,6 +383,7 @@ __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
     if (kind == SGS_PROP) sg_prop_serial(v);
     else if (kind == SGS_MARKS) sg_marks_serial(v, arg);
     else if (kind == SGS_APPLY_UNITS) sg_apply_units_serial(v, arg);
+    else if (kind == SGS_ERE_SPLIT) sg_ere_split_serial(v, arg, arg2);
 }
 
 __global__ void k_sort_units_small(SgView v, uint32_t n)
@@ -866,6 +871,9 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_ERE_CHUNKS: LAUNCH(k_items<SGK_ERE_CHUNKS>, blocks_for(n), TPB, s, v, n); break;
     case SGK_ERE_PROPOSE: LAUNCH(k_items<SGK_ERE_PROPOSE>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_ERE_DIRTY: LAUNCH(k_items<SGK_ERE_DIRTY>, blocks_for(n, 128), 128, s, v, n); break;
+    case SGK_ERE_CLAIM: LAUNCH(k_items<SGK_ERE_CLAIM>, blocks_for(32ull * n, 128), 128, s, v, n); break;
+    case SGK_ERE_SAFE: LAUNCH(k_items<SGK_ERE_SAFE>, blocks_for(32ull * n, 128), 128, s, v, n); break;
+    case SGK_ERE_APPLY: LAUNCH(k_items<SGK_ERE_APPLY>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_ERE_FLAG01: LAUNCH(k_items<SGK_ERE_FLAG01>, blocks_for(n), TPB, s, v, n); break;
     case SGK_ERE_LIST: LAUNCH(k_items<SGK_ERE_LIST>, blocks_for(n), TPB, s, v, n); break;
     default: snprintf(g_err, sizeof g_err, "be_items: bad kind %d", kind);

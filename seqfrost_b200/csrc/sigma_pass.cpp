@@ -137,6 +137,7 @@ SgView make_view(sigma_ctx *c)
     v.ve_aux = c->ve_aux.p; v.ve_cls_off = c->ve_cls_off.p; v.ve_lit_off = c->ve_lit_off.p; v.ve_mod_off = c->ve_mod_off.p;
     v.scr_off = c->scr_off.p; v.scratch = c->scratch.p; v.ubuf = c->ubuf.p; v.ubuf_cap = (uint32_t)c->ubuf.cap;
     v.ot_add = c->ot_add.p; v.ot_add_cap = (uint32_t)(c->ot_add.cap / 2);
+    v.ere_owner = nullptr; v.ere_done = nullptr;
     v.ere_touched = c->ere_touched.p; v.ere_flags = c->ere_flags.p; v.ere_eidx = c->scores.p;
     v.sc = c->sc.p;
     v.nvars = c->nvars; v.nlit = c->nlit; v.n_cls = c->n_cls; v.pool_used = c->pool_used;
@@ -474,6 +475,8 @@ int stage_ere(sigma_ctx *c)
     c->hsc.ere_events += n;
     if (n) {
         be_sort_units(c->stream, v, n);
+        c->hsc.ere_first_dirty = 0xFFFFFFFFu; c->hsc.ere_applied = 0; c->hsc.ere_par_events = 0; c->hsc.ere_list_start = 0;
+        CK(push_scalars(c));
         be_items(c->stream, SGK_ERE_DIRTY, v, E);
         /* ordered list of the positions to visit: flags -> 0/1 -> exclusive scan -> scatter into v.acting */
         be_memset(c->stream, c->ve_ncls.p, 0, (size_t)E * 4);
@@ -482,6 +485,22 @@ int stage_ere(sigma_ctx *c)
         CK(pull_totals(c, 1));
         const uint32_t n_list = c->h_totals[0];
         be_items(c->stream, SGK_ERE_LIST, v, E);
+        /* recorded pairs before the first dirty variable: parallel claim/apply rounds */
+        be_serial(c->stream, SGS_ERE_SPLIT, v, n, n_list);
+        CK(pull_scalars(c));
+        const uint32_t P = c->hsc.ere_par_events;
+        if (P && 2ull * n <= c->flags.cap) {
+            NOMEM(c->c_newid.ensure((size_t)c->n_cls + 16));
+            v.ere_owner = c->c_newid.p; v.ere_done = c->flags.p;
+            be_memset(c->stream, v.ere_done, 0, (size_t)n * 4);
+            for (int round = 0; round < 256 && c->hsc.ere_applied < P; ++round) {
+                be_memset(c->stream, v.ere_owner, 0xFF, (size_t)c->n_cls * 4);
+                be_items(c->stream, SGK_ERE_CLAIM, v, P);
+                be_items(c->stream, SGK_ERE_SAFE, v, P);
+                be_items(c->stream, SGK_ERE_APPLY, v, P);
+                CK(pull_scalars(c));
+            }
+        }
         c->hsc.ere_npending = 0; c->hsc.ere_overflow = 0;
         CK(push_scalars(c));
         be_serial(c->stream, SGS_ERE_REPLAY, v, n, n_list);

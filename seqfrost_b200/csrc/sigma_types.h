@@ -91,6 +91,7 @@ typedef struct SgScalars {
     uint32_t core[12];        /* orgcore[] (lcve.cpp:24): variables holding marks 0..11 */
     uint32_t n_core, n_ot_add;
     uint32_t ere_npending, ere_overflow;
+    uint32_t ere_first_dirty, ere_par_events, ere_list_start, ere_applied;
     uint32_t ere_pending[64];  /* elected positions that turned dirty during the replay and are not on its list */
 } SgScalars;
 
@@ -124,6 +125,8 @@ typedef struct SgView {
     uint8_t  *ere_touched;   /* per clause: may be deleted/strengthened by ERE */
     uint8_t  *ere_flags;     /* per elected variable: 1 = has recorded pairs, 2 = dirty */
     uint32_t *ere_eidx;      /* variable -> position in `elected` */
+    uint32_t *ere_owner;     /* per clause: earliest pending recorded pair that could write it (parallel rounds) */
+    uint32_t *ere_done;      /* per recorded pair: 0 pending, 2 apply this round, 1 applied; NULL = no parallel rounds */
     SgScalars *sc;
     uint32_t nvars, nlit;    /* nlit = 2*nvars + 2 */
     uint32_t n_cls;          /* clause ids in use */

@@ -187,6 +187,9 @@ void be_items(void *, int kind, const SgView &v, uint32_t n)
         case SGK_ERE_CHUNKS: sg_ere_chunks_item(v, i); break;
         case SGK_ERE_PROPOSE: sg_ere_propose_item(v, i); break;
         case SGK_ERE_DIRTY: sg_ere_dirty_item(v, i); break;
+        case SGK_ERE_CLAIM: sg_ere_claim_item(v, i); break;
+        case SGK_ERE_SAFE: sg_ere_safe_item(v, i); break;
+        case SGK_ERE_APPLY: sg_ere_apply_item(v, i); break;
         case SGK_ERE_FLAG01: v.ve_ncls[i] = v.ere_flags[i] != 0; break;
         case SGK_ERE_LIST: if (v.ere_flags[i]) v.acting[v.ve_cls_off[i]] = i; break;
         default: abort();
@@ -201,6 +204,7 @@ void be_serial(void *, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
     case SGS_MARKS: sg_marks_serial(v, arg); break;
     case SGS_APPLY_UNITS: sg_apply_units_serial(v, arg); break;
     case SGS_ERE_REPLAY: sg_ere_replay_serial(v, arg, arg2); break;
+    case SGS_ERE_SPLIT: sg_ere_split_serial(v, arg, arg2); break;
     default: abort();
     }
 }

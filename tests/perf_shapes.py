@@ -34,5 +34,5 @@ if __name__ == "__main__":
                           "elected": r["elected_per_phase"], "rounds": r["election_rounds"],
                           "stage_ms": {k: round(v, 2) for k, v in r["stage_ms"].items() if v > 0.005},
                           "eliminated": r["max_melted_delta"], "gates": [r[k] for k in ("inverters", "andors", "ites", "xors", "funs", "resolutions")],
-                          "launches": r["kernel_launches"]}))
+                          "launches": r["kernel_launches"], "ere": r["ere"]}))
     s.close()
