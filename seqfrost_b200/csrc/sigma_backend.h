@@ -73,22 +73,26 @@ void be_hist(void *s, const SgView &v, uint32_t *counts);
 /* scatter clause ids into the lists; cursor must hold a copy of ot_off (absolute write positions) */
 void be_scatter(void *s, const SgView &v, uint32_t *cursor);
 /* Incremental createOT for phases after the first.  The occurrence table the reference rebuilds from
- * scratch (simplify.cpp:39-61) differs from the table at the end of the previous phase only by: deleted
- * clauses (dropped), lists of eliminated variables (emptied), the order inside the elected lists (sortOT),
- * clause renumbering by shrinkSimp (newid, or NULL), the clauses with id >= first_new (resolvents) and the
- * (literal, clause) pairs in v.ot_add (equivalence substitution).  Writes the new table into
- * off2/len2/data2 exactly as a full rebuild would.  tmp: be_ot_update_tmp_words() words. */
+ * scratch (simplify.cpp:39-61) differs from the table at the end of the previous phase only in the lists that
+ * hold a clause deleted since (entries dropped), the lists of the last elected variables (sortOT order, or
+ * emptied when eliminated), and the lists that gain entries: literals of the clauses with id >= first_new
+ * (resolvents) and the (literal, clause) pairs in v.ot_add (equivalence substitution).  Only those lists are
+ * rewritten, in place; a list that gains entries moves to fresh room at the end of ot_data (lists are
+ * (offset, length) pairs and need not be packed).  Clause ids must be unchanged since the table was built.
+ *   be_ot_bitmap      : after a full build: bits = clauses represented in the table
+ *   be_ot_update_plan : marks the lists to rewrite; *total receives the words of fresh room needed
+ *   be_ot_update      : rewrites them (ot_data must have *bump + needed words of capacity) */
 struct SgOtUpdate {
-    int      renumber;          /* the store was compacted since be_ot_prepare: clause ids change to their rank among the live */
-    uint32_t n_cls_old;         /* clause ids covered by the old numbering */
-    uint32_t first_new;         /* first clause id (OLD numbering) that has no entry in the old table */
-    uint32_t n_add;             /* pairs in v.ot_add (old numbering) */
-    uint32_t *off2, *len2, *data2, *tmp, *total;
+    uint32_t *bits;             /* clauses represented in the table (updated) */
+    uint32_t first_new;         /* first clause id that has no entry in the table */
+    uint32_t n_add;             /* pairs in v.ot_add */
+    uint32_t n_elected;         /* entries of v.elected from the previous phase */
+    uint32_t *tmp, *total, *bump;
 };
 size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls);
-/* step 1, on the store BEFORE an optional compaction: liveness bitmap + rank prefix of the old clause ids */
-void be_ot_prepare(void *s, const SgView &v, uint32_t *tmp);
-/* step 2, on the store AFTER it: v = new store + old table */
+size_t be_ot_bits_words(uint32_t n_cls);
+void be_ot_bitmap(void *s, const SgView &v, uint32_t *bits);
+void be_ot_update_plan(void *s, const SgView &v, const SgOtUpdate &u);
 void be_ot_update(void *s, const SgView &v, const SgOtUpdate &u);
 /* compare two occurrence tables entry by entry (test hook); *mismatch receives the number of differences */
 void be_ot_compare(void *s, const SgView &v, const uint32_t *off2, const uint32_t *len2, const uint32_t *data2, uint32_t *mismatch);

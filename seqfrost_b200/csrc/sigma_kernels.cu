@@ -580,119 +580,140 @@ __global__ void k_live_apply(SgView v, const uint2 *__restrict__ part, uint4 *__
 }
 
 /* ---------------------------------------------------------------------------------------------- */
-/* incremental occurrence-table update (see sigma_backend.h)                                         */
+/* incremental occurrence-table update (see sigma_backend.h): only the lists that changed are touched  */
 /* ---------------------------------------------------------------------------------------------- */
-struct OtuTmp { uint32_t *bits, *prefix, *kept, *addc, *cursor, *flag, *scan; uint32_t words; };
-__host__ __device__ inline OtuTmp otu_layout(uint32_t *tmp, uint32_t nlit, uint32_t n_cls)
+struct OtuTmp { uint32_t *addc, *cursor, *flag; };
+__host__ __device__ inline OtuTmp otu_layout(uint32_t *tmp, uint32_t nlit)
 {
     OtuTmp t;
-    t.words = n_cls / 32 + 1;
-    t.bits = tmp; t.prefix = t.bits + t.words; t.kept = t.prefix + t.words + 1; t.addc = t.kept + nlit;
-    t.cursor = t.addc + nlit; t.flag = t.cursor + nlit; t.scan = t.flag + nlit;
+    t.addc = tmp; t.cursor = t.addc + nlit; t.flag = t.cursor + nlit;
     return t;
 }
-__device__ __forceinline__ bool otu_live(const uint32_t *bits, uint32_t c) { return (bits[c >> 5] >> (c & 31)) & 1u; }
-__device__ __forceinline__ uint32_t otu_rank(const uint32_t *bits, const uint32_t *prefix, uint32_t c)
-{
-    return prefix[c >> 5] + __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u));
-}
+enum { OTU_DIRTY = 1u, OTU_GROWN = 2u };
 
-__global__ void k_otu_bitmap(SgView v, uint32_t *__restrict__ bits, uint32_t *__restrict__ pop)
+/* bitmap of the clauses represented in the table (= live when it was last built or updated) */
+__global__ void k_otu_bitmap(SgView v, uint32_t *__restrict__ bits)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = c < v.n_cls && !(v.hdr[c].z & SG_DELETED);
     const uint32_t m = __ballot_sync(0xffffffffu, live);
-    if ((threadIdx.x & 31) == 0 && (c >> 5) <= v.n_cls / 32) { bits[c >> 5] = m; pop[c >> 5] = __popc(m); }
+    if ((threadIdx.x & 31) == 0) bits[c >> 5] = m;
 }
 
-/* occurrences that are not in the old table: literals of the clauses created last phase ... */
-__global__ void k_otu_new_clauses(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber,
-                                  uint32_t first_new, uint32_t n_cls_old, uint32_t *__restrict__ ctr, uint32_t *__restrict__ flag,
-                                  uint32_t *__restrict__ data2)
+/* clauses that died since: their lists are dirty; clauses that are new: their literals are additions */
+__global__ void k_otu_mark(SgView v, uint32_t *__restrict__ bits, uint32_t first_new, uint32_t *__restrict__ addc, uint32_t *__restrict__ flag)
 {
-    const uint32_t c = first_new + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cls_old || !otu_live(bits, c)) return;
-    const uint32_t id = renumber ? otu_rank(bits, prefix, c) : c;
-    const uint4 h = v.hdr[id];
-    const uint32_t *l = v.lits + h.x;
-    for (uint32_t k = 0; k < h.y; ++k) {
-        const uint32_t pos = atomicAdd(&ctr[l[k]], 1u);
-        if (data2) data2[pos] = id; else flag[l[k]] = 1;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = false;
+    if (c < v.n_cls) {
+        const uint4 h = v.hdr[c];
+        live = !(h.z & SG_DELETED);
+        const uint32_t *l = v.lits + h.x;
+        if (c >= first_new) {
+            if (live) for (uint32_t k = 0; k < h.y; ++k) { atomicAdd(&addc[l[k]], 1u); flag[l[k]] = OTU_DIRTY; }
+        } else if (!live && ((bits[c >> 5] >> (c & 31)) & 1u)) {
+            for (uint32_t k = 0; k < h.y; ++k) flag[l[k]] = OTU_DIRTY;
+        }
     }
+    const uint32_t m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0) bits[c >> 5] = m;
 }
-/* ... and the (literal, clause) pairs created by equivalence substitution */
-__global__ void k_otu_pairs(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber, uint32_t n,
-                            uint32_t *__restrict__ ctr, uint32_t *__restrict__ flag, uint32_t *__restrict__ data2)
+__global__ void k_otu_pairs_count(SgView v, uint32_t n, uint32_t *__restrict__ addc, uint32_t *__restrict__ flag)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t lit = v.ot_add[2 * i], c = v.ot_add[2 * i + 1];
-    if (!otu_live(bits, c)) return;
-    const uint32_t pos = atomicAdd(&ctr[lit], 1u);
-    if (data2) data2[pos] = renumber ? otu_rank(bits, prefix, c) : c; else flag[lit] = 1;
+    if (v.hdr[c].z & SG_DELETED) return;
+    atomicAdd(&addc[lit], 1u);
+    flag[lit] = OTU_DIRTY;
+}
+/* the lists of last phase's elected variables are in sortOT order (or belong to an eliminated variable) */
+__global__ void k_otu_elected(SgView v, uint32_t n, uint32_t *__restrict__ flag)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t x = v.elected[i];
+    flag[2 * x] = OTU_DIRTY; flag[2 * x + 1] = OTU_DIRTY;
+}
+/* words the grown lists need at the end of ot_data */
+__global__ void k_otu_need(SgView v, const uint32_t *__restrict__ addc, uint32_t *need)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w = 0;
+    if (lit < v.nlit && addc[lit] && !(v.state[lit >> 1] & SG_MELTED_M)) w = v.ot_len[lit] + addc[lit];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) w += __shfl_down_sync(0xffffffffu, w, d);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(need, w);
 }
 
-/* room for every list: its current length (an upper bound of what survives) plus its additions; the lists need
- * not be packed, so no liveness count is needed before the copy */
-__global__ void k_otu_room(SgView v, const uint32_t *__restrict__ addc, uint32_t *__restrict__ room)
+__global__ void k_otu_apply(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ addc,
+                            uint32_t *__restrict__ cursor, uint32_t *__restrict__ flag, uint32_t *bump)
 {
     const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
     if (lit >= v.nlit) return;
-    room[lit] = ((v.state[lit >> 1] & SG_MELTED_M) ? 0u : v.ot_len[lit]) + addc[lit];
-}
-
-__global__ void k_otu_copy(SgView v, const uint32_t *__restrict__ bits, const uint32_t *__restrict__ prefix, int renumber,
-                           const uint32_t *__restrict__ off2, uint32_t *__restrict__ cursor, uint32_t *__restrict__ flag,
-                           uint32_t *__restrict__ len2, const uint32_t *__restrict__ addc, uint32_t *__restrict__ data2)
-{
-    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lit >= v.nlit) return;
-    const uint32_t base = off2[lit];
-    uint32_t n = 0, unsorted = 0;
-    if (!(v.state[lit >> 1] & SG_MELTED_M)) {
-        const uint32_t len = v.ot_len[lit];
-        const uint32_t *d = v.ot_data + v.ot_off[lit];
-        uint32_t prev = 0;
-        for (uint32_t i0 = 0; i0 < len; i0 += 8) {
-            /* 8 entries at a time: ids, then their bitmap words, then their rank prefixes - independent loads */
-            uint32_t c[8], w[8], r[8];
+    if (v.state[lit >> 1] & SG_MELTED_M) { v.ot_len[lit] = 0; flag[lit] = 0; return; }   /* eliminated: no live clause holds it */
+    const uint32_t f = flag[lit];
+    if (!f) return;                                       /* untouched list */
+    const uint32_t len = v.ot_len[lit], a = addc[lit];
+    const uint32_t *src = v.ot_data + v.ot_off[lit];
+    uint32_t *dst = v.ot_data + v.ot_off[lit];
+    if (a) {                                              /* grows: move to fresh room at the end of the table */
+        const uint32_t base = atomicAdd(bump, len + a);
+        dst = v.ot_data + base;
+        v.ot_off[lit] = base;
+    }
+    uint32_t n = 0, prev = 0, unsorted = 0;
+    for (uint32_t i0 = 0; i0 < len; i0 += 8) {
+        /* liveness from the bitmap the plan just refreshed (1 bit per clause, cache resident); 8 entries per step */
+        uint32_t c[8], w[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) c[k] = i0 + k < len ? d[i0 + k] : 0xFFFFFFFFu;
+        for (int k = 0; k < 8; ++k) c[k] = i0 + k < len ? src[i0 + k] : 0xFFFFFFFFu;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = c[k] != 0xFFFFFFFFu ? bits[c[k] >> 5] : 0u;
+        for (int k = 0; k < 8; ++k) w[k] = c[k] != 0xFFFFFFFFu ? bits[c[k] >> 5] : 0u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = (renumber && c[k] != 0xFFFFFFFFu) ? prefix[c[k] >> 5] : 0u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (c[k] == 0xFFFFFFFFu || !((w[k] >> (c[k] & 31)) & 1u)) continue;
-                const uint32_t id = renumber ? r[k] + __popc(w[k] & ((1u << (c[k] & 31)) - 1u)) : c[k];
-                if (n && id < prev) unsorted = 1;
-                prev = id;
-                data2[base + n++] = id;
-            }
-        }
-        if (unsorted) {                       /* an elected list (sortOT order): back to clause-id order */
-            uint32_t *o = data2 + base;
-            for (uint32_t i = 1; i < n; ++i) {
-                const uint32_t t = o[i];
-                uint32_t j = i;
-                while (j > 0 && o[j - 1] > t) { o[j] = o[j - 1]; --j; }
-                o[j] = t;
-            }
+        for (int k = 0; k < 8; ++k) {
+            if (c[k] == 0xFFFFFFFFu || !((w[k] >> (c[k] & 31)) & 1u)) continue;
+            if (n && c[k] < prev) unsorted = 1;
+            prev = c[k];
+            dst[n++] = c[k];
         }
     }
-    cursor[lit] = base + n;
-    len2[lit] = n + addc[lit];
-    (void)flag;
+    if (unsorted) {                                       /* sortOT order -> clause-id order */
+        for (uint32_t i = 1; i < n; ++i) {
+            const uint32_t t = dst[i];
+            uint32_t j = i;
+            while (j > 0 && dst[j - 1] > t) { dst[j] = dst[j - 1]; --j; }
+            dst[j] = t;
+        }
+    }
+    v.ot_len[lit] = n + a;
+    cursor[lit] = v.ot_off[lit] + n;
+    flag[lit] = a ? OTU_GROWN : 0u;
 }
 
-__global__ void k_otu_sort(uint32_t nlit, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ off2,
-                           const uint32_t *__restrict__ len2, uint32_t *__restrict__ data2)
+__global__ void k_otu_append_clauses(SgView v, uint32_t first_new, uint32_t *__restrict__ cursor)
+{
+    const uint32_t c = first_new + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.n_cls) return;
+    const uint4 h = v.hdr[c];
+    if (h.z & SG_DELETED) return;
+    const uint32_t *l = v.lits + h.x;
+    for (uint32_t k = 0; k < h.y; ++k) v.ot_data[atomicAdd(&cursor[l[k]], 1u)] = c;
+}
+__global__ void k_otu_append_pairs(SgView v, uint32_t n, uint32_t *__restrict__ cursor)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lit = v.ot_add[2 * i], c = v.ot_add[2 * i + 1];
+    if (v.hdr[c].z & SG_DELETED) return;
+    v.ot_data[atomicAdd(&cursor[lit], 1u)] = c;
+}
+__global__ void k_otu_sort(SgView v, const uint32_t *__restrict__ flag)
 {
     const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lit >= nlit || !flag[lit]) return;
-    uint32_t *d = data2 + off2[lit];
-    const int n = (int)len2[lit];
+    if (lit >= v.nlit || flag[lit] != OTU_GROWN) return;
+    uint32_t *d = v.ot_data + v.ot_off[lit];
+    const int n = (int)v.ot_len[lit];
     for (int i = 1; i < n; ++i) {
         const uint32_t t = d[i];
         int j = i;
@@ -933,32 +954,30 @@ void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *ar
     if (nb) LAUNCH(k_live_apply<true>, nb, TPB, s, v, (const uint2 *)tmp, (uint4 *)nullptr, (uint32_t *)nullptr, arena, (unsigned long long *)refs);
 }
 
-size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls)
+size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls) { (void)n_cls; return 3 * (size_t)nlit + 64; }
+size_t be_ot_bits_words(uint32_t n_cls) { return (size_t)n_cls / 32 + 2; }
+void be_ot_bitmap(void *s, const SgView &v, uint32_t *bits)
 {
-    const size_t words = (size_t)n_cls / 32 + 1;
-    return 2 * words + 1 + 4 * (size_t)nlit + be_scan_tmp_words(nlit > words ? nlit : (uint32_t)words) + 64;
+    LAUNCH(k_otu_bitmap, blocks_for(((uint64_t)v.n_cls / 32 + 1) * 32), TPB, s, v, bits);
 }
-void be_ot_prepare(void *s, const SgView &v, uint32_t *tmp)
+void be_ot_update_plan(void *s, const SgView &v, const SgOtUpdate &u)
 {
-    const OtuTmp t = otu_layout(tmp, v.nlit, v.n_cls);
-    LAUNCH(k_otu_bitmap, blocks_for((uint64_t)t.words * 32), TPB, s, v, t.bits, t.prefix);
-    be_scan_u32(s, t.prefix, t.prefix, t.words, nullptr, t.scan);
+    const OtuTmp t = otu_layout(u.tmp, v.nlit);
+    cudaMemsetAsync(t.addc, 0, (size_t)v.nlit * 4, ST(s));
+    cudaMemsetAsync(t.flag, 0, (size_t)v.nlit * 4, ST(s));
+    cudaMemsetAsync(u.total, 0, 4, ST(s));
+    LAUNCH(k_otu_mark, blocks_for(((uint64_t)v.n_cls / 32 + 1) * 32), TPB, s, v, u.bits, u.first_new, t.addc, t.flag);
+    if (u.n_add) LAUNCH(k_otu_pairs_count, blocks_for(u.n_add), TPB, s, v, u.n_add, t.addc, t.flag);
+    if (u.n_elected) LAUNCH(k_otu_elected, blocks_for(u.n_elected), TPB, s, v, u.n_elected, t.flag);
+    LAUNCH(k_otu_need, blocks_for(v.nlit), TPB, s, v, t.addc, u.total);
 }
 void be_ot_update(void *s, const SgView &v, const SgOtUpdate &u)
 {
-    const OtuTmp t = otu_layout(u.tmp, v.nlit, u.n_cls_old);
-    const uint32_t nlit = v.nlit;
-    cudaMemsetAsync(t.addc, 0, (size_t)nlit * 4, ST(s));
-    cudaMemsetAsync(t.flag, 0, (size_t)nlit * 4, ST(s));
-    const uint32_t n_new = u.n_cls_old > u.first_new ? u.n_cls_old - u.first_new : 0;
-    if (n_new) LAUNCH(k_otu_new_clauses, blocks_for(n_new), TPB, s, v, t.bits, t.prefix, u.renumber, u.first_new, u.n_cls_old, t.addc, t.flag, (uint32_t *)nullptr);
-    if (u.n_add) LAUNCH(k_otu_pairs, blocks_for(u.n_add), TPB, s, v, t.bits, t.prefix, u.renumber, u.n_add, t.addc, t.flag, (uint32_t *)nullptr);
-    LAUNCH(k_otu_room, blocks_for(nlit), TPB, s, v, t.addc, t.kept);
-    be_scan_u32(s, t.kept, u.off2, nlit, u.total, t.scan);
-    LAUNCH(k_otu_copy, blocks_for(nlit), TPB, s, v, t.bits, t.prefix, u.renumber, u.off2, t.cursor, t.flag, u.len2, t.addc, u.data2);
-    if (n_new) LAUNCH(k_otu_new_clauses, blocks_for(n_new), TPB, s, v, t.bits, t.prefix, u.renumber, u.first_new, u.n_cls_old, t.cursor, t.flag, u.data2);
-    if (u.n_add) LAUNCH(k_otu_pairs, blocks_for(u.n_add), TPB, s, v, t.bits, t.prefix, u.renumber, u.n_add, t.cursor, t.flag, u.data2);
-    LAUNCH(k_otu_sort, blocks_for(nlit), TPB, s, nlit, t.flag, u.off2, u.len2, u.data2);
+    const OtuTmp t = otu_layout(u.tmp, v.nlit);
+    LAUNCH(k_otu_apply, blocks_for(v.nlit), TPB, s, v, u.bits, t.addc, t.cursor, t.flag, u.bump);
+    if (v.n_cls > u.first_new) LAUNCH(k_otu_append_clauses, blocks_for(v.n_cls - u.first_new), TPB, s, v, u.first_new, t.cursor);
+    if (u.n_add) LAUNCH(k_otu_append_pairs, blocks_for(u.n_add), TPB, s, v, u.n_add, t.cursor);
+    LAUNCH(k_otu_sort, blocks_for(v.nlit), TPB, s, v, t.flag);
 }
 void be_ot_compare(void *s, const SgView &v, const uint32_t *off2, const uint32_t *len2, const uint32_t *data2, uint32_t *mismatch)
 {

@@ -64,11 +64,12 @@ struct sigma_ctx {
     DBuf<uint32_t> ve_type, ve_ncls, ve_nlits, ve_nmodel, ve_aux, ve_cls_off, ve_lit_off, ve_mod_off, scr_len, scr_off, scratch;
     DBuf<SgUnit> ubuf;
     DBuf<uint8_t> ere_touched, ere_flags;
-    DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add;
+    DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add, otbits;
+    uint64_t phase_add_lits = 0;     /* literals of the resolvents the latest VE stage added */
+    uint32_t last_elected = 0;       /* size of `elected` after the latest election (hsc.n_elected does not survive a pull) */
+    uint64_t ot_end = 0;             /* words of ot_data in use (the updated table is not packed) */
     bool ot_valid = false, ot_incremental = true, ot_verify = false;
     uint32_t ot_first_new = 0;
-    uint64_t ot_room = 0;            /* upper bound of the words the (unpacked) table can occupy */
-    uint64_t ot_pending_add = 0;     /* literals of the clauses created since the table was last built/updated */
     DBuf<uint32_t> totals;          /* device slots for scan totals */
     DBuf<SgScalars> sc;
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
@@ -206,10 +207,9 @@ int stage_ingest(sigma_ctx *c)
 }
 
 /* ---- createOT (simplify.cpp:39-61) ------------------------------------------------------------ */
-int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
+int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls, bool track = true)
 {
     const uint32_t nlit = c->nlit;
-    c->ot_room = live_lits; c->ot_pending_add = 0;
     NOMEM(c->ot_data.ensure((size_t)live_lits + 16));
     SgView v = make_view(c);
     {
@@ -231,35 +231,52 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls)
         be_items(c->stream, SGK_IDSORT, v, nlit);
     }
     (void)live_cls;
+    if (track && c->ot_incremental) {
+        /* remember which clauses the table represents: later phases update it instead of rebuilding */
+        NOMEM(c->otbits.ensure(be_ot_bits_words(c->n_cls) + 64));
+        Stage st(c, SIGMA_T_OT_UPDATE, 16ull * c->n_cls);
+        be_ot_bitmap(c->stream, v, c->otbits.p);
+        c->ot_end = live_lits;
+    }
     return SIGMA_OK;
 }
 
 /* ---- createOT for a later phase, as an update of the previous phase's table (sigma_backend.h) ---- */
-int stage_update_ot(sigma_ctx *c, uint64_t live_lits, uint32_t n_cls_old, bool renumber)
+int stage_update_ot(sigma_ctx *c, uint64_t live_lits)
 {
     const uint32_t nlit = c->nlit;
-    /* the updated lists are not packed: each keeps room for its previous length plus its additions */
-    c->ot_room += c->ot_pending_add + c->hsc.n_ot_add;
-    c->ot_pending_add = 0;
-    NOMEM(c->ot_off2.ensure(nlit + 1)); NOMEM(c->ot_len2.ensure(nlit)); NOMEM(c->ot_data2.ensure((size_t)c->ot_room + 16));
-    SgView v = make_view(c);
-    SgOtUpdate u;
-    u.renumber = renumber ? 1 : 0; u.n_cls_old = n_cls_old; u.first_new = c->ot_first_new; u.n_add = c->hsc.n_ot_add;
-    u.off2 = c->ot_off2.p; u.len2 = c->ot_len2.p; u.data2 = c->ot_data2.p; u.tmp = c->otutmp.p; u.total = c->totals.p;
+    NOMEM(c->otutmp.ensure(be_ot_update_tmp_words(nlit, c->n_cls)));
     {
-        Stage st(c, SIGMA_T_OT_UPDATE, 12 * live_lits + 16ull * nlit);
-        be_ot_update(c->stream, v, u);
+        const size_t have = c->otbits.cap;
+        const size_t need = be_ot_bits_words(c->n_cls) + 64;
+        if (need > have) NOMEM(c->otbits.ensure(need, c->stream, have));
     }
-    { DBuf<uint32_t> t = c->ot_off; c->ot_off = c->ot_off2; c->ot_off2 = t; }
-    { DBuf<uint32_t> t = c->ot_len; c->ot_len = c->ot_len2; c->ot_len2 = t; }
-    { DBuf<uint32_t> t = c->ot_data; c->ot_data = c->ot_data2; c->ot_data2 = t; }
+    SgOtUpdate u;
+    u.bits = c->otbits.p; u.first_new = c->ot_first_new; u.n_add = c->hsc.n_ot_add; u.n_elected = c->last_elected;
+    u.tmp = c->otutmp.p; u.total = c->totals.p + 12; u.bump = c->totals.p + 13;
+    {
+        Stage st(c, SIGMA_T_OT_UPDATE, 16ull * c->n_cls + 12ull * nlit);
+        SgView v = make_view(c);
+        be_ot_update_plan(c->stream, v, u);
+        CK(pull_totals(c, 13));
+        const uint32_t need = c->h_totals[12];
+        if (c->ot_end + need >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "occurrence table exceeds 32-bit offsets");
+        NOMEM(c->ot_data.ensure((size_t)c->ot_end + need + 16, c->stream, (size_t)c->ot_end));
+        c->h_totals[13] = (uint32_t)c->ot_end;
+        be_h2d(c->stream, c->totals.p + 13, c->h_totals + 13, 4);
+        v = make_view(c);
+        be_ot_update(c->stream, v, u);
+        c->rep.stage_bytes[SIGMA_T_OT_UPDATE] += 8ull * need;
+        if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;   /* h_totals[13] is reused below */
+        c->ot_end += need;
+    }
     if (c->ot_verify) {
-        /* test hook: rebuild from scratch into the spare buffers and compare */
+        /* test hook: rebuild from scratch into the spare buffers and compare list by list */
         sigma_ctx &x = *c;
         DBuf<uint32_t> so = x.ot_off, sl = x.ot_len, sd = x.ot_data;
-        NOMEM(x.ot_data2.ensure((size_t)live_lits + 16));
+        NOMEM(x.ot_off2.ensure(nlit + 1)); NOMEM(x.ot_len2.ensure(nlit)); NOMEM(x.ot_data2.ensure((size_t)live_lits + 16));
         x.ot_off = x.ot_off2; x.ot_len = x.ot_len2; x.ot_data = x.ot_data2;
-        int rc = stage_create_ot(c, live_lits, 0);
+        int rc = stage_create_ot(c, live_lits, 0, false);
         x.ot_off2 = x.ot_off; x.ot_len2 = x.ot_len; x.ot_data2 = x.ot_data;
         x.ot_off = so; x.ot_len = sl; x.ot_data = sd;
         if (rc != SIGMA_OK) return rc;
@@ -352,6 +369,7 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         be_acting_scatter(c->stream, v, c->flags.p, c->pos.p, c->flags.p + V, c->pos.p + V);
         CK(pull_totals(c, 2));
         c->hsc.n_acting = c->h_totals[0]; c->hsc.n_elected = c->h_totals[1];
+        c->last_elected = c->h_totals[1];
         be_serial(c->stream, SGS_MARKS, v, c->hsc.n_acting);
     }
     if (phase < 8) { c->rep.elected_per_phase[phase] = c->hsc.n_elected; c->rep.election_rounds[phase] = rounds; }
@@ -378,7 +396,7 @@ int apply_units(sigma_ctx *c, SgView &v)
 /* sortOT (simplify.cpp:85-100) */
 int stage_sortot(sigma_ctx *c)
 {
-    const uint32_t E = c->hsc.n_elected;
+    const uint32_t E = c->last_elected;
     Stage st(c, SIGMA_T_SOT);
     SgView v = make_view(c);
     v.n_elected = E;
@@ -388,7 +406,7 @@ int stage_sortot(sigma_ctx *c)
 
 int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
 {
-    const uint32_t E = c->hsc.n_elected;
+    const uint32_t E = c->last_elected;
     NOMEM(c->ve_type.ensure(E + 1)); NOMEM(c->ve_ncls.ensure(E + 1)); NOMEM(c->ve_nlits.ensure(E + 1));
     NOMEM(c->ve_nmodel.ensure(E + 1)); NOMEM(c->ve_aux.ensure(E + 1)); NOMEM(c->ve_cls_off.ensure(E + 1));
     NOMEM(c->ve_lit_off.ensure(E + 1)); NOMEM(c->ve_mod_off.ensure(E + 1)); NOMEM(c->scr_len.ensure(E + 1));
@@ -407,6 +425,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     NOMEM(c->ubuf.ensure(2ull * scr_total + 4096));
     NOMEM(c->ot_add.ensure(2ull * scr_total + 128));
     c->ot_first_new = c->n_cls;
+    c->phase_add_lits = 0;
     v = make_view(c);
     v.n_elected = E;
     v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
@@ -437,7 +456,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         be_items(c->stream, SGK_VE_EMIT, v, E);
         c->n_cls += add_cls;
         c->pool_used += add_lits;
-        c->ot_pending_add += add_lits;
+        c->phase_add_lits = add_lits;
         c->model_words += add_model;
         v = make_view(c);
         int rc = apply_units(c, v);
@@ -452,7 +471,7 @@ int stage_ere(sigma_ctx *c)
     if (!c->opts.ere_en) return SIGMA_OK;
     if (c->opts.ere_clause_max > 256) return fail(c, SIGMA_E_UNSUPPORTED, "--redundancyclausemax above 256 is not supported");
     if (c->opts.ere_max_occurs > 65535) return fail(c, SIGMA_E_UNSUPPORTED, "--redundancymaxoccurs above 65535 is not supported");
-    const uint32_t E = c->hsc.n_elected;
+    const uint32_t E = c->last_elected;
     if (!E) return SIGMA_OK;
     NOMEM(c->ere_touched.ensure((size_t)c->n_cls + 16)); NOMEM(c->ere_flags.ensure((size_t)E + 16));
     NOMEM(c->ubuf.ensure((size_t)(1u << 20) + 4ull * E));
@@ -578,21 +597,21 @@ int run_phases(sigma_ctx *c)
     uint32_t multiplier = 0;
     int64_t litsbefore = (int64_t)c->in_literals, diff = INT64_MAX;
     uint64_t live_lits = c->in_literals;
+    int64_t prev_live_lits = (int64_t)c->in_literals;
     uint32_t live_cls = c->in_ncls;
     while (litsbefore) {
         if (interrupted(c)) return SIGMA_INTERRUPTED;
         const int times = phase + 1;                       /* resizeCNF, solve.hpp:626-630 */
-        const bool compact = times > 1 && times != o.phases && (times % o.collect_freq) == 0;
-        const bool incr = c->ot_incremental && c->ot_valid && c->hsc.n_ot_add <= c->ot_add.cap / 2;
-        const uint32_t n_cls_old = c->n_cls;
-        if (incr) {
-            NOMEM(c->otutmp.ensure(be_ot_update_tmp_words(c->nlit, n_cls_old)));
-            Stage st(c, SIGMA_T_OT_UPDATE, 16ull * n_cls_old);
-            SgView v = make_view(c);
-            be_ot_prepare(c->stream, v, c->otutmp.p);
-        }
+        /* update the table in place when the last phase changed little of it (literals added + literals
+         * removed under 10 % of the live ones) and the store is still mostly live; otherwise rebuild */
+        const uint64_t removed = (uint64_t)(prev_live_lits + (int64_t)c->phase_add_lits - (int64_t)live_lits);
+        const bool incr = c->ot_incremental && c->ot_valid && c->hsc.n_ot_add <= c->ot_add.cap / 2 &&
+                          2ull * live_cls >= c->n_cls && 10ull * (c->phase_add_lits + removed) < live_lits;
+        /* shrinkSimp between phases only renumbers the clauses (order, flags and literals are preserved), so it
+         * is skipped while the table is being updated in place; it still runs when half of the store is dead */
+        const bool compact = !incr && times > 1 && times != o.phases && (times % o.collect_freq) == 0;
         if (compact) CK(stage_compact(c));
-        if (incr) CK(stage_update_ot(c, live_lits, n_cls_old, compact));
+        if (incr) CK(stage_update_ot(c, live_lits));
         else CK(stage_create_ot(c, live_lits, live_cls));
         c->ot_valid = false;
         if (stop_here(c, phase, SIGMA_T_OT_ORDER)) return SIGMA_OK;
@@ -611,6 +630,7 @@ int run_phases(sigma_ctx *c)
         if (stop_here(c, phase, SIGMA_T_VE)) return SIGMA_OK;
         CK(stage_count(c));
         c->ot_valid = true;                                /* a complete phase: the table can be updated in place of a rebuild */
+        prev_live_lits = (int64_t)live_lits;
         live_cls = c->hsc.live_cls; live_lits = c->hsc.live_lits;
         diff = litsbefore - (int64_t)live_lits; litsbefore = (int64_t)live_lits;
         phase++;
@@ -670,7 +690,7 @@ void sigma_destroy(sigma_ctx *c)
         c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
         c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
         c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release();
-        c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->totals.release(); c->sc.release();
+        c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->otbits.release(); c->totals.release(); c->sc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
         c->arena_out.release(); c->refs_out.release();
         for (void *e2 : c->evpool) be_event_destroy(e2);

@@ -263,26 +263,91 @@ void be_export_apply(void *, const SgView &v, const uint32_t *tmp, uint32_t *are
     }
 }
 
-size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t) { return (size_t)nlit + 16; }
-void be_ot_prepare(void *, const SgView &, uint32_t *) { g_launches++; }
-void be_ot_update(void *st, const SgView &v, const SgOtUpdate &u)
-{   /* the stand-in simply rebuilds the table from the (new) store: what the incremental kernels must equal */
-    SgView w = v;
-    w.ot_off = u.off2; w.ot_len = u.len2; w.ot_data = u.data2;
-    memset(u.len2, 0, (size_t)v.nlit * 4);
-    be_hist(st, w, u.len2);
-    be_scan_u32(st, u.len2, u.off2, v.nlit, u.total, nullptr);
-    memcpy(u.tmp, u.off2, (size_t)v.nlit * 4);
-    be_scatter(st, w, u.tmp);
-    be_items(st, SGK_IDSORT, w, v.nlit);
+/* serial restatement of the incremental occurrence-table update (k_otu_* in sigma_kernels.cu) */
+size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t) { return 3 * (size_t)nlit + 64; }
+size_t be_ot_bits_words(uint32_t n_cls) { return (size_t)n_cls / 32 + 2; }
+void be_ot_bitmap(void *, const SgView &v, uint32_t *bits)
+{
+    g_launches++;
+    for (uint32_t w = 0; w <= v.n_cls / 32; ++w) bits[w] = 0;
+    for (uint32_t c = 0; c < v.n_cls; ++c) if (!(v.hdr[c].z & SG_DELETED)) bits[c >> 5] |= 1u << (c & 31);
+}
+void be_ot_update_plan(void *, const SgView &v, const SgOtUpdate &u)
+{
+    g_launches++;
+    uint32_t *addc = u.tmp, *flag = u.tmp + 2 * (size_t)v.nlit;
+    memset(addc, 0, (size_t)v.nlit * 4); memset(flag, 0, (size_t)v.nlit * 4);
+    for (uint32_t c = 0; c < v.n_cls; ++c) {
+        const sg_u4 h = v.hdr[c];
+        const bool live = !(h.z & SG_DELETED);
+        const uint32_t *l = v.lits + h.x;
+        if (c >= u.first_new) { if (live) for (uint32_t k = 0; k < h.y; ++k) { addc[l[k]]++; flag[l[k]] = 1; } }
+        else if (!live && ((u.bits[c >> 5] >> (c & 31)) & 1u)) for (uint32_t k = 0; k < h.y; ++k) flag[l[k]] = 1;
+        if (live) u.bits[c >> 5] |= 1u << (c & 31); else u.bits[c >> 5] &= ~(1u << (c & 31));
+    }
+    for (uint32_t i = 0; i < u.n_add; ++i) {
+        const uint32_t lit = v.ot_add[2 * i], c = v.ot_add[2 * i + 1];
+        if (v.hdr[c].z & SG_DELETED) continue;
+        addc[lit]++; flag[lit] = 1;
+    }
+    for (uint32_t i = 0; i < u.n_elected; ++i) { flag[2 * v.elected[i]] = 1; flag[2 * v.elected[i] + 1] = 1; }
+    uint32_t need = 0;
+    for (uint32_t lit = 0; lit < v.nlit; ++lit) if (addc[lit] && !(v.state[lit >> 1] & SG_MELTED_M)) need += v.ot_len[lit] + addc[lit];
+    *u.total = need;
+}
+void be_ot_update(void *, const SgView &v, const SgOtUpdate &u)
+{
+    g_launches++;
+    uint32_t *addc = u.tmp, *cursor = u.tmp + (size_t)v.nlit, *flag = u.tmp + 2 * (size_t)v.nlit;
+    for (uint32_t lit = 0; lit < v.nlit; ++lit) {
+        if (v.state[lit >> 1] & SG_MELTED_M) { v.ot_len[lit] = 0; flag[lit] = 0; continue; }
+        if (!flag[lit]) continue;
+        const uint32_t len = v.ot_len[lit], a = addc[lit];
+        const uint32_t *src = v.ot_data + v.ot_off[lit];
+        uint32_t *dst = v.ot_data + v.ot_off[lit];
+        if (a) { const uint32_t base = *u.bump; *u.bump += len + a; dst = v.ot_data + base; v.ot_off[lit] = base; }
+        uint32_t n = 0;
+        for (uint32_t i = 0; i < len; ++i) { const uint32_t c = src[i]; if (v.hdr[c].z & SG_DELETED) continue; dst[n++] = c; }
+        std::sort(dst, dst + n);
+        v.ot_len[lit] = n + a;
+        cursor[lit] = v.ot_off[lit] + n;
+        flag[lit] = a ? 2u : 0u;
+    }
+    for (uint32_t c = u.first_new; c < v.n_cls; ++c) {
+        const sg_u4 h = v.hdr[c];
+        if (h.z & SG_DELETED) continue;
+        for (uint32_t k = 0; k < h.y; ++k) v.ot_data[cursor[v.lits[h.x + k]]++] = c;
+    }
+    for (uint32_t i = 0; i < u.n_add; ++i) {
+        const uint32_t lit = v.ot_add[2 * i], c = v.ot_add[2 * i + 1];
+        if (v.hdr[c].z & SG_DELETED) continue;
+        v.ot_data[cursor[lit]++] = c;
+    }
+    for (uint32_t lit = 0; lit < v.nlit; ++lit) if (flag[lit] == 2u) std::sort(v.ot_data + v.ot_off[lit], v.ot_data + v.ot_off[lit] + v.ot_len[lit]);
 }
 void be_ot_compare(void *, const SgView &v, const uint32_t *off2, const uint32_t *len2, const uint32_t *data2, uint32_t *mismatch)
 {
     g_launches++;
     uint32_t bad = 0;
     for (uint32_t l = 0; l < v.nlit; ++l) {
-        if (v.ot_len[l] != len2[l]) { bad++; continue; }
-        for (uint32_t i = 0; i < len2[l]; ++i) if (v.ot_data[v.ot_off[l] + i] != data2[off2[l] + i]) { bad++; break; }
+        if (v.ot_len[l] != len2[l]) {
+            if (getenv("SIGMA_EMUL_DEBUG") && bad < 4) {
+                fprintf(stderr, "lit %u: len %u vs rebuild %u state %u\n  upd:", l, v.ot_len[l], len2[l], v.state[l >> 1]);
+                for (uint32_t i = 0; i < v.ot_len[l]; ++i) fprintf(stderr, " %u%s", v.ot_data[v.ot_off[l] + i], (v.hdr[v.ot_data[v.ot_off[l] + i]].z & SG_DELETED) ? "x" : "");
+                fprintf(stderr, "\n  new:");
+                for (uint32_t i = 0; i < len2[l]; ++i) fprintf(stderr, " %u", data2[off2[l] + i]);
+                fprintf(stderr, "\n");
+            }
+            bad++; continue; }
+        for (uint32_t i = 0; i < len2[l]; ++i) if (v.ot_data[v.ot_off[l] + i] != data2[off2[l] + i]) {
+            if (getenv("SIGMA_EMUL_DEBUG") && bad < 4) {
+                fprintf(stderr, "lit %u: entries differ (len %u) state %u off %u\n  upd:", l, len2[l], v.state[l >> 1], v.ot_off[l]);
+                for (uint32_t q = 0; q < v.ot_len[l]; ++q) fprintf(stderr, " %u", v.ot_data[v.ot_off[l] + q]);
+                fprintf(stderr, "\n  new:");
+                for (uint32_t q = 0; q < len2[l]; ++q) fprintf(stderr, " %u", data2[off2[l] + q]);
+                fprintf(stderr, "\n");
+            }
+            bad++; break; }
     }
     *mismatch = bad;
 }
