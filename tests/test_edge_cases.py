@@ -1,0 +1,157 @@
+"""Edge cases the reference's own code paths make special: occurrence lists longer than 24 with tied sort keys
+(std::sort branch of sortOT, sort.hpp:64-72), clauses beyond --subsumeclausemax / --boundedclausemax, hub
+variables beyond the election caps, formulas the pass empties completely, and the C-ABI error paths.
+CPU: serial stand-in of the launch layer; GPU (-m gpu): the CUDA library.  Checker: oracle/_ref/ref_sigma."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity
+from conftest import GOLDEN, REF_BIN
+from seqfrost_b200 import boundary as B, sigma
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ref_sigma not built")
+
+
+def _cases():
+    rng = random.Random(1)
+    out = {}
+    cl = [[1, 2 + (r % 3), 50] for r in range(28)] + [[-1, 60 + r, 70 + r] for r in range(3)]
+    for _ in range(900):
+        vs = rng.sample(range(2, 401), 3)
+        cl.append([v if rng.random() < .5 else -v for v in vs])
+    out["ties_gt24"] = (400, cl, [])
+    cl = []
+    for _ in range(40):
+        vs = rng.sample(range(1, 601), rng.choice([120, 150, 30, 26]))
+        cl.append([v if rng.random() < .5 else -v for v in vs])
+    for _ in range(1500):
+        vs = rng.sample(range(1, 601), 3)
+        cl.append([v if rng.random() < .5 else -v for v in vs])
+    out["big_clauses"] = (600, cl, [])
+    cl = [[1 if k % 2 else -1, 2 + k, 1300 + k] for k in range(1200)]
+    for _ in range(6000):
+        vs = rng.sample(range(2, 3001), 3)
+        cl.append([v if rng.random() < .5 else -v for v in vs])
+    out["hub"] = (3000, cl, [])
+    out["hub_wide_mu"] = (3000, cl, ["--mupos=2000", "--muneg=2000", "--subsumemaxoccurs=100"])
+    out["emptied_4"] = (3, [[1, 2], [-1, 3], [2, 3], [-2, -3, 1]], [])
+    out["emptied_2"] = (2, [[1, 2], [-1, -2]], [])
+    return out
+
+
+CASES = _cases()
+
+
+def _reference(tmp_path, name):
+    nv, cl, opts = CASES[name]
+    cnf = str(tmp_path / (name + ".cnf"))
+    with open(cnf, "w") as f:
+        f.write(f"p cnf {nv} {len(cl)}\n")
+        for c in cl:
+            f.write(" ".join(map(str, c)) + " 0\n")
+    fin, fout = str(tmp_path / (name + ".in")), str(tmp_path / (name + ".out"))
+    subprocess.run([REF_BIN, cnf, "-quiet", f"--sgin={fin}", f"--sgout={fout}", *opts], capture_output=True, timeout=120)
+    return B.read(fin), B.read(fout)
+
+
+def _check(s, tmp_path, name):
+    bi, bo = _reference(tmp_path, name)
+    try:
+        out, rep = s.simplify(bi)
+    except sigma.Unsat:
+        out, rep = B.Boundary(status=1), {}
+    assert parity.diff(out, bo) == []
+    if name == "ties_gt24":
+        assert rep["sort_ties_gt24"] > 0          # the std::sort branch with equal keys really ran
+    if name.startswith("emptied"):
+        assert out.refs.size == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_edge_case_cpu_standin(emul_lib, tmp_path, name):
+    s = sigma.Sigma(0, emul_lib)
+    _check(s, tmp_path, name)
+    s.close()
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_edge_case_gpu(gpu_sigma, tmp_path, name):
+    _check(gpu_sigma, tmp_path, name)
+
+
+def _abi_errors(lib_path):
+    s = sigma.Sigma(0, lib_path)
+    lib = s.lib
+    # execute / download before upload
+    assert lib.sigma_execute(s.ctx) == sigma.SIGMA_E_ARG
+    f = sigma.SigmaFormula()
+    assert lib.sigma_download(s.ctx, C.byref(f)) == sigma.SIGMA_E_ARG
+    assert lib.sigma_upload(s.ctx, None, None) == sigma.SIGMA_E_ARG
+    # null arrays
+    assert lib.sigma_upload(s.ctx, None, C.byref(f)) == sigma.SIGMA_E_ARG
+    # output buffers too small: required sizes come back, the result stays downloadable
+    bi = B.read(os.path.join(GOLDEN, "fuzz_ok_a.in"))
+    s.upload(bi)
+    s.execute()
+    small = sigma.SigmaFormula()
+    assert lib.sigma_download(s.ctx, C.byref(small)) == sigma.SIGMA_E_NOSPACE
+    assert small.n_buckets > 0 and small.n_clauses > 0
+    out = s.download()
+    bo = B.read(os.path.join(GOLDEN, "fuzz_ok_a.out"))
+    assert parity.diff(out, bo) == []
+    assert lib.sigma_strerror(sigma.SIGMA_E_NOSPACE).decode() != ""
+    # collect_freq = 0 would divide by zero in the reference (solve.hpp:628): rejected
+    with pytest.raises(sigma.SigmaError) as e:
+        s.simplify(bi, dict(bi.opts, collect_freq=0))
+    assert e.value.code == sigma.SIGMA_E_ARG
+    s.close()
+
+
+def test_abi_error_paths_cpu_standin(emul_lib):
+    _abi_errors(emul_lib)
+
+
+@pytest.mark.gpu
+def test_abi_error_paths_gpu(cuda_lib):
+    _abi_errors(cuda_lib)
+
+
+def test_no_device_fails_loudly(cuda_lib):
+    """In the GPU-less container the CUDA library must refuse to create a context (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(sigma.SigmaError) as e:
+        sigma.Sigma(0, cuda_lib)
+    assert e.value.code == sigma.SIGMA_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_header_symbols_are_exported(cuda_lib):
+    """Every entry point include/sigma_b200.h declares is exported by libsigma_b200.so."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "sigma_b200.h")).read()
+    names = set(re.findall(r"\b(sigma_[a-z_]+)\s*\(", hdr))
+    lib = C.CDLL(cuda_lib)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(sigma.EXPORTS) <= names
+
+
+def test_ctypes_mirror_matches_the_header(tmp_path):
+    """sizeof of the three ABI structs as gcc sees them == the ctypes mirrors in seqfrost_b200/sigma.py."""
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "sigma_b200.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(sigma_opts), '
+                   'sizeof(sigma_formula), sizeof(sigma_report));return 0;}\n')
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(GOLDEN), "..", "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(sigma.SigmaOpts), C.sizeof(sigma.SigmaFormula), C.sizeof(sigma.SigmaReport)]
