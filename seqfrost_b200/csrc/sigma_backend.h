@@ -23,6 +23,8 @@ enum SgItemKind {
     SGK_SUB,            /* n = elected                                                             */
     SGK_VE_COUNT,       /* n = elected                                                             */
     SGK_VE_EMIT,        /* n = elected                                                             */
+    SGK_BCE_COUNT,      /* n = elected                                                             */
+    SGK_BCE_EMIT,       /* n = elected                                                             */
     SGK_ERE_CHUNKS,     /* n = elected   : 256-pair work items per variable                        */
     SGK_ERE_PROPOSE,    /* n = work items: one warp each                                           */
     SGK_ERE_DIRTY,      /* n = elected                                                             */

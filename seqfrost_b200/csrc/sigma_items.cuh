@@ -1946,4 +1946,64 @@ SG_HDN inline void sg_ve_emit_item(const SgView &v, uint32_t eidx)
     sg_atomic_sub(&v.sc->unassigned, 1u);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* BCE: blocked clause elimination (blocked.cpp:23-58), after VE, on the elected variables that  */
+/* were not eliminated.  Two passes like VE: mark + size the model records, scan, then write.    */
+/* ------------------------------------------------------------------------------------------ */
+SG_HD bool sg_is_tautology(uint32_t x, const uint32_t *d1, int n1, const uint32_t *d2, int n2)
+{   /* simplify.hpp:159-179 */
+    int i = 0, j = 0;
+    while (i < n1 && j < n2) {
+        const uint32_t l1 = d1[i], l2 = d2[j];
+        const uint32_t v1 = SG_ABS(l1), v2 = SG_ABS(l2);
+        if (v1 == x) i++;
+        else if (v2 == x) j++;
+        else if ((l1 ^ l2) == 1u) return true;
+        else if (v1 < v2) i++;
+        else if (v2 < v1) j++;
+        else { i++; j++; }
+    }
+    return false;
+}
+SG_HDN inline void sg_bce_count_item(const SgView &v, uint32_t eidx)
+{
+    const uint32_t var = v.elected[eidx];
+    uint32_t words = 0;
+    if (!v.state[var]) {                                   /* VE zeroes the slot of an eliminated variable (bounded.cpp:178-181) */
+        const uint32_t p = 2 * var, n = p | 1u;
+        const int np = (int)v.ot_len[p], nn = (int)v.ot_len[n];
+        if (np <= v.o.bce_max_occurs && nn <= v.o.bce_max_occurs) {
+            const uint32_t *dp = sg_list(v, p), *dn = sg_list(v, n);
+            for (int i = 0; i < nn; ++i) {
+                const sg_u4 hn = v.hdr[dn[i]];
+                if (hn.z & SG_ST_MASK) continue;
+                bool all = true;
+                for (int j = 0; j < np && all; ++j) {
+                    const sg_u4 hp = v.hdr[dp[j]];
+                    if (hp.z & SG_ST_MASK) continue;
+                    if (!sg_is_tautology(var, v.lits + hn.x, (int)hn.y, v.lits + hp.x, (int)hp.y)) all = false;
+                }
+                if (all) { v.ere_touched[dn[i]] = 1; words += hn.y + 1; }
+            }
+        }
+    }
+    v.ve_nmodel[eidx] = words;
+}
+SG_HDN inline void sg_bce_emit_item(const SgView &v, uint32_t eidx)
+{
+    if (!v.ve_nmodel[eidx]) return;
+    const uint32_t var = v.elected[eidx];
+    const uint32_t n = 2 * var + 1;
+    const int nn = (int)v.ot_len[n];
+    const uint32_t *dn = sg_list(v, n);
+    unsigned long long mpos = v.model_base + v.ve_mod_off[eidx];
+    for (int i = 0; i < nn; ++i) {
+        const uint32_t c = dn[i];
+        if (!v.ere_touched[c]) continue;
+        sg_save_clause(v, c, n, mpos);                     /* model.saveClause(neg, neg.size(), n) */
+        sg_mark_deleted(v, c);
+        v.ere_touched[c] = 0;
+    }
+}
+
 #endif /* SIGMA_ITEMS_CUH */

@@ -366,6 +366,8 @@ template <int KIND> __global__ void k_items(SgView v, uint32_t n)
     else if (KIND == SGK_SUB) sg_sub_item(v, i);
     else if (KIND == SGK_VE_COUNT) sg_ve_count_item(v, i);
     else if (KIND == SGK_VE_EMIT) sg_ve_emit_item(v, i);
+    else if (KIND == SGK_BCE_COUNT) sg_bce_count_item(v, i);
+    else if (KIND == SGK_BCE_EMIT) sg_bce_emit_item(v, i);
     else if (KIND == SGK_ERE_CHUNKS) sg_ere_chunks_item(v, i);
     else if (KIND == SGK_ERE_PROPOSE) sg_ere_propose_item(v, i);
     else if (KIND == SGK_ERE_DIRTY) sg_ere_dirty_item(v, i);
@@ -889,6 +891,8 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_EMIT: LAUNCH(k_items<SGK_VE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_BCE_COUNT: LAUNCH(k_items<SGK_BCE_COUNT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_BCE_EMIT: LAUNCH(k_items<SGK_BCE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
     case SGK_ERE_CHUNKS: LAUNCH(k_items<SGK_ERE_CHUNKS>, blocks_for(n), TPB, s, v, n); break;
     case SGK_ERE_PROPOSE: LAUNCH(k_items<SGK_ERE_PROPOSE>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_ERE_DIRTY: LAUNCH(k_items<SGK_ERE_DIRTY>, blocks_for(n, 128), 128, s, v, n); break;

@@ -462,6 +462,24 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         int rc = apply_units(c, v);
         if (rc != SIGMA_OK) return rc;
     }
+    if (c->opts.bce_en) {                                  /* blocked.cpp:25 */
+        Stage st(c, SIGMA_T_VE);
+        NOMEM(c->ere_touched.ensure((size_t)c->n_cls + 16));
+        be_memset(c->stream, c->ere_touched.p, 0, c->n_cls);
+        v = make_view(c);
+        v.n_elected = E;
+        be_items(c->stream, SGK_BCE_COUNT, v, E);
+        be_scan_u32(c->stream, c->ve_nmodel.p, c->ve_mod_off.p, E, c->totals.p, c->scantmp.p);
+        CK(pull_totals(c, 1));
+        const uint32_t add_model = c->h_totals[0];
+        if (add_model) {
+            NOMEM(c->model.ensure((size_t)c->model_words + add_model, c->stream, (size_t)c->model_words));
+            v = make_view(c);
+            v.n_elected = E;
+            be_items(c->stream, SGK_BCE_EMIT, v, E);
+            c->model_words += add_model;
+        }
+    }
     return SIGMA_OK;
 }
 
@@ -588,8 +606,6 @@ bool stop_here(sigma_ctx *c, int phase, int stage) { return c->stop_phase == pha
 int run_phases(sigma_ctx *c)
 {
     const sigma_opts &o = c->opts;
-    if (o.bce_en || o.all_en)
-        return fail(c, SIGMA_E_UNSUPPORTED, "BCE is not built yet: run without -blocked/-all");
     if (o.proof_en) return fail(c, SIGMA_E_UNSUPPORTED, "DRAT proof emission from the device pass is not built");
     if (o.collect_freq <= 0) return fail(c, SIGMA_E_ARG, "collect_freq must be positive");
     CK(stage_ingest(c));

@@ -17,6 +17,8 @@ GOLDEN_OPTS = {
     "gates_bvebound": ["-bvebound"],
     "gates_phases2": ["--phases=2"],
     "gates_nofun_cm4": ["-no-function", "--boundedclausemax=4"],
+    "ere_extend2": ["--redundancyextend=2"],
+    "bce_gates": ["-blocked"], "bce_ksat3": ["-blocked"], "all_gates": ["-all"],
 }
 
 

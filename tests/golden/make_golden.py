@@ -45,6 +45,10 @@ CASES = [
     ("ere_xorphp", "xor_php_mix", dict(nclauses=6000, seed=4), ["+ere"]),
     ("ere_extend2", "gate_circuit", dict(nvars=2500, seed=32), ["+ere", "--redundancyextend=2"]),
     ("ere_fuzz", "fuzz_mix", dict(seed=5), ["+ere"]),
+    # BCE (-blocked) and -all (BVE + SUB + BCE + ERE forced on, options.cpp:343-345)
+    ("bce_gates", "gate_circuit", dict(nvars=2500, seed=41), ["+ere", "-blocked"]),
+    ("bce_ksat3", "random_ksat", dict(nvars=1500, nclauses=5400, k=3, seed=4), ["-blocked"]),
+    ("all_gates", "gate_circuit", dict(nvars=2500, seed=42), ["+ere", "-all"]),
     # LATER calls: the reference's own first simplify() + 3000 conflicts of its CDCL loop run first
     # (ref_harness --presolve-conflicts), so the store holds learnt clauses and stats.simplify.calls == 2
     ("later_ksat3", "random_ksat", dict(nvars=2000, nclauses=7800, k=3, seed=6), ["--presolve-conflicts=3000"]),
