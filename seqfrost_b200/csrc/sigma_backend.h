@@ -110,6 +110,9 @@ void be_rank(void *s, const SgView &v);                                         
 /* worklist of the still-undecided candidates with rank in [r0, r1): fills wl, sc->wl_count[0] (must be 0) */
 void be_elect_batch(void *s, const SgView &v, uint32_t r0, uint32_t r1, uint32_t *wl);
 void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *wl_out, int parity);
+/* every batch and round of one election in a single launch; returns non-zero when unavailable (the caller then
+ * drives be_elect_batch / be_elect_round itself).  sc->wl_count[0] receives the number of rounds. */
+int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow);
 void be_acting_flags(void *s, const SgView &v, uint32_t *flags_acting, uint32_t *flags_elected);   /* per rank position */
 void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe);
 /* generic item / serial launches */

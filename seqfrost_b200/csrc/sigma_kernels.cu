@@ -6,6 +6,7 @@
  * thread with the bodies of sigma_items.cuh.  Everything is launched on one stream per context.
  */
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -321,6 +322,73 @@ __global__ void k_elect_round(SgView v, const uint32_t *__restrict__ wl_in, uint
         base = __shfl_sync(0xffffffffu, base, 0);
         if (lane < held) wl_out[base + lane] = s_buf[wib][lane];
     }
+}
+
+/* The whole election in ONE cooperative launch: the rank batches and their pull rounds run inside the kernel,
+ * separated by grid-wide barriers (a few microseconds) instead of kernel launches and host round trips, which
+ * makes small batch growth factors - fewer wasted scans - and deep dependency chains (hundreds of rounds on
+ * XOR/pigeonhole instances) cheap.  Same per-candidate body as k_elect_round. */
+__global__ void __launch_bounds__(128) k_elect_persistent(SgView v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_buf[4][32];
+    const uint32_t V = v.nvars;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    const uint32_t gwarp = gtid >> 5, nwarps = gsize >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    volatile uint32_t *cnt = v.sc->ere_pending;            /* three rotating queue counters (scratch words of SgScalars) */
+    uint32_t r0 = 0, bsize = b0, rounds = 0;
+    while (r0 < V) {
+        const uint32_t r1 = (V - r0 <= bsize) ? V : r0 + bsize;
+        if (gtid == 0) { cnt[0] = 0; cnt[1] = 0; cnt[2] = 0; }
+        grid.sync();
+        for (uint32_t r = r0 + gtid; r < r1; r += gsize) {
+            const uint32_t var = v.order[r];
+            if (SG_ER_STAT(sg_er_load(v, var)) == SG_E_UNDECIDED) wl0[atomicAdd((uint32_t *)&cnt[0], 1u)] = var;
+        }
+        grid.sync();
+        uint32_t k = 0;                                    /* queue k%3 is read, (k+1)%3 written, (k+2)%3 cleared */
+        uint32_t *bufs[2] = { wl0, wl1 };
+        while (true) {
+            const uint32_t n = cnt[k % 3];
+            if (n == 0) break;
+            const uint32_t *wl_in = bufs[k & 1];
+            uint32_t *wl_out = bufs[(k + 1) & 1];
+            volatile uint32_t *out_cnt = &cnt[(k + 1) % 3];
+            if (gtid == 0) cnt[(k + 2) % 3] = 0;
+            uint32_t held = 0;
+            for (uint32_t i = gwarp; i < n; i += nwarps) {
+                __syncwarp();
+                const uint32_t cand = __ldcg(&wl_in[i]);
+                const bool stay = sg_elect_round_item(v, cand);
+                if (stay) {
+                    if (lane == 0) s_buf[wib][held] = cand;
+                    held++;
+                    if (held == 32) {
+                        __syncwarp();
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd((uint32_t *)out_cnt, 32u);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        wl_out[base + lane] = s_buf[wib][lane];
+                        held = 0;
+                    }
+                }
+            }
+            __syncwarp();
+            if (held) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd((uint32_t *)out_cnt, held);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lane < held) wl_out[base + lane] = s_buf[wib][lane];
+            }
+            grid.sync();
+            k++; rounds++;
+        }
+        if (*(volatile uint32_t *)&v.sc->brk_rank < r1) break;      /* the sequential loop ended inside this batch */
+        r0 = r1;
+        if (bsize < (1u << 28)) bsize *= grow;
+    }
+    if (gtid == 0) v.sc->wl_count[0] = rounds;
 }
 
 __global__ void k_acting_flags(SgView v, uint32_t *__restrict__ fa, uint32_t *__restrict__ fe)
@@ -872,6 +940,25 @@ void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *w
     if (grid > 148u * 16u) grid = 148u * 16u;
     if (!grid) grid = 1;
     LAUNCH(k_elect_round, grid, 128, s, v, wl_in, wl_out, parity);
+}
+int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow)
+{
+    static int blocks_per_sm = -1, sms = 0;
+    if (blocks_per_sm < 0) {
+        int dev = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_elect_persistent, 128, 0) != cudaSuccess) blocks_per_sm = 0;
+        (void)cudaGetLastError();
+    }
+    if (blocks_per_sm <= 0 || !v.nvars) return 1;
+    SgView vv = v;
+    void *args[] = { (void *)&vv, (void *)&wl0, (void *)&wl1, (void *)&b0, (void *)&grow };
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_elect_persistent, dim3((unsigned)(blocks_per_sm * sms)), dim3(128), args, 0, ST(s));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); blocks_per_sm = 0; return 1; }
+    g_launches++;
+    return 0;
 }
 void be_acting_flags(void *s, const SgView &v, uint32_t *fa, uint32_t *fe) { if (v.nvars) LAUNCH(k_acting_flags, blocks_for(v.nvars), TPB, s, v, fa, fe); }
 void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe)

@@ -342,8 +342,21 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
             if (env_grow < 2) env_grow = 2;
             if (env_rps < 1) env_rps = 1;
         }
+        static long env_pers = -1, env_pgrow = -1;
+        if (env_pers < 0) {
+            const char *e;
+            env_pers = (e = getenv("SIGMA_ELECT_PERSISTENT")) ? atol(e) : 1;
+            env_pgrow = (e = getenv("SIGMA_ELECT_PGROW")) ? atol(e) : 2;
+            if (env_pgrow < 2) env_pgrow = 2;
+        }
+        bool done = false;
+        if (env_pers && be_elect_all(c->stream, v, c->wl0.p, c->wl1.p, (uint32_t)(env_b0 < 16384 ? 16384 : env_b0), (uint32_t)env_pgrow) == 0) {
+            CK(pull_scalars(c));
+            rounds = c->hsc.wl_count[0];
+            done = true;
+        }
         uint32_t r0 = 0, bsize = (uint32_t)env_b0;
-        while (r0 < V) {
+        while (!done && r0 < V) {
             const uint32_t r1 = (V - r0 <= bsize) ? V : r0 + bsize;
             be_memset(c->stream, &c->sc.p->wl_count[0], 0, 2 * sizeof(uint32_t));
             be_elect_batch(c->stream, v, r0, r1, c->wl0.p);
