@@ -179,7 +179,8 @@ class Sigma:
     def make_formula(b: B.Boundary):
         f = SigmaFormula()
         f.nvars, f.n_clauses = b.nvars, int(b.refs.size)
-        f.n_buckets, f.n_literals = int(b.arena.size), int(b.arena.size) - 3 * int(b.refs.size)
+        f.n_buckets = int(b.arena.size)
+        f.n_literals = int(b.n_literals) if b.n_literals else int(b.arena.size) - 3 * int(b.refs.size)
         f.arena, f.refs, f.state, f.value = _ptr(b.arena), _ptr(b.refs), _ptr(b.state), _ptr(b.value)
         f.trail, f.trail_size, f.propagated = _ptr(b.trail), int(b.trail.size), b.propagated
         f.vorg, f.ifrozen = _ptr(b.vorg), None

@@ -155,3 +155,36 @@ def test_ctypes_mirror_matches_the_header(tmp_path):
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [C.sizeof(sigma.SigmaOpts), C.sizeof(sigma.SigmaFormula), C.sizeof(sigma.SigmaReport)]
+
+
+def _gapped(b: B.Boundary, pad=2):
+    """Same formula in an arena with `pad` unused buckets after every clause (the general ingest path:
+    refs are then not ref[i] = ref[i-1] + 3 + size)."""
+    g = B.Boundary(**{k: getattr(b, k) for k in ("status", "nvars", "n_clauses", "n_literals", "unassigned", "max_frozen", "max_melted",
+                                                  "propagated", "simplify_calls", "state", "value", "trail", "vorg", "model", "opts")})
+    sizes = b.arena[b.refs.astype(np.int64) + 2].astype(np.int64)
+    newrefs = np.concatenate([[0], np.cumsum(sizes + 3 + pad)[:-1]]).astype(np.uint64)
+    arena = np.full(int((sizes + 3 + pad).sum()), 0xDEADBEEF, dtype=np.uint32)
+    for r_old, r_new, sz in zip(b.refs.astype(np.int64).tolist(), newrefs.astype(np.int64).tolist(), sizes.tolist()):
+        arena[r_new:r_new + 3 + sz] = b.arena[r_old:r_old + 3 + sz]
+    g.arena, g.refs = arena, newrefs
+    return g
+
+
+def _gapped_check(lib_path):
+    for name in ("fuzz_ok_a", "gates_w200"):
+        bi, bo = B.read(os.path.join(GOLDEN, name + ".in")), B.read(os.path.join(GOLDEN, name + ".out"))
+        s = sigma.Sigma(0, lib_path)
+        f = sigma.Sigma.make_formula(_gapped(bi))
+        out, _ = s.simplify(_gapped(bi))
+        assert parity.diff(out, bo) == []
+        s.close()
+
+
+def test_arena_with_gaps_cpu_standin(emul_lib):
+    _gapped_check(emul_lib)
+
+
+@pytest.mark.gpu
+def test_arena_with_gaps_gpu(cuda_lib):
+    _gapped_check(cuda_lib)
