@@ -117,6 +117,7 @@ enum { SIGMA_T_H2D = 0,      /* sigma_upload: host -> device copies             
        SIGMA_T_TOTAL_DEVICE, /* first kernel of sigma_execute to its last                              */
        SIGMA_T_ERE,          /* ERE: propose + ordered replay              (redundancy.cpp:26-123)    */
        SIGMA_T_OT_UPDATE,    /* createOT of a later phase as an update of the previous table          */
+       SIGMA_T_NBH,          /* sortOT + SUB + BVE decision fused per elected variable (one warp each) */
        SIGMA_T_N = 20 };
 
 typedef struct sigma_report {

@@ -23,6 +23,7 @@ enum SgItemKind {
     SGK_SUB,            /* n = elected                                                             */
     SGK_VE_COUNT,       /* n = elected                                                             */
     SGK_VE_EMIT,        /* n = elected                                                             */
+    SGK_NBH,            /* n = elected   : sortOT + SUB + BVE decision of one variable by one warp */
     SGK_BCE_COUNT,      /* n = elected                                                             */
     SGK_BCE_EMIT,       /* n = elected                                                             */
     SGK_ERE_CHUNKS,     /* n = elected   : 256-pair work items per variable                        */

@@ -1877,7 +1877,7 @@ SG_HDN inline void sg_ve_emit_item(const SgView &v, uint32_t eidx)
             if ((w0 & SG_LEARNT) || (w0 & SG_MOLTEN) || sg_clause_has(v, c, def)) sg_mark_deleted(v, c);
             else if (!(w0 & SG_ST_MASK)) {
                 const uint32_t unit = sg_substitute_clause(v, c, n, def_f);
-                if (unit) sg_push_unit(v, eidx, seq, unit);
+                if (unit) sg_push_unit(v, eidx | 0x80000000u, seq, unit);
             }
         }
         for (int i = 0; i < np; ++i) {
@@ -1886,7 +1886,7 @@ SG_HDN inline void sg_ve_emit_item(const SgView &v, uint32_t eidx)
             if ((w0 & SG_LEARNT) || (w0 & SG_MOLTEN) || sg_clause_has(v, c, def_f)) sg_mark_deleted(v, c);
             else if (!(w0 & SG_ST_MASK)) {
                 const uint32_t unit = sg_substitute_clause(v, c, p, def);
-                if (unit) sg_push_unit(v, eidx, seq, unit);
+                if (unit) sg_push_unit(v, eidx | 0x80000000u, seq, unit);
             }
         }
     } else {
@@ -1923,7 +1923,7 @@ SG_HDN inline void sg_ve_emit_item(const SgView &v, uint32_t eidx)
                         (void)sig; tmp[0] = 0;
                         for (int k = 0; k < (int)hi.y; ++k) if (SG_ABS(a1[k]) != var) tmp[0] = a1[k];
                         for (int k = 0; k < (int)hj.y; ++k) if (SG_ABS(a2[k]) != var) tmp[0] = a2[k];
-                        if (tmp[0]) sg_push_unit(v, eidx, seq, tmp[0]);
+                        if (tmp[0]) sg_push_unit(v, eidx | 0x80000000u, seq, tmp[0]);
                     }
                 }
             }
@@ -1944,6 +1944,27 @@ SG_HDN inline void sg_ve_emit_item(const SgView &v, uint32_t eidx)
     /* markEliminated (solve.hpp:491-498) */
     v.state[var] = (uint8_t)SG_MELTED_M;
     sg_atomic_sub(&v.sc->unassigned, 1u);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* one elected variable, start to finish of the per-variable stages: sortOT of its two lists,   */
+/* SUB, then the BVE decision, by ONE warp, so that the clause neighbourhood is fetched from HBM */
+/* once and stays in L1 for all three (the reference runs the three stages as separate loops    */
+/* over the elected variables; their neighbourhoods are disjoint, so the order is immaterial).  */
+/* Units found by SUB keep their place before those found by BVE (bit 31 of the unit key).      */
+/* ------------------------------------------------------------------------------------------ */
+SG_HDN inline void sg_neighbourhood_item(const SgView &v, uint32_t eidx)
+{
+    const SgLane L = sg_lane_ctx();
+    const uint32_t var = v.elected[eidx];
+    if (v.nbh_sort && (L.lane < 2 || L.width == 1)) {
+        sg_sortot_item(v, 2 * var + (L.width == 1 ? 0u : L.lane));
+        if (L.width == 1) sg_sortot_item(v, 2 * var + 1);
+    }
+    sg_wsync();
+    if (v.o.sub_en || v.o.ve_plus_en) sg_sub_item(v, eidx);
+    sg_wsync();
+    sg_ve_count_item(v, eidx);
 }
 
 /* ------------------------------------------------------------------------------------------ */

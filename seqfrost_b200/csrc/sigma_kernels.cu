@@ -417,7 +417,7 @@ __global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, cons
 template <int KIND> __global__ void k_items(SgView v, uint32_t n)
 {
     /* SUB and the BVE decision run one warp per elected variable, everything else one thread */
-    const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
+    const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_NBH || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
                             KIND == SGK_ERE_SAFE || KIND == SGK_ERE_APPLY);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = warp_item ? (t >> 5) : t;
@@ -434,6 +434,7 @@ template <int KIND> __global__ void k_items(SgView v, uint32_t n)
     else if (KIND == SGK_SUB) sg_sub_item(v, i);
     else if (KIND == SGK_VE_COUNT) sg_ve_count_item(v, i);
     else if (KIND == SGK_VE_EMIT) sg_ve_emit_item(v, i);
+    else if (KIND == SGK_NBH) sg_neighbourhood_item(v, i);
     else if (KIND == SGK_BCE_COUNT) sg_bce_count_item(v, i);
     else if (KIND == SGK_BCE_EMIT) sg_bce_emit_item(v, i);
     else if (KIND == SGK_ERE_CHUNKS) sg_ere_chunks_item(v, i);
@@ -978,6 +979,7 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_EMIT: LAUNCH(k_items<SGK_VE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_NBH: LAUNCH(k_items<SGK_NBH>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_BCE_COUNT: LAUNCH(k_items<SGK_BCE_COUNT>, blocks_for(n, 64), 64, s, v, n); break;
     case SGK_BCE_EMIT: LAUNCH(k_items<SGK_BCE_EMIT>, blocks_for(n, 64), 64, s, v, n); break;
     case SGK_ERE_CHUNKS: LAUNCH(k_items<SGK_ERE_CHUNKS>, blocks_for(n), TPB, s, v, n); break;

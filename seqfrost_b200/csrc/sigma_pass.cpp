@@ -69,6 +69,7 @@ struct sigma_ctx {
     uint32_t last_elected = 0;       /* size of `elected` after the latest election (hsc.n_elected does not survive a pull) */
     uint64_t ot_end = 0;             /* words of ot_data in use (the updated table is not packed) */
     bool ot_valid = false, ot_incremental = true, ot_verify = false;
+    int nbh_fused = 0;               /* 0: separate sortOT / SUB / BVE kernels; 1: fused per variable; 2: fused SUB + BVE only */
     uint32_t ot_first_new = 0;
     DBuf<uint32_t> totals;          /* device slots for scan totals */
     DBuf<SgScalars> sc;
@@ -443,15 +444,25 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     v.n_elected = E;
     v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
     v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
-    if (c->opts.sub_en || c->opts.ve_plus_en) {            /* subsume.cpp:25 */
-        Stage st(c, SIGMA_T_SUB);
-        be_items(c->stream, SGK_SUB, v, E);
-        int rc = apply_units(c, v);
-        if (rc != SIGMA_OK) return rc;
+    const bool fused = c->nbh_fused && c->opts.ve_en;
+    if (fused) {
+        /* sortOT + SUB + BVE decision per variable in one kernel (sigma_items.cuh: sg_neighbourhood_item) */
+        if (c->nbh_fused == 2) CK(stage_sortot(c));
+        Stage st(c, SIGMA_T_NBH);
+        v.nbh_sort = c->nbh_fused == 1;
+        be_items(c->stream, SGK_NBH, v, E);
+    } else {
+        CK(stage_sortot(c));
+        if (c->opts.sub_en || c->opts.ve_plus_en) {        /* subsume.cpp:25 */
+            Stage st(c, SIGMA_T_SUB);
+            be_items(c->stream, SGK_SUB, v, E);
+            int rc = apply_units(c, v);
+            if (rc != SIGMA_OK) return rc;
+        }
     }
     if (c->opts.ve_en) {                                   /* bounded.cpp:29 */
         Stage st(c, SIGMA_T_VE);
-        be_items(c->stream, SGK_VE_COUNT, v, E);
+        if (!fused) be_items(c->stream, SGK_VE_COUNT, v, E);
         be_scan_u32(c->stream, c->ve_ncls.p, c->ve_cls_off.p, E, c->totals.p + 0, c->scantmp.p);
         be_scan_u32(c->stream, c->ve_nlits.p, c->ve_lit_off.p, E, c->totals.p + 1, c->scantmp.p);
         be_scan_u32(c->stream, c->ve_nmodel.p, c->ve_mod_off.p, E, c->totals.p + 2, c->scantmp.p);
@@ -650,8 +661,8 @@ int run_phases(sigma_ctx *c)
         CK(stage_lcve(c, phase, multiplier, !had_units, &enough));
         if (stop_here(c, phase, SIGMA_T_ELECT)) return SIGMA_OK;
         if (!enough) break;
-        CK(stage_sortot(c));
         if (phase == o.phases || (diff <= o.phase_lits_min && phase > 2)) {
+            CK(stage_sortot(c));                            /* simplify.cpp:187 */
             CK(stage_ere(c));                               /* simplify.cpp:189 */
             break;
         }
@@ -815,6 +826,7 @@ int sigma_execute(sigma_ctx *c)
     c->ot_valid = false;
     { const char *e = getenv("SIGMA_OT_INCREMENTAL"); c->ot_incremental = !(e && e[0] == '0'); }
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
+    { const char *e = getenv("SIGMA_NBH_FUSED"); c->nbh_fused = e ? atoi(e) : 0; }
     c->launches0 = be_launch_count();
     const uint32_t V = c->nvars, nlit = c->nlit;
     /* restore the pristine solver state */

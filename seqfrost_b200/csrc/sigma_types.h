@@ -134,6 +134,7 @@ typedef struct SgView {
     uint32_t n_elected;
     uint32_t ubuf_cap;
     uint32_t pmax, nmax;     /* mu << multiplier (lcve.cpp:59-60) */
+    uint32_t nbh_sort;       /* the fused per-variable kernel also sorts the two lists (sortOT) */
     uint64_t model_base;     /* model words present before this VE stage */
     SgOpts   o;
 } SgView;

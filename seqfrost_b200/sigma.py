@@ -23,7 +23,7 @@ DEFAULT_LIB = os.path.join(_HERE, "csrc", "libsigma_b200.so")
 
 SIGMA_OK, SIGMA_UNSAT, SIGMA_INTERRUPTED, SIGMA_E_NOMEM, SIGMA_E_CUDA, SIGMA_E_NOSPACE, SIGMA_E_ARG, SIGMA_E_UNSUPPORTED = range(8)
 STAGES = ["h2d", "ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "prop", "vo", "elect", "sot", "sub", "ve",
-          "count", "gc", "export", "d2h", "total_device", "ere", "ot_update"]
+          "count", "gc", "export", "d2h", "total_device", "ere", "ot_update", "nbh"]
 T_N = 20
 
 EXPORTS = [

@@ -185,6 +185,7 @@ void be_items(void *, int kind, const SgView &v, uint32_t n)
         case SGK_SUB: sg_sub_item(v, i); break;
         case SGK_VE_COUNT: sg_ve_count_item(v, i); break;
         case SGK_VE_EMIT: sg_ve_emit_item(v, i); break;
+        case SGK_NBH: sg_neighbourhood_item(v, i); break;
         case SGK_BCE_COUNT: sg_bce_count_item(v, i); break;
         case SGK_BCE_EMIT: sg_bce_emit_item(v, i); break;
         case SGK_ERE_CHUNKS: sg_ere_chunks_item(v, i); break;
