@@ -59,7 +59,9 @@ void *be_event_create(void);
 void  be_event_destroy(void *ev);
 void  be_event_record(void *stream, void *ev);
 float be_event_ms(void *a, void *b);
-uint64_t be_launch_count(void);                /* kernels launched so far by this library */
+uint64_t be_launch_count(void);
+/* small control blocks between device memory and mapped pinned host memory, without the copy engine (bytes % 4 == 0) */
+void  be_copy_words(void *stream, void *dst, const void *src, size_t bytes);                /* kernels launched so far by this library */
 
 /* ---- streaming kernels ------------------------------------------------------------------------ */
 /* AoS SCNF arena -> device store (reference hand-off layout, sclause.hpp:45-49) */

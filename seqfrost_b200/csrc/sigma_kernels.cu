@@ -540,6 +540,13 @@ __global__ void k_count_live(SgView v)
 }
 
 __global__ void k_zero_u32(uint32_t *p) { *p = 0; }
+/* control words between device memory and MAPPED pinned host memory, by a kernel instead of the copy engine: the
+ * DMA queues then carry only the bulk formula transfers (a second context's 400 MB copy would otherwise sit in
+ * front of every little read-back of this one) */
+__global__ void k_copy_words(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint32_t n)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
 __global__ void k_count_melted(SgView v, uint32_t *out)
 {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x + 1;
@@ -837,7 +844,7 @@ void be_free(void *p) { if (p) cudaFree(p); }
 void *be_host_alloc(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
     return p;
 }
 void be_host_free(void *p) { if (p) cudaFreeHost(p); }
@@ -857,6 +864,11 @@ void be_event_destroy(void *e) { cudaEventDestroy((cudaEvent_t)e); }
 void be_event_record(void *s, void *e) { cudaEventRecord((cudaEvent_t)e, ST(s)); }
 float be_event_ms(void *a, void *b) { float ms = 0; if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) { (void)cudaGetLastError(); ms = 0; } return ms; }
 uint64_t be_launch_count(void) { return g_launches; }
+void be_copy_words(void *s, void *dst, const void *src, size_t bytes)
+{
+    k_copy_words<<<1, 128, 0, ST(s)>>>((uint32_t *)dst, (const uint32_t *)src, (uint32_t)(bytes / 4));
+    note_err("k_copy_words");
+}
 
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {

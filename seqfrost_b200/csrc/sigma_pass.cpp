@@ -161,7 +161,7 @@ SgView make_view(sigma_ctx *c)
 /* device scalars -> host mirror (one small D2H + sync) */
 int pull_scalars(sigma_ctx *c)
 {
-    be_d2h(c->stream, c->h_sc, c->sc.p, sizeof(SgScalars));
+    be_copy_words(c->stream, c->h_sc, c->sc.p, sizeof(SgScalars));
     if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
     c->hsc = *c->h_sc;
     return SIGMA_OK;
@@ -169,13 +169,13 @@ int pull_scalars(sigma_ctx *c)
 int push_scalars(sigma_ctx *c)
 {
     *c->h_sc = c->hsc;
-    be_h2d(c->stream, c->sc.p, c->h_sc, sizeof(SgScalars));
+    be_copy_words(c->stream, c->sc.p, c->h_sc, sizeof(SgScalars));
     if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
     return SIGMA_OK;
 }
 int pull_totals(sigma_ctx *c, uint32_t n)
 {
-    be_d2h(c->stream, c->h_totals, c->totals.p, n * sizeof(uint32_t));
+    be_copy_words(c->stream, c->h_totals, c->totals.p, n * sizeof(uint32_t));
     if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
     return SIGMA_OK;
 }
@@ -264,7 +264,7 @@ int stage_update_ot(sigma_ctx *c, uint64_t live_lits)
         if (c->ot_end + need >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "occurrence table exceeds 32-bit offsets");
         NOMEM(c->ot_data.ensure((size_t)c->ot_end + need + 16, c->stream, (size_t)c->ot_end));
         c->h_totals[13] = (uint32_t)c->ot_end;
-        be_h2d(c->stream, c->totals.p + 13, c->h_totals + 13, 4);
+        be_copy_words(c->stream, c->totals.p + 13, c->h_totals + 13, 4);
         v = make_view(c);
         be_ot_update(c->stream, v, u);
         c->rep.stage_bytes[SIGMA_T_OT_UPDATE] += 8ull * need;

@@ -53,6 +53,7 @@ void be_event_destroy(void *e) { delete (Ev *)e; }
 void be_event_record(void *, void *e) { ((Ev *)e)->t = now_ms(); }
 float be_event_ms(void *a, void *b) { return (float)(((Ev *)b)->t - ((Ev *)a)->t); }
 uint64_t be_launch_count(void) { return g_launches; }
+void be_copy_words(void *, void *d, const void *s, size_t n) { memmove(d, s, n); }
 
 void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
