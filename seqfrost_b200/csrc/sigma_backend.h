@@ -46,6 +46,7 @@ extern "C++" {
 /* ---- device lifetime / memory ---------------------------------------------------------------- */
 int   be_init(int device, void **stream_out, char *err, size_t errlen);   /* 0 = ok */
 void  be_shutdown(void *stream);
+void  be_bind(int device);                     /* make the context's device current for the calling host thread */
 void *be_malloc(size_t bytes);                 /* NULL on failure */
 void  be_free(void *p);
 void *be_host_alloc(size_t bytes);             /* pinned host memory */

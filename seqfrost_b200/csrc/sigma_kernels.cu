@@ -834,6 +834,7 @@ int be_init(int device, void **stream_out, char *err, size_t errlen)
     return 0;
 }
 void be_shutdown(void *s) { if (s) cudaStreamDestroy(ST(s)); }
+void be_bind(int device) { cudaSetDevice(device); }
 void *be_malloc(size_t bytes)
 {
     void *p = nullptr;

@@ -719,6 +719,7 @@ void sigma_destroy(sigma_ctx *c)
 {
     if (!c) return;
     if (c->stream) {
+        be_bind(c->device);
         char e[64]; be_sync(c->stream, e, sizeof e);
         c->d_arena_in.release(); c->d_refs_in.release(); c->d_state_in.release(); c->d_value_in.release();
         c->d_trail_in.release(); c->d_model_in.release(); c->d_vorg.release(); c->d_ifrozen.release();
@@ -769,6 +770,7 @@ int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
 {
     if (!c || !in) return SIGMA_E_ARG;
     if (!c->stream) return fail(c, SIGMA_E_CUDA, c->err[0] ? c->err : "no CUDA device");
+    be_bind(c->device);                                    /* callers may use one host thread per context */
     if (o) c->opts = *o;
     if (!in->arena || !in->refs || !in->state || !in->value || !in->vorg) return fail(c, SIGMA_E_ARG, "null input array");
     if (in->n_buckets >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "arena exceeds 32-bit bucket offsets");
@@ -817,6 +819,7 @@ int sigma_execute(sigma_ctx *c)
 {
     if (!c) return SIGMA_E_ARG;
     if (!c->uploaded) return fail(c, SIGMA_E_ARG, "sigma_execute before sigma_upload");
+    be_bind(c->device);
     const float h2d_ms = c->rep.stage_ms[SIGMA_T_H2D];
     const uint64_t h2d_bytes = c->rep.h2d_bytes;
     memset(&c->rep, 0, sizeof c->rep);
@@ -882,6 +885,7 @@ int sigma_download(sigma_ctx *c, sigma_formula *out)
 {
     if (!c || !out) return SIGMA_E_ARG;
     if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    be_bind(c->device);
     const uint32_t V = c->nvars, nlit = c->nlit;
     const bool small = out->arena_cap < c->out_buckets || out->refs_cap < c->out_ncls || out->trail_cap < c->hsc.n_trail ||
                        out->model_cap < c->model_words;
@@ -924,6 +928,7 @@ int sigma_run(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, sigma_
 int sigma_snapshot(sigma_ctx *c, const char *name, void *dst, uint64_t cap_bytes, uint64_t *nbytes)
 {
     if (!c || !name || !nbytes) return SIGMA_E_ARG;
+    be_bind(c->device);
     const void *src = nullptr;
     uint64_t n = 0;
     const uint32_t V = c->nvars, nlit = c->nlit;

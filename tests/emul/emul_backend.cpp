@@ -37,6 +37,7 @@ int be_init(int, void **stream_out, char *, size_t)
     return 0;
 }
 void be_shutdown(void *) {}
+void be_bind(int) {}
 void *be_malloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void be_free(void *p) { free(p); }
 void *be_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
