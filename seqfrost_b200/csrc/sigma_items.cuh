@@ -260,11 +260,18 @@ SG_HDN inline void sg_sortot_small(const SgView &v, uint32_t *d, int size)
 {
     SgKey key[24];
     uint32_t id[24];
-    for (int i = 0; i < size; ++i) {
-        id[i] = d[i];
-        const sg_u4 h = v.hdr[id[i]];
-        key[i].size = h.y; key[i].sig = h.w;
-        key[i].first = v.lits[h.x]; key[i].last = v.lits[h.x + h.y - 1];
+    for (int b = 0; b < size; b += 8) {
+        /* ids, then headers, then first/last literals of 8 entries: independent loads issued together */
+        sg_u4 h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (b + k < size) id[b + k] = d[b + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (b + k < size) h[k] = v.hdr[id[b + k]];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (b + k < size) {
+            key[b + k].size = h[k].y; key[b + k].sig = h[k].w;
+            key[b + k].first = v.lits[h[k].x]; key[b + k].last = v.lits[h[k].x + h[k].y - 1];
+        }
     }
     bool moved = false;
     if (size == 2) {
@@ -892,12 +899,12 @@ SG_HDN inline bool sg_count_pairs(const SgView &v, const SgLane &L, int mode, ui
     const int nme = (int)v.ot_len[me], noth = (int)v.ot_len[other];
     const uint32_t *dm = sg_list(v, me), *dt = sg_list(v, other);
     const long long total = (long long)nme * noth;
-    const long long chunk = (long long)L.width * 8;
+    const long long chunk = (long long)L.width * 2;       /* bound check every 64 pairs: a variable that blows up is dropped early */
     int cnt = 0, lits = 0;
     for (long long base = 0; base < total; base += chunk) {
         int c1 = 0, l1 = 0;
         bool over = false;
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 2; ++k) {
             const long long q = base + (long long)k * L.width + L.lane;
             if (q >= total) break;
             const int i = (int)(q / noth), j = (int)(q - (long long)i * noth);
@@ -1549,10 +1556,22 @@ SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t chunk)
         const int nm = (int)v.ot_len[best];
         const uint32_t *ml = sg_list(v, best);
         bool hit = false;
-        for (int m = 0; m < nm; ++m) {
-            const uint32_t c = ml[m];
-            if (c == iref || c == jref) continue;
-            if (sg_ere_hits(v, merged, len, sig, c)) { hit = true; v.ere_touched[c] = 1; }
+        for (int m0 = 0; m0 < nm; m0 += 8) {
+            /* 8 entries of the shortest list at a time: ids, then headers (independent loads), then the cheap
+             * size/signature screen; the literal comparison runs only for the survivors */
+            uint32_t cc[8];
+            sg_u4 hh[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cc[k] = m0 + k < nm ? ml[m0 + k] : iref;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hh[k] = v.hdr[cc[k]];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (cc[k] == iref || cc[k] == jref || (hh[k].z & SG_DELETED)) continue;
+                if (len <= (int)hh[k].y && sg_sig_sub(sig, hh[k].w) && sg_sub_lits(merged, len, v.lits + hh[k].x, (int)hh[k].y)) {
+                    hit = true; v.ere_touched[cc[k]] = 1;
+                }
+            }
         }
         if (hit) { uint32_t s2 = ((uint32_t)i << 16) | (uint32_t)j; sg_push_unit(v, eidx, s2, 0); any = true; }
     }

@@ -333,8 +333,8 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         /* rank-ordered batches of geometrically growing size: inside a batch, pull rounds until every
          * candidate is decided; acting candidates push FROZEN onto their undecided neighbours, so the
          * later (large) batches hold few candidates that are still undecided */
-        static long env_b0 = -1, env_grow = -1, env_rps = -1;
-        if (env_b0 < 0) {
+        long env_b0 = -1, env_grow = -1, env_rps = -1;
+        {
             const char *e;
             env_b0 = (e = getenv("SIGMA_ELECT_B0")) ? atol(e) : 4096;
             env_grow = (e = getenv("SIGMA_ELECT_GROW")) ? atol(e) : 4;
@@ -343,8 +343,8 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
             if (env_grow < 2) env_grow = 2;
             if (env_rps < 1) env_rps = 1;
         }
-        static long env_pers = -1, env_pgrow = -1;
-        if (env_pers < 0) {
+        long env_pers = -1, env_pgrow = -1;
+        {
             const char *e;
             env_pers = (e = getenv("SIGMA_ELECT_PERSISTENT")) ? atol(e) : 1;
             env_pgrow = (e = getenv("SIGMA_ELECT_PGROW")) ? atol(e) : 2;
