@@ -516,26 +516,37 @@ __global__ void k_units_gather(SgView v, uint32_t n, const uint32_t *idx, SgUnit
 __global__ void k_zero_live(SgView v) { v.sc->live_cls = 0; v.sc->live_lits = 0; }
 
 __global__ void k_count_live(SgView v)
-{
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t nc = 0, nl = 0;
-    if (c < v.n_cls) {
+{   /* persistent grid (a few blocks per SM), four independent 16-byte header loads in flight per thread,
+     * one pair of atomics per block */
+    uint32_t nc = 0;
+    unsigned long long nl = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; c + 3 * stride < v.n_cls; c += 4 * stride) {
+        const uint4 h0 = v.hdr[c], h1 = v.hdr[c + stride], h2 = v.hdr[c + 2 * stride], h3 = v.hdr[c + 3 * stride];
+        if (!(h0.z & SG_DELETED)) { nc++; nl += h0.y; }
+        if (!(h1.z & SG_DELETED)) { nc++; nl += h1.y; }
+        if (!(h2.z & SG_DELETED)) { nc++; nl += h2.y; }
+        if (!(h3.z & SG_DELETED)) { nc++; nl += h3.y; }
+    }
+    for (; c < v.n_cls; c += stride) {
         const uint4 h = v.hdr[c];
-        if (!(h.z & SG_DELETED)) { nc = 1; nl = h.y; }
+        if (!(h.z & SG_DELETED)) { nc++; nl += h.y; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         nc += __shfl_down_sync(0xffffffffu, nc, d);
         nl += __shfl_down_sync(0xffffffffu, nl, d);
     }
-    __shared__ uint32_t sc_[TPB / 32], sl_[TPB / 32];
+    __shared__ uint32_t sc_[TPB / 32];
+    __shared__ unsigned long long sl_[TPB / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { sc_[warp] = nc; sl_[warp] = nl; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t a = 0; unsigned long long b = 0;
-        for (int w = 0; w < TPB / 32; ++w) { a += sc_[w]; b += sl_[w]; }
-        if (a) { atomicAdd(&v.sc->live_cls, a); atomicAdd(&v.sc->live_lits, b); }
+        uint32_t a2 = 0; unsigned long long b2 = 0;
+        for (int w = 0; w < TPB / 32; ++w) { a2 += sc_[w]; b2 += sl_[w]; }
+        if (a2) { atomicAdd(&v.sc->live_cls, a2); atomicAdd(&v.sc->live_lits, b2); }
     }
 }
 
@@ -877,7 +888,7 @@ void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint3
 }
 void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap)
 {
-    LAUNCH(k_zero_u32, 1, 1, s, gap);
+    cudaMemsetAsync(gap, 0, sizeof(uint32_t), ST(s));
     if (n) LAUNCH(k_ingest_fused, blocks_for(n), TPB, s, arena, refs, n, hdr, lits, gap);
 }
 void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs, sg_u4 *hdr, uint32_t *lits)
@@ -1035,8 +1046,13 @@ void be_sort_units(void *s, const SgView &v, uint32_t n)
 
 void be_count_live(void *s, const SgView &v)
 {
-    LAUNCH(k_zero_live, 1, 1, s, v);
-    if (v.n_cls) LAUNCH(k_count_live, blocks_for(v.n_cls), TPB, s, v);
+    cudaMemsetAsync(&v.sc->live_cls, 0, sizeof(uint32_t), ST(s));
+    cudaMemsetAsync(&v.sc->live_lits, 0, sizeof(unsigned long long), ST(s));
+    if (v.n_cls) {
+        unsigned grid = blocks_for(v.n_cls);
+        if (grid > 148u * 8u) grid = 148u * 8u;
+        LAUNCH(k_count_live, grid, TPB, s, v);
+    }
 }
 void be_count_melted(void *s, const SgView &v, uint32_t *out)
 {
