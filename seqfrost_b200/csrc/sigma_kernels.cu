@@ -213,9 +213,15 @@ __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restr
 __global__ void k_scores(SgView v)
 {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (x > v.nvars) return;
-    v.scores[x] = v.occ[2 * x] * v.occ[2 * x + 1];
-    v.order[x - 1] = x;
+    uint32_t sc = 0;
+    if (x <= v.nvars) {
+        sc = v.occ[2 * x] * v.occ[2 * x + 1];
+        v.scores[x] = sc;
+        v.order[x - 1] = x;
+    }
+    /* largest score: the radix sort only needs the digit passes that can differ */
+    const uint32_t m = __reduce_max_sync(0xffffffffu, sc);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&v.sc->max_score, m);
 }
 
 constexpr int RS_ITEMS = 16;
@@ -691,21 +697,30 @@ __global__ void k_otu_bitmap(SgView v, uint32_t *__restrict__ bits)
 
 /* clauses that died since: their lists are dirty; clauses that are new: their literals are additions */
 __global__ void k_otu_mark(SgView v, uint32_t *__restrict__ bits, uint32_t first_new, uint32_t *__restrict__ addc, uint32_t *__restrict__ flag)
-{
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = false;
-    if (c < v.n_cls) {
-        const uint4 h = v.hdr[c];
-        live = !(h.z & SG_DELETED);
-        const uint32_t *l = v.lits + h.x;
-        if (c >= first_new) {
-            if (live) for (uint32_t k = 0; k < h.y; ++k) { atomicAdd(&addc[l[k]], 1u); flag[l[k]] = OTU_DIRTY; }
-        } else if (!live && ((bits[c >> 5] >> (c & 31)) & 1u)) {
-            for (uint32_t k = 0; k < h.y; ++k) flag[l[k]] = OTU_DIRTY;
-        }
+{   /* one warp per 128 consecutive clause ids: four independent header loads per lane, four bitmap words per warp */
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 128u;
+    uint4 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = base + k * 32u + lane;
+        h[k] = c < v.n_cls ? v.hdr[c] : make_uint4(0, 0, SG_DELETED, 0);
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, live);
-    if ((threadIdx.x & 31) == 0) bits[c >> 5] = m;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = base + k * 32u + lane;
+        const bool live = c < v.n_cls && !(h[k].z & SG_DELETED);
+        if (c < v.n_cls) {
+            const uint32_t *l = v.lits + h[k].x;
+            if (c >= first_new) {
+                if (live) for (uint32_t q = 0; q < h[k].y; ++q) { atomicAdd(&addc[l[q]], 1u); flag[l[q]] = OTU_DIRTY; }
+            } else if (!live && ((bits[c >> 5] >> (c & 31)) & 1u)) {
+                for (uint32_t q = 0; q < h[k].y; ++q) flag[l[q]] = OTU_DIRTY;
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0 && (c >> 5) <= v.n_cls / 32) bits[c >> 5] = m;
+    }
 }
 __global__ void k_otu_pairs_count(SgView v, uint32_t n, uint32_t *__restrict__ addc, uint32_t *__restrict__ flag)
 {
@@ -925,7 +940,11 @@ void be_scatter(void *s, const SgView &v, uint32_t *cursor)
         LAUNCH(k_scatter, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, cursor, v.ot_data, lo, hi);
     }
 }
-void be_scores(void *s, const SgView &v) { if (v.nvars) LAUNCH(k_scores, blocks_for(v.nvars), TPB, s, v); }
+void be_scores(void *s, const SgView &v)
+{
+    cudaMemsetAsync(&v.sc->max_score, 0, sizeof(uint32_t), ST(s));
+    if (v.nvars) LAUNCH(k_scores, blocks_for(v.nvars), TPB, s, v);
+}
 
 size_t be_sort_tmp_words(uint32_t n)
 {
@@ -1090,7 +1109,7 @@ void be_ot_update_plan(void *s, const SgView &v, const SgOtUpdate &u)
     cudaMemsetAsync(t.addc, 0, (size_t)v.nlit * 4, ST(s));
     cudaMemsetAsync(t.flag, 0, (size_t)v.nlit * 4, ST(s));
     cudaMemsetAsync(u.total, 0, 4, ST(s));
-    LAUNCH(k_otu_mark, blocks_for(((uint64_t)v.n_cls / 32 + 1) * 32), TPB, s, v, u.bits, u.first_new, t.addc, t.flag);
+    LAUNCH(k_otu_mark, blocks_for(((uint64_t)v.n_cls / 128 + 1) * 32), TPB, s, v, u.bits, u.first_new, t.addc, t.flag);
     if (u.n_add) LAUNCH(k_otu_pairs_count, blocks_for(u.n_add), TPB, s, v, u.n_add, t.addc, t.flag);
     if (u.n_elected) LAUNCH(k_otu_elected, blocks_for(u.n_elected), TPB, s, v, u.n_elected, t.flag);
     LAUNCH(k_otu_need, blocks_for(v.nlit), TPB, s, v, t.addc, u.total);

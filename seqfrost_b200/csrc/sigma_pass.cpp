@@ -319,7 +319,10 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
             be_hist(c->stream, v, c->occ.p);                 /* histCNF (histogram.cpp:84-97) */
         }
         be_scores(c->stream, v);
-        be_sort_pairs(c->stream, c->scores.p + 1, c->order.p, V, c->tmpk.p, c->tmpv.p, c->sorttmp.p, 32);
+        CK(pull_scalars(c));
+        uint32_t key_bits = 8;                             /* digit passes that can differ: up to the top bit of the largest score */
+        while (key_bits < 32 && (c->hsc.max_score >> key_bits)) key_bits += 8;
+        be_sort_pairs(c->stream, c->scores.p + 1, c->order.p, V, c->tmpk.p, c->tmpv.p, c->sorttmp.p, key_bits);
         be_rank(c->stream, v);
     }
     uint32_t rounds = 0;

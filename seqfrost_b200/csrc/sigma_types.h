@@ -82,7 +82,7 @@ typedef struct SgScalars {
     uint32_t n_trail, propagated, unassigned, max_frozen;
     uint32_t unsat, n_units, wl_count[2];
     uint32_t brk_rank, n_acting, n_ponly, n_elected;
-    uint32_t live_cls, pad0;
+    uint32_t live_cls, max_score;
     unsigned long long live_lits;
     unsigned long long n_model;
     unsigned long long pures, inverters, andors, ites, xors, funs, resolutions, subsumed, strengthened;

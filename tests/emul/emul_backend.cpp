@@ -113,7 +113,11 @@ void be_scatter(void *, const SgView &v, uint32_t *cursor)
 void be_scores(void *, const SgView &v)
 {
     g_launches++;
-    for (uint32_t x = 1; x <= v.nvars; ++x) { v.scores[x] = v.occ[2 * x] * v.occ[2 * x + 1]; v.order[x - 1] = x; }
+    v.sc->max_score = 0;
+    for (uint32_t x = 1; x <= v.nvars; ++x) {
+        v.scores[x] = v.occ[2 * x] * v.occ[2 * x + 1]; v.order[x - 1] = x;
+        if (v.scores[x] > v.sc->max_score) v.sc->max_score = v.scores[x];
+    }
 }
 size_t be_sort_tmp_words(uint32_t) { return 1; }
 void be_sort_pairs(void *, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t *, uint32_t *, uint32_t *, uint32_t)
