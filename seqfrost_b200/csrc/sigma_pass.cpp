@@ -88,13 +88,25 @@ struct sigma_ctx {
     std::vector<StageEv> evs;
     std::vector<void *> evpool;
     size_t evused = 0;
-    uint64_t launches0 = 0;
+    uint64_t launches0 = 0, n_syncs = 0;
+    int cur_stage = -1; bool sync_trace = false;
+    bool push_in_flight = false;    /* the pinned scalar mirror is still being read by a queued copy */
+    bool count_fresh = false;       /* hsc.live_cls / live_lits already describe the store */
 };
 
 namespace {
 
 const char *const kErr[] = { "ok", "formula is UNSATISFIABLE", "interrupted", "out of memory", "CUDA error",
                              "output buffer too small", "bad argument", "unsupported option combination" };
+
+/* every host <-> device round trip of the pass goes through here (counted: sigma_report.reserved[4]) */
+int ctx_sync(sigma_ctx *c)
+{
+    c->n_syncs++;
+    c->push_in_flight = false;
+    if (c->sync_trace) fprintf(stderr, "sync %d\n", c->cur_stage);
+    return be_sync(c->stream, c->err, sizeof c->err);
+}
 
 int fail(sigma_ctx *c, int code, const char *msg)
 {
@@ -111,6 +123,7 @@ void *get_event(sigma_ctx *c)
 struct Stage {
     sigma_ctx *c; int stage; void *a; uint64_t l0;
     Stage(sigma_ctx *ctx, int st, uint64_t bytes = 0) : c(ctx), stage(st) {
+        c->cur_stage = st;
         a = get_event(c);
         be_event_record(c->stream, a);
         l0 = be_launch_count();
@@ -121,6 +134,7 @@ struct Stage {
         be_event_record(c->stream, b);
         c->evs.push_back({ a, b, stage });
         c->rep.stage_launches[stage] += (uint32_t)(be_launch_count() - l0);
+        c->cur_stage = -1;
     }
 };
 
@@ -162,22 +176,31 @@ SgView make_view(sigma_ctx *c)
 int pull_scalars(sigma_ctx *c)
 {
     be_copy_words(c->stream, c->h_sc, c->sc.p, sizeof(SgScalars));
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
     c->hsc = *c->h_sc;
     return SIGMA_OK;
 }
+/* host mirror -> device scalars.  No round trip: the copy is queued, and the pinned staging copy stays untouched
+ * until the next synchronisation (every pull synchronises before it rewrites the mirror) */
 int push_scalars(sigma_ctx *c)
 {
+    if (c->push_in_flight && ctx_sync(c)) return SIGMA_E_CUDA;
     *c->h_sc = c->hsc;
     be_copy_words(c->stream, c->sc.p, c->h_sc, sizeof(SgScalars));
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    c->push_in_flight = true;
     return SIGMA_OK;
 }
 int pull_totals(sigma_ctx *c, uint32_t n)
 {
     be_copy_words(c->stream, c->h_totals, c->totals.p, n * sizeof(uint32_t));
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
     return SIGMA_OK;
+}
+/* scan totals and scalars with one round trip */
+int pull_both(sigma_ctx *c, uint32_t n)
+{
+    be_copy_words(c->stream, c->h_totals, c->totals.p, n * sizeof(uint32_t));
+    return pull_scalars(c);
 }
 
 #define CK(x) do { int rc_ = (x); if (rc_ != SIGMA_OK) return rc_; } while (0)
@@ -268,8 +291,7 @@ int stage_update_ot(sigma_ctx *c, uint64_t live_lits)
         v = make_view(c);
         be_ot_update(c->stream, v, u);
         c->rep.stage_bytes[SIGMA_T_OT_UPDATE] += 8ull * need;
-        if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;   /* h_totals[13] is reused below */
-        c->ot_end += need;
+        c->ot_end += need;                     /* h_totals[13] is not written again before the next round trip */
     }
     if (c->ot_verify) {
         /* test hook: rebuild from scratch into the spare buffers and compare list by list */
@@ -354,11 +376,9 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
             if (env_pgrow < 2) env_pgrow = 2;
         }
         bool done = false;
-        if (env_pers && be_elect_all(c->stream, v, c->wl0.p, c->wl1.p, (uint32_t)(env_b0 < 16384 ? 16384 : env_b0), (uint32_t)env_pgrow) == 0) {
-            CK(pull_scalars(c));
-            rounds = c->hsc.wl_count[0];
-            done = true;
-        }
+        if (env_pers && be_elect_all(c->stream, v, c->wl0.p, c->wl1.p, (uint32_t)(env_b0 < 16384 ? 16384 : env_b0), (uint32_t)env_pgrow) == 0)
+            done = true;                                   /* the round count comes back with the totals below */
+        const bool persistent = done;
         uint32_t r0 = 0, bsize = (uint32_t)env_b0;
         while (!done && r0 < V) {
             const uint32_t r1 = (V - r0 <= bsize) ? V : r0 + bsize;
@@ -384,7 +404,8 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         be_scan_u32(c->stream, c->flags.p, c->pos.p, V, c->totals.p, c->scantmp.p);
         be_scan_u32(c->stream, c->flags.p + V, c->pos.p + V, V, c->totals.p + 1, c->scantmp.p);
         be_acting_scatter(c->stream, v, c->flags.p, c->pos.p, c->flags.p + V, c->pos.p + V);
-        CK(pull_totals(c, 2));
+        CK(pull_both(c, 2));
+        if (persistent) rounds = c->hsc.wl_count[0];
         c->hsc.n_acting = c->h_totals[0]; c->hsc.n_elected = c->h_totals[1];
         c->last_elected = c->h_totals[1];
         be_serial(c->stream, SGS_MARKS, v, c->hsc.n_acting);
@@ -432,15 +453,16 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     v.n_elected = E;
     v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
     v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
-    /* scratch slices + unit buffer sized from the elected lists */
+    /* scratch slices + unit buffer.  A slice is max(|P|, |N|) + 2 words; elected variables share no clause (lcve.cpp:121-145),
+     * so all their lists together hold at most n_cls entries: sized from that bound, no round trip for the exact total
+     * (which is checked when it comes back with the BVE totals) */
     v.scr_off = c->scr_len.p;              /* SGK_SCRATCH_LEN writes lengths through scr_off */
     be_items(c->stream, SGK_SCRATCH_LEN, v, E);
-    be_scan_u32(c->stream, c->scr_len.p, c->scr_off.p, E, c->totals.p, c->scantmp.p);
-    CK(pull_totals(c, 1));
-    const uint32_t scr_total = c->h_totals[0];
-    NOMEM(c->scratch.ensure((size_t)scr_total + 64));
-    NOMEM(c->ubuf.ensure(2ull * scr_total + 4096));
-    NOMEM(c->ot_add.ensure(2ull * scr_total + 128));
+    be_scan_u32(c->stream, c->scr_len.p, c->scr_off.p, E, c->totals.p + 4, c->scantmp.p);
+    const size_t scr_bound = (size_t)c->n_cls + 2ull * E;
+    NOMEM(c->scratch.ensure(scr_bound + 64));
+    NOMEM(c->ubuf.ensure(scr_bound + 4096));
+    NOMEM(c->ot_add.ensure(2 * scr_bound + 128));
     c->ot_first_new = c->n_cls;
     c->phase_add_lits = 0;
     v = make_view(c);
@@ -459,8 +481,8 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         if (c->opts.sub_en || c->opts.ve_plus_en) {        /* subsume.cpp:25 */
             Stage st(c, SIGMA_T_SUB);
             be_items(c->stream, SGK_SUB, v, E);
-            int rc = apply_units(c, v);
-            if (rc != SIGMA_OK) return rc;
+            /* its units wait in the buffer: nothing before the end of this phase reads an assignment, and the
+             * (elected index, sequence) keys put them in front of the BVE units (enqueueUnit order) */
         }
     }
     if (c->opts.ve_en) {                                   /* bounded.cpp:29 */
@@ -469,8 +491,8 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         be_scan_u32(c->stream, c->ve_ncls.p, c->ve_cls_off.p, E, c->totals.p + 0, c->scantmp.p);
         be_scan_u32(c->stream, c->ve_nlits.p, c->ve_lit_off.p, E, c->totals.p + 1, c->scantmp.p);
         be_scan_u32(c->stream, c->ve_nmodel.p, c->ve_mod_off.p, E, c->totals.p + 2, c->scantmp.p);
-        CK(pull_totals(c, 3));
-        CK(pull_scalars(c));
+        CK(pull_both(c, 5));
+        if (c->h_totals[4] > scr_bound) return fail(c, SIGMA_E_CUDA, "internal: elected lists overlap (scratch bound exceeded)");
         if (c->hsc.unsat) return SIGMA_UNSAT;              /* function-table UNSAT, bounded.cpp:141-145 */
         const uint32_t add_cls = c->h_totals[0], add_lits = c->h_totals[1], add_model = c->h_totals[2];
         if ((uint64_t)c->pool_used + add_lits >= 0xFFFFFFF0ull)
@@ -485,9 +507,6 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         c->pool_used += add_lits;
         c->phase_add_lits = add_lits;
         c->model_words += add_model;
-        v = make_view(c);
-        int rc = apply_units(c, v);
-        if (rc != SIGMA_OK) return rc;
     }
     if (c->opts.bce_en) {                                  /* blocked.cpp:25 */
         Stage st(c, SIGMA_T_VE);
@@ -506,6 +525,16 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
             be_items(c->stream, SGK_BCE_EMIT, v, E);
             c->model_words += add_model;
         }
+    }
+    /* end of the phase: the live counts (countAll, solve.hpp:661-671) come back with the round trip that fetches the
+     * units of SUB and BVE; applying units assigns values and never changes a clause, so the counts stay valid */
+    {
+        Stage st(c, SIGMA_T_COUNT, 8ull * c->n_cls);
+        v = make_view(c);
+        v.n_elected = E;
+        be_count_live(c->stream, v);
+        CK(apply_units(c, v));
+        c->count_fresh = true;
     }
     return SIGMA_OK;
 }
@@ -577,6 +606,7 @@ int stage_ere(sigma_ctx *c)
 
 int stage_count(sigma_ctx *c)
 {
+    if (c->count_fresh) { c->count_fresh = false; return SIGMA_OK; }
     {
         Stage st(c, SIGMA_T_COUNT, 8ull * c->n_cls);
         SgView v = make_view(c);
@@ -690,9 +720,8 @@ int run_phases(sigma_ctx *c)
         be_count_melted(c->stream, v, c->totals.p + 3);
     }
     CK(stage_export(c));
-    CK(pull_totals(c, 4));
+    CK(pull_both(c, 4));
     c->out_max_melted = c->h_totals[3];
-    CK(pull_scalars(c));
     return SIGMA_OK;
 }
 
@@ -810,7 +839,7 @@ int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
     be_h2d(c->stream, c->d_vorg.p, in->vorg, (size_t)(V + 1) * 4);
     if (in->ifrozen) be_h2d(c->stream, c->d_ifrozen.p, in->ifrozen, V + 1);
     be_event_record(c->stream, e1);
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
     c->rep.stage_ms[SIGMA_T_H2D] = be_event_ms(e0, e1);
     c->rep.h2d_bytes = in->n_buckets * 4 + (uint64_t)n * 8 + (V + 1) + nlit + (uint64_t)in->trail_size * 4 +
                        (uint64_t)in->model_size * 4 + (uint64_t)(V + 1) * 4 + (in->ifrozen ? V + 1 : 0);
@@ -834,6 +863,8 @@ int sigma_execute(sigma_ctx *c)
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
     { const char *e = getenv("SIGMA_NBH_FUSED"); c->nbh_fused = e ? atoi(e) : 0; }
     c->launches0 = be_launch_count();
+    c->n_syncs = 0; c->count_fresh = false; c->push_in_flight = false;
+    c->sync_trace = getenv("SIGMA_SYNC_TRACE") != nullptr;
     const uint32_t V = c->nvars, nlit = c->nlit;
     /* restore the pristine solver state */
     NOMEM(c->model.ensure((size_t)c->in_model + (1u << 16)));
@@ -853,11 +884,12 @@ int sigma_execute(sigma_ctx *c)
     int rc = push_scalars(c);
     if (rc == SIGMA_OK) rc = run_phases(c);
     be_event_record(c->stream, e1);
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
     /* resolve timers */
     for (const StageEv &e : c->evs) c->rep.stage_ms[e.stage] += be_event_ms(e.a, e.b);
     c->rep.stage_ms[SIGMA_T_TOTAL_DEVICE] = be_event_ms(e0, e1);
     c->rep.kernel_launches = be_launch_count() - c->launches0;
+    c->rep.reserved[4] = c->n_syncs;
     c->rep.status = rc;
     c->rep.literals_in = c->in_literals;
     c->rep.n_clauses = c->out_ncls; c->rep.n_literals = c->out_literals;
@@ -906,7 +938,7 @@ int sigma_download(sigma_ctx *c, sigma_formula *out)
     if (c->hsc.n_trail) be_d2h(c->stream, out->trail, c->trail.p, (size_t)c->hsc.n_trail * 4);
     if (c->model_words) be_d2h(c->stream, out->model, c->model.p, (size_t)c->model_words * 4);
     be_event_record(c->stream, e1);
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
     c->rep.stage_ms[SIGMA_T_D2H] = be_event_ms(e0, e1);
     c->rep.d2h_bytes = c->out_buckets * 4 + (uint64_t)c->out_ncls * 8 + (V + 1) + nlit + (uint64_t)c->hsc.n_trail * 4 + c->model_words * 4;
     return SIGMA_OK;
@@ -952,7 +984,7 @@ int sigma_snapshot(sigma_ctx *c, const char *name, void *dst, uint64_t cap_bytes
     *nbytes = n;
     if (!dst || cap_bytes < n) return SIGMA_E_NOSPACE;
     if (n) be_d2h(c->stream, dst, src, n);
-    if (be_sync(c->stream, c->err, sizeof c->err)) return SIGMA_E_CUDA;
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
     return SIGMA_OK;
 }
 
