@@ -304,6 +304,20 @@ def main():
                  "clauses_out": rep["n_clauses"], "literals_out": rep["n_literals"], "eliminated": rep["max_melted_delta"],
                  "subsumed": rep["subsumed"], "strengthened": rep["strengthened"]},
     }
+    # ---- widening #1: extract() on the device (sigma_upload_cnf), informational ------------------
+    if rank == 0 and world == 1:
+        db = B.clause_db_from_boundary(b, seed=args.seed, dead_frac=0.05)
+        ex_us, ex_bytes = [], 0
+        for _ in range(4):
+            s.upload_cnf(db, b)
+            r = s.report()
+            ex_us.append(r["extract_us"]); ex_bytes = r["extract_bytes"]
+        ex_ms = float(np.mean(ex_us[1:])) / 1e3
+        line["extract"] = {"what": "extract(orgs)+extract(learnts) on the device: clause database (5 % deleted records, literals in "
+                                   "watch order) -> SCNF with sorted literals and signatures; kernels k_extract_sizes + 2 scans + k_extract_write",
+                           "ms": ex_ms, "algorithmic_bytes": ex_bytes, "GB/s": ex_bytes / 1e9 / (ex_ms / 1e3),
+                           "frac": ex_bytes / 1e9 / (ex_ms / 1e3) / peak, "h2d_bytes": r["h2d_bytes"], "h2d_ms": r["stage_ms"]["h2d"]}
+        del db
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
         sv, sc = args.vars // args.sample_div, args.clauses // args.sample_div
         li, secs = reference_pass(sv, sc, args.seed, runs=1, ere=not args.no_ere)

@@ -161,6 +161,30 @@ int  sigma_download(sigma_ctx *ctx, sigma_formula *out);                        
 int  sigma_get_report(sigma_ctx *ctx, sigma_report *rep);
 /* sigma_execute always starts from the uploaded formula, so it can be repeated for timing.     */
 
+/* ---- widening #1: extract() on the device ------------------------------------
+ * The solver's clause database as it stands when awaken() is entered (simplify.cpp:135-153), i.e.
+ * BEFORE the reference's extract(orgs); extract(learnts) (simplify.cpp:118-133) has built the SCNF.
+ * sigma_upload_cnf copies it to the device and builds there what extract() builds on the host: one
+ * SCLAUSE per clause that cm.deleted(ref) does not flag, originals first, then learnts, each in list
+ * order; status / usage / lbd taken over as SCLAUSE(const CLAUSE&) does (sclause.hpp:61-75), literals
+ * sorted ascending (SORT, sort.hpp:44-52), signature = calcSig (sclause.hpp:158-162).  Afterwards the
+ * context is in the state sigma_upload would have left it in; `in->arena / refs / n_clauses /
+ * n_buckets / n_literals` are ignored (the counts are what extract() would leave in inf.nClauses /
+ * inf.nLiterals and are returned by sigma_extracted_sizes). */
+typedef struct sigma_cnf {
+    const uint32_t *cm;        /* CMM arena (solvetypes.hpp:57): CLAUSE records, clause.hpp:47-59 -
+                                  4 header buckets {flags|_l|_v|_used, _sz, _pos, _lbd} + _sz literals */
+    uint64_t  cm_buckets;      /* cm.size(): used buckets                                          */
+    const uint64_t *orgs;      /* Solver::orgs (BCNF = Vec<C_REF>)                                  */
+    uint64_t  n_orgs;
+    const uint64_t *learnts;   /* Solver::learnts                                                  */
+    uint64_t  n_learnts;
+    const uint8_t *stencil;    /* cm.stencil(): 1 = deleted, indexed by C_REF (solvetypes.hpp:59,81) */
+    uint64_t  stencil_size;    /* valid entries; refs at or beyond it count as not deleted         */
+} sigma_cnf;
+int  sigma_upload_cnf(sigma_ctx *ctx, const sigma_opts *o, const sigma_cnf *cnf, const sigma_formula *in);
+int  sigma_extracted_sizes(sigma_ctx *ctx, uint32_t *n_clauses, uint64_t *n_buckets, uint64_t *n_literals);
+
 /* pinned host memory for the hand-off buffers (the solver's SCNF arena allocator would call this
  * instead of malloc, malloc.hpp:60-69, so that H2D/D2H run at full PCIe rate) */
 void *sigma_host_alloc(uint64_t bytes);

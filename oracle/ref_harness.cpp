@@ -4,6 +4,8 @@
 // /root/reference/src) through one SIGmA pass, stage by stage, exactly as
 // Solver::simplifying() does (reference simplify.cpp:155-233), and writes
 //   --sgin=<file>   the drop-in boundary INPUT  (state right after awaken(), simplify.cpp:171)
+//   --cmin=<file>   the solver's clause database right BEFORE awaken() (input of extract(), simplify.cpp:118-153):
+//                   CMM arena, orgs, learnts, deleted stencil
 //   --sgout=<file>  the drop-in boundary OUTPUT (state right after shrinkSimp(), simplify.cpp:210)
 //   --trace=<file>  per-phase elected lists / counters (debug aid for stage-level parity)
 // in the sectioned binary format read by seqfrost_b200/boundary.py.  It is also the
@@ -132,7 +134,19 @@ public:
 		return UNSOLVED;
 	}
 
-	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts) {
+	void dumpClauseDb(Writer& w) {
+		// CMM arena verbatim (solvetypes.hpp:57, clause.hpp:47-59) + the two ref lists + cm.stencil() up to the last ref
+		const uint64_t buckets = cm.size();
+		w.section("cm", cm.address(0), buckets * sizeof(uint32));
+		w.section("orgs", orgs.data(), uint64_t(orgs.size()) * sizeof(C_REF));
+		w.section("learnts", learnts.data(), uint64_t(learnts.size()) * sizeof(C_REF));
+		uint64_t top = 0;
+		for (uint32 i = 0; i < orgs.size(); ++i) if (orgs[i] + 1 > top) top = orgs[i] + 1;
+		for (uint32 i = 0; i < learnts.size(); ++i) if (learnts[i] + 1 > top) top = learnts[i] + 1;
+		w.section("stencil", cm.stencil(), top);
+	}
+
+	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts, const std::string& cmin = std::string()) {
 		using clk = std::chrono::steady_clock;
 		timer.start();
 		initLimits();
@@ -143,6 +157,12 @@ public:
 		rootify();                         // simplify.cpp:161
 		shrinkTop(false);                  // simplify.cpp:162
 		if (orgs.empty()) { fprintf(stderr, "ref_sigma: formula empty after root shrinking\n"); return 3; }
+		if (!cmin.empty()) {
+			Writer w;
+			if (!w.open(cmin)) return 5;
+			dumpClauseDb(w);
+			w.close();
+		}
 		awaken();                          // simplify.cpp:171
 		if (simpstate == AWAKEN_FAIL) return 4;
 		if (!sgin.empty()) {
@@ -219,7 +239,7 @@ int main(int argc, char** argv)
 	INT_OPT opt_timeout("timeout", "set out-of-time limit in seconds", 0, INT32R(0, INT32_MAX));
 	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
-	std::string sgin, sgout, tracep;
+	std::string sgin, sgout, tracep, cmin;
 	long long presolve_conflicts = 0;
 	std::vector<char*> pass;
 	for (int i = 0; i < argc; ++i) {
@@ -227,6 +247,7 @@ int main(int argc, char** argv)
 		if (a.rfind("--sgin=", 0) == 0) sgin = a.substr(7);
 		else if (a.rfind("--sgout=", 0) == 0) sgout = a.substr(8);
 		else if (a.rfind("--trace=", 0) == 0) tracep = a.substr(8);
+		else if (a.rfind("--cmin=", 0) == 0) cmin = a.substr(7);
 		else if (a.rfind("--presolve-conflicts=", 0) == 0) presolve_conflicts = atoll(a.substr(21).c_str());
 		else pass.push_back(argv[i]);
 	}
@@ -242,7 +263,7 @@ int main(int argc, char** argv)
 		std::string formula = argv[1];
 		Probe* p = new Probe(formula);
 		solver = p;
-		int rc = p->run(sgin, sgout, tracep, presolve_conflicts);
+		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin);
 		g_out_written = g_out_written || rc != 0;
 		fflush(stdout);
 		_exit(rc); // skip the reference's destructors (process-global singletons)

@@ -126,6 +126,74 @@ def read(path) -> Boundary:
     return b
 
 
+@dataclasses.dataclass
+class ClauseDb:
+    """The solver's clause database right before ``awaken()`` (input of ``extract()``, reference
+    simplify.cpp:118-153): CMM arena of CLAUSE records (clause.hpp:47-59), the ``orgs`` / ``learnts`` ref
+    lists and the deleted stencil (solvetypes.hpp:57-81)."""
+    cm: np.ndarray = None                # uint32 buckets
+    orgs: np.ndarray = None              # uint64 C_REF
+    learnts: np.ndarray = None           # uint64 C_REF
+    stencil: np.ndarray = None           # uint8, indexed by C_REF
+
+
+def read_clause_db(path) -> ClauseDb:
+    with open(path, "rb") as f:
+        blob = f.read()
+    if blob[:8] != MAGIC:
+        raise ValueError(f"{path}: not a sigma boundary file")
+    pos, sec = 8, {}
+    while pos < len(blob):
+        name = blob[pos:pos + 8].rstrip(b"\0").decode()
+        (n,) = struct.unpack_from("<Q", blob, pos + 8)
+        sec[name] = blob[pos + 16:pos + 16 + n]
+        pos += 16 + n
+    return ClauseDb(cm=np.frombuffer(sec["cm"], dtype=np.uint32).copy(), orgs=np.frombuffer(sec["orgs"], dtype=np.uint64).copy(),
+                    learnts=np.frombuffer(sec["learnts"], dtype=np.uint64).copy(),
+                    stencil=np.frombuffer(sec["stencil"], dtype=np.uint8).copy())
+
+
+def clause_db_from_boundary(b: "Boundary", seed=0, shuffle_lits=True, dead_frac=0.0) -> ClauseDb:
+    """Synthesises a clause database whose extract() is exactly `b`'s store: every clause of `b` becomes a CLAUSE
+    record (literals shuffled, since the solver keeps watches first, not sorted order), originals listed before
+    learnts, plus `dead_frac` extra records flagged deleted in the stencil.  Test / bench helper."""
+    rng = np.random.default_rng(seed)
+    w0, sig, sz, off, lits = b.soa()
+    n = int(sz.size)
+    learnt = (w0 & ST_MASK) == ST_LEARNT
+    assert not np.any(learnt[:-1] & ~learnt[1:]), "extract() lists originals before learnts"
+    n_dead = int(n * dead_frac)
+    total = n + n_dead
+    is_dead = np.zeros(total, dtype=bool)                   # dead records at random places of the arena
+    if n_dead:
+        is_dead[rng.choice(total, n_dead, replace=False)] = True
+    src = np.empty(total, dtype=np.int64)                   # which clause of `b` a record copies
+    src[~is_dead] = np.arange(n)
+    src[is_dead] = rng.integers(0, max(n, 1), n_dead)
+    rsz = sz[src]
+    ref = np.concatenate([[0], np.cumsum(rsz + 4)]).astype(np.int64)
+    cm = np.zeros(int(ref[-1]), dtype=np.uint32)
+    ref = ref[:-1]
+    lrn = learnt[src]
+    flags = np.uint32(1 << 4) | np.where(rsz == 2, np.uint32(1 << 5), np.uint32(0))          # _k = 1, _b = (size == 2)
+    cm[ref] = flags | (lrn.astype(np.uint32) << 8) | ((((w0[src] >> 4) & 3) * lrn).astype(np.uint32) << 24)
+    cm[ref + 1] = rsz.astype(np.uint32)
+    cm[ref + 2] = 2                                          # _pos
+    cm[ref + 3] = ((w0[src] >> 6) * lrn).astype(np.uint32)  # _lbd
+    start = np.concatenate([[0], np.cumsum(rsz)])[:-1]
+    k = np.arange(int(rsz.sum()), dtype=np.int64)
+    gl = lits[np.repeat(off[:-1][src] - start, rsz) + k]
+    if shuffle_lits:                                         # random order inside every clause
+        perm = np.lexsort((rng.random(gl.size), np.repeat(np.arange(total), rsz)))
+        gl = gl[perm]
+    cm[np.repeat(ref + 4 - start, rsz) + k] = gl
+    stencil = np.zeros(int(ref[-1]) + 1 if total else 0, dtype=np.uint8)
+    stencil[ref[is_dead]] = 1
+    # dead records also sit in the lists (extract() skips them through cm.deleted())
+    in_learnts = np.where(is_dead, rng.random(total) < 0.5, lrn)
+    return ClauseDb(cm=cm, orgs=ref[~in_learnts].astype(np.uint64), learnts=ref[in_learnts].astype(np.uint64), stencil=stencil)
+
+
 def read_trace(path):
     with open(path, "rb") as f:
         blob = f.read()

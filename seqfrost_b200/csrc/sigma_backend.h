@@ -71,6 +71,12 @@ void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32
                     sg_u4 *hdr, uint32_t *lits);
 /* one-kernel ingest for a gap-free arena (what awaken() leaves); *gap != 0 afterwards: use the general path */
 void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap);
+/* extract() on the device (simplify.cpp:118-133): sizes[i] = SCNF buckets of source clause i (0 = deleted), live[i] = 0/1;
+ * then, with the two exclusive scans, the SCLAUSE records and their refs */
+void be_extract_sizes(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
+                      uint32_t *sizes, uint32_t *live);
+void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
+                      const uint32_t *newid, uint32_t *arena, uint64_t *refs);
 /* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */
 void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp);
 size_t be_scan_tmp_words(uint32_t n);

@@ -669,6 +669,84 @@ SG_HDN inline void sg_marks_serial(const SgView &v, uint32_t n_acting)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* extract (simplify.cpp:118-133): CLAUSE records of the solver's clause arena -> SCLAUSE records */
+/* ------------------------------------------------------------------------------------------ */
+#define SG_CM_HDR 4u          /* header buckets of a CLAUSE (clause.hpp:47-59: sizeof == 24, two of them literals) */
+
+/* buckets the clause will take in the SCNF arena: 0 when cm.deleted(ref) (simplify.cpp:124) */
+SG_HD uint32_t sg_extract_size(const uint32_t *cm, const uint8_t *stencil, uint64_t stencil_size, uint64_t ref)
+{
+    if (ref < stencil_size && stencil[ref]) return 0;
+    return 3u + cm[ref + 1];
+}
+
+/* in-place heap sort (ascending) for the rare long clause */
+SG_HD void sg_sift_down_u32(uint32_t *a, int root, int end)
+{
+    const uint32_t val = a[root];
+    int hole = root;
+    for (;;) {
+        int child = 2 * hole + 1;
+        if (child >= end) break;
+        if (child + 1 < end && a[child + 1] > a[child]) child++;
+        if (a[child] <= val) break;
+        a[hole] = a[child];
+        hole = child;
+    }
+    a[hole] = val;
+}
+SG_HD void sg_heapsort_u32(uint32_t *a, int n)
+{
+    for (int s = n / 2 - 1; s >= 0; --s) sg_sift_down_u32(a, s, n);
+    for (int end = n - 1; end > 0; --end) {
+        const uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+        sg_sift_down_u32(a, 0, end);
+    }
+}
+
+/* SCLAUSE(const CLAUSE&) + calcSig + SORT (sclause.hpp:61-75,158-162; sort.hpp:44-52): dst = {w0, sig, size, lits} */
+SG_HD void sg_extract_write(const uint32_t *cm, uint64_t ref, uint32_t *dst)
+{
+    const uint32_t f = cm[ref], size = cm[ref + 1], lbd = cm[ref + 3];
+    const bool learnt = ((f >> 8) & 0xFFu) != 0;                      /* bool _l: byte 1 of the first bucket */
+    const uint32_t used = (f >> 24) & 3u;                             /* CL_ST _used: byte 3 */
+    const uint32_t *src = cm + ref + SG_CM_HDR;
+    uint32_t sig = 0;
+    uint32_t *out = dst + 3;
+    if (size <= 8) {
+        uint32_t a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = k < (int)size ? src[k] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k < (int)size) sig |= SG_HASH(a[k]);
+        /* odd-even transposition network: data-independent, stays in registers */
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = r & 1; k + 1 < 8; k += 2) {
+                const uint32_t lo = a[k] < a[k + 1] ? a[k] : a[k + 1], hi = a[k] < a[k + 1] ? a[k + 1] : a[k];
+                a[k] = lo; a[k + 1] = hi;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (k < (int)size) out[k] = a[k];
+    } else {
+        for (uint32_t k = 0; k < size; ++k) { const uint32_t l = src[k]; sig |= SG_HASH(l); out[k] = l; }
+        if (size <= 32) {
+            for (uint32_t i = 1; i < size; ++i) {
+                const uint32_t x = out[i];
+                uint32_t j = i;
+                while (j > 0 && out[j - 1] > x) { out[j] = out[j - 1]; --j; }
+                out[j] = x;
+            }
+        } else sg_heapsort_u32(out, (int)size);
+    }
+    dst[0] = learnt ? (SG_LEARNT | (used << SG_USAGE_SH) | ((lbd & 0x03FFFFFFu) << SG_LBD_SH)) : 0u;
+    dst[1] = sig;
+    dst[2] = size;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* SUB: self-subsuming strengthening + backward subsumption (subsume.hpp:26-218, subsume.cpp:45-76) */
 /* ------------------------------------------------------------------------------------------ */
 SG_HD bool sg_sig_sub(uint32_t A, uint32_t B) { return !(A & ~B); }                 /* simplify.hpp:119 */

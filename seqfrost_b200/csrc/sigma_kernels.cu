@@ -39,6 +39,29 @@ inline unsigned blocks_for(uint64_t n, int tpb = TPB) { return (unsigned)((n + t
 /* ---------------------------------------------------------------------------------------------- */
 /* ingest                                                                                           */
 /* ---------------------------------------------------------------------------------------------- */
+__global__ void k_extract_sizes(const uint32_t *__restrict__ cm, const uint64_t *__restrict__ crefs, uint32_t n,
+                                const uint8_t *__restrict__ stencil, uint64_t stencil_size, uint32_t *__restrict__ sizes,
+                                uint32_t *__restrict__ live)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t sz = sg_extract_size(cm, stencil, stencil_size, crefs[i]);
+    sizes[i] = sz;
+    live[i] = sz != 0;
+}
+
+__global__ void k_extract_write(const uint32_t *__restrict__ cm, const uint64_t *__restrict__ crefs, uint32_t n,
+                                const uint32_t *__restrict__ sizes, const uint32_t *__restrict__ newoff,
+                                const uint32_t *__restrict__ newid, uint32_t *__restrict__ arena,
+                                unsigned long long *__restrict__ refs)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !sizes[i]) return;
+    const uint32_t off = newoff[i];
+    refs[newid[i]] = off;
+    sg_extract_write(cm, crefs[i], arena + off);
+}
+
 __global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
                                uint32_t *__restrict__ sizes)
 {
@@ -897,6 +920,16 @@ void be_copy_words(void *s, void *dst, const void *src, size_t bytes)
     note_err("k_copy_words");
 }
 
+void be_extract_sizes(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
+                      uint32_t *sizes, uint32_t *live)
+{
+    if (n) LAUNCH(k_extract_sizes, blocks_for(n), TPB, s, cm, crefs, n, stencil, stencil_size, sizes, live);
+}
+void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
+                      const uint32_t *newid, uint32_t *arena, uint64_t *refs)
+{
+    if (n) LAUNCH(k_extract_write, blocks_for(n), TPB, s, cm, crefs, n, sizes, newoff, newid, arena, (unsigned long long *)refs);
+}
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
     if (n) LAUNCH(k_ingest_sizes, blocks_for(n), TPB, s, arena, refs, n, sizes);

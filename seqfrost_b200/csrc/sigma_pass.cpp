@@ -51,6 +51,8 @@ struct sigma_ctx {
     uint64_t in_buckets = 0, in_literals = 0, in_model = 0;
     bool in_has_ifrozen = false;
     DBuf<uint32_t> d_arena_in; DBuf<uint64_t> d_refs_in;
+    DBuf<uint32_t> d_cm; DBuf<uint64_t> d_crefs; DBuf<uint8_t> d_stencil;   /* sigma_upload_cnf: the solver's clause database */
+    uint64_t extract_us = 0, extract_bytes = 0;
     DBuf<uint8_t> d_state_in; DBuf<int8_t> d_value_in; DBuf<uint32_t> d_trail_in, d_model_in;
     DBuf<uint32_t> d_vorg; DBuf<uint8_t> d_ifrozen;
 
@@ -753,7 +755,7 @@ void sigma_destroy(sigma_ctx *c)
     if (c->stream) {
         be_bind(c->device);
         char e[64]; be_sync(c->stream, e, sizeof e);
-        c->d_arena_in.release(); c->d_refs_in.release(); c->d_state_in.release(); c->d_value_in.release();
+        c->d_arena_in.release(); c->d_refs_in.release(); c->d_cm.release(); c->d_crefs.release(); c->d_stencil.release(); c->d_state_in.release(); c->d_value_in.release();
         c->d_trail_in.release(); c->d_model_in.release(); c->d_vorg.release(); c->d_ifrozen.release();
         c->hdr.release(); c->hdr2.release(); c->lits.release(); c->lits2.release();
         c->ot_off.release(); c->ot_len.release(); c->ot_data.release(); c->occ.release(); c->cursor.release();
@@ -798,25 +800,48 @@ int sigma_set_stop(sigma_ctx *c, int phase, int stage)
     return SIGMA_OK;
 }
 
-int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
+} /* extern "C" */
+
+namespace {
+
+/* sigma_upload (cnf == nullptr: the SCNF arena comes from the host) and sigma_upload_cnf (the solver's clause
+ * database comes from the host, extract() runs here) */
+int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, const sigma_cnf *cnf)
 {
     if (!c || !in) return SIGMA_E_ARG;
     if (!c->stream) return fail(c, SIGMA_E_CUDA, c->err[0] ? c->err : "no CUDA device");
     be_bind(c->device);                                    /* callers may use one host thread per context */
     if (o) c->opts = *o;
-    if (!in->arena || !in->refs || !in->state || !in->value || !in->vorg) return fail(c, SIGMA_E_ARG, "null input array");
-    if (in->n_buckets >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "arena exceeds 32-bit bucket offsets");
-    if (in->n_buckets < 3ull * in->n_clauses) return fail(c, SIGMA_E_ARG, "n_buckets smaller than the clause headers");
+    if (!in->state || !in->value || !in->vorg) return fail(c, SIGMA_E_ARG, "null input array");
+    uint64_t n_src = 0;
+    if (cnf) {
+        n_src = cnf->n_orgs + cnf->n_learnts;
+        if (!cnf->cm || (cnf->n_orgs && !cnf->orgs) || (cnf->n_learnts && !cnf->learnts) || (cnf->stencil_size && !cnf->stencil))
+            return fail(c, SIGMA_E_ARG, "null clause database array");
+        if (cnf->cm_buckets >= 0xFFFFFFF0ull || n_src >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "clause database exceeds 32-bit bucket offsets");
+    } else {
+        if (!in->arena || !in->refs) return fail(c, SIGMA_E_ARG, "null input array");
+        if (in->n_buckets >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "arena exceeds 32-bit bucket offsets");
+        if (in->n_buckets < 3ull * in->n_clauses) return fail(c, SIGMA_E_ARG, "n_buckets smaller than the clause headers");
+    }
     c->uploaded = c->executed = false;
     c->evused = 0; c->evs.clear();
     memset(&c->rep, 0, sizeof c->rep);
-    const uint32_t V = in->nvars, nlit = 2 * V + 2, n = in->n_clauses;
-    c->in_nvars = V; c->in_ncls = n; c->in_buckets = in->n_buckets; c->in_literals = in->n_literals;
+    c->extract_us = 0; c->extract_bytes = 0;
+    const uint32_t V = in->nvars, nlit = 2 * V + 2, n = cnf ? 0 : in->n_clauses;
+    c->in_nvars = V; c->in_ncls = n; c->in_buckets = cnf ? 0 : in->n_buckets; c->in_literals = cnf ? 0 : in->n_literals;
     c->in_trail = in->trail_size; c->in_propagated = in->propagated; c->in_unassigned = in->unassigned;
     c->in_max_frozen = in->max_frozen; c->in_max_melted = in->max_melted; c->in_calls = in->simplify_calls ? in->simplify_calls : 1;
     c->in_model = in->model_size; c->in_has_ifrozen = in->ifrozen != nullptr;
     c->nvars = V; c->nlit = nlit;
-    NOMEM(c->d_arena_in.ensure(in->n_buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)n + 16));
+    if (cnf) {
+        NOMEM(c->d_cm.ensure(cnf->cm_buckets + 16)); NOMEM(c->d_crefs.ensure(n_src + 16)); NOMEM(c->d_stencil.ensure(cnf->stencil_size + 16));
+        NOMEM(c->c_sizes.ensure(n_src + 16)); NOMEM(c->c_flags.ensure(n_src + 16));
+        NOMEM(c->c_newoff.ensure(n_src + 16)); NOMEM(c->c_newid.ensure(n_src + 16));
+        NOMEM(c->scantmp.ensure(be_scan_tmp_words((uint32_t)n_src) + 64));
+    } else {
+        NOMEM(c->d_arena_in.ensure(in->n_buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)n + 16));
+    }
     NOMEM(c->d_state_in.ensure(V + 1)); NOMEM(c->d_value_in.ensure(nlit)); NOMEM(c->d_trail_in.ensure((size_t)V + 16));
     NOMEM(c->d_model_in.ensure((size_t)in->model_size + 16)); NOMEM(c->d_vorg.ensure(V + 1));
     if (in->ifrozen) NOMEM(c->d_ifrozen.ensure(V + 1));
@@ -830,8 +855,15 @@ int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
     NOMEM(c->acting.ensure(V + 1)); NOMEM(c->elected.ensure(V + 1));
     void *e0 = get_event(c), *e1 = get_event(c);
     be_event_record(c->stream, e0);
-    be_h2d(c->stream, c->d_arena_in.p, in->arena, in->n_buckets * 4);
-    be_h2d(c->stream, c->d_refs_in.p, in->refs, (size_t)n * 8);
+    if (cnf) {
+        be_h2d(c->stream, c->d_cm.p, cnf->cm, cnf->cm_buckets * 4);
+        if (cnf->n_orgs) be_h2d(c->stream, c->d_crefs.p, cnf->orgs, cnf->n_orgs * 8);
+        if (cnf->n_learnts) be_h2d(c->stream, c->d_crefs.p + cnf->n_orgs, cnf->learnts, cnf->n_learnts * 8);
+        if (cnf->stencil_size) be_h2d(c->stream, c->d_stencil.p, cnf->stencil, cnf->stencil_size);
+    } else {
+        be_h2d(c->stream, c->d_arena_in.p, in->arena, in->n_buckets * 4);
+        be_h2d(c->stream, c->d_refs_in.p, in->refs, (size_t)n * 8);
+    }
     be_h2d(c->stream, c->d_state_in.p, in->state, V + 1);
     be_h2d(c->stream, c->d_value_in.p, in->value, nlit);
     if (in->trail_size) be_h2d(c->stream, c->d_trail_in.p, in->trail, (size_t)in->trail_size * 4);
@@ -839,11 +871,52 @@ int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in)
     be_h2d(c->stream, c->d_vorg.p, in->vorg, (size_t)(V + 1) * 4);
     if (in->ifrozen) be_h2d(c->stream, c->d_ifrozen.p, in->ifrozen, V + 1);
     be_event_record(c->stream, e1);
+    void *e2 = nullptr;
+    if (cnf) {
+        /* extract(orgs); extract(learnts) (simplify.cpp:118-133,146-148): sizes -> two scans -> write */
+        const uint32_t ns = (uint32_t)n_src;
+        be_extract_sizes(c->stream, c->d_cm.p, c->d_crefs.p, ns, c->d_stencil.p, cnf->stencil_size, c->c_sizes.p, c->c_flags.p);
+        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, ns, c->totals.p + 0, c->scantmp.p);
+        be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, ns, c->totals.p + 1, c->scantmp.p);
+        CK(pull_totals(c, 2));
+        const uint32_t buckets = ns ? c->h_totals[0] : 0, ncls = ns ? c->h_totals[1] : 0;
+        NOMEM(c->d_arena_in.ensure((size_t)buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)ncls + 16));
+        be_extract_write(c->stream, c->d_cm.p, c->d_crefs.p, ns, c->c_sizes.p, c->c_newoff.p, c->c_newid.p, c->d_arena_in.p, c->d_refs_in.p);
+        e2 = get_event(c);
+        be_event_record(c->stream, e2);
+        c->in_ncls = ncls; c->in_buckets = buckets; c->in_literals = (uint64_t)buckets - 3ull * ncls;
+        /* read 16-byte header + literals + ref + stencil byte, write 12-byte header + literals + ref */
+        c->extract_bytes = 2 * 4ull * c->in_literals + 28ull * ncls + 9ull * ns + 8ull * ncls;
+    }
     if (ctx_sync(c)) return SIGMA_E_CUDA;
     c->rep.stage_ms[SIGMA_T_H2D] = be_event_ms(e0, e1);
-    c->rep.h2d_bytes = in->n_buckets * 4 + (uint64_t)n * 8 + (V + 1) + nlit + (uint64_t)in->trail_size * 4 +
+    if (e2) c->extract_us = (uint64_t)(1000.0f * be_event_ms(e1, e2));
+    c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
+    c->rep.h2d_bytes = (cnf ? cnf->cm_buckets * 4 + n_src * 8 + cnf->stencil_size : in->n_buckets * 4 + (uint64_t)n * 8) +
+                       (V + 1) + nlit + (uint64_t)in->trail_size * 4 +
                        (uint64_t)in->model_size * 4 + (uint64_t)(V + 1) * 4 + (in->ifrozen ? V + 1 : 0);
     c->uploaded = true;
+    return SIGMA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sigma_upload(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in) { return upload_impl(c, o, in, nullptr); }
+
+int sigma_upload_cnf(sigma_ctx *c, const sigma_opts *o, const sigma_cnf *cnf, const sigma_formula *in)
+{
+    if (!cnf) return SIGMA_E_ARG;
+    return upload_impl(c, o, in, cnf);
+}
+
+int sigma_extracted_sizes(sigma_ctx *c, uint32_t *n_clauses, uint64_t *n_buckets, uint64_t *n_literals)
+{
+    if (!c || !c->uploaded) return SIGMA_E_ARG;
+    if (n_clauses) *n_clauses = c->in_ncls;
+    if (n_buckets) *n_buckets = c->in_buckets;
+    if (n_literals) *n_literals = c->in_literals;
     return SIGMA_OK;
 }
 
@@ -856,6 +929,7 @@ int sigma_execute(sigma_ctx *c)
     const uint64_t h2d_bytes = c->rep.h2d_bytes;
     memset(&c->rep, 0, sizeof c->rep);
     c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
+    c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
     c->evused = 0; c->evs.clear();
     c->executed = false;
     c->ot_valid = false;
@@ -967,7 +1041,9 @@ int sigma_snapshot(sigma_ctx *c, const char *name, void *dst, uint64_t cap_bytes
     const void *src = nullptr;
     uint64_t n = 0;
     const uint32_t V = c->nvars, nlit = c->nlit;
-    if (!strcmp(name, "hdr")) { src = c->hdr.p; n = 16ull * c->n_cls; }
+    if (!strcmp(name, "arena_in")) { src = c->d_arena_in.p; n = 4ull * c->in_buckets; }
+    else if (!strcmp(name, "refs_in")) { src = c->d_refs_in.p; n = 8ull * c->in_ncls; }
+    else if (!strcmp(name, "hdr")) { src = c->hdr.p; n = 16ull * c->n_cls; }
     else if (!strcmp(name, "lits")) { src = c->lits.p; n = 4ull * c->pool_used; }
     else if (!strcmp(name, "ot_off")) { src = c->ot_off.p; n = 4ull * (nlit + 1); }
     else if (!strcmp(name, "ot_len")) { src = c->ot_len.p; n = 4ull * nlit; }

@@ -6,7 +6,9 @@
 // (newBeginning -> addClause(SCLAUSE&), sclause.cpp:22-62) and the watch rebuild.  Solver::solve(),
 // simplify() and simplifying() are not virtual, so this subclass re-states their few lines of
 // top-level control flow (solve.cpp:155-181, simplify.cpp:102-116,155-233) and swaps the phase
-// loop simplify.cpp:180-210 for one sigma_run() call.  Usage is the reference CLI's:
+// loop simplify.cpp:180-210 for one sigma_run() call.  By default extract() (simplify.cpp:118-133) runs on the
+// device as well: awaken() is re-stated without it and the clause database itself is uploaded (sigma_upload_cnf);
+// SIGMA_HOST_EXTRACT=1 keeps the reference's awaken() and uploads the SCNF it builds.  Usage is the reference CLI's:
 //
 //     seqfrost_sigma <formula.cnf> [reference options]
 //
@@ -19,6 +21,7 @@
 #include "../../include/sigma_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -33,12 +36,21 @@ namespace {
 class SigmaSolver : public Solver {
 	sigma_ctx* ctx = nullptr;
 	std::vector<uint8_t> st;
+	int64 clausesBefore = 0, literalsBefore = 0;      // inf.nClauses / inf.nLiterals after extract()
 
 public:
 	explicit SigmaSolver(const std::string& path) : Solver(path) {}
 
+	// awaken() (simplify.cpp:135-153) without extract(): the SCNF and the occurrence table live on the device
+	void sigmaAwaken() {
+		printStats(1, '-', CGREEN0);
+		initSimp();
+		wt.clear(true);
+		inf.nClauses = inf.nLiterals = 0;
+	}
+
 	// simplify.cpp:180-210 on the GPU.  Inputs and outputs are the reference's own objects.
-	void sigmaPass() {
+	void sigmaPass(const bool deviceExtract) {
 		if (!ctx) {
 			const int rc = sigma_create(0, &ctx);
 			if (rc != SIGMA_OK) {
@@ -61,8 +73,11 @@ public:
 		st.resize(V + 1);
 		for (uint32 v = 0; v <= V; ++v) st[v] = (uint8_t)sp->state[v].state;
 		sigma_formula in = {};
-		in.nvars = V; in.n_clauses = scnf.size(); in.n_buckets = scnf.STYPE::size(); in.n_literals = inf.nLiterals;
-		in.arena = (uint32_t*)scnf.clause(0); in.refs = (uint64_t*)scnf.refs().data();
+		in.nvars = V;
+		if (!deviceExtract) {
+			in.n_clauses = scnf.size(); in.n_buckets = scnf.STYPE::size(); in.n_literals = inf.nLiterals;
+			in.arena = (uint32_t*)scnf.clause(0); in.refs = (uint64_t*)scnf.refs().data();
+		}
 		in.state = st.data(); in.value = (int8_t*)sp->value;
 		in.trail = trail.data(); in.trail_size = trail.size(); in.propagated = sp->propagated;
 		in.vorg = vorg.data(); in.ifrozen = incremental ? (uint8_t*)ifrozen.data() : nullptr;
@@ -70,7 +85,28 @@ public:
 		in.unassigned = inf.unassigned; in.max_frozen = inf.maxFrozen; in.max_melted = inf.maxMelted;
 		in.simplify_calls = (uint32_t)stats.simplify.calls;
 
-		int rc = sigma_upload(ctx, &o, &in);
+		int rc;
+		if (deviceExtract) {
+			// extract(orgs), extract(learnts), cm.destroy() (simplify.cpp:146-149) - the first two on the device
+			sigma_cnf db = {};
+			db.cm = (const uint32_t*)cm.address(0); db.cm_buckets = cm.size();
+			db.orgs = (const uint64_t*)orgs.data(); db.n_orgs = orgs.size();
+			db.learnts = (const uint64_t*)learnts.data(); db.n_learnts = learnts.size();
+			uint64_t top = 0;                                  // the stencil is valid up to the last allocated ref
+			for (uint32 i = 0; i < orgs.size(); ++i) if (orgs[i] >= top) top = orgs[i] + 1;
+			for (uint32 i = 0; i < learnts.size(); ++i) if (learnts[i] >= top) top = learnts[i] + 1;
+			db.stencil = (const uint8_t*)cm.stencil(); db.stencil_size = top;
+			rc = sigma_upload_cnf(ctx, &o, &db, &in);
+			if (rc == SIGMA_OK) {
+				uint32_t ncls = 0; uint64_t nbuckets = 0, nlits = 0;
+				sigma_extracted_sizes(ctx, &ncls, &nbuckets, &nlits);
+				inf.nClauses = ncls; inf.nLiterals = (uint32)nlits;
+				orgs.clear(true), learnts.clear(true);
+				cm.destroy();
+			}
+		}
+		else rc = sigma_upload(ctx, &o, &in);
+		clausesBefore = inf.nClauses; literalsBefore = inf.nLiterals;
 		if (rc == SIGMA_OK) rc = sigma_execute(ctx);
 		if (rc == SIGMA_UNSAT) { learnEmpty(); killSolver(); }           // propelim.cpp:60, subsume.cpp:66, bounded.cpp:74
 		if (rc != SIGMA_OK) { fprintf(stderr, "c sigma_b200: %s: %s\n", sigma_strerror(rc), sigma_last_error(ctx)); exit(EXIT_FAILURE); }
@@ -124,11 +160,15 @@ public:
 		timer.stop();
 		timer.solve += timer.cpuTime();
 		if (!opts.profile_simplifier) timer.start();
-		awaken();
+		const char* he = getenv("SIGMA_HOST_EXTRACT");
+		const bool deviceExtract = !(he && he[0] == '1');
+		if (deviceExtract) sigmaAwaken();
+		else awaken();
 		if (simpstate == AWAKEN_FAIL) { recycle(); return; }
 		if (INTERRUPTED) killSolver();
-		const int64 bmelted = inf.maxMelted, bclauses = inf.nClauses, bliterals = inf.nLiterals;
-		sigmaPass();
+		const int64 bmelted = inf.maxMelted;
+		sigmaPass(deviceExtract);
+		const int64 bclauses = clausesBefore, bliterals = literalsBefore;
 		occurs.clear(true), ot.clear(true);
 		const bool success = (bliterals != inf.nLiterals);
 		stats.simplify.all.variables += int64(inf.maxMelted) - bmelted;

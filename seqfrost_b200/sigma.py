@@ -29,7 +29,7 @@ T_N = 20
 EXPORTS = [
     "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",
     "sigma_upload", "sigma_execute", "sigma_result_sizes", "sigma_download", "sigma_get_report", "sigma_host_alloc",
-    "sigma_host_free", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot",
+    "sigma_host_free", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot", "sigma_upload_cnf", "sigma_extracted_sizes",
 ]
 
 
@@ -46,6 +46,12 @@ class SigmaFormula(C.Structure):
         ("unassigned", C.c_uint32), ("max_frozen", C.c_uint32), ("max_melted", C.c_uint32), ("simplify_calls", C.c_uint32),
         ("arena_cap", C.c_uint64), ("refs_cap", C.c_uint32), ("trail_cap", C.c_uint32), ("model_cap", C.c_uint64),
     ]
+
+
+class SigmaCnf(C.Structure):
+    """sigma_cnf (include/sigma_b200.h)."""
+    _fields_ = [("cm", C.c_void_p), ("cm_buckets", C.c_uint64), ("orgs", C.c_void_p), ("n_orgs", C.c_uint64),
+                ("learnts", C.c_void_p), ("n_learnts", C.c_uint64), ("stencil", C.c_void_p), ("stencil_size", C.c_uint64)]
 
 
 class SigmaReport(C.Structure):
@@ -70,6 +76,8 @@ class SigmaReport(C.Structure):
         d["elected_per_phase"] = list(self.elected_per_phase)
         d["election_rounds"] = list(self.election_rounds)
         d["ere"] = dict(zip(("events", "dirty_vars", "full_pairs", "event_pairs"), list(self.reserved)[:4]))
+        d["host_round_trips"] = int(self.reserved[4])
+        d["extract_us"], d["extract_bytes"] = int(self.reserved[5]), int(self.reserved[6])
         return d
 
 
@@ -97,6 +105,8 @@ def load(path=None):
     lib.sigma_last_error.argtypes = [C.c_void_p]
     lib.sigma_run.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaFormula), C.POINTER(SigmaFormula), C.POINTER(SigmaReport)]
     lib.sigma_upload.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaFormula)]
+    lib.sigma_upload_cnf.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaCnf), C.POINTER(SigmaFormula)]
+    lib.sigma_extracted_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sigma_execute.argtypes = [C.c_void_p]
     lib.sigma_result_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
     lib.sigma_download.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
@@ -192,6 +202,24 @@ class Sigma:
     def upload(self, b: B.Boundary, opts=None):
         self._keep = (b, self.make_opts(opts if opts is not None else b.opts), self.make_formula(b))
         self._check(self.lib.sigma_upload(self.ctx, C.byref(self._keep[1]), C.byref(self._keep[2])))
+
+    def upload_cnf(self, db: B.ClauseDb, b: B.Boundary, opts=None):
+        """extract() on the device (reference simplify.cpp:118-153): `db` is the solver's clause database, `b` supplies
+        everything else (state, value, trail, vorg, model, counters); b.arena / b.refs are not read."""
+        f = self.make_formula(b)
+        f.arena, f.refs, f.n_clauses, f.n_buckets, f.n_literals = None, None, 0, 0, 0
+        cnf = SigmaCnf()
+        cnf.cm, cnf.cm_buckets = _ptr(db.cm), 0 if db.cm is None else int(db.cm.size)
+        cnf.orgs, cnf.n_orgs = _ptr(db.orgs), int(db.orgs.size)
+        cnf.learnts, cnf.n_learnts = _ptr(db.learnts), int(db.learnts.size)
+        cnf.stencil, cnf.stencil_size = _ptr(db.stencil), int(db.stencil.size)
+        self._keep = (b, self.make_opts(opts if opts is not None else b.opts), f, cnf, db)
+        self._check(self.lib.sigma_upload_cnf(self.ctx, C.byref(self._keep[1]), C.byref(cnf), C.byref(f)))
+
+    def extracted_sizes(self):
+        n, nb, nl = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.sigma_extracted_sizes(self.ctx, C.byref(n), C.byref(nb), C.byref(nl)))
+        return n.value, nb.value, nl.value
 
     def execute(self):
         self._check(self.lib.sigma_execute(self.ctx))

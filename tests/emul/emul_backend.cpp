@@ -56,6 +56,22 @@ float be_event_ms(void *a, void *b) { return (float)(((Ev *)b)->t - ((Ev *)a)->t
 uint64_t be_launch_count(void) { return g_launches; }
 void be_copy_words(void *, void *d, const void *s, size_t n) { memmove(d, s, n); }
 
+void be_extract_sizes(void *, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
+                      uint32_t *sizes, uint32_t *live)
+{
+    g_launches++;
+    for (uint32_t i : item_order(n)) { sizes[i] = sg_extract_size(cm, stencil, stencil_size, crefs[i]); live[i] = sizes[i] != 0; }
+}
+void be_extract_write(void *, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
+                      const uint32_t *newid, uint32_t *arena, uint64_t *refs)
+{
+    g_launches++;
+    for (uint32_t i : item_order(n)) {
+        if (!sizes[i]) continue;
+        refs[newid[i]] = newoff[i];
+        sg_extract_write(cm, crefs[i], arena + newoff[i]);
+    }
+}
 void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
     g_launches++;

@@ -5,7 +5,9 @@ built by `make -C oracle ref` from /root/reference/src).  Run in the build conta
 
 For every case it writes <name>.in (boundary right after awaken(), simplify.cpp:171) and
 <name>.out (boundary right after shrinkSimp(), simplify.cpp:210) in the sectioned format of
-seqfrost_b200/boundary.py.  The reference is run with -no-redundancy (ERE is SURVEY §8 "next #1").
+seqfrost_b200/boundary.py; cases without "+ere" run the reference with -no-redundancy.  For the cases in
+CM_CASES it also writes <name>.cm: the solver's clause database right BEFORE awaken() (CMM arena, orgs,
+learnts, deleted stencil - the input of extract(), simplify.cpp:118-153), for the device-side extract.
 """
 from __future__ import annotations
 
@@ -56,6 +58,10 @@ CASES = [
 ]
 
 
+# cases that also get the pre-awaken() clause database (ref_harness --cmin)
+CM_CASES = {"gates_small", "ksat5_planted", "xorphp_small", "fuzz_units4", "ere_fuzz", "later_ksat3", "later_gates"}
+
+
 def main():
     if not os.path.exists(REF):
         raise SystemExit(f"{REF} missing: run `make -C oracle ref` first")
@@ -69,7 +75,13 @@ def main():
                 if os.path.exists(f):
                     os.remove(f)
             base = [] if "+ere" in opts else ["-no-redundancy"]
-            r = subprocess.run([REF, cnf, *base, "-quiet", f"--sgin={fin}", f"--sgout={fout}"] + [o for o in opts if o != "+ere"],
+            extra = []
+            if name in CM_CASES:
+                fcm = os.path.join(HERE, name + ".cm")
+                if os.path.exists(fcm):
+                    os.remove(fcm)
+                extra = [f"--cmin={fcm}"]
+            r = subprocess.run([REF, cnf, *base, "-quiet", f"--sgin={fin}", f"--sgout={fout}"] + extra + [o for o in opts if o != "+ere"],
                                capture_output=True, text=True)
             print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"rc={r.returncode}",
                   os.path.getsize(fin), os.path.getsize(fout))

@@ -1,0 +1,115 @@
+"""extract() on the device (reference simplify.cpp:118-153): the solver's clause database goes in, the
+SCNF the reference's awaken() builds must come out bit for bit - and the pass on top of it must give the reference's
+result.  Fixtures: tests/golden/<name>.cm (clause database right before awaken(), dumped from the unmodified
+reference by oracle/ref_harness --cmin) next to <name>.in (the SCNF right after awaken()) and <name>.out."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from conftest import GOLDEN
+from seqfrost_b200 import boundary as B
+from seqfrost_b200 import cnfgen, sigma
+
+CM_CASES = ["gates_small", "ksat5_planted", "xorphp_small", "fuzz_units4", "ere_fuzz", "later_ksat3", "later_gates"]
+
+
+def _load(name):
+    return (B.read_clause_db(os.path.join(GOLDEN, name + ".cm")), B.read(os.path.join(GOLDEN, name + ".in")),
+            B.read(os.path.join(GOLDEN, name + ".out")))
+
+
+def _check_extract(s, db, bi):
+    s.upload_cnf(db, bi)
+    n, nb, nl = s.extracted_sizes()
+    assert (n, nb, nl) == (bi.refs.size, bi.arena.size, bi.n_literals)            # inf.nClauses / inf.nLiterals after extract()
+    assert np.array_equal(s.snapshot("arena_in", np.uint32), bi.arena)            # status, usage, lbd, sig, size, sorted literals
+    assert np.array_equal(s.snapshot("refs_in", np.uint64), bi.refs)
+
+
+def _run_cases(lib, names):
+    s = sigma.Sigma(0, lib)
+    for name in names:
+        db, bi, bo = _load(name)
+        _check_extract(s, db, bi)
+        s.execute()
+        assert parity.diff(s.download(), bo) == [], name
+    s.close()
+
+
+def test_fixture_clause_databases_are_what_the_reference_extracts_from():
+    """Sanity of the fixtures themselves (numpy restatement of extract()): every live record of the .cm, originals first,
+    is the corresponding clause of the .in with its literals in some other order."""
+    for name in CM_CASES:
+        db, bi, _ = _load(name)
+        refs = np.concatenate([db.orgs, db.learnts]).astype(np.int64)
+        live = refs[db.stencil[refs] == 0]
+        assert live.size == bi.refs.size
+        w0, sig, sz, off, lits = bi.soa()
+        assert np.array_equal(db.cm[live + 1], sz.astype(np.uint32))
+        assert np.array_equal((db.cm[live] >> 8) & 0xFF, w0 & 3)                   # _l  <->  LEARNT status
+        for k in (0, live.size // 2, live.size - 1):
+            r = int(live[k])
+            assert sorted(db.cm[r + 4:r + 4 + int(sz[k])].tolist()) == lits[off[k]:off[k + 1]].tolist()
+        if name.startswith("later"):
+            assert db.learnts.size and (w0 & 3).max() == 1                          # learnt clauses, later simplify() call
+
+
+def test_emul_extract_matches_reference(emul_lib):
+    _run_cases(emul_lib, CM_CASES)
+
+
+def test_emul_extract_synthetic_database(emul_lib):
+    """Deleted records in both lists, long clauses (all three sort paths: <= 8, <= 32, heap sort), shuffled literals."""
+    rng = np.random.default_rng(5)
+    nv, off, lits = cnfgen.random_ksat(300, 900, k=3, seed=9)
+    # add clauses of 9..200 distinct literals
+    rows = [rng.choice(np.arange(1, nv + 1), size=int(k), replace=False) * rng.choice([-1, 1], int(k))     # DIMACS-signed
+            for k in rng.integers(9, 200, 40)]
+    off = np.concatenate([off, off[-1] + np.cumsum([r.size for r in rows])])
+    lits = np.concatenate([lits] + [r.astype(lits.dtype) for r in rows])
+    bi = B.from_cnf(nv, off, lits)
+    db = B.clause_db_from_boundary(bi, seed=3, dead_frac=0.2)
+    assert db.stencil.sum() > 0
+    s = sigma.Sigma(0, emul_lib)
+    _check_extract(s, db, bi)
+    s.execute()
+    out_a = s.download()
+    s.upload(bi); s.execute()
+    assert parity.diff(out_a, s.download()) == []
+    s.close()
+
+
+def test_upload_cnf_argument_errors(emul_lib):
+    db, bi, _ = _load("fuzz_units4")
+    s = sigma.Sigma(0, emul_lib)
+    bad = B.ClauseDb(cm=db.cm, orgs=db.orgs, learnts=db.learnts, stencil=db.stencil)
+    bad.cm = None
+    with pytest.raises(sigma.SigmaError):
+        s.upload_cnf(bad, bi)
+    with pytest.raises(sigma.SigmaError):
+        s.extracted_sizes()                                  # nothing uploaded
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_extract_matches_reference(cuda_lib):
+    _run_cases(cuda_lib, CM_CASES)
+
+
+@pytest.mark.gpu
+def test_gpu_extract_at_scale(cuda_lib):
+    """1M-clause 5-SAT with 10 % deleted records and shuffled literals: the device-extracted store equals the host one,
+    and the pass on top of it gives the same bits as the pass on the host-extracted store."""
+    bi = B.from_cnf(*cnfgen.planted_subsumption_ksat(200_000, 1_000_000, k=5, seed=7))
+    db = B.clause_db_from_boundary(bi, seed=1, dead_frac=0.1)
+    s = sigma.Sigma(0, cuda_lib)
+    _check_extract(s, db, bi)
+    s.execute()
+    a = s.download()
+    rep = s.report()
+    assert rep["extract_us"] > 0 and rep["extract_bytes"] > 0
+    s.upload(bi); s.execute()
+    assert parity.diff(a, s.download()) == []
+    s.close()

@@ -22,9 +22,9 @@ KEYS = ("s SATISFIABLE", "s UNSATISFIABLE", "s UNKNOWN", "VERIFIED", "Conflicts"
 ANSI = re.compile(r"\x1b\[[0-9;]*m")
 
 
-def _digest(exe, cnf, opts):
+def _digest(exe, cnf, opts, env=None):
     r = subprocess.run([exe, cnf, "-model", "-modelverify", "-no-modelprint", "-report", *opts],     # reference defaults (ERE on)
-                       capture_output=True, text=True, timeout=120)
+                       capture_output=True, text=True, timeout=120, env=None if env is None else {**os.environ, **env})
     lines = [ANSI.sub("", l).strip() for l in r.stdout.splitlines()]
     return [l for l in lines if any(k in l for k in KEYS) and "ORG" not in l], r.stdout[-400:] + r.stderr[-400:]
 
@@ -40,11 +40,11 @@ CASES = [   # every case: the reference finishes in a few seconds (it is slow on
 ]
 
 
-def _check(exe, tmp_path, name, gen, opts):
+def _check(exe, tmp_path, name, gen, opts, env=None):
     cnf = str(tmp_path / (name + ".cnf"))
     cnfgen.write_dimacs(cnf, *gen())
     ref, _ = _digest(REF_SOLVER, cnf, opts)
-    ours, tail = _digest(exe, cnf, opts)
+    ours, tail = _digest(exe, cnf, opts, env)
     assert any(l.startswith("s ") for l in ref), ref
     assert ours == ref, tail
     if "s SATISFIABLE" in ref:
@@ -57,6 +57,16 @@ def test_solver_with_replaced_pass_cpu_standin(tmp_path, case):
     import __graft_entry__ as ge
     exe = ge.build_host(emul=True)
     _check(exe, tmp_path, *case)
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_SOLVER) and os.path.exists("/root/reference/src")), reason="reference not present")
+def test_solver_with_host_side_extract_cpu_standin(tmp_path):
+    """SIGMA_HOST_EXTRACT=1: the reference's own awaken()/extract() builds the SCNF and sigma_upload ships it (the default
+    ships the clause database and extracts on the device, sigma_upload_cnf)."""
+    import __graft_entry__ as ge
+    exe = ge.build_host(emul=True)
+    _check(exe, tmp_path, *CASES[0], env={"SIGMA_HOST_EXTRACT": "1"})
+    _check(exe, tmp_path, *CASES[2], env={"SIGMA_HOST_EXTRACT": "1"})
 
 
 @pytest.mark.gpu
