@@ -185,6 +185,30 @@ typedef struct sigma_cnf {
 int  sigma_upload_cnf(sigma_ctx *ctx, const sigma_opts *o, const sigma_cnf *cnf, const sigma_formula *in);
 int  sigma_extracted_sizes(sigma_ctx *ctx, uint32_t *n_clauses, uint64_t *n_buckets, uint64_t *n_literals);
 
+/* ---- widening #2: newBeginning() on the device ---------------------------------
+ * The simplified formula handed back as the solver's own clause database instead of an SCNF: what
+ * newBeginning() (simplify.cpp:249-268) builds by calling addClause(SCLAUSE&) (sclause.cpp:22-62) for
+ * every clause of the compacted SCNF, WITHOUT variable mapping (`mapped == false`) and without
+ * --aggresivesort: one CLAUSE record (clause.hpp:47-59, constructor :77-92) per clause, back to back in
+ * refs order - _k = 1 except learnt clauses with size > 2 and lbd > lbd_tier1, _b = (size == 2), _l / _lbd /
+ * _used from the SCLAUSE, _pos = 2, literals copied -, the ref of every ORIGINAL clause in `orgs` and of
+ * every LEARNT clause in `learnts` (list order = clause order), stats.literals.{original,learnt}, and,
+ * for simplify() calls after the first, the variables of added clauses (mark_ssubsume, sclause.hpp:209-215)
+ * as one byte per variable.  The two padding bits of a CLAUSE's first byte are written as 0 (the reference
+ * leaves them uninitialised).  `rest` receives state / value / trail / model exactly like sigma_download
+ * (its arena / refs are ignored). */
+typedef struct sigma_cnf_out {
+    uint32_t *cm;       uint64_t cm_cap;        /* buckets                                            */
+    uint64_t *orgs;     uint64_t orgs_cap;
+    uint64_t *learnts;  uint64_t learnts_cap;
+    uint8_t  *subsume;                          /* nvars + 1 bytes, may be NULL                       */
+    /* filled in (also by sigma_cnf_out_sizes, and on SIGMA_E_NOSPACE) */
+    uint64_t  cm_buckets, n_orgs, n_learnts, lits_original, lits_learnt;
+    uint64_t  last_ref;                         /* C_REF of the last record (its size = cm_buckets - last_ref - 4) */
+} sigma_cnf_out;
+int  sigma_cnf_out_sizes(sigma_ctx *ctx, sigma_cnf_out *sizes);                       /* after execute */
+int  sigma_download_cnf(sigma_ctx *ctx, sigma_cnf_out *out, sigma_formula *rest);
+
 /* pinned host memory for the hand-off buffers (the solver's SCNF arena allocator would call this
  * instead of malloc, malloc.hpp:60-69, so that H2D/D2H run at full PCIe rate) */
 void *sigma_host_alloc(uint64_t bytes);

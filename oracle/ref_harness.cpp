@@ -4,6 +4,8 @@
 // /root/reference/src) through one SIGmA pass, stage by stage, exactly as
 // Solver::simplifying() does (reference simplify.cpp:155-233), and writes
 //   --sgin=<file>   the drop-in boundary INPUT  (state right after awaken(), simplify.cpp:171)
+//   --cmout=<file>  the solver's clause database right AFTER newBeginning() without variable mapping (simplify.cpp:249-268):
+//                   CMM arena, orgs, learnts, stats.literals, sp->state[v].subsume before / after
 //   --cmin=<file>   the solver's clause database right BEFORE awaken() (input of extract(), simplify.cpp:118-153):
 //                   CMM arena, orgs, learnts, deleted stencil
 //   --sgout=<file>  the drop-in boundary OUTPUT (state right after shrinkSimp(), simplify.cpp:210)
@@ -146,7 +148,8 @@ public:
 		w.section("stencil", cm.stencil(), top);
 	}
 
-	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts, const std::string& cmin = std::string()) {
+	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts, const std::string& cmin = std::string(),
+		const std::string& cmout = std::string()) {
 		using clk = std::chrono::steady_clock;
 		timer.start();
 		initLimits();
@@ -222,6 +225,23 @@ public:
 			w.close();
 		}
 		g_out_written = true;
+		if (!cmout.empty() && inf.unassigned && inf.nClauses) {
+			// simplify.cpp:215-217 with canMap() false: newBeginning() builds cm / orgs / learnts from the compacted SCNF
+			std::vector<uint8_t> s0(inf.maxVar + 1), s1(inf.maxVar + 1);
+			for (uint32 v = 0; v <= inf.maxVar; ++v) s0[v] = sp->state[v].subsume;
+			newBeginning();
+			for (uint32 v = 0; v <= inf.maxVar; ++v) s1[v] = sp->state[v].subsume;
+			Writer w;
+			if (!w.open(cmout)) return 5;
+			w.section("cm", cm.address(0), uint64_t(cm.size()) * sizeof(uint32));
+			w.section("orgs", orgs.data(), uint64_t(orgs.size()) * sizeof(C_REF));
+			w.section("learnts", learnts.data(), uint64_t(learnts.size()) * sizeof(C_REF));
+			uint64_t m[4] = { stats.literals.original, stats.literals.learnt, stats.clauses.original, stats.clauses.learnt };
+			w.section("cmmeta", m, sizeof m);
+			w.section("subsume0", s0.data(), s0.size());
+			w.section("subsume1", s1.data(), s1.size());
+			w.close();
+		}
 		printf("ref_sigma: pass_ms=%.3f final_compact_ms=%.3f phases=%d vars=%u clauses=%u literals=%u melted=%u units=%u model=%u\n",
 			passms, gcms, phase, inf.maxVar, inf.nClauses, inf.nLiterals, inf.maxMelted, (unsigned)trail.size(), (unsigned)model.resolved.size());
 		fflush(stdout);
@@ -239,7 +259,7 @@ int main(int argc, char** argv)
 	INT_OPT opt_timeout("timeout", "set out-of-time limit in seconds", 0, INT32R(0, INT32_MAX));
 	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
-	std::string sgin, sgout, tracep, cmin;
+	std::string sgin, sgout, tracep, cmin, cmout;
 	long long presolve_conflicts = 0;
 	std::vector<char*> pass;
 	for (int i = 0; i < argc; ++i) {
@@ -248,6 +268,7 @@ int main(int argc, char** argv)
 		else if (a.rfind("--sgout=", 0) == 0) sgout = a.substr(8);
 		else if (a.rfind("--trace=", 0) == 0) tracep = a.substr(8);
 		else if (a.rfind("--cmin=", 0) == 0) cmin = a.substr(7);
+		else if (a.rfind("--cmout=", 0) == 0) cmout = a.substr(8);
 		else if (a.rfind("--presolve-conflicts=", 0) == 0) presolve_conflicts = atoll(a.substr(21).c_str());
 		else pass.push_back(argv[i]);
 	}
@@ -263,7 +284,7 @@ int main(int argc, char** argv)
 		std::string formula = argv[1];
 		Probe* p = new Probe(formula);
 		solver = p;
-		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin);
+		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout);
 		g_out_written = g_out_written || rc != 0;
 		fflush(stdout);
 		_exit(rc); // skip the reference's destructors (process-global singletons)

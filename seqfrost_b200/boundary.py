@@ -135,6 +135,11 @@ class ClauseDb:
     orgs: np.ndarray = None              # uint64 C_REF
     learnts: np.ndarray = None           # uint64 C_REF
     stencil: np.ndarray = None           # uint8, indexed by C_REF
+    # only in dumps taken after newBeginning() (ref_harness --cmout)
+    lits_original: int = 0
+    lits_learnt: int = 0
+    subsume_before: np.ndarray = None    # sp->state[v].subsume before / after newBeginning()
+    subsume_after: np.ndarray = None
 
 
 def read_clause_db(path) -> ClauseDb:
@@ -148,9 +153,16 @@ def read_clause_db(path) -> ClauseDb:
         (n,) = struct.unpack_from("<Q", blob, pos + 8)
         sec[name] = blob[pos + 16:pos + 16 + n]
         pos += 16 + n
-    return ClauseDb(cm=np.frombuffer(sec["cm"], dtype=np.uint32).copy(), orgs=np.frombuffer(sec["orgs"], dtype=np.uint64).copy(),
-                    learnts=np.frombuffer(sec["learnts"], dtype=np.uint64).copy(),
-                    stencil=np.frombuffer(sec["stencil"], dtype=np.uint8).copy())
+    db = ClauseDb(cm=np.frombuffer(sec["cm"], dtype=np.uint32).copy(), orgs=np.frombuffer(sec["orgs"], dtype=np.uint64).copy(),
+                  learnts=np.frombuffer(sec["learnts"], dtype=np.uint64).copy())
+    if "stencil" in sec:
+        db.stencil = np.frombuffer(sec["stencil"], dtype=np.uint8).copy()
+    if "cmmeta" in sec:
+        m = np.frombuffer(sec["cmmeta"], dtype=np.uint64)
+        db.lits_original, db.lits_learnt = int(m[0]), int(m[1])
+        db.subsume_before = np.frombuffer(sec["subsume0"], dtype=np.uint8).copy()
+        db.subsume_after = np.frombuffer(sec["subsume1"], dtype=np.uint8).copy()
+    return db
 
 
 def clause_db_from_boundary(b: "Boundary", seed=0, shuffle_lits=True, dead_frac=0.0) -> ClauseDb:

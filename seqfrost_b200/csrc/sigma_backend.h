@@ -77,6 +77,12 @@ void be_extract_sizes(void *s, const uint32_t *cm, const uint64_t *crefs, uint32
                       uint32_t *sizes, uint32_t *live);
 void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
                       const uint32_t *newid, uint32_t *arena, uint64_t *refs);
+/* newBeginning() on the device (simplify.cpp:249-268, sclause.cpp:22-62): exported SCNF -> CLAUSE records + orgs / learnts.
+ * learnt[i] = 0/1 first; then, with its exclusive scan, the records (clause i at bucket refs[i] + i), the two ref lists,
+ * counts[0] / counts[1] = literals of original / learnt clauses and, when subsume != NULL, the mark_ssubsume bytes */
+void be_cm_flags(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *learnt);
+void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *learnt_before, int lbd_tier1,
+                 uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume);
 /* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */
 void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp);
 size_t be_scan_tmp_words(uint32_t n);

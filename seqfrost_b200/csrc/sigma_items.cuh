@@ -746,6 +746,21 @@ SG_HD void sg_extract_write(const uint32_t *cm, uint64_t ref, uint32_t *dst)
     dst[2] = size;
 }
 
+/* addClause(SCLAUSE&) (sclause.cpp:22-62): one CLAUSE record (clause.hpp:47-59,77-92) from an exported SCLAUSE */
+SG_HD void sg_cm_write(const uint32_t *src, uint32_t *dst, int lbd_tier1)
+{
+    const uint32_t w0 = src[0], size = src[2];
+    const bool learnt = (w0 & SG_ST_MASK) == SG_LEARNT;
+    const uint32_t lbd = w0 >> SG_LBD_SH, used = (w0 >> SG_USAGE_SH) & 3u;
+    const bool keep = !(learnt && size > 2 && (int)lbd > lbd_tier1);
+    /* byte 0: _r _m _s _h _k _b; byte 1: _l; byte 2: _v; byte 3: _used */
+    dst[0] = (keep ? 1u << 4 : 0u) | (size == 2 ? 1u << 5 : 0u) | (learnt ? 1u << 8 : 0u) | (learnt ? used << 24 : 0u);
+    dst[1] = size;
+    dst[2] = 2u;                                  /* _pos */
+    dst[3] = learnt ? lbd : 0u;
+    for (uint32_t k = 0; k < size; ++k) dst[SG_CM_HDR + k] = src[3 + k];
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* SUB: self-subsuming strengthening + backward subsumption (subsume.hpp:26-218, subsume.cpp:45-76) */
 /* ------------------------------------------------------------------------------------------ */

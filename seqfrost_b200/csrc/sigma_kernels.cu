@@ -62,6 +62,39 @@ __global__ void k_extract_write(const uint32_t *__restrict__ cm, const uint64_t 
     sg_extract_write(cm, crefs[i], arena + off);
 }
 
+__global__ void k_cm_flags(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
+                           uint32_t *__restrict__ learnt)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) learnt[i] = (arena[refs[i]] & SG_ST_MASK) == SG_LEARNT;
+}
+
+__global__ void k_cm_write(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
+                           const uint32_t *__restrict__ learnt_before, int lbd_tier1, uint32_t *__restrict__ cm,
+                           unsigned long long *__restrict__ orgs, unsigned long long *__restrict__ learnts,
+                           unsigned long long *__restrict__ counts, uint8_t *__restrict__ subsume)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lo = 0, ll = 0;
+    if (i < n) {
+        const unsigned long long r = refs[i];
+        const uint32_t *src = arena + r;
+        const uint32_t w0 = src[0], size = src[2];
+        sg_cm_write(src, cm + r + i, lbd_tier1);
+        const uint32_t lb = learnt_before[i];
+        if ((w0 & SG_ST_MASK) == SG_LEARNT) { learnts[lb] = r + i; ll = size; }
+        else { orgs[i - lb] = r + i; lo = size; }
+        if (subsume && (w0 & SG_ADDED))
+            for (uint32_t k = 0; k < size; ++k) subsume[SG_ABS(src[3 + k])] = 1;
+    }
+    /* literal totals (stats.literals.original / learnt): one atomic per warp */
+    for (int d = 16; d; d >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, d); ll += __shfl_xor_sync(0xffffffffu, ll, d); }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo) atomicAdd(&counts[0], (unsigned long long)lo);
+        if (ll) atomicAdd(&counts[1], (unsigned long long)ll);
+    }
+}
+
 __global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
                                uint32_t *__restrict__ sizes)
 {
@@ -357,7 +390,10 @@ __global__ void k_elect_round(SgView v, const uint32_t *__restrict__ wl_in, uint
  * separated by grid-wide barriers (a few microseconds) instead of kernel launches and host round trips, which
  * makes small batch growth factors - fewer wasted scans - and deep dependency chains (hundreds of rounds on
  * XOR/pigeonhole instances) cheap.  Same per-candidate body as k_elect_round. */
-__global__ void __launch_bounds__(128) k_elect_persistent(SgView v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow)
+#ifndef SG_LB_ELECT
+#define SG_LB_ELECT 1          /* minimum resident blocks per SM asked of the compiler (register budget) */
+#endif
+__global__ void __launch_bounds__(128, SG_LB_ELECT) k_elect_persistent(SgView v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -443,7 +479,14 @@ __global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, cons
 /* ---------------------------------------------------------------------------------------------- */
 /* one item per thread                                                                              */
 /* ---------------------------------------------------------------------------------------------- */
-template <int KIND> __global__ void k_items(SgView v, uint32_t n)
+/* resident blocks per SM asked of the compiler, per kind (measured on the 10M-clause instance: these kernels wait on
+ * random sector fetches, so the BVE decision, SUB and the ERE proposal gain from more warps in flight even at the price
+ * of a few spilled registers; sortOT and the election lose) */
+constexpr int items_min_blocks(int kind)
+{
+    return kind == SGK_VE_COUNT ? 6 : kind == SGK_SUB ? 8 : kind == SGK_ERE_PROPOSE ? 5 : 1;
+}
+template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND)) k_items(SgView v, uint32_t n)
 {
     /* SUB and the BVE decision run one warp per elected variable, everything else one thread */
     const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_NBH || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
@@ -929,6 +972,17 @@ void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32
                       const uint32_t *newid, uint32_t *arena, uint64_t *refs)
 {
     if (n) LAUNCH(k_extract_write, blocks_for(n), TPB, s, cm, crefs, n, sizes, newoff, newid, arena, (unsigned long long *)refs);
+}
+void be_cm_flags(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *learnt)
+{
+    if (n) LAUNCH(k_cm_flags, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt);
+}
+void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *learnt_before, int lbd_tier1,
+                 uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
+{
+    cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ST(s));
+    if (n) LAUNCH(k_cm_write, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt_before, lbd_tier1, cm,
+                  (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume);
 }
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {

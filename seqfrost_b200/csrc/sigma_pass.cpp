@@ -77,6 +77,8 @@ struct sigma_ctx {
     DBuf<SgScalars> sc;
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
     DBuf<uint32_t> arena_out; DBuf<uint64_t> refs_out;
+    DBuf<uint32_t> cm_out; DBuf<uint64_t> orgs_out, learnts_out; DBuf<uint8_t> subsume_out;   /* sigma_download_cnf */
+    bool cm_built = false; uint32_t cm_learnts = 0; uint64_t cm_lits_org = 0, cm_lits_learnt = 0, cm_last_ref = 0;
     SgScalars hsc;                  /* host mirror */
     uint32_t *h_totals = nullptr;   /* pinned */
     SgScalars *h_sc = nullptr;      /* pinned */
@@ -767,7 +769,7 @@ void sigma_destroy(sigma_ctx *c)
         c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release();
         c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->otbits.release(); c->totals.release(); c->sc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
-        c->arena_out.release(); c->refs_out.release();
+        c->arena_out.release(); c->refs_out.release(); c->cm_out.release(); c->orgs_out.release(); c->learnts_out.release(); c->subsume_out.release();
         for (void *e2 : c->evpool) be_event_destroy(e2);
         if (c->h_totals) be_host_free(c->h_totals);
         if (c->h_sc) be_host_free(c->h_sc);
@@ -931,7 +933,7 @@ int sigma_execute(sigma_ctx *c)
     c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
     c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
     c->evused = 0; c->evs.clear();
-    c->executed = false;
+    c->executed = false; c->cm_built = false;
     c->ot_valid = false;
     { const char *e = getenv("SIGMA_OT_INCREMENTAL"); c->ot_incremental = !(e && e[0] == '0'); }
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
@@ -990,23 +992,72 @@ int sigma_result_sizes(sigma_ctx *c, sigma_formula *sz)
     return SIGMA_OK;
 }
 
-int sigma_download(sigma_ctx *c, sigma_formula *out)
+} /* extern "C" */
+
+namespace {
+
+/* newBeginning() on the device: the exported SCNF -> CLAUSE records + orgs / learnts (built once per execute) */
+int build_cm(sigma_ctx *c)
+{
+    if (c->cm_built) return SIGMA_OK;
+    const uint32_t n = c->out_ncls;
+    NOMEM(c->cm_out.ensure(c->out_buckets + n + 16)); NOMEM(c->orgs_out.ensure((size_t)n + 16)); NOMEM(c->learnts_out.ensure((size_t)n + 16));
+    NOMEM(c->c_flags.ensure((size_t)n + 16)); NOMEM(c->c_newid.ensure((size_t)n + 16)); NOMEM(c->subsume_out.ensure(c->nvars + 16));
+    NOMEM(c->scantmp.ensure(be_scan_tmp_words(n) + 64));
+    void *e0 = get_event(c), *e1 = get_event(c);
+    be_event_record(c->stream, e0);
+    be_memset(c->stream, c->subsume_out.p, 0, c->nvars + 1);
+    be_cm_flags(c->stream, c->arena_out.p, c->refs_out.p, n, c->c_flags.p);
+    be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
+    unsigned long long *counts = (unsigned long long *)(c->totals.p + 2);
+    be_cm_write(c->stream, c->arena_out.p, c->refs_out.p, n, c->c_newid.p, c->opts.lbd_tier1, c->cm_out.p, c->orgs_out.p,
+                c->learnts_out.p, counts, c->in_calls > 1 ? c->subsume_out.p : nullptr);        /* sclause.cpp:29-31 */
+    be_event_record(c->stream, e1);
+    if (n) be_copy_words(c->stream, c->h_totals + 8, c->refs_out.p + (n - 1), 8);
+    CK(pull_totals(c, 6));
+    c->cm_last_ref = n ? ((uint64_t)c->h_totals[8] | ((uint64_t)c->h_totals[9] << 32)) + (n - 1) : 0;
+    c->cm_learnts = n ? c->h_totals[0] : 0;
+    c->cm_lits_org = (uint64_t)c->h_totals[2] | ((uint64_t)c->h_totals[3] << 32);
+    c->cm_lits_learnt = (uint64_t)c->h_totals[4] | ((uint64_t)c->h_totals[5] << 32);
+    c->rep.reserved[7] = (uint64_t)(1000.0f * be_event_ms(e0, e1));
+    c->cm_built = true;
+    return SIGMA_OK;
+}
+
+int download_impl(sigma_ctx *c, sigma_formula *out, sigma_cnf_out *cnf)
 {
     if (!c || !out) return SIGMA_E_ARG;
     if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
     be_bind(c->device);
     const uint32_t V = c->nvars, nlit = c->nlit;
-    const bool small = out->arena_cap < c->out_buckets || out->refs_cap < c->out_ncls || out->trail_cap < c->hsc.n_trail ||
-                       out->model_cap < c->model_words;
+    bool small = out->trail_cap < c->hsc.n_trail || out->model_cap < c->model_words;
+    if (cnf) {
+        CK(build_cm(c));
+        const uint64_t n_orgs = c->out_ncls - c->cm_learnts;
+        small = small || cnf->cm_cap < c->out_buckets + c->out_ncls || cnf->orgs_cap < n_orgs || cnf->learnts_cap < c->cm_learnts;
+        cnf->cm_buckets = c->out_buckets + c->out_ncls; cnf->n_orgs = n_orgs; cnf->n_learnts = c->cm_learnts;
+        cnf->lits_original = c->cm_lits_org; cnf->lits_learnt = c->cm_lits_learnt; cnf->last_ref = c->cm_last_ref;
+    } else small = small || out->arena_cap < c->out_buckets || out->refs_cap < c->out_ncls;
     const uint64_t acap = out->arena_cap, mcap = out->model_cap; const uint32_t rcap = out->refs_cap, tcap = out->trail_cap;
     sigma_result_sizes(c, out);
     out->arena_cap = acap; out->model_cap = mcap; out->refs_cap = rcap; out->trail_cap = tcap;
     if (small) return fail(c, SIGMA_E_NOSPACE, "output buffers too small (required sizes filled in)");
-    if (!out->arena || !out->refs || !out->state || !out->value || !out->trail || !out->model) return fail(c, SIGMA_E_ARG, "null output array");
+    if (!out->state || !out->value || !out->trail || !out->model) return fail(c, SIGMA_E_ARG, "null output array");
+    if (cnf ? (!cnf->cm || !cnf->orgs || !cnf->learnts) : (!out->arena || !out->refs)) return fail(c, SIGMA_E_ARG, "null output array");
     void *e0 = get_event(c), *e1 = get_event(c);
     be_event_record(c->stream, e0);
-    if (c->out_buckets) be_d2h(c->stream, out->arena, c->arena_out.p, c->out_buckets * 4);
-    if (c->out_ncls) be_d2h(c->stream, out->refs, c->refs_out.p, (size_t)c->out_ncls * 8);
+    uint64_t clause_bytes;
+    if (cnf) {
+        if (cnf->cm_buckets) be_d2h(c->stream, cnf->cm, c->cm_out.p, cnf->cm_buckets * 4);
+        if (cnf->n_orgs) be_d2h(c->stream, cnf->orgs, c->orgs_out.p, cnf->n_orgs * 8);
+        if (cnf->n_learnts) be_d2h(c->stream, cnf->learnts, c->learnts_out.p, cnf->n_learnts * 8);
+        if (cnf->subsume) be_d2h(c->stream, cnf->subsume, c->subsume_out.p, V + 1);
+        clause_bytes = cnf->cm_buckets * 4 + (cnf->n_orgs + cnf->n_learnts) * 8 + (cnf->subsume ? V + 1 : 0);
+    } else {
+        if (c->out_buckets) be_d2h(c->stream, out->arena, c->arena_out.p, c->out_buckets * 4);
+        if (c->out_ncls) be_d2h(c->stream, out->refs, c->refs_out.p, (size_t)c->out_ncls * 8);
+        clause_bytes = c->out_buckets * 4 + (uint64_t)c->out_ncls * 8;
+    }
     be_d2h(c->stream, out->state, c->state.p, V + 1);
     be_d2h(c->stream, out->value, c->value.p, nlit);
     if (c->hsc.n_trail) be_d2h(c->stream, out->trail, c->trail.p, (size_t)c->hsc.n_trail * 4);
@@ -1014,7 +1065,30 @@ int sigma_download(sigma_ctx *c, sigma_formula *out)
     be_event_record(c->stream, e1);
     if (ctx_sync(c)) return SIGMA_E_CUDA;
     c->rep.stage_ms[SIGMA_T_D2H] = be_event_ms(e0, e1);
-    c->rep.d2h_bytes = c->out_buckets * 4 + (uint64_t)c->out_ncls * 8 + (V + 1) + nlit + (uint64_t)c->hsc.n_trail * 4 + c->model_words * 4;
+    c->rep.d2h_bytes = clause_bytes + (V + 1) + nlit + (uint64_t)c->hsc.n_trail * 4 + c->model_words * 4;
+    return SIGMA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sigma_download(sigma_ctx *c, sigma_formula *out) { return download_impl(c, out, nullptr); }
+
+int sigma_download_cnf(sigma_ctx *c, sigma_cnf_out *out, sigma_formula *rest)
+{
+    if (!out) return SIGMA_E_ARG;
+    return download_impl(c, rest, out);
+}
+
+int sigma_cnf_out_sizes(sigma_ctx *c, sigma_cnf_out *sz)
+{
+    if (!c || !sz) return SIGMA_E_ARG;
+    if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    be_bind(c->device);
+    CK(build_cm(c));
+    sz->cm_buckets = c->out_buckets + c->out_ncls; sz->n_learnts = c->cm_learnts; sz->n_orgs = c->out_ncls - c->cm_learnts;
+    sz->lits_original = c->cm_lits_org; sz->lits_learnt = c->cm_lits_learnt; sz->last_ref = c->cm_last_ref;
     return SIGMA_OK;
 }
 

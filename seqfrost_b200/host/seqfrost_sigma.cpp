@@ -37,6 +37,7 @@ class SigmaSolver : public Solver {
 	sigma_ctx* ctx = nullptr;
 	std::vector<uint8_t> st;
 	int64 clausesBefore = 0, literalsBefore = 0;      // inf.nClauses / inf.nLiterals after extract()
+	bool newBeginningDone = false;                    // cm / orgs / learnts already hold the simplified formula
 
 public:
 	explicit SigmaSolver(const std::string& path) : Solver(path) {}
@@ -103,6 +104,7 @@ public:
 				inf.nClauses = ncls; inf.nLiterals = (uint32)nlits;
 				orgs.clear(true), learnts.clear(true);
 				cm.destroy();
+				if (verbose >= 2) printf("c  sigma_b200: extracted on the device (%u clauses, %llu literals)\n", ncls, (unsigned long long)nlits);
 			}
 		}
 		else rc = sigma_upload(ctx, &o, &in);
@@ -112,31 +114,61 @@ public:
 		if (rc != SIGMA_OK) { fprintf(stderr, "c sigma_b200: %s: %s\n", sigma_strerror(rc), sigma_last_error(ctx)); exit(EXIT_FAILURE); }
 		sigma_formula sz = {};
 		sigma_result_sizes(ctx, &sz);
-
-		// receive into a fresh SCNF exactly like shrinkSimp() builds one (simplify.cpp:235-247)
-		SCNF fresh;
-		fresh.init(sz.n_clauses ? sz.n_clauses : 1, sz.n_literals ? sz.n_literals : 1);
-		if (sz.n_buckets) fresh.STYPE::alloc(sz.n_buckets);
-		fresh.refs().resize(sz.n_clauses);
+		inf.nClauses = sz.n_clauses; inf.nLiterals = (uint32)sz.n_literals;
+		inf.unassigned = sz.unassigned; inf.maxFrozen = sz.max_frozen; inf.maxMelted = sz.max_melted;
 		const uint32 oldtrail = trail.size();
 		trail.resize(sz.trail_size);
 		model.resolved.resize((uint32)sz.model_size);
 		sigma_formula out = {};
-		out.arena = sz.n_buckets ? (uint32_t*)fresh.clause(0) : (uint32_t*)st.data();
-		out.refs = (uint64_t*)fresh.refs().data();
 		out.state = st.data(); out.value = (int8_t*)sp->value; out.trail = trail.data(); out.model = model.resolved.data();
-		out.arena_cap = sz.n_buckets ? sz.n_buckets : 1; out.refs_cap = sz.n_clauses; out.trail_cap = sz.trail_size; out.model_cap = sz.model_size;
-		if (!out.refs) out.refs = (uint64_t*)st.data();
+		out.trail_cap = sz.trail_size; out.model_cap = sz.model_size;
 		if (!out.trail) out.trail = (uint32_t*)st.data();
 		if (!out.model) out.model = (uint32_t*)st.data();
-		rc = sigma_download(ctx, &out);
-		if (rc != SIGMA_OK) { fprintf(stderr, "c sigma_b200: download: %s\n", sigma_last_error(ctx)); exit(EXIT_FAILURE); }
-		fresh.migrateTo(scnf);
+
+		// newBeginning() (simplify.cpp:249-268) on the device too when no variable mapping follows (simplify.cpp:215-216):
+		// the CLAUSE records, orgs and learnts arrive ready-made
+		const char* hn = getenv("SIGMA_HOST_NEWBEGINNING");
+		newBeginningDone = false;
+		if (!(hn && hn[0] == '1') && inf.unassigned && inf.nClauses && !canMap() && !opts.aggr_cnf_sort) {
+			sigma_cnf_out co = {};
+			rc = sigma_cnf_out_sizes(ctx, &co);
+			if (rc != SIGMA_OK) { fprintf(stderr, "c sigma_b200: %s\n", sigma_last_error(ctx)); exit(EXIT_FAILURE); }
+			cm.init(inf.nClauses, inf.nLiterals);
+			if (co.last_ref) cm.CTYPE::alloc(co.last_ref);                     // every record in front of the last one, in bulk
+			C_REF last = 0;
+			cm.alloc(last, int(co.cm_buckets - co.last_ref) - 4);              // the last one through CMM::alloc: it sizes the deleted stencil
+			orgs.resize((uint32)co.n_orgs); learnts.resize((uint32)co.n_learnts);
+			std::vector<uint8_t> sub(V + 1);
+			co.cm = (uint32_t*)cm.address(0); co.cm_cap = co.cm_buckets;
+			co.orgs = orgs.size() ? (uint64_t*)orgs.data() : (uint64_t*)st.data(); co.orgs_cap = co.n_orgs;
+			co.learnts = learnts.size() ? (uint64_t*)learnts.data() : (uint64_t*)st.data(); co.learnts_cap = co.n_learnts;
+			co.subsume = sub.data();
+			rc = sigma_download_cnf(ctx, &co, &out);
+			if (rc != SIGMA_OK) { fprintf(stderr, "c sigma_b200: download: %s\n", sigma_last_error(ctx)); exit(EXIT_FAILURE); }
+			for (uint32 v = 1; v <= V; ++v) if (sub[v]) sp->state[v].subsume = 1;   // mark_ssubsume, sclause.hpp:209-215
+			stats.literals.original = co.lits_original; stats.literals.learnt = co.lits_learnt;
+			stats.clauses.original = orgs.size(); stats.clauses.learnt = learnts.size();
+			scnf.destroy();
+			newBeginningDone = true;
+			if (verbose >= 2) printf("c  sigma_b200: clause database built on the device (%u originals, %u learnts)\n", orgs.size(), learnts.size());
+		}
+		else {
+			// receive into a fresh SCNF exactly like shrinkSimp() builds one (simplify.cpp:235-247)
+			SCNF fresh;
+			fresh.init(sz.n_clauses ? sz.n_clauses : 1, sz.n_literals ? sz.n_literals : 1);
+			if (sz.n_buckets) fresh.STYPE::alloc(sz.n_buckets);
+			fresh.refs().resize(sz.n_clauses);
+			out.arena = sz.n_buckets ? (uint32_t*)fresh.clause(0) : (uint32_t*)st.data();
+			out.refs = (uint64_t*)fresh.refs().data();
+			out.arena_cap = sz.n_buckets ? sz.n_buckets : 1; out.refs_cap = sz.n_clauses;
+			if (!out.refs) out.refs = (uint64_t*)st.data();
+			rc = sigma_download(ctx, &out);
+			if (rc != SIGMA_OK) { fprintf(stderr, "c sigma_b200: download: %s\n", sigma_last_error(ctx)); exit(EXIT_FAILURE); }
+			fresh.migrateTo(scnf);
+		}
 		for (uint32 v = 1; v <= V; ++v) sp->state[v].state = st[v];
 		for (uint32 i = oldtrail; i < trail.size(); ++i) sp->level[ABS(trail[i])] = 0;     // enqueueUnit, solve.hpp:379
 		sp->propagated = sz.propagated;
-		inf.nClauses = sz.n_clauses; inf.nLiterals = (uint32)sz.n_literals;
-		inf.unassigned = sz.unassigned; inf.maxFrozen = sz.max_frozen; inf.maxMelted = sz.max_melted;
 #ifdef STATISTICS
 		sigma_report rep;
 		sigma_get_report(ctx, &rep);
@@ -177,7 +209,8 @@ public:
 		last.shrink.removed = stats.shrunken;
 		if (inf.maxFrozen > sp->simplified) stats.units.forced += inf.maxFrozen - sp->simplified;
 		if (!inf.unassigned || !inf.nClauses) { SET_SAT; printStats(1, 's', CGREEN); return; }
-		if (canMap()) map(true);
+		if (newBeginningDone) { /* simplify.cpp:216 happened on the device */ }
+		else if (canMap()) map(true);
 		else newBeginning();
 		rebuildWT(opts.simplify_priorbins);
 		if (retrail()) LOG2(2, " Propagation after simplify proved a contradiction");

@@ -29,7 +29,7 @@ T_N = 20
 EXPORTS = [
     "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",
     "sigma_upload", "sigma_execute", "sigma_result_sizes", "sigma_download", "sigma_get_report", "sigma_host_alloc",
-    "sigma_host_free", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot", "sigma_upload_cnf", "sigma_extracted_sizes",
+    "sigma_host_free", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot", "sigma_upload_cnf", "sigma_extracted_sizes", "sigma_cnf_out_sizes", "sigma_download_cnf",
 ]
 
 
@@ -52,6 +52,14 @@ class SigmaCnf(C.Structure):
     """sigma_cnf (include/sigma_b200.h)."""
     _fields_ = [("cm", C.c_void_p), ("cm_buckets", C.c_uint64), ("orgs", C.c_void_p), ("n_orgs", C.c_uint64),
                 ("learnts", C.c_void_p), ("n_learnts", C.c_uint64), ("stencil", C.c_void_p), ("stencil_size", C.c_uint64)]
+
+
+class SigmaCnfOut(C.Structure):
+    """sigma_cnf_out (include/sigma_b200.h)."""
+    _fields_ = [("cm", C.c_void_p), ("cm_cap", C.c_uint64), ("orgs", C.c_void_p), ("orgs_cap", C.c_uint64),
+                ("learnts", C.c_void_p), ("learnts_cap", C.c_uint64), ("subsume", C.c_void_p),
+                ("cm_buckets", C.c_uint64), ("n_orgs", C.c_uint64), ("n_learnts", C.c_uint64),
+                ("lits_original", C.c_uint64), ("lits_learnt", C.c_uint64), ("last_ref", C.c_uint64)]
 
 
 class SigmaReport(C.Structure):
@@ -107,6 +115,8 @@ def load(path=None):
     lib.sigma_upload.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaFormula)]
     lib.sigma_upload_cnf.argtypes = [C.c_void_p, C.POINTER(SigmaOpts), C.POINTER(SigmaCnf), C.POINTER(SigmaFormula)]
     lib.sigma_extracted_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.sigma_cnf_out_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaCnfOut)]
+    lib.sigma_download_cnf.argtypes = [C.c_void_p, C.POINTER(SigmaCnfOut), C.POINTER(SigmaFormula)]
     lib.sigma_execute.argtypes = [C.c_void_p]
     lib.sigma_result_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
     lib.sigma_download.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
@@ -257,6 +267,29 @@ class Sigma:
         out.unassigned, out.max_frozen, out.max_melted, out.propagated = f.unassigned, f.max_frozen, f.max_melted, f.propagated
         out._pinned = keep
         return out
+
+    def download_cnf(self):
+        """newBeginning() on the device (reference simplify.cpp:249-268): returns (ClauseDb, Boundary without arena / refs)."""
+        sz, co = SigmaFormula(), SigmaCnfOut()
+        self._check(self.lib.sigma_result_sizes(self.ctx, C.byref(sz)))
+        self._check(self.lib.sigma_cnf_out_sizes(self.ctx, C.byref(co)))
+        src = self._keep[0]
+        out = B.Boundary(status=0, nvars=sz.nvars, simplify_calls=sz.simplify_calls, vorg=src.vorg, opts=src.opts)
+        db = B.ClauseDb(cm=np.empty(int(co.cm_buckets), np.uint32), orgs=np.empty(int(co.n_orgs), np.uint64),
+                        learnts=np.empty(int(co.n_learnts), np.uint64))
+        db.subsume_after = np.empty(sz.nvars + 1, np.uint8)
+        out.state, out.value = np.empty(sz.nvars + 1, np.uint8), np.empty(2 * sz.nvars + 2, np.int8)
+        out.trail, out.model = np.empty(int(sz.trail_size), np.uint32), np.empty(int(sz.model_size), np.uint32)
+        co.cm, co.orgs, co.learnts, co.subsume = _ptr(db.cm), _ptr(db.orgs), _ptr(db.learnts), _ptr(db.subsume_after)
+        co.cm_cap, co.orgs_cap, co.learnts_cap = db.cm.size, db.orgs.size, db.learnts.size
+        f = SigmaFormula()
+        f.state, f.value, f.trail, f.model = _ptr(out.state), _ptr(out.value), _ptr(out.trail), _ptr(out.model)
+        f.trail_cap, f.model_cap = sz.trail_size, sz.model_size
+        self._check(self.lib.sigma_download_cnf(self.ctx, C.byref(co), C.byref(f)))
+        db.lits_original, db.lits_learnt = int(co.lits_original), int(co.lits_learnt)
+        out.n_clauses, out.n_literals = f.n_clauses, f.n_literals
+        out.unassigned, out.max_frozen, out.max_melted, out.propagated = f.unassigned, f.max_frozen, f.max_melted, f.propagated
+        return db, out
 
     # ---- reusable pinned hand-off buffers (what an integrated solver would own) -----------
     def alloc_pinned_like(self, b: B.Boundary, slack=1.25):

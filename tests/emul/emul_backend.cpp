@@ -72,6 +72,26 @@ void be_extract_write(void *, const uint32_t *cm, const uint64_t *crefs, uint32_
         sg_extract_write(cm, crefs[i], arena + newoff[i]);
     }
 }
+void be_cm_flags(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *learnt)
+{
+    g_launches++;
+    for (uint32_t i : item_order(n)) learnt[i] = (arena[refs[i]] & SG_ST_MASK) == SG_LEARNT;
+}
+void be_cm_write(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *learnt_before, int lbd_tier1,
+                 uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
+{
+    g_launches++;
+    counts[0] = counts[1] = 0;
+    for (uint32_t i : item_order(n)) {
+        const uint64_t r = refs[i];
+        const uint32_t *src = arena + r;
+        sg_cm_write(src, cm + r + i, lbd_tier1);
+        if ((src[0] & SG_ST_MASK) == SG_LEARNT) { learnts[learnt_before[i]] = r + i; counts[1] += src[2]; }
+        else { orgs[i - learnt_before[i]] = r + i; counts[0] += src[2]; }
+        if (subsume && (src[0] & SG_ADDED))
+            for (uint32_t k = 0; k < src[2]; ++k) subsume[SG_ABS(src[3 + k])] = 1;
+    }
+}
 void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
     g_launches++;

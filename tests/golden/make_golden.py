@@ -7,7 +7,9 @@ For every case it writes <name>.in (boundary right after awaken(), simplify.cpp:
 <name>.out (boundary right after shrinkSimp(), simplify.cpp:210) in the sectioned format of
 seqfrost_b200/boundary.py; cases without "+ere" run the reference with -no-redundancy.  For the cases in
 CM_CASES it also writes <name>.cm: the solver's clause database right BEFORE awaken() (CMM arena, orgs,
-learnts, deleted stencil - the input of extract(), simplify.cpp:118-153), for the device-side extract.
+learnts, deleted stencil - the input of extract(), simplify.cpp:118-153), for the device-side extract, and
+<name>.cmo: the clause database right AFTER newBeginning() without variable mapping (simplify.cpp:249-268), for
+the device-side newBeginning.
 """
 from __future__ import annotations
 
@@ -80,7 +82,10 @@ def main():
                 fcm = os.path.join(HERE, name + ".cm")
                 if os.path.exists(fcm):
                     os.remove(fcm)
-                extra = [f"--cmin={fcm}"]
+                fco = os.path.join(HERE, name + ".cmo")
+                if os.path.exists(fco):
+                    os.remove(fco)
+                extra = [f"--cmin={fcm}", f"--cmout={fco}"]
             r = subprocess.run([REF, cnf, *base, "-quiet", f"--sgin={fin}", f"--sgout={fout}"] + extra + [o for o in opts if o != "+ere"],
                                capture_output=True, text=True)
             print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"rc={r.returncode}",

@@ -81,6 +81,47 @@ def test_emul_extract_synthetic_database(emul_lib):
     s.close()
 
 
+def _check_new_beginning(s, name):
+    """After execute: the device-built clause database equals the one the reference's newBeginning() builds."""
+    exp = B.read_clause_db(os.path.join(GOLDEN, name + ".cmo"))
+    db, rest = s.download_cnf()
+    mask = np.full(exp.cm.size, 0xFFFFFFFF, dtype=np.uint32)
+    mask[np.concatenate([exp.orgs, exp.learnts]).astype(np.int64)] = 0xFFFFFF3F      # 2 padding bits of the CLAUSE bitfield byte
+    assert db.cm.size == exp.cm.size
+    assert np.array_equal(db.cm & mask, exp.cm & mask), name                          # _k _b _l _used _sz _pos _lbd + literals
+    assert np.array_equal(db.orgs, exp.orgs) and np.array_equal(db.learnts, exp.learnts)
+    assert (db.lits_original, db.lits_learnt) == (exp.lits_original, exp.lits_learnt)
+    assert np.array_equal(exp.subsume_before | db.subsume_after, exp.subsume_after)   # mark_ssubsume, sclause.hpp:209
+    bo = B.read(os.path.join(GOLDEN, name + ".out"))
+    for k in ("state", "value", "trail", "model"):
+        assert np.array_equal(getattr(rest, k), getattr(bo, k)), k
+    return db
+
+
+def test_emul_new_beginning_matches_reference(emul_lib):
+    s = sigma.Sigma(0, emul_lib)
+    marks = 0
+    for name in CM_CASES:
+        db, bi, _ = _load(name)
+        s.upload_cnf(db, bi)
+        s.execute()
+        marks += int(_check_new_beginning(s, name).subsume_after.sum())
+        s.upload(bi); s.execute()                             # same through the SCNF upload
+        _check_new_beginning(s, name)
+    assert marks > 0                                          # the later_* cases mark the variables of their resolvents
+    s.close()
+
+
+def test_download_cnf_reports_required_sizes(emul_lib):
+    _, bi, _ = _load("gates_small")
+    s = sigma.Sigma(0, emul_lib)
+    s.upload(bi); s.execute()
+    co, f = sigma.SigmaCnfOut(), sigma.SigmaFormula()
+    rc = s.lib.sigma_download_cnf(s.ctx, co, f)
+    assert rc == sigma.SIGMA_E_NOSPACE and co.cm_buckets > 0 and co.n_orgs > 0
+    s.close()
+
+
 def test_upload_cnf_argument_errors(emul_lib):
     db, bi, _ = _load("fuzz_units4")
     s = sigma.Sigma(0, emul_lib)
@@ -99,6 +140,17 @@ def test_gpu_extract_matches_reference(cuda_lib):
 
 
 @pytest.mark.gpu
+def test_gpu_new_beginning_matches_reference(cuda_lib):
+    s = sigma.Sigma(0, cuda_lib)
+    for name in CM_CASES:
+        db, bi, _ = _load(name)
+        s.upload_cnf(db, bi)
+        s.execute()
+        _check_new_beginning(s, name)
+    s.close()
+
+
+@pytest.mark.gpu
 def test_gpu_extract_at_scale(cuda_lib):
     """1M-clause 5-SAT with 10 % deleted records and shuffled literals: the device-extracted store equals the host one,
     and the pass on top of it gives the same bits as the pass on the host-extracted store."""
@@ -111,5 +163,14 @@ def test_gpu_extract_at_scale(cuda_lib):
     rep = s.report()
     assert rep["extract_us"] > 0 and rep["extract_bytes"] > 0
     s.upload(bi); s.execute()
-    assert parity.diff(a, s.download()) == []
+    b2 = s.download()
+    assert parity.diff(a, b2) == []
+    # newBeginning() on the device against its numpy restatement on the downloaded SCNF
+    out, _ = s.download_cnf()
+    w0, sig, sz, off, lits = b2.soa()
+    ref = b2.refs.astype(np.int64) + np.arange(b2.refs.size)
+    assert np.array_equal(out.orgs, ref[(w0 & 3) == 0].astype(np.uint64)) and out.learnts.size == 0
+    assert np.array_equal(out.cm[ref + 1], sz.astype(np.uint32)) and out.lits_original == int(sz.sum())
+    idx = np.repeat(ref + 4 - off[:-1], sz) + np.arange(int(off[-1]), dtype=np.int64)
+    assert np.array_equal(out.cm[idx], lits)
     s.close()

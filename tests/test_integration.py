@@ -65,8 +65,9 @@ def test_solver_with_host_side_extract_cpu_standin(tmp_path):
     ships the clause database and extracts on the device, sigma_upload_cnf)."""
     import __graft_entry__ as ge
     exe = ge.build_host(emul=True)
-    _check(exe, tmp_path, *CASES[0], env={"SIGMA_HOST_EXTRACT": "1"})
-    _check(exe, tmp_path, *CASES[2], env={"SIGMA_HOST_EXTRACT": "1"})
+    host = {"SIGMA_HOST_EXTRACT": "1", "SIGMA_HOST_NEWBEGINNING": "1"}   # newBeginning() by the reference as well
+    _check(exe, tmp_path, *CASES[0], env=host)
+    _check(exe, tmp_path, *CASES[2], env=host)
 
 
 @pytest.mark.gpu
