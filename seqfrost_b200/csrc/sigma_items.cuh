@@ -1653,9 +1653,23 @@ SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t chunk)
             /* 8 entries of the shortest list at a time: ids, then headers (independent loads), then the cheap
              * size/signature screen; the literal comparison runs only for the survivors */
             uint32_t cc[8];
-            sg_u4 hh[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) cc[k] = m0 + k < nm ? ml[m0 + k] : iref;
+            if (v.ere_filt) {
+                /* the screen reads the 8-byte {size, sig} snapshot (nothing is modified during the proposal pass) */
+                uint32_t fs2[8], fg[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { fs2[k] = v.ere_filt[2 * (size_t)cc[k]]; fg[k] = v.ere_filt[2 * (size_t)cc[k] + 1]; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (cc[k] == iref || cc[k] == jref) continue;
+                    if (len <= (int)fs2[k] && sg_sig_sub(sig, fg[k]) && sg_sub_lits(merged, len, v.lits + v.hdr[cc[k]].x, (int)fs2[k])) {
+                        hit = true; v.ere_touched[cc[k]] = 1;
+                    }
+                }
+                continue;
+            }
+            sg_u4 hh[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) hh[k] = v.hdr[cc[k]];
 #pragma unroll

@@ -95,6 +95,14 @@ __global__ void k_cm_write(const uint32_t *__restrict__ arena, const unsigned lo
     }
 }
 
+__global__ void k_ere_filt(SgView v, uint2 *__restrict__ filt)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.n_cls) return;
+    const uint4 h = v.hdr[c];
+    filt[c] = make_uint2((h.z & SG_DELETED) ? 0u : h.y, h.w);
+}
+
 __global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
                                uint32_t *__restrict__ sizes)
 {
@@ -237,12 +245,14 @@ __global__ void k_hist(const uint4 *__restrict__ hdr, const uint32_t *__restrict
  * stays resident in L2, so the 4-byte scattered stores merge there instead of each costing a
  * 32-byte sector read + write in HBM (ncu: 3.9 GB of DRAM traffic for 0.48 GB of payload when the
  * whole 204 MB table was scattered in one pass). */
+template <bool STREAM_IN>
 __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
                           uint32_t *__restrict__ cursor, uint32_t *__restrict__ ot_data, uint32_t lo, uint32_t hi)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cls) return;
-    const uint4 h = hdr[c];
+    /* STREAM_IN: the store is read once per pass - evict-first loads keep the slice of the table resident in L2 */
+    const uint4 h = STREAM_IN ? __ldcs(hdr + c) : hdr[c];
     if (h.z & SG_DELETED) return;
     const uint32_t *l = lits + h.x;
     for (uint32_t base = 0; base < h.y; base += 8) {
@@ -253,7 +263,7 @@ __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restr
         for (int k = 0; k < 8; ++k) {
             take[k] = false;
             if (base + k < h.y) {
-                const uint32_t lit = l[base + k];
+                const uint32_t lit = STREAM_IN ? __ldcs(l + base + k) : l[base + k];
                 take[k] = lit >= lo && lit < hi;
                 if (take[k]) pos[k] = atomicAdd(&cursor[lit], 1u);
             }
@@ -276,8 +286,14 @@ __global__ void k_scores(SgView v)
         v.order[x - 1] = x;
     }
     /* largest score: the radix sort only needs the digit passes that can differ */
+    /* one atomic per block (tens of thousands of same-address atomics cost more than the rest of the kernel) */
+    __shared__ uint32_t s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
     const uint32_t m = __reduce_max_sync(0xffffffffu, sc);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(&v.sc->max_score, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max, m);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) atomicMax(&v.sc->max_score, s_max);
 }
 
 constexpr int RS_ITEMS = 16;
@@ -715,13 +731,28 @@ __global__ void k_live_apply(SgView v, const uint2 *__restrict__ part, uint4 *__
     const uint2 b = part[blockIdx.x];                       /* (clauses, literals) before this tile */
     uint32_t id0 = b.x, off0 = b.y;
     __shared__ uint2 tot;
+    /* all headers first (independent loads), then the scans, then the copies */
+    uint4 hs[CP_ITEMS];
+    uint2 es[CP_ITEMS];
+#pragma unroll
     for (int k = 0; k < CP_ITEMS; ++k) {
         const uint64_t c = (uint64_t)blockIdx.x * CP_TILE + (uint64_t)k * TPB + threadIdx.x;
-        const uint4 h = c < v.n_cls ? v.hdr[c] : make_uint4(0, 0, SG_DELETED, 0);
+        hs[k] = c < v.n_cls ? v.hdr[c] : make_uint4(0, 0, SG_DELETED, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+        const bool live = !(hs[k].z & SG_DELETED);
+        const uint2 e = cp_block_scan(live ? 1u : 0u, live ? hs[k].y : 0u, &tot);
+        es[k] = make_uint2(id0 + e.x, off0 + e.y);
+        id0 += tot.x; off0 += tot.y;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+        const uint4 h = hs[k];
         const bool live = !(h.z & SG_DELETED);
-        const uint2 e = cp_block_scan(live ? 1u : 0u, live ? h.y : 0u, &tot);
         if (live) {
-            const uint32_t id = id0 + e.x, off = off0 + e.y;
+            const uint32_t id = es[k].x, off = es[k].y;
             const uint32_t *src = v.lits + h.x;
             if (EXPORT) {
                 const unsigned long long r = 3ull * id + off;
@@ -735,8 +766,6 @@ __global__ void k_live_apply(SgView v, const uint2 *__restrict__ part, uint4 *__
                 for (uint32_t q = 0; q < h.y; ++q) dst[q] = src[q];
             }
         }
-        id0 += tot.x; off0 += tot.y;
-        __syncthreads();
     }
 }
 
@@ -984,6 +1013,10 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
     if (n) LAUNCH(k_cm_write, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt_before, lbd_tier1, cm,
                   (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume);
 }
+void be_ere_filt(void *s, const SgView &v, uint32_t *filt)
+{
+    if (v.n_cls) LAUNCH(k_ere_filt, blocks_for(v.n_cls), TPB, s, v, (uint2 *)filt);
+}
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
     if (n) LAUNCH(k_ingest_sizes, blocks_for(n), TPB, s, arena, refs, n, sizes);
@@ -1016,7 +1049,9 @@ void be_scatter(void *s, const SgView &v, uint32_t *cursor)
 {
     if (!v.n_cls) return;
     static long l2_mb = -1;
+    static int stream_in = -1;
     if (l2_mb < 0) { const char *e = getenv("SIGMA_SCATTER_L2_MB"); l2_mb = e ? atol(e) : 64; if (l2_mb < 1) l2_mb = 1; }
+    if (stream_in < 0) { const char *e = getenv("SIGMA_SCATTER_CS"); stream_in = e ? atoi(e) : 0; }
     const uint64_t bytes = 4ull * v.pool_used;
     uint32_t passes = (uint32_t)((bytes + ((uint64_t)l2_mb << 20) - 1) / ((uint64_t)l2_mb << 20));
     if (passes < 1) passes = 1;
@@ -1024,7 +1059,8 @@ void be_scatter(void *s, const SgView &v, uint32_t *cursor)
     const uint32_t step = (v.nlit + passes - 1) / passes;
     for (uint32_t p = 0; p < passes; ++p) {
         const uint32_t lo = p * step, hi = (p + 1 == passes) ? 0xFFFFFFFFu : (p + 1) * step;
-        LAUNCH(k_scatter, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, cursor, v.ot_data, lo, hi);
+        if (stream_in) LAUNCH(k_scatter<true>, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, cursor, v.ot_data, lo, hi);
+        else LAUNCH(k_scatter<false>, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, cursor, v.ot_data, lo, hi);
     }
 }
 void be_scores(void *s, const SgView &v)

@@ -127,6 +127,7 @@ typedef struct SgView {
     uint32_t *ere_eidx;      /* variable -> position in `elected` */
     uint32_t *ere_owner;     /* per clause: earliest pending recorded pair that could write it (parallel rounds) */
     uint32_t *ere_done;      /* per recorded pair: 0 pending, 2 apply this round, 1 applied; NULL = no parallel rounds */
+    const uint32_t *ere_filt; /* proposal pass only: {size (0 = deleted), sig} per clause, 8 bytes, a snapshot small enough for L2 */
     SgScalars *sc;
     uint32_t nvars, nlit;    /* nlit = 2*nvars + 2 */
     uint32_t n_cls;          /* clause ids in use */
