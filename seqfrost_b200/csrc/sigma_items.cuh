@@ -565,6 +565,9 @@ SG_HD void sg_elect_prep_item(const SgView &v, uint32_t var)
  * out to act (depFreeze succeeded, lcve.cpp:76-78) freezes its still-undecided neighbours at
  * once, so later batches never have to look at them.  One warp per candidate: the lanes take
  * the clauses of both occurrence lists in turn. */
+#ifndef SG_ELECT_BATCH
+#define SG_ELECT_BATCH 8        /* literals (and their election words) in flight per lane */
+#endif
 SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
 {
     const SgLane L = sg_lane_ctx();
@@ -583,15 +586,15 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
         const int size = (int)h.y;
         if (size > maxcsize) { if (neg) failn = true; else failp = true; }
         const uint32_t *l = v.lits + h.x;
-        for (int base = 0; base < size; base += 8) {
+        for (int base = 0; base < size; base += SG_ELECT_BATCH) {
             /* literals first, then their election words: independent loads in flight together */
-            uint32_t other[8], w[8];
+            uint32_t other[SG_ELECT_BATCH], w[SG_ELECT_BATCH];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) other[k] = base + k < size ? l[base + k] : 2 * cand;
+            for (int k = 0; k < SG_ELECT_BATCH; ++k) other[k] = base + k < size ? l[base + k] : 2 * cand;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = SG_ABS(other[k]) == cand ? 0xFFFFFFFFu : sg_er_load(v, SG_ABS(other[k]));
+            for (int k = 0; k < SG_ELECT_BATCH; ++k) w[k] = SG_ABS(other[k]) == cand ? 0xFFFFFFFFu : sg_er_load(v, SG_ABS(other[k]));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < SG_ELECT_BATCH; ++k) {
                 if (w[k] == 0xFFFFFFFFu || SG_ER_RANK(w[k]) > rc) continue;
                 const uint32_t s = SG_ER_STAT(w[k]);
                 if (s == SG_E_UNDECIDED) blocked = true;
@@ -617,14 +620,14 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
             const sg_u4 h = v.hdr[q >= np ? dn[q - np] : dp[q]];
             if (h.z & SG_DELETED) continue;
             const uint32_t *l = v.lits + h.x;
-            for (int base = 0; base < (int)h.y; base += 8) {
-                uint32_t u[8], w[8];
+            for (int base = 0; base < (int)h.y; base += SG_ELECT_BATCH) {
+                uint32_t u[SG_ELECT_BATCH], w[SG_ELECT_BATCH];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) u[k] = base + k < (int)h.y ? SG_ABS(l[base + k]) : cand;
+                for (int k = 0; k < SG_ELECT_BATCH; ++k) u[k] = base + k < (int)h.y ? SG_ABS(l[base + k]) : cand;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[k] = u[k] == cand ? 0xFFFFFFFFu : sg_er_load(v, u[k]);
+                for (int k = 0; k < SG_ELECT_BATCH; ++k) w[k] = u[k] == cand ? 0xFFFFFFFFu : sg_er_load(v, u[k]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
+                for (int k = 0; k < SG_ELECT_BATCH; ++k)
                     if (w[k] != 0xFFFFFFFFu && SG_ER_STAT(w[k]) == SG_E_UNDECIDED && SG_ER_RANK(w[k]) > rc) sg_er_freeze(v, u[k], w[k]);
             }
         }

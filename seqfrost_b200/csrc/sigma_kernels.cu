@@ -508,8 +508,9 @@ template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND
     const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_NBH || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
                             KIND == SGK_ERE_SAFE || KIND == SGK_ERE_APPLY);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t i = warp_item ? (t >> 5) : t;
-    if (i >= n) return;
+    const uint32_t i0 = warp_item ? (t >> 5) : t;
+    if (i0 >= n) return;
+    const uint32_t i = v.item_base + i0;
     if (KIND == SGK_IDSORT) sg_idsort_item(v, i);
     else if (KIND == SGK_REDUCE) sg_reduce_item(v, i);
     else if (KIND == SGK_ELECT_PREP) sg_elect_prep_item(v, i + 1);

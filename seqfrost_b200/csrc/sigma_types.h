@@ -136,6 +136,7 @@ typedef struct SgView {
     uint32_t ubuf_cap;
     uint32_t pmax, nmax;     /* mu << multiplier (lcve.cpp:59-60) */
     uint32_t nbh_sort;       /* the fused per-variable kernel also sorts the two lists (sortOT) */
+    uint32_t item_base;      /* be_items processes items [item_base, item_base + n) */
     uint64_t model_base;     /* model words present before this VE stage */
     SgOpts   o;
 } SgView;

@@ -218,7 +218,8 @@ void be_acting_scatter(void *, const SgView &v, const uint32_t *fa, const uint32
 void be_items(void *, int kind, const SgView &v, uint32_t n)
 {
     g_launches++;
-    for (uint32_t i : item_order(n)) {
+    for (uint32_t i0 : item_order(n)) {
+        const uint32_t i = v.item_base + i0;
         switch (kind) {
         case SGK_IDSORT: sg_idsort_item(v, i); break;
         case SGK_REDUCE: sg_reduce_item(v, i); break;
