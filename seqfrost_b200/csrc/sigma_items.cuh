@@ -1785,9 +1785,14 @@ SG_HDN inline void sg_ere_pair(const SgView &v, const SgLane &L, uint32_t x, uin
  * position in the sequential order); a pair that holds all its claims is the earliest pending writer of each of
  * them, so the state it sees is the state it would see in the sequential run, and the pairs applied in one round
  * write disjoint clauses.  The earliest pending pair always qualifies, so the rounds terminate. */
+template <class F> SG_HD void sg_ere_pair_hits(const SgView &v, const SgLane &L, uint32_t eidx, uint32_t key, uint32_t *merged, F on_hit);
 template <class F> SG_HD void sg_ere_event_hits(const SgView &v, const SgLane &L, uint32_t k, uint32_t *merged, F on_hit)
 {
-    const uint32_t eidx = v.ubuf[k].eidx, key = v.ubuf[k].seq;
+    sg_ere_pair_hits(v, L, v.ubuf[k].eidx, v.ubuf[k].seq, merged, on_hit);
+}
+/* pair (key >> 16, key & 0xffff) of elected variable eidx: every clause of the resolvent's shortest list it subsumes NOW */
+template <class F> SG_HD void sg_ere_pair_hits(const SgView &v, const SgLane &L, uint32_t eidx, uint32_t key, uint32_t *merged, F on_hit)
+{
     const uint32_t x = v.elected[eidx];
     uint32_t dx, fx;
     if (!sg_ere_lists(v, x, dx, fx)) return;
@@ -1915,6 +1920,32 @@ SG_HDN inline void sg_ere_replay_serial(const SgView &v, uint32_t n_events, uint
         const uint32_t fl = sg_bcast(*(volatile uint8_t *)&v.ere_flags[e]);
         if (fl) sg_ere_replay_var(v, L, e, fl, ep, n_events, merged);
     }
+}
+
+/* Helper warps of the replay block: they walk the recorded pairs ahead of the replaying warp and evaluate them
+ * read-only (results discarded), which pulls the parents, the resolvent's shortest list and its candidates into
+ * L1/L2 - the replay itself is one long chain of dependent fetches.  No effect on the result. */
+SG_HDN inline void sg_ere_prefetch(const SgView &v, uint32_t n_events, uint32_t n_list, uint32_t helper, uint32_t n_helpers)
+{
+    const SgLane L = sg_lane_ctx();
+    uint32_t merged[SG_ERE_MAXLEN];
+    uint32_t hits = 0;
+    /* variables that are dirty from the start are replayed in full: all their pairs */
+    for (uint32_t li = helper; li < n_list; li += n_helpers) {
+        const uint32_t e = v.acting[li];
+        if (!(v.ere_flags[e] & 2u)) continue;
+        uint32_t dx, fx;
+        if (!sg_ere_lists(v, v.elected[e], dx, fx)) continue;
+        const uint32_t ds = v.ot_len[dx], fs = v.ot_len[fx];
+        if (ds > 0xffffu || fs > 0xffffu) continue;
+        for (uint32_t i = 0; i < ds; ++i)
+            for (uint32_t j = 0; j < fs; ++j) sg_ere_pair_hits(v, L, e, (i << 16) | j, merged, [&](uint32_t) { hits++; });
+    }
+    for (uint32_t k = helper; k < n_events; k += n_helpers) {
+        if (v.ere_done && v.ere_done[k] == 1u) continue;
+        sg_ere_event_hits(v, L, k, merged, [&](uint32_t) { hits++; });
+    }
+    if (hits == 0xFFFFFFFFu) v.ere_flags[0] |= 0x80u;      /* never true: keeps the loads alive */
 }
 
 /* ------------------------------------------------------------------------------------------ */

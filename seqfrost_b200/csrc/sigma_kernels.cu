@@ -537,8 +537,13 @@ template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND
 }
 
 __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
-{   /* launched with one warp; only the ERE replay uses more than lane 0 */
-    if (kind == SGS_ERE_REPLAY) { sg_ere_replay_serial(v, arg, arg2); return; }
+{   /* launched with one warp (only the ERE replay uses more than lane 0); the replay gets helper warps that prefetch */
+    if (kind == SGS_ERE_REPLAY) {
+        const uint32_t warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (warp == 0) sg_ere_replay_serial(v, arg, arg2);
+        else sg_ere_prefetch(v, arg, arg2, warp - 1, nw - 1);
+        return;
+    }
     if (threadIdx.x) return;
     if (kind == SGS_PROP) sg_prop_serial(v);
     else if (kind == SGS_MARKS) sg_marks_serial(v, arg);
@@ -1160,7 +1165,16 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     default: snprintf(g_err, sizeof g_err, "be_items: bad kind %d", kind);
     }
 }
-void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2) { LAUNCH(k_serial, 1, 32, s, v, kind, arg, arg2); }
+void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
+{
+    unsigned threads = 32;
+    if (kind == SGS_ERE_REPLAY) {
+        static int helpers = -1;
+        if (helpers < 0) { const char *e = getenv("SIGMA_ERE_HELPERS"); helpers = e ? atoi(e) : 15; if (helpers < 0) helpers = 0; if (helpers > 31) helpers = 31; }
+        threads = 32u * (1u + (unsigned)helpers);
+    }
+    LAUNCH(k_serial, 1, threads, s, v, kind, arg, arg2);
+}
 
 void be_sort_units(void *s, const SgView &v, uint32_t n)
 {
