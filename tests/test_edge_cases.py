@@ -146,15 +146,16 @@ def test_header_symbols_are_exported(cuda_lib):
 
 
 def test_ctypes_mirror_matches_the_header(tmp_path):
-    """sizeof of the three ABI structs as gcc sees them == the ctypes mirrors in seqfrost_b200/sigma.py."""
+    """sizeof of the five ABI structs as gcc sees them == the ctypes mirrors in seqfrost_b200/sigma.py."""
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "sigma_b200.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(sigma_opts), '
-                   'sizeof(sigma_formula), sizeof(sigma_report));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "sigma_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(sigma_opts), '
+                   'sizeof(sigma_formula), sizeof(sigma_report), sizeof(sigma_cnf), sizeof(sigma_cnf_out));return 0;}\n')
     exe = tmp_path / "sz"
     inc = os.path.join(os.path.dirname(GOLDEN), "..", "include")
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert got == [C.sizeof(sigma.SigmaOpts), C.sizeof(sigma.SigmaFormula), C.sizeof(sigma.SigmaReport)]
+    assert got == [C.sizeof(sigma.SigmaOpts), C.sizeof(sigma.SigmaFormula), C.sizeof(sigma.SigmaReport),
+                   C.sizeof(sigma.SigmaCnf), C.sizeof(sigma.SigmaCnfOut)]
 
 
 def _gapped(b: B.Boundary, pad=2):

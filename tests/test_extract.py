@@ -122,6 +122,24 @@ def test_download_cnf_reports_required_sizes(emul_lib):
     s.close()
 
 
+def test_emul_extract_of_an_empty_or_fully_deleted_database(emul_lib):
+    """extract() of nothing: no clauses, the pass has nothing to do, newBeginning() hands back an empty database."""
+    _, bi, _ = _load("fuzz_units4")
+    db, _, _ = _load("fuzz_units4")
+    dead = B.ClauseDb(cm=db.cm, orgs=db.orgs, learnts=db.learnts, stencil=np.ones(db.cm.size, np.uint8))
+    none = B.ClauseDb(cm=db.cm, orgs=np.zeros(0, np.uint64), learnts=np.zeros(0, np.uint64), stencil=np.zeros(0, np.uint8))
+    s = sigma.Sigma(0, emul_lib)
+    for d in (dead, none):
+        s.upload_cnf(d, bi)
+        assert s.extracted_sizes() == (0, 0, 0)
+        s.execute()
+        out = s.download()
+        assert out.refs.size == 0 and out.arena.size == 0
+        cdb, _ = s.download_cnf()
+        assert cdb.cm.size == 0 and cdb.orgs.size == 0 and cdb.learnts.size == 0 and cdb.lits_original == 0
+    s.close()
+
+
 def test_upload_cnf_argument_errors(emul_lib):
     db, bi, _ = _load("fuzz_units4")
     s = sigma.Sigma(0, emul_lib)
