@@ -1123,6 +1123,128 @@ static void ve_stage(sgo_ctx *c)
     }
 }
 
+/* ---- ERE: eager redundancy elimination (redundancy.cpp:24-123, redundancy.hpp:24-122) ------------------- */
+
+/* merge_ere, redundancy.hpp:26-122: resolvent of c1, c2 on x into out (no tautology), its signature and the literal
+ * with the shortest occurrence list; 0 = tautology or longer than maxlen (checked where the reference checks it) */
+static int merge_ere(const sgo_ctx *c, uint32_t x, uint32_t id1, uint32_t id2, int maxlen, uint32_t *out, uint32_t *sig, uint32_t *best)
+{
+    const uint32_t *d1 = cl_lits(c, id1), *e1 = d1 + c->c_size[id1];
+    const uint32_t *d2 = cl_lits(c, id2), *e2 = d2 + c->c_size[id2];
+    int n = 0;
+    uint32_t minsize = 0x7fffffffu;
+    *sig = 0; *best = 0;
+#define ERE_TAKE(L) do { const uint32_t l_ = (L); const uint32_t ls_ = c->ot_len[l_]; if (ls_ < minsize) { minsize = ls_; *best = l_; } \
+                         *sig |= MAPHASH(l_); out[n++] = l_; } while (0)
+    while (d1 != e1 && d2 != e2) {
+        if (n > maxlen) return 0;                                            /* redundancy.hpp:49-50 */
+        const uint32_t lit1 = *d1, lit2 = *d2, v1 = lit1 >> 1, v2 = lit2 >> 1;
+        if (v1 == x) d1++;
+        else if (v2 == x) d2++;
+        else if ((lit1 ^ lit2) == 1u) return 0;
+        else if (v1 < v2) { d1++; ERE_TAKE(lit1); }
+        else if (v2 < v1) { d2++; ERE_TAKE(lit2); }
+        else { d1++; d2++; ERE_TAKE(lit1); }
+    }
+    while (d1 != e1) { const uint32_t l = *d1++; if ((l >> 1) != x) ERE_TAKE(l); }
+    if (n > maxlen) return 0;
+    while (d2 != e2) { const uint32_t l = *d2++; if ((l >> 1) != x) ERE_TAKE(l); }
+#undef ERE_TAKE
+    return n > maxlen ? 0 : n;
+}
+
+/* Solver::ERE, redundancy.cpp:24-123 */
+static void ere_stage(sgo_ctx *c)
+{
+    if (!c->o.ere_en) return;
+    const int ereextend = c->o.ere_extend, maxoccurs = c->o.ere_max_occurs, maxsize = c->o.ere_clause_max;
+    uint32_t *merged = (uint32_t *)xrealloc(NULL, sizeof(uint32_t) * (size_t)(2 * (maxsize > 0 ? maxsize : 0) + 4096));
+    size_t merged_cap = (size_t)(2 * (maxsize > 0 ? maxsize : 0) + 4096);
+    for (uint32_t e = 0; e < c->n_elected; ++e) {
+        const uint32_t x = c->elected[e];
+        uint32_t dx = 2 * x, fx = dx | 1u;
+        if (c->ot_len[dx] > c->ot_len[fx]) { const uint32_t t = dx; dx = fx; fx = t; }
+        const int ds = (int)c->ot_len[dx], fs = (int)c->ot_len[fx];
+        if (!(ds && fs && ds <= maxoccurs && fs <= maxoccurs)) continue;
+        if (c->c_size[ol(c, dx)[0]] > maxsize || c->c_size[ol(c, fx)[0]] > maxsize) continue;   /* redundancy.cpp:50-51 */
+        for (int i = 0; i < ds; ++i) {
+            const uint32_t iref = ol(c, dx)[i];
+            if (cl_deleted(c, iref)) continue;
+            const int ciorg = cl_original(c, iref);
+            for (int j = 0; j < fs; ++j) {
+                const uint32_t jref = ol(c, fx)[j];
+                if (cl_deleted(c, jref)) continue;
+                const int cjorg = cl_original(c, jref);
+                const size_t need = (size_t)c->c_size[iref] + (size_t)c->c_size[jref] + 4;
+                if (need > merged_cap) { merged_cap = 2 * need; merged = (uint32_t *)xrealloc(merged, sizeof(uint32_t) * merged_cap); }
+                uint32_t sig, best;
+                const int len = merge_ere(c, x, iref, jref, maxsize, merged, &sig, &best);
+                if (len < 2) continue;
+                const int nm = (int)c->ot_len[best];
+                for (int m = 0; m < nm; ++m) {
+                    const uint32_t mref = ol(c, best)[m];
+                    if (mref == iref || mref == jref) continue;
+                    if (cl_deleted(c, mref)) continue;
+                    const int csize = c->c_size[mref];
+                    if (len <= csize && sig_sub(sig, c->c_sig[mref]) && lits_sub(merged, len, cl_lits(c, mref), csize)) {
+                        const int learnt = cl_learnt(c, mref), equal = len == csize;
+                        if (equal && (learnt || (ciorg && cjorg))) { cl_delete(c, mref); break; }     /* removeClause, solve.hpp:717 */
+                        else if (!equal && ereextend) {
+                            if (learnt && ereextend == 1) continue;
+                            memcpy(cl_lits(c, mref), merged, sizeof(uint32_t) * (size_t)len);            /* copyLitsFrom + resize: */
+                            c->c_size[mref] = len;                                                       /* the signature stays stale */
+                            if (learnt) bump_shrunken(c, mref);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    free(merged);
+}
+
+/* ---- BCE: blocked clause elimination (blocked.cpp:22-57) ---------------------------------------------------- */
+
+/* isTautology, simplify.hpp:159-179 */
+static int is_tautology(const sgo_ctx *c, uint32_t x, uint32_t id1, uint32_t id2)
+{
+    const uint32_t *a = cl_lits(c, id1), *b = cl_lits(c, id2);
+    const int n1 = c->c_size[id1], n2 = c->c_size[id2];
+    int i = 0, j = 0;
+    while (i < n1 && j < n2) {
+        const uint32_t l1 = a[i], l2 = b[j], v1 = l1 >> 1, v2 = l2 >> 1;
+        if (v1 == x) i++;
+        else if (v2 == x) j++;
+        else if ((l1 ^ l2) == 1u) return 1;
+        else if (v1 < v2) i++;
+        else if (v2 < v1) j++;
+        else { i++; j++; }
+    }
+    return 0;
+}
+
+/* Solver::BCE, blocked.cpp:22-57 */
+static void bce_stage(sgo_ctx *c)
+{
+    if (!c->o.bce_en) return;
+    for (uint32_t e = 0; e < c->n_elected; ++e) {
+        const uint32_t v = c->elected[e];
+        if (!v) continue;
+        const uint32_t p = 2 * v, n = p | 1u;
+        if ((int)c->ot_len[p] > c->o.bce_max_occurs || (int)c->ot_len[n] > c->o.bce_max_occurs) continue;
+        for (uint32_t i = 0; i < c->ot_len[n]; ++i) {
+            const uint32_t neg = ol(c, n)[i];
+            if (!cl_original(c, neg)) continue;
+            int all = 1;
+            for (uint32_t j = 0; j < c->ot_len[p]; ++j) {
+                const uint32_t pos = ol(c, p)[j];
+                if (cl_original(c, pos) && !is_tautology(c, v, neg, pos)) { all = 0; break; }
+            }
+            if (all) { save_clause(c, neg, n); cl_delete(c, neg); }                   /* model.saveClause(neg, size, n) */
+        }
+    }
+}
+
 /* countAll solve.hpp:661-671 */
 static void count_all(sgo_ctx *c, uint64_t *ncl, uint64_t *nli)
 {
@@ -1155,7 +1277,7 @@ static int run_pass(sgo_ctx *c)
         sort_ot(c);
         STOP_AFTER(SIGMA_T_SOT);
         if (c->phase == c->o.phases || (diff <= c->o.phase_lits_min && c->phase > 2)) {
-            if (c->o.ere_en) return SIGMA_E_UNSUPPORTED;                     /* ERE: deferred */
+            ere_stage(c);                                                    /* simplify.cpp:189 */
             break;
         }
         sub_stage(c);
@@ -1164,7 +1286,7 @@ static int run_pass(sgo_ctx *c)
         ve_stage(c);
         if (c->unsat) return SIGMA_UNSAT;
         STOP_AFTER(SIGMA_T_VE);
-        if (c->o.bce_en) return SIGMA_E_UNSUPPORTED;                         /* BCE: default off, deferred */
+        bce_stage(c);                                                        /* simplify.cpp:196 */
         uint64_t ncl, nli;
         count_all(c, &ncl, &nli);
         uint32_t j = 0;                                                      /* filterElected, solve.hpp:635-644 */
