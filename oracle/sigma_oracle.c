@@ -1311,6 +1311,68 @@ static int run_pass(sgo_ctx *c)
     return SIGMA_OK;
 }
 
+/* ---- hand-off stages ------------------------------------------------------------------------- */
+
+static int cmp_u32(const void *a, const void *b) { const uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b; return x < y ? -1 : x > y; }
+
+/* Solver::extract (simplify.cpp:118-133) over orgs then learnts (awaken(), simplify.cpp:146-148).  A CLAUSE record
+ * (clause.hpp:47-59) is 4 header buckets - byte 0 the flag bits, byte 1 _l, byte 2 _v, byte 3 _used; then _sz, _pos,
+ * _lbd - followed by the literals.  SCLAUSE(const CLAUSE&) (sclause.hpp:61-75): status LEARNT keeps lbd & MAX_LBD_M and
+ * usage, ORIGINAL zeroes both; calcSig (sclause.hpp:158-162); SORT = ascending literals (sort.hpp:44-52). */
+uint64_t sgo_extract(const sigma_cnf *cnf, uint32_t *arena, uint64_t *refs, uint64_t *n_buckets)
+{
+    uint64_t n = 0, pos = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const uint64_t *list = pass ? cnf->learnts : cnf->orgs;
+        const uint64_t cnt = pass ? cnf->n_learnts : cnf->n_orgs;
+        for (uint64_t i = 0; i < cnt; ++i) {
+            const uint64_t r = list[i];
+            if (r < cnf->stencil_size && cnf->stencil[r]) continue;          /* cm.deleted(ref), simplify.cpp:124 */
+            const uint32_t f = cnf->cm[r], size = cnf->cm[r + 1], lbd = cnf->cm[r + 3];
+            const int learnt = ((f >> 8) & 0xFFu) != 0;
+            const uint32_t used = (f >> 24) & 3u;
+            uint32_t *dst = arena + pos, sig = 0;
+            for (uint32_t k = 0; k < size; ++k) { const uint32_t l = cnf->cm[r + 4 + k]; dst[3 + k] = l; sig |= MAPHASH(l); }
+            qsort(dst + 3, size, sizeof(uint32_t), cmp_u32);
+            dst[0] = learnt ? (ST_LEARNT | (used << 4) | ((lbd & 0x03FFFFFFu) << 6)) : 0u;
+            dst[1] = sig;
+            dst[2] = size;
+            refs[n++] = pos;
+            pos += 3 + size;
+        }
+    }
+    *n_buckets = pos;
+    return n;
+}
+
+/* Solver::newBeginning with mapped == false (simplify.cpp:249-268): addClause(SCLAUSE&) (sclause.cpp:22-62) per clause
+ * in refs order - CLAUSE(size) constructor (clause.hpp:77-92: _k = 1, _b = size == 2, _pos = 2), learnt clauses take
+ * lbd / usage and lose `keep` when size > 2 and lbd > lbd_tier1 -, orgs / learnts, stats.literals, mark_ssubsume
+ * (sclause.hpp:209-215) for added clauses of later calls.  out->subsume (may be NULL) must be zeroed by the caller. */
+void sgo_new_beginning(const uint32_t *arena, const uint64_t *refs, uint64_t n_clauses, int lbd_tier1, int later_call,
+                       sigma_cnf_out *out)
+{
+    uint64_t pos = 0, no = 0, nl = 0, lo = 0, ll = 0;
+    for (uint64_t i = 0; i < n_clauses; ++i) {
+        const uint32_t *src = arena + refs[i];
+        const uint32_t w0 = src[0], size = src[2];
+        const int learnt = (w0 & ST_MASK) == ST_LEARNT;
+        const uint32_t lbd = w0 >> 6, used = (w0 >> 4) & 3u;
+        if (later_call && (w0 & F_ADDED) && out->subsume)
+            for (uint32_t k = 0; k < size; ++k) out->subsume[src[3 + k] >> 1] = 1;
+        uint32_t *dst = out->cm + pos;
+        const int keep = !(learnt && size > 2 && (int)lbd > lbd_tier1);
+        dst[0] = (keep ? 1u << 4 : 0u) | (size == 2 ? 1u << 5 : 0u) | (learnt ? 1u << 8 : 0u) | (learnt ? used << 24 : 0u);
+        dst[1] = size; dst[2] = 2u; dst[3] = learnt ? lbd : 0u;
+        memcpy(dst + 4, src + 3, sizeof(uint32_t) * size);
+        if (learnt) { out->learnts[nl++] = pos; ll += size; }
+        else { out->orgs[no++] = pos; lo += size; }
+        out->last_ref = pos;
+        pos += 4 + size;
+    }
+    out->cm_buckets = pos; out->n_orgs = no; out->n_learnts = nl; out->lits_original = lo; out->lits_learnt = ll;
+}
+
 /* ---- API ----------------------------------------------------------------------------------- */
 int sgo_create(sgo_ctx **out) { *out = (sgo_ctx *)xcalloc(1, sizeof(sgo_ctx)); (*out)->stop_phase = -1; return SIGMA_OK; }
 

@@ -8,7 +8,7 @@
  *
  * Parity pinning: the reference ships no golden vectors.  This port is pinned
  * against the UNMODIFIED reference compiled by oracle/Makefile (`make ref`, oracle/_ref/ref_sigma)
- * on seeded instances - tests/test_oracle_vs_reference.py - and against the fixtures generated
+ * on seeded instances - tests/test_oracle.py - and against the fixtures generated
  * from that binary and committed under tests/golden/ (tests/golden/make_golden.py).
  *
  * The entry points mirror include/sigma_b200.h one for one (sgo_* instead of sigma_*).
@@ -29,6 +29,13 @@ int  sgo_download(sgo_ctx *ctx, sigma_formula *out);
 int  sgo_get_report(sgo_ctx *ctx, sigma_report *rep);
 int  sgo_set_stop(sgo_ctx *ctx, int phase, int stage);
 int  sgo_snapshot(sgo_ctx *ctx, const char *name, void *dst, uint64_t cap_bytes, uint64_t *nbytes);
+/* the hand-off stages either side of the pass, stand-alone:
+ * extract(orgs); extract(learnts) of awaken() (simplify.cpp:118-133,146-148) into caller-sized arena / refs
+ * (upper bounds: cnf->cm_buckets buckets, n_orgs + n_learnts refs); returns the clause count */
+uint64_t sgo_extract(const sigma_cnf *cnf, uint32_t *arena, uint64_t *refs, uint64_t *n_buckets);
+/* newBeginning() without variable mapping (simplify.cpp:249-268, sclause.cpp:22-62) from a compacted SCNF */
+void sgo_new_beginning(const uint32_t *arena, const uint64_t *refs, uint64_t n_clauses, int lbd_tier1, int later_call,
+                       sigma_cnf_out *out);
 #ifdef __cplusplus
 }
 #endif

@@ -54,3 +54,38 @@ def run(b: B.Boundary, opts=None):
     out.unassigned, out.max_frozen, out.max_melted, out.propagated = g.unassigned, g.max_frozen, g.max_melted, g.propagated
     lib.sgo_destroy(ctx)
     return out, rep.as_dict()
+
+
+def extract(db: B.ClauseDb):
+    """oracle restatement of extract(orgs); extract(learnts): returns (arena, refs)."""
+    from seqfrost_b200.sigma import SigmaCnf
+    lib = C.CDLL(PORT_LIB)
+    cnf = SigmaCnf()
+    cnf.cm, cnf.cm_buckets = _ptr(db.cm), int(db.cm.size)
+    cnf.orgs, cnf.n_orgs = _ptr(db.orgs), int(db.orgs.size)
+    cnf.learnts, cnf.n_learnts = _ptr(db.learnts), int(db.learnts.size)
+    cnf.stencil, cnf.stencil_size = _ptr(db.stencil), int(db.stencil.size)
+    arena = np.zeros(int(db.cm.size) + 16, np.uint32)
+    refs = np.zeros(int(db.orgs.size + db.learnts.size) + 1, np.uint64)
+    nb = C.c_uint64()
+    lib.sgo_extract.restype = C.c_uint64
+    lib.sgo_extract.argtypes = [C.POINTER(SigmaCnf), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    n = lib.sgo_extract(C.byref(cnf), _ptr(arena), _ptr(refs), C.byref(nb))
+    return arena[:nb.value].copy(), refs[:n].copy()
+
+
+def new_beginning(b: B.Boundary, lbd_tier1=2):
+    """oracle restatement of newBeginning() without mapping: returns a ClauseDb (subsume_after = mark_ssubsume bytes)."""
+    from seqfrost_b200.sigma import SigmaCnfOut
+    lib = C.CDLL(PORT_LIB)
+    n = int(b.refs.size)
+    db = B.ClauseDb(cm=np.zeros(int(b.arena.size) + n + 16, np.uint32), orgs=np.zeros(n + 1, np.uint64), learnts=np.zeros(n + 1, np.uint64))
+    db.subsume_after = np.zeros(b.nvars + 1, np.uint8)
+    co = SigmaCnfOut()
+    co.cm, co.orgs, co.learnts, co.subsume = _ptr(db.cm), _ptr(db.orgs), _ptr(db.learnts), _ptr(db.subsume_after)
+    lib.sgo_new_beginning.restype = None
+    lib.sgo_new_beginning.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(SigmaCnfOut)]
+    lib.sgo_new_beginning(_ptr(b.arena), _ptr(b.refs), n, lbd_tier1, int(b.simplify_calls > 1), C.byref(co))
+    db.cm, db.orgs, db.learnts = db.cm[:co.cm_buckets].copy(), db.orgs[:co.n_orgs].copy(), db.learnts[:co.n_learnts].copy()
+    db.lits_original, db.lits_learnt = int(co.lits_original), int(co.lits_learnt)
+    return db
