@@ -81,8 +81,8 @@ void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32
  * learnt[i] = 0/1 first; then, with its exclusive scan, the records (clause i at bucket refs[i] + i), the two ref lists,
  * counts[0] / counts[1] = literals of original / learnt clauses and, when subsume != NULL, the mark_ssubsume bytes */
 void be_cm_flags(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *learnt);
-void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *learnt_before, int lbd_tier1,
-                 uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume);
+void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, const uint32_t *learnt_before,
+                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume);
 /* ERE proposal pass: filt[2c] = size of clause c (0 when deleted), filt[2c+1] = its signature */
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt);
 /* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */

@@ -39,6 +39,35 @@ inline unsigned blocks_for(uint64_t n, int tpb = TPB) { return (unsigned)((n + t
 /* ---------------------------------------------------------------------------------------------- */
 /* ingest                                                                                           */
 /* ---------------------------------------------------------------------------------------------- */
+/* Bulk (TMA) store of a staged tile: shared memory -> global, both 16-byte aligned, `bytes` a multiple of 16.
+ * Issued by one thread; the staged words were written through the generic proxy, hence the proxy fence (executed by
+ * every writer before the barrier that precedes this call). */
+__device__ __forceinline__ void stage_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+/* A contiguous run of W output words starting at global word `g0` of `out`, staged in `stage` at index (g0 & 3) so that
+ * shared and global addresses agree modulo 16 bytes: the aligned body goes out as one bulk store, the up-to-3-word head
+ * and tail as plain stores.  Called by the whole block after the barrier that follows the staging writes. */
+__device__ __forceinline__ void flush_staged(uint32_t *out, unsigned long long g0, const uint32_t *stage, uint32_t W)
+{
+    const uint32_t shift = (uint32_t)(g0 & 3ull);
+    uint32_t head = (4u - shift) & 3u;
+    if (head > W) head = W;
+    const uint32_t body = (W - head) & ~3u, tail = W - head - body;
+    if (threadIdx.x == 0 && body) bulk_store(out + g0 + head, stage + shift + head, body * 4u);
+    if (threadIdx.x >= 32 && threadIdx.x - 32 < head) out[g0 + (threadIdx.x - 32)] = stage[shift + (threadIdx.x - 32)];
+    if (threadIdx.x >= 64 && threadIdx.x - 64 < tail) out[g0 + head + body + (threadIdx.x - 64)] = stage[shift + head + body + (threadIdx.x - 64)];
+    if (threadIdx.x == 0 && body) bulk_store_wait();
+}
+
+constexpr uint32_t EX_CAP = 6144;      /* staging words per 256-clause tile (24 KB); larger tiles write directly */
+
 __global__ void k_extract_sizes(const uint32_t *__restrict__ cm, const uint64_t *__restrict__ crefs, uint32_t n,
                                 const uint8_t *__restrict__ stencil, uint64_t stencil_size, uint32_t *__restrict__ sizes,
                                 uint32_t *__restrict__ live)
@@ -50,16 +79,30 @@ __global__ void k_extract_sizes(const uint32_t *__restrict__ cm, const uint64_t 
     live[i] = sz != 0;
 }
 
-__global__ void k_extract_write(const uint32_t *__restrict__ cm, const uint64_t *__restrict__ crefs, uint32_t n,
+__global__ void __launch_bounds__(TPB) k_extract_write(const uint32_t *__restrict__ cm, const uint64_t *__restrict__ crefs, uint32_t n,
                                 const uint32_t *__restrict__ sizes, const uint32_t *__restrict__ newoff,
                                 const uint32_t *__restrict__ newid, uint32_t *__restrict__ arena,
                                 unsigned long long *__restrict__ refs)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !sizes[i]) return;
-    const uint32_t off = newoff[i];
-    refs[newid[i]] = off;
-    sg_extract_write(cm, crefs[i], arena + off);
+    /* the SCLAUSE records of a block's 256 source clauses are one contiguous run of the arena: assembled (and their
+     * literals sorted) in shared memory, written out with one bulk store */
+    __shared__ __align__(128) uint32_t stage[EX_CAP + 4];
+    const uint32_t i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x;
+    const uint32_t next = i0 + blockDim.x < n ? i0 + blockDim.x : n;
+    const unsigned long long g0 = newoff[i0];
+    const uint32_t end = next < n ? newoff[next] : newoff[n - 1] + sizes[n - 1];
+    const uint32_t W = end - (uint32_t)g0;
+    const bool staged = W <= EX_CAP;
+    if (i < n && sizes[i]) {
+        const uint32_t off = newoff[i];
+        refs[newid[i]] = off;
+        sg_extract_write(cm, crefs[i], staged ? stage + (uint32_t)(g0 & 3ull) + (off - (uint32_t)g0) : arena + off);
+    }
+    if (staged) {
+        stage_fence();
+        __syncthreads();
+        if (W) flush_staged(arena, g0, stage, W);
+    }
 }
 
 __global__ void k_cm_flags(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
@@ -69,23 +112,35 @@ __global__ void k_cm_flags(const uint32_t *__restrict__ arena, const unsigned lo
     if (i < n) learnt[i] = (arena[refs[i]] & SG_ST_MASK) == SG_LEARNT;
 }
 
-__global__ void k_cm_write(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
+__global__ void __launch_bounds__(TPB) k_cm_write(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
                            const uint32_t *__restrict__ learnt_before, int lbd_tier1, uint32_t *__restrict__ cm,
                            unsigned long long *__restrict__ orgs, unsigned long long *__restrict__ learnts,
-                           unsigned long long *__restrict__ counts, uint8_t *__restrict__ subsume)
+                           unsigned long long *__restrict__ counts, uint8_t *__restrict__ subsume, unsigned long long cm_total)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    /* the CLAUSE records of 256 consecutive clauses are one contiguous run of `cm`: staged, one bulk store */
+    __shared__ __align__(128) uint32_t stage[EX_CAP + 4];
+    const uint32_t i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x;
+    const uint32_t next = i0 + blockDim.x < n ? i0 + blockDim.x : n;
+    const unsigned long long g0 = refs[i0] + i0;
+    const unsigned long long end = next < n ? refs[next] + next : cm_total;
+    const uint32_t W = (uint32_t)(end - g0);
+    const bool staged = end - g0 <= EX_CAP;
     uint32_t lo = 0, ll = 0;
     if (i < n) {
         const unsigned long long r = refs[i];
         const uint32_t *src = arena + r;
         const uint32_t w0 = src[0], size = src[2];
-        sg_cm_write(src, cm + r + i, lbd_tier1);
+        sg_cm_write(src, staged ? stage + (uint32_t)(g0 & 3ull) + (uint32_t)(r + i - g0) : cm + r + i, lbd_tier1);
         const uint32_t lb = learnt_before[i];
         if ((w0 & SG_ST_MASK) == SG_LEARNT) { learnts[lb] = r + i; ll = size; }
         else { orgs[i - lb] = r + i; lo = size; }
         if (subsume && (w0 & SG_ADDED))
             for (uint32_t k = 0; k < size; ++k) subsume[SG_ABS(src[3 + k])] = 1;
+    }
+    if (staged) {
+        stage_fence();
+        __syncthreads();
+        if (W) flush_staged(cm, g0, stage, W);
     }
     /* literal totals (stats.literals.original / learnt): one atomic per warp */
     for (int d = 16; d; d >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, d); ll += __shfl_xor_sync(0xffffffffu, ll, d); }
@@ -775,6 +830,49 @@ __global__ void k_live_apply(SgView v, const uint2 *__restrict__ part, uint4 *__
     }
 }
 
+/* final shrinkSimp + export: like k_live_apply<true>, but every 256-clause sub-tile is assembled in shared memory (its
+ * output is one contiguous run of the arena) and leaves as one bulk store instead of eight 4-byte stores per thread
+ * at a 32-byte stride.  Sub-tiles whose output exceeds the staging buffer (long clauses) write directly. */
+__global__ void __launch_bounds__(TPB) k_export_staged(SgView v, const uint2 *__restrict__ part, uint32_t *__restrict__ arena,
+                                                       unsigned long long *__restrict__ refs)
+{
+    __shared__ __align__(128) uint32_t stage[EX_CAP + 4];
+    __shared__ uint2 tot;
+    const uint2 b = part[blockIdx.x];
+    uint32_t id0 = b.x, off0 = b.y;
+    uint4 hs[CP_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+        const uint64_t c = (uint64_t)blockIdx.x * CP_TILE + (uint64_t)k * TPB + threadIdx.x;
+        hs[k] = c < v.n_cls ? v.hdr[c] : make_uint4(0, 0, SG_DELETED, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+        const uint4 h = hs[k];
+        const bool live = !(h.z & SG_DELETED);
+        const uint2 e = cp_block_scan(live ? 1u : 0u, live ? h.y : 0u, &tot);
+        const unsigned long long g0 = 3ull * id0 + off0;             /* first arena word of this sub-tile */
+        const uint32_t W = 3u * tot.x + tot.y;
+        const bool staged = W <= EX_CAP;
+        if (live) {
+            const uint32_t id = id0 + e.x;
+            const unsigned long long r = 3ull * id + off0 + e.y;
+            refs[id] = r;
+            uint32_t *d = staged ? stage + (uint32_t)(g0 & 3ull) + (uint32_t)(r - g0) : arena + r;
+            d[0] = h.z; d[1] = h.w; d[2] = h.y;
+            const uint32_t *src = v.lits + h.x;
+            for (uint32_t q = 0; q < h.y; ++q) d[3 + q] = src[q];
+        }
+        if (staged) {
+            stage_fence();
+            __syncthreads();
+            if (W) flush_staged(arena, g0, stage, W);
+        }
+        id0 += tot.x; off0 += tot.y;
+        __syncthreads();
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* incremental occurrence-table update (see sigma_backend.h): only the lists that changed are touched  */
 /* ---------------------------------------------------------------------------------------------- */
@@ -1012,12 +1110,12 @@ void be_cm_flags(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
 {
     if (n) LAUNCH(k_cm_flags, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt);
 }
-void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *learnt_before, int lbd_tier1,
-                 uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
+void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, const uint32_t *learnt_before,
+                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
 {
     cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ST(s));
     if (n) LAUNCH(k_cm_write, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt_before, lbd_tier1, cm,
-                  (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume);
+                  (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume, (unsigned long long)(n_buckets + n));
 }
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt)
 {
@@ -1232,7 +1330,11 @@ void be_compact_apply(void *s, const SgView &v, const uint32_t *tmp, sg_u4 *hdr2
 void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *arena, uint64_t *refs)
 {
     const uint32_t nb = (v.n_cls + CP_TILE - 1) / CP_TILE;
-    if (nb) LAUNCH(k_live_apply<true>, nb, TPB, s, v, (const uint2 *)tmp, (uint4 *)nullptr, (uint32_t *)nullptr, arena, (unsigned long long *)refs);
+    static int staged = -1;
+    if (staged < 0) { const char *e = getenv("SIGMA_EXPORT_STAGED"); staged = e ? atoi(e) : 1; }
+    if (!nb) return;
+    if (staged) LAUNCH(k_export_staged, nb, TPB, s, v, (const uint2 *)tmp, arena, (unsigned long long *)refs);
+    else LAUNCH(k_live_apply<true>, nb, TPB, s, v, (const uint2 *)tmp, (uint4 *)nullptr, (uint32_t *)nullptr, arena, (unsigned long long *)refs);
 }
 
 size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls) { (void)n_cls; return 3 * (size_t)nlit + 64; }

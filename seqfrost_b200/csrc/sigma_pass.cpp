@@ -1048,7 +1048,7 @@ int build_cm(sigma_ctx *c)
     be_cm_flags(c->stream, c->arena_out.p, c->refs_out.p, n, c->c_flags.p);
     be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
     unsigned long long *counts = (unsigned long long *)(c->totals.p + 2);
-    be_cm_write(c->stream, c->arena_out.p, c->refs_out.p, n, c->c_newid.p, c->opts.lbd_tier1, c->cm_out.p, c->orgs_out.p,
+    be_cm_write(c->stream, c->arena_out.p, c->refs_out.p, n, c->out_buckets, c->c_newid.p, c->opts.lbd_tier1, c->cm_out.p, c->orgs_out.p,
                 c->learnts_out.p, counts, c->in_calls > 1 ? c->subsume_out.p : nullptr);        /* sclause.cpp:29-31 */
     be_event_record(c->stream, e1);
     if (n) be_copy_words(c->stream, c->h_totals + 8, c->refs_out.p + (n - 1), 8);

@@ -77,8 +77,8 @@ void be_cm_flags(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n
     g_launches++;
     for (uint32_t i : item_order(n)) learnt[i] = (arena[refs[i]] & SG_ST_MASK) == SG_LEARNT;
 }
-void be_cm_write(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *learnt_before, int lbd_tier1,
-                 uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
+void be_cm_write(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t, const uint32_t *learnt_before,
+                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
 {
     g_launches++;
     counts[0] = counts[1] = 0;
