@@ -85,6 +85,8 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
                  int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume);
 /* ERE proposal pass: filt[2c] = size of clause c (0 when deleted), filt[2c+1] = its signature */
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt);
+/* createOT: every list of the freshly built (packed) table into ascending clause id order (simplify.cpp:50-58) */
+void be_ot_order(void *s, const SgView &v);
 /* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */
 void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp);
 size_t be_scan_tmp_words(uint32_t n);

@@ -873,6 +873,36 @@ __global__ void __launch_bounds__(TPB) k_export_staged(SgView v, const uint2 *__
     }
 }
 
+/* createOT order fix, staged: right after the build the lists are packed in literal order, so the lists of 256 consecutive
+ * literals are one contiguous run of ot_data.  The run is loaded into shared memory with coalesced loads, every thread
+ * sorts its own list there (ascending clause id = the reference's push order), and the run goes back with one bulk store.
+ * Runs larger than the staging buffer fall back to sorting in global memory. */
+__global__ void __launch_bounds__(TPB) k_ot_order_staged(SgView v)
+{
+    __shared__ __align__(128) uint32_t stage[EX_CAP + 4];
+    const uint32_t l0 = blockIdx.x * blockDim.x, lit = l0 + threadIdx.x;
+    const uint32_t lend = l0 + blockDim.x < v.nlit ? l0 + blockDim.x : v.nlit;
+    const uint32_t g0 = v.ot_off[l0], g1 = lend < v.nlit ? v.ot_off[lend] : v.ot_off[v.nlit - 1] + v.ot_len[v.nlit - 1];
+    const uint32_t W = g1 - g0, shift = g0 & 3u;
+    if (W > EX_CAP) { if (lit < v.nlit) sg_idsort_item(v, lit); return; }
+    for (uint32_t k = threadIdx.x; k < W; k += blockDim.x) stage[shift + k] = v.ot_data[g0 + k];
+    __syncthreads();
+    bool changed = false;
+    if (lit < v.nlit) {
+        const int n = (int)v.ot_len[lit];
+        uint32_t *d = stage + shift + (v.ot_off[lit] - g0);
+        for (int i = 1; i < n; ++i) {
+            const uint32_t t = d[i];
+            int j = i;
+            while (j > 0 && d[j - 1] > t) { d[j] = d[j - 1]; --j; }
+            if (j != i) { d[j] = t; changed = true; }
+        }
+    }
+    stage_fence();
+    if (!__syncthreads_or(changed)) return;                             /* already in order: nothing to write */
+    flush_staged(v.ot_data, g0, stage, W);
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* incremental occurrence-table update (see sigma_backend.h): only the lists that changed are touched  */
 /* ---------------------------------------------------------------------------------------------- */
@@ -1120,6 +1150,10 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt)
 {
     if (v.n_cls) LAUNCH(k_ere_filt, blocks_for(v.n_cls), TPB, s, v, (uint2 *)filt);
+}
+void be_ot_order(void *s, const SgView &v)
+{
+    if (v.nlit) LAUNCH(k_ot_order_staged, blocks_for(v.nlit), TPB, s, v);
 }
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {

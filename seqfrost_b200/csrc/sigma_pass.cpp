@@ -258,7 +258,7 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls, bool tr
     }
     {
         Stage st(c, SIGMA_T_OT_ORDER, 8 * live_lits + 8ull * nlit);
-        be_items(c->stream, SGK_IDSORT, v, nlit);
+        be_ot_order(c->stream, v);
     }
     (void)live_cls;
     if (track && c->ot_incremental) {

@@ -97,6 +97,11 @@ void be_ere_filt(void *, const SgView &v, uint32_t *filt)
     g_launches++;
     for (uint32_t c = 0; c < v.n_cls; ++c) { filt[2 * c] = (v.hdr[c].z & SG_DELETED) ? 0u : v.hdr[c].y; filt[2 * c + 1] = v.hdr[c].w; }
 }
+void be_ot_order(void *, const SgView &v)
+{
+    g_launches++;
+    for (uint32_t lit : item_order(v.nlit)) sg_idsort_item(v, lit);
+}
 void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
     g_launches++;
