@@ -109,7 +109,7 @@ struct SgOtUpdate {
     uint32_t first_new;         /* first clause id that has no entry in the table */
     uint32_t n_add;             /* pairs in v.ot_add */
     uint32_t n_elected;         /* entries of v.elected from the previous phase */
-    uint32_t *tmp, *total, *bump;
+    uint32_t *tmp, *total, *bump;  /* total: words the growing lists need (NULL = not wanted); bump: end of the table, advanced */
 };
 size_t be_ot_update_tmp_words(uint32_t nlit, uint32_t n_cls);
 size_t be_ot_bits_words(uint32_t n_cls);

@@ -1186,8 +1186,8 @@ void be_hist(void *s, const SgView &v, uint32_t *counts)
 void be_scatter(void *s, const SgView &v, uint32_t *cursor)
 {
     if (!v.n_cls) return;
-    static long l2_mb = -1;
-    static int stream_in = -1;
+    long l2_mb = -1;               /* knobs are read per call: tests flip them inside one process */
+    int stream_in = -1;
     if (l2_mb < 0) { const char *e = getenv("SIGMA_SCATTER_L2_MB"); l2_mb = e ? atol(e) : 64; if (l2_mb < 1) l2_mb = 1; }
     if (stream_in < 0) { const char *e = getenv("SIGMA_SCATTER_CS"); stream_in = e ? atoi(e) : 0; }
     const uint64_t bytes = 4ull * v.pool_used;
@@ -1301,7 +1301,7 @@ void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
 {
     unsigned threads = 32;
     if (kind == SGS_ERE_REPLAY) {
-        static int helpers = -1;
+        int helpers = -1;
         if (helpers < 0) { const char *e = getenv("SIGMA_ERE_HELPERS"); helpers = e ? atoi(e) : 15; if (helpers < 0) helpers = 0; if (helpers > 31) helpers = 31; }
         threads = 32u * (1u + (unsigned)helpers);
     }
@@ -1364,7 +1364,7 @@ void be_compact_apply(void *s, const SgView &v, const uint32_t *tmp, sg_u4 *hdr2
 void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *arena, uint64_t *refs)
 {
     const uint32_t nb = (v.n_cls + CP_TILE - 1) / CP_TILE;
-    static int staged = -1;
+    int staged = -1;
     if (staged < 0) { const char *e = getenv("SIGMA_EXPORT_STAGED"); staged = e ? atoi(e) : 1; }
     if (!nb) return;
     if (staged) LAUNCH(k_export_staged, nb, TPB, s, v, (const uint2 *)tmp, arena, (unsigned long long *)refs);
@@ -1382,11 +1382,11 @@ void be_ot_update_plan(void *s, const SgView &v, const SgOtUpdate &u)
     const OtuTmp t = otu_layout(u.tmp, v.nlit);
     cudaMemsetAsync(t.addc, 0, (size_t)v.nlit * 4, ST(s));
     cudaMemsetAsync(t.flag, 0, (size_t)v.nlit * 4, ST(s));
-    cudaMemsetAsync(u.total, 0, 4, ST(s));
+    if (u.total) cudaMemsetAsync(u.total, 0, 4, ST(s));
     LAUNCH(k_otu_mark, blocks_for(((uint64_t)v.n_cls / 128 + 1) * 32), TPB, s, v, u.bits, u.first_new, t.addc, t.flag);
     if (u.n_add) LAUNCH(k_otu_pairs_count, blocks_for(u.n_add), TPB, s, v, u.n_add, t.addc, t.flag);
     if (u.n_elected) LAUNCH(k_otu_elected, blocks_for(u.n_elected), TPB, s, v, u.n_elected, t.flag);
-    LAUNCH(k_otu_need, blocks_for(v.nlit), TPB, s, v, t.addc, u.total);
+    if (u.total) LAUNCH(k_otu_need, blocks_for(v.nlit), TPB, s, v, t.addc, u.total);
 }
 void be_ot_update(void *s, const SgView &v, const SgOtUpdate &u)
 {

@@ -72,6 +72,8 @@ struct sigma_ctx {
     uint64_t phase_add_lits = 0;     /* literals of the resolvents the latest VE stage added */
     uint32_t last_elected = 0;       /* size of `elected` after the latest election (hsc.n_elected does not survive a pull) */
     uint64_t ot_end = 0;             /* words of ot_data in use (the updated table is not packed) */
+    uint32_t prev_max_score = 0; bool prev_max_valid = false;   /* largest score of the previous election of this pass */
+    bool ot_end_stale = false;       /* the device-side end (totals[13]) has moved since ot_end was read */
     bool ot_valid = false, ot_incremental = true, ot_verify = false;
     int nbh_fused = 0;               /* 0: separate sortOT / SUB / BVE kernels; 1: fused per variable; 2: fused SUB + BVE only */
     uint32_t ot_first_new = 0;
@@ -266,7 +268,9 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls, bool tr
         NOMEM(c->otbits.ensure(be_ot_bits_words(c->n_cls) + 64));
         Stage st(c, SIGMA_T_OT_UPDATE, 16ull * c->n_cls);
         be_ot_bitmap(c->stream, v, c->otbits.p);
-        c->ot_end = live_lits;
+        c->ot_end = live_lits; c->ot_end_stale = false;
+        c->h_totals[13] = (uint32_t)live_lits;             /* device-side end of the table (bump allocator of the updates) */
+        be_copy_words(c->stream, c->totals.p + 13, c->h_totals + 13, 4);
     }
     return SIGMA_OK;
 }
@@ -287,17 +291,33 @@ int stage_update_ot(sigma_ctx *c, uint64_t live_lits)
     {
         Stage st(c, SIGMA_T_OT_UPDATE, 16ull * c->n_cls + 12ull * nlit);
         SgView v = make_view(c);
+        if (c->ot_end_stale) {                             /* cannot happen in the phase loop (an election lies between two updates) */
+            CK(pull_totals(c, 14));
+            c->ot_end = c->h_totals[13]; c->ot_end_stale = false;
+        }
+        /* Room for the lists that grow (they move to the end of ot_data).  Their exact total is known on the device only;
+         * a bound is known here: the moved lists are disjoint parts of the ot_end words in use, plus the entries added.
+         * Sizing from the bound saves the round trip; the exact path remains for tables near the 32-bit limit. */
+        const uint64_t bound = c->ot_end + c->phase_add_lits + c->hsc.n_ot_add;
+        const char *ex = getenv("SIGMA_OT_EXACT_NEED");
+        const bool exact = (ex && ex[0] == '1') || c->ot_end + bound >= 0xFFFFFFF0ull;
+        if (!exact) u.total = nullptr;                     /* the plan skips the exact count */
         be_ot_update_plan(c->stream, v, u);
-        CK(pull_totals(c, 13));
-        const uint32_t need = c->h_totals[12];
-        if (c->ot_end + need >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "occurrence table exceeds 32-bit offsets");
-        NOMEM(c->ot_data.ensure((size_t)c->ot_end + need + 16, c->stream, (size_t)c->ot_end));
-        c->h_totals[13] = (uint32_t)c->ot_end;
-        be_copy_words(c->stream, c->totals.p + 13, c->h_totals + 13, 4);
-        v = make_view(c);
-        be_ot_update(c->stream, v, u);
-        c->rep.stage_bytes[SIGMA_T_OT_UPDATE] += 8ull * need;
-        c->ot_end += need;                     /* h_totals[13] is not written again before the next round trip */
+        if (exact) {
+            CK(pull_totals(c, 13));
+            const uint32_t need = c->h_totals[12];
+            if (c->ot_end + need >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "occurrence table exceeds 32-bit offsets");
+            NOMEM(c->ot_data.ensure((size_t)c->ot_end + need + 16, c->stream, (size_t)c->ot_end));
+            v = make_view(c);
+            be_ot_update(c->stream, v, u);
+            c->rep.stage_bytes[SIGMA_T_OT_UPDATE] += 8ull * need;
+            c->ot_end += need;                             /* the device-side bump advanced by the same amount */
+        } else {
+            NOMEM(c->ot_data.ensure((size_t)(c->ot_end + bound) + 16, c->stream, (size_t)c->ot_end));
+            v = make_view(c);
+            be_ot_update(c->stream, v, u);
+            c->ot_end_stale = true;                        /* the new end comes back with the election's totals */
+        }
     }
     if (c->ot_verify) {
         /* test hook: rebuild from scratch into the spare buffers and compare list by list */
@@ -339,6 +359,23 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
     SgView v = make_view(c);
     v.pmax = (uint32_t)c->opts.mu_pos << multiplier;
     v.nmax = (uint32_t)c->opts.mu_neg << multiplier;
+    /* election scalars first (the host mirror is current here: nothing since the last pull wrote a scalar), so that the
+     * largest score, which the ordering kernels leave in the scalars, survives until the election's pull */
+    c->hsc.brk_rank = 0xFFFFFFFFu; c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
+    c->hsc.n_acting = c->hsc.n_ponly = c->hsc.n_elected = 0;
+    c->hsc.n_ot_add = 0;
+    CK(push_scalars(c));
+    /* radix key width = top bit of the largest score.  From the second election of a pass on it is guessed from the
+     * previous phase's largest score (x4) instead of fetched - one round trip less -, and checked when the election's
+     * result comes back; a wrong guess (never seen so far) repeats ordering + election with the exact width */
+    uint32_t key_bits = 8;
+    bool guessed = false;
+    bool force_narrow = false;                             /* SIGMA_VO_GUESS=8 (tests): always guess 8 bits, so the repeat path runs */
+    { const char *e = getenv("SIGMA_VO_GUESS"); guessed = c->prev_max_valid && !(e && e[0] == '0'); force_narrow = e && e[0] == '8'; }
+    if (force_narrow) guessed = true;
+    else if (guessed) while (key_bits < 32 && ((4ull * c->prev_max_score + 1023) >> key_bits)) key_bits += 8;
+    uint32_t rounds = 0;
+again:
     {
         Stage st(c, SIGMA_T_VO, 8ull * V + 4 * 16ull * V);
         if (ot_is_hist) be_d2d(c->stream, c->occ.p, c->ot_len.p, nlit * sizeof(uint32_t));
@@ -347,19 +384,17 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
             be_hist(c->stream, v, c->occ.p);                 /* histCNF (histogram.cpp:84-97) */
         }
         be_scores(c->stream, v);
-        CK(pull_scalars(c));
-        uint32_t key_bits = 8;                             /* digit passes that can differ: up to the top bit of the largest score */
-        while (key_bits < 32 && (c->hsc.max_score >> key_bits)) key_bits += 8;
+        if (!guessed) {
+            CK(pull_scalars(c));
+            key_bits = 8;                                  /* digit passes that can differ: up to the top bit of the largest score */
+            while (key_bits < 32 && (c->hsc.max_score >> key_bits)) key_bits += 8;
+        }
         be_sort_pairs(c->stream, c->scores.p + 1, c->order.p, V, c->tmpk.p, c->tmpv.p, c->sorttmp.p, key_bits);
         be_rank(c->stream, v);
     }
-    uint32_t rounds = 0;
+    rounds = 0;
     {
         Stage st(c, SIGMA_T_ELECT);
-        c->hsc.brk_rank = 0xFFFFFFFFu; c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
-        c->hsc.n_acting = c->hsc.n_ponly = c->hsc.n_elected = 0;
-        c->hsc.n_ot_add = 0;
-        CK(push_scalars(c));
         be_items(c->stream, SGK_ELECT_PREP, v, V);
         /* rank-ordered batches of geometrically growing size: inside a batch, pull rounds until every
          * candidate is decided; acting candidates push FROZEN onto their undecided neighbours, so the
@@ -410,7 +445,20 @@ int stage_lcve(sigma_ctx *c, int phase, uint32_t multiplier, bool ot_is_hist, bo
         be_scan_u32(c->stream, c->flags.p, c->pos.p, V, c->totals.p, c->scantmp.p);
         be_scan_u32(c->stream, c->flags.p + V, c->pos.p + V, V, c->totals.p + 1, c->scantmp.p);
         be_acting_scatter(c->stream, v, c->flags.p, c->pos.p, c->flags.p + V, c->pos.p + V);
-        CK(pull_both(c, 2));
+        CK(pull_both(c, 14));
+        if (c->ot_end_stale) {
+            c->rep.stage_bytes[SIGMA_T_OT_UPDATE] += 8ull * (c->h_totals[13] - c->ot_end);
+            c->ot_end = c->h_totals[13]; c->ot_end_stale = false;
+        }
+        if (guessed && key_bits < 32 && (c->hsc.max_score >> key_bits)) {
+            /* the guess was too narrow: the order is wrong.  Everything above is recomputed from the store */
+            guessed = false;
+            c->hsc.brk_rank = 0xFFFFFFFFu; c->hsc.wl_count[0] = c->hsc.wl_count[1] = 0;
+            c->hsc.n_acting = c->hsc.n_ponly = c->hsc.n_elected = 0;
+            CK(push_scalars(c));
+            goto again;
+        }
+        c->prev_max_score = c->hsc.max_score; c->prev_max_valid = true;
         if (persistent) rounds = c->hsc.wl_count[0];
         c->hsc.n_acting = c->h_totals[0]; c->hsc.n_elected = c->h_totals[1];
         c->last_elected = c->h_totals[1];
@@ -594,7 +642,7 @@ int stage_ere(sigma_ctx *c)
     CK(pull_totals(c, 1));
     const uint32_t n_items = c->h_totals[0];
     if (n_items) {
-        static int use_filt = -1;
+        int use_filt = -1;
         if (use_filt < 0) { const char *e = getenv("SIGMA_ERE_FILT"); use_filt = e ? atoi(e) : 1; }
         if (use_filt) {
             NOMEM(c->ere_filt.ensure(2 * (size_t)c->n_cls + 16));
@@ -977,7 +1025,7 @@ int sigma_execute(sigma_ctx *c)
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
     { const char *e = getenv("SIGMA_NBH_FUSED"); c->nbh_fused = e ? atoi(e) : 0; }
     c->launches0 = be_launch_count();
-    c->n_syncs = 0; c->count_fresh = false; c->push_in_flight = false;
+    c->n_syncs = 0; c->count_fresh = false; c->push_in_flight = false; c->prev_max_valid = false;
     c->sync_trace = getenv("SIGMA_SYNC_TRACE") != nullptr;
     const uint32_t V = c->nvars, nlit = c->nlit;
     /* restore the pristine solver state */

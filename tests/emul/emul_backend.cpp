@@ -350,7 +350,7 @@ void be_ot_update_plan(void *, const SgView &v, const SgOtUpdate &u)
     for (uint32_t i = 0; i < u.n_elected; ++i) { flag[2 * v.elected[i]] = 1; flag[2 * v.elected[i] + 1] = 1; }
     uint32_t need = 0;
     for (uint32_t lit = 0; lit < v.nlit; ++lit) if (addc[lit] && !(v.state[lit >> 1] & SG_MELTED_M)) need += v.ot_len[lit] + addc[lit];
-    *u.total = need;
+    if (u.total) *u.total = need;
 }
 void be_ot_update(void *, const SgView &v, const SgOtUpdate &u)
 {
