@@ -87,6 +87,9 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt);
 /* createOT: every list of the freshly built (packed) table into ascending clause id order (simplify.cpp:50-58) */
 void be_ot_order(void *s, const SgView &v);
+/* `count` (<= 4) independent exclusive prefix sums of the same length with the launches of one; tmp: count x be_scan_tmp_words(n) */
+struct SgScanSet { const uint32_t *in[4]; uint32_t *out[4]; uint32_t *total[4]; };
+void be_scan_multi(void *s, const SgScanSet &ss, uint32_t count, uint32_t n, uint32_t *tmp);
 /* exclusive prefix sum; out may alias in; *total (device) receives the sum when non-NULL */
 void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *tmp);
 size_t be_scan_tmp_words(uint32_t n);

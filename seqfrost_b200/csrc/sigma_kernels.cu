@@ -282,6 +282,61 @@ __global__ void k_scan_down(const uint32_t *in, uint32_t *out, uint32_t n, const
     }
 }
 
+/* up to four independent scans of the same length in the same three launches: blockIdx.y selects the array */
+__global__ void k_scan_reduce_multi(SgScanSet ss, uint32_t n, uint32_t nb, uint32_t *__restrict__ partial)
+{
+    const uint32_t *in = ss.in[blockIdx.y];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * TPB + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    __shared__ uint32_t tot;
+    (void)block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * nb + blockIdx.x] = tot;
+}
+__global__ void k_scan_partials_multi(SgScanSet ss, uint32_t nb, uint32_t *__restrict__ partial_all)
+{
+    uint32_t *partial = partial_all + (size_t)blockIdx.x * nb;
+    uint32_t *total = ss.total[blockIdx.x];
+    __shared__ uint32_t carry, tot;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += TPB) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < nb ? partial[i] : 0;
+        const uint32_t e = block_exclusive_scan(x, &tot);
+        if (i < nb) partial[i] = carry + e;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void k_scan_down_multi(SgScanSet ss, uint32_t n, uint32_t nb, const uint32_t *__restrict__ partial)
+{
+    const uint32_t *in = ss.in[blockIdx.y];
+    uint32_t *out = ss.out[blockIdx.y];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t x[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + k;
+        x[k] = i < n ? in[i] : 0;
+        s += x[k];
+    }
+    uint32_t e = block_exclusive_scan(s, nullptr) + partial[(size_t)blockIdx.y * nb + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + k;
+        if (i < n) out[i] = e;
+        e += x[k];
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* occurrence table build                                                                           */
 /* ---------------------------------------------------------------------------------------------- */
@@ -1177,6 +1232,16 @@ void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_
     LAUNCH(k_scan_reduce, nb, TPB, s, in, n, tmp);
     LAUNCH(k_scan_partials, 1, TPB, s, tmp, nb, total);
     LAUNCH(k_scan_down, nb, TPB, s, in, out, n, tmp);
+}
+
+void be_scan_multi(void *s, const SgScanSet &ss, uint32_t count, uint32_t n, uint32_t *tmp)
+{
+    if (!count) return;
+    if (!n) { for (uint32_t k = 0; k < count; ++k) if (ss.total[k]) LAUNCH(k_zero_u32, 1, 1, s, ss.total[k]); return; }
+    const uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    LAUNCH(k_scan_reduce_multi, dim3(nb, count), TPB, s, ss, n, nb, tmp);
+    LAUNCH(k_scan_partials_multi, count, TPB, s, ss, nb, tmp);
+    LAUNCH(k_scan_down_multi, dim3(nb, count), TPB, s, ss, n, nb, tmp);
 }
 
 void be_hist(void *s, const SgView &v, uint32_t *counts)

@@ -442,8 +442,12 @@ again:
         }
         /* acting / elected candidates in election order, cut at the break (lcve.cpp:70,73) */
         be_acting_flags(c->stream, v, c->flags.p, c->flags.p + V);
-        be_scan_u32(c->stream, c->flags.p, c->pos.p, V, c->totals.p, c->scantmp.p);
-        be_scan_u32(c->stream, c->flags.p + V, c->pos.p + V, V, c->totals.p + 1, c->scantmp.p);
+        {
+            SgScanSet ss = { { c->flags.p, c->flags.p + V, nullptr, nullptr }, { c->pos.p, c->pos.p + V, nullptr, nullptr },
+                             { c->totals.p, c->totals.p + 1, nullptr, nullptr } };
+            NOMEM(c->scantmp.ensure(2 * be_scan_tmp_words(V) + 64));
+            be_scan_multi(c->stream, ss, 2, V, c->scantmp.p);
+        }
         be_acting_scatter(c->stream, v, c->flags.p, c->pos.p, c->flags.p + V, c->pos.p + V);
         CK(pull_both(c, 14));
         if (c->ot_end_stale) {
@@ -568,9 +572,12 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
     }
     if (c->opts.ve_en) {                                   /* bounded.cpp:29 */
         Stage st(c, SIGMA_T_VE);
-        be_scan_u32(c->stream, c->ve_ncls.p, c->ve_cls_off.p, E, c->totals.p + 0, c->scantmp.p);
-        be_scan_u32(c->stream, c->ve_nlits.p, c->ve_lit_off.p, E, c->totals.p + 1, c->scantmp.p);
-        be_scan_u32(c->stream, c->ve_nmodel.p, c->ve_mod_off.p, E, c->totals.p + 2, c->scantmp.p);
+        {
+            SgScanSet ss = { { c->ve_ncls.p, c->ve_nlits.p, c->ve_nmodel.p, nullptr }, { c->ve_cls_off.p, c->ve_lit_off.p, c->ve_mod_off.p, nullptr },
+                             { c->totals.p + 0, c->totals.p + 1, c->totals.p + 2, nullptr } };
+            NOMEM(c->scantmp.ensure(3 * be_scan_tmp_words(E) + 64));
+            be_scan_multi(c->stream, ss, 3, E, c->scantmp.p);  /* clause ids, pool offsets, model offsets in election order */
+        }
         CK(pull_both(c, 5));
         if (c->h_totals[4] > scr_bound) return fail(c, SIGMA_E_CUDA, "internal: elected lists overlap (scratch bound exceeded)");
         if (c->hsc.unsat) return SIGMA_UNSAT;              /* function-table UNSAT, bounded.cpp:141-145 */
@@ -926,7 +933,7 @@ int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, cons
         NOMEM(c->d_cm.ensure(cnf->cm_buckets + 16)); NOMEM(c->d_crefs.ensure(n_src + 16)); NOMEM(c->d_stencil.ensure(cnf->stencil_size + 16));
         NOMEM(c->c_sizes.ensure(n_src + 16)); NOMEM(c->c_flags.ensure(n_src + 16));
         NOMEM(c->c_newoff.ensure(n_src + 16)); NOMEM(c->c_newid.ensure(n_src + 16));
-        NOMEM(c->scantmp.ensure(be_scan_tmp_words((uint32_t)n_src) + 64));
+        NOMEM(c->scantmp.ensure(2 * be_scan_tmp_words((uint32_t)n_src) + 64));
     } else {
         NOMEM(c->d_arena_in.ensure(in->n_buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)n + 16));
     }
@@ -964,8 +971,11 @@ int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, cons
         /* extract(orgs); extract(learnts) (simplify.cpp:118-133,146-148): sizes -> two scans -> write */
         const uint32_t ns = (uint32_t)n_src;
         be_extract_sizes(c->stream, c->d_cm.p, c->d_crefs.p, ns, c->d_stencil.p, cnf->stencil_size, c->c_sizes.p, c->c_flags.p);
-        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, ns, c->totals.p + 0, c->scantmp.p);
-        be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, ns, c->totals.p + 1, c->scantmp.p);
+        {
+            SgScanSet ss = { { c->c_sizes.p, c->c_flags.p, nullptr, nullptr }, { c->c_newoff.p, c->c_newid.p, nullptr, nullptr },
+                             { c->totals.p + 0, c->totals.p + 1, nullptr, nullptr } };
+            be_scan_multi(c->stream, ss, 2, ns, c->scantmp.p);
+        }
         CK(pull_totals(c, 2));
         const uint32_t buckets = ns ? c->h_totals[0] : 0, ncls = ns ? c->h_totals[1] : 0;
         NOMEM(c->d_arena_in.ensure((size_t)buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)ncls + 16));

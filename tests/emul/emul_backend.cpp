@@ -102,6 +102,10 @@ void be_ot_order(void *, const SgView &v)
     g_launches++;
     for (uint32_t lit : item_order(v.nlit)) sg_idsort_item(v, lit);
 }
+void be_scan_multi(void *s, const SgScanSet &ss, uint32_t count, uint32_t n, uint32_t *tmp)
+{
+    for (uint32_t k = 0; k < count; ++k) be_scan_u32(s, ss.in[k], ss.out[k], n, ss.total[k], tmp);
+}
 void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
     g_launches++;
