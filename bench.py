@@ -297,6 +297,8 @@ def main():
                 "outputs_agree": bool(same),
                 "h2d_bytes_per_step": rep2["h2d_bytes"], "d2h_bytes_per_step": rep2["d2h_bytes"],
                 "h2d_ms": rep2["stage_ms"]["h2d"], "d2h_ms": rep2["stage_ms"]["d2h"]},
+        "instances_per_s": {"device": world * args.steps / (dev_ms / 1e3), "e2e": world * args.steps / (e2e_ms / 1e3),
+                            "note": "BASELINE metric 'instances/s at 1/2/4/8': one 10M-clause instance per GPU per step"},
         "gpu_launches": launches, "clocks": clocks,
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
