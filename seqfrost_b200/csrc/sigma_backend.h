@@ -18,7 +18,7 @@ enum SgItemKind {
     SGK_IDSORT = 0,     /* n = nlit      : order fix of every occurrence list                     */
     SGK_REDUCE,         /* n = nlit      : reduceOT                                                */
     SGK_ELECT_PREP,     /* n = nvars     : static election classes                                 */
-    SGK_SORTOT,         /* n = 2*elected : sortOT                                                  */
+    SGK_SORTOT,         /* n = 2*elected : sortOT, lists of up to 24 entries (one warp each)       */
     SGK_SCRATCH_LEN,    /* n = elected   : scratch words per elected variable                      */
     SGK_SUB,            /* n = elected                                                             */
     SGK_VE_COUNT,       /* n = elected                                                             */
@@ -34,6 +34,8 @@ enum SgItemKind {
     SGK_ERE_SAFE,
     SGK_ERE_APPLY,
     SGK_ERE_FLAG01,     /* n = elected   : ve_ncls[e] = (ere_flags[e] != 0)                               */
+    SGK_SORTOT_LONG,    /* n = 2*elected : sortOT, lists of more than 24 entries (one thread each)  */
+    SGK_IDSORT_LONG,    /* n = literals  : createOT order fix for the lists of more than 64 entries */
     SGK_N
 };
 /* sequential stages, one thread */

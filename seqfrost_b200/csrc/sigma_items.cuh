@@ -505,6 +505,45 @@ template <class P> SG_HD int sg_find_first(const SgLane &L, int n, P pred)
     return -1;
 }
 
+/* sortOT for the common short list (simplify.cpp:85-100, <= 24 entries: the reference's insertion sort, i.e. a STABLE sort
+ * by CNF_CMP_KEY): one warp per list.  Lane i fetches the key of entry i - all fetches of the list in flight at once, no
+ * per-thread key arrays - and its final position is its rank: the number of entries with a smaller key, or an equal key
+ * and a smaller index.  That is exactly the stable order. */
+SG_HDN inline void sg_sortot_warp_item(const SgView &v, uint32_t lit)
+{
+    const int n = (int)v.ot_len[lit];
+    if (n <= (int)v.sortot_warp_min || n > 24) return;
+    uint32_t *d = sg_list(v, lit);
+#if defined(__CUDA_ARCH__)
+    const int lane = (int)(threadIdx.x & 31u);
+    uint32_t id = 0;
+    SgKey k; k.size = 0; k.first = 0; k.last = 0; k.sig = 0;
+    if (lane < n) {
+        id = d[lane];
+        const sg_u4 h = v.hdr[id];
+        k.size = h.y; k.sig = h.w; k.first = v.lits[h.x]; k.last = v.lits[h.x + h.y - 1];
+    }
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        SgKey o;
+        o.size = __shfl_sync(0xffffffffu, k.size, j); o.first = __shfl_sync(0xffffffffu, k.first, j);
+        o.last = __shfl_sync(0xffffffffu, k.last, j); o.sig = __shfl_sync(0xffffffffu, k.sig, j);
+        if (sg_key_lt(o, k) || (j < lane && !sg_key_lt(k, o))) rank++;
+    }
+    const bool moved = lane < n && rank != lane;
+    if (__any_sync(0xffffffffu, moved)) { __syncwarp(); if (lane < n) d[rank] = id; }
+#else
+    sg_sortot_small(v, d, n);
+#endif
+}
+/* the rest, one thread per list: very short lists (a warp would idle; gate circuits have millions of them) and lists of
+ * more than 24 entries (libstdc++'s introsort restated step for step) */
+SG_HDN inline void sg_sortot_long_item(const SgView &v, uint32_t lit)
+{
+    const int n = (int)v.ot_len[lit];
+    if (n <= (int)v.sortot_warp_min || n > 24) sg_sortot_item(v, lit);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* LCVE election (lcve.cpp:52-83, depFreeze :121-145) as a deterministic parallel greedy:       */
 /* a candidate is decided once every earlier-ranked clause neighbour is decided.                */

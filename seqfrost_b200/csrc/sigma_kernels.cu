@@ -615,16 +615,18 @@ constexpr int items_min_blocks(int kind)
 template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND)) k_items(SgView v, uint32_t n)
 {
     /* SUB and the BVE decision run one warp per elected variable, everything else one thread */
-    const bool warp_item = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_NBH || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
+    const bool warp_item = (KIND == SGK_SORTOT || KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_NBH || KIND == SGK_ERE_PROPOSE || KIND == SGK_ERE_CLAIM ||
                             KIND == SGK_ERE_SAFE || KIND == SGK_ERE_APPLY);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i0 = warp_item ? (t >> 5) : t;
     if (i0 >= n) return;
     const uint32_t i = v.item_base + i0;
     if (KIND == SGK_IDSORT) sg_idsort_item(v, i);
+    else if (KIND == SGK_IDSORT_LONG) { if (v.ot_len[i] > 64u) sg_idsort_item(v, i); }
     else if (KIND == SGK_REDUCE) sg_reduce_item(v, i);
     else if (KIND == SGK_ELECT_PREP) sg_elect_prep_item(v, i + 1);
-    else if (KIND == SGK_SORTOT) sg_sortot_item(v, 2 * v.elected[i >> 1] + (i & 1));
+    else if (KIND == SGK_SORTOT) sg_sortot_warp_item(v, 2 * v.elected[i >> 1] + (i & 1));
+    else if (KIND == SGK_SORTOT_LONG) sg_sortot_long_item(v, 2 * v.elected[i >> 1] + (i & 1));
     else if (KIND == SGK_SCRATCH_LEN) {
         const uint32_t var = v.elected[i];
         const uint32_t a = v.ot_len[2 * var], b = v.ot_len[2 * var + 1];
@@ -939,11 +941,14 @@ __global__ void __launch_bounds__(TPB) k_ot_order_staged(SgView v)
     const uint32_t lend = l0 + blockDim.x < v.nlit ? l0 + blockDim.x : v.nlit;
     const uint32_t g0 = v.ot_off[l0], g1 = lend < v.nlit ? v.ot_off[lend] : v.ot_off[v.nlit - 1] + v.ot_len[v.nlit - 1];
     const uint32_t W = g1 - g0, shift = g0 & 3u;
-    if (W > EX_CAP) { if (lit < v.nlit) sg_idsort_item(v, lit); return; }
+    /* lists of more than 64 entries are left to k_items<SGK_IDSORT_LONG> (which runs with the whole L1: this kernel's
+     * staging buffers take most of it, and a long list sorted here would keep 255 threads waiting at the barrier) */
+    const bool mine = lit < v.nlit && v.ot_len[lit] <= 64u;
+    if (W > EX_CAP) { if (mine) sg_idsort_item(v, lit); return; }
     for (uint32_t k = threadIdx.x; k < W; k += blockDim.x) stage[shift + k] = v.ot_data[g0 + k];
     __syncthreads();
     bool changed = false;
-    if (lit < v.nlit) {
+    if (mine) {
         const int n = (int)v.ot_len[lit];
         uint32_t *d = stage + shift + (v.ot_off[lit] - g0);
         for (int i = 1; i < n; ++i) {
@@ -1208,7 +1213,13 @@ void be_ere_filt(void *s, const SgView &v, uint32_t *filt)
 }
 void be_ot_order(void *s, const SgView &v)
 {
-    if (v.nlit) LAUNCH(k_ot_order_staged, blocks_for(v.nlit), TPB, s, v);
+    if (!v.nlit) return;
+    const char *e = getenv("SIGMA_OT_ORDER_STAGED");
+    if (e && e[0] == '0') LAUNCH(k_items<SGK_IDSORT>, blocks_for(v.nlit), TPB, s, v, v.nlit);
+    else {
+        LAUNCH(k_ot_order_staged, blocks_for(v.nlit), TPB, s, v);
+        LAUNCH(k_items<SGK_IDSORT_LONG>, blocks_for(v.nlit), TPB, s, v, v.nlit);
+    }
 }
 void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
 {
@@ -1343,7 +1354,8 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_IDSORT: LAUNCH(k_items<SGK_IDSORT>, blocks_for(n), TPB, s, v, n); break;
     case SGK_REDUCE: LAUNCH(k_items<SGK_REDUCE>, blocks_for(n), TPB, s, v, n); break;
     case SGK_ELECT_PREP: LAUNCH(k_items<SGK_ELECT_PREP>, blocks_for(n), TPB, s, v, n); break;
-    case SGK_SORTOT: LAUNCH(k_items<SGK_SORTOT>, blocks_for(n, 64), 64, s, v, n); break;
+    case SGK_SORTOT: LAUNCH(k_items<SGK_SORTOT>, blocks_for(32ull * n, 128), 128, s, v, n); break;
+    case SGK_SORTOT_LONG: LAUNCH(k_items<SGK_SORTOT_LONG>, blocks_for(n, 64), 64, s, v, n); break;
     case SGK_SCRATCH_LEN: LAUNCH(k_items<SGK_SCRATCH_LEN>, blocks_for(n), TPB, s, v, n); break;
     case SGK_SUB: LAUNCH(k_items<SGK_SUB>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_VE_COUNT: LAUNCH(k_items<SGK_VE_COUNT>, blocks_for(32ull * n, 128), 128, s, v, n); break;

@@ -489,6 +489,17 @@ int apply_units(sigma_ctx *c, SgView &v)
     return SIGMA_OK;
 }
 
+/* sortOT work split: a warp per list pays off when lists have around a dozen entries (k-SAT); with the two- to six-entry
+ * lists of gate circuits, millions of warps would start only to find nothing to do, so everything goes to the
+ * thread-per-list kernel there */
+uint32_t sortot_warp_min(const sigma_ctx *c)
+{
+    const char *e = getenv("SIGMA_SORTOT_WARP_MIN");
+    if (e) return (uint32_t)atoi(e);
+    const uint64_t lits = c->hsc.live_lits ? c->hsc.live_lits : c->in_literals;
+    return lits < 7ull * c->nlit ? 24u : 8u;               /* average list shorter than 7 entries: no warp kernel */
+}
+
 /* sortOT (simplify.cpp:85-100) */
 int stage_sortot(sigma_ctx *c)
 {
@@ -496,7 +507,9 @@ int stage_sortot(sigma_ctx *c)
     Stage st(c, SIGMA_T_SOT);
     SgView v = make_view(c);
     v.n_elected = E;
-    be_items(c->stream, SGK_SORTOT, v, 2 * E);
+    v.sortot_warp_min = sortot_warp_min(c);
+    if (v.sortot_warp_min < 24) be_items(c->stream, SGK_SORTOT, v, 2 * E);   /* lists of 9..24 entries: one warp each */
+    be_items(c->stream, SGK_SORTOT_LONG, v, 2 * E);        /* the others: one thread each */
     return SIGMA_OK;
 }
 
@@ -556,7 +569,9 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
             {
                 Stage st(c, SIGMA_T_SOT);
                 v.item_base = 2 * first;
-                be_items(c->stream, SGK_SORTOT, v, 2 * cnt);
+                v.sortot_warp_min = sortot_warp_min(c);
+                if (v.sortot_warp_min < 24) be_items(c->stream, SGK_SORTOT, v, 2 * cnt);
+                be_items(c->stream, SGK_SORTOT_LONG, v, 2 * cnt);
             }
             v.item_base = first;
             if (do_sub) {

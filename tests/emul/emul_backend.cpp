@@ -233,7 +233,8 @@ void be_items(void *, int kind, const SgView &v, uint32_t n)
         case SGK_IDSORT: sg_idsort_item(v, i); break;
         case SGK_REDUCE: sg_reduce_item(v, i); break;
         case SGK_ELECT_PREP: sg_elect_prep_item(v, i + 1); break;
-        case SGK_SORTOT: sg_sortot_item(v, 2 * v.elected[i >> 1] + (i & 1)); break;
+        case SGK_SORTOT: sg_sortot_warp_item(v, 2 * v.elected[i >> 1] + (i & 1)); break;
+        case SGK_SORTOT_LONG: sg_sortot_long_item(v, 2 * v.elected[i >> 1] + (i & 1)); break;
         case SGK_SCRATCH_LEN: {
             const uint32_t var = v.elected[i];
             const uint32_t a = v.ot_len[2 * var], b = v.ot_len[2 * var + 1];
