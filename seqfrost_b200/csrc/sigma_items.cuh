@@ -102,6 +102,21 @@ SG_HD void sg_sort_lits(uint32_t *d, int n)
 /* <= 24 entries: the reference's insertion sort; larger: libstdc++ std::sort (introsort),       */
 /* restated step for step so that even the order of tied keys is the reference's.                */
 /* ------------------------------------------------------------------------------------------ */
+struct SgKey { uint32_t size, first, last, sig; };
+SG_HD bool sg_key_lt(const SgKey &x, const SgKey &y)
+{   /* CNF_CMP_KEY (simplify.hpp:30-47) */
+    if ((int)x.size < (int)y.size) return true;
+    if ((int)x.size > (int)y.size) return false;
+    if (x.first < y.first) return true;
+    if (x.first > y.first) return false;
+    if (x.last < y.last) return true;
+    if (x.last > y.last) return false;
+    return x.sig < y.sig;
+}
+/* the same order over keys fetched once: elements are positions in `key` */
+struct SgKeyCache { const SgKey *key; };
+SG_HD bool sg_key_less(const SgKeyCache &kc, uint32_t a, uint32_t b) { return sg_key_lt(kc.key[a], kc.key[b]); }
+
 SG_HD bool sg_key_less(const SgView &v, uint32_t a, uint32_t b)
 {
     const sg_u4 x = v.hdr[a], y = v.hdr[b];
@@ -133,14 +148,14 @@ SG_HD void sg_ins_sort_ref(const SgView &v, uint32_t *d, int size)
 }
 
 /* libstdc++ (GCC 13) bits/stl_algo.h + bits/stl_heap.h, restated over an index range */
-SG_HD void sg_std_unguarded_linear_insert(const SgView &v, uint32_t *d, int last)
+template <class K> SG_HD void sg_std_unguarded_linear_insert(const K &v, uint32_t *d, int last)
 {
     const uint32_t val = d[last];
     int next = last - 1;
     while (sg_key_less(v, val, d[next])) { d[last] = d[next]; last = next; --next; }
     d[last] = val;
 }
-SG_HD void sg_std_insertion_sort(const SgView &v, uint32_t *d, int first, int last)
+template <class K> SG_HD void sg_std_insertion_sort(const K &v, uint32_t *d, int first, int last)
 {
     if (first == last) return;
     for (int i = first + 1; i != last; ++i) {
@@ -151,7 +166,7 @@ SG_HD void sg_std_insertion_sort(const SgView &v, uint32_t *d, int first, int la
         } else sg_std_unguarded_linear_insert(v, d, i);
     }
 }
-SG_HD void sg_std_adjust_heap(const SgView &v, uint32_t *d, int first, int hole, int len, uint32_t value)
+template <class K> SG_HD void sg_std_adjust_heap(const K &v, uint32_t *d, int first, int hole, int len, uint32_t value)
 {
     const int top = hole;
     int child = hole;
@@ -174,7 +189,7 @@ SG_HD void sg_std_adjust_heap(const SgView &v, uint32_t *d, int first, int hole,
     }
     d[first + hole] = value;
 }
-SG_HD void sg_std_heapsort(const SgView &v, uint32_t *d, int first, int last)
+template <class K> SG_HD void sg_std_heapsort(const K &v, uint32_t *d, int first, int last)
 {   /* __partial_sort(first,last,last): __heap_select = make_heap, then __sort_heap */
     const int len = last - first;
     if (len >= 2) {
@@ -194,7 +209,7 @@ SG_HD void sg_std_heapsort(const SgView &v, uint32_t *d, int first, int last)
         sg_std_adjust_heap(v, d, first, 0, l - first, value);
     }
 }
-SG_HDN inline void sg_std_sort(const SgView &v, uint32_t *d, int n)
+template <class K> SG_HDN inline void sg_std_sort(const K &v, uint32_t *d, int n)
 {
     if (n < 2) return;
     int lg = 0;
@@ -245,17 +260,6 @@ SG_HDN inline void sg_std_sort(const SgView &v, uint32_t *d, int n)
 
 /* short lists (the common case): fetch every key once, then run the reference's insertion sort
  * (sort.hpp:92-108) on the local copies - the same comparisons in the same order, so the same result */
-struct SgKey { uint32_t size, first, last, sig; };
-SG_HD bool sg_key_lt(const SgKey &x, const SgKey &y)
-{   /* CNF_CMP_KEY (simplify.hpp:30-47) */
-    if ((int)x.size < (int)y.size) return true;
-    if ((int)x.size > (int)y.size) return false;
-    if (x.first < y.first) return true;
-    if (x.first > y.first) return false;
-    if (x.last < y.last) return true;
-    if (x.last > y.last) return false;
-    return x.sig < y.sig;
-}
 SG_HDN inline void sg_sortot_small(const SgView &v, uint32_t *d, int size)
 {
     SgKey key[24];
@@ -292,13 +296,39 @@ SG_HDN inline void sg_sortot_small(const SgView &v, uint32_t *d, int size)
 }
 
 /* one occurrence list of an elected variable */
+#define SG_SORTOT_CACHED_MAX 64
 SG_HDN inline void sg_sortot_item(const SgView &v, uint32_t lit)
 {
     const int n = (int)v.ot_len[lit];
     if (n < 2) return;
     uint32_t *d = sg_list(v, lit);
     if (n <= 24) sg_sortot_small(v, d, n);
-    else {
+    else if (n <= SG_SORTOT_CACHED_MAX) {
+        /* every key fetched once (batched), then std::sort over positions with the keys in local memory: the same
+         * comparisons and moves as sorting the ids themselves, without a header + literal fetch per comparison */
+        SgKey key[SG_SORTOT_CACHED_MAX];
+        uint32_t id[SG_SORTOT_CACHED_MAX], q[SG_SORTOT_CACHED_MAX];
+        for (int b = 0; b < n; b += 8) {
+            sg_u4 h[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (b + k < n) id[b + k] = d[b + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (b + k < n) h[k] = v.hdr[id[b + k]];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (b + k < n) {
+                key[b + k].size = h[k].y; key[b + k].sig = h[k].w;
+                key[b + k].first = v.lits[h[k].x]; key[b + k].last = v.lits[h[k].x + h[k].y - 1];
+                q[b + k] = (uint32_t)(b + k);
+            }
+        }
+        SgKeyCache kc; kc.key = key;
+        sg_std_sort(kc, q, n);
+        uint32_t ties = 0;
+        for (int i = 1; i < n; ++i)
+            if (!sg_key_less(kc, q[i - 1], q[i])) ties++;
+        for (int i = 0; i < n; ++i) d[i] = id[q[i]];
+        if (ties) sg_atomic_add64(&v.sc->sort_ties_gt24, ties);
+    } else {
         sg_std_sort(v, d, n);
         uint32_t ties = 0;
         for (int i = 1; i < n; ++i)
