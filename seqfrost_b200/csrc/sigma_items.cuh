@@ -1731,7 +1731,10 @@ SG_HDN inline void sg_ere_propose_item(const SgView &v, uint32_t chunk)
                 /* the screen reads the 8-byte {size, sig} snapshot (nothing is modified during the proposal pass) */
                 uint32_t fs2[8], fg[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { fs2[k] = v.ere_filt[2 * (size_t)cc[k]]; fg[k] = v.ere_filt[2 * (size_t)cc[k] + 1]; }
+                for (int k = 0; k < 8; ++k) {                 /* one 8-byte load per entry */
+                    const unsigned long long f = ((const unsigned long long *)v.ere_filt)[cc[k]];
+                    fs2[k] = (uint32_t)f; fg[k] = (uint32_t)(f >> 32);
+                }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     if (cc[k] == iref || cc[k] == jref) continue;
