@@ -337,6 +337,30 @@ SG_HDN inline void sg_sortot_item(const SgView &v, uint32_t lit)
     }
 }
 
+/* in-place heap sort (ascending): the O(n log n) fallback wherever an insertion sort could meet a long, badly ordered run */
+SG_HD void sg_sift_down_u32(uint32_t *a, int root, int end)
+{
+    const uint32_t val = a[root];
+    int hole = root;
+    for (;;) {
+        int child = 2 * hole + 1;
+        if (child >= end) break;
+        if (child + 1 < end && a[child + 1] > a[child]) child++;
+        if (a[child] <= val) break;
+        a[hole] = a[child];
+        hole = child;
+    }
+    a[hole] = val;
+}
+SG_HD void sg_heapsort_u32(uint32_t *a, int n)
+{
+    for (int s = n / 2 - 1; s >= 0; --s) sg_sift_down_u32(a, s, n);
+    for (int end = n - 1; end > 0; --end) {
+        const uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+        sg_sift_down_u32(a, 0, end);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* occurrence-list order fix after the atomic scatter: ascending clause id == the reference's   */
 /* push order (simplify.cpp:50-58)                                                              */
@@ -345,6 +369,10 @@ SG_HD void sg_idsort_item(const SgView &v, uint32_t lit)
 {
     const int n = (int)v.ot_len[lit];
     uint32_t *d = sg_list(v, lit);
+    /* the scatter leaves a list nearly sorted (an entry is displaced by at most the occurrences of its literal among the
+     * clauses in flight), which an insertion sort fixes in about one pass - except for a hub literal that sits in a large
+     * share of all clauses: there the displacement grows with the list, so long lists take the n log n route */
+    if (n > 1024) { sg_heapsort_u32(d, n); return; }
     for (int i = 1; i < n; ++i) {
         const uint32_t t = d[i];
         int j = i;
@@ -750,30 +778,6 @@ SG_HD uint32_t sg_extract_size(const uint32_t *cm, const uint8_t *stencil, uint6
 {
     if (ref < stencil_size && stencil[ref]) return 0;
     return 3u + cm[ref + 1];
-}
-
-/* in-place heap sort (ascending) for the rare long clause */
-SG_HD void sg_sift_down_u32(uint32_t *a, int root, int end)
-{
-    const uint32_t val = a[root];
-    int hole = root;
-    for (;;) {
-        int child = 2 * hole + 1;
-        if (child >= end) break;
-        if (child + 1 < end && a[child + 1] > a[child]) child++;
-        if (a[child] <= val) break;
-        a[hole] = a[child];
-        hole = child;
-    }
-    a[hole] = val;
-}
-SG_HD void sg_heapsort_u32(uint32_t *a, int n)
-{
-    for (int s = n / 2 - 1; s >= 0; --s) sg_sift_down_u32(a, s, n);
-    for (int end = n - 1; end > 0; --end) {
-        const uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
-        sg_sift_down_u32(a, 0, end);
-    }
 }
 
 /* SCLAUSE(const CLAUSE&) + calcSig + SORT (sclause.hpp:61-75,158-162; sort.hpp:44-52): dst = {w0, sig, size, lits} */

@@ -1071,7 +1071,8 @@ __global__ void k_otu_apply(SgView v, const uint32_t *__restrict__ bits, const u
             dst[n++] = c[k];
         }
     }
-    if (unsorted) {                                       /* sortOT order -> clause-id order */
+    if (unsorted && n > 256) sg_heapsort_u32(dst, (int)n);   /* a long list in sortOT order: no quadratic walk */
+    else if (unsorted) {                                  /* sortOT order -> clause-id order */
         for (uint32_t i = 1; i < n; ++i) {
             const uint32_t t = dst[i];
             uint32_t j = i;

@@ -39,6 +39,12 @@ def _cases():
         cl.append([v if rng.random() < .5 else -v for v in vs])
     out["hub"] = (3000, cl, [])
     out["hub_wide_mu"] = (3000, cl, ["--mupos=2000", "--muneg=2000", "--subsumemaxoccurs=100"])
+    # a literal in 3000 clauses: the order fix of its occurrence list takes the heap-sort route (> 1024 entries)
+    cl = [[1, 2 + k, 3100 + (k % 700)] for k in range(3000)] + [[-1, 2 + k, 3 + k] for k in range(50)]
+    for _ in range(5000):
+        vs = rng.sample(range(2, 3801), 3)
+        cl.append([v if rng.random() < .5 else -v for v in vs])
+    out["hub_huge"] = (3800, cl, [])
     out["emptied_4"] = (3, [[1, 2], [-1, 3], [2, 3], [-2, -3, 1]], [])
     out["emptied_2"] = (2, [[1, 2], [-1, -2]], [])
     return out
