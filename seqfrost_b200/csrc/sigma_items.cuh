@@ -918,6 +918,68 @@ SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x
     const int nme = (int)v.ot_len[x];
     const uint32_t *ot = sg_list(v, fx);
     const int not_ = (int)v.ot_len[fx];
+#if defined(__CUDA_ARCH__)
+    if (nme <= 32 && not_ <= 32) {
+        /* Both lists fit a warp (the common case): lane j keeps the header of ot[j] and of me[j] in registers, so one
+         * step of the loop is a broadcast of clause i's header, one predicate per lane and a ballot - the same tests in
+         * the same order as the general loop below, without re-fetching a dozen headers per clause. */
+        const int lane = (int)L.lane;
+        const uint32_t oc = lane < not_ ? ot[lane] : 0u;
+        const sg_u4 oh = lane < not_ ? v.hdr[oc] : make_uint4(0, 0, SG_DELETED, 0);
+        const uint32_t mc = lane < nme ? me[lane] : 0u;
+        sg_u4 mh = lane < nme ? v.hdr[mc] : make_uint4(0, 0, SG_DELETED, 0);
+        for (int i = 0; i < nme; ++i) {
+            const uint32_t c = __shfl_sync(0xffffffffu, mc, i);
+            sg_u4 ch;
+            ch.x = __shfl_sync(0xffffffffu, mh.x, i); ch.y = __shfl_sync(0xffffffffu, mh.y, i);
+            ch.z = __shfl_sync(0xffffffffu, mh.z, i); ch.w = __shfl_sync(0xffffffffu, mh.w, i);
+            if ((int)ch.y > maxsz) break;
+            if (ch.z & SG_DELETED) continue;
+            const uint32_t *cl = v.lits + ch.x;
+            {   /* selfsubsume (subsume.hpp:158-177) */
+                const int candsz = (int)ch.y;
+                bool hit = false;
+                if (lane < not_) {
+                    const int subsize = (int)oh.y;
+                    if (subsize > candsz) hit = true;
+                    else if (!(oh.z & SG_DELETED))
+                        hit = subsize > 1 && sg_sig_selfsub(oh.w, ch.w) && sg_selfsub_lits(x, fx, v.lits + oh.x, subsize, cl, candsz);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    const int k = __ffs((int)m) - 1;
+                    if ((int)__shfl_sync(0xffffffffu, oh.y, k) <= candsz) {
+                        sg_strengthen(v, L, c, x, eidx, seq);
+                        n_str++;
+                        if (lane == i) mh = v.hdr[c];                     /* size, signature and molten flag changed */
+                        ch.y = __shfl_sync(0xffffffffu, mh.y, i); ch.z = __shfl_sync(0xffffffffu, mh.z, i);
+                        ch.w = __shfl_sync(0xffffffffu, mh.w, i);
+                    }
+                }
+            }
+            {   /* subsume (subsume.hpp:139-156): the first earlier clause of the list that subsumes c */
+                const int candsz = (int)ch.y;
+                const bool cmolten = (ch.z & SG_MOLTEN) != 0;
+                bool hit = false;
+                if (lane < i && !(mh.z & SG_DELETED)) {
+                    const int ssz = (int)mh.y;
+                    if (!(cmolten && ssz > candsz))
+                        hit = ssz > 1 && sg_sig_sub(mh.w, ch.w) && sg_sub_lits(v.lits + mh.x, ssz, cl, candsz);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    const int k = __ffs((int)m) - 1;
+                    const bool corg = !(ch.z & SG_ST_MASK);
+                    if (lane == k && (mh.z & SG_LEARNT) && corg) { mh.z &= ~SG_ST_MASK; v.hdr[mc].z = mh.z; }   /* subsume.hpp:147-148 */
+                    if (lane == i) { mh.z = (mh.z & ~SG_ST_MASK) | SG_DELETED; v.hdr[c].z = mh.z; }
+                    __syncwarp();
+                    n_sub++;
+                }
+            }
+        }
+        goto update_ol;
+    }
+#endif
     for (int i = 0; i < nme; ++i) {
         const uint32_t c = me[i];
         if (SG_SIZE(v, c) > maxsz) break;
@@ -962,6 +1024,9 @@ SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x
             }
         }
     }
+#if defined(__CUDA_ARCH__)
+update_ol:
+#endif
     /* updateOL (subsume.hpp:26-36): in-place, order-preserving */
     int j = 0;
     for (int base = 0; base < nme; base += (int)L.width) {
