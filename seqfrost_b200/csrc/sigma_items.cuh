@@ -1324,6 +1324,15 @@ SG_HDN inline bool sg_find_ite_gate(const SgView &v, const SgLane &L, uint32_t d
     const uint32_t *dd = sg_list(v, dx);
     if (SG_SIZE(v, dd[nd - 1]) == 2) return false;
     const uint32_t var = SG_ABS(dx);
+#if defined(__CUDA_ARCH__)
+    if (nd <= 32) {
+        /* the loops below only ever stop at original ternary clauses: with fewer than two of them in the list (one
+         * look per lane) there is nothing to find - the usual case outside gate circuits */
+        bool tern = false;
+        if ((int)L.lane < nd) { const sg_u4 h = v.hdr[dd[L.lane]]; tern = !(h.z & SG_ST_MASK) && h.y == 3u; }
+        if (sg_popc(sg_ballot(tern)) < 2) return false;
+    }
+#endif
     for (int i = 0; i < nd; ++i) {
         const uint32_t ci = dd[i];
         if (!(sg_original(v, ci) && SG_SIZE(v, ci) == 3)) continue;
@@ -1451,6 +1460,21 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
     if (SG_SIZE(v, dd[0]) - 1 > maxarity) return false;
     const uint32_t var = SG_ABS(dx);
     uint32_t out_c[24];
+#if defined(__CUDA_ARCH__)
+    /* when both lists fit one warp, the count of the screen below - original clauses of the two lists with the same size
+     * and the same sign-blind signature - is two warp matches and a ballot: lane q looks at entry q of (dx list, fx list) */
+    const bool fits = nd + nf <= 32;
+    int same_fast = 0;
+    if (fits) {
+        const int q = (int)L.lane;
+        sg_u4 g = make_uint4(0, 0, SG_DELETED, 0);
+        if (q < nd + nf) g = v.hdr[q < nd ? dd[q] : df[q - nd]];
+        const uint32_t gw = g.w | ((g.w & 0xAAAAAAAAu) >> 1) | ((g.w & 0x55555555u) << 1);
+        const uint32_t m_sig = __match_any_sync(0xffffffffu, gw), m_size = __match_any_sync(0xffffffffu, g.y);
+        const uint32_t m_org = __ballot_sync(0xffffffffu, q < nd + nf && !(g.z & SG_ST_MASK));
+        same_fast = __popc(m_sig & m_size & m_org);
+    }
+#endif
     for (int base = 0; base < nd; base += (int)L.width) {
         /* the reference tries the clauses of dx in list order and stops at the first complete XOR */
         const int idx = base + (int)L.lane;
@@ -1464,6 +1488,10 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
                  * clauses of this size with the same sign-blind signature must be in the two lists */
                 const uint32_t wide = h.w | ((h.w & 0xAAAAAAAAu) >> 1) | ((h.w & 0x55555555u) << 1);
                 int same = 0;
+#if defined(__CUDA_ARCH__)
+                if (fits) same = same_fast;
+                else
+#endif
                 for (int q = 0; q < nd + nf; ++q) {
                     const sg_u4 g = v.hdr[q < nd ? dd[q] : df[q - nd]];
                     if ((g.z & SG_ST_MASK) || (int)g.y != size) continue;
