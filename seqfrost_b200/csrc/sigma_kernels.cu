@@ -519,11 +519,14 @@ __global__ void k_elect_round(SgView v, const uint32_t *__restrict__ wl_in, uint
 #ifndef SG_LB_ELECT
 #define SG_LB_ELECT 1          /* minimum resident blocks per SM asked of the compiler (register budget) */
 #endif
-__global__ void __launch_bounds__(128, SG_LB_ELECT) k_elect_persistent(SgView v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow)
+#ifndef SG_ELECT_TPB
+#define SG_ELECT_TPB 1024      /* threads per block of the cooperative election: fewer, larger blocks make grid.sync cheaper */
+#endif
+__global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_persistent(SgView v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    __shared__ uint32_t s_buf[4][32];
+    __shared__ uint32_t s_buf[SG_ELECT_TPB / 32][32];
     const uint32_t V = v.nvars;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     const uint32_t gwarp = gtid >> 5, nwarps = gsize >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1331,13 +1334,13 @@ int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_elect_persistent, 128, 0) != cudaSuccess) blocks_per_sm = 0;
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_elect_persistent, SG_ELECT_TPB, 0) != cudaSuccess) blocks_per_sm = 0;
         (void)cudaGetLastError();
     }
     if (blocks_per_sm <= 0 || !v.nvars) return 1;
     SgView vv = v;
     void *args[] = { (void *)&vv, (void *)&wl0, (void *)&wl1, (void *)&b0, (void *)&grow };
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_elect_persistent, dim3((unsigned)(blocks_per_sm * sms)), dim3(128), args, 0, ST(s));
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_elect_persistent, dim3((unsigned)(blocks_per_sm * sms)), dim3(SG_ELECT_TPB), args, 0, ST(s));
     if (e != cudaSuccess) { (void)cudaGetLastError(); blocks_per_sm = 0; return 1; }
     g_launches++;
     return 0;
