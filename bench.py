@@ -287,7 +287,7 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     # stages that are one kernel (launched once, or once per slice) vs groups of small kernels
-    single = {"ingest": "k_ingest_fused", "ot_hist": "k_hist", "ot_scatter": "k_scatter", "ot_order": "k_items<IDSORT>", "count": "k_count_live"}
+    single = {"ingest": "k_ingest_fused", "ot_hist": "k_hist", "ot_scatter": "k_scatter", "ot_order": "k_ot_order_staged", "count": "k_count_live"}
     streaming = [k for k in ("ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "ot_update", "vo", "count", "gc", "export") if stage_bytes.get(k)]
     dom = max([k for k in streaming if k in single], key=lambda k: stage_ms[k])
     dom_launches = max(1, stage_launches[dom])
