@@ -150,12 +150,14 @@ __global__ void __launch_bounds__(TPB) k_cm_write(const uint32_t *__restrict__ a
     }
 }
 
-__global__ void k_ere_filt(SgView v, uint2 *__restrict__ filt)
+__global__ void k_ere_filt(SgView v, uint2 *__restrict__ filt, uint8_t *__restrict__ size8)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= v.n_cls) return;
     const uint4 h = v.hdr[c];
-    filt[c] = make_uint2((h.z & SG_DELETED) ? 0u : h.y, h.w);
+    const uint32_t size = (h.z & SG_DELETED) ? 0u : h.y;
+    filt[c] = make_uint2(size, h.w);
+    size8[c] = (uint8_t)(size < 255u ? size : 255u);
 }
 
 __global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
@@ -1211,9 +1213,9 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
     if (n) LAUNCH(k_cm_write, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt_before, lbd_tier1, cm,
                   (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume, (unsigned long long)(n_buckets + n));
 }
-void be_ere_filt(void *s, const SgView &v, uint32_t *filt)
+void be_ere_filt(void *s, const SgView &v, uint32_t *filt, uint8_t *size8)
 {
-    if (v.n_cls) LAUNCH(k_ere_filt, blocks_for(v.n_cls), TPB, s, v, (uint2 *)filt);
+    if (v.n_cls) LAUNCH(k_ere_filt, blocks_for(v.n_cls), TPB, s, v, (uint2 *)filt, size8);
 }
 void be_ot_order(void *s, const SgView &v)
 {

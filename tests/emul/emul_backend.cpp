@@ -92,10 +92,14 @@ void be_cm_write(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n
             for (uint32_t k = 0; k < src[2]; ++k) subsume[SG_ABS(src[3 + k])] = 1;
     }
 }
-void be_ere_filt(void *, const SgView &v, uint32_t *filt)
+void be_ere_filt(void *, const SgView &v, uint32_t *filt, uint8_t *size8)
 {
     g_launches++;
-    for (uint32_t c = 0; c < v.n_cls; ++c) { filt[2 * c] = (v.hdr[c].z & SG_DELETED) ? 0u : v.hdr[c].y; filt[2 * c + 1] = v.hdr[c].w; }
+    for (uint32_t c = 0; c < v.n_cls; ++c) {
+        const uint32_t size = (v.hdr[c].z & SG_DELETED) ? 0u : v.hdr[c].y;
+        filt[2 * c] = size; filt[2 * c + 1] = v.hdr[c].w;
+        size8[c] = (uint8_t)(size < 255u ? size : 255u);
+    }
 }
 void be_ot_order(void *, const SgView &v)
 {
