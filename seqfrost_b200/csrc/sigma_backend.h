@@ -62,21 +62,22 @@ void *be_event_create(void);
 void  be_event_destroy(void *ev);
 void  be_event_record(void *stream, void *ev);
 float be_event_ms(void *a, void *b);
-uint64_t be_launch_count(void);
+uint64_t be_launch_count(void *stream);        /* kernels launched so far on this context's stream */
 /* small control blocks between device memory and mapped pinned host memory, without the copy engine (bytes % 4 == 0) */
-void  be_copy_words(void *stream, void *dst, const void *src, size_t bytes);                /* kernels launched so far by this library */
+void  be_copy_words(void *stream, void *dst, const void *src, size_t bytes);
 
 /* ---- streaming kernels ------------------------------------------------------------------------ */
 /* AoS SCNF arena -> device store (reference hand-off layout, sclause.hpp:45-49) */
-void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes);
+/* *bad != 0 afterwards: a ref or a size word points outside the n_buckets words of the arena (sizes[] are then 0 there) */
+void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, uint32_t *sizes, uint32_t *bad);
 void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs,
                     sg_u4 *hdr, uint32_t *lits);
 /* one-kernel ingest for a gap-free arena (what awaken() leaves); *gap != 0 afterwards: use the general path */
-void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap);
+void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, sg_u4 *hdr, uint32_t *lits, uint32_t *gap);
 /* extract() on the device (simplify.cpp:118-133): sizes[i] = SCNF buckets of source clause i (0 = deleted), live[i] = 0/1;
  * then, with the two exclusive scans, the SCLAUSE records and their refs */
-void be_extract_sizes(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
-                      uint32_t *sizes, uint32_t *live);
+void be_extract_sizes(void *s, const uint32_t *cm, uint64_t cm_buckets, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
+                      uint32_t *sizes, uint32_t *live, uint32_t *bad);   /* *bad != 0: a ref / record leaves the cm_buckets words */
 void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
                       const uint32_t *newid, uint32_t *arena, uint64_t *refs);
 /* newBeginning() on the device (simplify.cpp:249-268, sclause.cpp:22-62): exported SCNF -> CLAUSE records + orgs / learnts.

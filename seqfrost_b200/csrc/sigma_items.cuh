@@ -774,9 +774,12 @@ SG_HDN inline void sg_marks_serial(const SgView &v, uint32_t n_acting)
 #define SG_CM_HDR 4u          /* header buckets of a CLAUSE (clause.hpp:47-59: sizeof == 24, two of them literals) */
 
 /* buckets the clause will take in the SCNF arena: 0 when cm.deleted(ref) (simplify.cpp:124) */
-SG_HD uint32_t sg_extract_size(const uint32_t *cm, const uint8_t *stencil, uint64_t stencil_size, uint64_t ref)
+#define SG_EXTRACT_BAD 0xFFFFFFFFu   /* the ref (or the record's size word) points outside the cm_buckets words of the database */
+SG_HD uint32_t sg_extract_size(const uint32_t *cm, uint64_t cm_buckets, const uint8_t *stencil, uint64_t stencil_size, uint64_t ref)
 {
+    if (ref + SG_CM_HDR > cm_buckets) return SG_EXTRACT_BAD;
     if (ref < stencil_size && stencil[ref]) return 0;
+    if (ref + SG_CM_HDR + cm[ref + 1] > cm_buckets) return SG_EXTRACT_BAD;
     return 3u + cm[ref + 1];
 }
 

@@ -10,27 +10,34 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <new>
 
 #include "sigma_backend.h"
 #include "sigma_items.cuh"
 
 namespace {
 
-unsigned long long g_launches = 0;
-char g_err[256] = { 0 };
+/* Per-context launch state: the handle sigma_pass.cpp passes around as its "stream".  The launch counter and the first
+ * CUDA error belong to the context that saw them (contexts are independent and may be driven by different host threads). */
+struct BeStream {
+    cudaStream_t st;
+    unsigned long long launches;
+    char err[256];
+};
 
-inline void note_err(const char *what)
+inline void note_err(void *s, const char *what)
 {
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess && !g_err[0]) snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    BeStream *b = (BeStream *)s;
+    if (e != cudaSuccess && !b->err[0]) snprintf(b->err, sizeof b->err, "%s: %s", what, cudaGetErrorString(e));
 }
 
-#define ST(s) ((cudaStream_t)(s))
+#define ST(s) (((BeStream *)(s))->st)
 #define LAUNCH(kernel, grid, block, stream, ...)                      \
     do {                                                              \
         kernel<<<(grid), (block), 0, ST(stream)>>>(__VA_ARGS__);      \
-        g_launches++;                                                 \
-        note_err(#kernel);                                            \
+        ((BeStream *)(stream))->launches++;                           \
+        note_err(stream, #kernel);                                    \
     } while (0)
 
 constexpr int TPB = 256;
@@ -68,13 +75,14 @@ __device__ __forceinline__ void flush_staged(uint32_t *out, unsigned long long g
 
 constexpr uint32_t EX_CAP = 6144;      /* staging words per 256-clause tile (24 KB); larger tiles write directly */
 
-__global__ void k_extract_sizes(const uint32_t *__restrict__ cm, const uint64_t *__restrict__ crefs, uint32_t n,
+__global__ void k_extract_sizes(const uint32_t *__restrict__ cm, uint64_t cm_buckets, const uint64_t *__restrict__ crefs, uint32_t n,
                                 const uint8_t *__restrict__ stencil, uint64_t stencil_size, uint32_t *__restrict__ sizes,
-                                uint32_t *__restrict__ live)
+                                uint32_t *__restrict__ live, uint32_t *bad)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t sz = sg_extract_size(cm, stencil, stencil_size, crefs[i]);
+    uint32_t sz = sg_extract_size(cm, cm_buckets, stencil, stencil_size, crefs[i]);
+    if (sz == SG_EXTRACT_BAD) { *bad = 1; sz = 0; }
     sizes[i] = sz;
     live[i] = sz != 0;
 }
@@ -160,11 +168,21 @@ __global__ void k_ere_filt(SgView v, uint2 *__restrict__ filt, uint8_t *__restri
     size8[c] = (uint8_t)(size < 255u ? size : 255u);
 }
 
+/* a ref or size word that points outside the uploaded arena raises *bad (the driver returns SIGMA_E_ARG) instead of
+ * being followed */
 __global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
-                               uint32_t *__restrict__ sizes)
+                               uint64_t n_buckets, uint32_t *__restrict__ sizes, uint32_t *bad)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) sizes[i] = arena[refs[i] + 2];
+    if (i >= n) return;
+    const uint64_t r = refs[i];
+    uint32_t size = 0;
+    if (r + 3 > n_buckets) *bad = 2;
+    else {
+        size = arena[r + 2];
+        if (r + 3 + size > n_buckets) { *bad = 2; size = 0; }
+    }
+    sizes[i] = size;
 }
 
 __global__ void k_ingest_copy(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
@@ -184,14 +202,16 @@ __global__ void k_ingest_copy(const uint32_t *__restrict__ arena, const uint64_t
  * pool offset is refs[i] - 3*i and no scan is needed; any gap raises *gap and the driver re-runs the
  * general path above */
 __global__ void k_ingest_fused(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
-                               uint4 *__restrict__ hdr, uint32_t *__restrict__ lits, uint32_t *gap)
+                               uint64_t n_buckets, uint4 *__restrict__ hdr, uint32_t *__restrict__ lits, uint32_t *gap)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t r = refs[i];
+    if (r + 3 > n_buckets) { *gap = 1; return; }            /* the general path reports malformed input */
     const uint32_t w0 = arena[r], sig = arena[r + 1], size = arena[r + 2];
+    if (r + 3 + size > n_buckets) { *gap = 1; return; }
     const uint64_t expect = i ? r : 0;
-    if ((i + 1 < n && refs[i + 1] != r + 3 + size) || (i == 0 && r != expect) || r < 3ull * i) { *gap = 1; return; }
+    if ((i + 1 < n && refs[i + 1] != r + 3 + size) || (i + 1 == n && r + 3 + size != n_buckets) || (i == 0 && r != expect) || r < 3ull * i) { *gap = 1; return; }
     const uint32_t off = (uint32_t)(r - 3ull * i);
     hdr[i] = make_uint4(off, size, w0, sig);
     const uint32_t *src = arena + r + 3;
@@ -1148,13 +1168,14 @@ int be_init(int device, void **stream_out, char *err, size_t errlen)
     }
     if (device < 0 || device >= n) { snprintf(err, errlen, "device %d out of range (%d devices)", device, n); return 1; }
     if ((e = cudaSetDevice(device)) != cudaSuccess) { snprintf(err, errlen, "cudaSetDevice: %s", cudaGetErrorString(e)); return 1; }
-    cudaStream_t s;
-    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) { snprintf(err, errlen, "cudaStreamCreate: %s", cudaGetErrorString(e)); return 1; }
-    *stream_out = (void *)s;
-    g_err[0] = 0;
+    BeStream *b = new (std::nothrow) BeStream();
+    if (!b) { snprintf(err, errlen, "out of host memory"); return 1; }
+    b->launches = 0; b->err[0] = 0;
+    if ((e = cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking)) != cudaSuccess) { snprintf(err, errlen, "cudaStreamCreate: %s", cudaGetErrorString(e)); delete b; return 1; }
+    *stream_out = (void *)b;
     return 0;
 }
-void be_shutdown(void *s) { if (s) cudaStreamDestroy(ST(s)); }
+void be_shutdown(void *s) { if (s) { cudaStreamDestroy(ST(s)); delete (BeStream *)s; } }
 void be_bind(int device) { cudaSetDevice(device); }
 void *be_malloc(size_t bytes)
 {
@@ -1170,32 +1191,34 @@ void *be_host_alloc(size_t bytes)
     return p;
 }
 void be_host_free(void *p) { if (p) cudaFreeHost(p); }
-int be_h2d(void *s, void *d, const void *h, size_t n) { if (n) cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ST(s)); note_err("h2d"); return 0; }
-int be_d2h(void *s, void *h, const void *d, size_t n) { if (n) cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, ST(s)); note_err("d2h"); return 0; }
-int be_d2d(void *s, void *d, const void *src, size_t n) { if (n) cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, ST(s)); note_err("d2d"); return 0; }
-int be_memset(void *s, void *d, int b, size_t n) { if (n) cudaMemsetAsync(d, b, n, ST(s)); note_err("memset"); return 0; }
+int be_h2d(void *s, void *d, const void *h, size_t n) { if (n) cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ST(s)); note_err(s, "h2d"); return 0; }
+int be_d2h(void *s, void *h, const void *d, size_t n) { if (n) cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, ST(s)); note_err(s, "d2h"); return 0; }
+int be_d2d(void *s, void *d, const void *src, size_t n) { if (n) cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, ST(s)); note_err(s, "d2d"); return 0; }
+int be_memset(void *s, void *d, int b, size_t n) { if (n) cudaMemsetAsync(d, b, n, ST(s)); note_err(s, "memset"); return 0; }
 int be_sync(void *s, char *err, size_t errlen)
 {
     cudaError_t e = cudaStreamSynchronize(ST(s));
-    if (e != cudaSuccess && !g_err[0]) snprintf(g_err, sizeof g_err, "stream sync: %s", cudaGetErrorString(e));
-    if (g_err[0]) { snprintf(err, errlen, "%s", g_err); return 1; }
+    BeStream *b = (BeStream *)s;
+    if (e != cudaSuccess && !b->err[0]) snprintf(b->err, sizeof b->err, "stream sync: %s", cudaGetErrorString(e));
+    if (b->err[0]) { snprintf(err, errlen, "%s", b->err); return 1; }
     return 0;
 }
 void *be_event_create(void) { cudaEvent_t e; cudaEventCreate(&e); return (void *)e; }
 void be_event_destroy(void *e) { cudaEventDestroy((cudaEvent_t)e); }
 void be_event_record(void *s, void *e) { cudaEventRecord((cudaEvent_t)e, ST(s)); }
 float be_event_ms(void *a, void *b) { float ms = 0; if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) { (void)cudaGetLastError(); ms = 0; } return ms; }
-uint64_t be_launch_count(void) { return g_launches; }
+uint64_t be_launch_count(void *s) { return ((BeStream *)s)->launches; }
 void be_copy_words(void *s, void *dst, const void *src, size_t bytes)
 {
     k_copy_words<<<1, 128, 0, ST(s)>>>((uint32_t *)dst, (const uint32_t *)src, (uint32_t)(bytes / 4));
-    note_err("k_copy_words");
+    note_err(s, "k_copy_words");
 }
 
-void be_extract_sizes(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
-                      uint32_t *sizes, uint32_t *live)
+void be_extract_sizes(void *s, const uint32_t *cm, uint64_t cm_buckets, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
+                      uint32_t *sizes, uint32_t *live, uint32_t *bad)
 {
-    if (n) LAUNCH(k_extract_sizes, blocks_for(n), TPB, s, cm, crefs, n, stencil, stencil_size, sizes, live);
+    cudaMemsetAsync(bad, 0, sizeof(uint32_t), ST(s));
+    if (n) LAUNCH(k_extract_sizes, blocks_for(n), TPB, s, cm, cm_buckets, crefs, n, stencil, stencil_size, sizes, live, bad);
 }
 void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
                       const uint32_t *newid, uint32_t *arena, uint64_t *refs)
@@ -1227,14 +1250,15 @@ void be_ot_order(void *s, const SgView &v)
         LAUNCH(k_items<SGK_IDSORT_LONG>, blocks_for(v.nlit), TPB, s, v, v.nlit);
     }
 }
-void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
+void be_ingest_sizes(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, uint32_t *sizes, uint32_t *bad)
 {
-    if (n) LAUNCH(k_ingest_sizes, blocks_for(n), TPB, s, arena, refs, n, sizes);
+    cudaMemsetAsync(bad, 0, sizeof(uint32_t), ST(s));
+    if (n) LAUNCH(k_ingest_sizes, blocks_for(n), TPB, s, arena, refs, n, n_buckets, sizes, bad);
 }
-void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap)
+void be_ingest_fused(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, sg_u4 *hdr, uint32_t *lits, uint32_t *gap)
 {
     cudaMemsetAsync(gap, 0, sizeof(uint32_t), ST(s));
-    if (n) LAUNCH(k_ingest_fused, blocks_for(n), TPB, s, arena, refs, n, hdr, lits, gap);
+    if (n) LAUNCH(k_ingest_fused, blocks_for(n), TPB, s, arena, refs, n, n_buckets, hdr, lits, gap);
 }
 void be_ingest_copy(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, const uint32_t *offs, sg_u4 *hdr, uint32_t *lits)
 {
@@ -1344,7 +1368,7 @@ int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_
     void *args[] = { (void *)&vv, (void *)&wl0, (void *)&wl1, (void *)&b0, (void *)&grow };
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_elect_persistent, dim3((unsigned)(blocks_per_sm * sms)), dim3(SG_ELECT_TPB), args, 0, ST(s));
     if (e != cudaSuccess) { (void)cudaGetLastError(); blocks_per_sm = 0; return 1; }
-    g_launches++;
+    ((BeStream *)s)->launches++;
     return 0;
 }
 void be_acting_flags(void *s, const SgView &v, uint32_t *fa, uint32_t *fe) { if (v.nvars) LAUNCH(k_acting_flags, blocks_for(v.nvars), TPB, s, v, fa, fe); }
@@ -1377,7 +1401,7 @@ void be_items(void *s, int kind, const SgView &v, uint32_t n)
     case SGK_ERE_APPLY: LAUNCH(k_items<SGK_ERE_APPLY>, blocks_for(32ull * n, 128), 128, s, v, n); break;
     case SGK_ERE_FLAG01: LAUNCH(k_items<SGK_ERE_FLAG01>, blocks_for(n), TPB, s, v, n); break;
     case SGK_ERE_LIST: LAUNCH(k_items<SGK_ERE_LIST>, blocks_for(n), TPB, s, v, n); break;
-    default: snprintf(g_err, sizeof g_err, "be_items: bad kind %d", kind);
+    default: { BeStream *b = (BeStream *)s; snprintf(b->err, sizeof b->err, "be_items: bad kind %d", kind); }
     }
 }
 void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
@@ -1403,7 +1427,7 @@ void be_sort_units(void *s, const SgView &v, uint32_t n)
     uint32_t *tk = (uint32_t *)be_malloc(4ull * n), *tv = (uint32_t *)be_malloc(4ull * n);
     uint32_t *tmp = (uint32_t *)be_malloc(4ull * be_sort_tmp_words(n));
     SgUnit *ut = (SgUnit *)be_malloc(sizeof(SgUnit) * (size_t)n);
-    if (!keys || !idx || !tk || !tv || !tmp || !ut) { snprintf(g_err, sizeof g_err, "be_sort_units: out of memory"); }
+    if (!keys || !idx || !tk || !tv || !tmp || !ut) { BeStream *b = (BeStream *)s; snprintf(b->err, sizeof b->err, "be_sort_units: out of memory"); }
     else {
         for (int which = 0; which < 2; ++which) {
             LAUNCH(k_units_keys, blocks_for(n), TPB, s, v, n, keys, idx, which);

@@ -43,7 +43,7 @@ struct sigma_ctx {
     char err[512] = { 0 };
     const volatile int *interrupt = nullptr;
     int stop_phase = -1, stop_stage = -1;
-    bool uploaded = false, executed = false;
+    bool uploaded = false, executed = false, stopped = false;
 
     sigma_opts opts;
     /* uploaded input (pristine, device + small host scalars) */
@@ -134,14 +134,14 @@ struct Stage {
         c->cur_stage = st;
         a = get_event(c);
         be_event_record(c->stream, a);
-        l0 = be_launch_count();
+        l0 = be_launch_count(c->stream);
         c->rep.stage_bytes[st] += bytes;
     }
     ~Stage() {
         void *b = get_event(c);
         be_event_record(c->stream, b);
         c->evs.push_back({ a, b, stage });
-        c->rep.stage_launches[stage] += (uint32_t)(be_launch_count() - l0);
+        c->rep.stage_launches[stage] += (uint32_t)(be_launch_count(c->stream) - l0);
         c->cur_stage = -1;
     }
 };
@@ -226,15 +226,26 @@ int stage_ingest(sigma_ctx *c)
     NOMEM(c->hdr.ensure(cap_cls)); NOMEM(c->lits.ensure(cap_lits));
     NOMEM(c->c_sizes.ensure(n + 1)); NOMEM(c->c_newoff.ensure(n + 1));
     NOMEM(c->scantmp.ensure(be_scan_tmp_words((uint32_t)cap_cls) + be_scan_tmp_words(c->nlit + 1) + 64));
-    be_ingest_fused(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->hdr.p, c->lits.p, c->totals.p + 8);
+    be_ingest_fused(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->in_buckets, c->hdr.p, c->lits.p, c->totals.p + 8);
     CK(pull_totals(c, 9));
-    if (c->h_totals[8]) {                                  /* arena with gaps: general path */
-        be_ingest_sizes(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_sizes.p);
-        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, nullptr, c->scantmp.p);
+    if (c->h_totals[8]) {                                  /* arena with gaps (or malformed): general path */
+        be_ingest_sizes(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->in_buckets, c->c_sizes.p, c->totals.p + 8);
+        be_scan_u32(c->stream, c->c_sizes.p, c->c_newoff.p, n, c->totals.p + 9, c->scantmp.p);
+        CK(pull_totals(c, 10));
+        /* the sigma_formula contract (include/sigma_b200.h): every ref and every size word stays inside the arena, and the
+         * clauses account for exactly n_buckets - 3 n_clauses literals (an arena with unused words is fine, overlapping or
+         * truncated records are not) */
+        if (c->h_totals[8]) return fail(c, SIGMA_E_ARG, "malformed arena: a clause ref or size points outside n_buckets");
+        if ((uint64_t)c->h_totals[9] > L) return fail(c, SIGMA_E_ARG, "malformed arena: clause sizes exceed n_buckets - 3 n_clauses");
         be_ingest_copy(c->stream, c->d_arena_in.p, c->d_refs_in.p, n, c->c_newoff.p, c->hdr.p, c->lits.p);
+        c->in_literals = c->h_totals[9];
+        c->pool_used = c->h_totals[9];
+        c->n_cls = n;
+        return SIGMA_OK;
     }
     c->n_cls = n;
     c->pool_used = (uint32_t)L;
+    c->in_literals = L;                                    /* gap-free: exactly the words that are not headers */
     return SIGMA_OK;
 }
 
@@ -770,7 +781,12 @@ int stage_export(sigma_ctx *c)
 }
 
 bool interrupted(sigma_ctx *c) { return c->interrupt && *c->interrupt; }
-bool stop_here(sigma_ctx *c, int phase, int stage) { return c->stop_phase == phase && c->stop_stage == stage; }
+bool stop_here(sigma_ctx *c, int phase, int stage)
+{
+    if (c->stop_phase != phase || c->stop_stage != stage) return false;
+    c->stopped = true;
+    return true;
+}
 
 int run_phases(sigma_ctx *c)
 {
@@ -934,6 +950,13 @@ int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, cons
         if (in->n_buckets >= 0xFFFFFFF0ull) return fail(c, SIGMA_E_UNSUPPORTED, "arena exceeds 32-bit bucket offsets");
         if (in->n_buckets < 3ull * in->n_clauses) return fail(c, SIGMA_E_ARG, "n_buckets smaller than the clause headers");
     }
+    if (in->trail_size > in->nvars) return fail(c, SIGMA_E_ARG, "trail_size exceeds nvars");
+    if (in->propagated > in->trail_size) return fail(c, SIGMA_E_ARG, "propagated exceeds trail_size");
+    if (in->trail_size && !in->trail) return fail(c, SIGMA_E_ARG, "null trail");
+    if (in->model_size && !in->model) return fail(c, SIGMA_E_ARG, "null model");
+    if (in->nvars >= 0x1FFFFFF0u) return fail(c, SIGMA_E_UNSUPPORTED, "more than 2^29 variables");   /* election word: rank | status << 29 */
+    if (!cnf && in->n_literals > in->n_buckets - 3ull * in->n_clauses)
+        return fail(c, SIGMA_E_ARG, "n_literals exceeds n_buckets - 3 n_clauses");    /* the count used is derived from the arena itself */
     c->uploaded = c->executed = false;
     c->evused = 0; c->evs.clear();
     memset(&c->rep, 0, sizeof c->rep);
@@ -985,13 +1008,14 @@ int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, cons
     if (cnf) {
         /* extract(orgs); extract(learnts) (simplify.cpp:118-133,146-148): sizes -> two scans -> write */
         const uint32_t ns = (uint32_t)n_src;
-        be_extract_sizes(c->stream, c->d_cm.p, c->d_crefs.p, ns, c->d_stencil.p, cnf->stencil_size, c->c_sizes.p, c->c_flags.p);
+        be_extract_sizes(c->stream, c->d_cm.p, cnf->cm_buckets, c->d_crefs.p, ns, c->d_stencil.p, cnf->stencil_size, c->c_sizes.p, c->c_flags.p, c->totals.p + 8);
         {
             SgScanSet ss = { { c->c_sizes.p, c->c_flags.p, nullptr, nullptr }, { c->c_newoff.p, c->c_newid.p, nullptr, nullptr },
                              { c->totals.p + 0, c->totals.p + 1, nullptr, nullptr } };
             be_scan_multi(c->stream, ss, 2, ns, c->scantmp.p);
         }
-        CK(pull_totals(c, 2));
+        CK(pull_totals(c, 9));
+        if (c->h_totals[8]) return fail(c, SIGMA_E_ARG, "malformed clause database: a ref or a record points outside cm_buckets");
         const uint32_t buckets = ns ? c->h_totals[0] : 0, ncls = ns ? c->h_totals[1] : 0;
         NOMEM(c->d_arena_in.ensure((size_t)buckets + 16)); NOMEM(c->d_refs_in.ensure((size_t)ncls + 16));
         be_extract_write(c->stream, c->d_cm.p, c->d_crefs.p, ns, c->c_sizes.p, c->c_newoff.p, c->c_newid.p, c->d_arena_in.p, c->d_refs_in.p);
@@ -1044,12 +1068,12 @@ int sigma_execute(sigma_ctx *c)
     c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
     c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
     c->evused = 0; c->evs.clear();
-    c->executed = false; c->cm_built = false;
+    c->executed = false; c->cm_built = false; c->stopped = false;
     c->ot_valid = false;
     { const char *e = getenv("SIGMA_OT_INCREMENTAL"); c->ot_incremental = !(e && e[0] == '0'); }
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
     { const char *e = getenv("SIGMA_NBH_FUSED"); c->nbh_fused = e ? atoi(e) : 0; }
-    c->launches0 = be_launch_count();
+    c->launches0 = be_launch_count(c->stream);
     c->n_syncs = 0; c->count_fresh = false; c->push_in_flight = false; c->prev_max_valid = false;
     c->sync_trace = getenv("SIGMA_SYNC_TRACE") != nullptr;
     const uint32_t V = c->nvars, nlit = c->nlit;
@@ -1075,7 +1099,7 @@ int sigma_execute(sigma_ctx *c)
     /* resolve timers */
     for (const StageEv &e : c->evs) c->rep.stage_ms[e.stage] += be_event_ms(e.a, e.b);
     c->rep.stage_ms[SIGMA_T_TOTAL_DEVICE] = be_event_ms(e0, e1);
-    c->rep.kernel_launches = be_launch_count() - c->launches0;
+    c->rep.kernel_launches = be_launch_count(c->stream) - c->launches0;
     c->rep.reserved[4] = c->n_syncs;
     c->rep.status = rc;
     c->rep.literals_in = c->in_literals;
@@ -1088,7 +1112,7 @@ int sigma_execute(sigma_ctx *c)
     c->rep.strengthened = (int64_t)s.strengthened; c->rep.units = (int64_t)s.units_forced;
     c->rep.sort_ties_gt24 = (int64_t)s.sort_ties_gt24;
     c->rep.reserved[0] = s.ere_events; c->rep.reserved[1] = s.ere_dirty_vars; c->rep.reserved[2] = s.ere_full_pairs; c->rep.reserved[3] = s.ere_event_pairs;
-    c->executed = (rc == SIGMA_OK);
+    c->executed = (rc == SIGMA_OK) && !c->stopped;            /* a run cut short by sigma_set_stop has no result to download */
     return rc;
 }
 

@@ -53,14 +53,19 @@ void *be_event_create(void) { return new Ev{ 0 }; }
 void be_event_destroy(void *e) { delete (Ev *)e; }
 void be_event_record(void *, void *e) { ((Ev *)e)->t = now_ms(); }
 float be_event_ms(void *a, void *b) { return (float)(((Ev *)b)->t - ((Ev *)a)->t); }
-uint64_t be_launch_count(void) { return g_launches; }
+uint64_t be_launch_count(void *) { return g_launches; }
 void be_copy_words(void *, void *d, const void *s, size_t n) { memmove(d, s, n); }
 
-void be_extract_sizes(void *, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
-                      uint32_t *sizes, uint32_t *live)
+void be_extract_sizes(void *, const uint32_t *cm, uint64_t cm_buckets, const uint64_t *crefs, uint32_t n, const uint8_t *stencil, uint64_t stencil_size,
+                      uint32_t *sizes, uint32_t *live, uint32_t *bad)
 {
     g_launches++;
-    for (uint32_t i : item_order(n)) { sizes[i] = sg_extract_size(cm, stencil, stencil_size, crefs[i]); live[i] = sizes[i] != 0; }
+    *bad = 0;
+    for (uint32_t i : item_order(n)) {
+        sizes[i] = sg_extract_size(cm, cm_buckets, stencil, stencil_size, crefs[i]);
+        if (sizes[i] == SG_EXTRACT_BAD) { *bad = 1; sizes[i] = 0; }
+        live[i] = sizes[i] != 0;
+    }
 }
 void be_extract_write(void *, const uint32_t *cm, const uint64_t *crefs, uint32_t n, const uint32_t *sizes, const uint32_t *newoff,
                       const uint32_t *newid, uint32_t *arena, uint64_t *refs)
@@ -110,19 +115,27 @@ void be_scan_multi(void *s, const SgScanSet &ss, uint32_t count, uint32_t n, uin
 {
     for (uint32_t k = 0; k < count; ++k) be_scan_u32(s, ss.in[k], ss.out[k], n, ss.total[k], tmp);
 }
-void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *sizes)
+void be_ingest_sizes(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, uint32_t *sizes, uint32_t *bad)
 {
     g_launches++;
-    for (uint32_t i = 0; i < n; ++i) sizes[i] = arena[refs[i] + 2];
+    *bad = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t r = refs[i];
+        sizes[i] = 0;
+        if (r + 3 > n_buckets) { *bad = 2; continue; }
+        if (r + 3 + arena[r + 2] > n_buckets) { *bad = 2; continue; }
+        sizes[i] = arena[r + 2];
+    }
 }
-void be_ingest_fused(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, sg_u4 *hdr, uint32_t *lits, uint32_t *gap)
+void be_ingest_fused(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, sg_u4 *hdr, uint32_t *lits, uint32_t *gap)
 {
     g_launches++;
     *gap = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint64_t r = refs[i];
+        if (r + 3 > n_buckets || r + 3 + arena[r + 2] > n_buckets) { *gap = 1; return; }
         const uint32_t size = arena[r + 2];
-        if ((i + 1 < n && refs[i + 1] != r + 3 + size) || (i == 0 && r != 0) || r < 3ull * i) { *gap = 1; return; }
+        if ((i + 1 < n && refs[i + 1] != r + 3 + size) || (i + 1 == n && r + 3 + size != n_buckets) || (i == 0 && r != 0) || r < 3ull * i) { *gap = 1; return; }
         sg_u4 h; h.x = (uint32_t)(r - 3ull * i); h.y = size; h.z = arena[r]; h.w = arena[r + 1];
         hdr[i] = h;
         for (uint32_t k = 0; k < size; ++k) lits[h.x + k] = arena[r + 3 + k];

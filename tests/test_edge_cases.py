@@ -114,6 +114,48 @@ def _abi_errors(lib_path):
     bo = B.read(os.path.join(GOLDEN, "fuzz_ok_a.out"))
     assert parity.diff(out, bo) == []
     assert lib.sigma_strerror(sigma.SIGMA_E_NOSPACE).decode() != ""
+    # malformed input is answered with SIGMA_E_ARG, never followed (the ABI's promise): scalars first ...
+    def code_of(mutate, run=False):
+        b2 = B.read(os.path.join(GOLDEN, "fuzz_ok_a.in"))
+        f2 = sigma.Sigma.make_formula(b2)
+        keep = mutate(b2, f2)                       # noqa: F841  (keeps replaced arrays alive)
+        rc = lib.sigma_upload(s.ctx, C.byref(sigma.Sigma.make_opts(b2.opts)), C.byref(f2))
+        if rc == sigma.SIGMA_OK and run:
+            rc = lib.sigma_execute(s.ctx)
+        return rc
+
+    def set_(f2, **kw):
+        for k, v in kw.items():
+            setattr(f2, k, v)
+    assert code_of(lambda b2, f2: set_(f2, trail_size=b2.nvars + 1)) == sigma.SIGMA_E_ARG
+    assert code_of(lambda b2, f2: set_(f2, propagated=f2.trail_size + 1)) == sigma.SIGMA_E_ARG
+    assert code_of(lambda b2, f2: set_(f2, n_literals=f2.n_buckets)) == sigma.SIGMA_E_ARG
+    assert code_of(lambda b2, f2: set_(f2, n_buckets=3 * f2.n_clauses - 1)) == sigma.SIGMA_E_ARG
+    # ... then refs / size words that leave the arena: caught on the device by the ingest kernels
+
+    def bad_ref(b2, f2):
+        r = b2.refs.copy(); r[r.size // 2] = b2.arena.size + 100
+        f2.refs = r.ctypes.data_as(C.c_void_p)
+        return r
+
+    def bad_size(b2, f2):
+        a = b2.arena.copy(); a[int(b2.refs[b2.refs.size // 2]) + 2] = 0x7FFFFFF0
+        f2.arena = a.ctypes.data_as(C.c_void_p)
+        return a
+
+    def overlap(b2, f2):                            # two refs to the same record: more literals than the arena holds
+        r = b2.refs.copy(); r[1:] = r[0]; a = b2.arena.copy(); a[int(r[0]) + 2] = 40
+        f2.refs, f2.arena = r.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p)
+        return r, a
+    assert code_of(bad_ref, run=True) == sigma.SIGMA_E_ARG
+    assert code_of(bad_size, run=True) == sigma.SIGMA_E_ARG
+    assert code_of(overlap, run=True) == sigma.SIGMA_E_ARG
+    # a run cut short by sigma_set_stop leaves nothing to download
+    s.upload(bi)
+    s.set_stop(0, "elect")
+    s.execute()
+    assert lib.sigma_download(s.ctx, C.byref(sigma.SigmaFormula())) == sigma.SIGMA_E_ARG
+    s.set_stop(-1, -1)
     # collect_freq = 0 would divide by zero in the reference (solve.hpp:628): rejected
     with pytest.raises(sigma.SigmaError) as e:
         s.simplify(bi, dict(bi.opts, collect_freq=0))
