@@ -214,8 +214,18 @@ int  sigma_download_cnf(sigma_ctx *ctx, sigma_cnf_out *out, sigma_formula *rest)
 void *sigma_host_alloc(uint64_t bytes);
 void  sigma_host_free(void *p);
 
-/* host-polled interrupt flag (reference `interrupted`, control.cpp:130-159) */
-void sigma_set_interrupt_flag(sigma_ctx *ctx, const volatile int *flag);
+/* pin / unpin memory the caller already owns (the solver's malloc'ed clause arena, malloc.hpp:60-69) for the duration
+ * of an upload or download, so that the copy runs at PCIe rate without changing the solver's allocator.  Returns
+ * SIGMA_OK or SIGMA_E_CUDA (the memory then simply stays pageable). */
+int   sigma_host_register(void *p, uint64_t bytes);
+int   sigma_host_unregister(void *p);
+
+/* host-polled interrupt flag: the address of the reference's `bool interrupted` (solve.hpp:126, set by
+ * Solver::interrupt() from the signal handlers, control.cpp:130-159).  Polled where the reference polls INTERRUPTED
+ * (simplify.cpp:176,206; subsume.cpp:26; bounded.cpp:31): at the top of every phase, before SUB, before VE and after
+ * the trailing prop(); sigma_execute then returns SIGMA_INTERRUPTED and leaves no result (the uploaded input stays
+ * valid, so the call can be repeated).  NULL detaches. */
+void sigma_set_interrupt_flag(sigma_ctx *ctx, const volatile unsigned char *flag);
 
 /* stage-level parity hooks: stop after `stage` (SIGMA_T_* id of the stage) of `phase`, then copy
  * a named device array to the host.  Names: hdr lits ot_off ot_len ot_data occ order elected

@@ -13,7 +13,9 @@
 // in the sectioned binary format read by seqfrost_b200/boundary.py.  It is also the
 // "reference" CPU baseline: it times the replaced region (simplify.cpp:180-206) on one core.
 //
-// usage: ref_sigma <file.cnf> [reference CLI options] [--sgin=..] [--sgout=..] [--trace=..] [--repeat-timing]
+//   --incr=seed:permille:nassume   incremental solver (Solver() + iadd/itoClause): isolve()'s prologue, a seeded subset of the variables
+//                   frozen through ifreeze() plus `nassume` assumptions; the .in then carries the `ifrozen` mask
+// usage: ref_sigma <file.cnf> [reference CLI options] [--sgin=..] [--sgout=..] [--trace=..] [--incr=..]
 //
 // All members touched are public/protected in the reference's Solver (solve.hpp:75-844);
 // the reference sources are not modified.
@@ -65,6 +67,32 @@ void write_unsat_at_exit() {
 class Probe : public Solver {
 public:
 	Probe(const std::string& path) : Solver(path) {}
+	Probe() : Solver() {}                 // the library's incremental constructor (solveinc.cpp:26-49)
+
+	// incremental front end: feeds a DIMACS file through the public incremental API, variable by variable and clause by
+	// clause (iadd / itoClause, addinc.cpp:33-150), as an embedding program would.  (The reference's own -parseincr path
+	// is not usable: dimacs.cpp:94 calls makeClause() before it looks at the option and stops with "too many variables".)
+	bool loadIncremental(const std::string& path) {
+		FILE* f = fopen(path.c_str(), "r");
+		if (!f) return false;
+		Lits_t in_c, org;
+		char tok[64];
+		int c;
+		while ((c = fgetc(f)) != EOF) {
+			if (c == 'c' || c == 'p') { while ((c = fgetc(f)) != EOF && c != '\n'); continue; }
+			if (c == ' ' || c == '\n' || c == '\r' || c == '\t') continue;
+			int n = 0;
+			do { if (n < 62) tok[n++] = (char)c; c = fgetc(f); } while (c != EOF && c != ' ' && c != '\n' && c != '\r' && c != '\t');
+			tok[n] = 0;
+			const long x = atol(tok);
+			if (x == 0) { if (!itoClause(in_c, org)) { fclose(f); return false; } continue; }
+			const uint32 v = (uint32)(x < 0 ? -x : x);
+			while (v > inf.maxVar) iadd();
+			org.push(V2DEC(v, LIT_ST(x < 0)));
+		}
+		fclose(f);
+		return true;
+	}
 
 	void dumpStore(Writer& w) {
 		// SCNF arena verbatim (sclause.hpp:45-49 AoS, simptypes.hpp:48-95) + refs in allocation order
@@ -98,6 +126,8 @@ public:
 		w.section("trail", trail.data(), uint64_t(trail.size()) * 4);
 		w.section("vorg", vorg.data(), uint64_t(vorg.size()) * 4);
 		w.section("model", model.resolved.data(), uint64_t(model.resolved.size()) * 4);
+		if (incremental && ifrozen.size() >= inf.maxVar + 1)   // the mask iassumed() reads (solve.hpp:816)
+			w.section("ifrozen", ifrozen.data(), uint64_t(inf.maxVar) + 1);
 		int32_t o[32] = { 0 };
 		o[0] = opts.phases; o[1] = opts.phase_lits_min; o[2] = opts.mu_pos; o[3] = opts.mu_neg;
 		o[4] = opts.lcve_max_occurs; o[5] = opts.lcve_clause_max; o[6] = opts.lcve_min_vars;
@@ -148,10 +178,37 @@ public:
 		w.section("stencil", cm.stencil(), top);
 	}
 
+	// incremental mode (--incr=seed:permille:nassume; the formula came in through iadd()/itoClause()): the prologue of isolve() (solveinc.cpp:82-93) with a seeded subset of the
+	// variables frozen through ifreeze() (assume.cpp:45) and `nassume` assumptions through iassume() (assume.cpp:68), so
+	// that LCVE skips them (iassumed, lcve.cpp:67, solve.hpp:816).  Returns false when BCP finds a root conflict.
+	bool incrPrologue(const uint64_t seed, const uint32 permille, const uint32 nassume) {
+		iallocSpace();
+		iunassume();
+		if (BCP()) return false;
+		initLimits();
+		uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+		auto next = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+		Lits_t assumed;
+		for (uint32 v = 1; v <= inf.maxVar; ++v) {
+			const uint64_t r = next();
+			if (sp->state[v].state || !UNASSIGNED(sp->value[V2L(v)])) continue;
+			if (r % 1000 < permille) ifreeze(v);
+			else if ((uint32)assumed.size() < nassume && (r >> 20) % 97 == 0) assumed.push(V2DEC(v, LIT_ST((r >> 40) & 1)));
+		}
+		iassume(assumed);
+		return true;
+	}
+
 	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts, const std::string& cmin = std::string(),
-		const std::string& cmout = std::string()) {
+		const std::string& cmout = std::string(), const std::string& incr = std::string()) {
 		using clk = std::chrono::steady_clock;
 		timer.start();
+		if (!incr.empty()) {
+			unsigned long long seed = 1; unsigned permille = 100, nassume = 0;
+			sscanf(incr.c_str(), "%llu:%u:%u", &seed, &permille, &nassume);
+			if (!incrPrologue(seed, permille, nassume)) { fprintf(stderr, "ref_sigma: incremental prologue failed\n"); return 7; }
+		}
+		else
 		initLimits();
 		if (presolve_conflicts > 0 && !presolve(presolve_conflicts)) { fprintf(stderr, "ref_sigma: solved during the prologue\n"); return 6; }
 		if (!opts.preprocess_en) { fprintf(stderr, "ref_sigma: preprocess disabled\n"); return 2; }
@@ -259,7 +316,7 @@ int main(int argc, char** argv)
 	INT_OPT opt_timeout("timeout", "set out-of-time limit in seconds", 0, INT32R(0, INT32_MAX));
 	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
-	std::string sgin, sgout, tracep, cmin, cmout;
+	std::string sgin, sgout, tracep, cmin, cmout, incr;
 	long long presolve_conflicts = 0;
 	std::vector<char*> pass;
 	for (int i = 0; i < argc; ++i) {
@@ -269,6 +326,7 @@ int main(int argc, char** argv)
 		else if (a.rfind("--trace=", 0) == 0) tracep = a.substr(8);
 		else if (a.rfind("--cmin=", 0) == 0) cmin = a.substr(7);
 		else if (a.rfind("--cmout=", 0) == 0) cmout = a.substr(8);
+		else if (a.rfind("--incr=", 0) == 0) incr = a.substr(7);
 		else if (a.rfind("--presolve-conflicts=", 0) == 0) presolve_conflicts = atoll(a.substr(21).c_str());
 		else pass.push_back(argv[i]);
 	}
@@ -282,9 +340,15 @@ int main(int argc, char** argv)
 		if (quiet_en || competition_en) verbose = 0;
 		else if (!verbose || competition_en) quiet_en = true;
 		std::string formula = argv[1];
-		Probe* p = new Probe(formula);
+		Probe* p = nullptr;
+		if (incr.empty()) p = new Probe(formula);
+		else {
+			p = new Probe();
+			solver = p;
+			if (!p->loadIncremental(formula)) { fprintf(stderr, "ref_sigma: incremental load failed (empty clause or conflicting units)\n"); g_out_written = true; _exit(8); }
+		}
 		solver = p;
-		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout);
+		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout, incr);
 		g_out_written = g_out_written || rc != 0;
 		fflush(stdout);
 		_exit(rc); // skip the reference's destructors (process-global singletons)

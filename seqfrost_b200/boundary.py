@@ -64,6 +64,7 @@ class Boundary:
     trail: np.ndarray = None             # uint32
     vorg: np.ndarray = None              # uint32[nvars+1]
     model: np.ndarray = None             # uint32 (MODEL::resolved)
+    ifrozen: np.ndarray = None           # uint8[nvars+1] or None: incremental freeze mask (solve.hpp:789,816; lcve.cpp:67)
     opts: dict = None
     stats: np.ndarray = None
 
@@ -123,6 +124,8 @@ def read(path) -> Boundary:
         b.opts = {k: int(o[i]) for i, k in enumerate(OPT_NAMES)}
     if "stats" in sec:
         b.stats = np.frombuffer(sec["stats"], dtype=np.int64).copy()
+    if "ifrozen" in sec:
+        b.ifrozen = np.frombuffer(sec["ifrozen"], dtype=np.uint8).copy()
     return b
 
 
@@ -236,6 +239,8 @@ def write(path, b: Boundary):
             return
         for name in ("state", "value", "trail", "vorg", "model", "arena", "refs"):
             section(f, name, getattr(b, name))
+        if b.ifrozen is not None:
+            section(f, "ifrozen", b.ifrozen)
         if b.opts:
             section(f, "opts", np.array([b.opts.get(k, 0) for k in OPT_NAMES] + [0] * (32 - len(OPT_NAMES)), dtype=np.int32))
 

@@ -53,6 +53,8 @@ void *be_malloc(size_t bytes);                 /* NULL on failure */
 void  be_free(void *p);
 void *be_host_alloc(size_t bytes);             /* pinned host memory */
 void  be_host_free(void *p);
+int   be_host_register(void *p, size_t bytes);   /* pin caller-owned pageable memory; 0 = ok */
+int   be_host_unregister(void *p);
 int   be_h2d(void *stream, void *dst, const void *src, size_t bytes);
 int   be_d2h(void *stream, void *dst, const void *src, size_t bytes);
 int   be_d2d(void *stream, void *dst, const void *src, size_t bytes);

@@ -1191,6 +1191,16 @@ void *be_host_alloc(size_t bytes)
     return p;
 }
 void be_host_free(void *p) { if (p) cudaFreeHost(p); }
+int be_host_register(void *p, size_t bytes)
+{
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+    return 0;
+}
+int be_host_unregister(void *p)
+{
+    if (cudaHostUnregister(p) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+    return 0;
+}
 int be_h2d(void *s, void *d, const void *h, size_t n) { if (n) cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, ST(s)); note_err(s, "h2d"); return 0; }
 int be_d2h(void *s, void *h, const void *d, size_t n) { if (n) cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, ST(s)); note_err(s, "d2h"); return 0; }
 int be_d2d(void *s, void *d, const void *src, size_t n) { if (n) cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, ST(s)); note_err(s, "d2d"); return 0; }

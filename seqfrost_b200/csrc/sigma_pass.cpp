@@ -41,7 +41,7 @@ struct sigma_ctx {
     int device = 0;
     void *stream = nullptr;
     char err[512] = { 0 };
-    const volatile int *interrupt = nullptr;
+    const volatile unsigned char *interrupt = nullptr;
     int stop_phase = -1, stop_stage = -1;
     bool uploaded = false, executed = false, stopped = false;
 
@@ -115,6 +115,8 @@ int ctx_sync(sigma_ctx *c)
     if (c->sync_trace) fprintf(stderr, "sync %d\n", c->cur_stage);
     return be_sync(c->stream, c->err, sizeof c->err);
 }
+
+bool interrupted(sigma_ctx *c) { return c->interrupt && *c->interrupt; }
 
 int fail(sigma_ctx *c, int code, const char *msg)
 {
@@ -585,6 +587,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
                 be_items(c->stream, SGK_SORTOT_LONG, v, 2 * cnt);
             }
             v.item_base = first;
+            if (interrupted(c)) return SIGMA_INTERRUPTED;  /* subsume.cpp:26, bounded.cpp:31 */
             if (do_sub) {
                 Stage st(c, SIGMA_T_SUB);
                 be_items(c->stream, SGK_SUB, v, cnt);
@@ -621,6 +624,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
         c->phase_add_lits = add_lits;
         c->model_words += add_model;
     }
+    if (c->opts.bce_en && interrupted(c)) return SIGMA_INTERRUPTED;   /* blocked.cpp:26 */
     if (c->opts.bce_en) {                                  /* blocked.cpp:25 */
         Stage st(c, SIGMA_T_VE);
         NOMEM(c->ere_touched.ensure((size_t)c->n_cls + 16));
@@ -656,6 +660,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
 int stage_ere(sigma_ctx *c)
 {
     if (!c->opts.ere_en) return SIGMA_OK;
+    if (interrupted(c)) return SIGMA_INTERRUPTED;          /* redundancy.cpp:29 */
     if (c->opts.ere_clause_max > 256) return fail(c, SIGMA_E_UNSUPPORTED, "--redundancyclausemax above 256 is not supported");
     if (c->opts.ere_max_occurs > 65535) return fail(c, SIGMA_E_UNSUPPORTED, "--redundancymaxoccurs above 65535 is not supported");
     const uint32_t E = c->last_elected;
@@ -780,7 +785,6 @@ int stage_export(sigma_ctx *c)
     return SIGMA_OK;
 }
 
-bool interrupted(sigma_ctx *c) { return c->interrupt && *c->interrupt; }
 bool stop_here(sigma_ctx *c, int phase, int stage)
 {
     if (c->stop_phase != phase || c->stop_stage != stage) return false;
@@ -915,7 +919,9 @@ void sigma_default_opts(sigma_opts *o)
 
 const char *sigma_strerror(int code) { return (code >= 0 && code <= 7) ? kErr[code] : "unknown"; }
 const char *sigma_last_error(sigma_ctx *c) { return c ? c->err : "null context"; }
-void sigma_set_interrupt_flag(sigma_ctx *c, const volatile int *flag) { if (c) c->interrupt = flag; }
+void sigma_set_interrupt_flag(sigma_ctx *c, const volatile unsigned char *flag) { if (c) c->interrupt = flag; }
+int sigma_host_register(void *p, uint64_t bytes) { return (p && bytes && be_host_register(p, (size_t)bytes) == 0) ? SIGMA_OK : SIGMA_E_CUDA; }
+int sigma_host_unregister(void *p) { return (p && be_host_unregister(p) == 0) ? SIGMA_OK : SIGMA_E_CUDA; }
 void *sigma_host_alloc(uint64_t bytes) { return be_host_alloc((size_t)bytes); }
 void sigma_host_free(void *p) { be_host_free(p); }
 

@@ -29,7 +29,7 @@ T_N = 20
 EXPORTS = [
     "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",
     "sigma_upload", "sigma_execute", "sigma_result_sizes", "sigma_download", "sigma_get_report", "sigma_host_alloc",
-    "sigma_host_free", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot", "sigma_upload_cnf", "sigma_extracted_sizes", "sigma_cnf_out_sizes", "sigma_download_cnf",
+    "sigma_host_free", "sigma_host_register", "sigma_host_unregister", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot", "sigma_upload_cnf", "sigma_extracted_sizes", "sigma_cnf_out_sizes", "sigma_download_cnf",
 ]
 
 
@@ -125,6 +125,8 @@ def load(path=None):
     lib.sigma_host_alloc.argtypes = [C.c_uint64]
     lib.sigma_host_free.argtypes = [C.c_void_p]
     lib.sigma_set_stop.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.sigma_set_interrupt_flag.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sigma_set_interrupt_flag.restype = None
     lib.sigma_snapshot.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     return lib
 
@@ -203,7 +205,7 @@ class Sigma:
         f.n_literals = int(b.n_literals) if b.n_literals else int(b.arena.size) - 3 * int(b.refs.size)
         f.arena, f.refs, f.state, f.value = _ptr(b.arena), _ptr(b.refs), _ptr(b.state), _ptr(b.value)
         f.trail, f.trail_size, f.propagated = _ptr(b.trail), int(b.trail.size), b.propagated
-        f.vorg, f.ifrozen = _ptr(b.vorg), None
+        f.vorg, f.ifrozen = _ptr(b.vorg), _ptr(getattr(b, "ifrozen", None))     # incremental freeze mask (lcve.cpp:67)
         f.model, f.model_size = _ptr(b.model), int(b.model.size)
         f.unassigned, f.max_frozen, f.max_melted, f.simplify_calls = b.unassigned, b.max_frozen, b.max_melted, b.simplify_calls
         return f
@@ -307,6 +309,7 @@ class Sigma:
                                                        "max_melted", "propagated", "simplify_calls", "opts")})
         bi.arena, bi.refs, bi.state, bi.value = pin(b.arena), pin(b.refs), pin(b.state), pin(b.value)
         bi.trail, bi.vorg, bi.model = pin(b.trail), pin(b.vorg), pin(b.model)
+        bi.ifrozen = None if b.ifrozen is None else pin(b.ifrozen)
         bufs = dict(arena=pin(b.arena, int(b.arena.size * slack) + 1024), refs=pin(b.refs, int(b.refs.size * slack) + 1024),
                     state=pin(b.state, b.nvars + 1), value=pin(b.value, 2 * b.nvars + 2),
                     trail=pin(np.zeros(0, np.uint32), b.nvars + 16),
@@ -331,6 +334,12 @@ class Sigma:
         self.execute()
         out = self.download()
         return out, self.report()
+
+    def set_interrupt_flag(self, flag):
+        """`flag`: a one-byte numpy array the caller may set to non-zero from another thread / a signal handler (the
+        reference's `bool interrupted`, solve.hpp:126); polled where the reference polls INTERRUPTED.  None detaches."""
+        self._flag = flag
+        self.lib.sigma_set_interrupt_flag(self.ctx, _ptr(flag))
 
     def set_stop(self, phase, stage):
         self._check(self.lib.sigma_set_stop(self.ctx, phase, STAGES.index(stage) if isinstance(stage, str) else stage))

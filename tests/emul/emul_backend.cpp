@@ -42,6 +42,8 @@ void *be_malloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void be_free(void *p) { free(p); }
 void *be_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void be_host_free(void *p) { free(p); }
+int be_host_register(void *, size_t) { return 0; }
+int be_host_unregister(void *) { return 0; }
 int be_h2d(void *, void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int be_d2h(void *, void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int be_d2d(void *, void *d, const void *s, size_t n) { memmove(d, s, n); return 0; }

@@ -57,6 +57,10 @@ CASES = [
     # (ref_harness --presolve-conflicts), so the store holds learnt clauses and stats.simplify.calls == 2
     ("later_ksat3", "random_ksat", dict(nvars=2000, nclauses=7800, k=3, seed=6), ["--presolve-conflicts=3000"]),
     ("later_gates", "gate_circuit", dict(nvars=8000, seed=7), ["--presolve-conflicts=500"]),
+    # incremental solver (Solver() + iadd / itoClause), isolve()'s prologue with a seeded 15 % / 8 % of the variables frozen
+    # through ifreeze() and a few assumptions through iassume(): the .in carries the `ifrozen` mask (lcve.cpp:67)
+    ("incr_gates", "gate_circuit", dict(nvars=3000, seed=51), ["+ere", "--incr=3:150:6"]),
+    ("incr_ksat3", "random_ksat", dict(nvars=2000, nclauses=8000, k=3, seed=9), ["+ere", "--incr=5:80:4"]),
 ]
 
 
@@ -67,7 +71,10 @@ CM_CASES = {"gates_small", "ksat5_planted", "xorphp_small", "fuzz_units4", "ere_
 def main():
     if not os.path.exists(REF):
         raise SystemExit(f"{REF} missing: run `make -C oracle ref` first")
+    only = set(sys.argv[1:])                 # optional: regenerate just the named cases
     for name, gen, kw, opts in CASES:
+        if only and name not in only:
+            continue
         nv, off, lits = getattr(cnfgen, gen)(**kw)
         with tempfile.TemporaryDirectory() as td:
             cnf = os.path.join(td, name + ".cnf")

@@ -237,3 +237,40 @@ def test_arena_with_gaps_cpu_standin(emul_lib):
 @pytest.mark.gpu
 def test_arena_with_gaps_gpu(cuda_lib):
     _gapped_check(cuda_lib)
+
+
+def _incremental_and_interrupt(lib_path):
+    """(1) The incremental freeze mask (`ifrozen`, solve.hpp:789,816): LCVE must skip frozen / assumed variables
+    (lcve.cpp:67); the fixture comes from the reference's incremental solver (ref_harness --incr).  Dropping the mask must
+    change the result, otherwise the fixture would not test anything.  (2) The interrupt flag: set before the pass =>
+    SIGMA_INTERRUPTED and no result; cleared => the same uploaded input runs to the reference's result."""
+    s = sigma.Sigma(0, lib_path)
+    for name in ("incr_gates", "incr_ksat3"):
+        bi, bo = B.read(os.path.join(GOLDEN, name + ".in")), B.read(os.path.join(GOLDEN, name + ".out"))
+        assert bi.ifrozen is not None and bi.ifrozen.sum() > 0
+        out, _ = s.simplify(bi)
+        assert parity.diff(out, bo) == []
+        assert not (bi.ifrozen[out.eliminated()]).any()
+        frozen, bi.ifrozen = bi.ifrozen, None
+        out2, _ = s.simplify(bi)
+        assert frozen[out2.eliminated()].any()          # without the mask some frozen variable is eliminated
+        bi.ifrozen = frozen
+    flag = np.ones(1, dtype=np.uint8)
+    s.set_interrupt_flag(flag)
+    s.upload(bi)
+    assert s.lib.sigma_execute(s.ctx) == sigma.SIGMA_INTERRUPTED
+    assert s.lib.sigma_download(s.ctx, C.byref(sigma.SigmaFormula())) == sigma.SIGMA_E_ARG
+    flag[0] = 0
+    s.execute()
+    assert parity.diff(s.download(), bo) == []
+    s.set_interrupt_flag(None)
+    s.close()
+
+
+def test_incremental_mask_and_interrupt_cpu_standin(emul_lib):
+    _incremental_and_interrupt(emul_lib)
+
+
+@pytest.mark.gpu
+def test_incremental_mask_and_interrupt_gpu(cuda_lib):
+    _incremental_and_interrupt(cuda_lib)
