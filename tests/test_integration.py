@@ -75,3 +75,44 @@ def test_solver_with_host_side_extract_cpu_standin(tmp_path):
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
 def test_solver_with_replaced_pass_gpu(tmp_path, case):
     _check(HOST_BIN, tmp_path, *case)
+
+
+# ---- incremental library API: Solver() + iadd / itoClause / ifreeze + isolve(assumptions) ---------------------------------
+# tests/incr/incr_driver.cpp is an embedding program; built against the unmodified reference (isolve, solveinc.cpp:80-116)
+# and against the binding (sigmaISolve).  Three isolve() rounds with different assumptions on the same solver: later rounds
+# run later simplify() calls on a formula with learnt clauses, frozen and assumed variables (lcve.cpp:67).
+# --mapperc=1 keeps the reference's map() out of the way: in incremental mode it crashes (SIGSEGV in Solver::map, and in BCP
+# after a restart on harder instances) in the UNMODIFIED reference, with or without this repo's pass.
+INCR_BUILD = os.path.join(ROOT, "tests", "incr", "_build")
+INCR_ARGS = ["-quiet", "--mapperc=1", "--freeze=5,17,99,150", "--assume=3,-8,40", "--assume=-3,12", "--assume="]
+INCR_CASES = [("gates_4000", lambda: cnfgen.gate_circuit(4000, seed=8)), ("xorphp_20k", lambda: cnfgen.xor_php_mix(20000, seed=3))]
+
+
+def _incr_digest(exe, cnf):
+    r = subprocess.run([exe, cnf, *INCR_ARGS], capture_output=True, text=True, timeout=300)
+    return [l for l in r.stdout.splitlines() if l.startswith("incr")], r.stdout[-300:] + r.stderr[-300:]
+
+
+def _incr_check(exe_ours, tmp_path, name, gen):
+    cnf = str(tmp_path / (name + ".cnf"))
+    cnfgen.write_dimacs(cnf, *gen())
+    ref, tail = _incr_digest(os.path.join(INCR_BUILD, "incr_ref"), cnf)
+    assert len(ref) == 3, tail                       # three completed isolve() rounds
+    assert "melted=0 " not in ref[0]                 # the pass really eliminated variables
+    ours, tail = _incr_digest(exe_ours, cnf)
+    assert ours == ref, tail
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_SOLVER) and os.path.exists("/root/reference/src")), reason="reference not present")
+@pytest.mark.parametrize("case", INCR_CASES, ids=lambda c: c[0])
+def test_incremental_isolve_cpu_standin(tmp_path, case):
+    import __graft_entry__ as ge
+    ge.build_incr("ref")
+    _incr_check(ge.build_incr("sigma", emul=True), tmp_path, *case)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(INCR_BUILD, "incr_sigma")), reason="binaries are built in the container (build())")
+@pytest.mark.parametrize("case", INCR_CASES, ids=lambda c: c[0])
+def test_incremental_isolve_gpu(tmp_path, case):
+    _incr_check(os.path.join(INCR_BUILD, "incr_sigma"), tmp_path, *case)
