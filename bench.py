@@ -1,30 +1,39 @@
 #!/usr/bin/env python
 """bench.py - SIGmA pass throughput on B200 (BASELINE.json metric: pass ms and literals/s per GPU,
-HBM GB/s vs peak, instances at 1/2/4/8 GPUs).
+HBM GB/s vs peak, instances/s at 1/2/4/8 GPUs).
 
 A "step" is one whole SIGmA pass (reference simplify.cpp:180-210: every phase of createOT, prop,
-LCVE, sortOT, SUB, VE, counts, compaction, export) over one synthetic instance.  At N=1 the
-workload is BASELINE.json configs[1]: random 5-SAT, 2M variables / 10M clauses with planted
-subsumption work.  At N>1 every rank owns an independent instance of the same
-shape (different seed): the formula does not shard, so there is no collective on the data path
-(scaling = weak); torch.distributed is used only for the barrier and the max-over-ranks reduce.
+LCVE, sortOT, SUB, VE, ERE, counts, compaction, export) over one synthetic instance.
+
+  --config c2 (default)  BASELINE.json configs[1]: random 5-SAT, 2M variables / 10M clauses with planted
+                         subsumption work - the configuration the metric is quoted on
+  --config c1 | c3 | c4  configs[0], [2], [3] at their stated sizes (same JSON shape; results under profiles/)
+  --config c5            configs[4]: the batch of 64 mixed instances as a largest-first work queue (seqfrost_b200/batch.py)
+
+At N>1 every rank owns an independent instance of the same shape (different seed): the formula does not
+shard, so there is no collective on the data path (scaling = weak); torch.distributed is used only for the
+barrier and the max-over-ranks reduce.
 
   value : literals/s with the formula already resident in HBM (sigma_execute only), timed with
           the library's CUDA events on its own stream, max over ranks
-  e2e   : the same through the C ABI with pinned HOST buffers: sigma_upload (H2D) +
-          sigma_execute + sigma_download (D2H) inside the timed region
-  --impl reference : the unmodified reference (oracle/_ref/ref_sigma, single-threaded like
-          SeqFROST itself) timed on the host cores on a bounded sample of the same workload
+  e2e   : the same through the C ABI with pinned HOST buffers, ONE context, blocking like the solver's own call:
+          sigma_upload (H2D) + sigma_execute + sigma_download (D2H) inside the timed region.
+          e2e.pipelined is the batch-mode figure (two contexts per GPU, copies of one instance under the kernels
+          of the other)
+  binding_e2e : "Simplifier time" of `seqfrost_sigma <cnf> -no-solve` (reference solver + this pass, pageable solver
+          arenas pinned for the copies) next to the reference's own whole simplifying() call on the same file
+  --impl reference : the unmodified reference (oracle/_ref/ref_sigma, single-threaded like SeqFROST itself) on the
+          host cores, on the FULL instance of the config (same_config), one process per rank's instance at --gpus N
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -32,37 +41,86 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_sigma")
+HOST_BIN = os.path.join(ROOT, "seqfrost_b200", "host", "_build", "seqfrost_sigma")
 METRIC, UNIT = "sigma_pass_literals_per_s", "literals/s"
+CACHE = os.environ.get("SIGMA_BENCH_CACHE", "/tmp/seqfrost_b200_bench")
+REF_BUDGET_S = float(os.environ.get("SIGMA_REF_BUDGET_S", "240"))     # wall-clock cap of the reference arm's timed steps
+
+CONFIGS = {
+    "c1": dict(gen="random_ksat", kw=dict(nvars=100_000, nclauses=426_000, k=3, seed=1),
+               name="random 3-SAT 100k vars / 426k clauses, ratio 4.26 (BASELINE.json configs[0], SURVEY 8d C1)"),
+    "c2": dict(gen="planted_subsumption_ksat", kw=dict(nvars=2_000_000, nclauses=10_000_000, k=5, seed=7),
+               name="random 5-SAT 2M vars / 10M clauses + planted subsumption (BASELINE.json configs[1], SURVEY 8d C2)"),
+    "c3": dict(gen="gate_circuit", kw=dict(nvars=5_000_000, seed=11),
+               name="BMC-style gate circuit (AND/XOR/ITE/equivalence), 5M vars (BASELINE.json configs[2], SURVEY 8d C3)"),
+    "c4": dict(gen="xor_php_mix", kw=dict(nclauses=1_000_000, seed=3),
+               name="XOR chains + pigeonhole mix, 1M clauses (BASELINE.json configs[3], SURVEY 8d C4)"),
+}
 
 
-def workload(nvars, nclauses, seed):
+def config_kw(args, rank=0):
+    from seqfrost_b200 import batch
+    c = CONFIGS[args.config]
+    kw = dict(c["kw"])
+    if args.config == "c2":
+        kw.update(nvars=args.vars, nclauses=args.clauses)
+    kw["seed"] = batch.rank_seed(args.seed if args.seed is not None else kw["seed"], rank)
+    return c["gen"], kw
+
+
+def workload(args, rank=0):
     from seqfrost_b200 import cnfgen
-    return cnfgen.planted_subsumption_ksat(nvars, nclauses, k=5, seed=seed)
+    gen, kw = config_kw(args, rank)
+    return getattr(cnfgen, gen)(**kw)
 
 
-def workload_name(nvars, nclauses, ere=True):
-    return (f"random 5-SAT {nvars / 1e6:g}M vars / {nclauses / 1e6:g}M clauses + planted subsumption "
-            f"(BASELINE.json configs[1], SURVEY 8d C2), " + ("reference default options (ERE on)" if ere else "-no-redundancy"))
+def workload_name(args):
+    name = CONFIGS[args.config]["name"]
+    if args.config == "c2" and (args.vars, args.clauses) != (2_000_000, 10_000_000):
+        name = f"random 5-SAT {args.vars / 1e6:g}M vars / {args.clauses / 1e6:g}M clauses + planted subsumption (C2 generator, reduced size)"
+    return name + ", " + ("-no-redundancy" if args.no_ere else "reference default options (ERE on)")
 
 
-def reference_pass(nvars, nclauses, seed, runs=1, warm=0, ere=True):
-    """Runs the unmodified reference on a DIMACS file of the given shape; returns
-    (literals_in, [pass seconds per run]) for the replaced region simplify.cpp:180-206."""
+def dimacs_file(args, rank=0, inst=None):
+    """The DIMACS file of rank `rank`'s instance, written once per (config, size, seed) under CACHE."""
     from seqfrost_b200 import cnfgen
-    nv, off, lits = workload(nvars, nclauses, seed)
-    secs, lits_in = [], int(off[-1])
-    with tempfile.TemporaryDirectory() as td:
-        cnf = os.path.join(td, "sample.cnf")
-        cnfgen.write_dimacs(cnf, nv, off, lits)
-        for i in range(warm + runs):
-            r = subprocess.run([REF_BIN, cnf, "-quiet"] + ([] if ere else ["-no-redundancy"]), capture_output=True, text=True)
-            line = [l for l in r.stdout.splitlines() if l.startswith("ref_sigma:")]
-            if not line:
-                raise RuntimeError("ref_sigma failed: " + r.stdout[-300:] + r.stderr[-300:])
-            ms = float(line[-1].split("pass_ms=")[1].split()[0])
-            if i >= warm:
-                secs.append(ms / 1e3)
-    return lits_in, secs
+    gen, kw = config_kw(args, rank)
+    key = gen + "_" + "_".join(f"{k}{v}" for k, v in sorted(kw.items()))
+    os.makedirs(CACHE, exist_ok=True)
+    path = os.path.join(CACHE, key + ".cnf")
+    if not os.path.exists(path):
+        nv, off, lits = inst if inst is not None else getattr(cnfgen, gen)(**kw)
+        tmp = path + f".{os.getpid()}.tmp"
+        cnfgen.write_dimacs(tmp, nv, off, lits)
+        os.replace(tmp, path)
+    return path
+
+
+REF_LINE = re.compile(r"(\w+)=([0-9.]+)")
+
+
+def ref_sigma(cnf, ere=True, cpu=None, full=False):
+    """One run of the unmodified reference on `cnf`; returns the numbers its harness prints (pass_ms = the replaced
+    region simplify.cpp:180-206; with full=True also awaken / newBeginning / rebuildWT = the whole simplifying())."""
+    cmd = [REF_BIN, cnf, "-quiet"] + ([] if ere else ["-no-redundancy"]) + (["--full-timing"] if full else [])
+    if cpu is not None:
+        cmd = ["taskset", "-c", str(cpu)] + cmd
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def ref_result(p):
+    out, err = p.communicate()
+    d = {}
+    for l in out.splitlines():
+        if l.startswith("ref_sigma:"):
+            d.update({k: float(v) for k, v in REF_LINE.findall(l)})
+    if "pass_ms" not in d:
+        raise RuntimeError("ref_sigma failed: " + out[-300:] + err[-300:])
+    return d
+
+
+def host_cpus():
+    return sorted(os.sched_getaffinity(0))
 
 
 def pin_to_gpu_numa_node(torch, dev):
@@ -133,27 +191,81 @@ def clocks_stop(p):
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the unmodified reference's own pass (simplify.cpp:180-206) on the FULL instance of the config.
+    SeqFROST is single-threaded, so "all the host threads it can use" is one per process; at --gpus N rank 0 starts N
+    reference processes, each pinned to its own core, one per instance of the N-GPU batch (the same DIMACS file: every
+    rank's instance has the same shape), and reports their aggregate.  A step is one such run; the number of timed steps is
+    capped so that the arm ends within REF_BUDGET_S (there is no warm-up to speak of on a CPU: --warmup runs are skipped
+    once a single run takes more than a few seconds)."""
     if rank != 0:
         return
-    sv, sc = args.vars // args.sample_div, args.clauses // args.sample_div
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_sigma not built (make -C oracle ref needs /root/reference)"}))
         return
-    lits_in, secs = reference_pass(sv, sc, args.seed, runs=args.steps, warm=args.warmup, ere=not args.no_ere)
-    total = sum(secs)
-    value = lits_in * len(secs) / total
+    cnf = dimacs_file(args)
+    cpus = host_cpus()
+    nproc = min(args.gpus, len(cpus))
+    steps_ms, lits_in, t_begin = [], 0, time.perf_counter()
+    n_warm = args.warmup
+    i = 0
+    while True:
+        t0 = time.perf_counter()
+        procs = [ref_sigma(cnf, ere=not args.no_ere, cpu=cpus[(k * max(1, len(cpus) // nproc)) % len(cpus)]) for k in range(nproc)]
+        res = [ref_result(p) for p in procs]
+        run_s = time.perf_counter() - t0
+        lits_in = int(res[0]["literals_in"]) if "literals_in" in res[0] else lits_in
+        step_ms = max(r["pass_ms"] for r in res)
+        if i == 0 and run_s > 5.0:
+            n_warm = 0                                   # a run this long is its own warm-up
+        if i >= n_warm:
+            steps_ms.append(step_ms)
+        i += 1
+        elapsed = time.perf_counter() - t_begin
+        if len(steps_ms) >= args.steps or (steps_ms and elapsed + run_s > REF_BUDGET_S):
+            break
+    if not lits_in:
+        from seqfrost_b200 import boundary as B  # noqa: F401
+        nv, off, lits = workload(args)
+        lits_in = int(off[-1])
+    total_ms = sum(steps_ms)
+    value = nproc * lits_in * len(steps_ms) / (total_ms / 1e3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(secs), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_ms / len(steps_ms), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.vars, args.clauses, not args.no_ere), "sample": f"1/{args.sample_div} of the workload per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": f"same generator at 1/{args.sample_div} size ({sv} vars / {sc} clauses / {lits_in} literals), "
-                                   f"replaced region simplify.cpp:180-206, {cpu_model()}, {os.cpu_count()} host cores, SeqFROST is single-threaded"},
+        "config": {"workload": workload_name(args), "same_config": True, "literals_per_instance": lits_in, "instances_per_step": nproc,
+                   "steps_timed": len(steps_ms), "warmup_run": n_warm,
+                   "capped": None if len(steps_ms) >= args.steps else f"timed steps capped at {len(steps_ms)} to stay within {REF_BUDGET_S:.0f} s"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference",
+                         "sample": f"the full instance ({lits_in} literals), {nproc} process(es) of the unmodified reference pinned to "
+                                   f"{nproc} core(s), region simplify.cpp:180-206, {cpu_model()}, {os.cpu_count()} host cores "
+                                   f"(SeqFROST is single-threaded)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def binding_e2e(cnf, ref):
+    """`seqfrost_sigma <cnf> -no-solve -report`: the reference CLI with this pass behind it, on the reference's own
+    (pageable, malloc'ed) arenas - what a maintainer who links the binding sees as "Simplifier time"."""
+    if not os.path.exists(HOST_BIN):
+        return {"unavailable": "seqfrost_b200/host/_build/seqfrost_sigma not built (needs the reference headers)"}
+    out = {}
+    for tag, env in (("pinned_for_copies", {}), ("pageable", {"SIGMA_HOST_REGISTER": "0"})):
+        r = subprocess.run([HOST_BIN, cnf, "-no-solve", "-report"], capture_output=True, text=True, env={**os.environ, **env})
+        m = re.search(r"Simplifier time\s*:\s*(?:\x1b\[[0-9;]*m)*([0-9.]+)", r.stdout)
+        if not m:
+            return {"unavailable": "could not parse Simplifier time: " + (r.stdout[-200:] + r.stderr[-200:]).replace("\n", " ")}
+        out[tag] = {"simplifier_s": float(m.group(1))}
+    out["what"] = ("timer.simplify of Solver::simplifying() (simplify.cpp:170,230): awaken/extract, pass, newBeginning, rebuildWT, "
+                   "retrail; ours = seqfrost_sigma (device extract + pass + device newBeginning, host rebuildWT/retrail), "
+                   "reference = the same call of the unmodified reference")
+    if ref and "simplifier_ms" in ref:
+        out["reference_simplifier_s"] = ref["simplifier_ms"] / 1e3
+        out["reference_parts_ms"] = {k: ref[k] for k in ("awaken_ms", "pass_ms", "final_compact_ms", "newbeginning_ms", "rebuildwt_ms") if k in ref}
+        out["speedup"] = out["reference_simplifier_s"] / out["pinned_for_copies"]["simplifier_s"]
+    return out
 
 
 def main():
@@ -162,21 +274,27 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--vars", type=int, default=2_000_000)
-    ap.add_argument("--clauses", type=int, default=10_000_000)
-    ap.add_argument("--seed", type=int, default=7)
-    ap.add_argument("--sample-div", type=int, default=10, help="CPU baseline sample = workload / this")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["c5"])
+    ap.add_argument("--vars", type=int, default=2_000_000, help="c2 only")
+    ap.add_argument("--clauses", type=int, default=10_000_000, help="c2 only")
+    ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-binding", action="store_true")
     ap.add_argument("--no-ere", action="store_true", help="run both sides with -no-redundancy")
+    ap.add_argument("--instances", type=int, default=64, help="c5 only: size of the batch")
+    ap.add_argument("--verify", action="store_true", help="c5 only: check every output against tests/golden/c5_digests.json")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.config == "c5":
+        from seqfrost_b200 import batch
+        return batch.bench_c5(args, rank, world, local)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
     import torch
-    from seqfrost_b200 import boundary as B, sigma
+    from seqfrost_b200 import boundary as B, sigma, batch
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -186,11 +304,12 @@ def main():
     numa = pin_to_gpu_numa_node(torch, dev) if world > 1 else None      # host buffers next to the GPU they feed
 
     # ---- instance (synthetic, seeded; one independent instance per rank) ------------------------
-    from seqfrost_b200 import batch
-    nv, off, lits = workload(args.vars, args.clauses, batch.rank_seed(args.seed, rank))
+    inst = workload(args, rank)
+    nv, off, lits = inst
     b = B.from_cnf(nv, off, lits)
     b.opts["ere_en"] = 0 if args.no_ere else 1          # reference default: ERE on (options.cpp:28)
-    del off, lits
+    cnf = dimacs_file(args, 0, inst) if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_binding)) else None
+    del off, lits, inst
     s = sigma.Sigma(dev)
     bi, bufs = s.alloc_pinned_like(b)
     lits_in = int(b.n_literals)
@@ -229,7 +348,7 @@ def main():
     wall_ms = max_over_ranks(wall_ms)
 
     # ---- end-to-end arm: pinned host buffers, H2D + pass + D2H per step ---------------------------
-    # (a) serial: one context, upload -> execute -> download, step after step (single-instance latency)
+    # (a) the blocking call the solver makes: one context, upload -> execute -> download, step after step
     for _ in range(min(args.warmup, 2)):
         s.upload(bi); s.execute(); s.download_into(bufs)
     barrier()
@@ -240,7 +359,8 @@ def main():
         s.download_into(bufs)
     barrier()
     e2e_serial_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    # (b) pipelined: two contexts per GPU (the ABI's unit of concurrency), one host thread each, taking
+    rep2 = s.report()
+    # (b) batch mode: two contexts per GPU (the ABI's unit of concurrency), one host thread each, taking
     # alternate steps, so that the PCIe copies of one instance overlap the kernels of the other.  Every step
     # still uploads its input from pinned host memory and downloads its result.
     import threading
@@ -269,16 +389,15 @@ def main():
     for t in th:
         t.join()
     barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    e2e_pipe_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     if errs:
         raise errs[0]
     same = all(np.array_equal(bufs[k][:n_], bufs2[k][:n_]) for k, n_ in (("arena", 1024), ("refs", 1024))) if args.steps > 1 else True
     s2.close()
-    rep2 = s.report()
 
     total_lits = batch.sum_over_ranks(lits_in, dist, f"cuda:{dev}") * args.steps     # all ranks' instances
     value = batch.throughput(total_lits, dev_ms)
-    # ---- roofline of the dominant streaming stage ------------------------------------------------
+    # ---- roofline of the dominant streaming kernel -----------------------------------------------
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -286,22 +405,26 @@ def main():
     except OSError:
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    # stages that are one kernel (launched once, or once per slice) vs groups of small kernels
-    single = {"ingest": "k_ingest_fused", "ot_hist": "k_hist", "ot_scatter": "k_scatter", "ot_order": "k_ot_order_staged", "count": "k_count_live"}
-    streaming = [k for k in ("ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "ot_update", "vo", "count", "gc", "export") if stage_bytes.get(k)]
+    # stages that are ONE kernel per launch group (its CUDA-event time / launches = that kernel's launch duration)
+    single = sigma.SINGLE_KERNEL_STAGES
+    streaming = [k for k in sigma.STREAMING_STAGES if stage_bytes.get(k) and stage_ms.get(k)]
     dom = max([k for k in streaming if k in single], key=lambda k: stage_ms[k])
     dom_launches = max(1, stage_launches[dom])
     ach = stage_bytes[dom] / 1e9 / (stage_ms[dom] / 1e3)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"].get(single[dom])
     except (OSError, KeyError, ValueError):
         pass
+    sb = sum(stage_bytes[k] for k in streaming)
+    sm = sum(stage_ms[k] for k in streaming)
     roof = {"bound": "hbm", "kernel": single[dom], "stage": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": traffic, "peak_source": peak_src, "launches_timed": dom_launches,
             "algorithmic_bytes_per_launch": stage_bytes[dom] / dom_launches, "ms_per_launch": stage_ms[dom] / dom_launches,
             "note": "dominant single streaming kernel by time; the irregular stages (election, SUB, BVE, ERE) are latency bound and listed under stage_ms_per_step",
+            "all_streaming_aggregate": {"GB/s": sb / 1e9 / (sm / 1e3), "frac": sb / 1e9 / (sm / 1e3) / peak, "ms_per_step": sm / args.steps,
+                                        "algorithmic_bytes_per_step": sb / args.steps},
             "all_streaming": {k: {"kernel": single.get(k, "group of kernels"), "GB/s": stage_bytes[k] / 1e9 / (stage_ms[k] / 1e3),
                                   "frac": stage_bytes[k] / 1e9 / (stage_ms[k] / 1e3) / peak, "ms_per_step": stage_ms[k] / args.steps,
                                   "launches_per_step": stage_launches[k] / args.steps} for k in streaming}}
@@ -309,30 +432,34 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.vars, args.clauses, not args.no_ere), "literals_per_instance": lits_in,
-                   "instances_per_step": world, "l2": "inputs larger than L2 (arena %.0f MB per instance)" % (b.arena.nbytes / 1e6),
+        "config": {"workload": workload_name(args), "config": args.config, "literals_per_instance": lits_in,
+                   "instances_per_step": world, "l2": "inputs larger than L2 (arena %.0f MB per instance)" % (b.arena.nbytes / 1e6)
+                   if b.arena.nbytes > 126e6 else "the instance (arena %.0f MB) fits the 126 MB L2: between steps the pass itself "
+                   "rewrites the whole store and its occurrence table" % (b.arena.nbytes / 1e6),
                    "options": "reference defaults" + (", -no-redundancy" if args.no_ere else "")},
         "roofline": roof,
-        "e2e": {"value": batch.throughput(total_lits, e2e_ms), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "mode": "pipelined over 2 contexts per GPU (alternate steps; every step uploads and downloads)",
-                "serial": {"value": batch.throughput(total_lits, e2e_serial_ms), "ms_per_step": e2e_serial_ms / args.steps,
-                           "note": "one context, upload -> execute -> download back to back"},
+        "e2e": {"value": batch.throughput(total_lits, e2e_serial_ms), "unit": UNIT, "ms_per_step": e2e_serial_ms / args.steps,
+                "mode": "one context, blocking: upload -> execute -> download back to back (the call the solver makes)",
+                "pipelined": {"value": batch.throughput(total_lits, e2e_pipe_ms), "ms_per_step": e2e_pipe_ms / args.steps,
+                              "note": "batch mode: 2 contexts per GPU on alternate steps; every step uploads and downloads"},
                 "outputs_agree": bool(same),
                 "h2d_bytes_per_step": rep2["h2d_bytes"], "d2h_bytes_per_step": rep2["d2h_bytes"],
                 "h2d_ms": rep2["stage_ms"]["h2d"], "d2h_ms": rep2["stage_ms"]["d2h"]},
-        "instances_per_s": {"device": world * args.steps / (dev_ms / 1e3), "e2e": world * args.steps / (e2e_ms / 1e3),
-                            "note": "BASELINE metric 'instances/s at 1/2/4/8': one 10M-clause instance per GPU per step"},
+        "instances_per_s": {"device": world * args.steps / (dev_ms / 1e3), "e2e": world * args.steps / (e2e_serial_ms / 1e3),
+                            "e2e_pipelined": world * args.steps / (e2e_pipe_ms / 1e3),
+                            "note": "BASELINE metric 'instances/s at 1/2/4/8': one instance of this config per GPU per step; "
+                                    "the mixed 64-instance work queue is --config c5"},
         "host_affinity": numa,
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "launches_per_step": launches / args.steps, "clocks": clocks,
         "wall_ms_per_step": wall_ms / args.steps,
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "pass": {"phases": rep["phases_run"], "elected_per_phase": rep["elected_per_phase"], "election_rounds": rep["election_rounds"],
                  "clauses_out": rep["n_clauses"], "literals_out": rep["n_literals"], "eliminated": rep["max_melted_delta"],
-                 "subsumed": rep["subsumed"], "strengthened": rep["strengthened"]},
+                 "subsumed": rep["subsumed"], "strengthened": rep["strengthened"], "host_round_trips": rep["host_round_trips"]},
     }
     # ---- widening #1: extract() on the device (sigma_upload_cnf), informational ------------------
     if rank == 0 and world == 1:
-        db = B.clause_db_from_boundary(b, seed=args.seed, dead_frac=0.05)
+        db = B.clause_db_from_boundary(b, seed=args.seed or 0, dead_frac=0.05)
         ex_us, ex_bytes = [], 0
         for _ in range(4):
             s.upload_cnf(db, b)
@@ -344,18 +471,20 @@ def main():
                            "ms": ex_ms, "algorithmic_bytes": ex_bytes, "GB/s": ex_bytes / 1e9 / (ex_ms / 1e3),
                            "frac": ex_bytes / 1e9 / (ex_ms / 1e3) / peak, "h2d_bytes": r["h2d_bytes"], "h2d_ms": r["stage_ms"]["h2d"]}
         del db
+    s.close()
+    ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
-        sv, sc = args.vars // args.sample_div, args.clauses // args.sample_div
-        li, secs = reference_pass(sv, sc, args.seed, runs=1, ere=not args.no_ere)
-        line["cpu_baseline"] = {"value": li / secs[0], "unit": UNIT, "cores": 1, "kind": "reference",
-                                "sample": f"same generator at 1/{args.sample_div} size ({sv} vars / {sc} clauses / {li} literals), one run of the "
-                                          f"unmodified reference, region simplify.cpp:180-206, {cpu_model()}, {os.cpu_count()} host cores "
-                                          f"(SeqFROST is single-threaded)", "pass_s": secs[0]}
+        ref = ref_result(ref_sigma(cnf, ere=not args.no_ere, cpu=host_cpus()[0], full=True))
+        line["cpu_baseline"] = {"value": lits_in / (ref["pass_ms"] / 1e3), "unit": UNIT, "cores": 1, "kind": "reference",
+                                "sample": f"the full instance ({lits_in} literals), one run of the unmodified reference, region "
+                                          f"simplify.cpp:180-206, {cpu_model()}, {os.cpu_count()} host cores (SeqFROST is single-threaded)",
+                                "pass_s": ref["pass_ms"] / 1e3, "same_config": True}
     elif rank == 0:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "measured at N=1 only"}
+    if rank == 0 and world == 1 and not args.no_binding:
+        line["binding_e2e"] = binding_e2e(cnf, ref)
     if rank == 0:
         print(json.dumps(line))
-    s.close()
     if dist is not None:
         dist.destroy_process_group()
 

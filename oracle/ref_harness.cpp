@@ -15,6 +15,7 @@
 //
 //   --incr=seed:permille:nassume   incremental solver (Solver() + iadd/itoClause): isolve()'s prologue, a seeded subset of the variables
 //                   frozen through ifreeze() plus `nassume` assumptions; the .in then carries the `ifrozen` mask
+//   --full-timing   also time awaken() (extract), newBeginning()/map(true) and rebuildWT(): the whole simplifying() call
 // usage: ref_sigma <file.cnf> [reference CLI options] [--sgin=..] [--sgout=..] [--trace=..] [--incr=..]
 //
 // All members touched are public/protected in the reference's Solver (solve.hpp:75-844);
@@ -200,7 +201,7 @@ public:
 	}
 
 	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts, const std::string& cmin = std::string(),
-		const std::string& cmout = std::string(), const std::string& incr = std::string()) {
+		const std::string& cmout = std::string(), const std::string& incr = std::string(), const bool fulltiming = false) {
 		using clk = std::chrono::steady_clock;
 		timer.start();
 		if (!incr.empty()) {
@@ -223,8 +224,11 @@ public:
 			dumpClauseDb(w);
 			w.close();
 		}
+		auto ta0 = clk::now();
 		awaken();                          // simplify.cpp:171
+		auto ta1 = clk::now();
 		if (simpstate == AWAKEN_FAIL) return 4;
+		const uint64_t literals_in = inf.nLiterals;   // after extract(): the "literals/s" numerator (simplify.cpp:146-150)
 		if (!sgin.empty()) {
 			Writer w;
 			if (!w.open(sgin)) return 5;
@@ -299,8 +303,23 @@ public:
 			w.section("subsume1", s1.data(), s1.size());
 			w.close();
 		}
-		printf("ref_sigma: pass_ms=%.3f final_compact_ms=%.3f phases=%d vars=%u clauses=%u literals=%u melted=%u units=%u model=%u\n",
-			passms, gcms, phase, inf.maxVar, inf.nClauses, inf.nLiterals, inf.maxMelted, (unsigned)trail.size(), (unsigned)model.resolved.size());
+		if (fulltiming && cmout.empty() && inf.unassigned && inf.nClauses) {
+			// the rest of simplifying() (simplify.cpp:215-229) for the whole-call figure the CLI prints as "Simplifier time":
+			// newBeginning() (or map(true)) and rebuildWT()
+			auto t3 = clk::now();
+			if (canMap()) map(true);
+			else newBeginning();
+			auto t4 = clk::now();
+			rebuildWT(opts.simplify_priorbins);
+			auto t5 = clk::now();
+			printf("ref_sigma: awaken_ms=%.3f newbeginning_ms=%.3f rebuildwt_ms=%.3f simplifier_ms=%.3f\n",
+				std::chrono::duration<double, std::milli>(ta1 - ta0).count(), std::chrono::duration<double, std::milli>(t4 - t3).count(),
+				std::chrono::duration<double, std::milli>(t5 - t4).count(),
+				std::chrono::duration<double, std::milli>(ta1 - ta0).count() + passms + gcms + std::chrono::duration<double, std::milli>(t5 - t3).count());
+		}
+		printf("ref_sigma: pass_ms=%.3f final_compact_ms=%.3f phases=%d vars=%u clauses=%u literals=%u melted=%u units=%u model=%u literals_in=%llu\n",
+			passms, gcms, phase, inf.maxVar, inf.nClauses, inf.nLiterals, inf.maxMelted, (unsigned)trail.size(), (unsigned)model.resolved.size(),
+			(unsigned long long)literals_in);
 		fflush(stdout);
 		return 0;
 	}
@@ -318,6 +337,7 @@ int main(int argc, char** argv)
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
 	std::string sgin, sgout, tracep, cmin, cmout, incr;
 	long long presolve_conflicts = 0;
+	bool fulltiming = false;
 	std::vector<char*> pass;
 	for (int i = 0; i < argc; ++i) {
 		std::string a = argv[i];
@@ -327,6 +347,7 @@ int main(int argc, char** argv)
 		else if (a.rfind("--cmin=", 0) == 0) cmin = a.substr(7);
 		else if (a.rfind("--cmout=", 0) == 0) cmout = a.substr(8);
 		else if (a.rfind("--incr=", 0) == 0) incr = a.substr(7);
+		else if (a == "--full-timing") fulltiming = true;
 		else if (a.rfind("--presolve-conflicts=", 0) == 0) presolve_conflicts = atoll(a.substr(21).c_str());
 		else pass.push_back(argv[i]);
 	}
@@ -348,7 +369,7 @@ int main(int argc, char** argv)
 			if (!p->loadIncremental(formula)) { fprintf(stderr, "ref_sigma: incremental load failed (empty clause or conflicting units)\n"); g_out_written = true; _exit(8); }
 		}
 		solver = p;
-		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout, incr);
+		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout, incr, fulltiming);
 		g_out_written = g_out_written || rc != 0;
 		fflush(stdout);
 		_exit(rc); // skip the reference's destructors (process-global singletons)

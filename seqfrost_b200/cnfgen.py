@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
-    "random_ksat", "planted_subsumption_ksat", "gate_circuit", "xor_php_mix",
+    "random_ksat", "planted_solution_ksat", "planted_subsumption_ksat", "gate_circuit", "xor_php_mix",
     "mixed_instance", "write_dimacs", "concat",
 ]
 
@@ -72,6 +72,24 @@ def random_ksat(nvars, nclauses, k=3, seed=1):
     rng = np.random.default_rng(seed)
     rows = _signed(rng, _distinct_rows(rng, nclauses, k, nvars))
     o, l = _csr_from_fixed(rows)
+    return nvars, o, l
+
+
+def planted_solution_ksat(nvars, nclauses, k=3, seed=1):
+    """Random k-SAT with a hidden satisfying assignment (every clause holds at least one literal the assignment makes
+    true): the solvable stand-in for C1's "sigmify + solve" at full size - uniform 3-SAT at ratio 4.26 with 100k
+    variables is beyond both binaries, and the reference's -boundsearch option is dead code (options.cpp never copies
+    it into opts.boundsearch_en), so the search cannot be bounded deterministically (SURVEY 8d C1 caveat)."""
+    rng = np.random.default_rng(seed)
+    hidden = rng.integers(0, 2, size=nvars + 1, dtype=np.int64) * 2 - 1          # +1 / -1 per variable
+    rows = _signed(rng, _distinct_rows(rng, nclauses, k, nvars)).astype(np.int64)
+    while True:
+        sat = (np.sign(rows) == hidden[np.abs(rows)]).any(axis=1)
+        bad = np.nonzero(~sat)[0]
+        if bad.size == 0:
+            break
+        rows[bad] = _signed(rng, _distinct_rows(rng, bad.size, k, nvars))
+    o, l = _csr_from_fixed(rows.astype(np.int32))
     return nvars, o, l
 
 

@@ -25,6 +25,11 @@ SIGMA_OK, SIGMA_UNSAT, SIGMA_INTERRUPTED, SIGMA_E_NOMEM, SIGMA_E_CUDA, SIGMA_E_N
 STAGES = ["h2d", "ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "prop", "vo", "elect", "sot", "sub", "ve",
           "count", "gc", "export", "d2h", "total_device", "ere", "ot_update", "nbh"]
 T_N = 20
+# stages whose work is HBM streaming (graded against the roofline) and, of those, the ones that are ONE kernel
+# per launch (stage time / stage launches = that kernel's launch duration)
+STREAMING_STAGES = ("ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "ot_update", "vo", "count", "gc", "export")
+SINGLE_KERNEL_STAGES = {"ingest": "k_ingest_fused", "ot_hist": "k_hist", "ot_scatter": "k_scatter", "ot_order": "k_ot_order_staged",
+                        "count": "k_count_live"}
 
 EXPORTS = [
     "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",

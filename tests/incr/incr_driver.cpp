@@ -6,6 +6,11 @@
 // Both print the same digest lines per isolve() call; tests/test_integration.py compares them.
 //
 // usage: incr_driver <file.cnf> [reference options] [--freeze=v,v,...] --assume=l,l,... [--assume=...]...
+//        incr_driver <file.cnf> [reference options] --solve [--bound]
+// --solve: the non-incremental client (Solver(path) + solve()).  --bound switches on opts.boundsearch_en, the flag behind
+// --conflictout / --decisionout (solve.hpp:64-66): the reference's own -boundsearch option never reaches it (options.cpp
+// registers the option but OPTION::init does not copy it), so a client that wants a deterministic search bound sets the
+// field itself - on both builds alike.
 #ifdef USE_SIGMA
 #include "../../seqfrost_b200/host/sigma_solver.hpp"
 #else
@@ -35,6 +40,15 @@ typedef Solver Base;
 class Client : public Base {
 public:
 	Client() : Base() {}
+	explicit Client(const std::string& path) : Base(path) {}
+	void boundSearch() { opts.boundsearch_en = true; }
+	void plainSolve() {
+#ifdef USE_SIGMA
+		sigmaSolve();
+#else
+		solve();
+#endif
+	}
 	bool load(const char* path) {                       // clause by clause through iadd / itoClause (addinc.cpp:33-150)
 		FILE* f = fopen(path, "r");
 		if (!f) return false;
@@ -94,11 +108,14 @@ int main(int argc, char** argv)
 	if (argc < 2) { fprintf(stderr, "usage: incr_driver <cnf> [options] [--freeze=..] --assume=.. ...\n"); return 1; }
 	std::vector<std::vector<long>> rounds;
 	std::vector<long> freeze;
+	bool plain = false, bound = false;
 	std::vector<char*> pass;
 	for (int i = 0; i < argc; ++i) {
 		std::string a = argv[i];
 		if (a.rfind("--assume=", 0) == 0) rounds.push_back(csv(a.substr(9)));
 		else if (a.rfind("--freeze=", 0) == 0) freeze = csv(a.substr(9));
+		else if (a == "--solve") plain = true;
+		else if (a == "--bound") bound = true;
 		else pass.push_back(argv[i]);
 	}
 	int pargc = (int)pass.size();
@@ -107,6 +124,14 @@ int main(int argc, char** argv)
 	quiet_en = opt_quiet_en, verbose = opt_verbose;
 	if (quiet_en || competition_en) verbose = 0;
 	else if (!verbose || competition_en) quiet_en = true;
+	if (plain) {
+		Client* s = new Client(std::string(argv[1]));
+		solver = s;
+		if (bound) s->boundSearch();
+		s->plainSolve();
+		s->digest(0);
+		_exit(0);
+	}
 	Client* s = new Client();
 	solver = s;
 	if (!s->load(argv[1])) { printf("incr load: UNSAT\n"); fflush(stdout); _exit(0); }
