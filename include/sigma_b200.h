@@ -136,6 +136,9 @@ typedef struct sigma_report {
     uint32_t elected_per_phase[8];
     uint32_t election_rounds[8];
     uint64_t reserved[8];
+    uint32_t ot_build_mode;         /* full occurrence-table builds of this run: 2 = two-level partition (k_otb_*), 1 = one-level
+                                       histogram + scatter + order fix (k_hist, k_scatter, k_ot_order_staged), 0 = none  */
+    uint32_t reserved32[15];
 } sigma_report;
 
 typedef struct sigma_ctx sigma_ctx;

@@ -100,6 +100,20 @@ void be_scan_u32(void *s, const uint32_t *in, uint32_t *out, uint32_t n, uint32_
 size_t be_scan_tmp_words(uint32_t n);
 /* per-literal occurrence histogram over live clauses (histogram.hpp:43-50, simplify.cpp:50-58) */
 void be_hist(void *s, const SgView &v, uint32_t *counts);
+/* createOT (simplify.cpp:39-61) as a two-level partition (sigma_kernels.cu): ot_off / ot_len / ot_data from the store, every
+ * list in ascending clause id order (= the reference's push order).
+ *   be_ot_build_plan    geometry + layout of tmp (be_ot_build_tmp_words words); `lits` = live literals (an upper bound is fine);
+ *                       non-zero / 0 words: the formula does not fit (caller: be_hist / scan / be_scatter / be_ot_order)
+ *   be_ot_build_count   per (bucket, tile) literal counts into plan.cnt; bits (may be NULL): bitmap of the live clauses
+ *   (caller)            exclusive scan of plan.cnt[0 .. plan.ncnt) in place, total -> device word
+ *   be_ot_build_scatter (literal, clause) pairs, bucket by bucket, tile by tile
+ *   be_ot_build_lists   one block per bucket: ot_len, ot_off, ordered lists */
+struct SgOtBuild { uint32_t shift, NB, T, per_tile; size_t ncnt; uint32_t *cnt, *scantmp; void *pairs; };
+size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits);
+int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp, SgOtBuild *plan);
+void be_ot_build_count(void *s, const SgView &v, const SgOtBuild &plan, uint32_t *bits);
+void be_ot_build_scatter(void *s, const SgView &v, const SgOtBuild &plan);
+void be_ot_build_lists(void *s, const SgView &v, const SgOtBuild &plan, const uint32_t *total);
 /* scatter clause ids into the lists; cursor must hold a copy of ot_off (absolute write positions) */
 void be_scatter(void *s, const SgView &v, uint32_t *cursor);
 /* Incremental createOT for phases after the first.  The occurrence table the reference rebuilds from

@@ -406,6 +406,164 @@ __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restr
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+/* occurrence table build as a two-level partition (the default createOT)                           */
+/* ---------------------------------------------------------------------------------------------- */
+/* createOT (simplify.cpp:39-61) is a stable counting sort of (literal, clause) pairs by literal.  With millions of
+ * literal bins a one-level scatter costs one global atomic per literal plus a 4-byte store at a random place (round 1:
+ * k_hist + 4 x k_scatter + order fix, 2.0 GB of DRAM traffic for 0.49 GB of payload).  Here the literal space is cut
+ * into NB buckets of W = 2^shift consecutive literals, chosen so that one bucket's share of the table fits in shared
+ * memory, and the clause ids are cut into T tiles:
+ *   k_otb_count    tile t counts its literals per bucket in shared memory            -> cnt[b][t]        (reads the store once)
+ *   scan           exclusive scan of cnt in (bucket, tile) order = where tile t's pairs of bucket b go
+ *   k_otb_scatter  tile t writes its (literal, clause) pairs there, shared-memory cursors               (reads the store once, writes 8 B per literal)
+ *   k_otb_lists    one block per bucket: per-literal counts (= ot_len), their scan (= ot_off: the bucket's pairs and its slice of
+ *                  ot_data share one index range), clause ids placed in shared memory, every list put in ascending clause
+ *                  id order there (= the reference's push order; the pairs arrive tile by tile, so the lists are nearly
+ *                  sorted already), one bulk (TMA) store of the bucket's slice
+ * No global atomics, the store is read twice instead of five times, every byte of ot_data is written once, coalesced.
+ * A bucket whose share exceeds the staging buffer (a literal with tens of thousands of occurrences) is placed and sorted
+ * in global memory instead. */
+constexpr int OTB_TPB = 512;
+constexpr uint32_t OTB_CAP = 20480;        /* staged clause ids per bucket (80 KB) */
+constexpr uint32_t OTB_WMAX = 4096;        /* literals per bucket: two shared arrays of that many words */
+constexpr uint32_t OTB_NBMAX = 12288;      /* buckets: one shared counter each in the tile kernels (48 KB) */
+
+__global__ void __launch_bounds__(OTB_TPB) k_otb_count(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
+                                                        uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile,
+                                                        uint32_t *__restrict__ cnt, uint32_t *__restrict__ bits)
+{
+    extern __shared__ uint32_t s_cnt[];
+    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cnt[b] = 0;
+    __syncthreads();
+    const uint32_t t = blockIdx.x;
+    const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
+    /* per_tile is a multiple of 32, so a warp's 32 clauses share one word of the liveness bitmap */
+    for (uint32_t base = c0; base < c1; base += blockDim.x) {
+        const uint32_t c = base + threadIdx.x;
+        bool live = false;
+        if (c < c1) {
+            const uint4 h = hdr[c];
+            live = !(h.z & SG_DELETED);
+            if (live) {
+                const uint32_t *l = lits + h.x;
+                for (uint32_t k = 0; k < h.y; ++k) atomicAdd(&s_cnt[l[k] >> shift], 1u);
+            }
+        }
+        if (bits) {
+            const uint32_t m = __ballot_sync(0xffffffffu, live);
+            if ((threadIdx.x & 31) == 0 && (base + (threadIdx.x & ~31u)) < c1) bits[c >> 5] = m;
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) cnt[(size_t)b * T + t] = s_cnt[b];
+}
+
+__global__ void __launch_bounds__(OTB_TPB) k_otb_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
+                                                          uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile,
+                                                          const uint32_t *__restrict__ base_of, uint2 *__restrict__ pairs)
+{
+    extern __shared__ uint32_t s_cur[];
+    const uint32_t t = blockIdx.x;
+    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cur[b] = base_of[(size_t)b * T + t];
+    __syncthreads();
+    const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
+    for (uint32_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        const uint4 h = hdr[c];
+        if (h.z & SG_DELETED) continue;
+        const uint32_t *l = lits + h.x;
+        for (uint32_t k = 0; k < h.y; ++k) {
+            const uint32_t lit = l[k];
+            pairs[atomicAdd(&s_cur[lit >> shift], 1u)] = make_uint2(lit, c);
+        }
+    }
+}
+
+/* ascending order of one list, by one thread: nearly sorted input (see above), so insertion; a long list that really is
+ * out of order goes through the heap sort instead of a quadratic walk */
+__device__ __forceinline__ void otb_sort_list(uint32_t *d, uint32_t n)
+{
+    if (n < 2) return;
+    if (n > 64) {
+        uint32_t inv = 0;
+        for (uint32_t i = 1; i < n && inv <= n; ++i) inv += d[i - 1] > d[i];
+        if (inv == 0) return;
+        if (inv > 8) { sg_heapsort_u32(d, (int)n); return; }
+    }
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint32_t x = d[i];
+        uint32_t j = i;
+        while (j > 0 && d[j - 1] > x) { d[j] = d[j - 1]; --j; }
+        d[j] = x;
+    }
+}
+
+__global__ void __launch_bounds__(OTB_TPB, 2) k_otb_lists(const uint2 *__restrict__ pairs, const uint32_t *__restrict__ base_of, uint32_t NB,
+                                                          uint32_t T, uint32_t shift, uint32_t nlit, const uint32_t *__restrict__ total,
+                                                          uint32_t *__restrict__ ot_off, uint32_t *__restrict__ ot_len, uint32_t *__restrict__ ot_data)
+{
+    extern __shared__ __align__(128) uint32_t s_mem[];
+    const uint32_t W = 1u << shift;
+    uint32_t *s_loc = s_mem;                 /* W + 1: exclusive offsets of the bucket's lists */
+    uint32_t *s_cur = s_mem + W + 4;         /* W: fill cursors */
+    uint32_t *stage = s_mem + 2 * W + 8;     /* OTB_CAP + 4 staged clause ids */
+    __shared__ uint32_t s_part[OTB_TPB / 32];
+    const uint32_t b = blockIdx.x;
+    const uint32_t g0 = base_of[(size_t)b * T], g1 = b + 1 < NB ? base_of[(size_t)(b + 1) * T] : *total;
+    const uint32_t P = g1 - g0, lit0 = b << shift;
+    for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) s_cur[i] = 0;
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) atomicAdd(&s_cur[pairs[g0 + p].x - lit0], 1u);
+    __syncthreads();
+    /* exclusive scan of the W counts: each thread owns W / blockDim consecutive literals */
+    const uint32_t per = (W + blockDim.x - 1) / blockDim.x;
+    const uint32_t i0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; ++k) if (i0 + k < W) sum += s_cur[i0 + k];
+    uint32_t incl = sum;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < OTB_TPB / 32 ? s_part[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < OTB_TPB / 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += y; }
+        if (lane < OTB_TPB / 32) s_part[lane] = w;
+    }
+    __syncthreads();
+    uint32_t e = (warp ? s_part[warp - 1] : 0) + incl - sum;
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t i = i0 + k;
+        if (i < W) {
+            const uint32_t n = s_cur[i];
+            s_loc[i] = e;
+            if (lit0 + i < nlit) { ot_off[lit0 + i] = g0 + e; ot_len[lit0 + i] = n; }
+            e += n;
+        }
+    }
+    if (threadIdx.x == blockDim.x - 1) s_loc[W] = P;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) s_cur[i] = s_loc[i];
+    __syncthreads();
+    const bool staged = P <= OTB_CAP;
+    const uint32_t shift4 = g0 & 3u;
+    uint32_t *dst = staged ? stage + shift4 : ot_data + g0;
+    for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) {
+        const uint2 q = pairs[g0 + p];
+        dst[atomicAdd(&s_cur[q.x - lit0], 1u)] = q.y;
+    }
+    __syncthreads();
+    if (!staged) __threadfence_block();
+    for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) otb_sort_list(dst + s_loc[i], s_loc[i + 1] - s_loc[i]);
+    if (staged) {
+        stage_fence();
+        __syncthreads();
+        if (P) flush_staged(ot_data, (unsigned long long)g0, stage, P);
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- */
 /* variable ordering: scores + stable LSD radix sort (8-bit digits)                                  */
 /* ---------------------------------------------------------------------------------------------- */
 __global__ void k_scores(SgView v)
@@ -1298,6 +1456,68 @@ void be_scan_multi(void *s, const SgScanSet &ss, uint32_t count, uint32_t n, uin
 void be_hist(void *s, const SgView &v, uint32_t *counts)
 {
     if (v.n_cls) LAUNCH(k_hist, blocks_for(v.n_cls), TPB, s, (const uint4 *)v.hdr, v.lits, v.n_cls, counts);
+}
+/* geometry of the two-level build; returns false when the formula does not fit it (caller: one-level path) */
+static bool otb_geometry(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *shift, uint32_t *NB, uint32_t *T, uint32_t *per_tile)
+{
+    if (!nlit || !n_cls) return false;
+    /* about half the staging buffer per bucket on average: W = 2^shift >= (CAP / 2) * nlit / lits */
+    const uint64_t want = lits ? ((uint64_t)(OTB_CAP / 2) * nlit + lits - 1) / lits : OTB_WMAX;
+    uint32_t sh = 8;
+    while ((1ull << sh) < want && (1u << sh) < OTB_WMAX) ++sh;
+    while (((uint64_t)nlit + (1u << sh) - 1) >> sh > OTB_NBMAX && (1u << sh) < OTB_WMAX) ++sh;
+    const uint64_t nb = ((uint64_t)nlit + (1u << sh) - 1) >> sh;
+    if (nb > OTB_NBMAX) return false;
+    /* tiles: a few per SM, at least 1024 clauses each, a multiple of 32 clauses (bitmap words) */
+    uint32_t tiles = 148u * 8u;
+    uint32_t pt = (n_cls + tiles - 1) / tiles;
+    if (pt < 1024u) pt = 1024u;
+    pt = (pt + 31u) & ~31u;
+    tiles = (n_cls + pt - 1) / pt;
+    if (nb * (uint64_t)tiles >= 0xFFFFFFF0ull) return false;
+    *shift = sh; *NB = (uint32_t)nb; *T = tiles; *per_tile = pt;
+    return true;
+}
+size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits)
+{
+    uint32_t sh, NB, T, pt;
+    if (!otb_geometry(nlit, n_cls, lits, &sh, &NB, &T, &pt)) return 0;
+    const size_t cnt = (size_t)NB * T + 8;
+    return cnt + be_scan_tmp_words((uint32_t)cnt) + 2 + 2 * (size_t)lits + 64;
+}
+int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp, SgOtBuild *p)
+{
+    if (!otb_geometry(nlit, n_cls, lits, &p->shift, &p->NB, &p->T, &p->per_tile)) return 1;
+    static int smem_ok = -1;
+    if (smem_ok < 0) {
+        const size_t lists_smem = (2ull * OTB_WMAX + 8 + OTB_CAP + 8) * 4;
+        smem_ok = cudaFuncSetAttribute(k_otb_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lists_smem) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_otb_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(OTB_NBMAX * 4)) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_otb_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(OTB_NBMAX * 4)) == cudaSuccess;
+        (void)cudaGetLastError();
+    }
+    if (!smem_ok) return 1;
+    p->ncnt = (size_t)p->NB * p->T;
+    p->cnt = tmp;
+    p->scantmp = tmp + p->ncnt + 8;
+    p->pairs = (void *)(p->scantmp + ((be_scan_tmp_words((uint32_t)(p->ncnt + 8)) + 1) & ~(size_t)1));
+    return 0;
+}
+void be_ot_build_count(void *s, const SgView &v, const SgOtBuild &p, uint32_t *bits)
+{
+    k_otb_count<<<p.T, OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, bits);
+    ((BeStream *)s)->launches++; note_err(s, "k_otb_count");
+}
+void be_ot_build_scatter(void *s, const SgView &v, const SgOtBuild &p)
+{
+    k_otb_scatter<<<p.T, OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, (uint2 *)p.pairs);
+    ((BeStream *)s)->launches++; note_err(s, "k_otb_scatter");
+}
+void be_ot_build_lists(void *s, const SgView &v, const SgOtBuild &p, const uint32_t *total)
+{
+    const size_t smem = (2ull * (1u << p.shift) + 8 + OTB_CAP + 8) * 4;
+    k_otb_lists<<<p.NB, OTB_TPB, smem, ST(s)>>>((const uint2 *)p.pairs, p.cnt, p.NB, p.T, p.shift, v.nlit, total, v.ot_off, v.ot_len, v.ot_data);
+    ((BeStream *)s)->launches++; note_err(s, "k_otb_lists");
 }
 void be_scatter(void *s, const SgView &v, uint32_t *cursor)
 {

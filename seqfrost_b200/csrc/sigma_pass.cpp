@@ -68,7 +68,7 @@ struct sigma_ctx {
     DBuf<SgUnit> ubuf;
     DBuf<uint8_t> ere_touched, ere_flags;
     DBuf<uint32_t> ere_filt; DBuf<uint8_t> ere_size8;
-    DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add, otbits;
+    DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add, otbits, otb_tmp;
     uint64_t phase_add_lits = 0;     /* literals of the resolvents the latest VE stage added */
     uint32_t last_elected = 0;       /* size of `elected` after the latest election (hsc.n_elected does not survive a pull) */
     uint64_t ot_end = 0;             /* words of ot_data in use (the updated table is not packed) */
@@ -257,6 +257,63 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls, bool tr
     const uint32_t nlit = c->nlit;
     NOMEM(c->ot_data.ensure((size_t)live_lits + 16));
     SgView v = make_view(c);
+    const bool want_bits = track && c->ot_incremental;
+    /* default: the two-level partition build (sigma_backend.h).  The one-level path below remains for formulas outside its
+     * geometry and as a second implementation the tests compare (SIGMA_OT_BUILD=0) */
+    const char *ob = getenv("SIGMA_OT_BUILD");
+    const size_t need = (ob && ob[0] == '0') ? 0 : be_ot_build_tmp_words(nlit, c->n_cls, live_lits);
+    SgOtBuild plan;
+    if (need && c->otb_tmp.ensure(need) && be_ot_build_plan(nlit, c->n_cls, live_lits, c->otb_tmp.p, &plan) == 0) {
+        if (want_bits) NOMEM(c->otbits.ensure(be_ot_bits_words(c->n_cls) + 64));
+        const uint64_t cw = 4ull * plan.ncnt;
+        {
+            Stage st(c, SIGMA_T_OT_HIST, 4 * live_lits + 8ull * c->n_cls + cw);
+            be_ot_build_count(c->stream, v, plan, want_bits ? c->otbits.p : nullptr);
+        }
+        {
+            Stage st(c, SIGMA_T_OT_SCAN, 2 * cw);
+            be_scan_u32(c->stream, plan.cnt, plan.cnt, (uint32_t)plan.ncnt, c->totals.p, plan.scantmp);
+        }
+        {
+            Stage st(c, SIGMA_T_OT_SCATTER, 4 * live_lits + 8ull * c->n_cls + cw + 8 * live_lits);
+            be_ot_build_scatter(c->stream, v, plan);
+        }
+        {
+            Stage st(c, SIGMA_T_OT_ORDER, 8 * live_lits + 4 * live_lits + 8ull * nlit);
+            be_ot_build_lists(c->stream, v, plan, c->totals.p);
+        }
+        c->rep.ot_build_mode = 2;
+        if (c->ot_verify && track) {
+            /* test hook (SIGMA_OT_VERIFY=1): the one-level build into the spare buffers, compared list by list on the device */
+            sigma_ctx &x = *c;
+            DBuf<uint32_t> so = x.ot_off, sl = x.ot_len, sd = x.ot_data;
+            NOMEM(x.ot_off2.ensure(nlit + 1)); NOMEM(x.ot_len2.ensure(nlit)); NOMEM(x.ot_data2.ensure((size_t)live_lits + 16));
+            x.ot_off = x.ot_off2; x.ot_len = x.ot_len2; x.ot_data = x.ot_data2;
+            SgView w = make_view(c);
+            be_memset(c->stream, x.ot_len.p, 0, nlit * sizeof(uint32_t));
+            be_hist(c->stream, w, x.ot_len.p);
+            be_scan_u32(c->stream, x.ot_len.p, x.ot_off.p, nlit, c->totals.p + 11, c->scantmp.p);
+            be_d2d(c->stream, c->cursor.p, x.ot_off.p, nlit * sizeof(uint32_t));
+            be_scatter(c->stream, w, c->cursor.p);
+            be_ot_order(c->stream, w);
+            x.ot_off2 = x.ot_off; x.ot_len2 = x.ot_len; x.ot_data2 = x.ot_data;
+            x.ot_off = so; x.ot_len = sl; x.ot_data = sd;
+            w = make_view(c);
+            be_ot_compare(c->stream, w, x.ot_off2.p, x.ot_len2.p, x.ot_data2.p, c->totals.p + 10);
+            CK(pull_totals(c, 12));
+            if (c->h_totals[10] || c->h_totals[11] != c->h_totals[0]) {
+                snprintf(c->err, sizeof c->err, "two-level occurrence table differs from the one-level build in %u lists (entries %u vs %u)", c->h_totals[10], c->h_totals[0], c->h_totals[11]);
+                return SIGMA_E_CUDA;
+            }
+        }
+        if (want_bits) {
+            c->ot_end = live_lits; c->ot_end_stale = false;
+            c->h_totals[13] = (uint32_t)live_lits;             /* device-side end of the table (bump allocator of the updates) */
+            be_copy_words(c->stream, c->totals.p + 13, c->h_totals + 13, 4);
+        }
+        return SIGMA_OK;
+    }
+    c->rep.ot_build_mode = 1;
     {
         Stage st(c, SIGMA_T_OT_HIST, 4 * live_lits + 8ull * c->n_cls + 4ull * nlit);
         be_memset(c->stream, c->ot_len.p, 0, nlit * sizeof(uint32_t));
@@ -895,7 +952,7 @@ void sigma_destroy(sigma_ctx *c)
         c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
         c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
         c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release(); c->ere_filt.release(); c->ere_size8.release();
-        c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->otbits.release(); c->totals.release(); c->sc.release();
+        c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->otbits.release(); c->otb_tmp.release(); c->totals.release(); c->sc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
         c->arena_out.release(); c->refs_out.release(); c->cm_out.release(); c->orgs_out.release(); c->learnts_out.release(); c->subsume_out.release();
         for (void *e2 : c->evpool) be_event_destroy(e2);

@@ -28,8 +28,8 @@ T_N = 20
 # stages whose work is HBM streaming (graded against the roofline) and, of those, the ones that are ONE kernel
 # per launch (stage time / stage launches = that kernel's launch duration)
 STREAMING_STAGES = ("ingest", "ot_hist", "ot_scan", "ot_scatter", "ot_order", "ot_update", "vo", "count", "gc", "export")
-SINGLE_KERNEL_STAGES = {"ingest": "k_ingest_fused", "ot_hist": "k_hist", "ot_scatter": "k_scatter", "ot_order": "k_ot_order_staged",
-                        "count": "k_count_live"}
+SINGLE_KERNEL_STAGES = {"ingest": "k_ingest_fused", "ot_hist": "k_otb_count", "ot_scatter": "k_otb_scatter", "ot_order": "k_otb_lists",
+                        "count": "k_count_live", "export": "k_export_staged"}
 
 EXPORTS = [
     "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",
@@ -77,6 +77,7 @@ class SigmaReport(C.Structure):
         ("stage_ms", C.c_float * T_N), ("stage_launches", C.c_uint32 * T_N), ("stage_bytes", C.c_uint64 * T_N),
         ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
         ("elected_per_phase", C.c_uint32 * 8), ("election_rounds", C.c_uint32 * 8), ("reserved", C.c_uint64 * 8),
+        ("ot_build_mode", C.c_uint32), ("reserved32", C.c_uint32 * 15),
     ]
 
     def as_dict(self):
@@ -91,6 +92,7 @@ class SigmaReport(C.Structure):
         d["ere"] = dict(zip(("events", "dirty_vars", "full_pairs", "event_pairs"), list(self.reserved)[:4]))
         d["host_round_trips"] = int(self.reserved[4])
         d["extract_us"], d["extract_bytes"] = int(self.reserved[5]), int(self.reserved[6])
+        d["ot_build_mode"] = int(self.ot_build_mode)
         return d
 
 

@@ -170,6 +170,67 @@ void be_hist(void *, const SgView &v, uint32_t *counts)
         for (uint32_t k = 0; k < v.hdr[c].y; ++k) counts[l[k]]++;
     }
 }
+/* two-level createOT: the stand-in keeps the call structure (count / caller's scan / scatter / lists) with one bucket
+ * per 256 literals and tiles of 64 clauses, so that the driver's scan and buffer layout are exercised */
+size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits)
+{
+    if (!nlit || !n_cls) return 0;
+    const size_t NB = (nlit + 255) / 256, T = (n_cls + 63) / 64;
+    return NB * T + 8 + be_scan_tmp_words((uint32_t)(NB * T + 8)) + 2 + 2 * (size_t)lits + 64;
+}
+int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp, SgOtBuild *p)
+{
+    if (!nlit || !n_cls) return 1;
+    (void)lits;
+    p->shift = 8; p->NB = (nlit + 255) / 256; p->per_tile = 64; p->T = (n_cls + 63) / 64;
+    p->ncnt = (size_t)p->NB * p->T;
+    p->cnt = tmp; p->scantmp = tmp + p->ncnt + 8;
+    p->pairs = (void *)(p->scantmp + ((be_scan_tmp_words((uint32_t)(p->ncnt + 8)) + 1) & ~(size_t)1));
+    return 0;
+}
+void be_ot_build_count(void *, const SgView &v, const SgOtBuild &p, uint32_t *bits)
+{
+    g_launches++;
+    memset(p.cnt, 0, p.ncnt * 4);
+    if (bits) memset(bits, 0, ((size_t)v.n_cls / 32 + 1) * 4);
+    for (uint32_t c : item_order(v.n_cls)) {
+        if (v.hdr[c].z & SG_DELETED) continue;
+        if (bits) bits[c >> 5] |= 1u << (c & 31);
+        for (uint32_t k = 0; k < v.hdr[c].y; ++k) p.cnt[(size_t)(v.lits[v.hdr[c].x + k] >> p.shift) * p.T + c / p.per_tile]++;
+    }
+}
+void be_ot_build_scatter(void *, const SgView &v, const SgOtBuild &p)
+{
+    g_launches++;
+    uint32_t *pairs = (uint32_t *)p.pairs;
+    std::vector<uint32_t> cur(p.cnt, p.cnt + p.ncnt);
+    for (uint32_t c : item_order(v.n_cls)) {           /* any order inside a tile, as on the device */
+        if (v.hdr[c].z & SG_DELETED) continue;
+        for (uint32_t k = 0; k < v.hdr[c].y; ++k) {
+            const uint32_t lit = v.lits[v.hdr[c].x + k];
+            const uint32_t pos = cur[(size_t)(lit >> p.shift) * p.T + c / p.per_tile]++;
+            pairs[2 * (size_t)pos] = lit; pairs[2 * (size_t)pos + 1] = c;
+        }
+    }
+}
+void be_ot_build_lists(void *, const SgView &v, const SgOtBuild &p, const uint32_t *total)
+{
+    g_launches++;
+    const uint32_t *pairs = (const uint32_t *)p.pairs;
+    for (uint32_t b : item_order(p.NB)) {
+        const uint32_t g0 = p.cnt[(size_t)b * p.T], g1 = b + 1 < p.NB ? p.cnt[(size_t)(b + 1) * p.T] : *total;
+        const uint32_t lit0 = b << p.shift, W = 1u << p.shift;
+        std::vector<uint32_t> n(W + 1, 0), cur(W, 0);
+        for (uint32_t q = g0; q < g1; ++q) n[pairs[2 * (size_t)q] - lit0]++;
+        uint32_t e = 0;
+        for (uint32_t i = 0; i < W; ++i) {
+            if (lit0 + i < v.nlit) { v.ot_off[lit0 + i] = g0 + e; v.ot_len[lit0 + i] = n[i]; }
+            cur[i] = e; e += n[i];
+        }
+        for (uint32_t q = g0; q < g1; ++q) v.ot_data[g0 + cur[pairs[2 * (size_t)q] - lit0]++] = pairs[2 * (size_t)q + 1];
+        for (uint32_t i = 0; i < W && lit0 + i < v.nlit; ++i) std::sort(v.ot_data + v.ot_off[lit0 + i], v.ot_data + v.ot_off[lit0 + i] + v.ot_len[lit0 + i]);
+    }
+}
 void be_scatter(void *, const SgView &v, uint32_t *cursor)
 {
     g_launches++;
