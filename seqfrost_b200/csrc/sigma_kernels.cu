@@ -428,34 +428,41 @@ constexpr uint32_t OTB_CAP = 20480;        /* staged clause ids per bucket (80 K
 constexpr uint32_t OTB_WMAX = 4096;        /* literals per bucket: two shared arrays of that many words */
 constexpr uint32_t OTB_NBMAX = 12288;      /* buckets: one shared counter each in the tile kernels (48 KB) */
 
+/* The tile kernels run as a persistent grid: block g takes tiles g, g + G, g + 2G, ... in order, so that at any time the G
+ * tiles in flight are neighbours.  Their pairs for one bucket are neighbours in memory as well, hence the window of the pair
+ * buffer that is being filled (G / T of it) stays resident in L2 until its sectors are complete.  (With every tile resident
+ * at once half of the 408 MB buffer was open at a time, and the 8-byte stores of uniformly random literals went to HBM as
+ * partial sectors: 1.6 ms instead of 0.2.)  The store itself is streamed with evict-first loads for the same reason. */
 __global__ void __launch_bounds__(OTB_TPB) k_otb_count(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
                                                         uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile,
                                                         uint32_t *__restrict__ cnt, uint32_t *__restrict__ bits)
 {
     extern __shared__ uint32_t s_cnt[];
-    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cnt[b] = 0;
-    __syncthreads();
-    const uint32_t t = blockIdx.x;
-    const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
-    /* per_tile is a multiple of 32, so a warp's 32 clauses share one word of the liveness bitmap */
-    for (uint32_t base = c0; base < c1; base += blockDim.x) {
-        const uint32_t c = base + threadIdx.x;
-        bool live = false;
-        if (c < c1) {
-            const uint4 h = hdr[c];
-            live = !(h.z & SG_DELETED);
-            if (live) {
-                const uint32_t *l = lits + h.x;
-                for (uint32_t k = 0; k < h.y; ++k) atomicAdd(&s_cnt[l[k] >> shift], 1u);
+    for (uint32_t t = blockIdx.x; t < T; t += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cnt[b] = 0;
+        __syncthreads();
+        const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
+        /* per_tile is a multiple of 32, so a warp's 32 clauses share one word of the liveness bitmap */
+        for (uint32_t base = c0; base < c1; base += blockDim.x) {
+            const uint32_t c = base + threadIdx.x;
+            bool live = false;
+            if (c < c1) {
+                const uint4 h = __ldcs(hdr + c);
+                live = !(h.z & SG_DELETED);
+                if (live) {
+                    const uint32_t *l = lits + h.x;
+                    for (uint32_t k = 0; k < h.y; ++k) atomicAdd(&s_cnt[__ldcs(l + k) >> shift], 1u);
+                }
+            }
+            if (bits) {
+                const uint32_t m = __ballot_sync(0xffffffffu, live);
+                if ((threadIdx.x & 31) == 0 && (base + (threadIdx.x & ~31u)) < c1) bits[c >> 5] = m;
             }
         }
-        if (bits) {
-            const uint32_t m = __ballot_sync(0xffffffffu, live);
-            if ((threadIdx.x & 31) == 0 && (base + (threadIdx.x & ~31u)) < c1) bits[c >> 5] = m;
-        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) cnt[(size_t)b * T + t] = s_cnt[b];
+        __syncthreads();
     }
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) cnt[(size_t)b * T + t] = s_cnt[b];
 }
 
 __global__ void __launch_bounds__(OTB_TPB) k_otb_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
@@ -463,18 +470,25 @@ __global__ void __launch_bounds__(OTB_TPB) k_otb_scatter(const uint4 *__restrict
                                                           const uint32_t *__restrict__ base_of, uint2 *__restrict__ pairs)
 {
     extern __shared__ uint32_t s_cur[];
-    const uint32_t t = blockIdx.x;
-    for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cur[b] = base_of[(size_t)b * T + t];
-    __syncthreads();
-    const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
-    for (uint32_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-        const uint4 h = hdr[c];
-        if (h.z & SG_DELETED) continue;
-        const uint32_t *l = lits + h.x;
-        for (uint32_t k = 0; k < h.y; ++k) {
-            const uint32_t lit = l[k];
-            pairs[atomicAdd(&s_cur[lit >> shift], 1u)] = make_uint2(lit, c);
+    for (uint32_t t = blockIdx.x; t < T; t += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cur[b] = base_of[(size_t)b * T + t];
+        __syncthreads();
+        const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
+        for (uint32_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+            const uint4 h = __ldcs(hdr + c);
+            if (h.z & SG_DELETED) continue;
+            const uint32_t *l = lits + h.x;
+            for (uint32_t k0 = 0; k0 < h.y; k0 += 8) {
+                /* the literals of up to 8 positions first (independent loads), then their cursor atomics and stores */
+                uint32_t lit[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) lit[k] = k0 + k < h.y ? __ldcs(l + k0 + k) : 0u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k0 + k < h.y) pairs[atomicAdd(&s_cur[lit[k] >> shift], 1u)] = make_uint2(lit[k], c);
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -512,7 +526,14 @@ __global__ void __launch_bounds__(OTB_TPB, 2) k_otb_lists(const uint2 *__restric
     const uint32_t P = g1 - g0, lit0 = b << shift;
     for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) s_cur[i] = 0;
     __syncthreads();
-    for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) atomicAdd(&s_cur[pairs[g0 + p].x - lit0], 1u);
+    /* eight pairs per thread in flight: the loop would otherwise wait on one HBM access per iteration */
+    for (uint32_t p0 = 0; p0 < P; p0 += 8 * blockDim.x) {
+        uint32_t x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t p = p0 + k * blockDim.x + threadIdx.x; x[k] = p < P ? pairs[g0 + p].x : 0xFFFFFFFFu; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (x[k] != 0xFFFFFFFFu) atomicAdd(&s_cur[x[k] - lit0], 1u);
+    }
     __syncthreads();
     /* exclusive scan of the W counts: each thread owns W / blockDim consecutive literals */
     const uint32_t per = (W + blockDim.x - 1) / blockDim.x;
@@ -549,9 +570,12 @@ __global__ void __launch_bounds__(OTB_TPB, 2) k_otb_lists(const uint2 *__restric
     const bool staged = P <= OTB_CAP;
     const uint32_t shift4 = g0 & 3u;
     uint32_t *dst = staged ? stage + shift4 : ot_data + g0;
-    for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) {
-        const uint2 q = pairs[g0 + p];
-        dst[atomicAdd(&s_cur[q.x - lit0], 1u)] = q.y;
+    for (uint32_t p0 = 0; p0 < P; p0 += 8 * blockDim.x) {        /* second read of the bucket's pairs: L2 hits */
+        uint2 q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const uint32_t p = p0 + k * blockDim.x + threadIdx.x; q[k] = p < P ? pairs[g0 + p] : make_uint2(0xFFFFFFFFu, 0u); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (q[k].x != 0xFFFFFFFFu) dst[atomicAdd(&s_cur[q[k].x - lit0], 1u)] = q[k].y;
     }
     __syncthreads();
     if (!staged) __threadfence_block();
@@ -1468,8 +1492,9 @@ static bool otb_geometry(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t 
     while (((uint64_t)nlit + (1u << sh) - 1) >> sh > OTB_NBMAX && (1u << sh) < OTB_WMAX) ++sh;
     const uint64_t nb = ((uint64_t)nlit + (1u << sh) - 1) >> sh;
     if (nb > OTB_NBMAX) return false;
-    /* tiles: a few per SM, at least 1024 clauses each, a multiple of 32 clauses (bitmap words) */
-    uint32_t tiles = 148u * 8u;
+    /* tiles: sixteen per SM (two resident blocks take them in order, eight rounds), at least 1024 clauses each, a multiple
+     * of 32 clauses (bitmap words) */
+    uint32_t tiles = 148u * 16u;
     uint32_t pt = (n_cls + tiles - 1) / tiles;
     if (pt < 1024u) pt = 1024u;
     pt = (pt + 31u) & ~31u;
@@ -1483,7 +1508,7 @@ size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits)
     uint32_t sh, NB, T, pt;
     if (!otb_geometry(nlit, n_cls, lits, &sh, &NB, &T, &pt)) return 0;
     const size_t cnt = (size_t)NB * T + 8;
-    return cnt + be_scan_tmp_words((uint32_t)cnt) + 2 + 2 * (size_t)lits + 64;
+    return cnt + be_scan_tmp_words((uint32_t)cnt) + 8 + 2 * (size_t)lits + 64;
 }
 int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp, SgOtBuild *p)
 {
@@ -1500,17 +1525,19 @@ int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp
     p->ncnt = (size_t)p->NB * p->T;
     p->cnt = tmp;
     p->scantmp = tmp + p->ncnt + 8;
-    p->pairs = (void *)(p->scantmp + ((be_scan_tmp_words((uint32_t)(p->ncnt + 8)) + 1) & ~(size_t)1));
+    uint32_t *after = p->scantmp + be_scan_tmp_words((uint32_t)(p->ncnt + 8));
+    p->pairs = (void *)(((uintptr_t)after + 15) & ~(uintptr_t)15);                  /* uint2 records: 8-byte alignment needed */
     return 0;
 }
+static unsigned otb_grid(uint32_t T) { return T < 148u * 2u ? T : 148u * 2u; }
 void be_ot_build_count(void *s, const SgView &v, const SgOtBuild &p, uint32_t *bits)
 {
-    k_otb_count<<<p.T, OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, bits);
+    k_otb_count<<<otb_grid(p.T), OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, bits);
     ((BeStream *)s)->launches++; note_err(s, "k_otb_count");
 }
 void be_ot_build_scatter(void *s, const SgView &v, const SgOtBuild &p)
 {
-    k_otb_scatter<<<p.T, OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, (uint2 *)p.pairs);
+    k_otb_scatter<<<otb_grid(p.T), OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, (uint2 *)p.pairs);
     ((BeStream *)s)->launches++; note_err(s, "k_otb_scatter");
 }
 void be_ot_build_lists(void *s, const SgView &v, const SgOtBuild &p, const uint32_t *total)

@@ -176,7 +176,7 @@ size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits)
 {
     if (!nlit || !n_cls) return 0;
     const size_t NB = (nlit + 255) / 256, T = (n_cls + 63) / 64;
-    return NB * T + 8 + be_scan_tmp_words((uint32_t)(NB * T + 8)) + 2 + 2 * (size_t)lits + 64;
+    return NB * T + 8 + be_scan_tmp_words((uint32_t)(NB * T + 8)) + 8 + 2 * (size_t)lits + 64;
 }
 int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp, SgOtBuild *p)
 {
@@ -185,7 +185,7 @@ int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp
     p->shift = 8; p->NB = (nlit + 255) / 256; p->per_tile = 64; p->T = (n_cls + 63) / 64;
     p->ncnt = (size_t)p->NB * p->T;
     p->cnt = tmp; p->scantmp = tmp + p->ncnt + 8;
-    p->pairs = (void *)(p->scantmp + ((be_scan_tmp_words((uint32_t)(p->ncnt + 8)) + 1) & ~(size_t)1));
+    p->pairs = (void *)(((uintptr_t)(p->scantmp + be_scan_tmp_words((uint32_t)(p->ncnt + 8))) + 15) & ~(uintptr_t)15);
     return 0;
 }
 void be_ot_build_count(void *, const SgView &v, const SgOtBuild &p, uint32_t *bits)
