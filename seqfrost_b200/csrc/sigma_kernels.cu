@@ -412,51 +412,137 @@ __global__ void k_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restr
  * literal bins a one-level scatter costs one global atomic per literal plus a 4-byte store at a random place (round 1:
  * k_hist + 4 x k_scatter + order fix, 2.0 GB of DRAM traffic for 0.49 GB of payload).  Here the literal space is cut
  * into NB buckets of W = 2^shift consecutive literals, chosen so that one bucket's share of the table fits in shared
- * memory, and the clause ids are cut into T tiles:
+ * memory, and the clause ids are cut into T tiles (a tile's literals fit in shared memory as well):
  *   k_otb_count    tile t counts its literals per bucket in shared memory            -> cnt[b][t]        (reads the store once)
- *   scan           exclusive scan of cnt in (bucket, tile) order = where tile t's pairs of bucket b go
- *   k_otb_scatter  tile t writes its (literal, clause) pairs there, shared-memory cursors               (reads the store once, writes 8 B per literal)
- *   k_otb_lists    one block per bucket: per-literal counts (= ot_len), their scan (= ot_off: the bucket's pairs and its slice of
- *                  ot_data share one index range), clause ids placed in shared memory, every list put in ascending clause
- *                  id order there (= the reference's push order; the pairs arrive tile by tile, so the lists are nearly
- *                  sorted already), one bulk (TMA) store of the bucket's slice
+ *   scan           exclusive scan of cnt in (bucket, tile) order = where tile t's records of bucket b go
+ *   k_otb_scatter  tile t sorts its literals by bucket in shared memory (4-byte records: literal within the bucket |
+ *                  clause within the tile << shift) and writes every bucket's run with consecutive lanes: whole sectors
+ *                  instead of one partial sector per literal (ncu, 8-byte records stored one by one: 0.8 GB read + 0.8 GB
+ *                  written in DRAM for 0.36 + 0.41 GB, every sector filled before and written back after its last store)
+ *   k_otb_lists    one block per bucket: the bucket's records are T runs, one warp per run (the run number is the tile,
+ *                  which gives the clause id back); per-literal counts (= ot_len), their scan (= ot_off: the bucket's
+ *                  records and its slice of ot_data share one index range), clause ids placed in shared memory, every
+ *                  list put in ascending clause id order there (= the reference's push order; the warps walk the runs
+ *                  in tile order, so the lists are nearly sorted already), one bulk (TMA) store of the bucket's slice
  * No global atomics, the store is read twice instead of five times, every byte of ot_data is written once, coalesced.
- * A bucket whose share exceeds the staging buffer (a literal with tens of thousands of occurrences) is placed and sorted
- * in global memory instead. */
-constexpr int OTB_TPB = 512;
-constexpr uint32_t OTB_CAP = 20480;        /* staged clause ids per bucket (80 KB) */
+ * A tile or a bucket whose share exceeds the staging buffer (a literal with tens of thousands of occurrences) is
+ * written / placed and sorted in global memory instead. */
+constexpr int OTB_TPB = 1024;
+constexpr uint32_t OTB_SMEM_WORDS = 55000; /* dynamic shared memory of the scatter and the lists kernel (220 000 bytes) */
 constexpr uint32_t OTB_WMAX = 4096;        /* literals per bucket: two shared arrays of that many words */
-constexpr uint32_t OTB_NBMAX = 12288;      /* buckets: one shared counter each in the tile kernels (48 KB) */
+constexpr uint32_t OTB_NBMAX = 4096;       /* buckets: three shared words each in the scatter kernel */
+constexpr uint32_t OTB_TMAX = 148 * 32;    /* tiles: the run bounds of one bucket sit in shared memory in the lists kernel */
+constexpr uint32_t OTB_PAD = 0xFFFFFFFFu;
 
-/* The tile kernels run as a persistent grid: block g takes tiles g, g + G, g + 2G, ... in order, so that at any time the G
- * tiles in flight are neighbours.  Their pairs for one bucket are neighbours in memory as well, hence the window of the pair
- * buffer that is being filled (G / T of it) stays resident in L2 until its sectors are complete.  (With every tile resident
- * at once half of the 408 MB buffer was open at a time, and the 8-byte stores of uniformly random literals went to HBM as
- * partial sectors: 1.6 ms instead of 0.2.)  The store itself is streamed with evict-first loads for the same reason. */
-__global__ void __launch_bounds__(OTB_TPB) k_otb_count(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
-                                                        uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile,
-                                                        uint32_t *__restrict__ cnt, uint32_t *__restrict__ bits)
+/* block-wide exclusive scan of one value per thread (1024 threads); s_part: 32 words */
+__device__ __forceinline__ uint32_t otb_block_scan(uint32_t x, uint32_t *s_part, uint32_t *total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_part[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += y; }
+        s_part[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t e = (warp ? s_part[warp - 1] : 0) + incl - x;
+    if (total) *total = s_part[31];
+    __syncthreads();
+    return e;
+}
+
+/* The records of a tile (scatter) or of a bucket (lists) are a sequence of runs, given by n + 1 ascending bounds; runs may
+ * be empty.  otb_compact_runs keeps the non-empty ones: starts[0 .. NR] strictly ascending (starts[NR] = bounds[n]) and their
+ * numbers ids[0 .. NR).  Whole block; `starts` / `ids` must not alias `bounds`. */
+__device__ __forceinline__ uint32_t otb_compact_runs(const uint32_t *bounds, uint32_t n, uint32_t *starts, uint32_t *ids, uint32_t *s_part)
+{
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x, i0 = threadIdx.x * per;
+    uint32_t cnt = 0;
+    for (uint32_t k = 0; k < per; ++k) { const uint32_t i = i0 + k; if (i < n && bounds[i + 1] > bounds[i]) ++cnt; }
+    uint32_t NR;
+    uint32_t e = otb_block_scan(cnt, s_part, &NR);
+    for (uint32_t k = 0; k < per; ++k) {
+        const uint32_t i = i0 + k;
+        if (i < n && bounds[i + 1] > bounds[i]) { starts[e] = bounds[i]; ids[e] = i; ++e; }
+    }
+    if (threadIdx.x == 0) starts[NR] = bounds[n];
+    __syncthreads();
+    return NR;
+}
+/* the run r with starts[r] <= p < starts[r + 1], searched by the whole warp: 32 probes per round */
+__device__ __forceinline__ uint32_t otb_locate_warp(const uint32_t *starts, uint32_t n, uint32_t p)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 31) >> 5;
+        const uint32_t idx = lo + (lane + 1) * step;
+        const bool le = idx < hi && starts[idx] <= p;
+        const uint32_t k = __popc(__ballot_sync(0xffffffffu, le));
+        lo += k * step;
+        if (lo + step < hi) hi = lo + step;
+    }
+    return lo;
+}
+/* A warp at the 32 consecutive positions p0 .. p0 + 31, p0 inside run rc (starts[rc] <= p0 <= starts[rc + 1]): returns the run
+ * of this lane's position and moves rc on to the run of p0 + 32.  At most 32 runs can start inside 32 positions, so one load
+ * per lane and one warp-wide OR see them all. */
+__device__ __forceinline__ uint32_t otb_group_runs(const uint32_t *starts, uint32_t NR, uint32_t &rc, uint32_t p0)
+{
+    const uint32_t lane = threadIdx.x & 31, k = rc + 1 + lane;
+    uint32_t bit = 0;
+    if (k <= NR) { const uint32_t d = starts[k] - p0; if (d < 32u) bit = 1u << d; }
+    const uint32_t mask = __reduce_or_sync(0xffffffffu, bit);
+    const uint32_t mine = rc + __popc(mask & (0xFFFFFFFFu >> (31u - lane)));
+    rc += __popc(mask);
+    return mine;
+}
+
+/* The tile kernels run as a persistent grid: block g takes tiles g, g + G, g + 2G, ... in order, so that at any time the
+ * tiles in flight are neighbours, and so are their runs inside every bucket: the sectors two neighbouring runs share are
+ * completed in L2. */
+__global__ void __launch_bounds__(OTB_TPB, 2) k_otb_count(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
+                                                           uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile,
+                                                           uint32_t *__restrict__ cnt, uint32_t *__restrict__ bits)
 {
     extern __shared__ uint32_t s_cnt[];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(size_t)NB * T] = 0;          /* the scan's last word: the total */
     for (uint32_t t = blockIdx.x; t < T; t += gridDim.x) {
         for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cnt[b] = 0;
         __syncthreads();
         const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
         /* per_tile is a multiple of 32, so a warp's 32 clauses share one word of the liveness bitmap */
-        for (uint32_t base = c0; base < c1; base += blockDim.x) {
-            const uint32_t c = base + threadIdx.x;
-            bool live = false;
-            if (c < c1) {
-                const uint4 h = __ldcs(hdr + c);
-                live = !(h.z & SG_DELETED);
-                if (live) {
-                    const uint32_t *l = lits + h.x;
-                    for (uint32_t k = 0; k < h.y; ++k) atomicAdd(&s_cnt[__ldcs(l + k) >> shift], 1u);
-                }
+        for (uint32_t base = c0; base < c1; base += 2 * blockDim.x) {
+            uint4 h[2];
+            bool live[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t c = base + j * blockDim.x + threadIdx.x;
+                live[j] = false;
+                if (c < c1) { h[j] = __ldcs(hdr + c); live[j] = !(h[j].z & SG_DELETED); }
             }
-            if (bits) {
-                const uint32_t m = __ballot_sync(0xffffffffu, live);
-                if ((threadIdx.x & 31) == 0 && (base + (threadIdx.x & ~31u)) < c1) bits[c >> 5] = m;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t c = base + j * blockDim.x + threadIdx.x;
+                if (live[j]) {
+                    const uint32_t *l = lits + h[j].x;
+                    for (uint32_t k0 = 0; k0 < h[j].y; k0 += 8) {
+                        uint32_t lit[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) lit[k] = k0 + k < h[j].y ? __ldcs(l + k0 + k) : 0u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) if (k0 + k < h[j].y) atomicAdd(&s_cnt[lit[k] >> shift], 1u);
+                    }
+                }
+                if (bits) {
+                    const uint32_t m = __ballot_sync(0xffffffffu, live[j]);
+                    if ((threadIdx.x & 31) == 0 && (c & ~31u) < c1) bits[c >> 5] = m;
+                }
             }
         }
         __syncthreads();
@@ -465,27 +551,93 @@ __global__ void __launch_bounds__(OTB_TPB) k_otb_count(const uint4 *__restrict__
     }
 }
 
-__global__ void __launch_bounds__(OTB_TPB) k_otb_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
-                                                          uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile,
-                                                          const uint32_t *__restrict__ base_of, uint2 *__restrict__ pairs)
+__global__ void __launch_bounds__(OTB_TPB, 1) k_otb_scatter(const uint4 *__restrict__ hdr, const uint32_t *__restrict__ lits, uint32_t n_cls,
+                                                             uint32_t shift, uint32_t NB, uint32_t T, uint32_t per_tile, uint32_t rcap,
+                                                             const uint32_t *__restrict__ base_of, uint32_t *__restrict__ recs)
 {
-    extern __shared__ uint32_t s_cur[];
+    extern __shared__ __align__(128) uint32_t s_mem[];
+    __shared__ uint32_t s_part[32];
+    __shared__ uint32_t s_total;
+    uint32_t *s_off = s_mem;                       /* NB + 1: start of bucket b's run in the staged tile */
+    uint32_t *s_cur = s_mem + NB + 4;              /* NB: fill cursors */
+    uint32_t *s_gb = s_mem + 2 * NB + 8;           /* NB: where the run goes in recs */
+    uint32_t *s_ids = s_mem + 3 * NB + 12;         /* NB: non-empty buckets of the tile (their starts reuse s_cur) */
+    uint32_t *stage = s_mem + 4 * NB + 16;         /* rcap records */
+    const uint32_t per = (NB + blockDim.x - 1) / blockDim.x;                    /* <= 4 */
+    const uint32_t lmask = (1u << shift) - 1u;
     for (uint32_t t = blockIdx.x; t < T; t += gridDim.x) {
-        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) s_cur[b] = base_of[(size_t)b * T + t];
-        __syncthreads();
-        const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
-        for (uint32_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-            const uint4 h = __ldcs(hdr + c);
-            if (h.z & SG_DELETED) continue;
-            const uint32_t *l = lits + h.x;
-            for (uint32_t k0 = 0; k0 < h.y; k0 += 8) {
-                /* the literals of up to 8 positions first (independent loads), then their cursor atomics and stores */
-                uint32_t lit[8];
+        uint32_t g[4], n[4], sum = 0;
+        const uint32_t b0 = threadIdx.x * per;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) lit[k] = k0 + k < h.y ? __ldcs(l + k0 + k) : 0u;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = b0 + k;
+            n[k] = 0; g[k] = 0;
+            if ((uint32_t)k < per && b < NB) {
+                const size_t i = (size_t)b * T + t;
+                g[k] = base_of[i];
+                n[k] = base_of[i + 1] - g[k];
+                sum += n[k];
+            }
+        }
+        uint32_t e = otb_block_scan(sum, s_part, &s_total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = b0 + k;
+            if ((uint32_t)k < per && b < NB) { s_off[b] = e; s_cur[b] = e; s_gb[b] = g[k]; e += n[k]; }
+        }
+        if (threadIdx.x == 0) s_off[NB] = s_total;
+        __syncthreads();
+        const uint32_t R = s_total;
+        const bool staged = R <= rcap;
+        const uint32_t c0 = t * per_tile, c1 = min(n_cls, c0 + per_tile);
+        for (uint32_t base = c0; base < c1; base += 4 * blockDim.x) {
+            /* four clauses per thread: their headers, then the first eight literals of each, in flight together */
+            uint4 h[4];
+            uint32_t lit[4][8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t c = base + j * blockDim.x + threadIdx.x;
+                h[j] = c < c1 ? __ldcs(hdr + c) : make_uint4(0u, 0u, SG_DELETED, 0u);
+                if (h[j].z & SG_DELETED) h[j].y = 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) lit[j][k] = (uint32_t)k < h[j].y ? __ldcs(lits + h[j].x + k) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t cl = (base + j * blockDim.x + threadIdx.x - c0) << shift;
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if (k0 + k < h.y) pairs[atomicAdd(&s_cur[lit[k] >> shift], 1u)] = make_uint2(lit[k], c);
+                    if ((uint32_t)k < h[j].y) {
+                        const uint32_t b = lit[j][k] >> shift;
+                        const uint32_t slot = atomicAdd(&s_cur[b], 1u);
+                        const uint32_t rec = (lit[j][k] & lmask) | cl;
+                        if (staged) stage[slot] = rec; else recs[s_gb[b] + (slot - s_off[b])] = rec;
+                    }
+                for (uint32_t k = 8; k < h[j].y; ++k) {
+                    const uint32_t x = __ldcs(lits + h[j].x + k);
+                    const uint32_t b = x >> shift;
+                    const uint32_t slot = atomicAdd(&s_cur[b], 1u);
+                    const uint32_t rec = (x & lmask) | cl;
+                    if (staged) stage[slot] = rec; else recs[s_gb[b] + (slot - s_off[b])] = rec;
+                }
+            }
+        }
+        __syncthreads();
+        if (staged) {
+            /* consecutive lanes, consecutive staged records -> consecutive words of a run in recs; which run: the non-empty
+             * buckets compacted, then a mask of the run starts inside each group of 32 records */
+            const uint32_t NR = otb_compact_runs(s_off, NB, s_cur, s_ids, s_part);
+            const uint32_t lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+            for (uint32_t i0 = (threadIdx.x >> 5) * 128; i0 < R; i0 += nw * 128) {
+                uint32_t rc = otb_locate_warp(s_cur, NR, i0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    const uint32_t r = otb_group_runs(s_cur, NR, rc, i0 + q * 32);
+                    if (i < R) recs[s_gb[s_ids[r]] + (i - s_cur[r])] = stage[i];
+                }
             }
         }
         __syncthreads();
@@ -511,49 +663,57 @@ __device__ __forceinline__ void otb_sort_list(uint32_t *d, uint32_t n)
     }
 }
 
-__global__ void __launch_bounds__(OTB_TPB, 2) k_otb_lists(const uint2 *__restrict__ pairs, const uint32_t *__restrict__ base_of, uint32_t NB,
-                                                          uint32_t T, uint32_t shift, uint32_t nlit, const uint32_t *__restrict__ total,
+/* the records of one bucket, 128 consecutive ones per warp and step (the warps walk the bucket side by side, so the
+ * records of a list are met nearly in tile order); f(record, tile).  The tile of a record is the run it lies in. */
+template <bool LAST_USE, class F>
+__device__ __forceinline__ void otb_for_records(const uint32_t *__restrict__ recs, const uint32_t *s_st, const uint32_t *s_tile, uint32_t NR, uint32_t P, F f)
+{
+    const uint32_t lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const uint32_t g0 = s_st[0];
+    for (uint32_t i0 = (threadIdx.x >> 5) * 128; i0 < P; i0 += nw * 128) {
+        uint32_t r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = i0 + q * 32 + lane;
+            r[q] = i < P ? (LAST_USE ? __ldcs(recs + g0 + i) : __ldg(recs + g0 + i)) : OTB_PAD;
+        }
+        uint32_t rc = otb_locate_warp(s_st, NR, g0 + i0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t run = otb_group_runs(s_st, NR, rc, g0 + i0 + q * 32);
+            if (i0 + q * 32 + lane < P) f(r[q], s_tile[run]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(OTB_TPB, 1) k_otb_lists(const uint32_t *__restrict__ recs, const uint32_t *__restrict__ base_of, uint32_t NB,
+                                                          uint32_t T, uint32_t shift, uint32_t per_tile, uint32_t pcap, uint32_t nlit,
                                                           uint32_t *__restrict__ ot_off, uint32_t *__restrict__ ot_len, uint32_t *__restrict__ ot_data)
 {
     extern __shared__ __align__(128) uint32_t s_mem[];
-    const uint32_t W = 1u << shift;
+    __shared__ uint32_t s_part[32];
+    const uint32_t W = 1u << shift, lmask = W - 1u;
     uint32_t *s_loc = s_mem;                 /* W + 1: exclusive offsets of the bucket's lists */
     uint32_t *s_cur = s_mem + W + 4;         /* W: fill cursors */
-    uint32_t *stage = s_mem + 2 * W + 8;     /* OTB_CAP + 4 staged clause ids */
-    __shared__ uint32_t s_part[OTB_TPB / 32];
+    const uint32_t Tq = (T + 1 + 3) & ~3u;
+    uint32_t *s_tb = s_mem + 2 * W + 8;      /* T + 1: run bounds */
+    uint32_t *s_st = s_tb + Tq;              /* T + 1: starts of the non-empty runs */
+    uint32_t *s_tile = s_st + Tq;            /* T: their tiles */
+    uint32_t *stage = s_tile + Tq;           /* pcap + 4 staged clause ids (16-byte aligned) */
     const uint32_t b = blockIdx.x;
-    const uint32_t g0 = base_of[(size_t)b * T], g1 = b + 1 < NB ? base_of[(size_t)(b + 1) * T] : *total;
-    const uint32_t P = g1 - g0, lit0 = b << shift;
+    for (uint32_t i = threadIdx.x; i <= T; i += blockDim.x) s_tb[i] = base_of[(size_t)b * T + i];
     for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) s_cur[i] = 0;
     __syncthreads();
-    /* eight pairs per thread in flight: the loop would otherwise wait on one HBM access per iteration */
-    for (uint32_t p0 = 0; p0 < P; p0 += 8 * blockDim.x) {
-        uint32_t x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const uint32_t p = p0 + k * blockDim.x + threadIdx.x; x[k] = p < P ? pairs[g0 + p].x : 0xFFFFFFFFu; }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (x[k] != 0xFFFFFFFFu) atomicAdd(&s_cur[x[k] - lit0], 1u);
-    }
+    const uint32_t g0 = s_tb[0], P = s_tb[T] - g0, lit0 = b << shift;
+    const uint32_t NR = otb_compact_runs(s_tb, T, s_st, s_tile, s_part);
+    if (P) otb_for_records<false>(recs, s_st, s_tile, NR, P, [&](uint32_t r, uint32_t) { atomicAdd(&s_cur[r & lmask], 1u); });
     __syncthreads();
     /* exclusive scan of the W counts: each thread owns W / blockDim consecutive literals */
     const uint32_t per = (W + blockDim.x - 1) / blockDim.x;
     const uint32_t i0 = threadIdx.x * per;
     uint32_t sum = 0;
     for (uint32_t k = 0; k < per; ++k) if (i0 + k < W) sum += s_cur[i0 + k];
-    uint32_t incl = sum;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
-    if (lane == 31) s_part[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = lane < OTB_TPB / 32 ? s_part[lane] : 0;
-#pragma unroll
-        for (int d = 1; d < OTB_TPB / 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (uint32_t)d) w += y; }
-        if (lane < OTB_TPB / 32) s_part[lane] = w;
-    }
-    __syncthreads();
-    uint32_t e = (warp ? s_part[warp - 1] : 0) + incl - sum;
+    uint32_t e = otb_block_scan(sum, s_part, nullptr);
     for (uint32_t k = 0; k < per; ++k) {
         const uint32_t i = i0 + k;
         if (i < W) {
@@ -567,16 +727,11 @@ __global__ void __launch_bounds__(OTB_TPB, 2) k_otb_lists(const uint2 *__restric
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) s_cur[i] = s_loc[i];
     __syncthreads();
-    const bool staged = P <= OTB_CAP;
+    const bool staged = P <= pcap;
     const uint32_t shift4 = g0 & 3u;
     uint32_t *dst = staged ? stage + shift4 : ot_data + g0;
-    for (uint32_t p0 = 0; p0 < P; p0 += 8 * blockDim.x) {        /* second read of the bucket's pairs: L2 hits */
-        uint2 q[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const uint32_t p = p0 + k * blockDim.x + threadIdx.x; q[k] = p < P ? pairs[g0 + p] : make_uint2(0xFFFFFFFFu, 0u); }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (q[k].x != 0xFFFFFFFFu) dst[atomicAdd(&s_cur[q[k].x - lit0], 1u)] = q[k].y;
-    }
+    /* second read of the bucket's records: L2 hits */
+    if (P) otb_for_records<true>(recs, s_st, s_tile, NR, P, [&](uint32_t r, uint32_t t) { dst[atomicAdd(&s_cur[r & lmask], 1u)] = t * per_tile + (r >> shift); });
     __syncthreads();
     if (!staged) __threadfence_block();
     for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) otb_sort_list(dst + s_loc[i], s_loc[i + 1] - s_loc[i]);
@@ -1485,22 +1640,32 @@ void be_hist(void *s, const SgView &v, uint32_t *counts)
 static bool otb_geometry(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *shift, uint32_t *NB, uint32_t *T, uint32_t *per_tile)
 {
     if (!nlit || !n_cls) return false;
-    /* about half the staging buffer per bucket on average: W = 2^shift >= (CAP / 2) * nlit / lits */
-    const uint64_t want = lits ? ((uint64_t)(OTB_CAP / 2) * nlit + lits - 1) / lits : OTB_WMAX;
-    uint32_t sh = 8;
-    while ((1ull << sh) < want && (1u << sh) < OTB_WMAX) ++sh;
-    while (((uint64_t)nlit + (1u << sh) - 1) >> sh > OTB_NBMAX && (1u << sh) < OTB_WMAX) ++sh;
+    if (!lits) lits = 1;
+    /* buckets: as wide as possible (long runs per tile and bucket = whole sectors in the scatter) while an average bucket
+     * takes at most 60 % of the lists kernel's staging room and every SM has two buckets to work on */
+    uint32_t sh = 12, best = 0;
+    for (; sh >= 6; --sh) {
+        const uint64_t nb = ((uint64_t)nlit + (1u << sh) - 1) >> sh;
+        if (nb > OTB_NBMAX) break;
+        const uint64_t avg = lits / nb + 1;
+        const uint64_t pcap = OTB_SMEM_WORDS - 2ull * (1u << sh) - 16 - 3 * (OTB_TMAX / 4 + 4);
+        if (avg * 10 <= pcap * 6) { best = sh; if (nb >= 296) break; }
+    }
+    if (!best) return false;
+    sh = best;
     const uint64_t nb = ((uint64_t)nlit + (1u << sh) - 1) >> sh;
-    if (nb > OTB_NBMAX) return false;
-    /* tiles: sixteen per SM (two resident blocks take them in order, eight rounds), at least 1024 clauses each, a multiple
-     * of 32 clauses (bitmap words) */
-    uint32_t tiles = 148u * 16u;
-    uint32_t pt = (n_cls + tiles - 1) / tiles;
-    if (pt < 1024u) pt = 1024u;
+    /* tiles: a multiple of the SM count, an average tile fills 80 % of the scatter's staging room; a multiple of 32 clauses
+     * (bitmap words) */
+    const uint64_t rcap = OTB_SMEM_WORDS - 4 * nb - 24;
+    uint64_t tiles = (lits * 10 + rcap * 8 - 1) / (rcap * 8);
+    tiles = (tiles + 147) / 148 * 148;
+    if (tiles > OTB_TMAX) return false;
+    uint32_t pt = (uint32_t)((n_cls + tiles - 1) / tiles);
     pt = (pt + 31u) & ~31u;
-    tiles = (n_cls + pt - 1) / pt;
-    if (nb * (uint64_t)tiles >= 0xFFFFFFF0ull) return false;
-    *shift = sh; *NB = (uint32_t)nb; *T = tiles; *per_tile = pt;
+    if ((uint64_t)pt >= (1ull << (32 - sh)) - 1) return false;          /* clause within the tile: 32 - shift bits of a record */
+    tiles = ((uint64_t)n_cls + pt - 1) / pt;
+    if (nb * tiles >= 0xFFFFFFF0ull) return false;
+    *shift = sh; *NB = (uint32_t)nb; *T = (uint32_t)tiles; *per_tile = pt;
     return true;
 }
 size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits)
@@ -1508,42 +1673,46 @@ size_t be_ot_build_tmp_words(uint32_t nlit, uint32_t n_cls, uint64_t lits)
     uint32_t sh, NB, T, pt;
     if (!otb_geometry(nlit, n_cls, lits, &sh, &NB, &T, &pt)) return 0;
     const size_t cnt = (size_t)NB * T + 8;
-    return cnt + be_scan_tmp_words((uint32_t)cnt) + 8 + 2 * (size_t)lits + 64;
+    return cnt + be_scan_tmp_words((uint32_t)cnt) + 8 + (size_t)lits + 64;
 }
 int be_ot_build_plan(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t *tmp, SgOtBuild *p)
 {
     if (!otb_geometry(nlit, n_cls, lits, &p->shift, &p->NB, &p->T, &p->per_tile)) return 1;
     static int smem_ok = -1;
     if (smem_ok < 0) {
-        const size_t lists_smem = (2ull * OTB_WMAX + 8 + OTB_CAP + 8) * 4;
-        smem_ok = cudaFuncSetAttribute(k_otb_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lists_smem) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_otb_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(OTB_NBMAX * 4)) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_otb_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(OTB_NBMAX * 4)) == cudaSuccess;
+        smem_ok = cudaFuncSetAttribute(k_otb_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(OTB_SMEM_WORDS * 4)) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_otb_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(OTB_SMEM_WORDS * 4)) == cudaSuccess;
         (void)cudaGetLastError();
     }
     if (!smem_ok) return 1;
-    p->ncnt = (size_t)p->NB * p->T;
+    p->ncnt = (size_t)p->NB * p->T + 1;                 /* + the word that receives the total */
     p->cnt = tmp;
-    p->scantmp = tmp + p->ncnt + 8;
-    uint32_t *after = p->scantmp + be_scan_tmp_words((uint32_t)(p->ncnt + 8));
-    p->pairs = (void *)(((uintptr_t)after + 15) & ~(uintptr_t)15);                  /* uint2 records: 8-byte alignment needed */
+    p->scantmp = tmp + p->ncnt + 7;
+    uint32_t *after = p->scantmp + be_scan_tmp_words((uint32_t)(p->ncnt + 7));
+    p->pairs = (void *)(((uintptr_t)after + 15) & ~(uintptr_t)15);
     return 0;
 }
-static unsigned otb_grid(uint32_t T) { return T < 148u * 2u ? T : 148u * 2u; }
+static unsigned otb_grid(uint32_t T, unsigned per_sm) { return T < 148u * per_sm ? T : 148u * per_sm; }
 void be_ot_build_count(void *s, const SgView &v, const SgOtBuild &p, uint32_t *bits)
 {
-    k_otb_count<<<otb_grid(p.T), OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, bits);
+    k_otb_count<<<otb_grid(p.T, 2), OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, bits);
     ((BeStream *)s)->launches++; note_err(s, "k_otb_count");
 }
 void be_ot_build_scatter(void *s, const SgView &v, const SgOtBuild &p)
 {
-    k_otb_scatter<<<otb_grid(p.T), OTB_TPB, p.NB * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, p.cnt, (uint2 *)p.pairs);
+    uint32_t rcap = OTB_SMEM_WORDS - 4 * p.NB - 24;
+    { const char *e = getenv("SIGMA_OTB_CAPS"); if (e && (uint32_t)atol(e) < rcap) rcap = (uint32_t)atol(e); }   /* test hook: unstaged tiles */
+    k_otb_scatter<<<otb_grid(p.T, 1), OTB_TPB, OTB_SMEM_WORDS * 4, ST(s)>>>((const uint4 *)v.hdr, v.lits, v.n_cls, p.shift, p.NB, p.T, p.per_tile, rcap,
+                                                                           p.cnt, (uint32_t *)p.pairs);
     ((BeStream *)s)->launches++; note_err(s, "k_otb_scatter");
 }
 void be_ot_build_lists(void *s, const SgView &v, const SgOtBuild &p, const uint32_t *total)
 {
-    const size_t smem = (2ull * (1u << p.shift) + 8 + OTB_CAP + 8) * 4;
-    k_otb_lists<<<p.NB, OTB_TPB, smem, ST(s)>>>((const uint2 *)p.pairs, p.cnt, p.NB, p.T, p.shift, v.nlit, total, v.ot_off, v.ot_len, v.ot_data);
+    (void)total;                                        /* the scan left it behind the last count */
+    uint32_t pcap = OTB_SMEM_WORDS - 2 * (1u << p.shift) - 16 - 3 * ((p.T + 4) & ~3u) - 4;
+    { const char *e = getenv("SIGMA_OTB_CAPS"); if (e && (uint32_t)atol(e) < pcap) pcap = (uint32_t)atol(e); }   /* test hook: unstaged buckets */
+    k_otb_lists<<<p.NB, OTB_TPB, OTB_SMEM_WORDS * 4, ST(s)>>>((const uint32_t *)p.pairs, p.cnt, p.NB, p.T, p.shift, p.per_tile, pcap, v.nlit,
+                                                             v.ot_off, v.ot_len, v.ot_data);
     ((BeStream *)s)->launches++; note_err(s, "k_otb_lists");
 }
 void be_scatter(void *s, const SgView &v, uint32_t *cursor)

@@ -275,11 +275,11 @@ int stage_create_ot(sigma_ctx *c, uint64_t live_lits, uint32_t live_cls, bool tr
             be_scan_u32(c->stream, plan.cnt, plan.cnt, (uint32_t)plan.ncnt, c->totals.p, plan.scantmp);
         }
         {
-            Stage st(c, SIGMA_T_OT_SCATTER, 4 * live_lits + 8ull * c->n_cls + cw + 8 * live_lits);
+            Stage st(c, SIGMA_T_OT_SCATTER, 4 * live_lits + 8ull * c->n_cls + cw + 4 * live_lits);      /* 4-byte records */
             be_ot_build_scatter(c->stream, v, plan);
         }
         {
-            Stage st(c, SIGMA_T_OT_ORDER, 8 * live_lits + 4 * live_lits + 8ull * nlit);
+            Stage st(c, SIGMA_T_OT_ORDER, 4 * live_lits + 4 * live_lits + 8ull * nlit);
             be_ot_build_lists(c->stream, v, plan, c->totals.p);
         }
         c->rep.ot_build_mode = 2;
