@@ -155,6 +155,9 @@ void be_elect_round(void *s, const SgView &v, const uint32_t *wl_in, uint32_t *w
 /* every batch and round of one election in a single launch; returns non-zero when unavailable (the caller then
  * drives be_elect_batch / be_elect_round itself).  sc->wl_count[0] receives the number of rounds. */
 int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_t b0, uint32_t grow);
+/* the whole election in one launch without rounds: every warp takes its candidates in rank order, parks the blocked ones
+ * and polls their blockers (sigma_kernels.cu, k_elect_async).  Same return convention; sc->wl_count[0] = looks of the busiest warp. */
+int be_elect_async(void *s, const SgView &v);
 void be_acting_flags(void *s, const SgView &v, uint32_t *flags_acting, uint32_t *flags_elected);   /* per rank position */
 void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe);
 /* generic item / serial launches */

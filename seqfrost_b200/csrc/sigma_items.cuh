@@ -665,9 +665,12 @@ SG_HD void sg_elect_prep_item(const SgView &v, uint32_t var)
 #ifndef SG_ELECT_BATCH
 #define SG_ELECT_BATCH 8        /* literals (and their election words) in flight per lane */
 #endif
-SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
+/* blocker (may be null): when the candidate stays undecided, *blocker receives the undecided earlier-ranked neighbour of the
+ * highest rank - the one most likely to be decided last; until its election word changes, looking again is pointless */
+SG_HDN inline bool sg_elect_eval(const SgView &v, uint32_t cand, uint32_t *blocker)
 {
     const SgLane L = sg_lane_ctx();
+    uint32_t bl_key = 0, bl_var = 0;                          /* rank + 1 of this lane's best blocker */
     const uint32_t wc = sg_bcast(sg_er_load(v, cand));
     if (SG_ER_STAT(wc) != SG_E_UNDECIDED) return false;       /* frozen by a push since it was queued */
     const uint32_t rc = SG_ER_RANK(wc);
@@ -694,14 +697,27 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
             for (int k = 0; k < SG_ELECT_BATCH; ++k) {
                 if (w[k] == 0xFFFFFFFFu || SG_ER_RANK(w[k]) > rc) continue;
                 const uint32_t s = SG_ER_STAT(w[k]);
-                if (s == SG_E_UNDECIDED) blocked = true;
+                if (s == SG_E_UNDECIDED) {
+                    blocked = true;
+                    if (SG_ER_RANK(w[k]) + 1 > bl_key) { bl_key = SG_ER_RANK(w[k]) + 1; bl_var = SG_ABS(other[k]); }
+                }
                 else if (s == SG_E_BOTH || (s == SG_E_PONLY && !SG_SIGN(other[k]))) frozen = true;
             }
         }
     }
     const uint32_t flags = sg_wor((blocked ? 1u : 0u) | (frozen ? 2u : 0u) | (failp ? 4u : 0u) | (failn ? 8u : 0u));
     if (flags & 2u) { if (L.lane == 0) sg_er_set(v, cand, SG_E_FROZEN); return false; }
-    if (flags & 1u) return true;
+    if (flags & 1u) {
+        if (blocker) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t best = __reduce_max_sync(0xffffffffu, bl_key);
+            *blocker = __shfl_sync(0xffffffffu, bl_var, __ffs((int)__ballot_sync(0xffffffffu, bl_key == best)) - 1);
+#else
+            *blocker = bl_var;
+#endif
+        }
+        return true;
+    }
     uint32_t st;
     if (sg_break_cond(v, cand)) { st = SG_E_BREAK; if (L.lane == 0) sg_atomic_min(&v.sc->brk_rank, rc); }
     else if (flags & 4u) st = SG_E_NONE;
@@ -731,6 +747,8 @@ SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand)
     }
     return false;
 }
+
+SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand) { return sg_elect_eval(v, cand, nullptr); }
 
 /* function-table core marks (lcve.cpp:85-102): the first 12 variables of the freeze stack.
  * ONE thread; `acting` holds the acting candidates in election order (bit31 = P only). */

@@ -944,6 +944,69 @@ __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_persistent(
     if (gtid == 0) v.sc->wl_count[0] = rounds;
 }
 
+/* The election without rounds and without grid-wide barriers.  Warp w takes the candidates of rank w, w + W, w + 2W, ...
+ * in that order.  A candidate that is blocked (an earlier-ranked neighbour is still undecided) is parked in one of the
+ * warp's 32 slots - lane j keeps slot j in registers - together with its blocker; the warp goes on with its next
+ * candidates, polls the blockers' election words (one load per lane), and looks at a parked candidate again only when its
+ * blocker's word has changed.  Progress: the warps are co-resident (cooperative launch) and take their ranks in ascending
+ * order, so the lowest undecided rank of the whole election is either parked - then nothing blocks it and its next look
+ * decides it - or next in a warp whose parked candidates all have lower ranks, i.e. none.  The outcome is the sequential
+ * one for the same reason as in the round version: a candidate is decided on final election words of all its
+ * earlier-ranked neighbours.  sc->wl_count[0] receives the largest number of looks any warp needed (a report figure). */
+__global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_async(SgView v)
+{
+    const uint32_t V = v.nvars;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t p_cand = 0, p_blk = 0;            /* slot `lane`: parked candidate (0 = free) and its blocker */
+    uint32_t f_var = 0, f_mask = 0;            /* the fetched block: lane j holds the candidate of rank f_base + j * nwarps */
+    uint64_t f_base = gwarp;                   /* rank of lane 0's entry of the NEXT block to fetch */
+    bool more = gwarp < V;
+    uint32_t looks = 0, ready = 0;
+    while (true) {
+        const uint32_t parked = __ballot_sync(0xffffffffu, p_cand != 0);
+        if (!ready && parked) {
+            /* parked candidates worth another look: the blocker has been decided, a push froze the candidate itself, or the
+             * break moved below its rank (its blocker may then never be looked at) */
+            bool rdy = false;
+            if (p_cand) {
+                const uint32_t w = sg_er_load(v, p_cand);
+                rdy = SG_ER_STAT(w) != SG_E_UNDECIDED || SG_ER_STAT(sg_er_load(v, p_blk)) != SG_E_UNDECIDED ||
+                      SG_ER_RANK(w) > *(volatile uint32_t *)&v.sc->brk_rank;
+            }
+            ready = __ballot_sync(0xffffffffu, rdy);
+        }
+        int j;
+        uint32_t cand;
+        if (ready) {
+            j = __ffs((int)ready) - 1;
+            ready &= ready - 1;
+            cand = __shfl_sync(0xffffffffu, p_cand, j);
+        } else if (parked != 0xFFFFFFFFu && f_mask) {
+            /* a new candidate, in rank order, into the first free slot if it has to wait */
+            const int k = __ffs((int)f_mask) - 1;
+            f_mask &= f_mask - 1;
+            cand = __shfl_sync(0xffffffffu, f_var, k);
+            j = __ffs((int)~parked) - 1;
+        } else if (parked != 0xFFFFFFFFu && more) {
+            const uint32_t brk = __shfl_sync(0xffffffffu, *(volatile uint32_t *)&v.sc->brk_rank, 0);
+            const uint64_t r = f_base + (uint64_t)lane * nwarps;
+            f_var = 0;
+            if (r < V && r <= brk) { const uint32_t x = v.order[(uint32_t)r]; if (SG_ER_STAT(sg_er_load(v, x)) == SG_E_UNDECIDED) f_var = x; }
+            f_mask = __ballot_sync(0xffffffffu, f_var != 0);
+            f_base += 32ull * nwarps;
+            more = f_base < V && f_base <= brk;
+            continue;
+        } else if (!parked && !f_mask && !more) break;
+        else { __nanosleep(200); continue; }
+        uint32_t blk = 0;
+        const bool stay = sg_elect_eval(v, cand, &blk);          /* returns at once when a push froze it meanwhile */
+        ++looks;
+        if ((int)lane == j) { p_cand = stay ? cand : 0u; p_blk = blk; }
+    }
+    if (lane == 0) atomicMax(&v.sc->wl_count[0], looks);
+}
+
 __global__ void k_acting_flags(SgView v, uint32_t *__restrict__ fa, uint32_t *__restrict__ fe)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1793,6 +1856,26 @@ int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_
     SgView vv = v;
     void *args[] = { (void *)&vv, (void *)&wl0, (void *)&wl1, (void *)&b0, (void *)&grow };
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_elect_persistent, dim3((unsigned)(blocks_per_sm * sms)), dim3(SG_ELECT_TPB), args, 0, ST(s));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); blocks_per_sm = 0; return 1; }
+    ((BeStream *)s)->launches++;
+    return 0;
+}
+int be_elect_async(void *s, const SgView &v)
+{
+    static int blocks_per_sm = -1, sms = 0;
+    if (blocks_per_sm < 0) {
+        int dev = 0, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_elect_async, SG_ELECT_TPB, 0) != cudaSuccess) blocks_per_sm = 0;
+        (void)cudaGetLastError();
+    }
+    if (blocks_per_sm <= 0 || !v.nvars) return 1;
+    SgView vv = v;
+    void *args[] = { (void *)&vv };
+    /* cooperative launch: the kernel has no grid-wide barrier, but its warps wait for each other, so all of them must be resident */
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_elect_async, dim3((unsigned)(blocks_per_sm * sms)), dim3(SG_ELECT_TPB), args, 0, ST(s));
     if (e != cudaSuccess) { (void)cudaGetLastError(); blocks_per_sm = 0; return 1; }
     ((BeStream *)s)->launches++;
     return 0;

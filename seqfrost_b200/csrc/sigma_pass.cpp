@@ -482,12 +482,15 @@ again:
         long env_pers = -1, env_pgrow = -1;
         {
             const char *e;
-            env_pers = (e = getenv("SIGMA_ELECT_PERSISTENT")) ? atol(e) : 1;
+            env_pers = (e = getenv("SIGMA_ELECT_PERSISTENT")) ? atol(e) : 2;
             env_pgrow = (e = getenv("SIGMA_ELECT_PGROW")) ? atol(e) : 2;
             if (env_pgrow < 2) env_pgrow = 2;
         }
         bool done = false;
-        if (env_pers && be_elect_all(c->stream, v, c->wl0.p, c->wl1.p, (uint32_t)(env_b0 < 16384 ? 16384 : env_b0), (uint32_t)env_pgrow) == 0)
+        /* default (2): no rounds at all - warps park blocked candidates and poll; 1: batches + rounds inside one cooperative
+         * launch; 0: host-driven rounds */
+        if (env_pers >= 2 && be_elect_async(c->stream, v) == 0) done = true;
+        if (!done && env_pers && be_elect_all(c->stream, v, c->wl0.p, c->wl1.p, (uint32_t)(env_b0 < 16384 ? 16384 : env_b0), (uint32_t)env_pgrow) == 0)
             done = true;                                   /* the round count comes back with the totals below */
         const bool persistent = done;
         uint32_t r0 = 0, bsize = (uint32_t)env_b0;

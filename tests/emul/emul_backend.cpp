@@ -284,7 +284,8 @@ void be_elect_round(void *, const SgView &v, const uint32_t *wl_in, uint32_t *wl
         if (sg_elect_round_item(v, wl_in[i])) wl_out[m++] = wl_in[i];
     v.sc->wl_count[parity ^ 1] = m;
 }
-int be_elect_all(void *, const SgView &, uint32_t *, uint32_t *, uint32_t, uint32_t) { return 1; }   /* host-driven rounds in the stand-in */
+int be_elect_all(void *, const SgView &, uint32_t *, uint32_t *, uint32_t, uint32_t) { return 1; }
+int be_elect_async(void *, const SgView &) { return 1; }   /* host-driven rounds in the stand-in */
 void be_acting_flags(void *, const SgView &v, uint32_t *fa, uint32_t *fe)
 {
     g_launches++;
