@@ -158,6 +158,9 @@ int be_elect_all(void *s, const SgView &v, uint32_t *wl0, uint32_t *wl1, uint32_
 /* the whole election in one launch without rounds: every warp takes its candidates in rank order, parks the blocked ones
  * and polls their blockers (sigma_kernels.cu, k_elect_async).  Same return convention; sc->wl_count[0] = looks of the busiest warp. */
 int be_elect_async(void *s, const SgView &v);
+/* scores + stable sort by (score, variable) + rank[] in one cooperative launch; forced_bits = 0: key width from the largest
+ * score, on the device.  Nonzero return: not available, use be_scores / be_sort_pairs / be_rank. */
+int be_vo_sort(void *s, const SgView &v, uint32_t *tmpk, uint32_t *tmpv, uint32_t *tmp, uint32_t forced_bits);
 void be_acting_flags(void *s, const SgView &v, uint32_t *flags_acting, uint32_t *flags_elected);   /* per rank position */
 void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint32_t *pa, const uint32_t *fe, const uint32_t *pe);
 /* generic item / serial launches */

@@ -671,13 +671,16 @@ SG_HDN inline bool sg_elect_eval(const SgView &v, uint32_t cand, uint32_t *block
 {
     const SgLane L = sg_lane_ctx();
     uint32_t bl_key = 0, bl_var = 0;                          /* rank + 1 of this lane's best blocker */
+    /* the list headers are fetched together with the election word, not after it: one memory round trip less on the
+     * chain word -> lists -> headers -> literals -> neighbours' words that bounds this function */
+    const int np = (int)v.ot_len[2 * cand], nn = (int)v.ot_len[2 * cand + 1];
+    const uint32_t *dp = sg_list(v, 2 * cand), *dn = sg_list(v, 2 * cand + 1);
+    const uint32_t brk = *(volatile uint32_t *)&v.sc->brk_rank;
     const uint32_t wc = sg_bcast(sg_er_load(v, cand));
     if (SG_ER_STAT(wc) != SG_E_UNDECIDED) return false;       /* frozen by a push since it was queued */
     const uint32_t rc = SG_ER_RANK(wc);
-    if (rc > sg_bcast(*(volatile uint32_t *)&v.sc->brk_rank)) { if (L.lane == 0) sg_er_set(v, cand, SG_E_SKIP); return false; }
+    if (rc > sg_bcast(brk)) { if (L.lane == 0) sg_er_set(v, cand, SG_E_SKIP); return false; }
     const int maxcsize = v.o.lcve_clause_max;
-    const int np = (int)v.ot_len[2 * cand], nn = (int)v.ot_len[2 * cand + 1];
-    const uint32_t *dp = sg_list(v, 2 * cand), *dn = sg_list(v, 2 * cand + 1);
     bool blocked = false, frozen = false, failp = false, failn = false;
     for (int q = (int)L.lane; q < np + nn; q += (int)L.width) {
         const bool neg = q >= np;

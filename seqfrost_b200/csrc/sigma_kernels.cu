@@ -825,6 +825,144 @@ __global__ void k_rank(SgView v)
     if (r < v.nvars) v.rank[v.order[r]] = r;
 }
 
+/* The whole variable ordering in ONE cooperative launch: scores (histogram.hpp:23-41), stable LSD radix sort of
+ * (score, variable) with 8-bit digits, rank[] (lcve.cpp:39 = wolfsort(..., STABLE_LCV): score ascending, ties by variable).
+ * The separate-launch version above costs 12 launches per election for 16 MB of keys - launch latency, not bandwidth.
+ * Block b owns the same contiguous chunk of positions in every pass; per pass: per-block digit histogram | grid barrier |
+ * every block sums the histograms before it (37 888 words in L2) and scatters its chunk in order, 1024 keys at a time,
+ * ranked with __match_any_sync inside a warp and a per-digit prefix over the 32 warps | grid barrier.  The number of
+ * passes comes from the largest score, which the first phase leaves in the scalars (forced_bits != 0: the caller's
+ * width, a test hook for the too-narrow-guess path of the separate-launch version). */
+constexpr int VO_TPB = 1024;
+__global__ void __launch_bounds__(VO_TPB, 1) k_vo_sort(SgView v, uint32_t *tmpk, uint32_t *tmpv, uint32_t *hist, uint32_t forced_bits)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t (*s_cnt)[256] = (uint32_t (*)[256])s_dyn;                 /* [32][256] keys of digit d in warp w of the sub-tile */
+    uint32_t (*s_off)[256] = (uint32_t (*)[256])(s_dyn + 32 * 256);    /* [32][256] where they go */
+    __shared__ uint32_t s_hist[256], s_base[256], s_wsum[8];
+    const uint32_t n = v.nvars, G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t chunk = (((n + G - 1) / G) + VO_TPB - 1) / VO_TPB * VO_TPB;
+    const uint64_t lo64 = (uint64_t)b * chunk;
+    const uint32_t i_lo = lo64 < n ? (uint32_t)lo64 : n, i_hi = (lo64 + chunk < n) ? (uint32_t)(lo64 + chunk) : n;
+    uint32_t *keys = v.scores + 1, *vals = v.order;
+    /* scores, identity order, digit-0 histogram, largest score (four positions per thread in flight) */
+    if (tid < 256) s_hist[tid] = 0;
+    for (uint32_t i = tid; i < 32 * 256; i += VO_TPB) s_dyn[i] = 0;
+    __syncthreads();
+    uint32_t m = 0;
+    const uint2 *occ2 = (const uint2 *)v.occ;                    /* occ[2x], occ[2x + 1] */
+    for (uint32_t i0 = i_lo + tid; i0 < i_hi; i0 += 4 * VO_TPB) {
+        uint2 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + q * VO_TPB; o[q] = i < i_hi ? __ldg(occ2 + i + 1) : make_uint2(0u, 0u); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = i0 + q * VO_TPB;
+            if (i < i_hi) {
+                const uint32_t sc = o[q].x * o[q].y;
+                keys[i] = sc; vals[i] = i + 1;
+                m = sc > m ? sc : m;
+                atomicAdd(&s_hist[sc & 255u], 1u);
+            }
+        }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0 && m) atomicMax(&v.sc->max_score, m);
+    __syncthreads();
+    if (tid < 256) hist[tid * G + b] = s_hist[tid];
+    grid.sync();
+    uint32_t bits = forced_bits;
+    if (!bits) { const uint32_t mx = *(volatile uint32_t *)&v.sc->max_score; bits = 8; while (bits < 32 && (mx >> bits)) bits += 8; }
+    uint32_t *ik = keys, *iv = vals, *ok = tmpk, *ov = tmpv;
+    for (uint32_t shift = 0; shift < bits; shift += 8) {
+        if (shift) {
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (uint32_t i0 = i_lo + tid; i0 < i_hi; i0 += 4 * VO_TPB) {
+                uint32_t k[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + q * VO_TPB; k[q] = i < i_hi ? __ldcg(ik + i) : 0u; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (i0 + q * VO_TPB < i_hi) atomicAdd(&s_hist[(k[q] >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 256) hist[tid * G + b] = s_hist[tid];
+            grid.sync();
+        }
+        /* where this block's keys of digit d start: all keys of smaller digits + the keys of digit d in earlier blocks.
+         * Four threads per digit, each a quarter of the blocks, eight loads in flight */
+        {
+            const uint32_t d = tid & 255u, part = tid >> 8, per = (G + 3) / 4;
+            const uint32_t k0 = part * per, k1 = k0 + per < G ? k0 + per : G;
+            const uint32_t *h = hist + d * G;
+            uint32_t tot = 0, pre = 0;
+            for (uint32_t k = k0; k < k1; k += 8) {
+                uint32_t x[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) x[q] = k + q < k1 ? __ldcg(h + k + q) : 0u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { tot += x[q]; pre += k + q < b ? x[q] : 0u; }
+            }
+            s_off[part][d] = tot; s_off[4 + part][d] = pre;
+        }
+        __syncthreads();
+        uint32_t tot = 0, pre = 0;
+        if (tid < 256) {
+            tot = s_off[0][tid] + s_off[1][tid] + s_off[2][tid] + s_off[3][tid];
+            pre = s_off[4][tid] + s_off[5][tid] + s_off[6][tid] + s_off[7][tid];
+        }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+        if (tid < 256 && lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; ++w) before += s_wsum[w];
+            s_base[tid] = before + incl - tot + pre;
+        }
+        __syncthreads();
+        /* the chunk in order, 1024 keys at a time; the next 1024 are fetched while these are ranked */
+        uint32_t nkey = 0, nval = 0;
+        if (i_lo + tid < i_hi) { nkey = __ldcg(ik + i_lo + tid); nval = __ldcg(iv + i_lo + tid); }
+        for (uint32_t base = i_lo; base < i_hi; base += VO_TPB) {
+            const uint32_t i = base + tid;
+            const bool valid = i < i_hi;
+            const uint32_t key = nkey, val = nval;
+            if (i + VO_TPB < i_hi) { nkey = __ldcg(ik + i + VO_TPB); nval = __ldcg(iv + i + VO_TPB); }
+            const uint32_t d = valid ? ((key >> shift) & 255u) : 256u;
+            const uint32_t mask = __match_any_sync(0xffffffffu, d);
+            const uint32_t before = __popc(mask & ((1u << lane) - 1u));
+            if (valid && before == 0) s_cnt[warp][d] = __popc(mask);
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t run = s_base[tid];
+#pragma unroll 8
+                for (int w = 0; w < 32; ++w) { const uint32_t c = s_cnt[w][tid]; s_off[w][tid] = run; s_cnt[w][tid] = 0; run += c; }
+                s_base[tid] = run;
+            }
+            __syncthreads();
+            if (valid) { const uint32_t o = s_off[warp][d] + before; ok[o] = key; ov[o] = val; }
+            /* the next round's s_off is written after its own barrier, which every reader above has passed by then */
+        }
+        grid.sync();
+        uint32_t *t = ik; ik = ok; ok = t;
+        t = iv; iv = ov; ov = t;
+    }
+    for (uint32_t i0 = i_lo + tid; i0 < i_hi; i0 += 4 * VO_TPB) {
+        uint32_t x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + q * VO_TPB; x[q] = i < i_hi ? __ldcg(iv + i) : 0u; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = i0 + q * VO_TPB;
+            if (i < i_hi) { if (iv != vals) vals[i] = x[q]; v.rank[x[q]] = i; }
+        }
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* election                                                                                         */
 /* ---------------------------------------------------------------------------------------------- */
@@ -994,6 +1132,14 @@ __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_async(SgVie
             f_var = 0;
             if (r < V && r <= brk) { const uint32_t x = v.order[(uint32_t)r]; if (SG_ER_STAT(sg_er_load(v, x)) == SG_E_UNDECIDED) f_var = x; }
             f_mask = __ballot_sync(0xffffffffu, f_var != 0);
+            /* the two occurrence lists of a candidate are neighbours in the table: ask for their lines now (one round trip
+             * for the whole block of candidates), so that the look finds them in L2 */
+            if (f_var) {
+                const uint32_t *dp = v.ot_data + v.ot_off[2 * f_var], *dn = v.ot_data + v.ot_off[2 * f_var + 1];
+                const uint32_t np = v.ot_len[2 * f_var], nn = v.ot_len[2 * f_var + 1];
+                if (np) asm volatile("prefetch.global.L2 [%0];" :: "l"(dp));
+                if (nn) asm volatile("prefetch.global.L2 [%0];" :: "l"(dn + nn - 1));
+            }
             f_base += 32ull * nwarps;
             more = f_base < V && f_base <= brk;
             continue;
@@ -1805,7 +1951,8 @@ void be_scores(void *s, const SgView &v)
 size_t be_sort_tmp_words(uint32_t n)
 {
     const size_t nb = ((size_t)n + RS_TILE - 1) / RS_TILE;
-    return 256 * nb + be_scan_tmp_words((uint32_t)(256 * nb)) + 16;
+    const size_t sep = 256 * nb + be_scan_tmp_words((uint32_t)(256 * nb)) + 16, fused = 256 * 2048;     /* k_vo_sort: 256 x grid */
+    return sep > fused ? sep : fused;
 }
 void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t *tmpk, uint32_t *tmpv, uint32_t *tmp, uint32_t key_bits)
 {
@@ -1826,6 +1973,30 @@ void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t
         be_d2d(s, keys, ik, (size_t)n * 4);
         be_d2d(s, vals, iv, (size_t)n * 4);
     }
+}
+/* scores + sort + rank in one cooperative launch (k_vo_sort); returns nonzero when that is not possible (caller: separate launches).
+ * tmp: 256 x grid words (be_sort_tmp_words covers it). */
+int be_vo_sort(void *s, const SgView &v, uint32_t *tmpk, uint32_t *tmpv, uint32_t *tmp, uint32_t forced_bits)
+{
+    static int ok = -1, sms = 0;
+    const int smem = 2 * 32 * 256 * 4;
+    if (ok < 0) {
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        ok = coop && cudaFuncSetAttribute(k_vo_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vo_sort, VO_TPB, smem) == cudaSuccess && per_sm >= 1;
+        (void)cudaGetLastError();
+    }
+    if (!ok || !v.nvars || sms > 2048) return 1;
+    cudaMemsetAsync(&v.sc->max_score, 0, sizeof(uint32_t), ST(s));
+    SgView vv = v;
+    void *args[] = { (void *)&vv, (void *)&tmpk, (void *)&tmpv, (void *)&tmp, (void *)&forced_bits };
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_vo_sort, dim3((unsigned)sms), dim3(VO_TPB), args, smem, ST(s));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); ok = 0; return 1; }
+    ((BeStream *)s)->launches++;
+    return 0;
 }
 void be_rank(void *s, const SgView &v) { if (v.nvars) LAUNCH(k_rank, blocks_for(v.nvars), TPB, s, v); }
 

@@ -453,14 +453,22 @@ again:
             be_memset(c->stream, c->occ.p, 0, nlit * sizeof(uint32_t));
             be_hist(c->stream, v, c->occ.p);                 /* histCNF (histogram.cpp:84-97) */
         }
-        be_scores(c->stream, v);
-        if (!guessed) {
-            CK(pull_scalars(c));
-            key_bits = 8;                                  /* digit passes that can differ: up to the top bit of the largest score */
-            while (key_bits < 32 && (c->hsc.max_score >> key_bits)) key_bits += 8;
+        /* default: one cooperative launch that takes the key width from the largest score on the device (no guess, no round
+         * trip); SIGMA_VO_FUSED=0 or a forced narrow guess (tests) keep the separate launches and their guess / repeat logic */
+        bool fused = false;
+        { const char *e = getenv("SIGMA_VO_FUSED"); fused = !(e && e[0] == '0'); }
+        if (fused && be_vo_sort(c->stream, v, c->tmpk.p, c->tmpv.p, c->sorttmp.p, force_narrow && guessed ? 8u : 0u) == 0) {
+            if (!(force_narrow && guessed)) { guessed = false; key_bits = 32; }
+        } else {
+            be_scores(c->stream, v);
+            if (!guessed) {
+                CK(pull_scalars(c));
+                key_bits = 8;                              /* digit passes that can differ: up to the top bit of the largest score */
+                while (key_bits < 32 && (c->hsc.max_score >> key_bits)) key_bits += 8;
+            }
+            be_sort_pairs(c->stream, c->scores.p + 1, c->order.p, V, c->tmpk.p, c->tmpv.p, c->sorttmp.p, key_bits);
+            be_rank(c->stream, v);
         }
-        be_sort_pairs(c->stream, c->scores.p + 1, c->order.p, V, c->tmpk.p, c->tmpv.p, c->sorttmp.p, key_bits);
-        be_rank(c->stream, v);
     }
     rounds = 0;
     {
