@@ -212,6 +212,39 @@ typedef struct sigma_cnf_out {
 int  sigma_cnf_out_sizes(sigma_ctx *ctx, sigma_cnf_out *sizes);                       /* after execute */
 int  sigma_download_cnf(sigma_ctx *ctx, sigma_cnf_out *out, sigma_formula *rest);
 
+/* ---- widening #3: the DIMACS parser on the device -------------------------------
+ * Replaces Solver::parser() + makeClause() (reference dimacs.cpp:25-177, dimacs.hpp:57-74) for a whole file held in host
+ * memory (the reference mmaps it, dimacs.cpp:37-39).  The header is read on the host; the clause part is copied to the
+ * device and parsed there (byte-level state machine evaluated by a scan of per-chunk transition functions, integers, clause
+ * boundaries, makeClause's literal checks, parse-time units acting on later clauses, CLAUSE records scan-allocated in file
+ * order - seqfrost_b200/csrc/sigma_dimacs.cuh).  The result is what the reference's solver holds when parser() returns:
+ *   cm / orgs   the CMM arena of CLAUSE records (clause.hpp:47-59; 4 header buckets {_k|_b flags, _sz, _pos = 2, _lbd = 0} +
+ *               literals in file order) and Solver::orgs, word for word
+ *   trail       the root units in the order parser() enqueued them; value[] / state[] as enqueueUnit leaves them
+ *               (solve.hpp:373-398: value[lit] = 1, value[~lit] = 0, state = FROZEN_M)
+ *   counters    formula.{units, binaries, ternaries, large, maxClauseSize}, stats.literals.original
+ * Returns SIGMA_OK, SIGMA_UNSAT (an empty clause: parser() returns false, solve.cpp:52) or SIGMA_E_ARG with
+ * sigma_last_error() naming what the reference would have stopped on (LOGERR: bad header, "expected a digit", "too many
+ * variables", "too many clauses").  Not supported (SIGMA_E_ARG): a second header line, -parseincr.
+ * Watches are not built here: the caller runs rebuildWT() (watch.cpp:135) or goes straight to sigma_upload_cnf. */
+typedef struct sigma_dimacs {
+    /* caller-owned output buffers for sigma_parse_download (ignored by sigma_parse_dimacs) */
+    uint32_t *cm;     uint64_t cm_cap;       /* buckets */
+    uint64_t *orgs;   uint64_t orgs_cap;
+    uint32_t *trail;  uint64_t trail_cap;
+    int8_t   *value;                          /* 2 nvars + 2 bytes, may be NULL */
+    uint8_t  *state;                          /* nvars + 1 bytes, may be NULL */
+    /* filled in by both calls */
+    uint32_t  nvars, header_clauses;          /* inf.orgVars, inf.orgCls */
+    uint64_t  cm_buckets, n_orgs, n_units;
+    uint64_t  binaries, ternaries, large, literals;
+    uint32_t  max_clause_size, unit_rounds;   /* unit_rounds: makeClause rounds needed (1 = no parse-time unit changed anything) */
+    uint64_t  body_offset;                    /* first byte after the header */
+    float     h2d_ms, device_ms;              /* copy of the file / kernels, CUDA events on the context's stream */
+} sigma_dimacs;
+int  sigma_parse_dimacs(sigma_ctx *ctx, const char *text, uint64_t bytes, sigma_dimacs *sizes);
+int  sigma_parse_download(sigma_ctx *ctx, sigma_dimacs *out);
+
 /* pinned host memory for the hand-off buffers (the solver's SCNF arena allocator would call this
  * instead of malloc, malloc.hpp:60-69, so that H2D/D2H run at full PCIe rate) */
 void *sigma_host_alloc(uint64_t bytes);

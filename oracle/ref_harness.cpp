@@ -15,6 +15,8 @@
 //
 //   --incr=seed:permille:nassume   incremental solver (Solver() + iadd/itoClause): isolve()'s prologue, a seeded subset of the variables
 //                   frozen through ifreeze() plus `nassume` assumptions; the .in then carries the `ifrozen` mask
+//   --parseout=<file>  only the reference's DIMACS parser (dimacs.cpp:25-177): CMM arena, orgs, parse-time units (trail), value[],
+//                   state[], header and formula counters, dumped right after parser() returns
 //   --full-timing   also time awaken() (extract), newBeginning()/map(true) and rebuildWT(): the whole simplifying() call
 // usage: ref_sigma <file.cnf> [reference CLI options] [--sgin=..] [--sgout=..] [--trace=..] [--incr=..]
 //
@@ -165,6 +167,33 @@ public:
 			else decide();
 		}
 		return UNSOLVED;
+	}
+
+	// --parseout: the reference's own DIMACS parser (dimacs.cpp:25-177) on `path`, through the library constructor so that the
+	// dump is taken right after parser() returns - before the BCP() the file constructor (solve.cpp:52) runs next.
+	int parseOnly(const std::string& path, const std::string& outp) {
+		formula = FORMULA(path);
+		const bool ok = parser();
+		Writer w;
+		if (!w.open(outp)) return 5;
+		uint64_t meta[16] = { 0 };
+		meta[0] = ok ? 1 : 0;
+		meta[1] = inf.orgVars; meta[2] = inf.orgCls; meta[3] = inf.maxVar;
+		meta[4] = formula.units; meta[5] = formula.binaries; meta[6] = formula.ternaries; meta[7] = formula.large;
+		meta[8] = (uint64_t)formula.maxClauseSize; meta[9] = stats.literals.original; meta[10] = stats.clauses.original;
+		meta[11] = trail.size(); meta[12] = inf.unassigned; meta[13] = inf.maxFrozen;
+		w.section("meta", meta, sizeof meta);
+		if (ok) {
+			w.section("cm", cm.address(0), uint64_t(cm.size()) * sizeof(uint32));
+			w.section("orgs", orgs.data(), uint64_t(orgs.size()) * sizeof(C_REF));
+			w.section("trail", trail.data(), uint64_t(trail.size()) * sizeof(uint32));
+			w.section("value", sp->value, uint64_t(inf.nDualVars));
+			std::vector<uint8_t> st(inf.maxVar + 1);
+			for (uint32 v = 0; v <= inf.maxVar; ++v) st[v] = sp->state[v].state;
+			w.section("state", st.data(), st.size());
+		}
+		w.close();
+		return 0;
 	}
 
 	void dumpClauseDb(Writer& w) {
@@ -335,7 +364,7 @@ int main(int argc, char** argv)
 	INT_OPT opt_timeout("timeout", "set out-of-time limit in seconds", 0, INT32R(0, INT32_MAX));
 	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
-	std::string sgin, sgout, tracep, cmin, cmout, incr;
+	std::string sgin, sgout, tracep, cmin, cmout, incr, parseout;
 	long long presolve_conflicts = 0;
 	bool fulltiming = false;
 	std::vector<char*> pass;
@@ -347,6 +376,7 @@ int main(int argc, char** argv)
 		else if (a.rfind("--cmin=", 0) == 0) cmin = a.substr(7);
 		else if (a.rfind("--cmout=", 0) == 0) cmout = a.substr(8);
 		else if (a.rfind("--incr=", 0) == 0) incr = a.substr(7);
+		else if (a.rfind("--parseout=", 0) == 0) parseout = a.substr(11);
 		else if (a == "--full-timing") fulltiming = true;
 		else if (a.rfind("--presolve-conflicts=", 0) == 0) presolve_conflicts = atoll(a.substr(21).c_str());
 		else pass.push_back(argv[i]);
@@ -362,6 +392,14 @@ int main(int argc, char** argv)
 		else if (!verbose || competition_en) quiet_en = true;
 		std::string formula = argv[1];
 		Probe* p = nullptr;
+		if (!parseout.empty()) {
+			p = new Probe();
+			solver = p;
+			g_out_written = true;
+			const int prc = p->parseOnly(formula, parseout);
+			fflush(stdout);
+			_exit(prc);
+		}
 		if (incr.empty()) p = new Probe(formula);
 		else {
 			p = new Probe();

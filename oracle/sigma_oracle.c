@@ -1517,3 +1517,104 @@ int sgo_snapshot(sgo_ctx *c, const char *name, void *dst, uint64_t cap, uint64_t
     if (n) memcpy(dst, src, n);
     return SIGMA_OK;
 }
+
+
+/* ---- the DIMACS parser (dimacs.cpp:25-177, dimacs.hpp:57-74), sequential restatement ------------------------------------
+ * One walk over the text, statement by statement, exactly as parser() does: eatWS; end marker; comment line; header;
+ * otherwise makeClause (literal marks, tautologies, root values of the units enqueued so far, unit / clause / dropped).
+ * Output into caller buffers as the reference's solver holds it when parser() returns (include/sigma_b200.h, sigma_dimacs).
+ * Returns SIGMA_OK, SIGMA_UNSAT (empty clause), SIGMA_E_ARG (anything the reference stops on with LOGERR), SIGMA_E_NOSPACE. */
+static int sgo_is_ws(char ch) { return (ch >= 9 && ch <= 13) || ch == 32; }
+int sgo_parse_dimacs(const char *t, uint64_t n, sigma_dimacs *out)
+{
+    uint64_t i = 0;
+    uint32_t nvars = 0, ncls = 0;
+    int have_header = 0;
+    int8_t *marks = NULL;                 /* l2marker: -1 unmarked, else the sign (dimacs.cpp:133-139) */
+    int8_t *value = NULL;
+    uint32_t *lits = NULL, *org = NULL;
+    uint64_t cap = 0, pos = 0, norgs = 0, nunits = 0;
+    int rc = SIGMA_OK;
+    out->cm_buckets = out->n_orgs = out->n_units = out->binaries = out->ternaries = out->large = out->literals = 0;
+    out->max_clause_size = 0; out->nvars = out->header_clauses = 0;
+#define SGO_FAIL(code) do { rc = (code); goto done; } while (0)
+    while (i < n) {
+        while (i < n && sgo_is_ws(t[i])) ++i;
+        if (i >= n || t[i] == 0 || t[i] == '%') break;                       /* dimacs.cpp:54 */
+        if (t[i] == 'c') { while (i < n && t[i] && t[i++] != '\n') { } continue; }
+        if (t[i] == 'p') {
+            if (have_header) SGO_FAIL(SIGMA_E_ARG);
+            if (n - i < 5 || memcmp(t + i, "p cnf", 5) != 0) SGO_FAIL(SIGMA_E_ARG);
+            i += 5;
+            for (int k = 0; k < 2; ++k) {
+                while (i < n && sgo_is_ws(t[i])) ++i;
+                int sign = 0;
+                if (i < n && t[i] == '-') { sign = 1; ++i; } else if (i < n && t[i] == '+') ++i;
+                if (i >= n || t[i] < '0' || t[i] > '9') SGO_FAIL(SIGMA_E_ARG);
+                uint32_t x = 0;
+                while (i < n && t[i] >= '0' && t[i] <= '9') x = x * 10u + (uint32_t)(t[i++] - '0');
+                if (sign || x == 0) SGO_FAIL(SIGMA_E_ARG);
+                if (k == 0) nvars = x; else ncls = x;
+            }
+            if (nvars >= 0x7FFFFFFEu) SGO_FAIL(SIGMA_E_ARG);
+            have_header = 1;
+            marks = (int8_t *)malloc(nvars + 1); value = (int8_t *)malloc(2 * (size_t)nvars + 2);
+            memset(marks, -1, nvars + 1); memset(value, -1, 2 * (size_t)nvars + 2);
+            if (out->state) memset(out->state, 0, nvars + 1);
+            out->nvars = nvars; out->header_clauses = ncls;
+            continue;
+        }
+        if (!have_header) SGO_FAIL(SIGMA_E_ARG);                               /* makeClause: "too many variables" with maxVar == 0 */
+        /* makeClause (dimacs.cpp:121-177) */
+        uint64_t nc = 0, no = 0;
+        int satisfied = 0;
+        while (1) {
+            while (i < n && sgo_is_ws(t[i])) ++i;
+            uint32_t sign = 0;
+            if (i < n && t[i] == '-') { sign = 1; ++i; } else if (i < n && t[i] == '+') ++i;
+            if (i >= n || t[i] < '0' || t[i] > '9') SGO_FAIL(SIGMA_E_ARG);       /* "expected a digit" */
+            uint32_t v = 0;
+            while (i < n && t[i] >= '0' && t[i] <= '9') v = v * 10u + (uint32_t)(t[i++] - '0');
+            if (!v) break;
+            if (v > nvars) SGO_FAIL(SIGMA_E_ARG);                                 /* "too many variables" */
+            if (no + 1 > cap) { cap = cap ? 2 * cap : 64; lits = (uint32_t *)realloc(lits, cap * 4); org = (uint32_t *)realloc(org, cap * 4); }
+            const uint32_t lit = 2u * v + sign;
+            org[no++] = lit;
+            if (marks[v] < 0) {
+                marks[v] = (int8_t)sign;
+                if (value[lit] < 0) lits[nc++] = lit;
+                else if (value[lit]) satisfied = 1;
+            } else if (marks[v] != (int8_t)sign) satisfied = 1;                   /* tautology */
+        }
+        for (uint64_t k = 0; k < no; ++k) marks[org[k] >> 1] = -1;
+        if (satisfied) continue;
+        if (!no) SGO_FAIL(SIGMA_UNSAT);                                           /* parser() returns false */
+        if (nc == 1) {
+            const uint32_t unit = lits[0];
+            if (nunits + 1 > out->trail_cap) SGO_FAIL(SIGMA_E_NOSPACE);
+            out->trail[nunits++] = unit;                                          /* enqueueUnit, solve.hpp:373-398 */
+            value[unit] = 1; value[unit ^ 1u] = 0;
+            if (out->state) out->state[unit >> 1] = 2;                            /* FROZEN_M */
+        } else if (norgs + 1 > ncls) SGO_FAIL(SIGMA_E_ARG);                        /* "too many clauses" (also for a clause left empty) */
+        else if (nc) {
+            if (nc == 2) out->binaries++; else if (nc == 3) out->ternaries++; else out->large++;
+            if (nc > out->max_clause_size) out->max_clause_size = (uint32_t)nc;
+            if (pos + 4 + nc > out->cm_cap || norgs + 1 > out->orgs_cap) SGO_FAIL(SIGMA_E_NOSPACE);
+            uint32_t *dst = out->cm + pos;                                        /* CLAUSE(const Lits_t&), clause.hpp:91-106 */
+            dst[0] = (1u << 4) | (nc == 2 ? 1u << 5 : 0u); dst[1] = (uint32_t)nc; dst[2] = 2u; dst[3] = 0u;
+            for (uint64_t k = 0; k < nc; ++k) dst[4 + k] = lits[k];
+            out->orgs[norgs++] = pos;
+            pos += 4 + nc;
+            out->literals += nc;
+        }
+    }
+    if (!have_header) rc = SIGMA_E_ARG;
+done:
+    if (rc == SIGMA_OK) {
+        out->cm_buckets = pos; out->n_orgs = norgs; out->n_units = nunits;
+        if (out->value && value) memcpy(out->value, value, 2 * (size_t)nvars + 2);
+    }
+    free(marks); free(value); free(lits); free(org);
+    return rc;
+#undef SGO_FAIL
+}

@@ -36,6 +36,8 @@ uint64_t sgo_extract(const sigma_cnf *cnf, uint32_t *arena, uint64_t *refs, uint
 /* newBeginning() without variable mapping (simplify.cpp:249-268, sclause.cpp:22-62) from a compacted SCNF */
 void sgo_new_beginning(const uint32_t *arena, const uint64_t *refs, uint64_t n_clauses, int lbd_tier1, int later_call,
                        sigma_cnf_out *out);
+/* Solver::parser() + makeClause() (dimacs.cpp:25-177) over a file image; output buffers and counters as sigma_parse_download */
+int  sgo_parse_dimacs(const char *text, uint64_t bytes, sigma_dimacs *out);
 #ifdef __cplusplus
 }
 #endif

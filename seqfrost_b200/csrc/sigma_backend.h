@@ -178,6 +178,23 @@ void be_compact_apply(void *s, const SgView &v, const uint32_t *tmp, sg_u4 *hdr2
 /* device store -> AoS SCNF arena + refs in the reference's layout */
 void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *arena, uint64_t *refs);
 
+/* ---- DIMACS parser (dimacs.cpp:25-177; method and per-item bodies in sigma_dimacs.cuh) ------------------------------ */
+/* start state of every 64-byte chunk of text[0, n) (the clause part of the file, after the header) + the state at the end */
+void be_dm_chunk_states(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, uint32_t *fn, uint32_t *tilefn, uint32_t *tstate, uint32_t *cstate,
+                        uint32_t *final_state);
+/* emit = 0: integers / terminators that start in each chunk (ntok, nterm); *bad = 2 on a byte the reference rejects.
+ * emit = 1: tok[] (0 = terminator, else 2 var + sign) and term[] (token index of every terminator); *bad = 3: variable > nvars */
+void be_dm_tokens(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, const uint32_t *cstate, uint32_t nvars, int emit, uint32_t *ntok,
+                  uint32_t *nterm, const uint32_t *tokoff, const uint32_t *termoff, uint32_t *tok, uint32_t *term, uint32_t *bad);
+/* one round of makeClause for all clauses: csize, units into utime_new (atomic min of the clause index), *unsat = first empty clause */
+void be_dm_clauses(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, uint32_t *utime_new, uint32_t *csize, uint32_t *unsat);
+void be_dm_diff(void *s, const uint32_t *a, const uint32_t *b, uint32_t n, uint32_t *changed);
+void be_dm_sizes(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, const uint32_t *csize, uint32_t *words,
+                 uint32_t *kept, uint32_t *isunit);
+void be_dm_write(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, const uint32_t *csize, const uint32_t *wordoff,
+                 const uint32_t *keptoff, const uint32_t *unitoff, const uint32_t *isunit, uint32_t *cm, unsigned long long *orgs, uint32_t *trail,
+                 int8_t *value, uint8_t *state, unsigned long long *stats, uint32_t header_clauses, uint32_t *bad /* 4: too many clauses */);
+
 #ifdef __cplusplus
 }
 #endif

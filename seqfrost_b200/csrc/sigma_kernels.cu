@@ -14,6 +14,7 @@
 
 #include "sigma_backend.h"
 #include "sigma_items.cuh"
+#include "sigma_dimacs.cuh"
 
 namespace {
 
@@ -1698,6 +1699,156 @@ __global__ void k_ot_compare(SgView v, const uint32_t *__restrict__ off2, const 
     if (bad) atomicAdd(mismatch, 1u);
 }
 
+/* ---------------------------------------------------------------------------------------------- */
+/* DIMACS parser (dimacs.cpp:25-177) - bodies and the method in sigma_dimacs.cuh                     */
+/* ---------------------------------------------------------------------------------------------- */
+/* inclusive scan over the block (256 threads) of transition functions under composition, in thread order */
+__device__ __forceinline__ uint32_t dm_block_scan_fn(uint32_t f, uint32_t *s_w /* 8 */, uint32_t *total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t g = __shfl_up_sync(0xffffffffu, f, d); if (lane >= (uint32_t)d) f = sgd_compose(g, f); }
+    if (lane == 31) s_w[warp] = f;
+    __syncthreads();
+    uint32_t pre = SGD_IDENT;
+    for (uint32_t w = 0; w < warp; ++w) pre = sgd_compose(pre, s_w[w]);
+    f = sgd_compose(pre, f);
+    if (total) { uint32_t t = SGD_IDENT; for (uint32_t w = 0; w < TPB / 32; ++w) t = sgd_compose(t, s_w[w]); *total = t; }
+    __syncthreads();
+    return f;
+}
+__global__ void __launch_bounds__(TPB) k_dm_fns(const uint8_t *__restrict__ text, uint64_t n, uint32_t nchunks, uint32_t *__restrict__ fn,
+                                                uint32_t *__restrict__ tilefn)
+{
+    __shared__ uint32_t s_w[TPB / 32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t f = SGD_IDENT;
+    if (i < nchunks) {
+        const uint64_t lo = (uint64_t)i * SGD_CHUNK, hi = lo + SGD_CHUNK < n ? lo + SGD_CHUNK : n;
+        f = sgd_chunk_fn(text, lo, hi);
+        fn[i] = f;
+    }
+    uint32_t tot;
+    (void)dm_block_scan_fn(f, s_w, &tot);
+    if (threadIdx.x == 0) tilefn[blockIdx.x] = tot;
+}
+/* one block: start state of every tile (exclusive scan of the tile functions applied to B); tiles in chunks of 256 */
+__global__ void __launch_bounds__(TPB) k_dm_tile_states(const uint32_t *__restrict__ tilefn, uint32_t ntiles, uint32_t *__restrict__ tstate,
+                                                        uint32_t *__restrict__ final_state)
+{
+    __shared__ uint32_t s_w[TPB / 32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = SGD_IDENT;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += TPB) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t f = i < ntiles ? tilefn[i] : SGD_IDENT;
+        uint32_t tot;
+        const uint32_t incl = dm_block_scan_fn(f, s_w, &tot);
+        const uint32_t carry = s_carry;
+        /* exclusive prefix = carry . (inclusive of the previous thread) */
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        __shared__ uint32_t s_last[TPB / 32];
+        if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t excl = (threadIdx.x & 31) ? prev : (threadIdx.x ? s_last[(threadIdx.x >> 5) - 1] : SGD_IDENT);
+        if (i < ntiles) tstate[i] = sgd_apply(sgd_compose(carry, excl), SGD_B);
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = sgd_compose(carry, tot);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *final_state = sgd_apply(s_carry, SGD_B);
+}
+__global__ void __launch_bounds__(TPB) k_dm_chunk_states(const uint32_t *__restrict__ fn, uint32_t nchunks, const uint32_t *__restrict__ tstate,
+                                                         uint32_t *__restrict__ cstate)
+{
+    __shared__ uint32_t s_w[TPB / 32];
+    __shared__ uint32_t s_last[TPB / 32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t f = i < nchunks ? fn[i] : SGD_IDENT;
+    const uint32_t incl = dm_block_scan_fn(f, s_w, nullptr);
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    const uint32_t excl = (threadIdx.x & 31) ? prev : (threadIdx.x ? s_last[(threadIdx.x >> 5) - 1] : SGD_IDENT);
+    if (i < nchunks) cstate[i] = sgd_apply(excl, tstate[blockIdx.x]);
+}
+__global__ void __launch_bounds__(TPB) k_dm_tokens(const uint8_t *__restrict__ text, uint64_t n, uint32_t nchunks, const uint32_t *__restrict__ cstate,
+                                                   uint32_t nvars, int emit, uint32_t *ntok, uint32_t *nterm, const uint32_t *__restrict__ tokoff,
+                                                   const uint32_t *__restrict__ termoff, uint32_t *__restrict__ tok, uint32_t *__restrict__ term, uint32_t *bad)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nchunks) return;
+    const uint64_t lo = (uint64_t)i * SGD_CHUNK, hi = lo + SGD_CHUNK < n ? lo + SGD_CHUNK : n;
+    uint32_t a, b;
+    const uint32_t end = sgd_chunk_tokens(text, lo, hi, n, cstate[i], nvars, emit != 0, &a, &b, emit ? tokoff[i] : 0u, emit ? termoff[i] : 0u, tok, term, bad);
+    if (!emit) { ntok[i] = a; nterm[i] = b; if (end == SGD_ERR) *bad = 2; }
+}
+/* one round of makeClause over all clauses from the units of the previous round; csize = literals left (0: dropped) */
+__global__ void __launch_bounds__(TPB) k_dm_clauses(const uint32_t *__restrict__ tok, const uint32_t *__restrict__ term, uint32_t ncl,
+                                                    const uint32_t *__restrict__ utime, uint32_t *__restrict__ utime_new, uint32_t *__restrict__ csize,
+                                                    uint32_t *unsat)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncl) return;
+    const uint32_t first = c ? term[c - 1] + 1 : 0u, last = term[c];
+    uint32_t kind;
+    const uint32_t n = sgd_make_clause(tok, first, last, c, utime, nullptr, &kind);
+    /* 0xFFFFFFFF: every literal false, nothing satisfied - dropped, but it still runs into the "too many clauses" check */
+    csize[c] = kind == 3 ? 0u : (kind == 0 && n == 0 && !sgd_satisfied_or_empty(tok, first, last, c, utime)) ? 0xFFFFFFFFu : n;
+    if (kind == 3) atomicMin(unsat, c);
+    if (kind == 1) atomicMin(&utime_new[sgd_unit_literal(tok, first, last, c, utime)], c);
+}
+__global__ void k_dm_diff(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t n, uint32_t *changed)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) *changed = 1;
+}
+/* per clause: words of its CLAUSE record (0: no record), 1 if it is kept, 1 if it is the unit that enqueues its literal */
+__global__ void k_dm_sizes(const uint32_t *__restrict__ tok, const uint32_t *__restrict__ term, uint32_t ncl, const uint32_t *__restrict__ utime,
+                           const uint32_t *__restrict__ csize, uint32_t *__restrict__ words, uint32_t *__restrict__ kept, uint32_t *__restrict__ isunit)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncl) return;
+    const uint32_t n = csize[c] == 0xFFFFFFFFu ? 0u : csize[c];
+    words[c] = n >= 2 ? n + 4u : 0u;
+    kept[c] = n >= 2;
+    uint32_t u = 0;
+    if (n == 1) {
+        const uint32_t first = c ? term[c - 1] + 1 : 0u;
+        u = utime[sgd_unit_literal(tok, first, term[c], c, utime)] == c;      /* the first clause that made it true enqueues it */
+    }
+    isunit[c] = u;
+}
+__global__ void k_dm_write(const uint32_t *__restrict__ tok, const uint32_t *__restrict__ term, uint32_t ncl, const uint32_t *__restrict__ utime,
+                           const uint32_t *__restrict__ csize, const uint32_t *__restrict__ wordoff, const uint32_t *__restrict__ keptoff,
+                           const uint32_t *__restrict__ unitoff, const uint32_t *__restrict__ isunit, uint32_t *__restrict__ cm,
+                           unsigned long long *__restrict__ orgs, uint32_t *__restrict__ trail, int8_t *__restrict__ value, uint8_t *__restrict__ state,
+                           unsigned long long *__restrict__ stats /* binaries, ternaries, large, literals, max size */, uint32_t header_clauses,
+                           uint32_t *bad)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncl) return;
+    if (csize[c] == 0xFFFFFFFFu) { if (keptoff[c] + 1 > header_clauses) *bad = 4; return; }     /* dimacs.cpp:160 */
+    const uint32_t n = csize[c];
+    const uint32_t first = c ? term[c - 1] + 1 : 0u, last = term[c];
+    if (n >= 2) {
+        uint32_t *dst = cm + wordoff[c];
+        uint32_t kind;
+        dst[0] = (1u << 4) | (n == 2 ? 1u << 5 : 0u); dst[1] = n; dst[2] = 2u; dst[3] = 0u;
+        (void)sgd_make_clause(tok, first, last, c, utime, dst + 4, &kind);
+        orgs[keptoff[c]] = wordoff[c];
+        atomicAdd(&stats[n == 2 ? 0 : n == 3 ? 1 : 2], 1ull);
+        atomicAdd(&stats[3], (unsigned long long)n);
+        atomicMax(&stats[4], (unsigned long long)n);
+    } else if (n == 1 && isunit[c]) {
+        const uint32_t lit = sgd_unit_literal(tok, first, last, c, utime);
+        trail[unitoff[c]] = lit;
+        value[lit] = 1; value[lit ^ 1u] = 0;                  /* enqueueUnit, solve.hpp:373-398 */
+        state[lit >> 1] = (uint8_t)SG_FROZEN_M;
+    }
+}
+
 } // namespace
 
 /* ================================================================================================ */
@@ -2187,4 +2338,36 @@ void be_ot_compare(void *s, const SgView &v, const uint32_t *off2, const uint32_
 {
     LAUNCH(k_zero_u32, 1, 1, s, mismatch);
     LAUNCH(k_ot_compare, blocks_for(v.nlit), TPB, s, v, off2, len2, data2, mismatch);
+}
+
+/* ---- DIMACS parser launches (sigma_backend.h) ------------------------------------------------------- */
+void be_dm_chunk_states(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, uint32_t *fn, uint32_t *tilefn, uint32_t *tstate, uint32_t *cstate,
+                        uint32_t *final_state)
+{
+    const uint32_t ntiles = blocks_for(nchunks);
+    LAUNCH(k_dm_fns, ntiles, TPB, s, text, n, nchunks, fn, tilefn);
+    LAUNCH(k_dm_tile_states, 1, TPB, s, tilefn, ntiles, tstate, final_state);
+    LAUNCH(k_dm_chunk_states, ntiles, TPB, s, fn, nchunks, tstate, cstate);
+}
+void be_dm_tokens(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, const uint32_t *cstate, uint32_t nvars, int emit, uint32_t *ntok,
+                  uint32_t *nterm, const uint32_t *tokoff, const uint32_t *termoff, uint32_t *tok, uint32_t *term, uint32_t *bad)
+{
+    LAUNCH(k_dm_tokens, blocks_for(nchunks), TPB, s, text, n, nchunks, cstate, nvars, emit, ntok, nterm, tokoff, termoff, tok, term, bad);
+}
+void be_dm_clauses(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, uint32_t *utime_new, uint32_t *csize, uint32_t *unsat)
+{
+    if (ncl) LAUNCH(k_dm_clauses, blocks_for(ncl), TPB, s, tok, term, ncl, utime, utime_new, csize, unsat);
+}
+void be_dm_diff(void *s, const uint32_t *a, const uint32_t *b, uint32_t n, uint32_t *changed) { if (n) LAUNCH(k_dm_diff, blocks_for(n), TPB, s, a, b, n, changed); }
+void be_dm_sizes(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, const uint32_t *csize, uint32_t *words,
+                 uint32_t *kept, uint32_t *isunit)
+{
+    if (ncl) LAUNCH(k_dm_sizes, blocks_for(ncl), TPB, s, tok, term, ncl, utime, csize, words, kept, isunit);
+}
+void be_dm_write(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, const uint32_t *csize, const uint32_t *wordoff,
+                 const uint32_t *keptoff, const uint32_t *unitoff, const uint32_t *isunit, uint32_t *cm, unsigned long long *orgs, uint32_t *trail,
+                 int8_t *value, uint8_t *state, unsigned long long *stats, uint32_t header_clauses, uint32_t *bad)
+{
+    if (ncl) LAUNCH(k_dm_write, blocks_for(ncl), TPB, s, tok, term, ncl, utime, csize, wordoff, keptoff, unitoff, isunit, cm, orgs, trail, value, state, stats,
+                    header_clauses, bad);
 }

@@ -7,6 +7,7 @@
  */
 #include "../../include/sigma_b200.h"
 #include "sigma_backend.h"
+#include "sigma_dimacs.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -82,6 +83,12 @@ struct sigma_ctx {
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
     DBuf<uint32_t> arena_out; DBuf<uint64_t> refs_out;
     DBuf<uint32_t> cm_out; DBuf<uint64_t> orgs_out, learnts_out; DBuf<uint8_t> subsume_out;   /* sigma_download_cnf */
+    /* sigma_parse_dimacs: the clause part of the file, its tokens, and the parsed clause database (all on the device) */
+    DBuf<uint8_t> dm_text, dm_state; DBuf<int8_t> dm_value;
+    DBuf<uint32_t> dm_fn, dm_tilefn, dm_tstate, dm_cstate, dm_ntok, dm_nterm, dm_tokoff, dm_termoff, dm_tok, dm_term;
+    DBuf<uint32_t> dm_utime, dm_utime2, dm_csize, dm_words, dm_kept, dm_isunit, dm_wordoff, dm_keptoff, dm_unitoff, dm_cm, dm_trail;
+    DBuf<uint64_t> dm_orgs, dm_stats;
+    bool dm_parsed = false; sigma_dimacs dm_out;
     bool cm_built = false; uint32_t cm_learnts = 0; uint64_t cm_lits_org = 0, cm_lits_learnt = 0, cm_last_ref = 0;
     SgScalars hsc;                  /* host mirror */
     uint32_t *h_totals = nullptr;   /* pinned */
@@ -1344,6 +1351,194 @@ int sigma_snapshot(sigma_ctx *c, const char *name, void *dst, uint64_t cap_bytes
     if (!dst || cap_bytes < n) return SIGMA_E_NOSPACE;
     if (n) be_d2h(c->stream, dst, src, n);
     if (ctx_sync(c)) return SIGMA_E_CUDA;
+    return SIGMA_OK;
+}
+
+} /* extern "C" */
+
+/* ---- DIMACS parser on the device (dimacs.cpp:25-177; method in sigma_dimacs.cuh) ------------------- */
+namespace {
+
+/* the part of parser() in front of the clauses, on the host: comments, then "p cnf <vars> <clauses>" (dimacs.cpp:52-86,
+ * dimacs.hpp:57-74).  Returns the offset of the first byte after the header, or 0 with *why set. */
+uint64_t dimacs_header(const char *t, uint64_t n, uint32_t *nvars, uint32_t *ncls, const char **why)
+{
+    uint64_t i = 0;
+    auto ws = [&]() { while (i < n && ((t[i] >= 9 && t[i] <= 13) || t[i] == 32)) ++i; };
+    auto integer = [&](uint32_t *v, uint32_t *sign) -> bool {
+        ws();
+        *sign = 0;
+        if (i < n && t[i] == '-') { *sign = 1; ++i; }
+        else if (i < n && t[i] == '+') ++i;
+        if (i >= n || t[i] < '0' || t[i] > '9') return false;
+        uint32_t x = 0;
+        while (i < n && t[i] >= '0' && t[i] <= '9') x = x * 10u + (uint32_t)(t[i++] - '0');
+        *v = x;
+        return true;
+    };
+    while (true) {
+        ws();
+        if (i >= n || t[i] == 0 || t[i] == '%') { *why = "no header before the end of the file"; return 0; }
+        if (t[i] == 'c') { while (i < n && t[i] && t[i++] != '\n') { } continue; }
+        if (t[i] != 'p') { *why = "a clause before the header (the reference stops with 'too many variables')"; return 0; }
+        if (n - i < 5 || memcmp(t + i, "p cnf", 5) != 0) { *why = "header has wrong format"; return 0; }
+        i += 5;
+        uint32_t sign = 0;
+        if (!integer(nvars, &sign)) { *why = "expected a digit in the header"; return 0; }
+        if (sign) { *why = "number of variables in header is negative"; return 0; }
+        if (*nvars == 0) { *why = "zero number of variables in header"; return 0; }
+        if (*nvars >= 0x7FFFFFFEu) { *why = "number of variables not supported"; return 0; }
+        if (!integer(ncls, &sign)) { *why = "expected a digit in the header"; return 0; }
+        if (sign) { *why = "number of clauses in header is negative"; return 0; }
+        if (*ncls == 0) { *why = "zero number of clauses in header"; return 0; }
+        return i;
+    }
+}
+
+int parse_dimacs_impl(sigma_ctx *c, const char *text, uint64_t bytes, sigma_dimacs *out)
+{
+    if (!c || !text || !out) return SIGMA_E_ARG;
+    if (!c->stream) return fail(c, SIGMA_E_CUDA, c->err[0] ? c->err : "no CUDA device");
+    be_bind(c->device);
+    c->dm_parsed = false;
+    sigma_dimacs &r = c->dm_out;
+    memset(&r, 0, sizeof r);
+    const char *why = nullptr;
+    const uint64_t body = dimacs_header(text, bytes, &r.nvars, &r.header_clauses, &why);
+    if (!body) return fail(c, SIGMA_E_ARG, why);
+    const uint64_t n = bytes - body;
+    if (n >= 0xFFFFFFFFull * SGD_CHUNK / 2) return fail(c, SIGMA_E_UNSUPPORTED, "file too large for 32-bit token indices");
+    const uint32_t V = r.nvars, nlit = 2 * V + 2;
+    const uint32_t nchunks = (uint32_t)((n + SGD_CHUNK - 1) / SGD_CHUNK), ntiles = (nchunks + 255) / 256;
+    NOMEM(c->dm_text.ensure(n + 64)); NOMEM(c->dm_fn.ensure(nchunks + 16)); NOMEM(c->dm_tilefn.ensure(ntiles + 16)); NOMEM(c->dm_tstate.ensure(ntiles + 16));
+    NOMEM(c->dm_cstate.ensure(nchunks + 16)); NOMEM(c->dm_ntok.ensure(nchunks + 16)); NOMEM(c->dm_nterm.ensure(nchunks + 16));
+    NOMEM(c->dm_tokoff.ensure(nchunks + 16)); NOMEM(c->dm_termoff.ensure(nchunks + 16));
+    NOMEM(c->scantmp.ensure(2 * be_scan_tmp_words(nchunks > 64 ? nchunks : 64) + 64));
+    NOMEM(c->dm_utime.ensure(nlit)); NOMEM(c->dm_utime2.ensure(nlit)); NOMEM(c->dm_value.ensure(nlit)); NOMEM(c->dm_state.ensure(V + 1));
+    NOMEM(c->dm_stats.ensure(8));
+    void *e0 = get_event(c), *e1 = get_event(c), *e2 = get_event(c);
+    be_event_record(c->stream, e0);
+    if (n) be_h2d(c->stream, c->dm_text.p, text + body, n);
+    be_event_record(c->stream, e1);
+    for (int k = 0; k < 8; ++k) c->h_totals[k] = 0;
+    c->h_totals[4] = 0xFFFFFFFFu;                          /* first empty clause */
+    be_copy_words(c->stream, c->totals.p, c->h_totals, 8 * sizeof(uint32_t));
+    /* totals: 0 tokens, 1 terminators, 2 final state, 3 bad, 4 first empty clause, 5 changed */
+    uint32_t ntok = 0, ncl = 0;
+    if (nchunks) {
+        be_dm_chunk_states(c->stream, c->dm_text.p, n, nchunks, c->dm_fn.p, c->dm_tilefn.p, c->dm_tstate.p, c->dm_cstate.p, c->totals.p + 2);
+        be_dm_tokens(c->stream, c->dm_text.p, n, nchunks, c->dm_cstate.p, V, 0, c->dm_ntok.p, c->dm_nterm.p, nullptr, nullptr, nullptr, nullptr, c->totals.p + 3);
+        SgScanSet ss = { { c->dm_ntok.p, c->dm_nterm.p, nullptr, nullptr }, { c->dm_tokoff.p, c->dm_termoff.p, nullptr, nullptr },
+                         { c->totals.p, c->totals.p + 1, nullptr, nullptr } };
+        be_scan_multi(c->stream, ss, 2, nchunks, c->scantmp.p);
+        CK(pull_totals(c, 8));
+        ntok = c->h_totals[0]; ncl = c->h_totals[1];
+        const uint32_t fin = c->h_totals[2];
+        if (c->h_totals[3] == 2 || fin == SGD_ERR) return fail(c, SIGMA_E_ARG, "expected a digit (a character the reference's parser rejects, or a comment inside a clause)");
+        if (fin == SGD_K || fin == SGD_TN || fin == SGD_SGN) return fail(c, SIGMA_E_ARG, "the last clause is not terminated by 0");
+    }
+    r.device_ms = 0;
+    if (ncl) {
+        NOMEM(c->dm_tok.ensure((size_t)ntok + 16)); NOMEM(c->dm_term.ensure((size_t)ncl + 16));
+        NOMEM(c->dm_csize.ensure((size_t)ncl + 16)); NOMEM(c->dm_words.ensure((size_t)ncl + 16)); NOMEM(c->dm_kept.ensure((size_t)ncl + 16));
+        NOMEM(c->dm_isunit.ensure((size_t)ncl + 16)); NOMEM(c->dm_wordoff.ensure((size_t)ncl + 16)); NOMEM(c->dm_keptoff.ensure((size_t)ncl + 16));
+        NOMEM(c->dm_unitoff.ensure((size_t)ncl + 16));
+        NOMEM(c->scantmp.ensure(3 * be_scan_tmp_words(ncl) + 64));
+        be_dm_tokens(c->stream, c->dm_text.p, n, nchunks, c->dm_cstate.p, V, 1, nullptr, nullptr, c->dm_tokoff.p, c->dm_termoff.p, c->dm_tok.p, c->dm_term.p,
+                     c->totals.p + 3);
+        /* makeClause rounds: units found while parsing act on the clauses after them (sigma_dimacs.cuh) */
+        be_memset(c->stream, c->dm_utime.p, 0xFF, (size_t)nlit * 4);
+        uint32_t rounds = 0;
+        while (true) {
+            be_memset(c->stream, c->dm_utime2.p, 0xFF, (size_t)nlit * 4);
+            be_dm_clauses(c->stream, c->dm_tok.p, c->dm_term.p, ncl, c->dm_utime.p, c->dm_utime2.p, c->dm_csize.p, c->totals.p + 4);
+            c->h_totals[5] = 0;
+            be_copy_words(c->stream, c->totals.p + 5, c->h_totals + 5, 4);
+            be_dm_diff(c->stream, c->dm_utime.p, c->dm_utime2.p, nlit, c->totals.p + 5);
+            CK(pull_totals(c, 8));
+            ++rounds;
+            if (c->h_totals[3] == 3) return fail(c, SIGMA_E_ARG, "too many variables (a literal beyond the header's variable count)");
+            if (!c->h_totals[5]) break;
+            DBuf<uint32_t> t = c->dm_utime; c->dm_utime = c->dm_utime2; c->dm_utime2 = t;
+            if (rounds > ncl + 2) return fail(c, SIGMA_E_CUDA, "unit rounds of the parser did not converge");
+        }
+        r.unit_rounds = rounds;
+        if (c->h_totals[4] != 0xFFFFFFFFu) {
+            /* an empty clause: parser() returns false at that clause; nothing after it matters (solve.cpp:52: learnEmpty) */
+            be_event_record(c->stream, e2);
+            if (ctx_sync(c)) return SIGMA_E_CUDA;
+            r.device_ms = be_event_ms(e1, e2);
+            return SIGMA_UNSAT;
+        }
+        be_dm_sizes(c->stream, c->dm_tok.p, c->dm_term.p, ncl, c->dm_utime.p, c->dm_csize.p, c->dm_words.p, c->dm_kept.p, c->dm_isunit.p);
+        SgScanSet ss = { { c->dm_words.p, c->dm_kept.p, c->dm_isunit.p, nullptr }, { c->dm_wordoff.p, c->dm_keptoff.p, c->dm_unitoff.p, nullptr },
+                         { c->totals.p, c->totals.p + 1, c->totals.p + 6, nullptr } };
+        be_scan_multi(c->stream, ss, 3, ncl, c->scantmp.p);
+        CK(pull_totals(c, 8));
+        r.cm_buckets = c->h_totals[0]; r.n_orgs = c->h_totals[1]; r.n_units = c->h_totals[6];
+        if (r.n_orgs > r.header_clauses) return fail(c, SIGMA_E_ARG, "too many clauses (more than the header announces)");
+    }
+    NOMEM(c->dm_cm.ensure((size_t)r.cm_buckets + 16)); NOMEM(c->dm_orgs.ensure((size_t)r.n_orgs + 16)); NOMEM(c->dm_trail.ensure((size_t)r.n_units + 16));
+    be_memset(c->stream, c->dm_value.p, 0xFF, nlit);                 /* UNDEF_VAL = -1 */
+    be_memset(c->stream, c->dm_state.p, 0, V + 1);
+    be_memset(c->stream, c->dm_stats.p, 0, 8 * sizeof(uint64_t));
+    if (ncl)
+        be_dm_write(c->stream, c->dm_tok.p, c->dm_term.p, ncl, c->dm_utime.p, c->dm_csize.p, c->dm_wordoff.p, c->dm_keptoff.p, c->dm_unitoff.p, c->dm_isunit.p,
+                    c->dm_cm.p, (unsigned long long *)c->dm_orgs.p, c->dm_trail.p, c->dm_value.p, c->dm_state.p, (unsigned long long *)c->dm_stats.p,
+                    r.header_clauses, c->totals.p + 3);
+    be_event_record(c->stream, e2);
+    uint64_t st[8];
+    be_d2h(c->stream, st, c->dm_stats.p, sizeof st);
+    CK(pull_totals(c, 8));
+    if (c->h_totals[3] == 4) return fail(c, SIGMA_E_ARG, "too many clauses (more than the header announces)");
+    r.binaries = st[0]; r.ternaries = st[1]; r.large = st[2]; r.literals = st[3]; r.max_clause_size = (uint32_t)st[4];
+    r.h2d_ms = be_event_ms(e0, e1);
+    r.device_ms = be_event_ms(e1, e2);
+    r.body_offset = body;
+    c->dm_parsed = true;
+    return SIGMA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sigma_parse_dimacs(sigma_ctx *c, const char *text, uint64_t bytes, sigma_dimacs *out)
+{
+    const int rc = parse_dimacs_impl(c, text, bytes, out);
+    if (c && out) {
+        sigma_dimacs keep = *out;
+        *out = c->dm_out;
+        out->cm = keep.cm; out->cm_cap = keep.cm_cap; out->orgs = keep.orgs; out->orgs_cap = keep.orgs_cap;
+        out->trail = keep.trail; out->trail_cap = keep.trail_cap; out->value = keep.value; out->state = keep.state;
+    }
+    return rc;
+}
+
+int sigma_parse_download(sigma_ctx *c, sigma_dimacs *out)
+{
+    if (!c || !out) return SIGMA_E_ARG;
+    if (!c->dm_parsed) return fail(c, SIGMA_E_ARG, "sigma_parse_download without a successful sigma_parse_dimacs");
+    be_bind(c->device);
+    const sigma_dimacs &r = c->dm_out;
+    if (out->cm_cap < r.cm_buckets || out->orgs_cap < r.n_orgs || out->trail_cap < r.n_units || (r.cm_buckets && !out->cm) || (r.n_orgs && !out->orgs) ||
+        (r.n_units && !out->trail)) {
+        sigma_dimacs keep = *out;
+        *out = r;
+        out->cm = keep.cm; out->cm_cap = keep.cm_cap; out->orgs = keep.orgs; out->orgs_cap = keep.orgs_cap;
+        out->trail = keep.trail; out->trail_cap = keep.trail_cap; out->value = keep.value; out->state = keep.state;
+        return SIGMA_E_NOSPACE;
+    }
+    if (r.cm_buckets) be_d2h(c->stream, out->cm, c->dm_cm.p, r.cm_buckets * 4);
+    if (r.n_orgs) be_d2h(c->stream, out->orgs, c->dm_orgs.p, r.n_orgs * 8);
+    if (r.n_units) be_d2h(c->stream, out->trail, c->dm_trail.p, r.n_units * 4);
+    if (out->value) be_d2h(c->stream, out->value, c->dm_value.p, 2ull * r.nvars + 2);
+    if (out->state) be_d2h(c->stream, out->state, c->dm_state.p, (size_t)r.nvars + 1);
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
+    sigma_dimacs keep = *out;
+    *out = r;
+    out->cm = keep.cm; out->cm_cap = keep.cm_cap; out->orgs = keep.orgs; out->orgs_cap = keep.orgs_cap;
+    out->trail = keep.trail; out->trail_cap = keep.trail_cap; out->value = keep.value; out->state = keep.state;
     return SIGMA_OK;
 }
 

@@ -67,6 +67,16 @@ class SigmaCnfOut(C.Structure):
                 ("lits_original", C.c_uint64), ("lits_learnt", C.c_uint64), ("last_ref", C.c_uint64)]
 
 
+class SigmaDimacs(C.Structure):
+    """sigma_dimacs (include/sigma_b200.h)."""
+    _fields_ = [("cm", C.c_void_p), ("cm_cap", C.c_uint64), ("orgs", C.c_void_p), ("orgs_cap", C.c_uint64),
+                ("trail", C.c_void_p), ("trail_cap", C.c_uint64), ("value", C.c_void_p), ("state", C.c_void_p),
+                ("nvars", C.c_uint32), ("header_clauses", C.c_uint32), ("cm_buckets", C.c_uint64), ("n_orgs", C.c_uint64),
+                ("n_units", C.c_uint64), ("binaries", C.c_uint64), ("ternaries", C.c_uint64), ("large", C.c_uint64),
+                ("literals", C.c_uint64), ("max_clause_size", C.c_uint32), ("unit_rounds", C.c_uint32),
+                ("body_offset", C.c_uint64), ("h2d_ms", C.c_float), ("device_ms", C.c_float)]
+
+
 class SigmaReport(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("phases_run", C.c_int32), ("n_clauses", C.c_uint32), ("max_melted_delta", C.c_uint32),
@@ -124,6 +134,8 @@ def load(path=None):
     lib.sigma_extracted_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sigma_cnf_out_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaCnfOut)]
     lib.sigma_download_cnf.argtypes = [C.c_void_p, C.POINTER(SigmaCnfOut), C.POINTER(SigmaFormula)]
+    lib.sigma_parse_dimacs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SigmaDimacs)]
+    lib.sigma_parse_download.argtypes = [C.c_void_p, C.POINTER(SigmaDimacs)]
     lib.sigma_execute.argtypes = [C.c_void_p]
     lib.sigma_result_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
     lib.sigma_download.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
@@ -341,6 +353,25 @@ class Sigma:
         self.execute()
         out = self.download()
         return out, self.report()
+
+    # ---- the DIMACS parser on the device (reference dimacs.cpp:25-177) ----------------------
+    def parse_dimacs(self, text, download=True):
+        """`text`: the file image (bytes / numpy uint8 / PinnedArray.array).  Returns a dict with the parsed clause database
+        (cm, orgs, trail, value, state as numpy arrays when download=True) and the counters.  Raises Unsat for an empty
+        clause, SigmaError(E_ARG) for anything the reference's parser stops on."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else text
+        d = SigmaDimacs()
+        self._check(self.lib.sigma_parse_dimacs(self.ctx, _ptr(buf), C.c_uint64(buf.size), C.byref(d)))
+        out = {k: getattr(d, k) for k in ("nvars", "header_clauses", "cm_buckets", "n_orgs", "n_units", "binaries", "ternaries", "large",
+                                          "literals", "max_clause_size", "unit_rounds", "body_offset", "h2d_ms", "device_ms")}
+        if download:
+            cm, orgs, trail = np.empty(d.cm_buckets, np.uint32), np.empty(d.n_orgs, np.uint64), np.empty(d.n_units, np.uint32)
+            value, state = np.empty(2 * d.nvars + 2, np.int8), np.empty(d.nvars + 1, np.uint8)
+            d.cm, d.cm_cap, d.orgs, d.orgs_cap, d.trail, d.trail_cap = _ptr(cm), cm.size, _ptr(orgs), orgs.size, _ptr(trail), trail.size
+            d.value, d.state = _ptr(value), _ptr(state)
+            self._check(self.lib.sigma_parse_download(self.ctx, C.byref(d)))
+            out.update(cm=cm, orgs=orgs, trail=trail, value=value, state=state)
+        return out
 
     def set_interrupt_flag(self, flag):
         """`flag`: a one-byte numpy array the caller may set to non-zero from another thread / a signal handler (the

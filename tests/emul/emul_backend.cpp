@@ -8,6 +8,7 @@
  */
 #include "../../seqfrost_b200/csrc/sigma_backend.h"
 #include "../../seqfrost_b200/csrc/sigma_items.cuh"
+#include "../../seqfrost_b200/csrc/sigma_dimacs.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -494,4 +495,84 @@ void be_ot_compare(void *, const SgView &v, const uint32_t *off2, const uint32_t
             bad++; break; }
     }
     *mismatch = bad;
+}
+
+/* ---- DIMACS parser: the bodies of sigma_dimacs.cuh, one work item after the other ---------------------------------- */
+void be_dm_chunk_states(void *, const uint8_t *text, uint64_t n, uint32_t nchunks, uint32_t *fn, uint32_t *, uint32_t *, uint32_t *cstate, uint32_t *final_state)
+{
+    g_launches++;
+    for (uint32_t i = 0; i < nchunks; ++i) {
+        const uint64_t lo = (uint64_t)i * SGD_CHUNK, hi = lo + SGD_CHUNK < n ? lo + SGD_CHUNK : n;
+        fn[i] = sgd_chunk_fn(text, lo, hi);
+    }
+    uint32_t pre = SGD_IDENT;                              /* composition, not state chasing: the scan the device runs */
+    for (uint32_t i = 0; i < nchunks; ++i) { cstate[i] = sgd_apply(pre, SGD_B); pre = sgd_compose(pre, fn[i]); }
+    *final_state = sgd_apply(pre, SGD_B);
+}
+void be_dm_tokens(void *, const uint8_t *text, uint64_t n, uint32_t nchunks, const uint32_t *cstate, uint32_t nvars, int emit, uint32_t *ntok,
+                  uint32_t *nterm, const uint32_t *tokoff, const uint32_t *termoff, uint32_t *tok, uint32_t *term, uint32_t *bad)
+{
+    g_launches++;
+    for (uint32_t i : item_order(nchunks)) {
+        const uint64_t lo = (uint64_t)i * SGD_CHUNK, hi = lo + SGD_CHUNK < n ? lo + SGD_CHUNK : n;
+        uint32_t a, b;
+        const uint32_t end = sgd_chunk_tokens(text, lo, hi, n, cstate[i], nvars, emit != 0, &a, &b, emit ? tokoff[i] : 0u, emit ? termoff[i] : 0u, tok, term, bad);
+        if (!emit) { ntok[i] = a; nterm[i] = b; if (end == SGD_ERR) *bad = 2; }
+    }
+}
+void be_dm_clauses(void *, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, uint32_t *utime_new, uint32_t *csize, uint32_t *unsat)
+{
+    g_launches++;
+    for (uint32_t c : item_order(ncl)) {
+        const uint32_t first = c ? term[c - 1] + 1 : 0u, last = term[c];
+        uint32_t kind;
+        const uint32_t n = sgd_make_clause(tok, first, last, c, utime, nullptr, &kind);
+        csize[c] = kind == 3 ? 0u : (kind == 0 && n == 0 && !sgd_satisfied_or_empty(tok, first, last, c, utime)) ? 0xFFFFFFFFu : n;
+        if (kind == 3 && c < *unsat) *unsat = c;
+        if (kind == 1) { uint32_t &u = utime_new[sgd_unit_literal(tok, first, last, c, utime)]; if (c < u) u = c; }
+    }
+}
+void be_dm_diff(void *, const uint32_t *a, const uint32_t *b, uint32_t n, uint32_t *changed)
+{
+    g_launches++;
+    for (uint32_t i = 0; i < n; ++i) if (a[i] != b[i]) *changed = 1;
+}
+void be_dm_sizes(void *, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, const uint32_t *csize, uint32_t *words,
+                 uint32_t *kept, uint32_t *isunit)
+{
+    g_launches++;
+    for (uint32_t c : item_order(ncl)) {
+        const uint32_t n = csize[c] == 0xFFFFFFFFu ? 0u : csize[c];
+        words[c] = n >= 2 ? n + 4u : 0u;
+        kept[c] = n >= 2;
+        uint32_t u = 0;
+        if (n == 1) u = utime[sgd_unit_literal(tok, c ? term[c - 1] + 1 : 0u, term[c], c, utime)] == c;
+        isunit[c] = u;
+    }
+}
+void be_dm_write(void *, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, const uint32_t *csize, const uint32_t *wordoff,
+                 const uint32_t *keptoff, const uint32_t *unitoff, const uint32_t *isunit, uint32_t *cm, unsigned long long *orgs, uint32_t *trail,
+                 int8_t *value, uint8_t *state, unsigned long long *stats, uint32_t header_clauses, uint32_t *bad)
+{
+    g_launches++;
+    for (uint32_t c : item_order(ncl)) {
+        if (csize[c] == 0xFFFFFFFFu) { if (keptoff[c] + 1 > header_clauses) *bad = 4; continue; }
+        const uint32_t n = csize[c];
+        const uint32_t first = c ? term[c - 1] + 1 : 0u, last = term[c];
+        if (n >= 2) {
+            uint32_t *dst = cm + wordoff[c];
+            uint32_t kind;
+            dst[0] = (1u << 4) | (n == 2 ? 1u << 5 : 0u); dst[1] = n; dst[2] = 2u; dst[3] = 0u;
+            (void)sgd_make_clause(tok, first, last, c, utime, dst + 4, &kind);
+            orgs[keptoff[c]] = wordoff[c];
+            stats[n == 2 ? 0 : n == 3 ? 1 : 2]++;
+            stats[3] += n;
+            if (n > stats[4]) stats[4] = n;
+        } else if (n == 1 && isunit[c]) {
+            const uint32_t lit = sgd_unit_literal(tok, first, last, c, utime);
+            trail[unitoff[c]] = lit;
+            value[lit] = 1; value[lit ^ 1u] = 0;
+            state[lit >> 1] = (uint8_t)SG_FROZEN_M;
+        }
+    }
 }
