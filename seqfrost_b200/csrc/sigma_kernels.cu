@@ -1717,15 +1717,37 @@ __device__ __forceinline__ uint32_t dm_block_scan_fn(uint32_t f, uint32_t *s_w /
     __syncthreads();
     return f;
 }
+/* the 64 bytes of chunk i as four 16-byte words (the text buffer is 16-byte aligned and padded) */
+__device__ __forceinline__ void dm_load_chunk(const uint8_t *__restrict__ text, uint32_t i, uint32_t w[16])
+{
+    const uint4 *p = (const uint4 *)text + (size_t)i * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const uint4 x = __ldg(p + q); w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w; }
+}
 __global__ void __launch_bounds__(TPB) k_dm_fns(const uint8_t *__restrict__ text, uint64_t n, uint32_t nchunks, uint32_t *__restrict__ fn,
                                                 uint32_t *__restrict__ tilefn)
 {
     __shared__ uint32_t s_w[TPB / 32];
+    __shared__ uint8_t s_cls[256];
+    __shared__ uint32_t s_pair[SGD_NCLASS * SGD_NCLASS];          /* transition function of two bytes, by their classes */
+    s_cls[threadIdx.x] = (uint8_t)sgd_class((uint8_t)threadIdx.x);
+    if (threadIdx.x < SGD_NCLASS * SGD_NCLASS)
+        s_pair[threadIdx.x] = sgd_compose(sgd_class_fn(threadIdx.x / SGD_NCLASS), sgd_class_fn(threadIdx.x % SGD_NCLASS));
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t f = SGD_IDENT;
     if (i < nchunks) {
-        const uint64_t lo = (uint64_t)i * SGD_CHUNK, hi = lo + SGD_CHUNK < n ? lo + SGD_CHUNK : n;
-        f = sgd_chunk_fn(text, lo, hi);
+        const uint64_t lo = (uint64_t)i * SGD_CHUNK;
+        if (lo + SGD_CHUNK <= n) {
+            uint32_t w[16];
+            dm_load_chunk(text, i, w);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t x = w[k];
+                f = sgd_compose(f, s_pair[s_cls[x & 255u] * SGD_NCLASS + s_cls[(x >> 8) & 255u]]);
+                f = sgd_compose(f, s_pair[s_cls[(x >> 16) & 255u] * SGD_NCLASS + s_cls[x >> 24]]);
+            }
+        } else f = sgd_chunk_fn(text, lo, n);
         fn[i] = f;
     }
     uint32_t tot;
@@ -1773,16 +1795,65 @@ __global__ void __launch_bounds__(TPB) k_dm_chunk_states(const uint32_t *__restr
     const uint32_t excl = (threadIdx.x & 31) ? prev : (threadIdx.x ? s_last[(threadIdx.x >> 5) - 1] : SGD_IDENT);
     if (i < nchunks) cstate[i] = sgd_apply(excl, tstate[blockIdx.x]);
 }
+/* The integers that start in chunk i, in one walk over its 64 bytes held in registers: the value is built digit by digit
+ * as the state machine moves (no second loop per integer, so the lanes of a warp stay together); an integer that runs past
+ * the end of the chunk is finished from global memory by the chunk it started in.  Same result as sgd_chunk_tokens. */
+template <bool EMIT>
 __global__ void __launch_bounds__(TPB) k_dm_tokens(const uint8_t *__restrict__ text, uint64_t n, uint32_t nchunks, const uint32_t *__restrict__ cstate,
-                                                   uint32_t nvars, int emit, uint32_t *ntok, uint32_t *nterm, const uint32_t *__restrict__ tokoff,
+                                                   uint32_t nvars, uint32_t *ntok, uint32_t *nterm, const uint32_t *__restrict__ tokoff,
                                                    const uint32_t *__restrict__ termoff, uint32_t *__restrict__ tok, uint32_t *__restrict__ term, uint32_t *bad)
 {
+    __shared__ uint8_t s_cls[256];
+    __shared__ uint32_t s_fn[16];
+    s_cls[threadIdx.x] = (uint8_t)sgd_class((uint8_t)threadIdx.x);
+    if (threadIdx.x < SGD_NCLASS) s_fn[threadIdx.x] = sgd_class_fn(threadIdx.x);
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nchunks) return;
-    const uint64_t lo = (uint64_t)i * SGD_CHUNK, hi = lo + SGD_CHUNK < n ? lo + SGD_CHUNK : n;
-    uint32_t a, b;
-    const uint32_t end = sgd_chunk_tokens(text, lo, hi, n, cstate[i], nvars, emit != 0, &a, &b, emit ? tokoff[i] : 0u, emit ? termoff[i] : 0u, tok, term, bad);
-    if (!emit) { ntok[i] = a; nterm[i] = b; if (end == SGD_ERR) *bad = 2; }
+    const uint64_t lo = (uint64_t)i * SGD_CHUNK;
+    if (lo + SGD_CHUNK > n) {                                                     /* the last, partial chunk: the plain walk */
+        uint32_t a, b;
+        const uint32_t end = sgd_chunk_tokens(text, lo, n, n, cstate[i], nvars, EMIT, &a, &b, EMIT ? tokoff[i] : 0u, EMIT ? termoff[i] : 0u, tok, term, bad);
+        if (!EMIT) { ntok[i] = a; nterm[i] = b; if (end == SGD_ERR) *bad = 2; }
+        return;
+    }
+    uint32_t w[16];
+    dm_load_chunk(text, i, w);
+    uint32_t state = cstate[i], nt = 0, nz = 0, cur = 0, sign = 0;
+    bool owned = false;
+    const uint32_t tb = EMIT ? tokoff[i] : 0u, zb = EMIT ? termoff[i] : 0u;
+    auto emit = [&]() {
+        if (EMIT) {
+            uint32_t v = cur;
+            if (v > nvars) { *bad = 3; v = 1; }
+            tok[tb + nt] = v ? 2u * v + sign : 0u;
+            if (!v) term[zb + nz] = tb + nt;
+        }
+        ++nt;
+        nz += cur == 0;
+        owned = false;
+    };
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t ch = (w[k] >> (8 * q)) & 255u;
+            const uint32_t cls = s_cls[ch];
+            if (sgd_token_start(state, cls)) {
+                if (owned) emit();                           /* "1-2": a sign ends the integer before it */
+                owned = true; cur = 0; sign = ch == '-';
+            }
+            if (owned && (cls == SGD_Z || cls == SGD_D)) cur = cur * 10u + (ch - '0');
+            state = sgd_apply(s_fn[cls], state);
+            if (owned && !sgd_in_token(state)) emit();
+        }
+    }
+    if (owned) {                                             /* runs on into the next chunk(s) */
+        uint64_t p = lo + SGD_CHUNK;
+        while (p < n && text[p] >= '0' && text[p] <= '9') cur = cur * 10u + (uint32_t)(text[p++] - '0');
+        emit();
+    }
+    if (!EMIT) { ntok[i] = nt; nterm[i] = nz; if (state == SGD_ERR) *bad = 2; }
 }
 /* one round of makeClause over all clauses from the units of the previous round; csize = literals left (0: dropped) */
 __global__ void __launch_bounds__(TPB) k_dm_clauses(const uint32_t *__restrict__ tok, const uint32_t *__restrict__ term, uint32_t ncl,
@@ -1827,26 +1898,33 @@ __global__ void k_dm_write(const uint32_t *__restrict__ tok, const uint32_t *__r
                            unsigned long long *__restrict__ stats /* binaries, ternaries, large, literals, max size */, uint32_t header_clauses,
                            uint32_t *bad)
 {
+    /* counters: one set of global atomics per block */
+    __shared__ uint32_t s_st[5];
+    if (threadIdx.x < 5) s_st[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncl) return;
-    if (csize[c] == 0xFFFFFFFFu) { if (keptoff[c] + 1 > header_clauses) *bad = 4; return; }     /* dimacs.cpp:160 */
-    const uint32_t n = csize[c];
-    const uint32_t first = c ? term[c - 1] + 1 : 0u, last = term[c];
+    const bool live = c < ncl;
+    if (live && csize[c] == 0xFFFFFFFFu && keptoff[c] + 1 > header_clauses) *bad = 4;            /* dimacs.cpp:160 */
+    const uint32_t n = live && csize[c] != 0xFFFFFFFFu ? csize[c] : 0u;
+    const uint32_t first = live && c ? term[c - 1] + 1 : 0u, last = live ? term[c] : 0u;
     if (n >= 2) {
         uint32_t *dst = cm + wordoff[c];
         uint32_t kind;
         dst[0] = (1u << 4) | (n == 2 ? 1u << 5 : 0u); dst[1] = n; dst[2] = 2u; dst[3] = 0u;
         (void)sgd_make_clause(tok, first, last, c, utime, dst + 4, &kind);
         orgs[keptoff[c]] = wordoff[c];
-        atomicAdd(&stats[n == 2 ? 0 : n == 3 ? 1 : 2], 1ull);
-        atomicAdd(&stats[3], (unsigned long long)n);
-        atomicMax(&stats[4], (unsigned long long)n);
+        atomicAdd(&s_st[n == 2 ? 0 : n == 3 ? 1 : 2], 1u);
+        atomicAdd(&s_st[3], n);
+        atomicMax(&s_st[4], n);
     } else if (n == 1 && isunit[c]) {
         const uint32_t lit = sgd_unit_literal(tok, first, last, c, utime);
         trail[unitoff[c]] = lit;
         value[lit] = 1; value[lit ^ 1u] = 0;                  /* enqueueUnit, solve.hpp:373-398 */
         state[lit >> 1] = (uint8_t)SG_FROZEN_M;
     }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_st[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_st[threadIdx.x]);
+    if (threadIdx.x == 4 && s_st[4]) atomicMax(&stats[4], (unsigned long long)s_st[4]);
 }
 
 } // namespace
@@ -2352,7 +2430,8 @@ void be_dm_chunk_states(void *s, const uint8_t *text, uint64_t n, uint32_t nchun
 void be_dm_tokens(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, const uint32_t *cstate, uint32_t nvars, int emit, uint32_t *ntok,
                   uint32_t *nterm, const uint32_t *tokoff, const uint32_t *termoff, uint32_t *tok, uint32_t *term, uint32_t *bad)
 {
-    LAUNCH(k_dm_tokens, blocks_for(nchunks), TPB, s, text, n, nchunks, cstate, nvars, emit, ntok, nterm, tokoff, termoff, tok, term, bad);
+    if (emit) LAUNCH(k_dm_tokens<true>, blocks_for(nchunks), TPB, s, text, n, nchunks, cstate, nvars, ntok, nterm, tokoff, termoff, tok, term, bad);
+    else LAUNCH(k_dm_tokens<false>, blocks_for(nchunks), TPB, s, text, n, nchunks, cstate, nvars, ntok, nterm, tokoff, termoff, tok, term, bad);
 }
 void be_dm_clauses(void *s, const uint32_t *tok, const uint32_t *term, uint32_t ncl, const uint32_t *utime, uint32_t *utime_new, uint32_t *csize, uint32_t *unsat)
 {
