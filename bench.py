@@ -282,6 +282,7 @@ def main():
     ap.add_argument("--no-binding", action="store_true")
     ap.add_argument("--no-ere", action="store_true", help="run both sides with -no-redundancy")
     ap.add_argument("--instances", type=int, default=64, help="c5 only: size of the batch")
+    ap.add_argument("--from-dimacs", action="store_true", help="c5 only: the queue starts from the DIMACS files (device parser + extract + pass)")
     ap.add_argument("--verify", action="store_true", help="c5 only: check every output against tests/golden/c5_digests.json")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

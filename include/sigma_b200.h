@@ -244,6 +244,12 @@ typedef struct sigma_dimacs {
 } sigma_dimacs;
 int  sigma_parse_dimacs(sigma_ctx *ctx, const char *text, uint64_t bytes, sigma_dimacs *sizes);
 int  sigma_parse_download(sigma_ctx *ctx, sigma_dimacs *out);
+/* file -> pass without leaving the device: the parsed clause database becomes the input of extract() (as sigma_upload_cnf
+ * would build it from host arrays: simplify.cpp:118-153), with the solver state of a fresh solver (nothing assigned, vorg =
+ * identity, empty model, first simplify() call).  Only for files without unit clauses - otherwise the solver's own BCP() and
+ * shrinkTop() come between parser() and simplify() (solve.cpp:52, simplify.cpp:161-162): SIGMA_E_UNSUPPORTED.  Afterwards
+ * sigma_execute / sigma_download / sigma_download_cnf as usual. */
+int  sigma_upload_parsed(sigma_ctx *ctx, const sigma_opts *o);
 
 /* pinned host memory for the hand-off buffers (the solver's SCNF arena allocator would call this
  * instead of malloc, malloc.hpp:60-69, so that H2D/D2H run at full PCIe rate) */

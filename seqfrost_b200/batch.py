@@ -138,12 +138,16 @@ class HandOff:
     """The pinned hand-off buffers of one host thread: input arrays sized for the largest instance of the batch, output
     buffers with 25 % slack (what an embedding solver owns once, sigma_host_alloc)."""
 
-    def __init__(self, sig, max_bytes, slack=1.25):
+    def __init__(self, sig, max_bytes, slack=1.25, text_bytes=0):
         import numpy as np
         from seqfrost_b200 import sigma as S
         self.np = np
         self.keep = {}
         self.inp = {}
+        self.text = None
+        if text_bytes:                                     # --from-dimacs: the file image instead of the boundary arrays
+            self.keep["text"] = S.PinnedArray(sig.lib, np.dtype(np.uint8), text_bytes + 64)
+            self.text = self.keep["text"].array
         for name, dt in _SECTION_DTYPES.items():
             n = max_bytes.get(name, 0) // np.dtype(dt).itemsize + 16      # trail / model are empty on a first call
             if name == "ifrozen":
@@ -158,6 +162,15 @@ class HandOff:
         for name, (dt, n) in caps.items():
             self.keep["out_" + name] = S.PinnedArray(sig.lib, np.dtype(dt), n)
             self.out[name] = self.keep["out_" + name].array
+
+    def load_text(self, path):
+        """Reads a DIMACS file into the pinned text buffer; returns the view of its bytes."""
+        n = os.path.getsize(path)
+        view = self.text[:n]
+        with open(path, "rb") as f:
+            if f.readinto(memoryview(view)) != n:
+                raise IOError(f"{path}: short read")
+        return view
 
     def load(self, path):
         """Reads a boundary file straight into the pinned input arrays; returns the Boundary (views) of that instance."""
@@ -223,7 +236,7 @@ class StoreCounter:
         return int(self.store.add(self.key, 1)) - 1
 
 
-def run_queue(ctxs, handoffs, items, cache, counter, digests=None):
+def run_queue(ctxs, handoffs, items, cache, counter, digests=None, from_dimacs=False):
     """Drains the queue with one host thread per (context, hand-off) pair.  Returns the per-instance records of THIS process:
     [{index, seed, literals, device_ms, h2d_bytes, d2h_bytes, digest?}], plus the aggregated report arrays."""
     done, errs = [], []
@@ -236,13 +249,22 @@ def run_queue(ctxs, handoffs, items, cache, counter, digests=None):
                 if i >= len(items):
                     return
                 it = items[i]
-                b = ho.load(c5_path(cache, it))
-                sig.upload(b)
+                parse_ms = 0.0
+                if from_dimacs:
+                    # file image -> parser -> extract -> pass, all on the device (sigma_parse_dimacs, sigma_upload_parsed)
+                    d = sig.parse_dimacs(ho.load_text(c5_path(cache, it, "cnf")), download=False)
+                    sig.upload_parsed({"ere_en": 1}, nvars=d["nvars"])
+                    parse_ms = d["device_ms"]
+                    b = sig._keep[0]
+                else:
+                    b = ho.load(c5_path(cache, it))
+                    sig.upload(b)
                 sig.execute()
                 f = sig.download_into(ho.out)
                 r = sig.report()
                 rec = {"index": i, "seed": it["seed"], "literals": int(r["literals_in"]), "device_ms": r["stage_ms"]["total_device"],
-                       "h2d_bytes": r["h2d_bytes"], "d2h_bytes": r["d2h_bytes"], "launches": r["kernel_launches"],
+                       "h2d_bytes": r["h2d_bytes"] + (os.path.getsize(c5_path(cache, it, "cnf")) if from_dimacs else 0),
+                       "d2h_bytes": r["d2h_bytes"], "launches": r["kernel_launches"], "parse_ms": parse_ms,
                        "stage_ms": r["stage_ms"], "stage_bytes": r["stage_bytes"], "stage_launches": r["stage_launches"]}
                 if digests is not None:
                     o = ho.out
@@ -286,7 +308,8 @@ def bench_c5(args, rank, world, local):
     dev = local
     torch.cuda.set_device(dev)
     pinned_to = Bn.pin_to_gpu_numa_node(torch, dev)
-    c5_prepare(items, cache, rank, world)
+    from_dimacs = bool(getattr(args, "from_dimacs", False))
+    c5_prepare(items, cache, rank, world, want_cnf=from_dimacs)
     device = f"cuda:{dev}"
 
     def barrier():
@@ -299,7 +322,8 @@ def bench_c5(args, rank, world, local):
         for name, (_, n) in boundary_sections(c5_path(cache, it)).items():
             max_bytes[name] = max(max_bytes.get(name, 0), n)
     ctxs = [sigma.Sigma(dev), sigma.Sigma(dev)]
-    handoffs = [HandOff(ctxs[0], max_bytes), HandOff(ctxs[1], max_bytes)]
+    text_bytes = max(os.path.getsize(c5_path(cache, it, "cnf")) for it in items) if from_dimacs else 0
+    handoffs = [HandOff(ctxs[0], max_bytes, text_bytes=text_bytes), HandOff(ctxs[1], max_bytes, text_bytes=text_bytes)]
     store = None
     if world > 1:
         port = int(os.environ.get("MASTER_PORT", "29500")) + 17
@@ -309,7 +333,7 @@ def bench_c5(args, rank, world, local):
         counter = LocalCounter() if store is None else StoreCounter(store, f"c5_{tag}")
         barrier()
         t0 = time.perf_counter()
-        recs = run_queue(ctxs, handoffs, items, cache, counter, digests)
+        recs = run_queue(ctxs, handoffs, items, cache, counter, digests, from_dimacs)
         torch.cuda.synchronize()
         mine_ms = 1e3 * (time.perf_counter() - t0)
         barrier()
@@ -377,7 +401,9 @@ def bench_c5(args, rank, world, local):
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"batch of {len(items)} mixed CNF instances (C2/C3/C4 generators, 0.5-5M clauses, seeds 100..{99 + len(items)}) "
                                    "as a largest-first work queue, reference default options (BASELINE.json configs[4], SURVEY 8e C5)",
-                       "config": "c5", "instances_per_step": len(items), "queue": "shared counter (torch.distributed TCPStore add), two contexts + two host threads per GPU",
+                       "config": "c5", "instances_per_step": len(items),
+                       "input": "DIMACS files: parsed, extracted and simplified on the device (sigma_parse_dimacs -> sigma_upload_parsed)" if from_dimacs
+                                else "the SCNF boundary awaken() hands over (sigma_upload)", "queue": "shared counter (torch.distributed TCPStore add), two contexts + two host threads per GPU",
                        "instances_per_rank": per_rank, "l2": "inputs larger than L2 (every instance is 40-450 MB)",
                        "value_is": "whole-queue wall-clock rate = e2e (two contexts share each GPU, so the passes' device times overlap "
                                    "and do not add up to a device-only figure; their sum on the busiest GPU is device_ms_busiest_gpu_per_step)"},

@@ -178,6 +178,7 @@ void be_compact_apply(void *s, const SgView &v, const uint32_t *tmp, sg_u4 *hdr2
 /* device store -> AoS SCNF arena + refs in the reference's layout */
 void be_export_apply(void *s, const SgView &v, const uint32_t *tmp, uint32_t *arena, uint64_t *refs);
 
+void be_iota_u32(void *s, uint32_t *p, uint32_t n);       /* p[i] = i */
 /* ---- DIMACS parser (dimacs.cpp:25-177; method and per-item bodies in sigma_dimacs.cuh) ------------------------------ */
 /* start state of every 64-byte chunk of text[0, n) (the clause part of the file, after the header) + the state at the end */
 void be_dm_chunk_states(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, uint32_t *fn, uint32_t *tilefn, uint32_t *tstate, uint32_t *cstate,

@@ -2418,6 +2418,8 @@ void be_ot_compare(void *s, const SgView &v, const uint32_t *off2, const uint32_
     LAUNCH(k_ot_compare, blocks_for(v.nlit), TPB, s, v, off2, len2, data2, mismatch);
 }
 
+namespace { __global__ void k_iota_u32(uint32_t *p, uint32_t n) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; } }
+void be_iota_u32(void *s, uint32_t *p, uint32_t n) { if (n) LAUNCH(k_iota_u32, blocks_for(n), TPB, s, p, n); }
 /* ---- DIMACS parser launches (sigma_backend.h) ------------------------------------------------------- */
 void be_dm_chunk_states(void *s, const uint8_t *text, uint64_t n, uint32_t nchunks, uint32_t *fn, uint32_t *tilefn, uint32_t *tstate, uint32_t *cstate,
                         uint32_t *final_state)

@@ -87,7 +87,7 @@ struct sigma_ctx {
     DBuf<uint8_t> dm_text, dm_state; DBuf<int8_t> dm_value;
     DBuf<uint32_t> dm_fn, dm_tilefn, dm_tstate, dm_cstate, dm_ntok, dm_nterm, dm_tokoff, dm_termoff, dm_tok, dm_term;
     DBuf<uint32_t> dm_utime, dm_utime2, dm_csize, dm_words, dm_kept, dm_isunit, dm_wordoff, dm_keptoff, dm_unitoff, dm_cm, dm_trail;
-    DBuf<uint64_t> dm_orgs, dm_stats;
+    DBuf<uint64_t> dm_orgs, dm_stats; DBuf<uint32_t> dm_vorg;
     bool dm_parsed = false; sigma_dimacs dm_out;
     bool cm_built = false; uint32_t cm_learnts = 0; uint64_t cm_lits_org = 0, cm_lits_learnt = 0, cm_last_ref = 0;
     SgScalars hsc;                  /* host mirror */
@@ -1013,8 +1013,10 @@ namespace {
 
 /* sigma_upload (cnf == nullptr: the SCNF arena comes from the host) and sigma_upload_cnf (the solver's clause
  * database comes from the host, extract() runs here) */
-int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, const sigma_cnf *cnf)
+int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, const sigma_cnf *cnf, bool from_device = false)
 {
+    /* from_device (sigma_upload_parsed): every pointer of `cnf` and `in` is device memory of this context */
+    auto be_in = [from_device](void *st, void *dst, const void *src, size_t bytes) { return from_device ? be_d2d(st, dst, src, bytes) : be_h2d(st, dst, src, bytes); };
     if (!c || !in) return SIGMA_E_ARG;
     if (!c->stream) return fail(c, SIGMA_E_CUDA, c->err[0] ? c->err : "no CUDA device");
     be_bind(c->device);                                    /* callers may use one host thread per context */
@@ -1070,20 +1072,20 @@ int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, cons
     void *e0 = get_event(c), *e1 = get_event(c);
     be_event_record(c->stream, e0);
     if (cnf) {
-        be_h2d(c->stream, c->d_cm.p, cnf->cm, cnf->cm_buckets * 4);
-        if (cnf->n_orgs) be_h2d(c->stream, c->d_crefs.p, cnf->orgs, cnf->n_orgs * 8);
-        if (cnf->n_learnts) be_h2d(c->stream, c->d_crefs.p + cnf->n_orgs, cnf->learnts, cnf->n_learnts * 8);
-        if (cnf->stencil_size) be_h2d(c->stream, c->d_stencil.p, cnf->stencil, cnf->stencil_size);
+        be_in(c->stream, c->d_cm.p, cnf->cm, cnf->cm_buckets * 4);
+        if (cnf->n_orgs) be_in(c->stream, c->d_crefs.p, cnf->orgs, cnf->n_orgs * 8);
+        if (cnf->n_learnts) be_in(c->stream, c->d_crefs.p + cnf->n_orgs, cnf->learnts, cnf->n_learnts * 8);
+        if (cnf->stencil_size) be_in(c->stream, c->d_stencil.p, cnf->stencil, cnf->stencil_size);
     } else {
-        be_h2d(c->stream, c->d_arena_in.p, in->arena, in->n_buckets * 4);
-        be_h2d(c->stream, c->d_refs_in.p, in->refs, (size_t)n * 8);
+        be_in(c->stream, c->d_arena_in.p, in->arena, in->n_buckets * 4);
+        be_in(c->stream, c->d_refs_in.p, in->refs, (size_t)n * 8);
     }
-    be_h2d(c->stream, c->d_state_in.p, in->state, V + 1);
-    be_h2d(c->stream, c->d_value_in.p, in->value, nlit);
-    if (in->trail_size) be_h2d(c->stream, c->d_trail_in.p, in->trail, (size_t)in->trail_size * 4);
-    if (in->model_size) be_h2d(c->stream, c->d_model_in.p, in->model, (size_t)in->model_size * 4);
-    be_h2d(c->stream, c->d_vorg.p, in->vorg, (size_t)(V + 1) * 4);
-    if (in->ifrozen) be_h2d(c->stream, c->d_ifrozen.p, in->ifrozen, V + 1);
+    be_in(c->stream, c->d_state_in.p, in->state, V + 1);
+    be_in(c->stream, c->d_value_in.p, in->value, nlit);
+    if (in->trail_size) be_in(c->stream, c->d_trail_in.p, in->trail, (size_t)in->trail_size * 4);
+    if (in->model_size) be_in(c->stream, c->d_model_in.p, in->model, (size_t)in->model_size * 4);
+    be_in(c->stream, c->d_vorg.p, in->vorg, (size_t)(V + 1) * 4);
+    if (in->ifrozen) be_in(c->stream, c->d_ifrozen.p, in->ifrozen, V + 1);
     be_event_record(c->stream, e1);
     void *e2 = nullptr;
     if (cnf) {
@@ -1110,7 +1112,7 @@ int upload_impl(sigma_ctx *c, const sigma_opts *o, const sigma_formula *in, cons
     c->rep.stage_ms[SIGMA_T_H2D] = be_event_ms(e0, e1);
     if (e2) c->extract_us = (uint64_t)(1000.0f * be_event_ms(e1, e2));
     c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
-    c->rep.h2d_bytes = (cnf ? cnf->cm_buckets * 4 + n_src * 8 + cnf->stencil_size : in->n_buckets * 4 + (uint64_t)n * 8) +
+    c->rep.h2d_bytes = from_device ? 0 : (cnf ? cnf->cm_buckets * 4 + n_src * 8 + cnf->stencil_size : in->n_buckets * 4 + (uint64_t)n * 8) +
                        (V + 1) + nlit + (uint64_t)in->trail_size * 4 +
                        (uint64_t)in->model_size * 4 + (uint64_t)(V + 1) * 4 + (in->ifrozen ? V + 1 : 0);
     c->uploaded = true;
@@ -1127,6 +1129,27 @@ int sigma_upload_cnf(sigma_ctx *c, const sigma_opts *o, const sigma_cnf *cnf, co
 {
     if (!cnf) return SIGMA_E_ARG;
     return upload_impl(c, o, in, cnf);
+}
+
+int sigma_upload_parsed(sigma_ctx *c, const sigma_opts *o)
+{
+    if (!c) return SIGMA_E_ARG;
+    if (!c->dm_parsed) return fail(c, SIGMA_E_ARG, "sigma_upload_parsed without a successful sigma_parse_dimacs");
+    const sigma_dimacs &r = c->dm_out;
+    if (r.n_units) return fail(c, SIGMA_E_UNSUPPORTED, "the file has unit clauses: the solver's BCP() and shrinkTop() come between parser() and simplify() "
+                                                        "(solve.cpp:52, simplify.cpp:161-162); download the parse and let the solver run them");
+    if (!r.n_orgs) return fail(c, SIGMA_E_ARG, "no clauses");
+    be_bind(c->device);
+    NOMEM(c->dm_vorg.ensure((size_t)r.nvars + 1));
+    be_iota_u32(c->stream, c->dm_vorg.p, r.nvars + 1);
+    sigma_cnf cnf;
+    memset(&cnf, 0, sizeof cnf);
+    cnf.cm = c->dm_cm.p; cnf.cm_buckets = r.cm_buckets; cnf.orgs = c->dm_orgs.p; cnf.n_orgs = r.n_orgs;
+    sigma_formula f;
+    memset(&f, 0, sizeof f);
+    f.nvars = r.nvars; f.state = c->dm_state.p; f.value = c->dm_value.p; f.vorg = c->dm_vorg.p;
+    f.unassigned = r.nvars; f.simplify_calls = 1;
+    return upload_impl(c, o, &f, &cnf, true);
 }
 
 int sigma_extracted_sizes(sigma_ctx *c, uint32_t *n_clauses, uint64_t *n_buckets, uint64_t *n_literals)

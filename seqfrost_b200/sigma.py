@@ -136,6 +136,7 @@ def load(path=None):
     lib.sigma_download_cnf.argtypes = [C.c_void_p, C.POINTER(SigmaCnfOut), C.POINTER(SigmaFormula)]
     lib.sigma_parse_dimacs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SigmaDimacs)]
     lib.sigma_parse_download.argtypes = [C.c_void_p, C.POINTER(SigmaDimacs)]
+    lib.sigma_upload_parsed.argtypes = [C.c_void_p, C.POINTER(SigmaOpts)]
     lib.sigma_execute.argtypes = [C.c_void_p]
     lib.sigma_result_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
     lib.sigma_download.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
@@ -372,6 +373,13 @@ class Sigma:
             self._check(self.lib.sigma_parse_download(self.ctx, C.byref(d)))
             out.update(cm=cm, orgs=orgs, trail=trail, value=value, state=state)
         return out
+
+    def upload_parsed(self, opts=None, nvars=None):
+        """The parsed file (parse_dimacs) becomes the pass input without leaving the device."""
+        o = self.make_opts(opts)
+        self._check(self.lib.sigma_upload_parsed(self.ctx, C.byref(o)))
+        src = B.Boundary(nvars=nvars or 0, vorg=None if nvars is None else np.arange(nvars + 1, dtype=np.uint32), opts=dict(B.DEFAULT_OPTS, **(opts or {})))
+        self._keep = (src, o, None)
 
     def set_interrupt_flag(self, flag):
         """`flag`: a one-byte numpy array the caller may set to non-zero from another thread / a signal handler (the

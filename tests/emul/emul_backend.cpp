@@ -497,6 +497,7 @@ void be_ot_compare(void *, const SgView &v, const uint32_t *off2, const uint32_t
     *mismatch = bad;
 }
 
+void be_iota_u32(void *, uint32_t *p, uint32_t n) { g_launches++; for (uint32_t i = 0; i < n; ++i) p[i] = i; }
 /* ---- DIMACS parser: the bodies of sigma_dimacs.cuh, one work item after the other ---------------------------------- */
 void be_dm_chunk_states(void *, const uint8_t *text, uint64_t n, uint32_t nchunks, uint32_t *fn, uint32_t *, uint32_t *, uint32_t *cstate, uint32_t *final_state)
 {

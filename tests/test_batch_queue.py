@@ -120,3 +120,23 @@ def test_gpu_queue_matches_reference(cuda_lib, tmp_path):
         assert r["digest"] == _reference_digest(cache, items[r["index"]]), f"seed {r['seed']}"
     for c in ctxs:
         c.close()
+
+
+def test_queue_from_dimacs_files_gives_the_same_outputs(emul_lib, tmp_path):
+    """--from-dimacs: file image -> device parser -> extract -> pass; same digests as the boundary hand-off."""
+    from seqfrost_b200 import sigma
+    cache, n, scale = str(tmp_path), 4, 0.003
+    items = batch.c5_items(n, scale=scale)
+    batch.c5_prepare(items, cache, want_cnf=True, workers=2)
+    max_bytes = {}
+    for it in items:
+        for name, (_, nb) in batch.boundary_sections(batch.c5_path(cache, it)).items():
+            max_bytes[name] = max(max_bytes.get(name, 0), nb)
+    tb = max(os.path.getsize(batch.c5_path(cache, it, "cnf")) for it in items)
+    ctxs = [sigma.Sigma(0, emul_lib), sigma.Sigma(0, emul_lib)]
+    hos = [batch.HandOff(c, max_bytes, text_bytes=tb) for c in ctxs]
+    a = batch.run_queue(ctxs, hos, items, cache, batch.LocalCounter(), digests=True, from_dimacs=True)
+    b = batch.run_queue(ctxs, hos, items, cache, batch.LocalCounter(), digests=True, from_dimacs=False)
+    assert {r["seed"]: r["digest"] for r in a} == {r["seed"]: r["digest"] for r in b} and len(a) == n
+    for c in ctxs:
+        c.close()

@@ -241,3 +241,46 @@ def test_cuda_parser_on_a_large_file(gpu_sigma, tmp_path):
     again, rc = _ours(gpu_sigma, text)                       # buffers allocated: the kernels alone
     assert rc == 0 and same(again, ref) == []
     assert again["device_ms"] > 0 and len(text) / 1e6 / again["device_ms"] > 5.0      # > 5 GB/s of text on the device
+
+
+def _file_to_pass(s, tmp_path, name, inst):
+    """DIMACS text -> parse -> extract -> pass, all on the device, against the reference run on the same file."""
+    import parity
+    from seqfrost_b200 import boundary as B
+    nv, off, lits = inst
+    cnf, fout = str(tmp_path / (name + ".cnf")), str(tmp_path / (name + ".out"))
+    cnfgen.write_dimacs(cnf, nv, off, lits)
+    subprocess.run([REF_BIN, cnf, "-quiet", f"--sgout={fout}"], capture_output=True, timeout=600, check=True)
+    with open(cnf, "rb") as f:
+        text = f.read()
+    d = s.parse_dimacs(text, download=False)
+    assert d["n_units"] == 0
+    s.upload_parsed({"ere_en": 1}, nvars=d["nvars"])
+    s.execute()
+    out = s.download()
+    assert parity.diff(out, B.read(fout)) == []
+
+
+@needs_ref
+def test_emulated_file_to_pass_without_leaving_the_device(emul_lib, tmp_path):
+    s = sigma.Sigma(0, emul_lib)
+    _file_to_pass(s, tmp_path, "g", cnfgen.gate_circuit(1500, seed=21))
+    _file_to_pass(s, tmp_path, "k", cnfgen.random_ksat(800, 3300, k=3, seed=22))
+    s.close()
+
+
+def test_upload_parsed_refuses_files_with_units(emul_lib):
+    s = sigma.Sigma(0, emul_lib)
+    s.parse_dimacs(HAND["unit_cascade"].encode(), download=False)
+    with pytest.raises(sigma.SigmaError) as e:
+        s.upload_parsed()
+    assert e.value.code == 7
+    s.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cuda_file_to_pass_without_leaving_the_device(gpu_sigma, tmp_path):
+    _file_to_pass(gpu_sigma, tmp_path, "g", cnfgen.gate_circuit(60_000, seed=21))
+    _file_to_pass(gpu_sigma, tmp_path, "k", cnfgen.planted_subsumption_ksat(40_000, 200_000, k=5, seed=22))
+    _file_to_pass(gpu_sigma, tmp_path, "x", cnfgen.xor_php_mix(50_000, seed=23))
