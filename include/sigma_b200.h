@@ -251,6 +251,23 @@ int  sigma_parse_download(sigma_ctx *ctx, sigma_dimacs *out);
  * sigma_execute / sigma_download / sigma_download_cnf as usual. */
 int  sigma_upload_parsed(sigma_ctx *ctx, const sigma_opts *o);
 
+/* ---- widening #4: rebuildWT() on the device -------------------------------------
+ * The watch table rebuildWT(opts.simplify_priorbins) builds from the new clause database (simplify.cpp:218,
+ * watch.cpp:135-157, attachBins / attachNonBins / attachClauses :22-133): for every clause in attach order - `priorbins`
+ * bit 0: binaries of orgs and learnts first, then the longer clauses; bit 1: learnt binaries before original ones; 0: orgs
+ * then learnts - sortClause (clause.cpp:116-173: best watches first, under the root assignment) on the CLAUSE record,
+ * then ATTACH_TWO_WATCHES (watch.hpp:87-96): WATCH{ref, size, the other watched literal} pushed to wt[FLIP(c[0])] and
+ * wt[FLIP(c[1])].  Handed back as one offsets array (nlit + 1 entries; list of literal l = records [offs[l], offs[l + 1]))
+ * and the 16-byte WATCH records {C_REF ref; uint32 imp; int size} (watch.hpp:28-46) of every list in push order.
+ * Call sigma_watches_sizes BEFORE sigma_download_cnf: sortClause reorders literals inside the CLAUSE records. */
+typedef struct sigma_watches {
+    uint32_t *offs;     uint64_t offs_cap;       /* entries */
+    void     *records;  uint64_t records_cap;    /* 16-byte records */
+    uint64_t  n_records; uint32_t nlit;          /* filled in */
+} sigma_watches;
+int  sigma_watches_sizes(sigma_ctx *ctx, int priorbins, sigma_watches *sizes);          /* after execute; builds them */
+int  sigma_download_watches(sigma_ctx *ctx, sigma_watches *out);
+
 /* pinned host memory for the hand-off buffers (the solver's SCNF arena allocator would call this
  * instead of malloc, malloc.hpp:60-69, so that H2D/D2H run at full PCIe rate) */
 void *sigma_host_alloc(uint64_t bytes);

@@ -330,6 +330,23 @@ public:
 			w.section("cmmeta", m, sizeof m);
 			w.section("subsume0", s0.data(), s0.size());
 			w.section("subsume1", s1.data(), s1.size());
+			// rebuildWT(opts.simplify_priorbins) (simplify.cpp:218, watch.cpp:135-157): the watch table as one offsets array +
+			// the WATCH records {C_REF ref; uint32 imp; int size} of every list in order, and the arena again (sortClause may
+			// have reordered literals)
+			rebuildWT(opts.simplify_priorbins);
+			std::vector<uint32_t> woff(inf.nDualVars + 1, 0);
+			std::vector<WATCH> wrec;
+			for (uint32 lit = 0; lit < inf.nDualVars; ++lit) {
+				woff[lit] = (uint32_t)wrec.size();
+				WL& ws = wt[lit];
+				for (uint32 k = 0; k < ws.size(); ++k) wrec.push_back(ws[k]);
+			}
+			woff[inf.nDualVars] = (uint32_t)wrec.size();
+			w.section("wtoff", woff.data(), woff.size() * sizeof(uint32_t));
+			w.section("wtrec", wrec.data(), wrec.size() * sizeof(WATCH));
+			w.section("cm2", cm.address(0), uint64_t(cm.size()) * sizeof(uint32));
+			uint64_t code = (uint64_t)opts.simplify_priorbins;
+			w.section("wtcode", &code, sizeof code);
 			w.close();
 		}
 		if (fulltiming && cmout.empty() && inf.unassigned && inf.nClauses) {

@@ -196,6 +196,16 @@ void be_dm_write(void *s, const uint32_t *tok, const uint32_t *term, uint32_t nc
                  const uint32_t *keptoff, const uint32_t *unitoff, const uint32_t *isunit, uint32_t *cm, unsigned long long *orgs, uint32_t *trail,
                  int8_t *value, uint8_t *state, unsigned long long *stats, uint32_t header_clauses, uint32_t *bad /* 4: too many clauses */);
 
+/* ---- rebuildWT (watch.cpp:135-157) on the device --------------------------------------------------------------------- */
+/* group of every clause of the exported SCNF in the attach order (0/1 flags per group) */
+void be_wt_groups(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t code, uint32_t *f0, uint32_t *f1, uint32_t *f2, uint32_t *f3);
+/* sortClause on the CLAUSE records + the scratch store of watched-literal pairs (one two-literal entry per clause, in
+ * attach order) + {ref, size, first ^ second} per entry; totals = the four group sizes (device) */
+void be_wt_fill(void *s, uint32_t *cm, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t code, const uint32_t *p0, const uint32_t *p1,
+                const uint32_t *p2, const uint32_t *p3, const uint32_t *totals, const int8_t *value, sg_u4 *hdr, uint32_t *lits, sg_u4 *winfo);
+/* WATCH records of every list from the occurrence table of the scratch store */
+void be_wt_records(void *s, uint32_t nlit, const uint32_t *ot_off, const uint32_t *ot_len, const uint32_t *ot_data, const sg_u4 *winfo, sg_u4 *rec);
+
 #ifdef __cplusplus
 }
 #endif

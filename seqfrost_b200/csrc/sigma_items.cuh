@@ -862,6 +862,47 @@ SG_HD void sg_cm_write(const uint32_t *src, uint32_t *dst, int lbd_tier1)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* rebuildWT (watch.cpp:135-157): sortClause + ATTACH_TWO_WATCHES for every clause of the new database  */
+/* ------------------------------------------------------------------------------------------ */
+/* sortClause(c, start, size, satonly) (clause.cpp:116-166) on the literals of a CLAUSE record; every assigned variable is
+ * assigned at the root here (the pass runs at decision level 0), so l2dl() is 0 for all of them */
+SG_HD int8_t sg_sort_clause_from(uint32_t *lits, int start, int size, bool satonly, const int8_t *value)
+{
+    const uint32_t x = lits[start];
+    int8_t xval = value[x];
+    if (xval < 0 || (xval && satonly)) return xval;
+    uint32_t best = x;
+    int pos = 0;
+    for (int i = start + 1; i < size; ++i) {
+        const uint32_t y = lits[i];
+        const int8_t yval = value[y];
+        if (yval < 0 || (yval && satonly)) { best = y; pos = i; xval = yval; break; }
+        bool better;
+        if (!xval && yval > 0) better = true;
+        else if (xval > 0 && !yval) better = false;
+        else better = false;                                  /* equal values: the levels decide, and they are all 0 */
+        if (better) { best = y; pos = i; xval = yval; }
+    }
+    if (!pos) return xval;
+    lits[start] = best;
+    lits[pos] = x;
+    return xval;
+}
+SG_HD void sg_sort_clause(uint32_t *lits, int size, const int8_t *value)
+{   /* clause.cpp:168-173 */
+    const int8_t val = sg_sort_clause_from(lits, 0, size, false, value);
+    if (size > 2) (void)sg_sort_clause_from(lits, 1, size, val != 0, value);       /* `const bool& satonly` bound to the LIT_ST */
+}
+/* the group of a clause in the order rebuildWT attaches them (watch.cpp:139-156): code bit 0 = binaries first,
+ * bit 1 = learnt binaries before original ones */
+SG_HD uint32_t sg_wt_group(bool binary, bool learnt, uint32_t code)
+{
+    if (!(code & 1u)) return learnt ? 1u : 0u;
+    if (binary) return (code & 2u) ? (learnt ? 0u : 1u) : (learnt ? 1u : 0u);
+    return learnt ? 3u : 2u;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* SUB: self-subsuming strengthening + backward subsumption (subsume.hpp:26-218, subsume.cpp:45-76) */
 /* ------------------------------------------------------------------------------------------ */
 SG_HD bool sg_sig_sub(uint32_t A, uint32_t B) { return !(A & ~B); }                 /* simplify.hpp:119 */

@@ -1927,6 +1927,57 @@ __global__ void k_dm_write(const uint32_t *__restrict__ tok, const uint32_t *__r
     if (threadIdx.x == 4 && s_st[4]) atomicMax(&stats[4], (unsigned long long)s_st[4]);
 }
 
+/* ---------------------------------------------------------------------------------------------- */
+/* rebuildWT (watch.cpp:135-157) from the CLAUSE records built by k_cm_write                          */
+/* ---------------------------------------------------------------------------------------------- */
+__global__ void k_wt_groups(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n, uint32_t code,
+                            uint32_t *__restrict__ f0, uint32_t *__restrict__ f1, uint32_t *__restrict__ f2, uint32_t *__restrict__ f3)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t *src = arena + refs[i];
+    const uint32_t g = sg_wt_group(src[2] == 2u, (src[0] & SG_ST_MASK) == SG_LEARNT, code);
+    f0[i] = g == 0; f1[i] = g == 1; f2[i] = g == 2; f3[i] = g == 3;
+}
+/* clause i becomes entry `seq` of the attach order: sortClause on its record, then its two watched literals as a
+ * two-literal "clause" of a scratch store, so that the occurrence-table build (stable by entry number) yields the watch
+ * lists in push order */
+__global__ void k_wt_fill(uint32_t *__restrict__ cm, const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
+                          uint32_t code, const uint32_t *__restrict__ p0, const uint32_t *__restrict__ p1, const uint32_t *__restrict__ p2,
+                          const uint32_t *__restrict__ p3, const uint32_t *__restrict__ totals, const int8_t *__restrict__ value,
+                          uint4 *__restrict__ hdr, uint32_t *__restrict__ lits, uint4 *__restrict__ winfo)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long r = refs[i];
+    const uint32_t *src = arena + r;
+    const uint32_t size = src[2];
+    const uint32_t g = sg_wt_group(size == 2u, (src[0] & SG_ST_MASK) == SG_LEARNT, code);
+    uint32_t seq = g == 0 ? p0[i] : g == 1 ? p1[i] : g == 2 ? p2[i] : p3[i];
+    if (g > 0) seq += totals[0];
+    if (g > 1) seq += totals[1];
+    if (g > 2) seq += totals[2];
+    const unsigned long long cref = r + i;
+    uint32_t *l = cm + cref + SG_CM_HDR;
+    if (size != 2u) sg_sort_clause(l, (int)size, value);               /* attachNonBins / attachClauses: if (!c.binary()) sortClause(c) */
+    const uint32_t a = l[0], b = l[1];
+    hdr[seq] = make_uint4(2u * seq, 2u, 0u, 0u);
+    lits[2 * seq] = SG_FLIP(a); lits[2 * seq + 1] = SG_FLIP(b);        /* ATTACH_TWO_WATCHES: wt[FLIP(first)], wt[FLIP(second)] */
+    winfo[seq] = make_uint4((uint32_t)cref, (uint32_t)(cref >> 32), size, a ^ b);
+}
+/* WATCH {C_REF ref; uint32 imp; int size} (watch.hpp:28-46) for every entry of every list; imp = the other watched literal */
+__global__ void k_wt_records(uint32_t nlit, const uint32_t *__restrict__ ot_off, const uint32_t *__restrict__ ot_len, const uint32_t *__restrict__ ot_data,
+                             const uint4 *__restrict__ winfo, uint4 *__restrict__ rec)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit >= nlit) return;
+    const uint32_t o = ot_off[lit], m = ot_len[lit];
+    for (uint32_t k = 0; k < m; ++k) {
+        const uint4 w = winfo[ot_data[o + k]];
+        rec[o + k] = make_uint4(w.x, w.y, w.w ^ SG_FLIP(lit), w.z);      /* a ^ b ^ watched = the other one */
+    }
+}
+
 } // namespace
 
 /* ================================================================================================ */
@@ -2451,4 +2502,19 @@ void be_dm_write(void *s, const uint32_t *tok, const uint32_t *term, uint32_t nc
 {
     if (ncl) LAUNCH(k_dm_write, blocks_for(ncl), TPB, s, tok, term, ncl, utime, csize, wordoff, keptoff, unitoff, isunit, cm, orgs, trail, value, state, stats,
                     header_clauses, bad);
+}
+
+/* ---- rebuildWT launches ------------------------------------------------------------------------------ */
+void be_wt_groups(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t code, uint32_t *f0, uint32_t *f1, uint32_t *f2, uint32_t *f3)
+{
+    if (n) LAUNCH(k_wt_groups, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, code, f0, f1, f2, f3);
+}
+void be_wt_fill(void *s, uint32_t *cm, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t code, const uint32_t *p0, const uint32_t *p1,
+                const uint32_t *p2, const uint32_t *p3, const uint32_t *totals, const int8_t *value, sg_u4 *hdr, uint32_t *lits, sg_u4 *winfo)
+{
+    if (n) LAUNCH(k_wt_fill, blocks_for(n), TPB, s, cm, arena, (const unsigned long long *)refs, n, code, p0, p1, p2, p3, totals, value, (uint4 *)hdr, lits, (uint4 *)winfo);
+}
+void be_wt_records(void *s, uint32_t nlit, const uint32_t *ot_off, const uint32_t *ot_len, const uint32_t *ot_data, const sg_u4 *winfo, sg_u4 *rec)
+{
+    if (nlit) LAUNCH(k_wt_records, blocks_for(nlit), TPB, s, nlit, ot_off, ot_len, ot_data, (const uint4 *)winfo, (uint4 *)rec);
 }

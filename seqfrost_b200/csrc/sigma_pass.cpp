@@ -89,6 +89,8 @@ struct sigma_ctx {
     DBuf<uint32_t> dm_utime, dm_utime2, dm_csize, dm_words, dm_kept, dm_isunit, dm_wordoff, dm_keptoff, dm_unitoff, dm_cm, dm_trail;
     DBuf<uint64_t> dm_orgs, dm_stats; DBuf<uint32_t> dm_vorg;
     bool dm_parsed = false; sigma_dimacs dm_out;
+    DBuf<uint32_t> wt_flags, wt_pos; DBuf<sg_u4> wt_info, wt_rec;                             /* sigma_watches_* */
+    int wt_code = -1; uint64_t wt_records = 0;
     bool cm_built = false; uint32_t cm_learnts = 0; uint64_t cm_lits_org = 0, cm_lits_learnt = 0, cm_last_ref = 0;
     SgScalars hsc;                  /* host mirror */
     uint32_t *h_totals = nullptr;   /* pinned */
@@ -1172,7 +1174,7 @@ int sigma_execute(sigma_ctx *c)
     c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
     c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
     c->evused = 0; c->evs.clear();
-    c->executed = false; c->cm_built = false; c->stopped = false;
+    c->executed = false; c->cm_built = false; c->stopped = false; c->wt_code = -1;
     c->ot_valid = false;
     { const char *e = getenv("SIGMA_OT_INCREMENTAL"); c->ot_incremental = !(e && e[0] == '0'); }
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
@@ -1263,6 +1265,50 @@ int build_cm(sigma_ctx *c)
     return SIGMA_OK;
 }
 
+/* rebuildWT(code) on the device (watch.cpp:135-157), from the CLAUSE records of build_cm: sortClause on every non-binary
+ * record, then the watch lists as a stable counting sort of (watched literal, position in the attach order) - the same
+ * two-level partition that builds the occurrence table, run on a scratch store of one two-literal entry per clause */
+int build_watches(sigma_ctx *c, uint32_t code)
+{
+    CK(build_cm(c));
+    if (c->wt_code == (int)code) return SIGMA_OK;
+    if (c->wt_code >= 0) { c->cm_built = false; CK(build_cm(c)); }      /* another order was built before: sortClause starts from the records as written */
+    const uint32_t n = c->out_ncls, nlit = c->nlit;
+    NOMEM(c->wt_flags.ensure(4 * (size_t)n + 64)); NOMEM(c->wt_pos.ensure(4 * (size_t)n + 64)); NOMEM(c->wt_info.ensure((size_t)n + 16));
+    NOMEM(c->wt_rec.ensure(2 * (size_t)n + 16)); NOMEM(c->hdr2.ensure((size_t)n + 16)); NOMEM(c->lits2.ensure(2 * (size_t)n + 16));
+    NOMEM(c->scantmp.ensure(4 * be_scan_tmp_words(n) + 64));
+    const sigma_report keep = c->rep;
+    void *e0 = get_event(c), *e1 = get_event(c);
+    be_event_record(c->stream, e0);
+    if (n) {
+        uint32_t *f = c->wt_flags.p, *p = c->wt_pos.p;
+        be_wt_groups(c->stream, c->arena_out.p, c->refs_out.p, n, code, f, f + n, f + 2 * (size_t)n, f + 3 * (size_t)n);
+        SgScanSet ss = { { f, f + n, f + 2 * (size_t)n, f + 3 * (size_t)n }, { p, p + n, p + 2 * (size_t)n, p + 3 * (size_t)n },
+                         { c->totals.p + 16, c->totals.p + 17, c->totals.p + 18, c->totals.p + 19 } };
+        be_scan_multi(c->stream, ss, 4, n, c->scantmp.p);
+        be_wt_fill(c->stream, c->cm_out.p, c->arena_out.p, c->refs_out.p, n, code, p, p + n, p + 2 * (size_t)n, p + 3 * (size_t)n, c->totals.p + 16,
+                   c->value.p, c->hdr2.p, c->lits2.p, c->wt_info.p);
+        /* the occurrence table of the scratch store = the watch lists (entries ascending = push order) */
+        { DBuf<sg_u4> t = c->hdr; c->hdr = c->hdr2; c->hdr2 = t; }
+        { DBuf<uint32_t> t = c->lits; c->lits = c->lits2; c->lits2 = t; }
+        const uint32_t s_ncls = c->n_cls, s_pool = c->pool_used;
+        const bool s_verify = c->ot_verify;
+        c->n_cls = n; c->pool_used = 2 * n; c->ot_verify = false;
+        const int rc = stage_create_ot(c, 2ull * n, n, false);
+        c->n_cls = s_ncls; c->pool_used = s_pool; c->ot_verify = s_verify; c->ot_valid = false;
+        { DBuf<sg_u4> t = c->hdr; c->hdr = c->hdr2; c->hdr2 = t; }
+        { DBuf<uint32_t> t = c->lits; c->lits = c->lits2; c->lits2 = t; }
+        if (rc != SIGMA_OK) { c->rep = keep; return rc; }
+        be_wt_records(c->stream, nlit, c->ot_off.p, c->ot_len.p, c->ot_data.p, c->wt_info.p, c->wt_rec.p);
+    } else be_memset(c->stream, c->ot_off.p, 0, ((size_t)nlit + 1) * 4);
+    be_event_record(c->stream, e1);
+    if (ctx_sync(c)) { c->rep = keep; return SIGMA_E_CUDA; }
+    c->rep = keep;
+    c->rep.reserved32[0] = (uint32_t)(1000.0f * be_event_ms(e0, e1));
+    c->wt_code = (int)code; c->wt_records = 2ull * n;
+    return SIGMA_OK;
+}
+
 int download_impl(sigma_ctx *c, sigma_formula *out, sigma_cnf_out *cnf)
 {
     if (!c || !out) return SIGMA_E_ARG;
@@ -1328,6 +1374,32 @@ int sigma_cnf_out_sizes(sigma_ctx *c, sigma_cnf_out *sz)
     CK(build_cm(c));
     sz->cm_buckets = c->out_buckets + c->out_ncls; sz->n_learnts = c->cm_learnts; sz->n_orgs = c->out_ncls - c->cm_learnts;
     sz->lits_original = c->cm_lits_org; sz->lits_learnt = c->cm_lits_learnt; sz->last_ref = c->cm_last_ref;
+    return SIGMA_OK;
+}
+
+int sigma_watches_sizes(sigma_ctx *c, int priorbins, sigma_watches *sz)
+{
+    if (!c || !sz || priorbins < 0 || priorbins > 3) return SIGMA_E_ARG;
+    if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    be_bind(c->device);
+    CK(build_watches(c, (uint32_t)priorbins));
+    sz->nlit = c->nlit; sz->n_records = c->wt_records;
+    return SIGMA_OK;
+}
+
+int sigma_download_watches(sigma_ctx *c, sigma_watches *out)
+{
+    if (!c || !out) return SIGMA_E_ARG;
+    if (!c->executed || c->wt_code < 0) return fail(c, SIGMA_E_ARG, "sigma_download_watches without sigma_watches_sizes");
+    be_bind(c->device);
+    const bool small = out->offs_cap < (uint64_t)c->nlit + 1 || out->records_cap < c->wt_records;
+    out->nlit = c->nlit; out->n_records = c->wt_records;
+    if (small) return fail(c, SIGMA_E_NOSPACE, "watch buffers too small (required sizes filled in)");
+    if (!out->offs || (c->wt_records && !out->records)) return fail(c, SIGMA_E_ARG, "null output array");
+    be_d2h(c->stream, out->offs, c->ot_off.p, (size_t)c->nlit * 4);
+    if (c->wt_records) be_d2h(c->stream, out->records, c->wt_rec.p, c->wt_records * 16);
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
+    out->offs[c->nlit] = (uint32_t)c->wt_records;
     return SIGMA_OK;
 }
 

@@ -31,6 +31,10 @@ class SigmaSolver : public Solver {
 	std::vector<uint8_t> st;
 	int64 clausesBefore = 0, literalsBefore = 0;      // inf.nClauses / inf.nLiterals after extract()
 	bool newBeginningDone = false;                    // cm / orgs / learnts already hold the simplified formula
+	bool watchesDone = false;                         // ... and wt holds what rebuildWT(opts.simplify_priorbins) would build
+	std::vector<uint32_t> wtoffs;                     // sigma_download_watches: list offsets and the WATCH records
+	struct WatchRec { uint64_t ref; uint32_t imp; int32_t size; };
+	std::vector<WatchRec> wtrecs;
 
 	// Options the device pass does not cover are refused once, before any solving, instead of ending a solve half way
 	// (sigma_execute would answer SIGMA_E_UNSUPPORTED for them).
@@ -147,6 +151,7 @@ public:
 		// the CLAUSE records, orgs and learnts arrive ready-made
 		const char* hn = getenv("SIGMA_HOST_NEWBEGINNING");
 		newBeginningDone = false;
+		watchesDone = false;
 		if (!(hn && hn[0] == '1') && inf.unassigned && inf.nClauses && !canMap() && !opts.aggr_cnf_sort) {
 			sigma_cnf_out co = {};
 			rc = sigma_cnf_out_sizes(ctx, &co);
@@ -164,9 +169,34 @@ public:
 			const char* hr = getenv("SIGMA_HOST_REGISTER");
 			const bool pin = !(hr && hr[0] == '0') && co.cm_buckets >= (1u << 20);
 			const bool pinned = pin && sigma_host_register(co.cm, co.cm_buckets * sizeof(uint32_t)) == SIGMA_OK;
+			// rebuildWT(opts.simplify_priorbins) (simplify.cpp:218) on the device as well: it runs sortClause on the CLAUSE records,
+			// so it comes before they are copied back
+			const char* hw = getenv("SIGMA_HOST_REBUILDWT");
+			sigma_watches ws = {};
+			const bool deviceWT = !(hw && hw[0] == '1') && sigma_watches_sizes(ctx, opts.simplify_priorbins, &ws) == SIGMA_OK;
 			rc = sigma_download_cnf(ctx, &co, &out);
 			if (pinned) sigma_host_unregister(co.cm);
 			if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_cnf");
+			watchesDone = false;
+			if (deviceWT) {
+				wtoffs.resize(ws.nlit + 1);
+				wtrecs.resize(ws.n_records ? ws.n_records : 1);
+				ws.offs = wtoffs.data(); ws.offs_cap = wtoffs.size();
+				ws.records = wtrecs.data(); ws.records_cap = wtrecs.size();
+				rc = sigma_download_watches(ctx, &ws);
+				if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_watches");
+				// the lists arrive ready-made, in push order; Vec<WATCH> by Vec<WATCH> (solvetypes.hpp:31-32)
+				wt.resize(inf.nDualVars);
+				for (uint32 lit = 0; lit < inf.nDualVars && lit < ws.nlit; ++lit) {
+					const uint32 n = wtoffs[lit + 1] - wtoffs[lit];
+					WL& list = wt[lit];
+					list.clear();
+					if (!n) continue;
+					list.resize(n);
+					memcpy((WATCH*)list, &wtrecs[wtoffs[lit]], size_t(n) * sizeof(WATCH));
+				}
+				watchesDone = true;
+			}
 			for (uint32 v = 1; v <= V; ++v) if (sub[v]) sp->state[v].subsume = 1;   // mark_ssubsume, sclause.hpp:209-215
 			stats.literals.original = co.lits_original; stats.literals.learnt = co.lits_learnt;
 			stats.clauses.original = orgs.size(); stats.clauses.learnt = learnts.size();
@@ -247,7 +277,7 @@ public:
 		if (newBeginningDone) { /* simplify.cpp:216 happened on the device */ }
 		else if (canMap()) map(true);
 		else newBeginning();
-		rebuildWT(opts.simplify_priorbins);
+		if (!(newBeginningDone && watchesDone)) rebuildWT(opts.simplify_priorbins);
 		if (retrail()) LOG2(2, " Propagation after simplify proved a contradiction");
 		UPDATE_SLEEPER(simplify, success);
 		printStats(1, 's', CGREEN);

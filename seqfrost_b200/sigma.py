@@ -77,6 +77,12 @@ class SigmaDimacs(C.Structure):
                 ("body_offset", C.c_uint64), ("h2d_ms", C.c_float), ("device_ms", C.c_float)]
 
 
+class SigmaWatches(C.Structure):
+    """sigma_watches (include/sigma_b200.h)."""
+    _fields_ = [("offs", C.c_void_p), ("offs_cap", C.c_uint64), ("records", C.c_void_p), ("records_cap", C.c_uint64),
+                ("n_records", C.c_uint64), ("nlit", C.c_uint32)]
+
+
 class SigmaReport(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("phases_run", C.c_int32), ("n_clauses", C.c_uint32), ("max_melted_delta", C.c_uint32),
@@ -137,6 +143,8 @@ def load(path=None):
     lib.sigma_parse_dimacs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SigmaDimacs)]
     lib.sigma_parse_download.argtypes = [C.c_void_p, C.POINTER(SigmaDimacs)]
     lib.sigma_upload_parsed.argtypes = [C.c_void_p, C.POINTER(SigmaOpts)]
+    lib.sigma_watches_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(SigmaWatches)]
+    lib.sigma_download_watches.argtypes = [C.c_void_p, C.POINTER(SigmaWatches)]
     lib.sigma_execute.argtypes = [C.c_void_p]
     lib.sigma_result_sizes.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
     lib.sigma_download.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
@@ -380,6 +388,16 @@ class Sigma:
         self._check(self.lib.sigma_upload_parsed(self.ctx, C.byref(o)))
         src = B.Boundary(nvars=nvars or 0, vorg=None if nvars is None else np.arange(nvars + 1, dtype=np.uint32), opts=dict(B.DEFAULT_OPTS, **(opts or {})))
         self._keep = (src, o, None)
+
+    def watches(self, priorbins=1):
+        """rebuildWT(priorbins) on the device; call before download_cnf.  Returns (offs uint32[nlit + 1], records uint32[n, 4] =
+        {ref lo, ref hi, imp, size})."""
+        w = SigmaWatches()
+        self._check(self.lib.sigma_watches_sizes(self.ctx, int(priorbins), C.byref(w)))
+        offs, rec = np.empty(w.nlit + 1, np.uint32), np.empty((int(w.n_records), 4), np.uint32)
+        w.offs, w.offs_cap, w.records, w.records_cap = _ptr(offs), offs.size, _ptr(rec), int(w.n_records)
+        self._check(self.lib.sigma_download_watches(self.ctx, C.byref(w)))
+        return offs, rec
 
     def set_interrupt_flag(self, flag):
         """`flag`: a one-byte numpy array the caller may set to non-zero from another thread / a signal handler (the

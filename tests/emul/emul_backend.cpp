@@ -577,3 +577,46 @@ void be_dm_write(void *, const uint32_t *tok, const uint32_t *term, uint32_t ncl
         }
     }
 }
+
+/* ---- rebuildWT --------------------------------------------------------------------------------------------------- */
+void be_wt_groups(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t code, uint32_t *f0, uint32_t *f1, uint32_t *f2, uint32_t *f3)
+{
+    g_launches++;
+    for (uint32_t i : item_order(n)) {
+        const uint32_t *src = arena + refs[i];
+        const uint32_t g = sg_wt_group(src[2] == 2u, (src[0] & SG_ST_MASK) == SG_LEARNT, code);
+        f0[i] = g == 0; f1[i] = g == 1; f2[i] = g == 2; f3[i] = g == 3;
+    }
+}
+void be_wt_fill(void *, uint32_t *cm, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t code, const uint32_t *p0, const uint32_t *p1,
+                const uint32_t *p2, const uint32_t *p3, const uint32_t *totals, const int8_t *value, sg_u4 *hdr, uint32_t *lits, sg_u4 *winfo)
+{
+    g_launches++;
+    for (uint32_t i : item_order(n)) {
+        const uint64_t r = refs[i];
+        const uint32_t *src = arena + r;
+        const uint32_t size = src[2];
+        const uint32_t g = sg_wt_group(size == 2u, (src[0] & SG_ST_MASK) == SG_LEARNT, code);
+        uint32_t seq = g == 0 ? p0[i] : g == 1 ? p1[i] : g == 2 ? p2[i] : p3[i];
+        if (g > 0) seq += totals[0];
+        if (g > 1) seq += totals[1];
+        if (g > 2) seq += totals[2];
+        const uint64_t cref = r + i;
+        uint32_t *l = cm + cref + SG_CM_HDR;
+        if (size != 2u) sg_sort_clause(l, (int)size, value);
+        const uint32_t a = l[0], b = l[1];
+        hdr[seq].x = 2u * seq; hdr[seq].y = 2u; hdr[seq].z = 0u; hdr[seq].w = 0u;
+        lits[2 * seq] = SG_FLIP(a); lits[2 * seq + 1] = SG_FLIP(b);
+        winfo[seq].x = (uint32_t)cref; winfo[seq].y = (uint32_t)(cref >> 32); winfo[seq].z = size; winfo[seq].w = a ^ b;
+    }
+}
+void be_wt_records(void *, uint32_t nlit, const uint32_t *ot_off, const uint32_t *ot_len, const uint32_t *ot_data, const sg_u4 *winfo, sg_u4 *rec)
+{
+    g_launches++;
+    for (uint32_t lit : item_order(nlit))
+        for (uint32_t k = 0; k < ot_len[lit]; ++k) {
+            const sg_u4 w = winfo[ot_data[ot_off[lit] + k]];
+            sg_u4 &o = rec[ot_off[lit] + k];
+            o.x = w.x; o.y = w.y; o.z = w.w ^ SG_FLIP(lit); o.w = w.z;
+        }
+}

@@ -192,3 +192,72 @@ def test_gpu_extract_at_scale(cuda_lib):
     idx = np.repeat(ref + 4 - off[:-1], sz) + np.arange(int(off[-1]), dtype=np.int64)
     assert np.array_equal(out.cm[idx], lits)
     s.close()
+
+
+# ---- rebuildWT on the device (reference watch.cpp:135-157): the .cmo fixtures also carry the reference's watch table --------
+def _read_sections(path):
+    import struct
+    with open(path, "rb") as f:
+        blob = f.read()
+    pos, sec = 8, {}
+    while pos < len(blob):
+        name = blob[pos:pos + 8].rstrip(b"\0").decode()
+        (n,) = struct.unpack_from("<Q", blob, pos + 8)
+        sec[name] = blob[pos + 16:pos + 16 + n]
+        pos += 16 + n
+    return sec
+
+
+def _check_watches(s, name):
+    sec = _read_sections(os.path.join(GOLDEN, name + ".cmo"))
+    code = int(np.frombuffer(sec["wtcode"], np.uint64)[0])
+    woff, wrec = np.frombuffer(sec["wtoff"], np.uint32), np.frombuffer(sec["wtrec"], np.uint32).reshape(-1, 4)
+    offs, rec = s.watches(code)
+    assert np.array_equal(offs, woff), name
+    assert np.array_equal(rec, wrec), name                                   # {ref, imp, size} of every list, in push order
+    exp = B.read_clause_db(os.path.join(GOLDEN, name + ".cmo"))
+    cm2 = np.frombuffer(sec["cm2"], np.uint32)
+    db, _ = s.download_cnf()                                                 # after the watch build: sortClause has run
+    mask = np.full(cm2.size, 0xFFFFFFFF, dtype=np.uint32)
+    mask[np.concatenate([exp.orgs, exp.learnts]).astype(np.int64)] = 0xFFFFFF3F
+    assert np.array_equal(db.cm & mask, cm2 & mask), name
+    # the other attach orders against a direct restatement over the downloaded records
+    for other in (0, 1, 3):
+        offs2, rec2 = s.watches(other)
+        db2, _ = s.download_cnf()
+        lists = [[] for _ in range(offs2.size - 1)]
+        groups = {}
+        for learnt, refs in ((0, db2.orgs), (1, db2.learnts)):
+            for r in refs.astype(np.int64).tolist():
+                size = int(db2.cm[r + 1])
+                g = (learnt if not other & 1 else ((learnt ^ 1 if other & 2 else learnt) if size == 2 else 2 + learnt))
+                groups.setdefault(g, []).append(r)
+        for g in sorted(groups):
+            for r in groups[g]:
+                size, a, b = int(db2.cm[r + 1]), int(db2.cm[r + 4]), int(db2.cm[r + 5])
+                lists[a ^ 1].append((r & 0xFFFFFFFF, r >> 32, b, size))
+                lists[b ^ 1].append((r & 0xFFFFFFFF, r >> 32, a, size))
+        flat = [w for l in lists for w in l]
+        assert np.array_equal(rec2, np.array(flat, dtype=np.uint32).reshape(-1, 4)), (name, other)
+        assert offs2.tolist() == np.concatenate([[0], np.cumsum([len(l) for l in lists])]).tolist()
+
+
+def test_emul_watch_table_matches_reference(emul_lib):
+    s = sigma.Sigma(0, emul_lib)
+    for name in CM_CASES:
+        db, bi, _ = _load(name)
+        s.upload_cnf(db, bi)
+        s.execute()
+        _check_watches(s, name)
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_watch_table_matches_reference(cuda_lib):
+    s = sigma.Sigma(0, cuda_lib)
+    for name in CM_CASES:
+        db, bi, _ = _load(name)
+        s.upload_cnf(db, bi)
+        s.execute()
+        _check_watches(s, name)
+    s.close()
