@@ -19,14 +19,41 @@
 #include "version.hpp"
 #include "../../include/sigma_b200.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace SeqFROST {
 
-class SigmaSolver : public Solver {
+// The device context is created on a helper thread that starts BEFORE the reference's constructor runs (a base class is
+// constructed first): CUDA initialisation and loading the kernels take about a second, the parser next to it several.
+struct SigmaCtxStarter {
+	sigma_ctx* early = nullptr;
+	int earlyrc = SIGMA_OK;
+	std::thread starter;
+	SigmaCtxStarter() {
+		const char* lazy = getenv("SIGMA_LAZY_CREATE");
+		if (lazy && lazy[0] == '1') return;
+		starter = std::thread([this]() {
+			const char* dev = getenv("SIGMA_DEVICE");
+			earlyrc = sigma_create(dev ? atoi(dev) : 0, &early);
+		});
+	}
+	~SigmaCtxStarter() { if (starter.joinable()) starter.join(); if (early) sigma_destroy(early); }
+	// hands the context over (once); nullptr when it was not started here
+	sigma_ctx* take(int& rc) {
+		if (starter.joinable()) starter.join();
+		sigma_ctx* c = early;
+		early = nullptr;
+		rc = earlyrc;
+		return c;
+	}
+};
+
+class SigmaSolver : private SigmaCtxStarter, public Solver {
 	sigma_ctx* ctx = nullptr;
 	std::vector<uint8_t> st;
 	int64 clausesBefore = 0, literalsBefore = 0;      // inf.nClauses / inf.nLiterals after extract()
@@ -35,6 +62,17 @@ class SigmaSolver : public Solver {
 	std::vector<uint32_t> wtoffs;                     // sigma_download_watches: list offsets and the WATCH records
 	struct WatchRec { uint64_t ref; uint32_t imp; int32_t size; };
 	std::vector<WatchRec> wtrecs;
+
+	// SIGMA_BINDING_TIMES=1: wall-clock split of one simplifying() call on stderr (where the host side of the drop-in goes)
+	std::chrono::steady_clock::time_point tmark;
+	bool timesOn = false;
+	void tstart() { const char* e = getenv("SIGMA_BINDING_TIMES"); timesOn = e && e[0] == '1'; tmark = std::chrono::steady_clock::now(); }
+	void tsplit(const char* what) {
+		if (!timesOn) return;
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "c sigma_b200 time: %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tmark).count());
+		tmark = now;
+	}
 
 	// Options the device pass does not cover are refused once, before any solving, instead of ending a solve half way
 	// (sigma_execute would answer SIGMA_E_UNSUPPORTED for them).
@@ -68,12 +106,17 @@ public:
 	// simplify.cpp:180-210 on the GPU.  Inputs and outputs are the reference's own objects.
 	void sigmaPass(const bool deviceExtract) {
 		if (!ctx) {
-			const char* dev = getenv("SIGMA_DEVICE");
-			const int rc = sigma_create(dev ? atoi(dev) : 0, &ctx);
+			int rc = SIGMA_OK;
+			ctx = take(rc);                                    // started next to the parser
+			if (!ctx && rc == SIGMA_OK) {
+				const char* dev = getenv("SIGMA_DEVICE");
+				rc = sigma_create(dev ? atoi(dev) : 0, &ctx);
+			}
 			if (rc != SIGMA_OK) sigmaFail(rc, "sigma_create");
 			// INTERRUPTED polls (simplify.cpp:176,206; subsume.cpp:26; bounded.cpp:31): the pass reads the solver's own flag,
 			// which Solver::interrupt() sets from the signal handlers (control.cpp:137-149)
 			sigma_set_interrupt_flag(ctx, (const volatile unsigned char*)&interrupted);
+			tsplit("sigma_create");
 		}
 		sigma_opts o;
 		sigma_default_opts(&o);
@@ -113,9 +156,11 @@ public:
 			for (uint32 i = 0; i < orgs.size(); ++i) if (orgs[i] >= top) top = orgs[i] + 1;
 			for (uint32 i = 0; i < learnts.size(); ++i) if (learnts[i] >= top) top = learnts[i] + 1;
 			db.stencil = (const uint8_t*)cm.stencil(); db.stencil_size = top;
-			// the clause arena is malloc'ed (pageable): pinned for the duration of the copy, so that it runs at PCIe rate
+			// the clause arena is malloc'ed (pageable)
 			const char* hr = getenv("SIGMA_HOST_REGISTER");
-			const bool pin = !(hr && hr[0] == '0') && db.cm_buckets >= (1u << 20);
+			// (SIGMA_HOST_REGISTER=1: pin it for the copy.  Off by default: registering and unregistering 400 MB costs about a second,
+			// the copy from pageable memory 30 ms)
+			const bool pin = hr && hr[0] == '1' && db.cm_buckets >= (1u << 20);
 			const bool pinned = pin && sigma_host_register((void*)db.cm, db.cm_buckets * sizeof(uint32_t)) == SIGMA_OK;
 			rc = sigma_upload_cnf(ctx, &o, &db, &in);
 			if (pinned) sigma_host_unregister((void*)db.cm);
@@ -130,7 +175,9 @@ public:
 		}
 		else rc = sigma_upload(ctx, &o, &in);
 		clausesBefore = inf.nClauses; literalsBefore = inf.nLiterals;
+		tsplit("upload (+ device extract)");
 		if (rc == SIGMA_OK) rc = sigma_execute(ctx);
+		tsplit("sigma_execute");
 		if (rc == SIGMA_UNSAT) { learnEmpty(); killSolver(); }           // propelim.cpp:60, subsume.cpp:66, bounded.cpp:74
 		if (rc == SIGMA_INTERRUPTED) killSolver();                        // simplify.cpp:206, subsume.cpp:26, bounded.cpp:31
 		if (rc != SIGMA_OK) sigmaFail(rc, "pass");
@@ -167,14 +214,17 @@ public:
 			co.learnts = learnts.size() ? (uint64_t*)learnts.data() : (uint64_t*)st.data(); co.learnts_cap = co.n_learnts;
 			co.subsume = sub.data();
 			const char* hr = getenv("SIGMA_HOST_REGISTER");
-			const bool pin = !(hr && hr[0] == '0') && co.cm_buckets >= (1u << 20);
+			const bool pin = hr && hr[0] == '1' && co.cm_buckets >= (1u << 20);
 			const bool pinned = pin && sigma_host_register(co.cm, co.cm_buckets * sizeof(uint32_t)) == SIGMA_OK;
 			// rebuildWT(opts.simplify_priorbins) (simplify.cpp:218) on the device as well: it runs sortClause on the CLAUSE records,
 			// so it comes before they are copied back
 			const char* hw = getenv("SIGMA_HOST_REBUILDWT");
 			sigma_watches ws = {};
+			tsplit("cm.init + bulk alloc");
 			const bool deviceWT = !(hw && hw[0] == '1') && sigma_watches_sizes(ctx, opts.simplify_priorbins, &ws) == SIGMA_OK;
+			tsplit("device newBeginning + rebuildWT");
 			rc = sigma_download_cnf(ctx, &co, &out);
+			tsplit("sigma_download_cnf");
 			if (pinned) sigma_host_unregister(co.cm);
 			if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_cnf");
 			watchesDone = false;
@@ -185,6 +235,7 @@ public:
 				ws.records = wtrecs.data(); ws.records_cap = wtrecs.size();
 				rc = sigma_download_watches(ctx, &ws);
 				if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_watches");
+				tsplit("sigma_download_watches");
 				// the lists arrive ready-made, in push order; Vec<WATCH> by Vec<WATCH> (solvetypes.hpp:31-32)
 				wt.resize(inf.nDualVars);
 				for (uint32 lit = 0; lit < inf.nDualVars && lit < ws.nlit; ++lit) {
@@ -196,6 +247,7 @@ public:
 					memcpy((WATCH*)list, &wtrecs[wtoffs[lit]], size_t(n) * sizeof(WATCH));
 				}
 				watchesDone = true;
+				tsplit("watch lists into wt");
 			}
 			for (uint32 v = 1; v <= V; ++v) if (sub[v]) sp->state[v].subsume = 1;   // mark_ssubsume, sclause.hpp:209-215
 			stats.literals.original = co.lits_original; stats.literals.learnt = co.lits_learnt;
@@ -259,8 +311,10 @@ public:
 		if (!opts.profile_simplifier) timer.start();
 		const char* he = getenv("SIGMA_HOST_EXTRACT");
 		const bool deviceExtract = !(he && he[0] == '1');
+		tstart();
 		if (deviceExtract) sigmaAwaken();
 		else awaken();
+		tsplit("awaken (host part)");
 		if (simpstate == AWAKEN_FAIL) { recycle(); return; }
 		if (INTERRUPTED) killSolver();
 		const int64 bmelted = inf.maxMelted;
@@ -277,8 +331,11 @@ public:
 		if (newBeginningDone) { /* simplify.cpp:216 happened on the device */ }
 		else if (canMap()) map(true);
 		else newBeginning();
+		tsplit("state / statistics");
 		if (!(newBeginningDone && watchesDone)) rebuildWT(opts.simplify_priorbins);
+		tsplit("host rebuildWT (if any)");
 		if (retrail()) LOG2(2, " Propagation after simplify proved a contradiction");
+		tsplit("retrail");
 		UPDATE_SLEEPER(simplify, success);
 		printStats(1, 's', CGREEN);
 		if (!opts.profile_simplifier) timer.stop(), timer.simplify += timer.cpuTime();
