@@ -93,13 +93,20 @@ class SigmaSolver : private SigmaCtxStarter, public Solver {
 public:
 	explicit SigmaSolver(const std::string& path) : Solver(path) { checkSupportedOptions(); }
 	SigmaSolver() : Solver() { checkSupportedOptions(); }     // incremental constructor (solveinc.cpp:26-49)
-	~SigmaSolver() { if (ctx) { sigma_destroy(ctx); ctx = nullptr; } }
+	~SigmaSolver() { if (wtFreer.joinable()) wtFreer.join(); if (ctx) { sigma_destroy(ctx); ctx = nullptr; } }
 
 	// awaken() (simplify.cpp:135-153) without extract(): the SCNF and the occurrence table live on the device
+	// wt.clear(true) (simplify.cpp:140) frees millions of small watch vectors - more than half a second on the 10M-clause
+	// instance.  The table is handed to a helper thread that frees it while the copies and the pass run; the solver's `wt` is
+	// empty from here on, exactly as after the reference's call.
+	WT oldwt;
+	std::thread wtFreer;
 	void sigmaAwaken() {
 		printStats(1, '-', CGREEN0);
 		initSimp();
-		wt.clear(true);
+		if (wtFreer.joinable()) wtFreer.join();
+		wt.migrateTo(oldwt);                               // wt: no memory, size 0 == wt.clear(true)
+		wtFreer = std::thread([this]() { oldwt.clear(true); });
 		inf.nClauses = inf.nLiterals = 0;
 	}
 
@@ -236,16 +243,24 @@ public:
 				rc = sigma_download_watches(ctx, &ws);
 				if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_watches");
 				tsplit("sigma_download_watches");
-				// the lists arrive ready-made, in push order; Vec<WATCH> by Vec<WATCH> (solvetypes.hpp:31-32)
+				// the lists arrive ready-made, in push order; Vec<WATCH> by Vec<WATCH> (solvetypes.hpp:31-32), a few host threads
+				// side by side (one allocation per list)
 				wt.resize(inf.nDualVars);
-				for (uint32 lit = 0; lit < inf.nDualVars && lit < ws.nlit; ++lit) {
-					const uint32 n = wtoffs[lit + 1] - wtoffs[lit];
-					WL& list = wt[lit];
-					list.clear();
-					if (!n) continue;
-					list.resize(n);
-					memcpy((WATCH*)list, &wtrecs[wtoffs[lit]], size_t(n) * sizeof(WATCH));
-				}
+				const uint32 nl = inf.nDualVars < ws.nlit ? inf.nDualVars : ws.nlit;
+				auto fill = [this](const uint32 lo, const uint32 hi) {
+					for (uint32 lit = lo; lit < hi; ++lit) {
+						const uint32 n = wtoffs[lit + 1] - wtoffs[lit];
+						if (!n) continue;
+						WL& list = wt[lit];
+						list.resize(n);
+						memcpy((WATCH*)list, &wtrecs[wtoffs[lit]], size_t(n) * sizeof(WATCH));
+					}
+				};
+				const uint32 nthreads = nl >= (1u << 18) ? 4 : 1;
+				std::vector<std::thread> fillers;
+				for (uint32 t = 1; t < nthreads; ++t) fillers.emplace_back(fill, uint32(uint64_t(nl) * t / nthreads), uint32(uint64_t(nl) * (t + 1) / nthreads));
+				fill(0, uint32(uint64_t(nl) / nthreads));
+				for (auto& th : fillers) th.join();
 				watchesDone = true;
 				tsplit("watch lists into wt");
 			}
@@ -332,6 +347,8 @@ public:
 		else if (canMap()) map(true);
 		else newBeginning();
 		tsplit("state / statistics");
+		if (wtFreer.joinable()) wtFreer.join();
+		tsplit("wait for the old watch table to be freed");
 		if (!(newBeginningDone && watchesDone)) rebuildWT(opts.simplify_priorbins);
 		tsplit("host rebuildWT (if any)");
 		if (retrail()) LOG2(2, " Propagation after simplify proved a contradiction");
