@@ -829,69 +829,72 @@ __global__ void k_rank(SgView v)
 /* The whole variable ordering in ONE cooperative launch: scores (histogram.hpp:23-41), stable LSD radix sort of
  * (score, variable) with 8-bit digits, rank[] (lcve.cpp:39 = wolfsort(..., STABLE_LCV): score ascending, ties by variable).
  * The separate-launch version above costs 12 launches per election for 16 MB of keys - launch latency, not bandwidth.
- * Block b owns the same contiguous chunk of positions in every pass; per pass: per-block digit histogram | grid barrier |
- * every block sums the histograms before it (37 888 words in L2) and scatters its chunk in order, 1024 keys at a time,
- * ranked with __match_any_sync inside a warp and a per-digit prefix over the 32 warps | grid barrier.  The number of
- * passes comes from the largest score, which the first phase leaves in the scalars (forced_bits != 0: the caller's
- * width, a test hook for the too-narrow-guess path of the separate-launch version). */
+ * Block b owns the same contiguous chunk of positions in every pass and warp w of the block a contiguous slice of it, so
+ * "stable" = (block, warp, position in the slice).  Per pass: every warp counts the digits of its slice in its own row of
+ * a shared [32][256] table | block totals to global memory | grid barrier | every block sums the totals of the blocks before
+ * it (37 888 words in L2) and turns its table into start offsets per (warp, digit) | every warp walks its slice 32 keys at a
+ * time: __match_any_sync ranks the lanes of one digit, the row entry moves on - no block barrier inside the walk | grid
+ * barrier.  The number of passes comes from the largest score, which the first phase leaves in the scalars
+ * (forced_bits != 0: the caller's width, a test hook for the too-narrow-guess path of the separate-launch version). */
 constexpr int VO_TPB = 1024;
 __global__ void __launch_bounds__(VO_TPB, 1) k_vo_sort(SgView v, uint32_t *tmpk, uint32_t *tmpv, uint32_t *hist, uint32_t forced_bits)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ uint32_t s_dyn[];
-    uint32_t (*s_cnt)[256] = (uint32_t (*)[256])s_dyn;                 /* [32][256] keys of digit d in warp w of the sub-tile */
-    uint32_t (*s_off)[256] = (uint32_t (*)[256])(s_dyn + 32 * 256);    /* [32][256] where they go */
-    __shared__ uint32_t s_hist[256], s_base[256], s_wsum[8];
+    uint32_t (*s_cnt)[256] = (uint32_t (*)[256])s_dyn;                 /* [32][256] digit counts, then start offsets, per warp */
+    uint32_t (*s_tmp)[256] = (uint32_t (*)[256])(s_dyn + 32 * 256);    /* [8][256] partial sums of the offsets phase */
+    __shared__ uint32_t s_base[256], s_wsum[8];
     const uint32_t n = v.nvars, G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t chunk = (((n + G - 1) / G) + VO_TPB - 1) / VO_TPB * VO_TPB;
-    const uint64_t lo64 = (uint64_t)b * chunk;
-    const uint32_t i_lo = lo64 < n ? (uint32_t)lo64 : n, i_hi = (lo64 + chunk < n) ? (uint32_t)(lo64 + chunk) : n;
+    const uint32_t chunk = (((n + G - 1) / G) + VO_TPB - 1) / VO_TPB * VO_TPB, slice = chunk / 32;     /* slice: a multiple of 32 */
+    const uint64_t lo64 = (uint64_t)b * chunk + (uint64_t)warp * slice;
+    const uint32_t w_lo = lo64 < n ? (uint32_t)lo64 : n, w_hi = (lo64 + slice < n) ? (uint32_t)(lo64 + slice) : n;
     uint32_t *keys = v.scores + 1, *vals = v.order;
-    /* scores, identity order, digit-0 histogram, largest score (four positions per thread in flight) */
-    if (tid < 256) s_hist[tid] = 0;
+    const uint2 *occ2 = (const uint2 *)v.occ;                          /* occ[2x], occ[2x + 1] */
     for (uint32_t i = tid; i < 32 * 256; i += VO_TPB) s_dyn[i] = 0;
     __syncthreads();
+    /* scores, identity order, digit-0 counts, largest score (four steps of the slice in flight) */
     uint32_t m = 0;
-    const uint2 *occ2 = (const uint2 *)v.occ;                    /* occ[2x], occ[2x + 1] */
-    for (uint32_t i0 = i_lo + tid; i0 < i_hi; i0 += 4 * VO_TPB) {
+    for (uint32_t i0 = w_lo + lane; i0 < w_hi; i0 += 128) {
         uint2 o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + q * VO_TPB; o[q] = i < i_hi ? __ldg(occ2 + i + 1) : make_uint2(0u, 0u); }
+        for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + 32 * q; o[q] = i < w_hi ? __ldg(occ2 + i + 1) : make_uint2(0u, 0u); }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t i = i0 + q * VO_TPB;
-            if (i < i_hi) {
+            const uint32_t i = i0 + 32 * q;
+            if (i < w_hi) {
                 const uint32_t sc = o[q].x * o[q].y;
                 keys[i] = sc; vals[i] = i + 1;
                 m = sc > m ? sc : m;
-                atomicAdd(&s_hist[sc & 255u], 1u);
+                atomicAdd(&s_cnt[warp][sc & 255u], 1u);
             }
         }
     }
     m = __reduce_max_sync(0xffffffffu, m);
     if (lane == 0 && m) atomicMax(&v.sc->max_score, m);
-    __syncthreads();
-    if (tid < 256) hist[tid * G + b] = s_hist[tid];
-    grid.sync();
     uint32_t bits = forced_bits;
-    if (!bits) { const uint32_t mx = *(volatile uint32_t *)&v.sc->max_score; bits = 8; while (bits < 32 && (mx >> bits)) bits += 8; }
     uint32_t *ik = keys, *iv = vals, *ok = tmpk, *ov = tmpv;
-    for (uint32_t shift = 0; shift < bits; shift += 8) {
+    for (uint32_t shift = 0; shift == 0 || shift < bits; shift += 8) {
         if (shift) {
-            if (tid < 256) s_hist[tid] = 0;
+            for (uint32_t i = tid; i < 32 * 256; i += VO_TPB) s_dyn[i] = 0;
             __syncthreads();
-            for (uint32_t i0 = i_lo + tid; i0 < i_hi; i0 += 4 * VO_TPB) {
+            for (uint32_t i0 = w_lo + lane; i0 < w_hi; i0 += 128) {
                 uint32_t k[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + q * VO_TPB; k[q] = i < i_hi ? __ldcg(ik + i) : 0u; }
+                for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + 32 * q; k[q] = i < w_hi ? __ldcg(ik + i) : 0u; }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (i0 + q * VO_TPB < i_hi) atomicAdd(&s_hist[(k[q] >> shift) & 255u], 1u);
+                for (int q = 0; q < 4; ++q) if (i0 + 32 * q < w_hi) atomicAdd(&s_cnt[warp][(k[q] >> shift) & 255u], 1u);
             }
-            __syncthreads();
-            if (tid < 256) hist[tid * G + b] = s_hist[tid];
-            grid.sync();
         }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t t = 0;
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) t += s_cnt[w][tid];
+            hist[tid * G + b] = t;
+        }
+        grid.sync();
+        if (!shift && !bits) { const uint32_t mx = *(volatile uint32_t *)&v.sc->max_score; bits = 8; while (bits < 32 && (mx >> bits)) bits += 8; }
         /* where this block's keys of digit d start: all keys of smaller digits + the keys of digit d in earlier blocks.
          * Four threads per digit, each a quarter of the blocks, eight loads in flight */
         {
@@ -906,13 +909,13 @@ __global__ void __launch_bounds__(VO_TPB, 1) k_vo_sort(SgView v, uint32_t *tmpk,
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { tot += x[q]; pre += k + q < b ? x[q] : 0u; }
             }
-            s_off[part][d] = tot; s_off[4 + part][d] = pre;
+            s_tmp[part][d] = tot; s_tmp[4 + part][d] = pre;
         }
         __syncthreads();
         uint32_t tot = 0, pre = 0;
         if (tid < 256) {
-            tot = s_off[0][tid] + s_off[1][tid] + s_off[2][tid] + s_off[3][tid];
-            pre = s_off[4][tid] + s_off[5][tid] + s_off[6][tid] + s_off[7][tid];
+            tot = s_tmp[0][tid] + s_tmp[1][tid] + s_tmp[2][tid] + s_tmp[3][tid];
+            pre = s_tmp[4][tid] + s_tmp[5][tid] + s_tmp[6][tid] + s_tmp[7][tid];
         }
         uint32_t incl = tot;
 #pragma unroll
@@ -920,46 +923,43 @@ __global__ void __launch_bounds__(VO_TPB, 1) k_vo_sort(SgView v, uint32_t *tmpk,
         if (tid < 256 && lane == 31) s_wsum[warp] = incl;
         __syncthreads();
         if (tid < 256) {
-            uint32_t before = 0;
-            for (uint32_t w = 0; w < warp; ++w) before += s_wsum[w];
-            s_base[tid] = before + incl - tot + pre;
+            uint32_t run = incl - tot + pre;
+            for (uint32_t w = 0; w < warp; ++w) run += s_wsum[w];
+            /* counts -> start offsets per (warp of the block, digit) */
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) { const uint32_t c = s_cnt[w][tid]; s_cnt[w][tid] = run; run += c; }
         }
         __syncthreads();
-        /* the chunk in order, 1024 keys at a time; the next 1024 are fetched while these are ranked */
+        /* the warp's slice in order, 32 keys per step, the next step's keys fetched while these are ranked */
         uint32_t nkey = 0, nval = 0;
-        if (i_lo + tid < i_hi) { nkey = __ldcg(ik + i_lo + tid); nval = __ldcg(iv + i_lo + tid); }
-        for (uint32_t base = i_lo; base < i_hi; base += VO_TPB) {
-            const uint32_t i = base + tid;
-            const bool valid = i < i_hi;
+        if (w_lo + lane < w_hi) { nkey = __ldcg(ik + w_lo + lane); nval = __ldcg(iv + w_lo + lane); }
+        for (uint32_t base = w_lo; base < w_hi; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < w_hi;
             const uint32_t key = nkey, val = nval;
-            if (i + VO_TPB < i_hi) { nkey = __ldcg(ik + i + VO_TPB); nval = __ldcg(iv + i + VO_TPB); }
+            if (i + 32 < w_hi) { nkey = __ldcg(ik + i + 32); nval = __ldcg(iv + i + 32); }
             const uint32_t d = valid ? ((key >> shift) & 255u) : 256u;
             const uint32_t mask = __match_any_sync(0xffffffffu, d);
             const uint32_t before = __popc(mask & ((1u << lane) - 1u));
-            if (valid && before == 0) s_cnt[warp][d] = __popc(mask);
-            __syncthreads();
-            if (tid < 256) {
-                uint32_t run = s_base[tid];
-#pragma unroll 8
-                for (int w = 0; w < 32; ++w) { const uint32_t c = s_cnt[w][tid]; s_off[w][tid] = run; s_cnt[w][tid] = 0; run += c; }
-                s_base[tid] = run;
-            }
-            __syncthreads();
-            if (valid) { const uint32_t o = s_off[warp][d] + before; ok[o] = key; ov[o] = val; }
-            /* the next round's s_off is written after its own barrier, which every reader above has passed by then */
+            uint32_t o = 0;
+            if (valid) o = s_cnt[warp][d] + before;
+            __syncwarp();
+            if (valid && before == 0) s_cnt[warp][d] += __popc(mask);
+            __syncwarp();
+            if (valid) { ok[o] = key; ov[o] = val; }
         }
         grid.sync();
         uint32_t *t = ik; ik = ok; ok = t;
         t = iv; iv = ov; ov = t;
     }
-    for (uint32_t i0 = i_lo + tid; i0 < i_hi; i0 += 4 * VO_TPB) {
+    for (uint32_t i0 = w_lo + lane; i0 < w_hi; i0 += 128) {
         uint32_t x[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + q * VO_TPB; x[q] = i < i_hi ? __ldcg(iv + i) : 0u; }
+        for (int q = 0; q < 4; ++q) { const uint32_t i = i0 + 32 * q; x[q] = i < w_hi ? __ldcg(iv + i) : 0u; }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t i = i0 + q * VO_TPB;
-            if (i < i_hi) { if (iv != vals) vals[i] = x[q]; v.rank[x[q]] = i; }
+            const uint32_t i = i0 + 32 * q;
+            if (i < w_hi) { if (iv != vals) vals[i] = x[q]; v.rank[x[q]] = i; }
         }
     }
 }
@@ -2259,7 +2259,7 @@ void be_sort_pairs(void *s, uint32_t *keys, uint32_t *vals, uint32_t n, uint32_t
 int be_vo_sort(void *s, const SgView &v, uint32_t *tmpk, uint32_t *tmpv, uint32_t *tmp, uint32_t forced_bits)
 {
     static int ok = -1, sms = 0;
-    const int smem = 2 * 32 * 256 * 4;
+    const int smem = (32 + 8) * 256 * 4;
     if (ok < 0) {
         int dev = 0, coop = 0, per_sm = 0;
         cudaGetDevice(&dev);
