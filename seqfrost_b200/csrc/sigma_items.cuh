@@ -667,19 +667,33 @@ SG_HD void sg_elect_prep_item(const SgView &v, uint32_t var)
 #endif
 /* blocker (may be null): when the candidate stays undecided, *blocker receives the undecided earlier-ranked neighbour of the
  * highest rank - the one most likely to be decided last; until its election word changes, looking again is pointless */
-SG_HDN inline bool sg_elect_eval(const SgView &v, uint32_t cand, uint32_t *blocker)
+/* GW = lanes that share one candidate: 32 (one candidate per warp), or 8 in the barrier-free election, where four
+ * candidates are looked at side by side - the function waits on a chain of dependent fetches, so four chains per warp in
+ * flight instead of one is what counts; every lane of a group must call it (the groups of a warp may diverge). */
+template <int GW> SG_HDN inline bool sg_elect_eval_g(const SgView &v, uint32_t cand, uint32_t *blocker)
 {
+#if defined(__CUDA_ARCH__)
+    SgLane L;
+    L.lane = threadIdx.x & (GW - 1); L.width = GW;
+    const uint32_t gmask = GW == 32 ? 0xffffffffu : (((1u << (GW & 31)) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(GW - 1)));
+    const int gleader = (int)((threadIdx.x & 31u) & ~(uint32_t)(GW - 1));
+#define SG_G_BCAST(x) __shfl_sync(gmask, (x), gleader)
+#define SG_G_WOR(x) __reduce_or_sync(gmask, (x))
+#else
     const SgLane L = sg_lane_ctx();
+#define SG_G_BCAST(x) (x)
+#define SG_G_WOR(x) (x)
+#endif
     uint32_t bl_key = 0, bl_var = 0;                          /* rank + 1 of this lane's best blocker */
     /* the list headers are fetched together with the election word, not after it: one memory round trip less on the
      * chain word -> lists -> headers -> literals -> neighbours' words that bounds this function */
     const int np = (int)v.ot_len[2 * cand], nn = (int)v.ot_len[2 * cand + 1];
     const uint32_t *dp = sg_list(v, 2 * cand), *dn = sg_list(v, 2 * cand + 1);
     const uint32_t brk = *(volatile uint32_t *)&v.sc->brk_rank;
-    const uint32_t wc = sg_bcast(sg_er_load(v, cand));
+    const uint32_t wc = SG_G_BCAST(sg_er_load(v, cand));
     if (SG_ER_STAT(wc) != SG_E_UNDECIDED) return false;       /* frozen by a push since it was queued */
     const uint32_t rc = SG_ER_RANK(wc);
-    if (rc > sg_bcast(brk)) { if (L.lane == 0) sg_er_set(v, cand, SG_E_SKIP); return false; }
+    if (rc > SG_G_BCAST(brk)) { if (L.lane == 0) sg_er_set(v, cand, SG_E_SKIP); return false; }
     const int maxcsize = v.o.lcve_clause_max;
     bool blocked = false, frozen = false, failp = false, failn = false;
     for (int q = (int)L.lane; q < np + nn; q += (int)L.width) {
@@ -708,13 +722,13 @@ SG_HDN inline bool sg_elect_eval(const SgView &v, uint32_t cand, uint32_t *block
             }
         }
     }
-    const uint32_t flags = sg_wor((blocked ? 1u : 0u) | (frozen ? 2u : 0u) | (failp ? 4u : 0u) | (failn ? 8u : 0u));
+    const uint32_t flags = SG_G_WOR((blocked ? 1u : 0u) | (frozen ? 2u : 0u) | (failp ? 4u : 0u) | (failn ? 8u : 0u));
     if (flags & 2u) { if (L.lane == 0) sg_er_set(v, cand, SG_E_FROZEN); return false; }
     if (flags & 1u) {
         if (blocker) {
 #if defined(__CUDA_ARCH__)
-            const uint32_t best = __reduce_max_sync(0xffffffffu, bl_key);
-            *blocker = __shfl_sync(0xffffffffu, bl_var, __ffs((int)__ballot_sync(0xffffffffu, bl_key == best)) - 1);
+            const uint32_t best = __reduce_max_sync(gmask, bl_key);
+            *blocker = __shfl_sync(gmask, bl_var, __ffs((int)(__ballot_sync(gmask, bl_key == best) & gmask)) - 1);
 #else
             *blocker = bl_var;
 #endif
@@ -750,6 +764,9 @@ SG_HDN inline bool sg_elect_eval(const SgView &v, uint32_t cand, uint32_t *block
     }
     return false;
 }
+#undef SG_G_BCAST
+#undef SG_G_WOR
+SG_HDN inline bool sg_elect_eval(const SgView &v, uint32_t cand, uint32_t *blocker) { return sg_elect_eval_g<32>(v, cand, blocker); }
 
 SG_HDN inline bool sg_elect_round_item(const SgView &v, uint32_t cand) { return sg_elect_eval(v, cand, nullptr); }
 

@@ -1092,13 +1092,18 @@ __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_persistent(
  * decides it - or next in a warp whose parked candidates all have lower ranks, i.e. none.  The outcome is the sequential
  * one for the same reason as in the round version: a candidate is decided on final election words of all its
  * earlier-ranked neighbours.  sc->wl_count[0] receives the largest number of looks any warp needed (a report figure). */
+#ifndef SG_ELECT_GW
+#define SG_ELECT_GW 8          /* lanes per candidate in k_elect_async: 32 / SG_ELECT_GW candidates are looked at side by side */
+#endif
 __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_async(SgView v)
 {
+    constexpr int NG = 32 / SG_ELECT_GW;       /* lane groups per warp */
     const uint32_t V = v.nvars;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, grp = lane / SG_ELECT_GW;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t p_cand = 0, p_blk = 0;            /* slot `lane`: parked candidate (0 = free) and its blocker */
     uint32_t f_var = 0, f_mask = 0;            /* the fetched block: lane j holds the candidate of rank f_base + j * nwarps */
+    bool p_small = false, f_small = false;     /* short lists: looked at by SG_ELECT_GW lanes, NG candidates side by side */
     uint64_t f_base = gwarp;                   /* rank of lane 0's entry of the NEXT block to fetch */
     bool more = gwarp < V;
     uint32_t looks = 0, ready = 0;
@@ -1115,41 +1120,80 @@ __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_async(SgVie
             }
             ready = __ballot_sync(0xffffffffu, rdy);
         }
-        int j;
-        uint32_t cand;
-        if (ready) {
-            j = __ffs((int)ready) - 1;
-            ready &= ready - 1;
-            cand = __shfl_sync(0xffffffffu, p_cand, j);
-        } else if (parked != 0xFFFFFFFFu && f_mask) {
-            /* a new candidate, in rank order, into the first free slot if it has to wait */
-            const int k = __ffs((int)f_mask) - 1;
-            f_mask &= f_mask - 1;
-            cand = __shfl_sync(0xffffffffu, f_var, k);
-            j = __ffs((int)~parked) - 1;
-        } else if (parked != 0xFFFFFFFFu && more) {
-            const uint32_t brk = __shfl_sync(0xffffffffu, *(volatile uint32_t *)&v.sc->brk_rank, 0);
-            const uint64_t r = f_base + (uint64_t)lane * nwarps;
-            f_var = 0;
-            if (r < V && r <= brk) { const uint32_t x = v.order[(uint32_t)r]; if (SG_ER_STAT(sg_er_load(v, x)) == SG_E_UNDECIDED) f_var = x; }
-            f_mask = __ballot_sync(0xffffffffu, f_var != 0);
-            /* the two occurrence lists of a candidate are neighbours in the table: ask for their lines now (one round trip
-             * for the whole block of candidates), so that the look finds them in L2 */
-            if (f_var) {
-                const uint32_t *dp = v.ot_data + v.ot_off[2 * f_var], *dn = v.ot_data + v.ot_off[2 * f_var + 1];
-                const uint32_t np = v.ot_len[2 * f_var], nn = v.ot_len[2 * f_var + 1];
-                if (np) asm volatile("prefetch.global.L2 [%0];" :: "l"(dp));
-                if (nn) asm volatile("prefetch.global.L2 [%0];" :: "l"(dn + nn - 1));
+        /* work items, chosen the same way by every lane: parked candidates that are ready first, then new candidates in rank
+         * order, each with a free slot reserved in case it has to wait.  A candidate with long lists is looked at by the whole
+         * warp, alone; candidates with short lists NG at a time, SG_ELECT_GW lanes each (the look waits on a chain of dependent
+         * fetches: several chains in flight per warp) */
+        const uint32_t psmall = __ballot_sync(0xffffffffu, p_small), fsmall = __ballot_sync(0xffffffffu, f_small);
+        uint32_t freeslots = ~parked;
+        int src = -1, slot = -1;               /* this lane's group: source lane (parked slot or fetch-block entry) */
+        bool from_parked = false, wide = false;
+        int slots[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) slots[g] = -1;
+        uint32_t have = 0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            int s_ = -1, d_ = -1;
+            bool fp = false;
+            if (!wide) {
+                if (ready) {
+                    const int j = __ffs((int)ready) - 1;
+                    const bool small = (psmall >> j) & 1u;
+                    if (small || g == 0) { s_ = j; ready &= ready - 1; d_ = j; fp = true; wide = !small; }
+                } else if (f_mask && freeslots) {
+                    const int k = __ffs((int)f_mask) - 1;
+                    const bool small = (fsmall >> k) & 1u;
+                    if (small || g == 0) { s_ = k; f_mask &= f_mask - 1; d_ = __ffs((int)freeslots) - 1; freeslots &= freeslots - 1; wide = !small; }
+                }
             }
-            f_base += 32ull * nwarps;
-            more = f_base < V && f_base <= brk;
+            slots[g] = d_;
+            if (s_ >= 0) have |= 1u << g;
+            if ((uint32_t)g == grp || (wide && g == 0)) { src = s_; slot = d_; from_parked = fp; }
+            if (wide) break;                                  /* the whole warp looks at this one */
+        }
+        if (!have) {
+            if (parked != 0xFFFFFFFFu && more) {
+                const uint32_t brk = __shfl_sync(0xffffffffu, *(volatile uint32_t *)&v.sc->brk_rank, 0);
+                const uint64_t r = f_base + (uint64_t)lane * nwarps;
+                f_var = 0; f_small = false;
+                if (r < V && r <= brk) { const uint32_t x = v.order[(uint32_t)r]; if (SG_ER_STAT(sg_er_load(v, x)) == SG_E_UNDECIDED) f_var = x; }
+                f_mask = __ballot_sync(0xffffffffu, f_var != 0);
+                /* the two occurrence lists of a candidate are neighbours in the table: ask for their lines now (one round trip
+                 * for the whole block of candidates), so that the look finds them in L2 */
+                if (f_var) {
+                    const uint32_t *dp = v.ot_data + v.ot_off[2 * f_var], *dn = v.ot_data + v.ot_off[2 * f_var + 1];
+                    const uint32_t np = v.ot_len[2 * f_var], nn = v.ot_len[2 * f_var + 1];
+                    if (np) asm volatile("prefetch.global.L2 [%0];" :: "l"(dp));
+                    if (nn) asm volatile("prefetch.global.L2 [%0];" :: "l"(dn + nn - 1));
+                    f_small = np + nn <= 2u * SG_ELECT_GW;
+                }
+                f_base += 32ull * nwarps;
+                more = f_base < V && f_base <= brk;
+                continue;
+            }
+            if (!parked && !f_mask && !more) break;
+            __nanosleep(200);
             continue;
-        } else if (!parked && !f_mask && !more) break;
-        else { __nanosleep(200); continue; }
+        }
+        const int srcl = src < 0 ? 0 : src;
+        const uint32_t c_p = __shfl_sync(0xffffffffu, p_cand, srcl), c_f = __shfl_sync(0xffffffffu, f_var, srcl);
+        const bool s_p = __shfl_sync(0xffffffffu, (int)p_small, srcl) != 0, s_f = __shfl_sync(0xffffffffu, (int)f_small, srcl) != 0;
+        const uint32_t cand = src < 0 ? 0u : (from_parked ? c_p : c_f);
+        const bool csmall = from_parked ? s_p : s_f;
         uint32_t blk = 0;
-        const bool stay = sg_elect_eval(v, cand, &blk);          /* returns at once when a push froze it meanwhile */
+        bool stay = false;
+        if (wide) stay = sg_elect_eval_g<32>(v, cand, &blk);                   /* every lane: one candidate */
+        else if (src >= 0) stay = sg_elect_eval_g<SG_ELECT_GW>(v, cand, &blk);  /* returns at once when a push froze it meanwhile */
+        __syncwarp();
         ++looks;
-        if ((int)lane == j) { p_cand = stay ? cand : 0u; p_blk = blk; }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const uint32_t cg_ = __shfl_sync(0xffffffffu, cand, g * SG_ELECT_GW), bg = __shfl_sync(0xffffffffu, blk, g * SG_ELECT_GW);
+            const bool sg_ = __shfl_sync(0xffffffffu, (int)stay, g * SG_ELECT_GW) != 0;
+            const bool sm_ = __shfl_sync(0xffffffffu, (int)csmall, g * SG_ELECT_GW) != 0;
+            if (((have >> g) & 1u) && (int)lane == slots[g]) { p_cand = sg_ ? cg_ : 0u; p_blk = bg; p_small = sg_ && sm_; }
+        }
     }
     if (lane == 0) atomicMax(&v.sc->wl_count[0], looks);
 }
