@@ -2186,6 +2186,7 @@ static bool otb_geometry(uint32_t nlit, uint32_t n_cls, uint64_t lits, uint32_t 
     }
     if (!best) return false;
     sh = best;
+    { const char *e = getenv("SIGMA_OTB_SHIFT"); if (e) { const uint32_t x = (uint32_t)atoi(e); if (x >= 6 && x <= 12 && (((uint64_t)nlit + (1u << x) - 1) >> x) <= OTB_NBMAX) sh = x; } }   /* experiments */
     const uint64_t nb = ((uint64_t)nlit + (1u << sh) - 1) >> sh;
     /* tiles: a multiple of the SM count, an average tile fills 80 % of the scatter's staging room; a multiple of 32 clauses
      * (bitmap words) */

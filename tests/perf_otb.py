@@ -1,0 +1,21 @@
+"""Dev aid (not a test): createOT stage times of the bench instance under different bucket widths (SIGMA_OTB_SHIFT)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from seqfrost_b200 import boundary as B, cnfgen, sigma
+b = B.from_cnf(*cnfgen.planted_subsumption_ksat(2_000_000, 10_000_000, k=5, seed=7))
+b.opts["ere_en"] = 1
+s = sigma.Sigma(0)
+s.upload(b)
+for sh in ("", "10", "11", "12"):
+    if sh:
+        os.environ["SIGMA_OTB_SHIFT"] = sh
+    elif "SIGMA_OTB_SHIFT" in os.environ:
+        del os.environ["SIGMA_OTB_SHIFT"]
+    acc = {}
+    for i in range(5):
+        s.execute()
+        if i >= 2:
+            for k, v in s.report()["stage_ms"].items():
+                acc[k] = acc.get(k, 0) + v / 3
+    print("shift", sh or "auto", {k: round(acc[k], 3) for k in ("ot_hist", "ot_scan", "ot_scatter", "ot_order", "total_device")}, flush=True)
