@@ -166,7 +166,11 @@ void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint3
 /* generic item / serial launches */
 void be_items(void *s, int kind, const SgView &v, uint32_t n);
 void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2 = 0);
-void be_sort_units(void *s, const SgView &v, uint32_t n);                          /* by (eidx, seq) */
+void be_sort_units(void *s, const SgView &v, uint32_t n);
+/* the ERE replay by one block of 32 warps: parallel claim / apply rounds for the recorded pairs between consecutive dirty
+ * variables (v.ere_owner all ones, v.ere_done zero on entry; claims: 8 words per recorded pair, ccnt: one).  Nonzero return:
+ * not available (be_serial(SGS_ERE_REPLAY) instead) */
+int be_ere_replay_block(void *s, const SgView &v, uint32_t n_events, uint32_t n_list, uint32_t *claims, uint32_t *ccnt);                          /* by (eidx, seq) */
 /* live clause / literal count (solve.hpp:661-671) and melted variable count (solve.hpp:645-654) */
 void be_count_live(void *s, const SgView &v);
 void be_count_melted(void *s, const SgView &v, uint32_t *out);

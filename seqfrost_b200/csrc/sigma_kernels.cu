@@ -1279,6 +1279,133 @@ __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
     else if (kind == SGS_ERE_SPLIT) sg_ere_split_serial(v, arg, arg2);
 }
 
+/* The ERE replay (redundancy.cpp:26-123 in elected order) by ONE block of 32 warps instead of one warp.
+ * Units of work in sequential order: the recorded pairs of clean variables, and the dirty variables (processed in full).
+ * A recorded pair only ever writes clauses the proposal pass marked `touched`, and the owner of a touched clause is dirty
+ * from the start; so between two consecutive dirty variables the pairs can be applied by the claim / safe / apply rounds
+ * of the prefix version (every pending pair claims the clauses it hits now - a superset of what it can hit later -, a pair
+ * that holds all its claims is the earliest pending writer of each of them and sees exactly the sequential state), here
+ * inside the block: warps over pairs, block barriers between the steps, the claimed clause ids kept per pair so that the
+ * check and the reset of the claim words need no second enumeration.  A dirty variable is a barrier: warp 0 processes it
+ * like the reference (it may turn LATER variables dirty, which the search for the next barrier then sees).  No host round
+ * trips, no per-round launches; the one-warp replay remains as fall-back (claim buffer missing, > 64 variables queued). */
+constexpr uint32_t ERE_CLAIMS = 8;
+__global__ void __launch_bounds__(1024, 1) k_ere_replay_block(SgView v, uint32_t n_events, uint32_t n_list, uint32_t *__restrict__ claims,
+                                                             uint32_t *__restrict__ ccnt)
+{
+    __shared__ uint32_t s_ep, s_cur, s_li, s_nd, s_P, s_left, s_stop, s_min;
+    const SgLane L = sg_lane_ctx();
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, nw = blockDim.x >> 5;
+    uint32_t merged[SG_ERE_MAXLEN];
+    SgScalars *sc = v.sc;
+    if (tid == 0) { s_ep = 0; s_cur = 0; s_li = 0; s_stop = 0; sc->ere_npending = 0; sc->ere_overflow = 0; }
+    __syncthreads();
+    while (true) {
+        /* the next dirty variable at or after s_cur: on the list (flags can have changed), or queued by sg_ere_mark_owner */
+        if (tid == 0) {
+            uint32_t li = s_li;
+            while (li < n_list && v.acting[li] < s_cur) ++li;
+            s_li = li; s_min = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        for (uint32_t base = s_li; base < n_list; base += blockDim.x) {
+            const uint32_t q = base + tid;
+            if (q < n_list) { const uint32_t e = v.acting[q]; if (*(volatile uint8_t *)&v.ere_flags[e] & 2u) atomicMin(&s_min, e); }
+            __syncthreads();
+            const uint32_t found = s_min;                  /* every thread reads it before anybody moves on to the next chunk */
+            __syncthreads();
+            if (found != 0xFFFFFFFFu) break;
+        }
+        if (tid == 0) {
+            uint32_t nd = s_min;
+            const uint32_t npend = *(volatile uint32_t *)&sc->ere_npending;
+            if (npend && *(volatile uint32_t *)&sc->ere_pending[0] < nd) nd = *(volatile uint32_t *)&sc->ere_pending[0];
+            s_nd = nd;
+            uint32_t lo = s_ep, hi = n_events;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (v.ubuf[mid].eidx < nd) lo = mid + 1; else hi = mid; }
+            s_P = lo;
+        }
+        __syncthreads();
+        const uint32_t ep = s_ep, P = s_P, nd = s_nd;
+        /* recorded pairs [ep, P) of the clean variables in front of it */
+        while (ep < P) {
+            if (tid == 0) s_left = 0;
+            for (uint32_t k = ep + warp; k < P; k += nw) {                       /* claim */
+                if (v.ere_done[k]) continue;
+                if (L.lane == 0) ccnt[k] = 0;
+                __syncwarp();
+                sg_ere_event_hits(v, L, k, merged, [&](uint32_t c) {
+                    atomicMin(&v.ere_owner[c], k);
+                    const uint32_t i = atomicAdd(&ccnt[k], 1u);
+                    if (i < ERE_CLAIMS) claims[(size_t)k * ERE_CLAIMS + i] = c;
+                });
+            }
+            __syncthreads();
+            for (uint32_t k = ep + warp; k < P; k += nw) {                       /* holds every claim? */
+                if (v.ere_done[k]) continue;
+                const uint32_t n = ccnt[k];
+                bool mine = true;
+                if (n <= ERE_CLAIMS) { if (L.lane < n) mine = v.ere_owner[claims[(size_t)k * ERE_CLAIMS + L.lane]] == k; }
+                else sg_ere_event_hits(v, L, k, merged, [&](uint32_t c) { if (v.ere_owner[c] != k) mine = false; });
+                const bool all = __ballot_sync(0xffffffffu, !mine) == 0;
+                __syncwarp();
+                if (L.lane == 0) v.ere_done[k] = all ? 2u : 0u;
+            }
+            __syncthreads();
+            for (uint32_t k = ep + warp; k < P; k += nw) {                       /* claim words back to "nobody" */
+                if (v.ere_done[k] == 1u) continue;
+                const uint32_t n = ccnt[k];
+                if (n <= ERE_CLAIMS) { if (L.lane < n) v.ere_owner[claims[(size_t)k * ERE_CLAIMS + L.lane]] = 0xFFFFFFFFu; }
+                else sg_ere_event_hits(v, L, k, merged, [&](uint32_t c) { v.ere_owner[c] = 0xFFFFFFFFu; });
+            }
+            __syncthreads();
+            for (uint32_t k = ep + warp; k < P; k += nw) {                       /* apply; the applied pairs write disjoint clauses */
+                const uint32_t d = v.ere_done[k];
+                if (d == 2u) {
+                    const uint32_t eidx = v.ubuf[k].eidx, key = v.ubuf[k].seq;
+                    const uint32_t x = v.elected[eidx];
+                    uint32_t dx, fx;
+                    if (sg_ere_lists(v, x, dx, fx)) sg_ere_pair(v, L, x, eidx, sg_list(v, dx)[key >> 16], sg_list(v, fx)[key & 0xffffu], merged);
+                    __syncwarp();
+                    if (L.lane == 0) { v.ere_done[k] = 1u; atomicAdd(&sc->ere_applied, 1u); atomicAdd((unsigned long long *)&sc->ere_event_pairs, 1ull); }
+                } else if (d == 0u && L.lane == 0) atomicAdd(&s_left, 1u);
+            }
+            __syncthreads();
+            const uint32_t left = s_left;                  /* read by everybody before thread 0 clears it for the next round */
+            __syncthreads();
+            if (left == 0) break;
+        }
+        if (nd == 0xFFFFFFFFu) break;
+        if (warp == 0) {
+            if (L.lane == 0 && sc->ere_npending && sc->ere_pending[0] == nd) {       /* pop the head of the queue */
+                for (uint32_t k = 1; k < sc->ere_npending; ++k) sc->ere_pending[k - 1] = sc->ere_pending[k];
+                sc->ere_npending--;
+            }
+            __syncwarp();
+            uint32_t epx = P;
+            sg_ere_replay_var(v, L, nd, 2u, epx, n_events, merged);
+            __syncwarp();
+            if (L.lane == 0) {
+                uint32_t q = P;
+                while (q < n_events && v.ubuf[q].eidx <= nd) ++q;                /* the recorded pairs of a dirty variable are not used */
+                s_ep = q; s_cur = nd + 1;
+                if (*(volatile uint32_t *)&sc->ere_overflow) s_stop = 1;
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    /* more than 64 variables were queued at once: finish like the one-warp replay, scanning the flags */
+    if (s_stop && warp == 0) {
+        uint32_t ep = s_ep;
+        for (uint32_t e = s_cur; e < v.n_elected; ++e) {
+            __syncwarp();
+            const uint32_t fl = sg_bcast(*(volatile uint8_t *)&v.ere_flags[e]);
+            if (fl) sg_ere_replay_var(v, L, e, fl, ep, n_events, merged);
+        }
+    }
+}
+
 __global__ void k_sort_units_small(SgView v, uint32_t n)
 {   /* one thread: insertion sort by (eidx, seq); n is tiny in practice */
     for (uint32_t i = 1; i < n; ++i) {
@@ -2562,4 +2689,10 @@ void be_wt_fill(void *s, uint32_t *cm, const uint32_t *arena, const uint64_t *re
 void be_wt_records(void *s, uint32_t nlit, const uint32_t *ot_off, const uint32_t *ot_len, const uint32_t *ot_data, const sg_u4 *winfo, sg_u4 *rec)
 {
     if (nlit) LAUNCH(k_wt_records, blocks_for(nlit), TPB, s, nlit, ot_off, ot_len, ot_data, (const uint4 *)winfo, (uint4 *)rec);
+}
+
+int be_ere_replay_block(void *s, const SgView &v, uint32_t n_events, uint32_t n_list, uint32_t *claims, uint32_t *ccnt)
+{
+    LAUNCH(k_ere_replay_block, 1, 1024, s, v, n_events, n_list, claims, ccnt);
+    return 0;
 }

@@ -68,7 +68,7 @@ struct sigma_ctx {
     DBuf<uint32_t> ve_type, ve_ncls, ve_nlits, ve_nmodel, ve_aux, ve_cls_off, ve_lit_off, ve_mod_off, scr_len, scr_off, scratch;
     DBuf<SgUnit> ubuf;
     DBuf<uint8_t> ere_touched, ere_flags;
-    DBuf<uint32_t> ere_filt; DBuf<uint8_t> ere_size8;
+    DBuf<uint32_t> ere_filt, ere_claims; DBuf<uint8_t> ere_size8;
     DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add, otbits, otb_tmp;
     uint64_t phase_add_lits = 0;     /* literals of the resolvents the latest VE stage added */
     uint32_t last_elected = 0;       /* size of `elected` after the latest election (hsc.n_elected does not survive a pull) */
@@ -783,6 +783,19 @@ int stage_ere(sigma_ctx *c)
         CK(pull_totals(c, 1));
         const uint32_t n_list = c->h_totals[0];
         be_items(c->stream, SGK_ERE_LIST, v, E);
+        /* default: the whole replay by one block - parallel claim / apply rounds between consecutive dirty variables
+         * (k_ere_replay_block); SIGMA_ERE_BLOCK=0: prefix rounds driven from the host + the one-warp replay */
+        bool by_block = false;
+        { const char *e = getenv("SIGMA_ERE_BLOCK"); by_block = !(e && e[0] == '0') && 2ull * n <= c->flags.cap; }
+        if (by_block && c->c_newid.ensure((size_t)c->n_cls + 16) && c->ere_claims.ensure(9 * (size_t)n + 64)) {
+            v.ere_owner = c->c_newid.p; v.ere_done = c->flags.p;
+            be_memset(c->stream, v.ere_done, 0, (size_t)n * 4);
+            be_memset(c->stream, v.ere_owner, 0xFF, (size_t)c->n_cls * 4);
+            /* (no scalar push here: the device copy holds what the kernels above left; the kernel clears its own queue words) */
+            if (be_ere_replay_block(c->stream, v, n, n_list, c->ere_claims.p, c->ere_claims.p + 8 * (size_t)n) != 0) by_block = false;
+        } else by_block = false;
+        if (!by_block) {
+        v.ere_owner = nullptr; v.ere_done = nullptr;
         /* recorded pairs before the first dirty variable: parallel claim/apply rounds */
         be_serial(c->stream, SGS_ERE_SPLIT, v, n, n_list);
         CK(pull_scalars(c));
@@ -802,6 +815,7 @@ int stage_ere(sigma_ctx *c)
         c->hsc.ere_npending = 0; c->hsc.ere_overflow = 0;
         CK(push_scalars(c));
         be_serial(c->stream, SGS_ERE_REPLAY, v, n, n_list);
+        }
     }
     CK(pull_scalars(c));
     c->hsc.n_units = 0;
