@@ -167,6 +167,9 @@ void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint3
 void be_items(void *s, int kind, const SgView &v, uint32_t n);
 void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2 = 0);
 void be_sort_units(void *s, const SgView &v, uint32_t n);
+/* sortOT of the lists with 25 .. SG_SOT_WIDE_MAX entries by one warp each (work list left by SGK_SORTOT_LONG when v.sot_wl is set) */
+int be_has_sortot_wide(void);
+int be_sortot_wide(void *s, const SgView &v);
 /* the ERE replay by one block of 32 warps: parallel claim / apply rounds for the recorded pairs between consecutive dirty
  * variables (v.ere_owner all ones, v.ere_done zero on entry; claims: 8 words per recorded pair, ccnt: one).  Nonzero return:
  * not available (be_serial(SGS_ERE_REPLAY) instead) */

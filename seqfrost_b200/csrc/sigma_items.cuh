@@ -596,9 +596,11 @@ SG_HDN inline void sg_sortot_warp_item(const SgView &v, uint32_t lit)
 }
 /* the rest, one thread per list: very short lists (a warp would idle; gate circuits have millions of them) and lists of
  * more than 24 entries (libstdc++'s introsort restated step for step) */
+#define SG_SOT_WIDE_MAX 512
 SG_HDN inline void sg_sortot_long_item(const SgView &v, uint32_t lit)
 {
     const int n = (int)v.ot_len[lit];
+    if (n > 24 && n <= SG_SOT_WIDE_MAX && v.sot_wl) { v.sot_wl[sg_atomic_add(&v.sc->wl_count[1], 1u)] = lit; return; }
     if (n <= (int)v.sortot_warp_min || n > 24) sg_sortot_item(v, lit);
 }
 

@@ -1264,6 +1264,61 @@ template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND
     else if (KIND == SGK_ERE_LIST) { if (v.ere_flags[i]) v.acting[v.ve_cls_off[i]] = i; }
 }
 
+/* sortOT for lists of 25 .. SG_SOT_WIDE_MAX entries (simplify.cpp:85-100: std::sort by CNF_CMP_KEY), one warp per list of the
+ * work list the thread-per-list kernel left.  std::sort is not stable, but when no two keys of the list are equal there is
+ * only one sorted order, whatever the algorithm: the keys of the list are fetched once into shared memory (all fetches in
+ * flight together), every entry's final position is its rank = the number of smaller keys (each lane ranks its share of the
+ * entries against all keys, broadcast reads), and equal keys are counted on the way.  A list WITH equal keys (duplicate
+ * clauses) goes through the step-for-step restatement of libstdc++'s introsort on one lane, as before. */
+__global__ void __launch_bounds__(128) k_sortot_wide(SgView v)
+{
+    __shared__ SgKey s_key[4][SG_SOT_WIDE_MAX];
+    __shared__ uint32_t s_id[4][SG_SOT_WIDE_MAX];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t count = *(volatile uint32_t *)&v.sc->wl_count[1];
+    for (uint32_t item = gwarp; item < count; item += nwarps) {
+        const uint32_t lit = v.sot_wl[item];
+        const int n = (int)v.ot_len[lit];
+        uint32_t *d = sg_list(v, lit);
+        __syncwarp();
+        for (int i = (int)lane; i < n; i += 32) {
+            const uint32_t id = d[i];
+            const sg_u4 h = v.hdr[id];
+            SgKey k; k.size = h.y; k.sig = h.w; k.first = v.lits[h.x]; k.last = v.lits[h.x + h.y - 1];
+            s_key[w][i] = k; s_id[w][i] = id;
+        }
+        __syncwarp();
+        bool tie = false;
+        uint32_t rank[SG_SOT_WIDE_MAX / 32];
+#pragma unroll
+        for (int q = 0; q < SG_SOT_WIDE_MAX / 32; ++q) {
+            const int i = q * 32 + (int)lane;
+            uint32_t r = 0;
+            if (i < n) {
+                const SgKey k = s_key[w][i];
+                for (int j = 0; j < n; ++j) {
+                    const SgKey o = s_key[w][j];
+                    if (sg_key_lt(o, k)) ++r;
+                    else if (j != i && !sg_key_lt(k, o)) tie = true;
+                }
+            }
+            rank[q] = r;
+            if (q * 32 + 32 >= n) break;
+        }
+        if (__any_sync(0xffffffffu, tie)) {
+            if (lane == 0) sg_sortot_item(v, lit);            /* equal keys: the order is std::sort's own */
+            continue;
+        }
+#pragma unroll
+        for (int q = 0; q < SG_SOT_WIDE_MAX / 32; ++q) {
+            const int i = q * 32 + (int)lane;
+            if (i < n) d[rank[q]] = s_id[w][i];
+            if (q * 32 + 32 >= n) break;
+        }
+    }
+}
+
 __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
 {   /* launched with one warp (only the ERE replay uses more than lane 0); the replay gets helper warps that prefetch */
     if (kind == SGS_ERE_REPLAY) {
@@ -2696,3 +2751,12 @@ int be_ere_replay_block(void *s, const SgView &v, uint32_t n_events, uint32_t n_
     LAUNCH(k_ere_replay_block, 1, 1024, s, v, n_events, n_list, claims, ccnt);
     return 0;
 }
+
+/* sortOT: the lists the thread-per-list kernel put on the work list (v.sot_wl, count in sc->wl_count[1]), one warp each */
+int be_sortot_wide(void *s, const SgView &v)
+{
+    if (!v.sot_wl) return 1;
+    LAUNCH(k_sortot_wide, 148 * 4, 128, s, v);
+    return 0;
+}
+int be_has_sortot_wide(void) { return 1; }

@@ -591,15 +591,29 @@ uint32_t sortot_warp_min(const sigma_ctx *c)
 }
 
 /* sortOT (simplify.cpp:85-100) */
+/* the sortOT launches for lists [v.item_base, v.item_base + n): 9..24 entries one warp each, 25..512 entries collected by the
+ * thread-per-list kernel and sorted one warp each (SIGMA_SOT_WIDE=0: by the thread-per-list kernel itself), the rest one
+ * thread each */
+void launch_sortot(sigma_ctx *c, SgView &v, uint32_t n)
+{
+    v.sortot_warp_min = sortot_warp_min(c);
+    if (v.sortot_warp_min < 24) be_items(c->stream, SGK_SORTOT, v, n);
+    bool wide = be_has_sortot_wide() && (uint64_t)n <= c->flags.cap;
+    { const char *e = getenv("SIGMA_SOT_WIDE"); if (e && e[0] == '0') wide = false; }
+    v.sot_wl = wide ? c->flags.p : nullptr;
+    if (wide) be_memset(c->stream, &c->sc.p->wl_count[1], 0, sizeof(uint32_t));
+    be_items(c->stream, SGK_SORTOT_LONG, v, n);
+    if (wide) be_sortot_wide(c->stream, v);
+    v.sot_wl = nullptr;
+}
+
 int stage_sortot(sigma_ctx *c)
 {
     const uint32_t E = c->last_elected;
     Stage st(c, SIGMA_T_SOT);
     SgView v = make_view(c);
     v.n_elected = E;
-    v.sortot_warp_min = sortot_warp_min(c);
-    if (v.sortot_warp_min < 24) be_items(c->stream, SGK_SORTOT, v, 2 * E);   /* lists of 9..24 entries: one warp each */
-    be_items(c->stream, SGK_SORTOT_LONG, v, 2 * E);        /* the others: one thread each */
+    launch_sortot(c, v, 2 * E);
     return SIGMA_OK;
 }
 
@@ -659,9 +673,7 @@ int stage_sub_ve(sigma_ctx *c, uint32_t multiplier)
             {
                 Stage st(c, SIGMA_T_SOT);
                 v.item_base = 2 * first;
-                v.sortot_warp_min = sortot_warp_min(c);
-                if (v.sortot_warp_min < 24) be_items(c->stream, SGK_SORTOT, v, 2 * cnt);
-                be_items(c->stream, SGK_SORTOT_LONG, v, 2 * cnt);
+                launch_sortot(c, v, 2 * cnt);
             }
             v.item_base = first;
             if (interrupted(c)) return SIGMA_INTERRUPTED;  /* subsume.cpp:26, bounded.cpp:31 */

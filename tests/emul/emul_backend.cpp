@@ -288,6 +288,8 @@ void be_elect_round(void *, const SgView &v, const uint32_t *wl_in, uint32_t *wl
 int be_elect_all(void *, const SgView &, uint32_t *, uint32_t *, uint32_t, uint32_t) { return 1; }
 int be_elect_async(void *, const SgView &) { return 1; }
 int be_vo_sort(void *, const SgView &, uint32_t *, uint32_t *, uint32_t *, uint32_t) { return 1; }
+int be_has_sortot_wide(void) { return 0; }
+int be_sortot_wide(void *, const SgView &) { return 1; }
 int be_ere_replay_block(void *, const SgView &, uint32_t, uint32_t, uint32_t *, uint32_t *) { return 1; }   /* host-driven rounds in the stand-in */
 void be_acting_flags(void *, const SgView &v, uint32_t *fa, uint32_t *fe)
 {
