@@ -251,6 +251,17 @@ int  sigma_parse_download(sigma_ctx *ctx, sigma_dimacs *out);
  * sigma_execute / sigma_download / sigma_download_cnf as usual. */
 int  sigma_upload_parsed(sigma_ctx *ctx, const sigma_opts *o);
 
+/* ---- newBeginning() under variable mapping: map(true) (map.cpp:24-46) --------------------------------------------------
+ * When canMap() holds (can.hpp:43: more than map_perc of the variables are inactive) the reference calls map(true) instead of
+ * newBeginning(): vmap.initiate(sp) numbers the active variables 1..n in order (map.hpp:78-95), and newBeginning() builds every
+ * CLAUSE with mapLit(lit) = 2 vmap[var] + sign (map.hpp:52-76,195-205; sclause.cpp:34-35).  The mapping is computed on the host
+ * from state[] / value[] AFTER the pass, so the order is: sigma_execute, sigma_download_state (state / value / trail / model
+ * only), vmap.initiate on the host, sigma_set_var_map(map = *vmap, new_nvars = vmap.numVars()), then sigma_watches_sizes /
+ * sigma_download_cnf (with rest->state == NULL: clause database only) / sigma_download_watches - all in the new numbering
+ * (the `subsume` bytes stay indexed by the old variables, sclause.cpp:29-31).  map == NULL switches back. */
+int  sigma_download_state(sigma_ctx *ctx, sigma_formula *out);
+int  sigma_set_var_map(sigma_ctx *ctx, const uint32_t *map, uint32_t new_nvars);
+
 /* ---- widening #4: rebuildWT() on the device -------------------------------------
  * The watch table rebuildWT(opts.simplify_priorbins) builds from the new clause database (simplify.cpp:218,
  * watch.cpp:135-157, attachBins / attachNonBins / attachClauses :22-133): for every clause in attach order - `priorbins`

@@ -15,6 +15,7 @@
 //
 //   --incr=seed:permille:nassume   incremental solver (Solver() + iadd/itoClause): isolve()'s prologue, a seeded subset of the variables
 //                   frozen through ifreeze() plus `nassume` assumptions; the .in then carries the `ifrozen` mask
+//   --cmmap=<file>  (instead of --cmout) the same after map(true): the variable mapping, the mapped clause database, the watch table
 //   --parseout=<file>  only the reference's DIMACS parser (dimacs.cpp:25-177): CMM arena, orgs, parse-time units (trail), value[],
 //                   state[], header and formula counters, dumped right after parser() returns
 //   --full-timing   also time awaken() (extract), newBeginning()/map(true) and rebuildWT(): the whole simplifying() call
@@ -230,7 +231,8 @@ public:
 	}
 
 	int run(const std::string& sgin, const std::string& sgout, const std::string& tracep, const int64 presolve_conflicts, const std::string& cmin = std::string(),
-		const std::string& cmout = std::string(), const std::string& incr = std::string(), const bool fulltiming = false) {
+		const std::string& cmout = std::string(), const std::string& incr = std::string(), const bool fulltiming = false,
+		const std::string& cmmap = std::string()) {
 		using clk = std::chrono::steady_clock;
 		timer.start();
 		if (!incr.empty()) {
@@ -349,6 +351,47 @@ public:
 			w.section("wtcode", &code, sizeof code);
 			w.close();
 		}
+		if (!cmmap.empty() && inf.unassigned && inf.nClauses) {
+			// simplify.cpp:215 with canMap() taken as true: map(true) (map.cpp:24-121) - variable mapping, newBeginning() with
+			// mapLit() on every literal - then rebuildWT() on the new numbering.  The mapping itself is dumped first, computed
+			// exactly as vmap.initiate() computes it (map.hpp:78-95); map(true) destroys its own copy.
+			std::vector<uint32_t> vm(inf.maxVar + 1, 0);
+			uint32_t newVars = 0, firstDL0 = 0;
+			for (uint32 v = 1; v <= inf.maxVar; ++v) {
+				if (!sp->state[v].state) vm[v] = ++newVars;
+				else if (!firstDL0 && !UNASSIGNED(sp->value[V2L(v)])) { firstDL0 = v; vm[v] = ++newVars; }
+			}
+			std::vector<uint8_t> s0(inf.maxVar + 1);
+			for (uint32 v = 0; v <= inf.maxVar; ++v) s0[v] = sp->state[v].subsume;
+			map(true);
+			Writer w;
+			if (!w.open(cmmap)) return 5;
+			w.section("vmap", vm.data(), vm.size() * sizeof(uint32_t));
+			uint64_t nv[2] = { newVars, inf.maxVar };
+			w.section("vmapn", nv, sizeof nv);
+			w.section("cm", cm.address(0), uint64_t(cm.size()) * sizeof(uint32));
+			w.section("orgs", orgs.data(), uint64_t(orgs.size()) * sizeof(C_REF));
+			w.section("learnts", learnts.data(), uint64_t(learnts.size()) * sizeof(C_REF));
+			uint64_t m[4] = { stats.literals.original, stats.literals.learnt, stats.clauses.original, stats.clauses.learnt };
+			w.section("cmmeta", m, sizeof m);
+			w.section("subsume0", s0.data(), s0.size());
+			w.section("subsume1", s0.data(), s0.size());
+			rebuildWT(opts.simplify_priorbins);
+			std::vector<uint32_t> woff(inf.nDualVars + 1, 0);
+			std::vector<WATCH> wrec;
+			for (uint32 lit = 0; lit < inf.nDualVars; ++lit) {
+				woff[lit] = (uint32_t)wrec.size();
+				WL& ws = wt[lit];
+				for (uint32 k = 0; k < ws.size(); ++k) wrec.push_back(ws[k]);
+			}
+			woff[inf.nDualVars] = (uint32_t)wrec.size();
+			w.section("wtoff", woff.data(), woff.size() * sizeof(uint32_t));
+			w.section("wtrec", wrec.data(), wrec.size() * sizeof(WATCH));
+			w.section("cm2", cm.address(0), uint64_t(cm.size()) * sizeof(uint32));
+			uint64_t code = (uint64_t)opts.simplify_priorbins;
+			w.section("wtcode", &code, sizeof code);
+			w.close();
+		}
 		if (fulltiming && cmout.empty() && inf.unassigned && inf.nClauses) {
 			// the rest of simplifying() (simplify.cpp:215-229) for the whole-call figure the CLI prints as "Simplifier time":
 			// newBeginning() (or map(true)) and rebuildWT()
@@ -381,7 +424,7 @@ int main(int argc, char** argv)
 	INT_OPT opt_timeout("timeout", "set out-of-time limit in seconds", 0, INT32R(0, INT32_MAX));
 	INT_OPT opt_memoryout("memoryout", "set out-of-memory limit in gigabytes", 0, INT32R(0, 256));
 	if (argc < 2) { fprintf(stderr, "usage: ref_sigma <cnf> [options] [--sgin=f] [--sgout=f] [--trace=f]\n"); return 1; }
-	std::string sgin, sgout, tracep, cmin, cmout, incr, parseout;
+	std::string sgin, sgout, tracep, cmin, cmout, incr, parseout, cmmap;
 	long long presolve_conflicts = 0;
 	bool fulltiming = false;
 	std::vector<char*> pass;
@@ -392,6 +435,7 @@ int main(int argc, char** argv)
 		else if (a.rfind("--trace=", 0) == 0) tracep = a.substr(8);
 		else if (a.rfind("--cmin=", 0) == 0) cmin = a.substr(7);
 		else if (a.rfind("--cmout=", 0) == 0) cmout = a.substr(8);
+		else if (a.rfind("--cmmap=", 0) == 0) cmmap = a.substr(8);
 		else if (a.rfind("--incr=", 0) == 0) incr = a.substr(7);
 		else if (a.rfind("--parseout=", 0) == 0) parseout = a.substr(11);
 		else if (a == "--full-timing") fulltiming = true;
@@ -424,7 +468,7 @@ int main(int argc, char** argv)
 			if (!p->loadIncremental(formula)) { fprintf(stderr, "ref_sigma: incremental load failed (empty clause or conflicting units)\n"); g_out_written = true; _exit(8); }
 		}
 		solver = p;
-		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout, incr, fulltiming);
+		int rc = p->run(sgin, sgout, tracep, presolve_conflicts, cmin, cmout, incr, fulltiming, cmmap);
 		g_out_written = g_out_written || rc != 0;
 		fflush(stdout);
 		_exit(rc); // skip the reference's destructors (process-global singletons)

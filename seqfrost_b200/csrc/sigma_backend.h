@@ -87,7 +87,7 @@ void be_extract_write(void *s, const uint32_t *cm, const uint64_t *crefs, uint32
  * counts[0] / counts[1] = literals of original / learnt clauses and, when subsume != NULL, the mark_ssubsume bytes */
 void be_cm_flags(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint32_t *learnt);
 void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, const uint32_t *learnt_before,
-                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume);
+                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume, const uint32_t *vmap /* device, may be NULL: variable mapping (map.hpp:52-76) */);
 /* ERE proposal pass: filt[2c] = size of clause c (0 when deleted), filt[2c+1] = its signature */
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt, uint8_t *size8);   /* size8[c] = min(size, 255), 0 when deleted */
 /* createOT: every list of the freshly built (packed) table into ascending clause id order (simplify.cpp:50-58) */

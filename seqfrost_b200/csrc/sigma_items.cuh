@@ -866,7 +866,10 @@ SG_HD void sg_extract_write(const uint32_t *cm, uint64_t ref, uint32_t *dst)
 }
 
 /* addClause(SCLAUSE&) (sclause.cpp:22-62): one CLAUSE record (clause.hpp:47-59,77-92) from an exported SCLAUSE */
-SG_HD void sg_cm_write(const uint32_t *src, uint32_t *dst, int lbd_tier1)
+/* vmap (may be null): variable mapping of map(true) (map.cpp:24-46, map.hpp:52-76,195-205): the clause is built with
+ * mapLit(lit) = 2 vmap[var] + sign instead of the literal itself (every literal of the simplified formula is unassigned and
+ * active, so mapLit's branch for root-assigned variables is never taken) */
+SG_HD void sg_cm_write(const uint32_t *src, uint32_t *dst, int lbd_tier1, const uint32_t *vmap = nullptr)
 {
     const uint32_t w0 = src[0], size = src[2];
     const bool learnt = (w0 & SG_ST_MASK) == SG_LEARNT;
@@ -877,7 +880,8 @@ SG_HD void sg_cm_write(const uint32_t *src, uint32_t *dst, int lbd_tier1)
     dst[1] = size;
     dst[2] = 2u;                                  /* _pos */
     dst[3] = learnt ? lbd : 0u;
-    for (uint32_t k = 0; k < size; ++k) dst[SG_CM_HDR + k] = src[3 + k];
+    if (vmap) for (uint32_t k = 0; k < size; ++k) dst[SG_CM_HDR + k] = 2u * vmap[SG_ABS(src[3 + k])] + SG_SIGN(src[3 + k]);
+    else for (uint32_t k = 0; k < size; ++k) dst[SG_CM_HDR + k] = src[3 + k];
 }
 
 /* ------------------------------------------------------------------------------------------ */

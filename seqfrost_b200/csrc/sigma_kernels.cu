@@ -124,7 +124,8 @@ __global__ void k_cm_flags(const uint32_t *__restrict__ arena, const unsigned lo
 __global__ void __launch_bounds__(TPB) k_cm_write(const uint32_t *__restrict__ arena, const unsigned long long *__restrict__ refs, uint32_t n,
                            const uint32_t *__restrict__ learnt_before, int lbd_tier1, uint32_t *__restrict__ cm,
                            unsigned long long *__restrict__ orgs, unsigned long long *__restrict__ learnts,
-                           unsigned long long *__restrict__ counts, uint8_t *__restrict__ subsume, unsigned long long cm_total)
+                           unsigned long long *__restrict__ counts, uint8_t *__restrict__ subsume, unsigned long long cm_total,
+                           const uint32_t *__restrict__ vmap)
 {
     /* the CLAUSE records of 256 consecutive clauses are one contiguous run of `cm`: staged, one bulk store */
     __shared__ __align__(128) uint32_t stage[EX_CAP + 4];
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(TPB) k_cm_write(const uint32_t *__restrict__ a
         const unsigned long long r = refs[i];
         const uint32_t *src = arena + r;
         const uint32_t w0 = src[0], size = src[2];
-        sg_cm_write(src, staged ? stage + (uint32_t)(g0 & 3ull) + (uint32_t)(r + i - g0) : cm + r + i, lbd_tier1);
+        sg_cm_write(src, staged ? stage + (uint32_t)(g0 & 3ull) + (uint32_t)(r + i - g0) : cm + r + i, lbd_tier1, vmap);
         const uint32_t lb = learnt_before[i];
         if ((w0 & SG_ST_MASK) == SG_LEARNT) { learnts[lb] = r + i; ll = size; }
         else { orgs[i - lb] = r + i; lo = size; }
@@ -2185,7 +2186,7 @@ __global__ void k_wt_fill(uint32_t *__restrict__ cm, const uint32_t *__restrict_
     if (g > 2) seq += totals[2];
     const unsigned long long cref = r + i;
     uint32_t *l = cm + cref + SG_CM_HDR;
-    if (size != 2u) sg_sort_clause(l, (int)size, value);               /* attachNonBins / attachClauses: if (!c.binary()) sortClause(c) */
+    if (size != 2u && value) sg_sort_clause(l, (int)size, value);               /* attachNonBins / attachClauses: if (!c.binary()) sortClause(c) */
     const uint32_t a = l[0], b = l[1];
     hdr[seq] = make_uint4(2u * seq, 2u, 0u, 0u);
     lits[2 * seq] = SG_FLIP(a); lits[2 * seq + 1] = SG_FLIP(b);        /* ATTACH_TWO_WATCHES: wt[FLIP(first)], wt[FLIP(second)] */
@@ -2292,11 +2293,11 @@ void be_cm_flags(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
     if (n) LAUNCH(k_cm_flags, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt);
 }
 void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t n_buckets, const uint32_t *learnt_before,
-                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
+                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume, const uint32_t *vmap)
 {
     cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ST(s));
     if (n) LAUNCH(k_cm_write, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt_before, lbd_tier1, cm,
-                  (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume, (unsigned long long)(n_buckets + n));
+                  (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume, (unsigned long long)(n_buckets + n), vmap);
 }
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt, uint8_t *size8)
 {

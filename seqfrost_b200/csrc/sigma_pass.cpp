@@ -90,7 +90,8 @@ struct sigma_ctx {
     DBuf<uint64_t> dm_orgs, dm_stats; DBuf<uint32_t> dm_vorg;
     bool dm_parsed = false; sigma_dimacs dm_out;
     DBuf<uint32_t> wt_flags, wt_pos; DBuf<sg_u4> wt_info, wt_rec;                             /* sigma_watches_* */
-    int wt_code = -1; uint64_t wt_records = 0;
+    int wt_code = -1; uint64_t wt_records = 0; uint32_t wt_nlit = 0;
+    DBuf<uint32_t> d_vmap; bool vmap_on = false; uint32_t vmap_nvars = 0;     /* sigma_set_var_map */
     bool cm_built = false; uint32_t cm_learnts = 0; uint64_t cm_lits_org = 0, cm_lits_learnt = 0, cm_last_ref = 0;
     SgScalars hsc;                  /* host mirror */
     uint32_t *h_totals = nullptr;   /* pinned */
@@ -1200,7 +1201,7 @@ int sigma_execute(sigma_ctx *c)
     c->rep.stage_ms[SIGMA_T_H2D] = h2d_ms; c->rep.h2d_bytes = h2d_bytes;
     c->rep.reserved[5] = c->extract_us; c->rep.reserved[6] = c->extract_bytes;
     c->evused = 0; c->evs.clear();
-    c->executed = false; c->cm_built = false; c->stopped = false; c->wt_code = -1;
+    c->executed = false; c->cm_built = false; c->stopped = false; c->wt_code = -1; c->vmap_on = false;
     c->ot_valid = false;
     { const char *e = getenv("SIGMA_OT_INCREMENTAL"); c->ot_incremental = !(e && e[0] == '0'); }
     { const char *e = getenv("SIGMA_OT_VERIFY"); c->ot_verify = e && e[0] == '1'; }
@@ -1278,7 +1279,8 @@ int build_cm(sigma_ctx *c)
     be_scan_u32(c->stream, c->c_flags.p, c->c_newid.p, n, c->totals.p + 0, c->scantmp.p);
     unsigned long long *counts = (unsigned long long *)(c->totals.p + 2);
     be_cm_write(c->stream, c->arena_out.p, c->refs_out.p, n, c->out_buckets, c->c_newid.p, c->opts.lbd_tier1, c->cm_out.p, c->orgs_out.p,
-                c->learnts_out.p, counts, c->in_calls > 1 ? c->subsume_out.p : nullptr);        /* sclause.cpp:29-31 */
+                c->learnts_out.p, counts, c->in_calls > 1 ? c->subsume_out.p : nullptr,          /* sclause.cpp:29-31 */
+                c->vmap_on ? c->d_vmap.p : nullptr);
     be_event_record(c->stream, e1);
     if (n) be_copy_words(c->stream, c->h_totals + 8, c->refs_out.p + (n - 1), 8);
     CK(pull_totals(c, 6));
@@ -1299,7 +1301,7 @@ int build_watches(sigma_ctx *c, uint32_t code)
     CK(build_cm(c));
     if (c->wt_code == (int)code) return SIGMA_OK;
     if (c->wt_code >= 0) { c->cm_built = false; CK(build_cm(c)); }      /* another order was built before: sortClause starts from the records as written */
-    const uint32_t n = c->out_ncls, nlit = c->nlit;
+    const uint32_t n = c->out_ncls, nlit = c->vmap_on ? 2 * c->vmap_nvars + 2 : c->nlit;      /* inf.nDualVars after map(true) */
     NOMEM(c->wt_flags.ensure(4 * (size_t)n + 64)); NOMEM(c->wt_pos.ensure(4 * (size_t)n + 64)); NOMEM(c->wt_info.ensure((size_t)n + 16));
     NOMEM(c->wt_rec.ensure(2 * (size_t)n + 16)); NOMEM(c->hdr2.ensure((size_t)n + 16)); NOMEM(c->lits2.ensure(2 * (size_t)n + 16));
     NOMEM(c->scantmp.ensure(4 * be_scan_tmp_words(n) + 64));
@@ -1313,15 +1315,16 @@ int build_watches(sigma_ctx *c, uint32_t code)
                          { c->totals.p + 16, c->totals.p + 17, c->totals.p + 18, c->totals.p + 19 } };
         be_scan_multi(c->stream, ss, 4, n, c->scantmp.p);
         be_wt_fill(c->stream, c->cm_out.p, c->arena_out.p, c->refs_out.p, n, code, p, p + n, p + 2 * (size_t)n, p + 3 * (size_t)n, c->totals.p + 16,
-                   c->value.p, c->hdr2.p, c->lits2.p, c->wt_info.p);
+                   c->vmap_on ? nullptr : c->value.p,          /* after map(true) every literal of the database is unassigned: sortClause moves nothing */
+                   c->hdr2.p, c->lits2.p, c->wt_info.p);
         /* the occurrence table of the scratch store = the watch lists (entries ascending = push order) */
         { DBuf<sg_u4> t = c->hdr; c->hdr = c->hdr2; c->hdr2 = t; }
         { DBuf<uint32_t> t = c->lits; c->lits = c->lits2; c->lits2 = t; }
-        const uint32_t s_ncls = c->n_cls, s_pool = c->pool_used;
+        const uint32_t s_ncls = c->n_cls, s_pool = c->pool_used, s_nlit = c->nlit;
         const bool s_verify = c->ot_verify;
-        c->n_cls = n; c->pool_used = 2 * n; c->ot_verify = false;
+        c->n_cls = n; c->pool_used = 2 * n; c->ot_verify = false; c->nlit = nlit;
         const int rc = stage_create_ot(c, 2ull * n, n, false);
-        c->n_cls = s_ncls; c->pool_used = s_pool; c->ot_verify = s_verify; c->ot_valid = false;
+        c->n_cls = s_ncls; c->pool_used = s_pool; c->ot_verify = s_verify; c->ot_valid = false; c->nlit = s_nlit;
         { DBuf<sg_u4> t = c->hdr; c->hdr = c->hdr2; c->hdr2 = t; }
         { DBuf<uint32_t> t = c->lits; c->lits = c->lits2; c->lits2 = t; }
         if (rc != SIGMA_OK) { c->rep = keep; return rc; }
@@ -1331,7 +1334,7 @@ int build_watches(sigma_ctx *c, uint32_t code)
     if (ctx_sync(c)) { c->rep = keep; return SIGMA_E_CUDA; }
     c->rep = keep;
     c->rep.reserved32[0] = (uint32_t)(1000.0f * be_event_ms(e0, e1));
-    c->wt_code = (int)code; c->wt_records = 2ull * n;
+    c->wt_code = (int)code; c->wt_records = 2ull * n; c->wt_nlit = nlit;
     return SIGMA_OK;
 }
 
@@ -1341,7 +1344,10 @@ int download_impl(sigma_ctx *c, sigma_formula *out, sigma_cnf_out *cnf)
     if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
     be_bind(c->device);
     const uint32_t V = c->nvars, nlit = c->nlit;
-    bool small = out->trail_cap < c->hsc.n_trail || out->model_cap < c->model_words;
+    /* sigma_download_cnf with rest->state == NULL: only the clause database (the solver state was fetched before, with
+     * sigma_download_state - the order map(true) needs) */
+    const bool with_state = !(cnf && !out->state);
+    bool small = with_state && (out->trail_cap < c->hsc.n_trail || out->model_cap < c->model_words);
     if (cnf) {
         CK(build_cm(c));
         const uint64_t n_orgs = c->out_ncls - c->cm_learnts;
@@ -1353,7 +1359,7 @@ int download_impl(sigma_ctx *c, sigma_formula *out, sigma_cnf_out *cnf)
     sigma_result_sizes(c, out);
     out->arena_cap = acap; out->model_cap = mcap; out->refs_cap = rcap; out->trail_cap = tcap;
     if (small) return fail(c, SIGMA_E_NOSPACE, "output buffers too small (required sizes filled in)");
-    if (!out->state || !out->value || !out->trail || !out->model) return fail(c, SIGMA_E_ARG, "null output array");
+    if (with_state && (!out->state || !out->value || !out->trail || !out->model)) return fail(c, SIGMA_E_ARG, "null output array");
     if (cnf ? (!cnf->cm || !cnf->orgs || !cnf->learnts) : (!out->arena || !out->refs)) return fail(c, SIGMA_E_ARG, "null output array");
     void *e0 = get_event(c), *e1 = get_event(c);
     be_event_record(c->stream, e0);
@@ -1369,10 +1375,12 @@ int download_impl(sigma_ctx *c, sigma_formula *out, sigma_cnf_out *cnf)
         if (c->out_ncls) be_d2h(c->stream, out->refs, c->refs_out.p, (size_t)c->out_ncls * 8);
         clause_bytes = c->out_buckets * 4 + (uint64_t)c->out_ncls * 8;
     }
-    be_d2h(c->stream, out->state, c->state.p, V + 1);
-    be_d2h(c->stream, out->value, c->value.p, nlit);
-    if (c->hsc.n_trail) be_d2h(c->stream, out->trail, c->trail.p, (size_t)c->hsc.n_trail * 4);
-    if (c->model_words) be_d2h(c->stream, out->model, c->model.p, (size_t)c->model_words * 4);
+    if (with_state) {
+        be_d2h(c->stream, out->state, c->state.p, V + 1);
+        be_d2h(c->stream, out->value, c->value.p, nlit);
+        if (c->hsc.n_trail) be_d2h(c->stream, out->trail, c->trail.p, (size_t)c->hsc.n_trail * 4);
+        if (c->model_words) be_d2h(c->stream, out->model, c->model.p, (size_t)c->model_words * 4);
+    }
     be_event_record(c->stream, e1);
     if (ctx_sync(c)) return SIGMA_E_CUDA;
     c->rep.stage_ms[SIGMA_T_D2H] = be_event_ms(e0, e1);
@@ -1403,13 +1411,49 @@ int sigma_cnf_out_sizes(sigma_ctx *c, sigma_cnf_out *sz)
     return SIGMA_OK;
 }
 
+int sigma_set_var_map(sigma_ctx *c, const uint32_t *map, uint32_t new_nvars)
+{
+    if (!c) return SIGMA_E_ARG;
+    if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    be_bind(c->device);
+    c->cm_built = false; c->wt_code = -1;                   /* whatever was built used the other numbering */
+    if (!map) { c->vmap_on = false; return SIGMA_OK; }
+    if (new_nvars > c->nvars) return fail(c, SIGMA_E_ARG, "variable map: more mapped variables than variables");
+    NOMEM(c->d_vmap.ensure((size_t)c->nvars + 1));
+    be_h2d(c->stream, c->d_vmap.p, map, ((size_t)c->nvars + 1) * 4);
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
+    c->vmap_on = true; c->vmap_nvars = new_nvars;
+    return SIGMA_OK;
+}
+
+int sigma_download_state(sigma_ctx *c, sigma_formula *out)
+{
+    if (!c || !out) return SIGMA_E_ARG;
+    if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
+    be_bind(c->device);
+    const bool small = out->trail_cap < c->hsc.n_trail || out->model_cap < c->model_words;
+    const uint64_t mcap = out->model_cap; const uint32_t tcap = out->trail_cap;
+    void *st = out->state, *va = out->value, *tr = out->trail, *mo = out->model;
+    sigma_result_sizes(c, out);
+    out->state = (uint8_t *)st; out->value = (int8_t *)va; out->trail = (uint32_t *)tr; out->model = (uint32_t *)mo;
+    out->model_cap = mcap; out->trail_cap = tcap;
+    if (small) return fail(c, SIGMA_E_NOSPACE, "output buffers too small (required sizes filled in)");
+    if (!out->state || !out->value || (c->hsc.n_trail && !out->trail) || (c->model_words && !out->model)) return fail(c, SIGMA_E_ARG, "null output array");
+    be_d2h(c->stream, out->state, c->state.p, (size_t)c->nvars + 1);
+    be_d2h(c->stream, out->value, c->value.p, c->nlit);
+    if (c->hsc.n_trail) be_d2h(c->stream, out->trail, c->trail.p, (size_t)c->hsc.n_trail * 4);
+    if (c->model_words) be_d2h(c->stream, out->model, c->model.p, (size_t)c->model_words * 4);
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
+    return SIGMA_OK;
+}
+
 int sigma_watches_sizes(sigma_ctx *c, int priorbins, sigma_watches *sz)
 {
     if (!c || !sz || priorbins < 0 || priorbins > 3) return SIGMA_E_ARG;
     if (!c->executed) return fail(c, SIGMA_E_ARG, "no result: sigma_execute did not complete");
     be_bind(c->device);
     CK(build_watches(c, (uint32_t)priorbins));
-    sz->nlit = c->nlit; sz->n_records = c->wt_records;
+    sz->nlit = c->wt_nlit; sz->n_records = c->wt_records;
     return SIGMA_OK;
 }
 
@@ -1418,14 +1462,14 @@ int sigma_download_watches(sigma_ctx *c, sigma_watches *out)
     if (!c || !out) return SIGMA_E_ARG;
     if (!c->executed || c->wt_code < 0) return fail(c, SIGMA_E_ARG, "sigma_download_watches without sigma_watches_sizes");
     be_bind(c->device);
-    const bool small = out->offs_cap < (uint64_t)c->nlit + 1 || out->records_cap < c->wt_records;
-    out->nlit = c->nlit; out->n_records = c->wt_records;
+    const bool small = out->offs_cap < (uint64_t)c->wt_nlit + 1 || out->records_cap < c->wt_records;
+    out->nlit = c->wt_nlit; out->n_records = c->wt_records;
     if (small) return fail(c, SIGMA_E_NOSPACE, "watch buffers too small (required sizes filled in)");
     if (!out->offs || (c->wt_records && !out->records)) return fail(c, SIGMA_E_ARG, "null output array");
-    be_d2h(c->stream, out->offs, c->ot_off.p, (size_t)c->nlit * 4);
+    be_d2h(c->stream, out->offs, c->ot_off.p, (size_t)c->wt_nlit * 4);
     if (c->wt_records) be_d2h(c->stream, out->records, c->wt_rec.p, c->wt_records * 16);
     if (ctx_sync(c)) return SIGMA_E_CUDA;
-    out->offs[c->nlit] = (uint32_t)c->wt_records;
+    out->offs[c->wt_nlit] = (uint32_t)c->wt_records;
     return SIGMA_OK;
 }
 

@@ -192,6 +192,8 @@ public:
 		sigma_result_sizes(ctx, &sz);
 		inf.nClauses = sz.n_clauses; inf.nLiterals = (uint32)sz.n_literals;
 		inf.unassigned = sz.unassigned; inf.maxFrozen = sz.max_frozen; inf.maxMelted = sz.max_melted;
+		// the solver state first (state / value / root trail / model stack): the SAT-by-elimination check, the statistics and
+		// vmap.initiate() of map(true) read it before any clause comes back
 		const uint32 oldtrail = trail.size();
 		trail.resize(sz.trail_size);
 		model.resolved.resize((uint32)sz.model_size);
@@ -200,13 +202,61 @@ public:
 		out.trail_cap = sz.trail_size; out.model_cap = sz.model_size;
 		if (!out.trail) out.trail = (uint32_t*)st.data();
 		if (!out.model) out.model = (uint32_t*)st.data();
+		rc = sigma_download_state(ctx, &out);
+		if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_state");
+		for (uint32 v = 1; v <= V; ++v) sp->state[v].state = st[v];
+		for (uint32 i = oldtrail; i < trail.size(); ++i) sp->level[ABS(trail[i])] = 0;     // enqueueUnit, solve.hpp:379
+		sp->propagated = sz.propagated;
+		tsplit("sigma_download_state");
+		sigma_report rep;
+		sigma_get_report(ctx, &rep);
+		if (opts.profile_simplifier) {
+			// -profilesimplifier (statistics.cpp:34-42): the reference accumulates host milliseconds per stage
+			// (timer.pstart/pstop around createOT, the ordering, sortOT, SUB, VE, ERE, shrinkSimp); here the same fields
+			// receive the CUDA-event milliseconds of the corresponding kernel groups
+			timer.cot += rep.stage_ms[SIGMA_T_OT_HIST] + rep.stage_ms[SIGMA_T_OT_SCAN] + rep.stage_ms[SIGMA_T_OT_SCATTER] +
+			             rep.stage_ms[SIGMA_T_OT_ORDER] + rep.stage_ms[SIGMA_T_OT_UPDATE];
+			timer.vo += rep.stage_ms[SIGMA_T_VO];
+			timer.sot += rep.stage_ms[SIGMA_T_SOT];
+			timer.sub += rep.stage_ms[SIGMA_T_SUB];
+			timer.ve += rep.stage_ms[SIGMA_T_VE] + rep.stage_ms[SIGMA_T_NBH];
+			timer.ere += rep.stage_ms[SIGMA_T_ERE];
+			timer.gc += rep.stage_ms[SIGMA_T_GC] + rep.stage_ms[SIGMA_T_EXPORT];   // in ms (the reference adds seconds here, simplify.cpp:246)
+		}
+#ifdef STATISTICS
+		BVESTATS& b = stats.simplify.bve;
+		b.pures += rep.pures; b.inverters += rep.inverters; b.andors += rep.andors; b.ites += rep.ites; b.xors += rep.xors;
+		b.funs += rep.funs; b.resolutions += rep.resolutions;
+		stats.simplify.sub.subsumed += rep.subsumed; stats.simplify.sub.strengthened += rep.strengthened;
+#endif
+	}
 
-		// newBeginning() (simplify.cpp:249-268) on the device too when no variable mapping follows (simplify.cpp:215-216):
-		// the CLAUSE records, orgs and learnts arrive ready-made
+	// simplify.cpp:215-218: `if (canMap()) map(true); else newBeginning();` and rebuildWT() - from the device when possible
+	// (newBeginningDone / watchesDone say what was done here; the caller runs the reference's own code for the rest)
+	void sigmaHandBack() {
+		const uint32 V = inf.maxVar;
+		int rc;
+		sigma_formula sz = {};
+		sigma_result_sizes(ctx, &sz);
 		const char* hn = getenv("SIGMA_HOST_NEWBEGINNING");
 		newBeginningDone = false;
 		watchesDone = false;
-		if (!(hn && hn[0] == '1') && inf.unassigned && inf.nClauses && !canMap() && !opts.aggr_cnf_sort) {
+		if (!(hn && hn[0] == '1') && inf.unassigned && inf.nClauses && !opts.aggr_cnf_sort) {
+			// map(true), map.cpp:24-46: the mapping is computed on the host exactly as the reference does, the clauses come back
+			// in the new numbering (mapLit on every literal, sclause.cpp:34-35 / map.hpp:195-205)
+			const bool mapping = canMap();
+			if (mapping) {
+				assert(!LEVEL);
+				stats.mapping.calls++;
+				vmap.initiate(sp);
+				vmap.mapOrgs(model.lits);
+				if (assumptions.size()) vmap.mapOrgs(assumptions);
+				if (ifrozen.size()) vmap.mapShrinkVars(ifrozen);
+				vmap.mapTransitive(last.transitive.literals);
+				rc = sigma_set_var_map(ctx, *vmap, vmap.numVars());
+				if (rc != SIGMA_OK) sigmaFail(rc, "sigma_set_var_map");
+				tsplit("map(true): vmap");
+			}
 			sigma_cnf_out co = {};
 			rc = sigma_cnf_out_sizes(ctx, &co);
 			if (rc != SIGMA_OK) sigmaFail(rc, "sigma_cnf_out_sizes");
@@ -230,11 +280,11 @@ public:
 			tsplit("cm.init + bulk alloc");
 			const bool deviceWT = !(hw && hw[0] == '1') && sigma_watches_sizes(ctx, opts.simplify_priorbins, &ws) == SIGMA_OK;
 			tsplit("device newBeginning + rebuildWT");
-			rc = sigma_download_cnf(ctx, &co, &out);
+			sigma_formula none = {};                                           // clause database only: the state came back before
+			rc = sigma_download_cnf(ctx, &co, &none);
 			tsplit("sigma_download_cnf");
 			if (pinned) sigma_host_unregister(co.cm);
 			if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_cnf");
-			watchesDone = false;
 			if (deviceWT) {
 				wtoffs.resize(ws.nlit + 1);
 				wtrecs.resize(ws.n_records ? ws.n_records : 1);
@@ -244,9 +294,10 @@ public:
 				if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download_watches");
 				tsplit("sigma_download_watches");
 				// the lists arrive ready-made, in push order; Vec<WATCH> by Vec<WATCH> (solvetypes.hpp:31-32), a few host threads
-				// side by side (one allocation per list)
-				wt.resize(inf.nDualVars);
-				const uint32 nl = inf.nDualVars < ws.nlit ? inf.nDualVars : ws.nlit;
+				// side by side (one allocation per list).  ws.nlit == inf.nDualVars, after map(true) the new one
+				if (wtFreer.joinable()) wtFreer.join();
+				wt.resize(ws.nlit);
+				const uint32 nl = ws.nlit;
 				auto fill = [this](const uint32 lo, const uint32 hi) {
 					for (uint32 lit = lo; lit < hi; ++lit) {
 						const uint32 n = wtoffs[lit + 1] - wtoffs[lit];
@@ -264,15 +315,21 @@ public:
 				watchesDone = true;
 				tsplit("watch lists into wt");
 			}
-			for (uint32 v = 1; v <= V; ++v) if (sub[v]) sp->state[v].subsume = 1;   // mark_ssubsume, sclause.hpp:209-215
+			for (uint32 v = 1; v <= V; ++v) if (sub[v]) sp->state[v].subsume = 1;   // mark_ssubsume, sclause.hpp:209-215 (old numbering)
 			stats.literals.original = co.lits_original; stats.literals.learnt = co.lits_learnt;
 			stats.clauses.original = orgs.size(); stats.clauses.learnt = learnts.size();
 			scnf.destroy();
 			newBeginningDone = true;
-			if (verbose >= 2) printf("c  sigma_b200: clause database built on the device (%u originals, %u learnts)\n", orgs.size(), learnts.size());
+			if (verbose >= 2) printf("c  sigma_b200: clause database built on the device (%u originals, %u learnts%s)\n", orgs.size(), learnts.size(), mapping ? ", mapped" : "");
+			if (mapping) sigmaMapTail();
 		}
 		else {
-			// receive into a fresh SCNF exactly like shrinkSimp() builds one (simplify.cpp:235-247)
+			// receive into a fresh SCNF exactly like shrinkSimp() builds one (simplify.cpp:235-247); map(true) / newBeginning() and
+			// rebuildWT() are then the reference's own
+			sigma_formula out = {};
+			out.state = st.data(); out.value = (int8_t*)sp->value; out.trail = trail.size() ? trail.data() : (uint32_t*)st.data();
+			out.model = model.resolved.size() ? model.resolved.data() : (uint32_t*)st.data();
+			out.trail_cap = sz.trail_size; out.model_cap = sz.model_size;
 			SCNF fresh;
 			fresh.init(sz.n_clauses ? sz.n_clauses : 1, sz.n_literals ? sz.n_literals : 1);
 			if (sz.n_buckets) fresh.STYPE::alloc(sz.n_buckets);
@@ -285,30 +342,72 @@ public:
 			if (rc != SIGMA_OK) sigmaFail(rc, "sigma_download");
 			fresh.migrateTo(scnf);
 		}
-		for (uint32 v = 1; v <= V; ++v) sp->state[v].state = st[v];
-		for (uint32 i = oldtrail; i < trail.size(); ++i) sp->level[ABS(trail[i])] = 0;     // enqueueUnit, solve.hpp:379
-		sp->propagated = sz.propagated;
-		sigma_report rep;
-		sigma_get_report(ctx, &rep);
-		if (opts.profile_simplifier) {
-			// -profilesimplifier (statistics.cpp:34-42): the reference accumulates host milliseconds per stage
-			// (timer.pstart/pstop around createOT, the ordering, sortOT, SUB, VE, ERE, shrinkSimp); here the same fields
-			// receive the CUDA-event milliseconds of the corresponding kernel groups
-			timer.cot += rep.stage_ms[SIGMA_T_OT_HIST] + rep.stage_ms[SIGMA_T_OT_SCAN] + rep.stage_ms[SIGMA_T_OT_SCATTER] +
-			             rep.stage_ms[SIGMA_T_OT_ORDER] + rep.stage_ms[SIGMA_T_OT_UPDATE];
-			timer.vo += rep.stage_ms[SIGMA_T_VO];
-			timer.sot += rep.stage_ms[SIGMA_T_SOT];
-			timer.sub += rep.stage_ms[SIGMA_T_SUB];
-			timer.ve += rep.stage_ms[SIGMA_T_VE] + rep.stage_ms[SIGMA_T_NBH];
-			timer.ere += rep.stage_ms[SIGMA_T_ERE];
-			timer.gc += rep.stage_ms[SIGMA_T_GC] + rep.stage_ms[SIGMA_T_EXPORT];   // in ms (the reference adds seconds here, simplify.cpp:246)
+	}
+
+	// the rest of Solver::map(true) after its newBeginning() (map.cpp:47-121), unchanged
+	void sigmaMapTail() {
+		// map trail, queue and heap
+		vmap.mapShrinkLits(trail);
+		sp->propagated = trail.size();
+		const uint32 firstFrozen = vmap.firstL0();
+		// - VMTF
+		vmtf.map(*vmap, firstFrozen, vmap.size());
+		vmap.mapShrinkVars(bumps);
+		// - VSIDS
+		uVec1D tmp;
+		while (vsidsheap.size()) {
+			uint32 x = vsidsheap.pop();
+			if (x == firstFrozen) continue;
+			uint32 mx = vmap.mapped(x);
+			if (mx) tmp.push(mx);
 		}
-#ifdef STATISTICS
-		BVESTATS& b = stats.simplify.bve;
-		b.pures += rep.pures; b.inverters += rep.inverters; b.andors += rep.andors; b.ites += rep.ites; b.xors += rep.xors;
-		b.funs += rep.funs; b.resolutions += rep.resolutions;
-		stats.simplify.sub.subsumed += rep.subsumed; stats.simplify.sub.strengthened += rep.strengthened;
-#endif
+		vmap.mapShrinkVars(vsids.scores);
+		vsidsheap.rebuild(tmp);
+		// - CHB
+		tmp.clear();
+		while (chbheap.size()) {
+			uint32 x = chbheap.pop();
+			if (x == firstFrozen) continue;
+			uint32 mx = vmap.mapped(x);
+			if (mx) tmp.push(mx);
+		}
+		vmap.mapShrinkVars(chb.scores);
+		vmap.mapShrinkVars(chb.conflicts);
+		chbheap.rebuild(tmp);
+		// shrink others without mapping
+		eligible.clear(true);
+		eligible.reserve(vmap.numVars());
+		elected.clear(true);
+		elected.reserve(vmap.numVars());
+		occurs.clear(true);
+		dlevel.clear(true);
+		dlevel.reserve(vmap.numVars());
+		dlevel.push(level_t());
+		// map search space
+		SP* newSP = new SP(vmap.size(), opts.polarity);
+		vmap.mapSP(newSP);
+		delete sp;
+		sp = newSP;
+		// map model and proof variables
+		vmap.mapShrinkVars(vorg);
+		model.init(vorg);
+		if (opts.proof_en) proof.init(sp, vorg);
+		// update phase-saving counters
+		sp->trailpivot = 0, last.rephase.best = last.rephase.target = 0;
+		for (uint32 v = 1; v <= vmap.numVars(); ++v) {
+			if (sp->state[v].state) continue;
+			Phase_t& ph = sp->phase[v];
+			if (!PHASE_UNASSIGNED(ph.best)) last.rephase.best++;
+			if (!PHASE_UNASSIGNED(ph.target)) last.rephase.target++;
+		}
+		stats.mapping.compressed += inf.maxVar - vmap.numVars();
+		LOG2(2, " Variable mapping compressed %d to %d", inf.maxVar, vmap.numVars());
+		inf.maxVar = vmap.numVars();
+		inf.nDualVars = V2L(inf.maxVar + 1);
+		inf.maxFrozen = inf.maxMelted = inf.maxSubstituted = 0;
+		vmap.destroy();
+		printStats(1, 'a', CGREEN2);
+		tsplit("map(true): search state");
 	}
 
 	// Solver::simplifying() (simplify.cpp:155-233) with :180-210 replaced
@@ -343,7 +442,8 @@ public:
 		last.shrink.removed = stats.shrunken;
 		if (inf.maxFrozen > sp->simplified) stats.units.forced += inf.maxFrozen - sp->simplified;
 		if (!inf.unassigned || !inf.nClauses) { SET_SAT; printStats(1, 's', CGREEN); return; }
-		if (newBeginningDone) { /* simplify.cpp:216 happened on the device */ }
+		sigmaHandBack();
+		if (newBeginningDone) { /* simplify.cpp:215-216 happened on the device (map(true) included) */ }
 		else if (canMap()) map(true);
 		else newBeginning();
 		tsplit("state / statistics");

@@ -143,6 +143,8 @@ def load(path=None):
     lib.sigma_parse_dimacs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SigmaDimacs)]
     lib.sigma_parse_download.argtypes = [C.c_void_p, C.POINTER(SigmaDimacs)]
     lib.sigma_upload_parsed.argtypes = [C.c_void_p, C.POINTER(SigmaOpts)]
+    lib.sigma_set_var_map.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.sigma_download_state.argtypes = [C.c_void_p, C.POINTER(SigmaFormula)]
     lib.sigma_watches_sizes.argtypes = [C.c_void_p, C.c_int, C.POINTER(SigmaWatches)]
     lib.sigma_download_watches.argtypes = [C.c_void_p, C.POINTER(SigmaWatches)]
     lib.sigma_execute.argtypes = [C.c_void_p]
@@ -388,6 +390,27 @@ class Sigma:
         self._check(self.lib.sigma_upload_parsed(self.ctx, C.byref(o)))
         src = B.Boundary(nvars=nvars or 0, vorg=None if nvars is None else np.arange(nvars + 1, dtype=np.uint32), opts=dict(B.DEFAULT_OPTS, **(opts or {})))
         self._keep = (src, o, None)
+
+    def set_var_map(self, vmap, new_nvars):
+        """map(true): clause database and watch table in the numbering vmap[old var] -> new var (None switches back)."""
+        if vmap is None:
+            self._check(self.lib.sigma_set_var_map(self.ctx, None, 0))
+        else:
+            m = np.ascontiguousarray(vmap, dtype=np.uint32)
+            self._check(self.lib.sigma_set_var_map(self.ctx, _ptr(m), int(new_nvars)))
+
+    def download_state(self):
+        """state / value / trail / model after execute (no clause arrays)."""
+        sz = SigmaFormula()
+        self._check(self.lib.sigma_result_sizes(self.ctx, C.byref(sz)))
+        out = B.Boundary(status=0, nvars=sz.nvars)
+        out.state, out.value = np.empty(sz.nvars + 1, np.uint8), np.empty(2 * sz.nvars + 2, np.int8)
+        out.trail, out.model = np.empty(int(sz.trail_size), np.uint32), np.empty(int(sz.model_size), np.uint32)
+        f = SigmaFormula()
+        f.state, f.value, f.trail, f.model = _ptr(out.state), _ptr(out.value), _ptr(out.trail), _ptr(out.model)
+        f.trail_cap, f.model_cap = sz.trail_size, sz.model_size
+        self._check(self.lib.sigma_download_state(self.ctx, C.byref(f)))
+        return out
 
     def watches(self, priorbins=1):
         """rebuildWT(priorbins) on the device; call before download_cnf.  Returns (offs uint32[nlit + 1], records uint32[n, 4] =

@@ -86,14 +86,14 @@ void be_cm_flags(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n
     for (uint32_t i : item_order(n)) learnt[i] = (arena[refs[i]] & SG_ST_MASK) == SG_LEARNT;
 }
 void be_cm_write(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n, uint64_t, const uint32_t *learnt_before,
-                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume)
+                 int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume, const uint32_t *vmap)
 {
     g_launches++;
     counts[0] = counts[1] = 0;
     for (uint32_t i : item_order(n)) {
         const uint64_t r = refs[i];
         const uint32_t *src = arena + r;
-        sg_cm_write(src, cm + r + i, lbd_tier1);
+        sg_cm_write(src, cm + r + i, lbd_tier1, vmap);
         if ((src[0] & SG_ST_MASK) == SG_LEARNT) { learnts[learnt_before[i]] = r + i; counts[1] += src[2]; }
         else { orgs[i - learnt_before[i]] = r + i; counts[0] += src[2]; }
         if (subsume && (src[0] & SG_ADDED))
@@ -606,7 +606,7 @@ void be_wt_fill(void *, uint32_t *cm, const uint32_t *arena, const uint64_t *ref
         if (g > 2) seq += totals[2];
         const uint64_t cref = r + i;
         uint32_t *l = cm + cref + SG_CM_HDR;
-        if (size != 2u) sg_sort_clause(l, (int)size, value);
+        if (size != 2u && value) sg_sort_clause(l, (int)size, value);
         const uint32_t a = l[0], b = l[1];
         hdr[seq].x = 2u * seq; hdr[seq].y = 2u; hdr[seq].z = 0u; hdr[seq].w = 0u;
         lits[2 * seq] = SG_FLIP(a); lits[2 * seq + 1] = SG_FLIP(b);

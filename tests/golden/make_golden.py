@@ -64,6 +64,9 @@ CASES = [
 ]
 
 
+# cases that also get the clause database + watch table after map(true) (ref_harness --cmmap, a second run of the binary)
+CMM_CASES = {"gates_small", "xorphp_small", "later_gates", "fuzz_units4"}
+
 # cases that also get the pre-awaken() clause database (ref_harness --cmin)
 CM_CASES = {"gates_small", "ksat5_planted", "xorphp_small", "fuzz_units4", "ere_fuzz", "later_ksat3", "later_gates"}
 
@@ -97,6 +100,9 @@ def main():
                                capture_output=True, text=True)
             print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"rc={r.returncode}",
                   os.path.getsize(fin), os.path.getsize(fout))
+            if name in CMM_CASES:
+                subprocess.run([REF, cnf, *base, "-quiet", f"--cmmap={os.path.join(HERE, name + '.cmm')}"] + [o for o in opts if o != "+ere"],
+                               capture_output=True, text=True)
 
 
 if __name__ == "__main__":

@@ -261,3 +261,55 @@ def test_gpu_watch_table_matches_reference(cuda_lib):
         s.execute()
         _check_watches(s, name)
     s.close()
+
+
+# ---- newBeginning() under variable mapping: map(true) (reference map.cpp:24-46) ------------------------------------------------
+CMM_CASES = ["gates_small", "xorphp_small", "later_gates", "fuzz_units4"]
+
+
+def _check_mapped(s, name):
+    sec = _read_sections(os.path.join(GOLDEN, name + ".cmm"))
+    vmap = np.frombuffer(sec["vmap"], np.uint32)
+    new_nvars = int(np.frombuffer(sec["vmapn"], np.uint64)[0])
+    st = s.download_state()
+    # vmap.initiate (map.hpp:78-95) from the downloaded state: active variables in order, plus the first root-assigned one
+    mine, n, first = np.zeros_like(vmap), 0, 0
+    for v in range(1, st.nvars + 1):
+        if not st.state[v]:
+            n += 1; mine[v] = n
+        elif not first and st.value[2 * v] >= 0:
+            first = v; n += 1; mine[v] = n
+    assert n == new_nvars and np.array_equal(mine, vmap), name
+    s.set_var_map(vmap, new_nvars)
+    code = int(np.frombuffer(sec["wtcode"], np.uint64)[0])
+    offs, rec = s.watches(code)
+    assert np.array_equal(offs, np.frombuffer(sec["wtoff"], np.uint32)), name
+    assert np.array_equal(rec, np.frombuffer(sec["wtrec"], np.uint32).reshape(-1, 4)), name
+    exp_orgs, exp_learnts = np.frombuffer(sec["orgs"], np.uint64), np.frombuffer(sec["learnts"], np.uint64)
+    cm2 = np.frombuffer(sec["cm2"], np.uint32)
+    db, _ = s.download_cnf()
+    mask = np.full(cm2.size, 0xFFFFFFFF, dtype=np.uint32)
+    mask[np.concatenate([exp_orgs, exp_learnts]).astype(np.int64)] = 0xFFFFFF3F
+    assert np.array_equal(db.cm & mask, cm2 & mask), name
+    assert np.array_equal(db.orgs, exp_orgs) and np.array_equal(db.learnts, exp_learnts)
+    s.set_var_map(None, 0)                                   # back to the unmapped database
+    _check_new_beginning(s, name) if name in CM_CASES else None
+
+
+def test_emul_mapped_new_beginning_matches_reference(emul_lib):
+    s = sigma.Sigma(0, emul_lib)
+    for name in CMM_CASES:
+        bi = B.read(os.path.join(GOLDEN, name + ".in"))
+        s.upload(bi); s.execute()
+        _check_mapped(s, name)
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_mapped_new_beginning_matches_reference(cuda_lib):
+    s = sigma.Sigma(0, cuda_lib)
+    for name in CMM_CASES:
+        bi = B.read(os.path.join(GOLDEN, name + ".in"))
+        s.upload(bi); s.execute()
+        _check_mapped(s, name)
+    s.close()
