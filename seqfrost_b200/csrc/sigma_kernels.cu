@@ -24,6 +24,8 @@ struct BeStream {
     cudaStream_t st;
     unsigned long long launches;
     char err[256];
+    void *scratch;                  /* be_sort_units (large n): kept between calls - cudaMalloc / cudaFree inside a stage cost up */
+    size_t scratch_bytes;           /* to a second now and then (seen as 34 -> 1500 ms ERE stages on the 5M-gate circuit) */
 };
 
 inline void note_err(void *s, const char *what)
@@ -2228,7 +2230,7 @@ int be_init(int device, void **stream_out, char *err, size_t errlen)
     *stream_out = (void *)b;
     return 0;
 }
-void be_shutdown(void *s) { if (s) { cudaStreamDestroy(ST(s)); delete (BeStream *)s; } }
+void be_shutdown(void *s) { if (s) { if (((BeStream *)s)->scratch) cudaFree(((BeStream *)s)->scratch); cudaStreamDestroy(ST(s)); delete (BeStream *)s; } }
 void be_bind(int device) { cudaSetDevice(device); }
 void *be_malloc(size_t bytes)
 {
@@ -2610,22 +2612,24 @@ void be_sort_units(void *s, const SgView &v, uint32_t n)
     const bool radix = force && force[0] == '1';
     if (n <= 32 && !radix) { LAUNCH(k_sort_units_small, 1, 1, s, v, n); return; }
     if (n <= 2048 && !radix) { LAUNCH(k_sort_units_block, 1, 512, s, v, n); return; }
-    /* rare: LSD by (seq, eidx) through an index permutation */
-    uint32_t *keys = (uint32_t *)be_malloc(4ull * n), *idx = (uint32_t *)be_malloc(4ull * n);
-    uint32_t *tk = (uint32_t *)be_malloc(4ull * n), *tv = (uint32_t *)be_malloc(4ull * n);
-    uint32_t *tmp = (uint32_t *)be_malloc(4ull * be_sort_tmp_words(n));
-    SgUnit *ut = (SgUnit *)be_malloc(sizeof(SgUnit) * (size_t)n);
-    if (!keys || !idx || !tk || !tv || !tmp || !ut) { BeStream *b = (BeStream *)s; snprintf(b->err, sizeof b->err, "be_sort_units: out of memory"); }
-    else {
-        for (int which = 0; which < 2; ++which) {
-            LAUNCH(k_units_keys, blocks_for(n), TPB, s, v, n, keys, idx, which);
-            be_sort_pairs(s, keys, idx, n, tk, tv, tmp, 32);
-        }
-        LAUNCH(k_units_gather, blocks_for(n), TPB, s, v, n, idx, ut);
-        be_d2d(s, v.ubuf, ut, sizeof(SgUnit) * (size_t)n);
+    /* rare: LSD by (seq, eidx) through an index permutation; the scratch memory belongs to the context and only ever grows */
+    BeStream *b = (BeStream *)s;
+    const size_t words = 4 * (size_t)n + be_sort_tmp_words(n) + 64, bytes = 4 * words + sizeof(SgUnit) * (size_t)n + 256;
+    if (b->scratch_bytes < bytes) {
+        cudaStreamSynchronize(ST(s));
+        if (b->scratch) cudaFree(b->scratch);
+        b->scratch = be_malloc(bytes + bytes / 2);
+        b->scratch_bytes = b->scratch ? bytes + bytes / 2 : 0;
     }
-    cudaStreamSynchronize(ST(s));
-    be_free(keys); be_free(idx); be_free(tk); be_free(tv); be_free(tmp); be_free(ut);
+    if (!b->scratch) { snprintf(b->err, sizeof b->err, "be_sort_units: out of memory"); return; }
+    uint32_t *keys = (uint32_t *)b->scratch, *idx = keys + n, *tk = idx + n, *tv = tk + n, *tmp = tv + n;
+    SgUnit *ut = (SgUnit *)(((uintptr_t)(tmp + be_sort_tmp_words(n) + 64) + 15) & ~(uintptr_t)15);
+    for (int which = 0; which < 2; ++which) {
+        LAUNCH(k_units_keys, blocks_for(n), TPB, s, v, n, keys, idx, which);
+        be_sort_pairs(s, keys, idx, n, tk, tv, tmp, 32);
+    }
+    LAUNCH(k_units_gather, blocks_for(n), TPB, s, v, n, idx, ut);
+    be_d2d(s, v.ubuf, ut, sizeof(SgUnit) * (size_t)n);
 }
 
 void be_count_live(void *s, const SgView &v)
