@@ -35,6 +35,8 @@ EXPORTS = [
     "sigma_create", "sigma_destroy", "sigma_default_opts", "sigma_strerror", "sigma_last_error", "sigma_run",
     "sigma_upload", "sigma_execute", "sigma_result_sizes", "sigma_download", "sigma_get_report", "sigma_host_alloc",
     "sigma_host_free", "sigma_host_register", "sigma_host_unregister", "sigma_set_interrupt_flag", "sigma_set_stop", "sigma_snapshot", "sigma_upload_cnf", "sigma_extracted_sizes", "sigma_cnf_out_sizes", "sigma_download_cnf",
+    "sigma_parse_dimacs", "sigma_parse_download", "sigma_upload_parsed", "sigma_watches_sizes", "sigma_download_watches",
+    "sigma_set_var_map", "sigma_download_state",
 ]
 
 

@@ -131,6 +131,9 @@ def _abi_errors(lib_path):
     assert code_of(lambda b2, f2: set_(f2, propagated=f2.trail_size + 1)) == sigma.SIGMA_E_ARG
     assert code_of(lambda b2, f2: set_(f2, n_literals=f2.n_buckets)) == sigma.SIGMA_E_ARG
     assert code_of(lambda b2, f2: set_(f2, n_buckets=3 * f2.n_clauses - 1)) == sigma.SIGMA_E_ARG
+    # the device store uses 32-bit bucket offsets (the reference's S_REF is 64-bit): a larger arena is refused, not truncated
+    assert code_of(lambda b2, f2: set_(f2, n_buckets=1 << 32)) == sigma.SIGMA_E_UNSUPPORTED
+    assert code_of(lambda b2, f2: set_(f2, nvars=1 << 29)) == sigma.SIGMA_E_UNSUPPORTED
     # ... then refs / size words that leave the arena: caught on the device by the ingest kernels
 
     def bad_ref(b2, f2):
@@ -196,14 +199,15 @@ def test_header_symbols_are_exported(cuda_lib):
 def test_ctypes_mirror_matches_the_header(tmp_path):
     """sizeof of the five ABI structs as gcc sees them == the ctypes mirrors in seqfrost_b200/sigma.py."""
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "sigma_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(sigma_opts), '
-                   'sizeof(sigma_formula), sizeof(sigma_report), sizeof(sigma_cnf), sizeof(sigma_cnf_out));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "sigma_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sigma_opts), '
+                   'sizeof(sigma_formula), sizeof(sigma_report), sizeof(sigma_cnf), sizeof(sigma_cnf_out), sizeof(sigma_dimacs), '
+                   'sizeof(sigma_watches));return 0;}\n')
     exe = tmp_path / "sz"
     inc = os.path.join(os.path.dirname(GOLDEN), "..", "include")
     subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [C.sizeof(sigma.SigmaOpts), C.sizeof(sigma.SigmaFormula), C.sizeof(sigma.SigmaReport),
-                   C.sizeof(sigma.SigmaCnf), C.sizeof(sigma.SigmaCnfOut)]
+                   C.sizeof(sigma.SigmaCnf), C.sizeof(sigma.SigmaCnfOut), C.sizeof(sigma.SigmaDimacs), C.sizeof(sigma.SigmaWatches)]
 
 
 def _gapped(b: B.Boundary, pad=2):
