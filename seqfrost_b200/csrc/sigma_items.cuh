@@ -1156,38 +1156,43 @@ SG_HDN inline void sg_sub_item(const SgView &v, uint32_t eidx)
 /* ------------------------------------------------------------------------------------------ */
 /* BVE: decision + resolvent counting (bounded.cpp:41-160 and the gate headers)                 */
 /* ------------------------------------------------------------------------------------------ */
-SG_HD int sg_merge_count(uint32_t x, const uint32_t *d1, int n1, const uint32_t *d2, int n2)
-{   /* simplify.hpp:228-260; x is a VARIABLE */
-    int i = 0, j = 0, len = n1 + n2 - 2;
-    while (i < n1 && j < n2) {
-        const uint32_t l1 = d1[i], l2 = d2[j];
-        const uint32_t v1 = SG_ABS(l1), v2 = SG_ABS(l2);
-        if (v1 == x) i++;
-        else if (v2 == x) j++;
-        else if ((l1 ^ l2) == 1u) return 0;
-        else if (v1 < v2) i++;
-        else if (v2 < v1) j++;
-        else { i++; j++; len--; }
+/* Clauses keep their literals in ascending code order (code = 2*var + sign), so two clauses can be walked like two sorted
+ * key lists.  At every step the smaller code is consumed, or both when they are equal (a literal the clauses share); codes
+ * that differ in the sign bit only make the resolvent a tautology; the pivot's own two codes are stepped over.  The walk
+ * ends when either clause is exhausted, as in the reference (simplify.hpp:181-260): what is left of the other one cannot
+ * hold a shared or a clashing variable. */
+SG_HD int sg_merge_count(uint32_t pivot, const uint32_t *a, int na, const uint32_t *b, int nb)
+{   /* size of the resolvent on VARIABLE `pivot`, 0 for a tautology */
+    int ia = 0, ib = 0, shared = 0;
+    while (ia < na && ib < nb) {
+        const uint32_t ka = a[ia], kb = b[ib];
+        const bool pa = (ka >> 1) == pivot, pb = (kb >> 1) == pivot;
+        if (pa | pb) { ia += pa; ib += pb; continue; }
+        const uint32_t diff = ka ^ kb;
+        if (diff == 1u) return 0;
+        shared += diff == 0u;
+        ia += ka <= kb;
+        ib += kb <= ka;
     }
-    return len;
+    return na + nb - 2 - shared;
 }
 
-SG_HD int sg_merge_emit(uint32_t x, const uint32_t *d1, int n1, const uint32_t *d2, int n2, uint32_t *out, uint32_t *sig_out)
-{   /* simplify.hpp:181-226; returns -1 for a tautology, else the resolvent size */
-    int i = 0, j = 0, n = 0;
+SG_HD int sg_merge_emit(uint32_t pivot, const uint32_t *a, int na, const uint32_t *b, int nb, uint32_t *out, uint32_t *sig_out)
+{   /* the same walk writing the resolvent and its signature; -1 for a tautology, else the resolvent size */
+    int ia = 0, ib = 0, n = 0;
     uint32_t sig = 0;
-    while (i < n1 && j < n2) {
-        const uint32_t l1 = d1[i], l2 = d2[j];
-        const uint32_t v1 = SG_ABS(l1), v2 = SG_ABS(l2);
-        if (v1 == x) i++;
-        else if (v2 == x) j++;
-        else if ((l1 ^ l2) == 1u) return -1;
-        else if (v1 < v2) { i++; out[n++] = l1; sig |= SG_HASH(l1); }
-        else if (v2 < v1) { j++; out[n++] = l2; sig |= SG_HASH(l2); }
-        else { i++; j++; out[n++] = l1; sig |= SG_HASH(l1); }
+    while (ia < na && ib < nb) {
+        const uint32_t ka = a[ia], kb = b[ib];
+        const bool pa = (ka >> 1) == pivot, pb = (kb >> 1) == pivot;
+        if (pa | pb) { ia += pa; ib += pb; continue; }
+        if ((ka ^ kb) == 1u) return -1;
+        const uint32_t k = ka < kb ? ka : kb;
+        out[n++] = k, sig |= SG_HASH(k);
+        ia += ka <= kb;
+        ib += kb <= ka;
     }
-    while (i < n1) { const uint32_t l1 = d1[i++]; if (SG_ABS(l1) != x) { out[n++] = l1; sig |= SG_HASH(l1); } }
-    while (j < n2) { const uint32_t l2 = d2[j++]; if (SG_ABS(l2) != x) { out[n++] = l2; sig |= SG_HASH(l2); } }
+    for (; ia < na; ++ia) if ((a[ia] >> 1) != pivot) { out[n++] = a[ia]; sig |= SG_HASH(a[ia]); }
+    for (; ib < nb; ++ib) if ((b[ib] >> 1) != pivot) { out[n++] = b[ib]; sig |= SG_HASH(b[ib]); }
     *sig_out = sig;
     return n;
 }
@@ -1329,8 +1334,8 @@ SG_HDN inline uint32_t sg_find_bn_gate(const SgView &v, const SgLane &L, uint32_
     return def;
 }
 
-/* AND/OR gate (and.hpp:27-111); `out_c` is this variable's scratch slice */
-SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx, uint32_t fx, uint32_t *out_c, int orgCls,
+/* AND/OR gate (and.hpp:27-111); `gate_in` is this variable's scratch slice */
+SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx, uint32_t fx, uint32_t *gate_in, int orgCls,
                                    int &nAddedCls, int &nAddedLits)
 {
     const int nd = (int)v.ot_len[dx], nf = (int)v.ot_len[fx];
@@ -1351,7 +1356,7 @@ SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx
         }
         const uint32_t m = sg_ballot(b);
         if (b) {
-            out_c[nout + sg_popc(m & ((1u << L.lane) - 1u))] = imp;
+            gate_in[nout + sg_popc(m & ((1u << L.lane) - 1u))] = imp;
             v.hdr[c].z |= SG_MOLTEN;
         }
         sig |= sg_wor(b ? SG_HASH(imp) : 0u);
@@ -1359,7 +1364,7 @@ SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx
     }
     sg_wsync();
     if (nout > 1) {
-        if (L.lane == 0) { out_c[nout] = fx; sg_sort_lits(out_c, nout + 1); }
+        if (L.lane == 0) { gate_in[nout] = fx; sg_sort_lits(gate_in, nout + 1); }
         nout++;
         sig |= SG_HASH(fx);
         sg_wsync();
@@ -1368,7 +1373,7 @@ SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx
             const sg_u4 h = v.hdr[df[i]];
             if ((h.z & SG_ST_MASK) || (int)h.y != nout || !sg_sig_sub(h.w, sig)) return false;
             const uint32_t *l = v.lits + h.x;
-            for (int q = 0; q < nout; ++q) if (l[q] != out_c[q]) return false;
+            for (int q = 0; q < nout; ++q) if (l[q] != gate_in[q]) return false;
             return true;
         });
         if (k >= 0) {
@@ -1386,21 +1391,24 @@ SG_HDN inline bool sg_find_ao_gate(const SgView &v, const SgLane &L, uint32_t dx
 /* ITE gate (ifthenelse.hpp:26-125) */
 SG_HD void sg_swap(uint32_t &a, uint32_t &b) { const uint32_t t = a; a = b; b = t; }
 
-SG_HDN inline uint32_t sg_fast_equality_check(const SgView &v, const SgLane &L, uint32_t x, uint32_t y, uint32_t z)
-{   /* returns clause id or 0xFFFFFFFF */
-    if (v.ot_len[y] > v.ot_len[z]) sg_swap(y, z);
-    if (v.ot_len[x] > v.ot_len[y]) sg_swap(x, y);
-    const int n = (int)v.ot_len[x];
-    const uint32_t *d = sg_list(v, x);
-    /* sort3 (simplify.hpp:150-157) */
-    { uint32_t a = y < z ? y : z, b = y < z ? z : y; y = a; z = b; }
-    { uint32_t a = x < z ? x : z, b = x < z ? z : x; x = a; z = b; }
-    { uint32_t a = x < y ? x : y, b = x < y ? y : x; x = a; y = b; }
+/* the original ternary clause {a, b, c}, looked for in the shortest of the three occurrence lists (the first of the shortest
+ * ones in the order a, b, c - that is what the reference's two conditional swaps select, and with duplicate clauses in the
+ * formula the list decides which copy is found; ifthenelse.hpp:26-45).  Returns the clause id or 0xFFFFFFFF. */
+SG_HDN inline uint32_t sg_find_ternary(const SgView &v, const SgLane &L, uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t via = a;
+    if (v.ot_len[b] < v.ot_len[via]) via = b;
+    if (v.ot_len[c] < v.ot_len[via]) via = c;
+    /* stored clauses are ascending: compare against (lo, mid, hi) of the three codes */
+    const uint32_t ab_lo = a < b ? a : b, ab_hi = a < b ? b : a;
+    const uint32_t lo = c < ab_lo ? c : ab_lo, hi = c > ab_hi ? c : ab_hi, mid = a ^ b ^ c ^ lo ^ hi;
+    const int n = (int)v.ot_len[via];
+    const uint32_t *d = sg_list(v, via);
     const int k = sg_find_first(L, n, [&](int i) {
         const sg_u4 h = v.hdr[d[i]];
-        if ((h.z & SG_MOLTEN) || (h.z & SG_ST_MASK) || h.y != 3) return false;
+        if (h.y != 3u || (h.z & (SG_MOLTEN | SG_ST_MASK))) return false;
         const uint32_t *l = v.lits + h.x;
-        return l[0] == x && l[1] == y && l[2] == z;
+        return l[0] == lo && l[1] == mid && l[2] == hi;
     });
     return k < 0 ? 0xFFFFFFFFu : d[k];
 }
@@ -1438,9 +1446,9 @@ SG_HDN inline bool sg_find_ite_gate(const SgView &v, const SgLane &L, uint32_t d
             if (SG_ABS(yi) == SG_ABS(zj)) sg_swap(yj, zj);
             if (SG_ABS(zi) == SG_ABS(zj)) continue;
             if (yi != SG_FLIP(yj)) continue;
-            const uint32_t d1 = sg_fast_equality_check(v, L, fx, yi, SG_FLIP(zi));
+            const uint32_t d1 = sg_find_ternary(v, L, fx, yi, SG_FLIP(zi));
             if (d1 == 0xFFFFFFFFu) continue;
-            const uint32_t d2 = sg_fast_equality_check(v, L, fx, yj, SG_FLIP(zj));
+            const uint32_t d2 = sg_find_ternary(v, L, fx, yj, SG_FLIP(zj));
             if (d2 == 0xFFFFFFFFu) continue;
             sg_wsync();
             if (L.lane == 0) { sg_melt(v, ci), sg_melt(v, cj), sg_melt(v, d1), sg_melt(v, d2); }
@@ -1465,28 +1473,24 @@ SG_HD void sg_freeze_arities(const SgView &v, const SgLane &L, uint32_t a, uint3
     sg_freeze_if(v, L, b, [](const sg_u4 &h) { return (int)h.y > 2; });
 }
 
-/* advances `parity` to the next even-popcount value and flips the literals whose bit changed (xor.hpp:26,72-78) */
-SG_HD void sg_next_arity(uint32_t &parity, uint32_t *literals, int size)
+/* An XOR over n variables is 2^(n-1) clauses: one base clause and every copy of it with an even number of literals
+ * negated.  The even-weight masks in ascending order are e(t) = 2t | (popcount(t) & 1), t = 0 .. 2^(n-1)-1 - the order in
+ * which the reference enumerates them (xor.hpp:26,72-78) - so partner t of a base clause is written down directly. */
+SG_HD void sg_xor_partner(const uint32_t *base, int size, uint32_t t, uint32_t *out)
 {
-    const uint32_t oldparity = parity;
-    do { ++parity; } while (sg_popc(parity) & 1);
-    for (int k = 0; k < size; ++k) {
-        const uint32_t bit = 1u << k;
-        if ((parity & bit) != (oldparity & bit)) literals[k] = SG_FLIP(literals[k]);
-    }
+    const uint32_t flips = (t << 1) | (uint32_t)(sg_popc(t) & 1);
+    for (int k = 0; k < size; ++k) out[k] = base[k] ^ ((flips >> k) & 1u);
 }
-/* the list makeArity searches: shortest occurrence list among the pattern's literals, first minimum (xor.hpp:81-92) */
+/* the list a partner is searched in: the first of the shortest occurrence lists of its literals (xor.hpp:81-92) */
 SG_HD uint32_t sg_arity_best(const SgView &v, const uint32_t *literals, int size, uint32_t *sig_out)
 {
-    uint32_t best = literals[0], sig = SG_HASH(literals[0]);
-    int minsize = (int)v.ot_len[best];
-    for (int k = 1; k < size; ++k) {
-        const int lsize = (int)v.ot_len[literals[k]];
+    uint32_t via = literals[0], sig = 0;
+    for (int k = 0; k < size; ++k) {
         sig |= SG_HASH(literals[k]);
-        if (lsize < minsize) { minsize = lsize; best = literals[k]; }
+        if (v.ot_len[literals[k]] < v.ot_len[via]) via = literals[k];
     }
     *sig_out = sig;
-    return best;
+    return via;
 }
 /* original clause of `size` literals made of exactly the pattern's literals (checkArity, xor.hpp:53-68);
  * equal literal sets have equal signatures, so the signature is compared first */
@@ -1502,14 +1506,14 @@ SG_HD bool sg_arity_match(const SgView &v, const sg_u4 &h, const uint32_t *liter
     return true;
 }
 
-SG_HDN inline bool sg_make_arity(const SgView &v, const SgLane &L, uint32_t &parity, uint32_t *literals, int size)
-{   /* xor.hpp:70-102 */
-    sg_next_arity(parity, literals, size);
+/* finds partner clause `pattern` and marks it molten (xor.hpp:70-102) */
+SG_HDN inline bool sg_melt_partner(const SgView &v, const SgLane &L, const uint32_t *pattern, int size)
+{
     uint32_t sig;
-    const uint32_t best = sg_arity_best(v, literals, size, &sig);
-    const int n = (int)v.ot_len[best];
-    const uint32_t *d = sg_list(v, best);
-    const int k = sg_find_first(L, n, [&](int i) { return sg_arity_match(v, v.hdr[d[i]], literals, size, sig); });
+    const uint32_t via = sg_arity_best(v, pattern, size, &sig);
+    const int n = (int)v.ot_len[via];
+    const uint32_t *d = sg_list(v, via);
+    const int k = sg_find_first(L, n, [&](int i) { return sg_arity_match(v, v.hdr[d[i]], pattern, size, sig); });
     if (k < 0) return false;
     sg_melt1(v, L, d[k]);
     return true;
@@ -1520,19 +1524,16 @@ SG_HDN inline bool sg_make_arity(const SgView &v, const SgLane &L, uint32_t &par
  * (freezeArities, xor.hpp:141-142), so the lanes can test different clauses at the same time. */
 SG_HDN inline bool sg_xor_complete(const SgView &v, uint32_t ci, int size)
 {
-    uint32_t lits[24];
-    const uint32_t *l = SG_LITS(v, ci);
-    for (int k = 0; k < size; ++k) lits[k] = l[k];
-    uint32_t parity = 0;
-    int itargets = 1 << (size - 1);
-    while (--itargets) {
-        sg_next_arity(parity, lits, size);
+    uint32_t pattern[24];
+    const uint32_t *base = SG_LITS(v, ci);
+    for (uint32_t t = 1; t < (1u << (size - 1)); ++t) {
+        sg_xor_partner(base, size, t, pattern);
         uint32_t sig;
-        const uint32_t best = sg_arity_best(v, lits, size, &sig);
-        const int n = (int)v.ot_len[best];
-        const uint32_t *d = sg_list(v, best);
+        const uint32_t via = sg_arity_best(v, pattern, size, &sig);
+        const int n = (int)v.ot_len[via];
+        const uint32_t *d = sg_list(v, via);
         bool found = false;
-        for (int i = 0; i < n && !found; ++i) found = sg_arity_match(v, v.hdr[d[i]], lits, size, sig);
+        for (int i = 0; i < n && !found; ++i) found = sg_arity_match(v, v.hdr[d[i]], pattern, size, sig);
         if (!found) return false;
     }
     return true;
@@ -1547,7 +1548,7 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
     const int maxarity = v.o.xor_max_arity;
     if (SG_SIZE(v, dd[0]) - 1 > maxarity) return false;
     const uint32_t var = SG_ABS(dx);
-    uint32_t out_c[24];
+    uint32_t pattern[24];
 #if defined(__CUDA_ARCH__)
     /* when both lists fit one warp, the count of the screen below - original clauses of the two lists with the same size
      * and the same sign-blind signature - is two warp matches and a ballot: lane q looks at entry q of (dx list, fx list) */
@@ -1593,12 +1594,13 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
         if (!m) continue;
         const uint32_t ci = dd[base + sg_ffs(m) - 1];
         const int size = SG_SIZE(v, ci);
-        const uint32_t *l = SG_LITS(v, ci);
-        for (int k = 0; k < size; ++k) out_c[k] = l[k];
-        uint32_t parity = 0;
-        int itargets = 1 << (size - 1);
-        while (--itargets && sg_make_arity(v, L, parity, out_c, size));
-        if (itargets) { sg_freeze_arities(v, L, dx, fx); continue; }      /* cannot happen: ci is complete */
+        const uint32_t *first = SG_LITS(v, ci);
+        bool all = true;
+        for (uint32_t t = 1; all && t < (1u << (size - 1)); ++t) {
+            sg_xor_partner(first, size, t, pattern);
+            all = sg_melt_partner(v, L, pattern, size);
+        }
+        if (!all) { sg_freeze_arities(v, L, dx, fx); continue; }           /* cannot happen: ci is complete */
         sg_melt1(v, L, ci);
         nAddedCls = 0, nAddedLits = 0;
         if (sg_count_pairs(v, L, SG_VE_SUBST, var, orgCls, dx, fx, nAddedCls, nAddedLits)) {
@@ -1749,10 +1751,10 @@ SG_HDN inline void sg_ve_count_item(const SgView &v, uint32_t eidx)
     } else {
         nAddedCls = 0, nAddedLits = 0;
         const int orgCls = pOrgs + nOrgs;
-        uint32_t *out_c = v.scratch + v.scr_off[eidx];
+        uint32_t *gate_in = v.scratch + v.scr_off[eidx];
         if (orgCls > 2) {
-            if (sg_find_ao_gate(v, L, n, p, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
-            else if (!nAddedCls && sg_find_ao_gate(v, L, p, n, out_c, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            if (sg_find_ao_gate(v, L, n, p, gate_in, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            else if (!nAddedCls && sg_find_ao_gate(v, L, p, n, gate_in, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
             if (type) stat = &v.sc->andors;
         }
         if (!type && orgCls > 3) {
