@@ -216,6 +216,45 @@ def gate_circuit(nvars, seed=11, window=2000, n_inputs=None, frac=(0.40, 0.25, 0
     return nvars, new_off, lits_in[idx]
 
 
+def unit_storm(nseeds=100_000, depth=8, seed=5, noise=2.0, planted=True):
+    """Unit-heavy instance for prop() (propelim.cpp:46-81).  Units that are in the file are propagated by the solver before
+    the simplifier starts (rootify(), simplify.cpp:160), so the units here are hidden: every seed literal a comes as
+    (a b)(a -b), which self-subsumption strengthens to the unit clause a during SUB.  The next prop() then starts with
+    about `nseeds` units on the trail and runs down `depth` layers of implications u & w -> y between consecutive
+    layers.  All literals follow a hidden assignment, so the instance is satisfiable; random ternary clauses over the
+    layer variables (`noise` per variable, at least one literal true under the hidden assignment) give the visits
+    clauses to shrink and clauses to delete, and keep most layer variables out of the first election."""
+    rng = np.random.default_rng(seed)
+    n = int(nseeds)
+    nl = n * depth
+    nv = 2 * n + nl
+    hidden = rng.integers(0, 2, size=nv + 1, dtype=np.int64) * 2 - 1              # +1 / -1 per variable
+    a = np.arange(1, n + 1, dtype=np.int64) * hidden[1:n + 1]                        # literals true under `hidden`
+    b = np.arange(n + 1, 2 * n + 1, dtype=np.int64)
+    rows2 = np.concatenate([np.stack([a, b], 1), np.stack([a, -b], 1)])
+    prev = a
+    horn = []
+    for k in range(depth):
+        yv = 2 * n + k * n + np.arange(1, n + 1, dtype=np.int64)
+        y = yv * hidden[yv]
+        u = prev[rng.integers(0, n, size=n)]
+        w = prev[rng.integers(0, n, size=n)]
+        keep = u != w
+        horn.append(np.stack([-u[keep], -w[keep], y[keep]], 1))
+        prev = y
+    nn = int(noise * nl)
+    rows = _signed(rng, 2 * n + _distinct_rows(rng, nn, 3, nl)).astype(np.int64)
+    while planted:
+        bad = np.nonzero(~(np.sign(rows) == hidden[np.abs(rows)]).any(axis=1))[0]
+        if bad.size == 0:
+            break
+        rows[bad] = _signed(rng, 2 * n + _distinct_rows(rng, bad.size, 3, nl))
+    rows3 = np.concatenate(horn + [rows])
+    o, l = _ragged([rows2.astype(np.int32), rows3.astype(np.int32)])
+    o, l = _shuffle_clauses(rng, o, l)
+    return nv, o, l
+
+
 def _xor_clauses(vars_, rhs):
     """CNF expansion of XOR(vars_) = rhs: all sign patterns with the wrong parity are forbidden."""
     k = len(vars_)

@@ -167,6 +167,19 @@ void be_acting_scatter(void *s, const SgView &v, const uint32_t *fa, const uint3
 void be_items(void *s, int kind, const SgView &v, uint32_t n);
 void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2 = 0);
 void be_sort_units(void *s, const SgView &v, uint32_t n);
+/* prop by frontiers (propelim.cpp:46-81; method in sigma_items.cuh).  be_has_prop_frontier() == 0: only be_serial(SGS_PROP).
+ * mark: fpos[] of the frontier's falsified literals, counters cleared.  round: every visit with the guess pp.disc, reports into
+ * pp.disc_new; diff != 0: ctl[2] = the report differs from the guess.  next: the report becomes the guess (the caller swaps the two
+ * pointer pairs afterwards).  count: cnt[] per position, ctl[3] = a visit ends in a conflict, base[] = prefix sum, ctl[4] =
+ * new units.  commit: units on the trail in visit order, clauses rewritten (claim[] zeroed by the caller), lists of the
+ * frontier emptied, values / states / scalars set, all side tables back to their idle state.  conflict: idle state + unsat. */
+int  be_has_prop_frontier(void);
+void be_pp_mark(void *s, const SgView &v, const SgProp &pp);
+void be_pp_round(void *s, const SgView &v, const SgProp &pp, int diff);
+void be_pp_next(void *s, const SgProp &pp);
+void be_pp_count(void *s, const SgView &v, const SgProp &pp, uint32_t *scan_tmp);
+void be_pp_commit(void *s, const SgView &v, const SgProp &pp, uint32_t n_new);
+void be_pp_conflict(void *s, const SgView &v, const SgProp &pp);
 /* sortOT of the lists with 25 .. SG_SOT_WIDE_MAX entries by one warp each (work list left by SGK_SORTOT_LONG when v.sot_wl is set) */
 int be_has_sortot_wide(void);
 int be_sortot_wide(void *s, const SgView &v);

@@ -433,10 +433,12 @@ SG_HD void sg_toblivion_list(const SgView &v, uint32_t lit)
     v.ot_len[lit] = 0;
 }
 
-SG_HDN inline void sg_prop_serial(const SgView &v)
+/* `wide` != 0: return as soon as that many units wait on the trail (the frontier kernels below take over) */
+SG_HDN inline void sg_prop_serial(const SgView &v, uint32_t wide)
 {
     SgScalars *sc = v.sc;
     while (sc->propagated < sc->n_trail) {
+        if (wide && sc->n_trail - sc->propagated >= wide) return;
         const uint32_t assign = v.trail[sc->propagated++], flipped = SG_FLIP(assign);
         const int n = (int)v.ot_len[flipped];
         const uint32_t *d = sg_list(v, flipped);
@@ -471,6 +473,116 @@ SG_HDN inline void sg_prop_serial(const SgView &v)
         v.ot_len[flipped] = 0;
         sg_toblivion_list(v, assign);
     }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* prop by frontiers.                                                                           */
+/*                                                                                              */
+/* The frontier is trail[p0, p1): every unit that is assigned and not yet propagated.  The      */
+/* reference takes them in trail order and walks the list of the falsified literal in list      */
+/* order, so every clause visit has a time t = (trail position p, list index i).  What a visit  */
+/* does depends on the past only through (a) how many literals of the clause earlier visits     */
+/* removed and (b) which of its other literals are true at t.  Literals assigned before the     */
+/* frontier started are true or false for every visit; the only moving part is the set of units */
+/* the frontier itself discovers, each true from the time of the visit that found it.  With     */
+/* disc[lit] = that time, a visit is a pure function of the clause, fpos[] (literal -> trail    */
+/* position that removes it) and the entries of disc[] that are EARLIER than t.  So the whole   */
+/* frontier is evaluated at once with a guess of disc[] (initially: nothing discovered), the    */
+/* discoveries it reports (earliest visit per literal) become the next guess, and the guess     */
+/* that reproduces itself is the sequential result: by induction over t, after k rounds all     */
+/* entries earlier than the k-th discovery are final.  Two rounds when the discovered units do  */
+/* not meet each other's clauses inside the frontier, which is the common case.                 */
+/* New units go on the trail in order of t: per frontier position a count, a prefix sum, and    */
+/* the list order inside the position.                                                          */
+/* ------------------------------------------------------------------------------------------ */
+#define SG_PP_NONE 0xFFFFFFFFu
+#define SG_PP_NEVER 0xFFFFFFFFFFFFFFFFull
+enum { SG_PP_SKIP = 0, SG_PP_SAT = 1, SG_PP_SHRINK = 2, SG_PP_UNIT = 3, SG_PP_CONFLICT = 4 };
+
+SG_HD uint32_t sg_pp_index(const SgView &v, uint32_t lit, uint32_t c)
+{
+    const uint32_t n = v.ot_len[lit];
+    const uint32_t *d = sg_list(v, lit);
+    for (uint32_t i = 0; i < n; ++i) if (d[i] == c) return i;
+    return SG_PP_NONE;
+}
+
+/* the visit (p, i) of clause c, reached through `flipped` */
+SG_HDN inline int sg_pp_visit(const SgView &v, const SgProp &pp, uint32_t p, uint32_t i, uint32_t flipped, uint32_t c, uint32_t *unit)
+{
+    const sg_u4 h = v.hdr[c];
+    if (h.z & SG_DELETED) return SG_PP_SKIP;
+    const uint32_t *l = v.lits + h.x;
+    unsigned long long m = SG_PP_NEVER;            /* first time one of the other literals turns true */
+    uint32_t earlier = 0, last_p = 0, last_lit = 0, left = 0, left_lit = 0;
+    for (uint32_t k = 0; k < h.y; ++k) {
+        const uint32_t other = l[k];
+        if (other == flipped) continue;
+        const int8_t val = v.value[other];
+        if (val > 0) return SG_PP_SKIP;            /* true since before the frontier: the clause goes with that literal's list */
+        const uint32_t fp = pp.fpos[other];
+        if (fp != SG_PP_NONE && fp < p) {          /* an earlier visit of this clause */
+            if (!earlier || fp > last_p) { last_p = fp; last_lit = other; }
+            earlier++;
+            continue;
+        }
+        left++; left_lit = other;
+        if (val & (int8_t)-2) { const unsigned long long d = pp.disc[other]; if (d < m) m = d; }
+    }
+    const unsigned long long t = ((unsigned long long)p << 32) | i;
+    if (earlier && m != SG_PP_NEVER) {
+        /* an earlier visit that came after m found the clause satisfied; the latest one decides */
+        const uint32_t mp = (uint32_t)(m >> 32);
+        bool gone = last_p > mp;
+        if (!gone && last_p == mp) gone = sg_pp_index(v, last_lit, c) > (uint32_t)m;
+        if (gone) return SG_PP_SKIP;
+    }
+    if (m < t) return SG_PP_SAT;
+    if (!left) return SG_PP_CONFLICT;
+    if (left == 1) {
+        if (!(v.value[left_lit] & (int8_t)-2)) return SG_PP_CONFLICT;       /* false: assigned, not propagated yet */
+        if (pp.disc[SG_FLIP(left_lit)] < t) return SG_PP_CONFLICT;
+        *unit = left_lit;
+        return SG_PP_UNIT;
+    }
+    return SG_PP_SHRINK;
+}
+
+/* the clause after the frontier (disc[] final): every visit before the first true literal removed its literal, a visit after
+ * it deleted the clause.  Run once per clause. */
+SG_HDN inline void sg_pp_rewrite(const SgView &v, const SgProp &pp, uint32_t c)
+{
+    const sg_u4 h = v.hdr[c];
+    if (h.z & SG_DELETED) return;
+    uint32_t *l = v.lits + h.x;
+    unsigned long long m = SG_PP_NEVER;
+    uint32_t visits = 0, last_p = 0, last_lit = 0;
+    for (uint32_t k = 0; k < h.y; ++k) {
+        const uint32_t other = l[k];
+        const int8_t val = v.value[other];
+        if (val > 0) return;                       /* deleted with the list of that literal */
+        const uint32_t fp = pp.fpos[other];
+        if (fp != SG_PP_NONE) {
+            if (!visits || fp > last_p) { last_p = fp; last_lit = other; }
+            visits++;
+        } else if (val & (int8_t)-2) { const unsigned long long d = pp.disc[other]; if (d < m) m = d; }
+    }
+    if (!visits) return;
+    if (m != SG_PP_NEVER) {
+        const uint32_t mp = (uint32_t)(m >> 32);
+        bool gone = last_p > mp;
+        if (!gone && last_p == mp) gone = sg_pp_index(v, last_lit, c) > (uint32_t)m;
+        if (gone) { v.hdr[c].z = (h.z & ~SG_ST_MASK) | SG_DELETED; return; }
+    }
+    uint32_t j = 0, sig = 0;
+    for (uint32_t k = 0; k < h.y; ++k) {
+        const uint32_t other = l[k];
+        if (pp.fpos[other] != SG_PP_NONE) continue;
+        l[j++] = other;
+        sig |= SG_HASH(other);
+    }
+    v.hdr[c].y = j;
+    v.hdr[c].w = sig;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -1322,6 +1322,106 @@ __global__ void __launch_bounds__(128) k_sortot_wide(SgView v)
     }
 }
 
+/* ---- prop by frontiers (method in sigma_items.cuh) ---------------------------------------------------------------------- */
+__global__ void k_pp_mark(SgView v, SgProp pp)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, n = pp.p1 - pp.p0;
+    if (k < n) { pp.fpos[SG_FLIP(v.trail[pp.p0 + k])] = pp.p0 + k; pp.cnt[k] = 0; }
+    if (k == 0) { pp.ctl[0] = pp.ctl[1] = pp.ctl[2] = pp.ctl[3] = pp.ctl[4] = 0; }
+}
+/* one warp per frontier position, lanes over the list of the falsified literal in list order.
+ * MODE 0: a round - discoveries into disc_new (earliest visit per literal).  MODE 1: units per position, conflicts.
+ * MODE 2: units onto the trail: position base + rank inside the list. */
+template <int MODE>
+__global__ void k_pp_visits(SgView v, SgProp pp)
+{
+    const uint32_t lane = threadIdx.x & 31u, nw = (gridDim.x * blockDim.x) >> 5, n = pp.p1 - pp.p0;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nw) {
+        const uint32_t p = pp.p0 + k, flipped = SG_FLIP(v.trail[p]);
+        const uint32_t len = v.ot_len[flipped];
+        const uint32_t *d = sg_list(v, flipped);
+        uint32_t run = 0;
+        for (uint32_t b = 0; b < len; b += 32) {
+            const uint32_t i = b + lane;
+            int out = SG_PP_SKIP;
+            uint32_t unit = 0;
+            if (i < len) out = sg_pp_visit(v, pp, p, i, flipped, d[i], &unit);
+            if (MODE == 0) {
+                if (out == SG_PP_UNIT) {
+                    const unsigned long long t = ((unsigned long long)p << 32) | i;
+                    if (atomicMin(&pp.disc_new[unit], t) == SG_PP_NEVER) pp.touched_new[atomicAdd(&pp.ctl[1], 1u)] = unit;
+                }
+            } else {
+                if (MODE == 1 && out == SG_PP_CONFLICT) pp.ctl[3] = 1;
+                const uint32_t mk = __ballot_sync(0xffffffffu, out == SG_PP_UNIT);
+                if (MODE == 2 && out == SG_PP_UNIT) v.trail[pp.p1 + pp.base[k] + run + __popc(mk & ((1u << lane) - 1u))] = unit;
+                run += __popc(mk);
+            }
+        }
+        if (MODE == 1 && lane == 0) pp.cnt[k] = run;
+    }
+}
+__global__ void k_pp_diff(SgProp pp)
+{
+    const uint32_t n0 = pp.ctl[0], n1 = pp.ctl[1];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n0 + n1; k += gridDim.x * blockDim.x) {
+        const uint32_t lit = k < n0 ? pp.touched[k] : pp.touched_new[k - n0];
+        if (pp.disc[lit] != pp.disc_new[lit]) pp.ctl[2] = 1;
+    }
+}
+/* forget the entries of `arr` named by list[0, *n) */
+__global__ void k_pp_forget(unsigned long long *arr, const uint32_t *list, const uint32_t *n)
+{
+    const uint32_t cnt = *n;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) arr[list[k]] = SG_PP_NEVER;
+}
+__global__ void k_pp_shift(SgProp pp) { pp.ctl[0] = pp.ctl[1]; pp.ctl[1] = 0; pp.ctl[2] = 0; }
+/* every clause of the frontier's lists once: the first visitor to set its bit rewrites it */
+__global__ void k_pp_rewrite(SgView v, SgProp pp)
+{
+    const uint32_t lane = threadIdx.x & 31u, nw = (gridDim.x * blockDim.x) >> 5, n = pp.p1 - pp.p0;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nw) {
+        const uint32_t flipped = SG_FLIP(v.trail[pp.p0 + k]);
+        const uint32_t len = v.ot_len[flipped];
+        const uint32_t *d = sg_list(v, flipped);
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t c = d[i], bit = 1u << (c & 31u);
+            if (atomicOr(&pp.claim[c >> 5], bit) & bit) continue;
+            sg_pp_rewrite(v, pp, c);
+        }
+    }
+}
+/* fot.clear, toblivion(ot[assign]) for the frontier; enqueueUnit for the new units; scalars */
+__global__ void k_pp_finish(SgView v, SgProp pp, uint32_t n_new, int conflict)
+{
+    const uint32_t lane = threadIdx.x & 31u, nw = (gridDim.x * blockDim.x) >> 5, n = pp.p1 - pp.p0;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nw) {
+        const uint32_t assign = v.trail[pp.p0 + k], flipped = SG_FLIP(assign);
+        if (!conflict) {
+            const uint32_t len = v.ot_len[assign];
+            const uint32_t *d = sg_list(v, assign);
+            for (uint32_t i = lane; i < len; i += 32) sg_mark_deleted(v, d[i]);
+            __syncwarp();
+            if (lane == 0) { v.ot_len[assign] = 0; v.ot_len[flipped] = 0; }
+        }
+        if (lane == 0) pp.fpos[flipped] = SG_PP_NONE;
+    }
+    if (conflict) { if (blockIdx.x == 0 && threadIdx.x == 0) v.sc->unsat = 1; return; }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
+        const uint32_t u = v.trail[pp.p1 + j];
+        v.state[SG_ABS(u)] = (uint8_t)SG_FROZEN_M;
+        v.value[u] = 1;
+        v.value[SG_FLIP(u)] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        SgScalars *sc = v.sc;
+        sc->propagated = pp.p1;
+        sc->n_trail = pp.p1 + n_new;
+        sc->max_frozen += n_new;
+        sc->unassigned -= n_new;
+    }
+}
+
 __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
 {   /* launched with one warp (only the ERE replay uses more than lane 0); the replay gets helper warps that prefetch */
     if (kind == SGS_ERE_REPLAY) {
@@ -1331,7 +1431,7 @@ __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
         return;
     }
     if (threadIdx.x) return;
-    if (kind == SGS_PROP) sg_prop_serial(v);
+    if (kind == SGS_PROP) sg_prop_serial(v, arg);
     else if (kind == SGS_MARKS) sg_marks_serial(v, arg);
     else if (kind == SGS_APPLY_UNITS) sg_apply_units_serial(v, arg);
     else if (kind == SGS_ERE_SPLIT) sg_ere_split_serial(v, arg, arg2);
@@ -2603,6 +2703,40 @@ void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
         threads = 32u * (1u + (unsigned)helpers);
     }
     LAUNCH(k_serial, 1, threads, s, v, kind, arg, arg2);
+}
+
+int be_has_prop_frontier(void) { return 1; }
+static unsigned pp_grid(uint32_t n_warps) { unsigned g = blocks_for((uint64_t)n_warps * 32u); return g > 148u * 8u ? 148u * 8u : (g ? g : 1u); }
+void be_pp_mark(void *s, const SgView &v, const SgProp &pp) { LAUNCH(k_pp_mark, blocks_for(pp.p1 - pp.p0), TPB, s, v, pp); }
+void be_pp_round(void *s, const SgView &v, const SgProp &pp, int diff)
+{
+    LAUNCH(k_pp_visits<0>, pp_grid(pp.p1 - pp.p0), TPB, s, v, pp);
+    if (diff) LAUNCH(k_pp_diff, 148, TPB, s, pp);
+}
+void be_pp_next(void *s, const SgProp &pp)
+{
+    LAUNCH(k_pp_forget, 148, TPB, s, pp.disc, pp.touched, pp.ctl);
+    LAUNCH(k_pp_shift, 1, 1, s, pp);
+}
+void be_pp_count(void *s, const SgView &v, const SgProp &pp, uint32_t *scan_tmp)
+{
+    LAUNCH(k_pp_visits<1>, pp_grid(pp.p1 - pp.p0), TPB, s, v, pp);
+    be_scan_u32(s, pp.cnt, pp.base, pp.p1 - pp.p0, pp.ctl + 4, scan_tmp);
+}
+void be_pp_commit(void *s, const SgView &v, const SgProp &pp, uint32_t n_new)
+{
+    if (n_new) LAUNCH(k_pp_visits<2>, pp_grid(pp.p1 - pp.p0), TPB, s, v, pp);
+    LAUNCH(k_pp_rewrite, pp_grid(pp.p1 - pp.p0), TPB, s, v, pp);
+    LAUNCH(k_pp_finish, pp_grid(pp.p1 - pp.p0), TPB, s, v, pp, n_new, 0);
+    /* guess and report are equal here: both go back to "nothing discovered" */
+    LAUNCH(k_pp_forget, 148, TPB, s, pp.disc, pp.touched, pp.ctl);
+    LAUNCH(k_pp_forget, 148, TPB, s, pp.disc_new, pp.touched_new, pp.ctl + 1);
+}
+void be_pp_conflict(void *s, const SgView &v, const SgProp &pp)
+{
+    LAUNCH(k_pp_finish, pp_grid(pp.p1 - pp.p0), TPB, s, v, pp, 0u, 1);
+    LAUNCH(k_pp_forget, 148, TPB, s, pp.disc, pp.touched, pp.ctl);
+    LAUNCH(k_pp_forget, 148, TPB, s, pp.disc_new, pp.touched_new, pp.ctl + 1);
 }
 
 void be_sort_units(void *s, const SgView &v, uint32_t n)

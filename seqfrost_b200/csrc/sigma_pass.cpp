@@ -79,6 +79,10 @@ struct sigma_ctx {
     int nbh_fused = 0;               /* 0: separate sortOT / SUB / BVE kernels; 1: fused per variable; 2: fused SUB + BVE only */
     uint32_t ot_first_new = 0;
     DBuf<uint32_t> totals;          /* device slots for scan totals */
+    /* prop by frontiers */
+    DBuf<uint32_t> pp_fpos, pp_lists, pp_cnt, pp_claim, pp_ctl, pp_tmp; DBuf<unsigned long long> pp_disc;
+    size_t pp_nlit = 0;
+    uint64_t pp_frontiers = 0, pp_rounds = 0, pp_units = 0;
     DBuf<SgScalars> sc;
     DBuf<uint32_t> c_flags, c_sizes, c_newid, c_newoff;
     DBuf<uint32_t> arena_out; DBuf<uint64_t> refs_out;
@@ -418,14 +422,88 @@ int stage_update_ot(sigma_ctx *c, uint64_t live_lits)
 }
 
 /* ---- prop (propelim.cpp:46-81) ---------------------------------------------------------------- */
+/* side tables of the frontier kernels: allocated on first use, idle state = "no literal marked, nothing discovered" */
+static int prop_tables(sigma_ctx *c)
+{
+    const size_t nlit = c->nlit;
+    if (c->pp_nlit < nlit) {
+        NOMEM(c->pp_fpos.ensure(nlit, c->stream) && c->pp_disc.ensure(2 * nlit, c->stream) && c->pp_lists.ensure(2 * nlit, c->stream) &&
+              c->pp_cnt.ensure(2 * ((size_t)c->nvars + 4), c->stream) && c->pp_ctl.ensure(16, c->stream) &&
+              c->pp_tmp.ensure(be_scan_tmp_words(c->nvars + 4), c->stream));
+        be_memset(c->stream, c->pp_fpos.p, 0xFF, 4 * nlit);
+        be_memset(c->stream, c->pp_disc.p, 0xFF, 16 * nlit);
+        c->pp_nlit = nlit;
+    }
+    NOMEM(c->pp_claim.ensure((size_t)c->n_cls / 32 + 2, c->stream));
+    return SIGMA_OK;
+}
+
+/* one frontier: trail[propagated, n_trail) all at once */
+static int prop_frontier(sigma_ctx *c)
+{
+    CK(prop_tables(c));
+    const size_t nlit = c->nlit;
+    const uint32_t n = c->hsc.n_trail - c->hsc.propagated;
+    SgView v = make_view(c);
+    SgProp pp;
+    pp.p0 = c->hsc.propagated; pp.p1 = c->hsc.n_trail;
+    pp.fpos = c->pp_fpos.p;
+    pp.disc = c->pp_disc.p; pp.disc_new = c->pp_disc.p + nlit;
+    pp.touched = c->pp_lists.p; pp.touched_new = c->pp_lists.p + nlit;
+    pp.cnt = c->pp_cnt.p; pp.base = c->pp_cnt.p + c->nvars + 4;
+    pp.claim = c->pp_claim.p; pp.ctl = c->pp_ctl.p;
+    uint32_t *h = c->h_totals + 32;
+    /* One evaluation with the empty guess is enough.  A visit ends as UNIT(u) only when u is the one literal left, so the only
+     * discovery that can change its outcome is an earlier one of u itself (the minimum already in the report) or of -u, which
+     * is a conflict; hence the first report is the fixpoint unless some visit conflicts under it, and the earliest such visit
+     * has the sequential past, so the reference conflicts as well.  SIGMA_PROP_CONFIRM=1 (tests) iterates to the fixpoint
+     * anyway and checks that claim. */
+    static const bool confirm = getenv("SIGMA_PROP_CONFIRM") && getenv("SIGMA_PROP_CONFIRM")[0] == '1';
+    uint32_t rounds = 0;
+    be_pp_mark(c->stream, v, pp);
+    for (;;) {
+        be_pp_round(c->stream, v, pp, confirm ? 1 : 0);
+        c->pp_rounds++; rounds++;
+        if (confirm) {
+            be_copy_words(c->stream, h, pp.ctl, 8 * sizeof(uint32_t));
+            if (ctx_sync(c)) return SIGMA_E_CUDA;
+            if (!h[2]) break;
+        }
+        be_pp_next(c->stream, pp);
+        std::swap(pp.disc, pp.disc_new);
+        std::swap(pp.touched, pp.touched_new);
+        if (!confirm) break;
+    }
+    be_pp_count(c->stream, v, pp, c->pp_tmp.p);
+    be_copy_words(c->stream, h, pp.ctl, 8 * sizeof(uint32_t));
+    if (ctx_sync(c)) return SIGMA_E_CUDA;
+    c->pp_frontiers++; c->pp_units += n;
+    if (getenv("SIGMA_PROP_TRACE")) fprintf(stderr, "prop frontier %u units at %u: %u new, conflict %u, rounds so far %llu\n", n, pp.p0, h[4], h[3], (unsigned long long)c->pp_rounds);
+    if (confirm && rounds > 2 && !h[3]) return fail(c, SIGMA_E_CUDA, "prop: the first report was not the fixpoint of a conflict-free frontier");
+    if (h[3]) { be_pp_conflict(c->stream, v, pp); return SIGMA_OK; }        /* learnEmpty (propelim.cpp:62,67): unsat comes back with the scalars */
+    be_memset(c->stream, pp.claim, 0, 4 * ((size_t)c->n_cls / 32 + 1));
+    be_pp_commit(c->stream, v, pp, h[4]);
+    return SIGMA_OK;
+}
+
 int stage_prop(sigma_ctx *c)
 {
     if (c->hsc.propagated >= c->hsc.n_trail) return SIGMA_OK;
+    /* frontiers of at least `wide` units go to the frontier kernels, shorter ones to the one-thread walk, which hands back as
+     * soon as that many units wait (SIGMA_PROP_WIDE: 0 = one thread only, 1 = frontiers only) */
+    uint32_t wide = 64;
+    { const char *e = getenv("SIGMA_PROP_WIDE"); if (e) wide = (uint32_t)strtoul(e, nullptr, 10); }
+    if (!be_has_prop_frontier()) wide = 0;
     {
         Stage st(c, SIGMA_T_PROP);
-        SgView v = make_view(c);
-        be_serial(c->stream, SGS_PROP, v, 0);
-        if (!c->opts.sub_en) be_items(c->stream, SGK_REDUCE, v, c->nlit);   /* propelim.cpp:79 */
+        for (;;) {
+            if (wide && c->hsc.n_trail - c->hsc.propagated >= wide) CK(prop_frontier(c));
+            else be_serial(c->stream, SGS_PROP, make_view(c), wide);
+            if (!wide) break;
+            CK(pull_scalars(c));
+            if (c->hsc.unsat || c->hsc.propagated >= c->hsc.n_trail) break;
+        }
+        if (!c->opts.sub_en) be_items(c->stream, SGK_REDUCE, make_view(c), c->nlit);   /* propelim.cpp:79 */
     }
     CK(pull_scalars(c));
     if (c->hsc.unsat) return SIGMA_UNSAT;
@@ -1000,6 +1078,7 @@ void sigma_destroy(sigma_ctx *c)
         c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
         c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release(); c->ere_filt.release(); c->ere_size8.release();
         c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->otbits.release(); c->otb_tmp.release(); c->totals.release(); c->sc.release();
+        c->pp_fpos.release(); c->pp_lists.release(); c->pp_cnt.release(); c->pp_claim.release(); c->pp_ctl.release(); c->pp_tmp.release(); c->pp_disc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();
         c->arena_out.release(); c->refs_out.release(); c->cm_out.release(); c->orgs_out.release(); c->learnts_out.release(); c->subsume_out.release();
         for (void *e2 : c->evpool) be_event_destroy(e2);

@@ -145,4 +145,17 @@ typedef struct SgView {
     SgOpts   o;
 } SgView;
 
+/* one frontier of prop (sigma_items.cuh, "prop by frontiers") */
+typedef struct SgProp {
+    uint32_t p0, p1;                      /* frontier */
+    uint32_t *fpos;                       /* per literal: frontier position whose unit falsifies it, else SG_PP_NONE */
+    unsigned long long *disc;             /* per literal: visit that makes it true in this frontier (the current guess) */
+    unsigned long long *disc_new;         /* what this round reports */
+    uint32_t *touched, *touched_new;      /* literals with an entry in disc / disc_new; counts in ctl[0], ctl[1] */
+    uint32_t *cnt;                        /* per frontier position: units discovered by its visits */
+    uint32_t *base;                       /* exclusive prefix sum of cnt; base[p1 - p0] = total */
+    uint32_t *claim;                      /* one bit per clause id: rewritten in this frontier */
+    uint32_t *ctl;                        /* 0,1: list counts; 2: guess changed; 3: conflict seen */
+} SgProp;
+
 #endif

@@ -348,7 +348,7 @@ void be_serial(void *, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
 {
     g_launches++;
     switch (kind) {
-    case SGS_PROP: sg_prop_serial(v); break;
+    case SGS_PROP: sg_prop_serial(v, arg); break;
     case SGS_MARKS: sg_marks_serial(v, arg); break;
     case SGS_APPLY_UNITS: sg_apply_units_serial(v, arg); break;
     case SGS_ERE_REPLAY: sg_ere_replay_serial(v, arg, arg2); break;
@@ -623,3 +623,89 @@ void be_wt_records(void *, uint32_t nlit, const uint32_t *ot_off, const uint32_t
             o.x = w.x; o.y = w.y; o.z = w.w ^ SG_FLIP(lit); o.w = w.z;
         }
 }
+
+/* prop by frontiers: the kernels' loops, one visit at a time (same per-visit functions) */
+int  be_has_prop_frontier(void) { return 1; }
+void be_pp_mark(void *, const SgView &v, const SgProp &pp)
+{
+    g_launches++;
+    for (uint32_t k = 0; k < pp.p1 - pp.p0; ++k) { pp.fpos[SG_FLIP(v.trail[pp.p0 + k])] = pp.p0 + k; pp.cnt[k] = 0; }
+    for (int q = 0; q < 5; ++q) pp.ctl[q] = 0;
+}
+template <class F> static void pp_for_visits(const SgView &v, const SgProp &pp, F f)
+{
+    for (uint32_t k = 0; k < pp.p1 - pp.p0; ++k) {
+        const uint32_t p = pp.p0 + k, flipped = SG_FLIP(v.trail[p]);
+        const uint32_t len = v.ot_len[flipped];
+        const uint32_t *d = sg_list(v, flipped);
+        for (uint32_t i = 0; i < len; ++i) f(k, p, i, flipped, d[i]);
+    }
+}
+void be_pp_round(void *, const SgView &v, const SgProp &pp, int diff)
+{
+    g_launches += 2;
+    pp_for_visits(v, pp, [&](uint32_t, uint32_t p, uint32_t i, uint32_t flipped, uint32_t c) {
+        uint32_t unit = 0;
+        if (sg_pp_visit(v, pp, p, i, flipped, c, &unit) != SG_PP_UNIT) return;
+        const unsigned long long t = ((unsigned long long)p << 32) | i;
+        if (pp.disc_new[unit] == SG_PP_NEVER) pp.touched_new[pp.ctl[1]++] = unit;
+        if (t < pp.disc_new[unit]) pp.disc_new[unit] = t;
+    });
+    if (!diff) return;
+    for (uint32_t k = 0; k < pp.ctl[0]; ++k) if (pp.disc[pp.touched[k]] != pp.disc_new[pp.touched[k]]) pp.ctl[2] = 1;
+    for (uint32_t k = 0; k < pp.ctl[1]; ++k) if (pp.disc[pp.touched_new[k]] != pp.disc_new[pp.touched_new[k]]) pp.ctl[2] = 1;
+}
+void be_pp_next(void *, const SgProp &pp)
+{
+    g_launches += 2;
+    for (uint32_t k = 0; k < pp.ctl[0]; ++k) pp.disc[pp.touched[k]] = SG_PP_NEVER;
+    pp.ctl[0] = pp.ctl[1]; pp.ctl[1] = 0; pp.ctl[2] = 0;
+}
+void be_pp_count(void *, const SgView &v, const SgProp &pp, uint32_t *)
+{
+    g_launches += 4;
+    pp_for_visits(v, pp, [&](uint32_t k, uint32_t p, uint32_t i, uint32_t flipped, uint32_t c) {
+        uint32_t unit = 0;
+        const int out = sg_pp_visit(v, pp, p, i, flipped, c, &unit);
+        if (out == SG_PP_CONFLICT) pp.ctl[3] = 1;
+        if (out == SG_PP_UNIT) pp.cnt[k]++;
+    });
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < pp.p1 - pp.p0; ++k) { pp.base[k] = run; run += pp.cnt[k]; }
+    pp.ctl[4] = run;
+}
+static void pp_idle(const SgView &v, const SgProp &pp)
+{
+    for (uint32_t k = 0; k < pp.p1 - pp.p0; ++k) pp.fpos[SG_FLIP(v.trail[pp.p0 + k])] = SG_PP_NONE;
+    for (uint32_t k = 0; k < pp.ctl[0]; ++k) pp.disc[pp.touched[k]] = SG_PP_NEVER;
+    for (uint32_t k = 0; k < pp.ctl[1]; ++k) pp.disc_new[pp.touched_new[k]] = SG_PP_NEVER;
+}
+void be_pp_commit(void *, const SgView &v, const SgProp &pp, uint32_t n_new)
+{
+    g_launches += 5;
+    std::vector<uint32_t> run(pp.p1 - pp.p0, 0);
+    std::vector<uint32_t> units(n_new);
+    pp_for_visits(v, pp, [&](uint32_t k, uint32_t p, uint32_t i, uint32_t flipped, uint32_t c) {
+        uint32_t unit = 0;
+        if (sg_pp_visit(v, pp, p, i, flipped, c, &unit) == SG_PP_UNIT) units[pp.base[k] + run[k]++] = unit;
+    });
+    for (uint32_t j = 0; j < n_new; ++j) v.trail[pp.p1 + j] = units[j];
+    pp_for_visits(v, pp, [&](uint32_t, uint32_t, uint32_t, uint32_t, uint32_t c) {
+        const uint32_t bit = 1u << (c & 31u);
+        if (pp.claim[c >> 5] & bit) return;
+        pp.claim[c >> 5] |= bit;
+        sg_pp_rewrite(v, pp, c);
+    });
+    for (uint32_t k = 0; k < pp.p1 - pp.p0; ++k) {
+        const uint32_t assign = v.trail[pp.p0 + k];
+        sg_toblivion_list(v, assign);
+        v.ot_len[SG_FLIP(assign)] = 0;
+    }
+    pp_idle(v, pp);
+    for (uint32_t j = 0; j < n_new; ++j) {
+        const uint32_t u = v.trail[pp.p1 + j];
+        v.state[SG_ABS(u)] = (uint8_t)SG_FROZEN_M; v.value[u] = 1; v.value[SG_FLIP(u)] = 0;
+    }
+    v.sc->propagated = pp.p1; v.sc->n_trail = pp.p1 + n_new; v.sc->max_frozen += n_new; v.sc->unassigned -= n_new;
+}
+void be_pp_conflict(void *, const SgView &v, const SgProp &pp) { g_launches += 3; pp_idle(v, pp); v.sc->unsat = 1; }

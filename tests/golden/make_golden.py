@@ -61,6 +61,10 @@ CASES = [
     # through ifreeze() and a few assumptions through iassume(): the .in carries the `ifrozen` mask (lcve.cpp:67)
     ("incr_gates", "gate_circuit", dict(nvars=3000, seed=51), ["+ere", "--incr=3:150:6"]),
     ("incr_ksat3", "random_ksat", dict(nvars=2000, nclauses=8000, k=3, seed=9), ["+ere", "--incr=5:80:4"]),
+    # prop() with hundreds of units per frontier (units hidden behind self-subsumption, implication layers below them);
+    # the second one is not planted: prop() ends in a conflict
+    ("unit_storm", "unit_storm", dict(nseeds=400, depth=6, seed=5), ["+ere"]),
+    ("unit_storm_unsat", "unit_storm", dict(nseeds=300, depth=5, seed=9, planted=False), []),
 ]
 
 
