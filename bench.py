@@ -8,6 +8,7 @@ LCVE, sortOT, SUB, VE, ERE, counts, compaction, export) over one synthetic insta
   --config c2 (default)  BASELINE.json configs[1]: random 5-SAT, 2M variables / 10M clauses with planted
                          subsumption work - the configuration the metric is quoted on
   --config c1 | c3 | c4  configs[0], [2], [3] at their stated sizes (same JSON shape; results under profiles/)
+  --config u1            prop() stress case (cnfgen.unit_storm), not a BASELINE config
   --config c5            configs[4]: the batch of 64 mixed instances as a largest-first work queue (seqfrost_b200/batch.py)
 
 At N>1 every rank owns an independent instance of the same shape (different seed): the formula does not
@@ -55,6 +56,9 @@ CONFIGS = {
                name="BMC-style gate circuit (AND/XOR/ITE/equivalence), 5M vars (BASELINE.json configs[2], SURVEY 8d C3)"),
     "c4": dict(gen="xor_php_mix", kw=dict(nclauses=1_000_000, seed=3),
                name="XOR chains + pigeonhole mix, 1M clauses (BASELINE.json configs[3], SURVEY 8d C4)"),
+    # not a BASELINE config: the prop() stress case (propelim.cpp:46-81), 810k units through one prop() call
+    "u1": dict(gen="unit_storm", kw=dict(nseeds=100_000, depth=8, seed=5),
+               name="unit storm: 100k units hidden behind self-subsumption, 8 implication layers, 1M vars / 2.6M clauses"),
 }
 
 

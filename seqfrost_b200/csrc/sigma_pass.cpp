@@ -494,6 +494,7 @@ int stage_prop(sigma_ctx *c)
     uint32_t wide = 64;
     { const char *e = getenv("SIGMA_PROP_WIDE"); if (e) wide = (uint32_t)strtoul(e, nullptr, 10); }
     if (!be_has_prop_frontier()) wide = 0;
+    bool fresh = false;                                    /* the scalars were pulled after the last launch */
     {
         Stage st(c, SIGMA_T_PROP);
         for (;;) {
@@ -501,11 +502,11 @@ int stage_prop(sigma_ctx *c)
             else be_serial(c->stream, SGS_PROP, make_view(c), wide);
             if (!wide) break;
             CK(pull_scalars(c));
-            if (c->hsc.unsat || c->hsc.propagated >= c->hsc.n_trail) break;
+            if (c->hsc.unsat || c->hsc.propagated >= c->hsc.n_trail) { fresh = c->opts.sub_en != 0; break; }
         }
         if (!c->opts.sub_en) be_items(c->stream, SGK_REDUCE, make_view(c), c->nlit);   /* propelim.cpp:79 */
     }
-    CK(pull_scalars(c));
+    if (!fresh) CK(pull_scalars(c));
     if (c->hsc.unsat) return SIGMA_UNSAT;
     return SIGMA_OK;
 }
