@@ -667,6 +667,37 @@ __device__ __forceinline__ void otb_sort_list(uint32_t *d, uint32_t n)
     }
 }
 
+/* ascending order of one list by a whole warp: bitonic network in its "flip / disperse" form, where every compare-exchange
+ * moves the smaller key to the lower index - so the keys a power-of-two length would need beyond n can be imagined as
+ * +infinity and never touched.  n log^2 n / 64 steps per lane whatever the input order: the clauses of one gate sit in
+ * one tile, and the scatter leaves the records of a tile in no particular order, which makes a thread's insertion sort
+ * quadratic on exactly the long lists (XOR gates: 64-96 entries per literal, 70 us per block on the 1M-clause XOR/PHP mix). */
+constexpr uint32_t OTB_WARP_SORT = 32;      /* lists longer than this are sorted by a warp */
+__device__ __forceinline__ void otb_sort_list_warp(uint32_t *d, uint32_t n)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lm = 1;
+    while ((1u << lm) < n) ++lm;
+    const uint32_t half = 1u << (lm - 1);
+    for (uint32_t lk = 1; lk <= lm; ++lk) {
+        const uint32_t k = 1u << lk;
+        for (uint32_t t = lane; t < half; t += 32) {       /* flip: i against its mirror inside the block of k */
+            const uint32_t o = t & ((k >> 1) - 1u), b0 = (t >> (lk - 1)) << lk;
+            const uint32_t i = b0 + o, l = b0 + (k - 1u - o);
+            if (l < n) { const uint32_t a = d[i], b = d[l]; if (a > b) { d[i] = b; d[l] = a; } }
+        }
+        __syncwarp();
+        for (int lj = (int)lk - 2; lj >= 0; --lj) {        /* disperse: i against i + j inside blocks of 2j */
+            const uint32_t j = 1u << lj;
+            for (uint32_t t = lane; t < half; t += 32) {
+                const uint32_t i = ((t >> lj) << (lj + 1)) + (t & (j - 1u)), l = i + j;
+                if (l < n) { const uint32_t a = d[i], b = d[l]; if (a > b) { d[i] = b; d[l] = a; } }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 /* the records of one bucket, 128 consecutive ones per warp and step (the warps walk the bucket side by side, so the
  * records of a list are met nearly in tile order); f(record, tile).  The tile of a record is the run it lies in. */
 template <bool LAST_USE, class F>
@@ -731,18 +762,59 @@ __global__ void __launch_bounds__(OTB_TPB, 1) k_otb_lists(const uint32_t *__rest
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) s_cur[i] = s_loc[i];
     __syncthreads();
-    const bool staged = P <= pcap;
-    const uint32_t shift4 = g0 & 3u;
-    uint32_t *dst = staged ? stage + shift4 : ot_data + g0;
-    /* second read of the bucket's records: L2 hits */
-    if (P) otb_for_records<true>(recs, s_st, s_tile, NR, P, [&](uint32_t r, uint32_t t) { dst[atomicAdd(&s_cur[r & lmask], 1u)] = t * per_tile + (r >> shift); });
-    __syncthreads();
-    if (!staged) __threadfence_block();
-    for (uint32_t i = threadIdx.x; i < W; i += blockDim.x) otb_sort_list(dst + s_loc[i], s_loc[i + 1] - s_loc[i]);
-    if (staged) {
-        stage_fence();
+    /* The bucket's slice of ot_data is assembled in shared memory and leaves with one bulk store.  A bucket that does not fit
+     * (the literals of one bucket can hold far more than the average: XOR gates next to pigeon-hole clauses) is taken as
+     * consecutive ranges of its lists that do fit, each with its own walk over the bucket's records (L2 hits); only a single
+     * list longer than the staging room is placed and sorted in global memory. */
+    __shared__ uint32_t s_hi;
+    uint32_t lo = 0;
+    while (lo < W) {
+        if (threadIdx.x == 0) {
+            uint32_t a = lo + 1, z = W;                    /* largest hi with s_loc[hi] - s_loc[lo] <= pcap, at least lo + 1 */
+            const uint32_t lim = s_loc[lo] + pcap;
+            while (a < z) { const uint32_t mid = (a + z + 1) >> 1; if (s_loc[mid] <= lim) a = mid; else z = mid - 1; }
+            s_hi = a;
+        }
         __syncthreads();
-        if (P) flush_staged(ot_data, (unsigned long long)g0, stage, P);
+        const uint32_t hi = s_hi, base = s_loc[lo], n = s_loc[hi] - base;
+        const bool whole = lo == 0 && hi == W;
+        if (n) {
+            const bool staged = n <= pcap;
+            const uint32_t shift4 = (g0 + base) & 3u;
+            uint32_t *dst = staged ? stage + shift4 - base : ot_data + g0;       /* indexed by the offset inside the bucket */
+            /* second read of the bucket's records: L2 hits */
+            if (whole) otb_for_records<true>(recs, s_st, s_tile, NR, P, [&](uint32_t r, uint32_t t) { dst[atomicAdd(&s_cur[r & lmask], 1u)] = t * per_tile + (r >> shift); });
+            else otb_for_records<false>(recs, s_st, s_tile, NR, P, [&](uint32_t r, uint32_t t) {
+                const uint32_t l = r & lmask;
+                if (l >= lo && l < hi) dst[atomicAdd(&s_cur[l], 1u)] = t * per_tile + (r >> shift);
+            });
+            __syncthreads();
+            if (!staged) __threadfence_block();
+            /* every list in ascending clause id order: short ones one thread each, the others one warp each */
+            bool any_long = false;
+            for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+                const uint32_t len = s_loc[i + 1] - s_loc[i];
+                uint32_t *d = dst + s_loc[i];
+                bool by_warp = false;
+                if (staged && len > OTB_WARP_SORT) {       /* nearly sorted (the usual case: one entry per tile) stays with the thread */
+                    uint32_t inv = 0;
+                    for (uint32_t q = 1; q < len && inv <= 4; ++q) inv += d[q - 1] > d[q];
+                    by_warp = inv > 4;
+                }
+                s_cur[i] = by_warp;                        /* the fill cursors are not needed any more */
+                if (by_warp) any_long = true; else otb_sort_list(d, len);
+            }
+            if (staged && __syncthreads_or(any_long))
+                for (uint32_t i = lo + (threadIdx.x >> 5); i < hi; i += blockDim.x >> 5)
+                    if (s_cur[i]) otb_sort_list_warp(dst + s_loc[i], s_loc[i + 1] - s_loc[i]);
+            if (staged) {
+                stage_fence();
+                __syncthreads();
+                flush_staged(ot_data, (unsigned long long)g0 + base, stage, n);
+            }
+        }
+        __syncthreads();                                   /* the staging room and s_hi are free again */
+        lo = hi;
     }
 }
 
@@ -1239,7 +1311,10 @@ template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i0 = warp_item ? (t >> 5) : t;
     if (i0 >= n) return;
-    const uint32_t i = v.item_base + i0;
+    /* the elected variables come in ascending score order, the heaviest neighbourhoods last: the warp-per-variable kernels
+     * start with those, so that the long items do not end up alone at the tail of the launch (items are independent) */
+    const bool heavy_first = (KIND == SGK_SUB || KIND == SGK_VE_COUNT || KIND == SGK_NBH || KIND == SGK_ERE_PROPOSE) && v.item_rev;
+    const uint32_t i = v.item_base + (heavy_first ? n - 1u - i0 : i0);
     if (KIND == SGK_IDSORT) sg_idsort_item(v, i);
     else if (KIND == SGK_IDSORT_LONG) { if (v.ot_len[i] > 64u) sg_idsort_item(v, i); }
     else if (KIND == SGK_REDUCE) sg_reduce_item(v, i);

@@ -166,6 +166,7 @@ SgView make_view(sigma_ctx *c)
 {
     SgView v;
     memset(&v, 0, sizeof v);
+    { static const int rev = [] { const char *e = getenv("SIGMA_ITEMS_HEAVY_FIRST"); return e ? atoi(e) : 1; }(); v.item_rev = (uint32_t)rev; }
     v.hdr = c->hdr.p; v.lits = c->lits.p;
     v.ot_off = c->ot_off.p; v.ot_len = c->ot_len.p; v.ot_data = c->ot_data.p;
     v.value = c->value.p; v.state = c->state.p; v.marks = c->marks.p;

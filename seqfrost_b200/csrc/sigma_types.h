@@ -140,6 +140,7 @@ typedef struct SgView {
     uint32_t *sot_wl;        /* sortOT: literals whose lists have 25 .. SG_SOT_WIDE_MAX entries, collected by the thread-per-list kernel for the
                                 warp-per-list kernel (count in sc->wl_count[1]); NULL = the thread-per-list kernel sorts them itself */
     uint32_t item_base;      /* be_items processes items [item_base, item_base + n) */
+    uint32_t item_rev;       /* warp-per-variable kernels take their items last to first */
     uint32_t sortot_warp_min; /* sortOT: lists longer than this (and <= 24) are sorted by a warp, the others by one thread */
     uint64_t model_base;     /* model words present before this VE stage */
     SgOpts   o;

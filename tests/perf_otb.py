@@ -3,11 +3,15 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from seqfrost_b200 import boundary as B, cnfgen, sigma
-b = B.from_cnf(*cnfgen.planted_subsumption_ksat(2_000_000, 10_000_000, k=5, seed=7))
+shape = os.environ.get("SHAPE", "c2")
+gen = {"c3": lambda: cnfgen.gate_circuit(int(os.environ.get("VARS", 5_000_000)), seed=11), "c4": lambda: cnfgen.xor_php_mix(1_000_000, seed=3),
+       "c1": lambda: cnfgen.random_ksat(100_000, 426_000, k=3, seed=1),
+       "c2": lambda: cnfgen.planted_subsumption_ksat(2_000_000, 10_000_000, k=5, seed=7)}[shape]
+b = B.from_cnf(*gen())
 b.opts["ere_en"] = 1
 s = sigma.Sigma(0)
 s.upload(b)
-for sh in ("", "10", "11", "12"):
+for sh in os.environ.get("SHIFTS", ",10,11,12").split(","):
     if sh:
         os.environ["SIGMA_OTB_SHIFT"] = sh
     elif "SIGMA_OTB_SHIFT" in os.environ:
