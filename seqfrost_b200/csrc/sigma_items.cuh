@@ -1651,6 +1651,32 @@ SG_HDN inline bool sg_xor_complete(const SgView &v, uint32_t ci, int size)
     return true;
 }
 
+/* the same question answered by the whole warp, lanes over the partners: for wide XORs (2^(arity-1) - 1 partners, each a
+ * search through a list of about 2^(arity-1) clauses) the first clause tried is nearly always the complete one, and testing
+ * 32 clauses at once, one per lane, does 32 times the work the reference does */
+#define SG_XOR_COOP_MIN 6                 /* clause size from which the partners are spread over the lanes */
+SG_HDN inline bool sg_xor_complete_warp(const SgView &v, const SgLane &L, uint32_t ci, int size)
+{
+    uint32_t pattern[24];
+    const uint32_t *base = SG_LITS(v, ci);
+    const uint32_t npat = 1u << (size - 1);
+    for (uint32_t t0 = 1; t0 < npat; t0 += L.width) {
+        const uint32_t t = t0 + L.lane;
+        bool found = true;
+        if (t < npat) {
+            sg_xor_partner(base, size, t, pattern);
+            uint32_t sig;
+            const uint32_t via = sg_arity_best(v, pattern, size, &sig);
+            const int n = (int)v.ot_len[via];
+            const uint32_t *d = sg_list(v, via);
+            found = false;
+            for (int i = 0; i < n && !found; ++i) found = sg_arity_match(v, v.hdr[d[i]], pattern, size, sig);
+        }
+        if (sg_ballot(!found)) return false;
+    }
+    return true;
+}
+
 SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t dx, uint32_t fx, int orgCls, int &nAddedCls,
                                     int &nAddedLits)
 {
@@ -1679,7 +1705,7 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
     for (int base = 0; base < nd; base += (int)L.width) {
         /* the reference tries the clauses of dx in list order and stops at the first complete XOR */
         const int idx = base + (int)L.lane;
-        bool complete = false;
+        bool complete = false, wide_cand = false;
         if (idx < nd) {
             const sg_u4 h = v.hdr[dd[idx]];
             const int size = (int)h.y;
@@ -1699,12 +1725,22 @@ SG_HDN inline bool sg_find_xor_gate(const SgView &v, const SgLane &L, uint32_t d
                     const uint32_t gw = g.w | ((g.w & 0xAAAAAAAAu) >> 1) | ((g.w & 0x55555555u) << 1);
                     if (gw == wide) same++;
                 }
-                if (same >= (1 << (size - 1))) complete = sg_xor_complete(v, dd[idx], size);
+                if (same >= (1 << (size - 1))) {
+                    if (size >= SG_XOR_COOP_MIN) wide_cand = true;
+                    else complete = sg_xor_complete(v, dd[idx], size);
+                }
             }
         }
-        const uint32_t m = sg_ballot(complete);
-        if (!m) continue;
-        const uint32_t ci = dd[base + sg_ffs(m) - 1];
+        /* first complete clause in list order: the narrow ones are answered already, a wide one is tested now, by the warp */
+        const uint32_t mc = sg_ballot(complete);
+        uint32_t m = mc | sg_ballot(wide_cand), ci = 0xFFFFFFFFu;
+        while (m) {
+            const int q = sg_ffs(m) - 1;
+            m &= m - 1u;
+            const uint32_t cq = dd[base + q];
+            if (((mc >> q) & 1u) || sg_xor_complete_warp(v, L, cq, SG_SIZE(v, cq))) { ci = cq; break; }
+        }
+        if (ci == 0xFFFFFFFFu) continue;
         const int size = SG_SIZE(v, ci);
         const uint32_t *first = SG_LITS(v, ci);
         bool all = true;
