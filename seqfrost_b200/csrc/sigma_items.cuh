@@ -1609,12 +1609,10 @@ SG_HD uint32_t sg_arity_best(const SgView &v, const uint32_t *literals, int size
 SG_HD bool sg_arity_match(const SgView &v, const sg_u4 &h, const uint32_t *literals, int size, uint32_t sig)
 {
     if ((h.z & SG_ST_MASK) || (int)h.y != size || h.w != sig) return false;
+    /* a stored clause is in ascending literal order, and so is a partner pattern: negating literals of the (ascending) base
+     * clause changes sign bits only, never the order of the variables - equal sets are equal sequences */
     const uint32_t *l = v.lits + h.x;
-    for (int a = 0; a < size; ++a) {
-        bool found = false;
-        for (int b = 0; b < size; ++b) if (l[a] == literals[b]) { found = true; break; }
-        if (!found) return false;
-    }
+    for (int a = 0; a < size; ++a) if (l[a] != literals[a]) return false;
     return true;
 }
 
