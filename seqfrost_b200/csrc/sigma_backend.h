@@ -174,6 +174,9 @@ void be_sort_units(void *s, const SgView &v, uint32_t n);
  * new units.  commit: units on the trail in visit order, clauses rewritten (claim[] zeroed by the caller), lists of the
  * frontier emptied, values / states / scalars set, all side tables back to their idle state.  conflict: idle state + unsat. */
 int  be_has_prop_frontier(void);
+/* the n units in v.ubuf (sorted) applied at once, same result as be_serial(SGS_APPLY_UNITS): first = one word per literal, all
+ * ones on entry and on return; flags / pos: n words each; total: one word */
+void be_apply_units(void *s, const SgView &v, uint32_t n, uint32_t *first, uint32_t *flags, uint32_t *pos, uint32_t *total, uint32_t *scan_tmp);
 void be_pp_mark(void *s, const SgView &v, const SgProp &pp);
 void be_pp_round(void *s, const SgView &v, const SgProp &pp, int diff);
 void be_pp_next(void *s, const SgProp &pp);

@@ -1497,6 +1497,55 @@ __global__ void k_pp_finish(SgView v, SgProp pp, uint32_t n_new, int conflict)
     }
 }
 
+/* ---- units of one SUB / VE stage, sorted by (elected index, sequence), applied at once ------------------------------------- */
+/* The one-thread walk (sg_apply_units_serial) enqueues a unit when its literal is unassigned, skips it when the literal is
+ * true and stops with the empty clause when it is false.  With first[lit] = the earliest position of lit in the sorted list:
+ * position k enqueues iff lit was unassigned before the stage and first[lit] == k and -lit does not come earlier; a literal
+ * that was false before the stage, or whose negation comes earlier, is the conflict (any conflict ends the pass, whichever
+ * position finds it).  Trail order = list order: a prefix sum over the enqueue flags. */
+__global__ void k_au_first(SgView v, uint32_t n, uint32_t *first)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) atomicMin(&first[v.ubuf[k].lit], k);
+}
+__global__ void k_au_flags(SgView v, uint32_t n, const uint32_t *first, uint32_t *flags)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t lit = v.ubuf[k].lit;
+    const int8_t val = v.value[lit];
+    uint32_t f = 0;
+    if (val & (int8_t)-2) {
+        if (first[lit] == k) { if (first[SG_FLIP(lit)] < k) v.sc->unsat = 1; else f = 1; }
+    } else if (!val) v.sc->unsat = 1;
+    flags[k] = f;
+}
+__global__ void k_au_write(SgView v, uint32_t n, uint32_t *first, const uint32_t *flags, const uint32_t *pos, const uint32_t *total)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    SgScalars *sc = v.sc;
+    const bool unsat = sc->unsat != 0;                     /* written by the launch before this one */
+    if (k < n) {
+        const uint32_t lit = v.ubuf[k].lit;
+        if (flags[k] && !unsat) {
+            v.trail[sc->n_trail + pos[k]] = lit;
+            v.state[SG_ABS(lit)] = (uint8_t)SG_FROZEN_M;
+            v.value[lit] = 1;
+            v.value[SG_FLIP(lit)] = 0;
+        }
+    }
+}
+__global__ void k_au_finish(SgView v, uint32_t n, uint32_t *first, const uint32_t *total)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) first[v.ubuf[k].lit] = 0xFFFFFFFFu;
+    if (k == 0 && !v.sc->unsat) {
+        SgScalars *sc = v.sc;
+        const uint32_t t = *total;
+        sc->n_trail += t; sc->max_frozen += t; sc->unassigned -= t; sc->units_forced += t;
+    }
+}
+
 __global__ void k_serial(SgView v, int kind, uint32_t arg, uint32_t arg2)
 {   /* launched with one warp (only the ERE replay uses more than lane 0); the replay gets helper warps that prefetch */
     if (kind == SGS_ERE_REPLAY) {
@@ -2780,6 +2829,14 @@ void be_serial(void *s, int kind, const SgView &v, uint32_t arg, uint32_t arg2)
     LAUNCH(k_serial, 1, threads, s, v, kind, arg, arg2);
 }
 
+void be_apply_units(void *s, const SgView &v, uint32_t n, uint32_t *first, uint32_t *flags, uint32_t *pos, uint32_t *total, uint32_t *scan_tmp)
+{
+    LAUNCH(k_au_first, blocks_for(n), TPB, s, v, n, first);
+    LAUNCH(k_au_flags, blocks_for(n), TPB, s, v, n, (const uint32_t *)first, flags);
+    be_scan_u32(s, flags, pos, n, total, scan_tmp);
+    LAUNCH(k_au_write, blocks_for(n), TPB, s, v, n, first, (const uint32_t *)flags, (const uint32_t *)pos, (const uint32_t *)total);
+    LAUNCH(k_au_finish, blocks_for(n), TPB, s, v, n, first, (const uint32_t *)total);
+}
 int be_has_prop_frontier(void) { return 1; }
 static unsigned pp_grid(uint32_t n_warps) { unsigned g = blocks_for((uint64_t)n_warps * 32u); return g > 148u * 8u ? 148u * 8u : (g ? g : 1u); }
 void be_pp_mark(void *s, const SgView &v, const SgProp &pp) { LAUNCH(k_pp_mark, blocks_for(pp.p1 - pp.p0), TPB, s, v, pp); }

@@ -644,6 +644,7 @@ again:
     return SIGMA_OK;
 }
 
+static int prop_tables(sigma_ctx *c);
 int apply_units(sigma_ctx *c, SgView &v)
 {
     CK(pull_scalars(c));
@@ -652,7 +653,15 @@ int apply_units(sigma_ctx *c, SgView &v)
     if (!n) return SIGMA_OK;
     if (n > c->ubuf.cap) return fail(c, SIGMA_E_UNSUPPORTED, "unit buffer overflow");
     be_sort_units(c->stream, v, n);
-    be_serial(c->stream, SGS_APPLY_UNITS, v, n);
+    /* many units (hundreds of thousands after a SUB stage on a unit storm: 24 ms for the one-thread walk): all positions at once */
+    uint32_t wide = 256;
+    { const char *e = getenv("SIGMA_UNITS_WIDE"); if (e) wide = (uint32_t)strtoul(e, nullptr, 10); }
+    if (wide && n >= wide && be_has_prop_frontier()) {
+        CK(prop_tables(c));
+        NOMEM(c->pp_cnt.ensure(2 * ((size_t)n + 4), c->stream) && c->pp_tmp.ensure(be_scan_tmp_words(n + 4), c->stream));
+        v = make_view(c);
+        be_apply_units(c->stream, v, n, c->pp_fpos.p, c->pp_cnt.p, c->pp_cnt.p + n + 4, c->pp_ctl.p + 8, c->pp_tmp.p);
+    } else be_serial(c->stream, SGS_APPLY_UNITS, v, n);
     CK(pull_scalars(c));
     c->hsc.n_units = 0;
     CK(push_scalars(c));

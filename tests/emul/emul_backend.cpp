@@ -626,6 +626,29 @@ void be_wt_records(void *, uint32_t nlit, const uint32_t *ot_off, const uint32_t
 
 /* prop by frontiers: the kernels' loops, one visit at a time (same per-visit functions) */
 int  be_has_prop_frontier(void) { return 1; }
+void be_apply_units(void *, const SgView &v, uint32_t n, uint32_t *first, uint32_t *flags, uint32_t *pos, uint32_t *total, uint32_t *)
+{   /* the kernels' steps, one position at a time */
+    g_launches += 7;
+    for (uint32_t k = 0; k < n; ++k) if (k < first[v.ubuf[k].lit]) first[v.ubuf[k].lit] = k;
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t lit = v.ubuf[k].lit;
+        const int8_t val = v.value[lit];
+        uint32_t f = 0;
+        if (val & (int8_t)-2) { if (first[lit] == k) { if (first[SG_FLIP(lit)] < k) v.sc->unsat = 1; else f = 1; } }
+        else if (!val) v.sc->unsat = 1;
+        flags[k] = f; pos[k] = run; run += f;
+    }
+    *total = run;
+    if (!v.sc->unsat) {
+        for (uint32_t k = 0; k < n; ++k) if (flags[k]) {
+            const uint32_t lit = v.ubuf[k].lit;
+            v.trail[v.sc->n_trail + pos[k]] = lit; v.state[SG_ABS(lit)] = (uint8_t)SG_FROZEN_M; v.value[lit] = 1; v.value[SG_FLIP(lit)] = 0;
+        }
+        v.sc->n_trail += run; v.sc->max_frozen += run; v.sc->unassigned -= run; v.sc->units_forced += run;
+    }
+    for (uint32_t k = 0; k < n; ++k) first[v.ubuf[k].lit] = 0xFFFFFFFFu;
+}
 void be_pp_mark(void *, const SgView &v, const SgProp &pp)
 {
     g_launches++;
