@@ -2197,6 +2197,31 @@ SG_HDN inline void sg_ere_pair(const SgView &v, const SgLane &L, uint32_t x, uin
     }
 }
 
+/* would sg_ere_pair change anything for (iref, jref) in the current state?  Read-only, the same tests in the same order */
+SG_HDN inline bool sg_ere_pair_acts(const SgView &v, const SgLane &L, uint32_t x, uint32_t iref, uint32_t jref, uint32_t *merged)
+{
+    const sg_u4 hi = v.hdr[iref];
+    if (hi.z & SG_DELETED) return false;
+    const sg_u4 hj = v.hdr[jref];
+    if (hj.z & SG_DELETED) return false;
+    const bool ciorg = !(hi.z & SG_ST_MASK), cjorg = !(hj.z & SG_ST_MASK);
+    uint32_t sig, best;
+    const int len = sg_merge_ere(v, x, v.lits + hi.x, (int)hi.y, v.lits + hj.x, (int)hj.y, v.o.ere_clause_max, merged, &sig, &best);
+    if (len < 2) return false;
+    const int ereextend = v.o.ere_extend;
+    const int nm = (int)v.ot_len[best];
+    const uint32_t *ml = sg_list(v, best);
+    bool acts = false;
+    for (int m = (int)L.lane; m < nm && !acts; m += (int)L.width) {
+        const uint32_t c = ml[m];
+        if (c == iref || c == jref || !sg_ere_hits(v, merged, len, sig, c)) continue;
+        const sg_u4 hc = v.hdr[c];
+        const bool learnt = (hc.z & SG_LEARNT) != 0, equal = len == (int)hc.y;
+        acts = equal ? (learnt || (ciorg && cjorg)) : (ereextend && !(learnt && ereextend == 1));
+    }
+    return sg_ballot(acts) != 0;
+}
+
 /* ---- recorded pairs of the variables BEFORE the first dirty one: parallel rounds ------------------------------
  * Such a pair reads only its (untouched) parents and the clauses of its shortest list, and writes only clauses
  * its resolvent subsumes.  Per round every pending pair claims the clauses it could write (atomicMin of its
