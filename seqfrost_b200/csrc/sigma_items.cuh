@@ -1276,6 +1276,7 @@ SG_HDN inline void sg_sub_item(const SgView &v, uint32_t eidx)
 SG_HD int sg_merge_count(uint32_t pivot, const uint32_t *a, int na, const uint32_t *b, int nb)
 {   /* size of the resolvent on VARIABLE `pivot`, 0 for a tautology */
     int ia = 0, ib = 0, shared = 0;
+#pragma unroll 1
     while (ia < na && ib < nb) {
         const uint32_t ka = a[ia], kb = b[ib];
         const bool pa = (ka >> 1) == pivot, pb = (kb >> 1) == pivot;
@@ -1321,6 +1322,7 @@ SG_HD int sg_count_lits_before(const SgView &v, const SgLane &L, uint32_t lit)
     const int len = (int)v.ot_len[lit];
     const uint32_t *d = sg_list(v, lit);
     int n = 0;
+#pragma unroll 1
     for (int i = (int)L.lane; i < len; i += (int)L.width) if (sg_original(v, d[i])) n += SG_SIZE(v, d[i]);
     return sg_wsum(n);
 }
@@ -1382,6 +1384,7 @@ template <class P> SG_HD void sg_freeze_if(const SgView &v, const SgLane &L, uin
     const int n = (int)v.ot_len[lit];
     const uint32_t *d = sg_list(v, lit);
     sg_wsync();
+#pragma unroll 1
     for (int i = (int)L.lane; i < n; i += (int)L.width) {
         const sg_u4 h = v.hdr[d[i]];
         if ((h.z & SG_MOLTEN) && pred(h)) v.hdr[d[i]].z = h.z & ~SG_MOLTEN;
@@ -1588,15 +1591,20 @@ SG_HD void sg_freeze_arities(const SgView &v, const SgLane &L, uint32_t a, uint3
 /* An XOR over n variables is 2^(n-1) clauses: one base clause and every copy of it with an even number of literals
  * negated.  The even-weight masks in ascending order are e(t) = 2t | (popcount(t) & 1), t = 0 .. 2^(n-1)-1 - the order in
  * which the reference enumerates them (xor.hpp:26,72-78) - so partner t of a base clause is written down directly. */
+/* The loops over a clause's literals in these helpers stay rolled: the BVE decision kernel waits for instructions more than
+ * for data (ncu: 9.9 warps per issue slot stalled on "no instruction" at 15 280 instructions), the helpers are inlined into
+ * every XOR attempt, and unrolled four times each they were a sixth of the kernel. */
 SG_HD void sg_xor_partner(const uint32_t *base, int size, uint32_t t, uint32_t *out)
 {
     const uint32_t flips = (t << 1) | (uint32_t)(sg_popc(t) & 1);
+#pragma unroll 1
     for (int k = 0; k < size; ++k) out[k] = base[k] ^ ((flips >> k) & 1u);
 }
 /* the list a partner is searched in: the first of the shortest occurrence lists of its literals (xor.hpp:81-92) */
 SG_HD uint32_t sg_arity_best(const SgView &v, const uint32_t *literals, int size, uint32_t *sig_out)
 {
     uint32_t via = literals[0], sig = 0;
+#pragma unroll 1
     for (int k = 0; k < size; ++k) {
         sig |= SG_HASH(literals[k]);
         if (v.ot_len[literals[k]] < v.ot_len[via]) via = literals[k];
@@ -1612,6 +1620,7 @@ SG_HD bool sg_arity_match(const SgView &v, const sg_u4 &h, const uint32_t *liter
     /* a stored clause is in ascending literal order, and so is a partner pattern: negating literals of the (ascending) base
      * clause changes sign bits only, never the order of the variables - equal sets are equal sequences */
     const uint32_t *l = v.lits + h.x;
+#pragma unroll 1
     for (int a = 0; a < size; ++a) if (l[a] != literals[a]) return false;
     return true;
 }
@@ -1652,7 +1661,7 @@ SG_HDN inline bool sg_xor_complete(const SgView &v, uint32_t ci, int size)
 /* the same question answered by the whole warp, lanes over the partners: for wide XORs (2^(arity-1) - 1 partners, each a
  * search through a list of about 2^(arity-1) clauses) the first clause tried is nearly always the complete one, and testing
  * 32 clauses at once, one per lane, does 32 times the work the reference does */
-#define SG_XOR_COOP_MIN 6                 /* clause size from which the partners are spread over the lanes */
+#define SG_XOR_COOP_MIN 4                 /* clause size from which the partners are spread over the lanes */
 SG_HDN inline bool sg_xor_complete_warp(const SgView &v, const SgLane &L, uint32_t ci, int size)
 {
     uint32_t pattern[24];
@@ -1776,6 +1785,7 @@ SG_HD unsigned long long sg_fun_clause_word(const SgView &v, uint32_t c, uint32_
     const uint32_t *l = SG_LITS(v, c);
     const int size = SG_SIZE(v, c);
     unsigned long long f = 0;
+#pragma unroll 1
     for (int k = 0; k < size; ++k) {
         const uint32_t other = l[k];
         if (other == lit) continue;
@@ -1859,6 +1869,7 @@ SG_HD uint32_t sg_model_words(const SgView &v, const SgLane &L, uint32_t p, int 
     const int n = (int)v.ot_len[side];
     const uint32_t *d = sg_list(v, side);
     int words = 0;
+#pragma unroll 1
     for (int i = (int)L.lane; i < n; i += (int)L.width) if (sg_original(v, d[i])) words += SG_SIZE(v, d[i]) + 1;
     return (uint32_t)sg_wsum(words) + 2u;
 }
@@ -1868,6 +1879,7 @@ SG_HD int sg_count_orgs(const SgView &v, const SgLane &L, uint32_t lit)
     const int n = (int)v.ot_len[lit];
     const uint32_t *d = sg_list(v, lit);
     int c = 0;
+#pragma unroll 1
     for (int i = (int)L.lane; i < n; i += (int)L.width) if (sg_original(v, d[i])) c++;
     return sg_wsum(c);
 }
