@@ -1910,16 +1910,29 @@ SG_HDN inline void sg_ve_count_item(const SgView &v, uint32_t eidx)
         nAddedCls = 0, nAddedLits = 0;
         const int orgCls = pOrgs + nOrgs;
         uint32_t *gate_in = v.scratch + v.scr_off[eidx];
+        /* each finder is tried on (definition side, other side) and then the other way round unless the first attempt already
+         * counted resolvents; written as two-trip loops that stay rolled, so that the kernel holds one copy of each finder */
         if (orgCls > 2) {
-            if (sg_find_ao_gate(v, L, n, p, gate_in, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
-            else if (!nAddedCls && sg_find_ao_gate(v, L, p, n, gate_in, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+#pragma unroll 1
+            for (int side = 0; side < 2 && !type; ++side) {
+                if (side && nAddedCls) break;
+                if (sg_find_ao_gate(v, L, side ? p : n, side ? n : p, gate_in, orgCls, nAddedCls, nAddedLits)) type = SG_VE_SUBST;
+            }
             if (type) stat = &v.sc->andors;
         }
         if (!type && orgCls > 3) {
-            if (sg_find_ite_gate(v, L, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->ites; }
-            else if (!nAddedCls && sg_find_ite_gate(v, L, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->ites; }
-            else if (sg_find_xor_gate(v, L, p, n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->xors; }
-            else if (!nAddedCls && sg_find_xor_gate(v, L, n, p, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->xors; }
+#pragma unroll 1
+            for (int side = 0; side < 2 && !type; ++side) {
+                if (side && nAddedCls) break;
+                if (sg_find_ite_gate(v, L, side ? n : p, side ? p : n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->ites; }
+            }
+            if (!type) {
+#pragma unroll 1
+                for (int side = 0; side < 2 && !type; ++side) {
+                    if (side && nAddedCls) break;
+                    if (sg_find_xor_gate(v, L, side ? n : p, side ? p : n, orgCls, nAddedCls, nAddedLits)) { type = SG_VE_SUBST; stat = &v.sc->xors; }
+                }
+            }
         }
         if (!type && orgCls > 2 && sg_find_fun_gate(v, L, p, orgCls, nAddedCls, nAddedLits)) {
             if (sg_bcast(*(volatile uint32_t *)&v.sc->unsat)) { type = SG_VE_NONE; nAddedCls = 0; nAddedLits = 0; }
