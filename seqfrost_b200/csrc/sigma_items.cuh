@@ -1110,6 +1110,7 @@ SG_HD void sg_strengthen(const SgView &v, const SgLane &L, uint32_t c, uint32_t 
     sg_wsync();
 }
 
+#define SG_SUB_PRECHECK_MAX 96           /* pairs up to which the side-by-side test runs first (three steps of the warp) */
 SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x, uint32_t fx, uint32_t eidx, uint32_t &seq,
                                     uint32_t &n_str, uint32_t &n_sub)
 {   /* one loop of self_sub_x (subsume.hpp:186-199): clauses of `x` against the list of `fx` */
@@ -1128,6 +1129,47 @@ SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x
         const sg_u4 oh = lane < not_ ? v.hdr[oc] : make_uint4(0, 0, SG_DELETED, 0);
         const uint32_t mc = lane < nme ? me[lane] : 0u;
         sg_u4 mh = lane < nme ? v.hdr[mc] : make_uint4(0, 0, SG_DELETED, 0);
+        {
+            /* Would the loop below change anything?  It strengthens clause i when a clause of the other list hits it and deletes
+             * it when an earlier clause of its own list subsumes it; as long as neither happens the state stays what it was at
+             * the start, so "no pair hits in the initial state" means the loop does nothing.  The pairs are tested side by
+             * side, one per lane, read-only (the loop itself keeps 32 - |list| lanes idle in every step, and on gate circuits,
+             * with two to six clauses per list, hits are rare): the usual case ends here. */
+            const uint32_t big = __ballot_sync(0xffffffffu, lane < nme && (int)mh.y > maxsz);
+            const int ilim = big ? __ffs((int)big) - 1 : nme;                 /* the loop stops at the first clause above the size limit */
+            const int W2 = not_ + ilim, tot = ilim * W2;
+            bool any = tot > SG_SUB_PRECHECK_MAX;                             /* long lists (k-SAT with planted subsumption: hits are the rule) go straight to the loop */
+            for (int q0 = 0; q0 < tot && !any; q0 += 32) {
+                const int q = q0 + lane;
+                const bool valid = q < tot;
+                const int i = valid ? q / W2 : 0, r = valid ? q - i * W2 : 0;
+                const bool cross = r < not_;                                  /* (clause i, clause r of the other list) or (clause i, earlier clause of its list) */
+                const int src = cross ? r : r - not_;
+                sg_u4 ch, so, sm;
+                ch.x = __shfl_sync(0xffffffffu, mh.x, i); ch.y = __shfl_sync(0xffffffffu, mh.y, i);
+                ch.z = __shfl_sync(0xffffffffu, mh.z, i); ch.w = __shfl_sync(0xffffffffu, mh.w, i);
+                so.x = __shfl_sync(0xffffffffu, oh.x, src); so.y = __shfl_sync(0xffffffffu, oh.y, src);
+                so.z = __shfl_sync(0xffffffffu, oh.z, src); so.w = __shfl_sync(0xffffffffu, oh.w, src);
+                sm.x = __shfl_sync(0xffffffffu, mh.x, src); sm.y = __shfl_sync(0xffffffffu, mh.y, src);
+                sm.z = __shfl_sync(0xffffffffu, mh.z, src); sm.w = __shfl_sync(0xffffffffu, mh.w, src);
+                bool hit = false;
+                if (valid && !(ch.z & SG_DELETED)) {
+                    const int candsz = (int)ch.y;
+                    const uint32_t *cl = v.lits + ch.x;
+                    if (cross) {
+                        const int subsize = (int)so.y;
+                        hit = !(so.z & SG_DELETED) && subsize <= candsz && subsize > 1 && sg_sig_selfsub(so.w, ch.w) &&
+                              sg_selfsub_lits(x, fx, v.lits + so.x, subsize, cl, candsz);
+                    } else if (src < i) {
+                        const int ssz = (int)sm.y;
+                        hit = !(sm.z & SG_DELETED) && !((ch.z & SG_MOLTEN) && ssz > candsz) && ssz > 1 && sg_sig_sub(sm.w, ch.w) &&
+                              sg_sub_lits(v.lits + sm.x, ssz, cl, candsz);
+                    }
+                }
+                any = __ballot_sync(0xffffffffu, hit) != 0;
+            }
+            if (!any) goto update_ol;
+        }
         for (int i = 0; i < nme; ++i) {
             const uint32_t c = __shfl_sync(0xffffffffu, mc, i);
             sg_u4 ch;
