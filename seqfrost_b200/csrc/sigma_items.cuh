@@ -1139,10 +1139,11 @@ SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x
             const int ilim = big ? __ffs((int)big) - 1 : nme;                 /* the loop stops at the first clause above the size limit */
             const int W2 = not_ + ilim, tot = ilim * W2;
             bool any = tot > SG_SUB_PRECHECK_MAX;                             /* long lists (k-SAT with planted subsumption: hits are the rule) go straight to the loop */
+            const float rcp = 1.0f / (float)(W2 > 0 ? W2 : 1);               /* q / W2 for q < 128, W2 <= 64: (q + 0.5) / W2 is at least 1/128 away from an integer */
             for (int q0 = 0; q0 < tot && !any; q0 += 32) {
                 const int q = q0 + lane;
                 const bool valid = q < tot;
-                const int i = valid ? q / W2 : 0, r = valid ? q - i * W2 : 0;
+                const int i = valid ? (int)(((float)q + 0.5f) * rcp) : 0, r = valid ? q - i * W2 : 0;
                 const bool cross = r < not_;                                  /* (clause i, clause r of the other list) or (clause i, earlier clause of its list) */
                 const int src = cross ? r : r - not_;
                 sg_u4 ch, so, sm;
@@ -1283,11 +1284,12 @@ update_ol:
         }
         const uint32_t m = sg_ballot(keep);
         sg_wsync();
-        if (keep) me[j + sg_popc(m & ((1u << L.lane) - 1u))] = c;
+        const int dst = j + sg_popc(m & ((1u << L.lane) - 1u));
+        if (keep && dst != idx) me[dst] = c;                   /* nothing dropped so far: the entry is where it belongs */
         j += sg_popc(m);
         sg_wsync();
     }
-    if (L.lane == 0) v.ot_len[x] = (uint32_t)j;
+    if (L.lane == 0 && j != nme) v.ot_len[x] = (uint32_t)j;
     sg_wsync();
 }
 
