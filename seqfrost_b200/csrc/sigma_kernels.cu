@@ -1301,7 +1301,7 @@ __global__ void k_acting_scatter(SgView v, const uint32_t *__restrict__ fa, cons
  * of a few spilled registers; sortOT and the election lose) */
 constexpr int items_min_blocks(int kind)
 {
-    return kind == SGK_VE_COUNT ? 6 : kind == SGK_SUB ? 8 : kind == SGK_ERE_PROPOSE ? 5 : 1;
+    return kind == SGK_VE_COUNT ? 8 : kind == SGK_SUB ? 8 : kind == SGK_ERE_PROPOSE ? 5 : 1;
 }
 template <int KIND> __global__ void __launch_bounds__(TPB, items_min_blocks(KIND)) k_items(SgView v, uint32_t n)
 {
