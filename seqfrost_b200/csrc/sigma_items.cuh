@@ -1110,7 +1110,7 @@ SG_HD void sg_strengthen(const SgView &v, const SgLane &L, uint32_t c, uint32_t 
     sg_wsync();
 }
 
-#define SG_SUB_PRECHECK_MAX 96           /* pairs up to which the side-by-side test runs first (three steps of the warp) */
+#define SG_SUB_PRECHECK_MAX 192          /* pairs up to which the side-by-side test runs first (six steps of the warp; measured: 96 / 192 / all) */
 SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x, uint32_t fx, uint32_t eidx, uint32_t &seq,
                                     uint32_t &n_str, uint32_t &n_sub)
 {   /* one loop of self_sub_x (subsume.hpp:186-199): clauses of `x` against the list of `fx` */
@@ -1139,7 +1139,7 @@ SG_HDN inline void sg_self_sub_half(const SgView &v, const SgLane &L, uint32_t x
             const int ilim = big ? __ffs((int)big) - 1 : nme;                 /* the loop stops at the first clause above the size limit */
             const int W2 = not_ + ilim, tot = ilim * W2;
             bool any = tot > SG_SUB_PRECHECK_MAX;                             /* long lists (k-SAT with planted subsumption: hits are the rule) go straight to the loop */
-            const float rcp = 1.0f / (float)(W2 > 0 ? W2 : 1);               /* q / W2 for q < 128, W2 <= 64: (q + 0.5) / W2 is at least 1/128 away from an integer */
+            const float rcp = 1.0f / (float)(W2 > 0 ? W2 : 1);               /* q / W2 for q < 256, W2 <= 64: (q + 0.5) / W2 is at least 1/128 away from an integer */
             for (int q0 = 0; q0 < tot && !any; q0 += 32) {
                 const int q = q0 + lane;
                 const bool valid = q < tot;
