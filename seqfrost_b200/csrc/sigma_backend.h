@@ -90,6 +90,7 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
                  int lbd_tier1, uint32_t *cm, uint64_t *orgs, uint64_t *learnts, unsigned long long *counts, uint8_t *subsume, const uint32_t *vmap /* device, may be NULL: variable mapping (map.hpp:52-76) */);
 /* ERE proposal pass: filt[2c] = size of clause c (0 when deleted), filt[2c+1] = its signature */
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt, uint8_t *size8);   /* size8[c] = min(size, 255), 0 when deleted */
+void be_ere_maxsz(void *s, const SgView &v, const uint8_t *size8, uint8_t *maxsz);   /* maxsz[lit] = largest size8 in the list of lit */
 /* createOT: every list of the freshly built (packed) table into ascending clause id order (simplify.cpp:50-58) */
 void be_ot_order(void *s, const SgView &v);
 /* `count` (<= 4) independent exclusive prefix sums of the same length with the launches of one; tmp: count x be_scan_tmp_words(n) */

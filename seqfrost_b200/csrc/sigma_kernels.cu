@@ -172,6 +172,18 @@ __global__ void k_ere_filt(SgView v, uint2 *__restrict__ filt, uint8_t *__restri
     size8[c] = (uint8_t)(size < 255u ? size : 255u);
 }
 
+/* largest clause (as in size8) in every occurrence list: a resolvent longer than that subsumes nothing in the list */
+__global__ void k_ere_maxsz(SgView v, const uint8_t *__restrict__ size8, uint8_t *__restrict__ maxsz)
+{
+    const uint32_t lit = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lit >= v.nlit) return;
+    const uint32_t n = v.ot_len[lit];
+    const uint32_t *d = v.ot_data + v.ot_off[lit];
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n; ++i) { const uint32_t s8 = size8[d[i]]; m = s8 > m ? s8 : m; }
+    maxsz[lit] = (uint8_t)m;
+}
+
 /* a ref or size word that points outside the uploaded arena raises *bad (the driver returns SIGMA_E_ARG) instead of
  * being followed */
 __global__ void k_ingest_sizes(const uint32_t *__restrict__ arena, const uint64_t *__restrict__ refs, uint32_t n,
@@ -2553,6 +2565,7 @@ void be_cm_write(void *s, const uint32_t *arena, const uint64_t *refs, uint32_t 
     if (n) LAUNCH(k_cm_write, blocks_for(n), TPB, s, arena, (const unsigned long long *)refs, n, learnt_before, lbd_tier1, cm,
                   (unsigned long long *)orgs, (unsigned long long *)learnts, counts, subsume, (unsigned long long)(n_buckets + n), vmap);
 }
+void be_ere_maxsz(void *s, const SgView &v, const uint8_t *size8, uint8_t *maxsz) { if (v.nlit) LAUNCH(k_ere_maxsz, blocks_for(v.nlit), TPB, s, v, size8, maxsz); }
 void be_ere_filt(void *s, const SgView &v, uint32_t *filt, uint8_t *size8)
 {
     if (v.n_cls) LAUNCH(k_ere_filt, blocks_for(v.n_cls), TPB, s, v, (uint2 *)filt, size8);

@@ -68,7 +68,7 @@ struct sigma_ctx {
     DBuf<uint32_t> ve_type, ve_ncls, ve_nlits, ve_nmodel, ve_aux, ve_cls_off, ve_lit_off, ve_mod_off, scr_len, scr_off, scratch;
     DBuf<SgUnit> ubuf;
     DBuf<uint8_t> ere_touched, ere_flags;
-    DBuf<uint32_t> ere_filt, ere_claims; DBuf<uint8_t> ere_size8;
+    DBuf<uint32_t> ere_filt, ere_claims; DBuf<uint8_t> ere_size8, ere_maxsz;
     DBuf<uint32_t> ot_off2, ot_len2, ot_data2, otutmp, ot_add, otbits, otb_tmp;
     uint64_t phase_add_lits = 0;     /* literals of the resolvents the latest VE stage added */
     uint32_t last_elected = 0;       /* size of `elected` after the latest election (hsc.n_elected does not survive a pull) */
@@ -865,9 +865,14 @@ int stage_ere(sigma_ctx *c)
             NOMEM(c->ere_filt.ensure(2 * (size_t)c->n_cls + 16)); NOMEM(c->ere_size8.ensure((size_t)c->n_cls + 16));
             be_ere_filt(c->stream, v, c->ere_filt.p, c->ere_size8.p);
             v.ere_filt = c->ere_filt.p; v.ere_size8 = c->ere_size8.p;
+            if (use_filt != 2) {                           /* SIGMA_ERE_FILT=2 (tests): without the per-list bound */
+                NOMEM(c->ere_maxsz.ensure((size_t)c->nlit + 16));
+                be_ere_maxsz(c->stream, v, c->ere_size8.p, c->ere_maxsz.p);
+                v.ere_maxsz = c->ere_maxsz.p;
+            }
         }
         be_items(c->stream, SGK_ERE_PROPOSE, v, n_items);
-        v.ere_filt = nullptr; v.ere_size8 = nullptr;
+        v.ere_filt = nullptr; v.ere_size8 = nullptr; v.ere_maxsz = nullptr;
     }
     CK(pull_scalars(c));
     const uint32_t n = c->hsc.n_units;
@@ -1087,7 +1092,7 @@ void sigma_destroy(sigma_ctx *c)
         c->sorttmp.release(); c->scantmp.release(); c->wl0.release(); c->wl1.release(); c->flags.release(); c->pos.release();
         c->acting.release(); c->elected.release(); c->ve_type.release(); c->ve_ncls.release(); c->ve_nlits.release();
         c->ve_nmodel.release(); c->ve_aux.release(); c->ve_cls_off.release(); c->ve_lit_off.release(); c->ve_mod_off.release();
-        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release(); c->ere_filt.release(); c->ere_size8.release();
+        c->scr_len.release(); c->scr_off.release(); c->scratch.release(); c->ubuf.release(); c->ere_touched.release(); c->ere_flags.release(); c->ere_filt.release(); c->ere_size8.release(); c->ere_maxsz.release();
         c->ot_off2.release(); c->ot_len2.release(); c->ot_data2.release(); c->otutmp.release(); c->ot_add.release(); c->otbits.release(); c->otb_tmp.release(); c->totals.release(); c->sc.release();
         c->pp_fpos.release(); c->pp_lists.release(); c->pp_cnt.release(); c->pp_claim.release(); c->pp_ctl.release(); c->pp_tmp.release(); c->pp_disc.release();
         c->c_flags.release(); c->c_sizes.release(); c->c_newid.release(); c->c_newoff.release();

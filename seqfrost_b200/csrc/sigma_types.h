@@ -129,6 +129,7 @@ typedef struct SgView {
     uint32_t *ere_done;      /* per recorded pair: 0 pending, 2 apply this round, 1 applied; NULL = no parallel rounds */
     const uint32_t *ere_filt; /* proposal pass only: {size (0 = deleted), sig} per clause, 8 bytes, a snapshot small enough for L2 */
     const uint8_t  *ere_size8; /* proposal pass only: min(size, 255) per clause, 0 = deleted: the first screen, one byte per clause */
+    const uint8_t  *ere_maxsz; /* proposal pass only: largest ere_size8 in the occurrence list of each literal; NULL = not built */
     SgScalars *sc;
     uint32_t nvars, nlit;    /* nlit = 2*nvars + 2 */
     uint32_t n_cls;          /* clause ids in use */

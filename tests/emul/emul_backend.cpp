@@ -100,6 +100,15 @@ void be_cm_write(void *, const uint32_t *arena, const uint64_t *refs, uint32_t n
             for (uint32_t k = 0; k < src[2]; ++k) subsume[SG_ABS(src[3 + k])] = 1;
     }
 }
+void be_ere_maxsz(void *, const SgView &v, const uint8_t *size8, uint8_t *maxsz)
+{
+    g_launches++;
+    for (uint32_t lit = 0; lit < v.nlit; ++lit) {
+        uint8_t m = 0;
+        for (uint32_t i = 0; i < v.ot_len[lit]; ++i) { const uint8_t s8 = size8[v.ot_data[v.ot_off[lit] + i]]; if (s8 > m) m = s8; }
+        maxsz[lit] = m;
+    }
+}
 void be_ere_filt(void *, const SgView &v, uint32_t *filt, uint8_t *size8)
 {
     g_launches++;
