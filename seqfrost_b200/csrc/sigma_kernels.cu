@@ -1182,6 +1182,9 @@ __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_persistent(
 #ifndef SG_ELECT_GW
 #define SG_ELECT_GW 8          /* lanes per candidate in k_elect_async: 32 / SG_ELECT_GW candidates are looked at side by side */
 #endif
+#ifndef SG_ELECT_SMALL
+#define SG_ELECT_SMALL (2u * SG_ELECT_GW)   /* list entries (both lists) up to which a candidate is looked at by a lane group (4x: C4 election 6.2 -> 7.6 ms) */
+#endif
 __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_async(SgView v)
 {
     constexpr int NG = 32 / SG_ELECT_GW;       /* lane groups per warp */
@@ -1253,7 +1256,7 @@ __global__ void __launch_bounds__(SG_ELECT_TPB, SG_LB_ELECT) k_elect_async(SgVie
                     const uint32_t np = v.ot_len[2 * f_var], nn = v.ot_len[2 * f_var + 1];
                     if (np) asm volatile("prefetch.global.L2 [%0];" :: "l"(dp));
                     if (nn) asm volatile("prefetch.global.L2 [%0];" :: "l"(dn + nn - 1));
-                    f_small = np + nn <= 2u * SG_ELECT_GW;
+                    f_small = np + nn <= SG_ELECT_SMALL;
                 }
                 f_base += 32ull * nwarps;
                 more = f_base < V && f_base <= brk;
